@@ -1,0 +1,209 @@
+/* b200force.h -- C-ABI of the B200-native TreePM + SPH force engine.
+ *
+ * Drop-in boundary for the MP-Gadget force step.  The
+ * reference has no FFI layer: its modules call each other through C headers in
+ * libgadget.a, so the replacement is link-time: a maintainer swaps
+ * gravpm.o / gravshort-tree.o / forcetree.o for thin shims with the reference
+ * signatures (mp-gadget_b200/host/libgadget_shims.c) that call
+ * the entry points below.  Each entry point cites the reference interface it
+ * replaces (paths relative to the MP-Gadget tree).
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a HOST pointer unless the function
+ *    name ends in _dev (then it is a device pointer on the context's GPU);
+ *  - every function returns 0 on success, non-zero on failure; the message is
+ *    available from b200_last_error().  The reference's convention is
+ *    endrun()/MPI_Abort (libgadget/utils/endrun.c:138-153); the shims map a
+ *    non-zero status to endrun(1, "%s", b200_last_error(ctx));
+ *  - particle arrays are indexed by the caller's particle index (the index into
+ *    the reference's global P[] array, libgadget/partmanager.h:73-85);
+ *  - there is NO CPU fallback: without a CUDA device b200_ctx_create fails.
+ */
+#ifndef B200FORCE_H
+#define B200FORCE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+typedef struct b200_ctx b200_ctx;
+
+/* Byte layout of the caller's array-of-structs particle record.  Defaults
+ * (b200_default_particle_layout) are the offsets of `struct particle_data`
+ * (libgadget/partmanager.h:9-71, 160 bytes, no -DDEBUG). */
+typedef struct b200_particle_layout {
+    int64_t stride;          /* sizeof(struct particle_data) = 160 */
+    int32_t off_pos;         /* double Pos[3]                    0 */
+    int32_t off_mass;        /* float  Mass                     28 */
+    int32_t off_flags;       /* bitfield byte (IsGarbage bit0, Swallowed bit1) 36 */
+    int32_t off_type;        /* unsigned char Type              39 */
+    int32_t off_vel;         /* double Vel[3]                   40 */
+    int32_t off_fulltreeacc; /* double FullTreeGravAccel[3]     64 */
+    int32_t off_gravpm;      /* double GravPM[3]                88 */
+    int32_t off_hsml;        /* double Hsml                    120 */
+    int32_t off_potential;   /* double Potential               152 */
+    int32_t off_pi;          /* int PI (slot index)             32 */
+    int32_t off_timebin_hydro;   /* unsigned char TimeBinHydro   37 */
+    int32_t off_timebin_gravity; /* unsigned char TimeBinGravity 38 */
+} b200_particle_layout;
+
+void b200_default_particle_layout(b200_particle_layout *layout);
+
+/* ---- context ------------------------------------------------------------ */
+
+/* Create an engine bound to CUDA device `device`.  Fails (non-zero, *out=NULL)
+ * when no CUDA device is present. */
+int b200_ctx_create(b200_ctx **out, int device);
+void b200_ctx_destroy(b200_ctx *ctx);
+const char *b200_last_error(const b200_ctx *ctx);
+int b200_abi_version(void);
+/* Number of kernel launches issued by this context since creation. */
+int64_t b200_kernel_launches(const b200_ctx *ctx);
+
+/* ---- particle ingest ------------------------------------------------------
+ * Replaces the reference's direct reads of the global P[] array
+ * (PartManager->Base, libgadget/partmanager.h:73-85).  The engine keeps a
+ * struct-of-arrays copy in HBM until the next call. */
+
+/* From the caller's AoS records (host memory). */
+int b200_set_particles_aos(b200_ctx *ctx, const void *P, int64_t n,
+                           const b200_particle_layout *layout);
+/* From separate arrays (host memory): pos[n][3] f64, mass[n] f32,
+ * type[n] u8 (NULL = all type 1), oldacc[n][3] f64 = FullTreeGravAccel+GravPM
+ * of the previous step (NULL = zeros). */
+int b200_set_particles_soa(b200_ctx *ctx, const double *pos, const float *mass,
+                           const uint8_t *type, const double *oldacc, int64_t n);
+/* Same, device-resident inputs (no host traffic). */
+int b200_set_particles_soa_dev(b200_ctx *ctx, const double *pos, const float *mass,
+                               const uint8_t *type, const double *oldacc, int64_t n);
+/* Set |FullTreeGravAccel + GravPM| inputs of the relative opening criterion
+ * from the accelerations the engine itself computed in the last
+ * b200_pm_force + b200_grav_short_tree pair (grav_get_abs_accel,
+ * libgadget/gravshort.h:69-86) -- keeps the step device-resident. */
+int b200_oldacc_from_last_step(b200_ctx *ctx);
+
+/* ---- PM long-range force ---------------------------------------------------
+ * b200_pm_init  replaces gravpm_init_periodic (libgadget/gravity.h:40,
+ *               gravpm.c:51-54) = petapm_init (petapm.c:104-223).
+ * b200_pm_force replaces gravpm_force (gravity.h:55, gravpm.c:60-119) =
+ *               petapm_force (petapm.h:133, petapm.c:364-379) with gravpm's
+ *               callback set {Potential, ForceX, ForceY, ForceZ}
+ *               (gravpm.c:32-39): CIC deposit, forward FFT, potential_transfer
+ *               (gravpm.c:383-454), gradient (gravpm.c:458-489), readout
+ *               (gravpm.c:499-510). */
+int b200_pm_init(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G);
+/* gravpm_out[n][3] (P[i].GravPM) and potential_out[n] (the PM contribution
+ * added to P[i].Potential) for every particle; either may be NULL. */
+int b200_pm_force(b200_ctx *ctx, double *gravpm_out, double *potential_out);
+int b200_pm_force_dev(b200_ctx *ctx, double *gravpm_out, double *potential_out);
+/* Parity hooks: integer CIC cell of every particle (iCell of pm_iterate_one,
+ * petapm.c:976-980) icell_out[n][3]; and a copy of the real-space mesh
+ * (density after deposit if which==0, potential after the inverse FFT if
+ * which==1), mesh_out[Nmesh^3], x slowest. */
+int b200_pm_cell_index(b200_ctx *ctx, int32_t *icell_out);
+int b200_pm_copy_mesh(b200_ctx *ctx, int which, double *mesh_out);
+
+/* ---- octree ------------------------------------------------------------------
+ * Replaces force_tree_full / force_tree_active_moments /
+ * force_tree_rebuild_mask / force_tree_calc_moments / force_tree_free
+ * (libgadget/forcetree.h:117-148, forcetree.c:110-183,196-270). */
+typedef struct b200_tree_info {
+    int64_t numnodes;      /* ForceTree.numnodes */
+    int64_t numparticles;  /* ForceTree.NumParticles */
+    int32_t maxdepth;      /* deepest level (root = 0) */
+    int32_t overfull_leaves; /* leaves at the key-depth limit holding > 8 particles */
+    double  root_mass;
+} b200_tree_info;
+
+/* mask: bit t set = include particle type t (ALLMASK = 63, forcetree.h:22-27).
+ * active: particle indices to insert (NULL = all n particles), as
+ *         ActiveParticles.ActiveParticle (libgadget/timestep.h:29-38).
+ * toplevel_depth: all nodes down to this level are forced to exist and are
+ *         never pruned (the replicated domain top-tree,
+ *         forcetree.c:654-687,869-934); 0 = the one-leaf domain. */
+int b200_tree_build(b200_ctx *ctx, double BoxSize, int mask, const int32_t *active,
+                    int64_t nactive, int toplevel_depth, b200_tree_info *info);
+void b200_tree_free(b200_ctx *ctx);
+
+/* Parity hook: export the tree in depth-first order (the order of the
+ * reference's sibling/first-child walk).  Arrays have info.numnodes entries;
+ * any may be NULL.  sibling/firstchild are DFS positions (-1 = none);
+ * nocc = particle count of a particle leaf, -1 for an internal node;
+ * leafpart[numnodes][8] original particle indices (unused = -1). */
+int b200_tree_export(b200_ctx *ctx, double *center /*[.][3]*/, double *len,
+                     double *cofm /*[.][3]*/, double *mass, double *hmax,
+                     int32_t *sibling, int32_t *firstchild, int32_t *nocc,
+                     int32_t *leafpart);
+
+/* ---- short-range tree gravity ----------------------------------------------
+ * Replaces grav_short_tree (libgadget/gravity.h:58, gravshort-tree.c:96-154)
+ * = treewalk_run (treewalk.c:801-902) with visit force_treeev_shortrange
+ * (gravshort-tree.c:253-379), fill grav_short_copy, postprocess
+ * grav_short_postprocess (gravshort.h:47-96).  Parameters mirror
+ * struct gravshort_tree_params (gravity.h:9-22) + GravShortPriv
+ * (gravshort.h:25-43). */
+typedef struct b200_gravshort_params {
+    double ErrTolForceAcc;
+    double BHOpeningAngle;
+    double MaxBHOpeningAngle;
+    int32_t TreeUseBH;      /* !=0: Barnes-Hut angle only; 0: relative criterion */
+    int32_t pad_;
+    double Rcut;            /* TreeRcut, in units of Asmth*cellsize */
+    double GravitySoftening;/* absolute Plummer-equivalent length (gravshort_set_softenings) */
+    double rho0;            /* mean matter density, for the potential self-term */
+} b200_gravshort_params;
+
+/* Per-particle walk counters (parity on tree opening). */
+typedef struct b200_walk_counts {
+    int32_t nodes_accepted;   /* monopoles applied           (gravshort-tree.c:314-323) */
+    int32_t nodes_opened;     /* internal nodes opened       (gravshort-tree.c:358-360) */
+    int32_t nodes_discarded;  /* nodes discarded beyond Rcut (gravshort-tree.c:304-309) */
+    int32_t particles;        /* particles of opened leaves = the reference's ninteractions (gravshort-tree.c:344-352,375) */
+} b200_walk_counts;
+
+/* active/nactive as above (NULL = all particles).  accel_out[n][3]: entry i is
+ * written for every active particle i (G applied), untouched otherwise --
+ * GravShortPriv.Accel (gravshort.h:41).  potential_out[n]: short-range
+ * potential after grav_short_postprocess (gravshort.h:59-64), only meaningful
+ * for full-particle trees; counts_out[n] optional. */
+int b200_grav_short_tree(b200_ctx *ctx, const b200_gravshort_params *par,
+                         const int32_t *active, int64_t nactive,
+                         double *accel_out, double *potential_out,
+                         b200_walk_counts *counts_out);
+int b200_grav_short_tree_dev(b200_ctx *ctx, const b200_gravshort_params *par,
+                             const int32_t *active, int64_t nactive,
+                             double *accel_out, double *potential_out,
+                             b200_walk_counts *counts_out);
+
+/* ---- whole DM force step on the caller's AoS (the e2e path) ----------------
+ * = gravpm_force + force_tree_full + grav_short_tree as run.c:519-548 does on a
+ * PM step with SplitGravityTimestepsOn=0: reads P[], writes P[i].GravPM,
+ * P[i].FullTreeGravAccel and P[i].Potential in place. */
+int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n,
+                        const b200_particle_layout *layout,
+                        const b200_gravshort_params *par);
+
+/* Device-side timing of the phases of the last call, milliseconds (CUDA
+ * events on the engine's stream).  Names follow the reference's walltime
+ * categories (libgadget/walltime.c, gravshort-tree.c:134-144, petapm.c:280-355). */
+typedef struct b200_timings {
+    double pm_deposit, pm_fft_forward, pm_transfer, pm_fft_inverse, pm_gradient, pm_readout, pm_total;
+    double tree_keys, tree_sort, tree_nodes, tree_moments, tree_total;
+    double walk, walk_post;
+    double h2d, d2h;
+} b200_timings;
+int b200_get_timings(const b200_ctx *ctx, b200_timings *t);
+
+/* Stream the engine launches on (cudaStream_t as void*), so harness code can
+ * record events on it. */
+void *b200_stream(const b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FORCE_H */

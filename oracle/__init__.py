@@ -1,0 +1,158 @@
+"""ctypes front-end of the CPU oracle (oracle/*.c) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.  See oracle/oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class Node(C.Structure):
+    _fields_ = [("sibling", C.c_int32), ("father", C.c_int32), ("firstchild", C.c_int32),
+                ("nocc", C.c_int32), ("part", C.c_int32 * 8), ("toplevel", C.c_int32),
+                ("level", C.c_int32), ("len", C.c_double), ("center", C.c_double * 3),
+                ("cofm", C.c_double * 3), ("mass", C.c_double), ("hmax", C.c_double)]
+
+
+NODE_DTYPE = np.dtype([("sibling", "i4"), ("father", "i4"), ("firstchild", "i4"), ("nocc", "i4"),
+                       ("part", "i4", (8,)), ("toplevel", "i4"), ("level", "i4"), ("len", "f8"),
+                       ("center", "f8", (3,)), ("cofm", "f8", (3,)), ("mass", "f8"), ("hmax", "f8")],
+                      align=True)
+assert NODE_DTYPE.itemsize == C.sizeof(Node)
+
+
+class Tree(C.Structure):
+    _fields_ = [("nodes", C.POINTER(Node)), ("numnodes", C.c_int64),
+                ("numparticles", C.c_int64), ("BoxSize", C.c_double)]
+
+
+class GravShortParams(C.Structure):
+    _fields_ = [("ErrTolForceAcc", C.c_double), ("BHOpeningAngle", C.c_double),
+                ("MaxBHOpeningAngle", C.c_double), ("TreeUseBH", C.c_int32), ("pad_", C.c_int32),
+                ("Rcut", C.c_double), ("GravitySoftening", C.c_double), ("rho0", C.c_double)]
+
+
+COUNTS_DTYPE = np.dtype([("nodes_accepted", "i4"), ("nodes_opened", "i4"),
+                         ("nodes_discarded", "i4"), ("particles", "i4")])
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_tree.c", "oracle_pm.c", "oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.oracle_tree_build.restype = C.c_int
+        _LIB.oracle_grav_short_tree.restype = C.c_int
+    return _LIB
+
+
+def _p(a, ty=C.c_void_p):
+    return None if a is None else a.ctypes.data_as(ty)
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+class OracleTree:
+    """oracle_tree_build wrapper; .nodes is a structured numpy view in DFS order."""
+
+    def __init__(self, pos, mass, box, type=None, hsml=None, mask=63, active=None, toplevel_depth=0):
+        self.pos = _c(pos, np.float64)
+        self.mass = _c(mass, np.float32)
+        self.type = _c(type, np.uint8)
+        self.hsml = _c(hsml, np.float64)
+        self.active = _c(active, np.int32)
+        self.n = len(self.mass)
+        self.t = Tree()
+        na = 0 if self.active is None else len(self.active)
+        rc = lib().oracle_tree_build(C.byref(self.t), _p(self.pos), _p(self.mass), _p(self.type),
+                                     _p(self.hsml), C.c_int64(self.n), C.c_double(box), C.c_int(mask),
+                                     _p(self.active), C.c_int64(na), C.c_int(toplevel_depth))
+        if rc:
+            raise RuntimeError("oracle_tree_build failed (coincident particles?)")
+        buf = (Node * self.t.numnodes).from_address(C.addressof(self.t.nodes.contents))
+        self.nodes = np.frombuffer(buf, dtype=NODE_DTYPE)
+
+    def __del__(self):
+        try:
+            self.nodes = None
+            lib().oracle_tree_free(C.byref(self.t))
+        except Exception:
+            pass
+
+    def grav_short_tree(self, par, G, Nmesh, Asmth, oldacc=None, active=None, full=True):
+        n = self.n
+        p = GravShortParams(**par) if isinstance(par, dict) else par
+        acc = np.zeros((n, 3))
+        pot = np.zeros(n)
+        cnt = np.zeros(n, dtype=COUNTS_DTYPE)
+        oldacc = _c(oldacc, np.float64)
+        active = _c(active, np.int32)
+        na = 0 if active is None else len(active)
+        rc = lib().oracle_grav_short_tree(C.byref(self.t), _p(self.pos), _p(self.mass), C.c_int64(n),
+                                          C.byref(p), C.c_double(G), C.c_int(Nmesh), C.c_double(Asmth),
+                                          _p(oldacc), _p(active), C.c_int64(na), C.c_int(1 if full else 0),
+                                          _p(acc), _p(pot), _p(cnt))
+        if rc:
+            raise MemoryError
+        return acc, pot, cnt
+
+
+def pm_force(pos, mass, box, nmesh, asmth, G, workers=-1, return_mesh=False):
+    """gravpm_force restated: deposit -> rfftn -> potential_transfer ->
+    {copy, force_transfer_d} -> irfftn (unnormalised) -> readout.
+    Returns (gravpm[n,3], potential[n], icell[n,3])."""
+    import scipy.fft as sfft
+    pos = _c(pos, np.float64)
+    mass = _c(mass, np.float32)
+    n = len(mass)
+    L = lib()
+    mesh = np.zeros((nmesh, nmesh, nmesh))
+    icell = np.zeros((n, 3), dtype=np.int32)
+    L.oracle_pm_deposit(_p(pos), _p(mass), C.c_int64(n), C.c_double(box), C.c_int(nmesh), _p(mesh), _p(icell))
+    dens = mesh.copy() if return_mesh else None
+    rhok = sfft.rfftn(mesh, workers=workers)                      # unnormalised forward
+    rhok = np.ascontiguousarray(rhok)
+    L.oracle_pm_potential_transfer(_p(rhok), C.c_int(nmesh), C.c_double(box), C.c_double(asmth), C.c_double(G))
+    ntot = float(nmesh) ** 3
+    out = np.zeros((n, 4))
+    potmesh = None
+    for f in range(4):
+        if f == 0:
+            fk = rhok
+        else:
+            fk = np.empty_like(rhok)
+            L.oracle_pm_force_transfer(_p(rhok), _p(fk), C.c_int(nmesh), C.c_double(box), C.c_int(f - 1))
+        real = sfft.irfftn(fk, s=(nmesh,) * 3, workers=workers, norm="forward")  # unnormalised inverse
+        real = np.ascontiguousarray(real)
+        if f == 0 and return_mesh:
+            potmesh = real.copy()
+        L.oracle_pm_readout(_p(real), _p(pos), C.c_int64(n), C.c_double(box), C.c_int(nmesh),
+                            out[:, f].ctypes.data_as(C.c_void_p), C.c_int64(4))
+    del ntot
+    res = (np.ascontiguousarray(out[:, 1:4]), np.ascontiguousarray(out[:, 0]), icell)
+    if return_mesh:
+        return res + (dens, potmesh)
+    return res
+
+
+def direct_sum(pos, mass, box, G, softening_h, repeat=1):
+    pos = _c(pos, np.float64)
+    mass = _c(mass, np.float32)
+    acc = np.zeros((len(mass), 3))
+    lib().oracle_direct_sum(_p(pos), _p(mass), C.c_int64(len(mass)), C.c_double(box), C.c_double(G),
+                            C.c_double(softening_h), C.c_int(repeat), _p(acc))
+    return acc
