@@ -1,0 +1,244 @@
+"""ctypes harness over libb200force.so (include/b200force.h).
+
+This is the Python-side test/bench harness of the B200 force engine.  The
+product is the C-ABI shared library built from csrc/ (see DESIGN.md); the
+reference's host code is C, and the reference-signature shims live in
+host/libgadget_shims.c.  Function names here follow the reference entry points
+they drive (gravpm_init_periodic, gravpm_force, force_tree_full,
+grav_short_tree: libgadget/gravity.h:40-58, forcetree.h:127).
+
+There is NO CPU fallback: loading fails loudly if the library is missing and
+Engine() fails if no CUDA device is present.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200force.so")
+_lib = None
+
+ALLMASK = 63   # libgadget/forcetree.h:22
+
+
+class ParticleLayout(C.Structure):
+    _fields_ = [("stride", C.c_int64), ("off_pos", C.c_int32), ("off_mass", C.c_int32),
+                ("off_flags", C.c_int32), ("off_type", C.c_int32), ("off_vel", C.c_int32),
+                ("off_fulltreeacc", C.c_int32), ("off_gravpm", C.c_int32), ("off_hsml", C.c_int32),
+                ("off_potential", C.c_int32), ("off_pi", C.c_int32), ("off_timebin_hydro", C.c_int32),
+                ("off_timebin_gravity", C.c_int32)]
+
+
+class TreeInfo(C.Structure):
+    _fields_ = [("numnodes", C.c_int64), ("numparticles", C.c_int64), ("maxdepth", C.c_int32),
+                ("overfull_leaves", C.c_int32), ("root_mass", C.c_double)]
+
+
+class GravShortParams(C.Structure):
+    """struct gravshort_tree_params (libgadget/gravity.h:9-22) + GravShortPriv scalars."""
+    _fields_ = [("ErrTolForceAcc", C.c_double), ("BHOpeningAngle", C.c_double),
+                ("MaxBHOpeningAngle", C.c_double), ("TreeUseBH", C.c_int32), ("pad_", C.c_int32),
+                ("Rcut", C.c_double), ("GravitySoftening", C.c_double), ("rho0", C.c_double)]
+
+
+class Timings(C.Structure):
+    _fields_ = [(k, C.c_double) for k in (
+        "pm_deposit", "pm_fft_forward", "pm_transfer", "pm_fft_inverse", "pm_gradient", "pm_readout", "pm_total",
+        "tree_keys", "tree_sort", "tree_nodes", "tree_moments", "tree_total", "walk", "walk_post", "h2d", "d2h")]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+COUNTS_DTYPE = np.dtype([("nodes_accepted", "i4"), ("nodes_opened", "i4"),
+                         ("nodes_discarded", "i4"), ("particles", "i4")])
+
+# struct particle_data of the reference (libgadget/partmanager.h:9-71), 160 bytes.
+PARTICLE_DTYPE = np.dtype({
+    "names": ["Pos", "TopLeaf", "Mass", "PI", "flags", "TimeBinHydro", "TimeBinGravity", "Type",
+              "Vel", "FullTreeGravAccel", "GravPM", "Ti_drift", "Hsml", "DtHsml", "ID", "GrNr", "Potential"],
+    "formats": [("f8", 3), "i4", "f4", "i4", "u1", "u1", "u1", "u1",
+                ("f8", 3), ("f8", 3), ("f8", 3), "i8", "f8", "f8", "u8", "i8", "f8"],
+    "offsets": [0, 24, 28, 32, 36, 37, 38, 39, 40, 64, 88, 112, 120, 128, 136, 144, 152],
+    "itemsize": 160})
+
+EXPORTED = [
+    "b200_default_particle_layout", "b200_ctx_create", "b200_ctx_destroy", "b200_last_error",
+    "b200_abi_version", "b200_kernel_launches", "b200_set_particles_aos", "b200_set_particles_soa",
+    "b200_set_particles_soa_dev", "b200_oldacc_from_last_step", "b200_pm_init", "b200_pm_force",
+    "b200_pm_force_dev", "b200_pm_cell_index", "b200_pm_copy_mesh", "b200_tree_build", "b200_tree_free",
+    "b200_tree_export", "b200_grav_short_tree", "b200_grav_short_tree_dev", "b200_force_step_aos",
+    "b200_get_timings", "b200_stream",
+]
+
+
+def build(verbose=False):
+    """Compile csrc/ for sm_100a into libb200force.so (in-tree)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "-j4"], stdout=out)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libb200force.so is not built (run __graft_entry__.build()); "
+                               "there is no fallback path")
+        L = C.CDLL(LIB_PATH)
+        L.b200_last_error.restype = C.c_char_p
+        L.b200_kernel_launches.restype = C.c_int64
+        L.b200_stream.restype = C.c_void_p
+        L.b200_ctx_destroy.restype = None
+        L.b200_tree_free.restype = None
+        L.b200_default_particle_layout.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class Engine:
+    """One engine = one GPU (b200_ctx)."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        self.ctx = C.c_void_p()
+        rc = self.L.b200_ctx_create(C.byref(self.ctx), C.c_int(device))
+        if rc != 0:
+            self.ctx = None
+            raise B200Error("b200_ctx_create failed (rc=%d): no CUDA device / no fallback" % rc)
+        self.n = 0
+        self.nmesh = 0
+
+    def close(self):
+        if self.ctx is not None:
+            self.L.b200_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise B200Error(self.L.b200_last_error(self.ctx).decode())
+
+    # -- particles ---------------------------------------------------------
+    def set_particles(self, pos, mass, type=None, oldacc=None):
+        pos = _c(pos, np.float64); mass = _c(mass, np.float32)
+        type = _c(type, np.uint8); oldacc = _c(oldacc, np.float64)
+        self.n = len(mass)
+        self._keep = (pos, mass, type, oldacc)
+        self._ck(self.L.b200_set_particles_soa(self.ctx, _p(pos), _p(mass), _p(type), _p(oldacc), C.c_int64(self.n)))
+
+    def set_particles_dev(self, pos_ptr, mass_ptr, n, type_ptr=None, oldacc_ptr=None):
+        self.n = int(n)
+        self._ck(self.L.b200_set_particles_soa_dev(self.ctx, C.c_void_p(pos_ptr), C.c_void_p(mass_ptr),
+                                                   C.c_void_p(type_ptr) if type_ptr else None,
+                                                   C.c_void_p(oldacc_ptr) if oldacc_ptr else None, C.c_int64(self.n)))
+
+    def set_particles_aos(self, P):
+        assert P.dtype.itemsize == 160
+        self.n = len(P)
+        self._ck(self.L.b200_set_particles_aos(self.ctx, _p(P), C.c_int64(self.n), None))
+
+    def oldacc_from_last_step(self):
+        self._ck(self.L.b200_oldacc_from_last_step(self.ctx))
+
+    # -- PM: gravpm_init_periodic / gravpm_force -----------------------------
+    def gravpm_init_periodic(self, BoxSize, Asmth, Nmesh, G):
+        self.nmesh = int(Nmesh)
+        self._ck(self.L.b200_pm_init(self.ctx, C.c_double(BoxSize), C.c_double(Asmth), C.c_int(Nmesh), C.c_double(G)))
+
+    def gravpm_force(self, want_potential=True):
+        g = np.empty((self.n, 3))
+        p = np.empty(self.n) if want_potential else None
+        self._ck(self.L.b200_pm_force(self.ctx, _p(g), _p(p)))
+        return g, p
+
+    def gravpm_force_dev(self, gravpm_ptr=None, pot_ptr=None):
+        self._ck(self.L.b200_pm_force_dev(self.ctx, C.c_void_p(gravpm_ptr) if gravpm_ptr else None,
+                                          C.c_void_p(pot_ptr) if pot_ptr else None))
+
+    def pm_cell_index(self):
+        ic = np.empty((self.n, 3), dtype=np.int32)
+        self._ck(self.L.b200_pm_cell_index(self.ctx, _p(ic)))
+        return ic
+
+    def pm_copy_mesh(self, which):
+        m = np.empty((self.nmesh,) * 3)
+        self._ck(self.L.b200_pm_copy_mesh(self.ctx, C.c_int(which), _p(m)))
+        return m
+
+    # -- tree: force_tree_full / force_tree_active_moments --------------------
+    def force_tree_build(self, BoxSize, mask=ALLMASK, active=None, toplevel_depth=0):
+        info = TreeInfo()
+        active = _c(active, np.int32)
+        na = 0 if active is None else len(active)
+        self._ck(self.L.b200_tree_build(self.ctx, C.c_double(BoxSize), C.c_int(mask), _p(active), C.c_int64(na),
+                                        C.c_int(toplevel_depth), C.byref(info)))
+        self.tree_info = info
+        return info
+
+    def force_tree_full(self, BoxSize):
+        return self.force_tree_build(BoxSize, ALLMASK, None, 0)
+
+    def tree_export(self):
+        nn = self.tree_info.numnodes
+        out = dict(center=np.empty((nn, 3)), len=np.empty(nn), cofm=np.empty((nn, 3)), mass=np.empty(nn),
+                   hmax=np.empty(nn), sibling=np.empty(nn, np.int32), firstchild=np.empty(nn, np.int32),
+                   nocc=np.empty(nn, np.int32), part=np.empty((nn, 8), np.int32))
+        self._ck(self.L.b200_tree_export(self.ctx, _p(out["center"]), _p(out["len"]), _p(out["cofm"]), _p(out["mass"]),
+                                         _p(out["hmax"]), _p(out["sibling"]), _p(out["firstchild"]), _p(out["nocc"]),
+                                         _p(out["part"])))
+        return out
+
+    # -- grav_short_tree -------------------------------------------------------
+    def grav_short_tree(self, par, active=None, want_counts=False, want_potential=True):
+        p = GravShortParams(**par) if isinstance(par, dict) else par
+        acc = np.zeros((self.n, 3))
+        pot = np.zeros(self.n) if want_potential else None
+        cnt = np.zeros(self.n, dtype=COUNTS_DTYPE) if want_counts else None
+        active = _c(active, np.int32)
+        na = 0 if active is None else len(active)
+        self._ck(self.L.b200_grav_short_tree(self.ctx, C.byref(p), _p(active), C.c_int64(na), _p(acc), _p(pot), _p(cnt)))
+        return acc, pot, cnt
+
+    def grav_short_tree_dev(self, par, acc_ptr=None, pot_ptr=None):
+        p = GravShortParams(**par) if isinstance(par, dict) else par
+        self._ck(self.L.b200_grav_short_tree_dev(self.ctx, C.byref(p), None, C.c_int64(0),
+                                                 C.c_void_p(acc_ptr) if acc_ptr else None,
+                                                 C.c_void_p(pot_ptr) if pot_ptr else None, None))
+
+    # -- whole step on the reference's AoS -------------------------------------
+    def force_step_aos(self, P, par, ptr=None, n=None):
+        p = GravShortParams(**par) if isinstance(par, dict) else par
+        if ptr is None:
+            ptr, n = P.ctypes.data, len(P)
+        self.n = int(n)
+        self._ck(self.L.b200_force_step_aos(self.ctx, C.c_void_p(ptr), C.c_int64(n), None, C.byref(p)))
+
+    def timings(self):
+        t = Timings()
+        self.L.b200_get_timings(self.ctx, C.byref(t))
+        return t.asdict()
+
+    def kernel_launches(self):
+        return int(self.L.b200_kernel_launches(self.ctx))
+
+    def stream(self):
+        return self.L.b200_stream(self.ctx)

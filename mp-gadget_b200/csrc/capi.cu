@@ -1,0 +1,443 @@
+// capi.cu -- the extern "C" surface declared in include/b200force.h.
+#include "engine.h"
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+namespace b200 {
+
+int fail(Engine *e, const char *what, cudaError_t err, const char *file, int line)
+{
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s failed: %s (%s:%d)", what, cudaGetErrorString(err), file, line);
+    e->err = buf;
+    return 1;
+}
+int failmsg(Engine *e, const std::string &msg) { e->err = msg; return 1; }
+
+void timer_start(Engine *E, int id)
+{
+    Timer &t = E->timers[id];
+    if(!t.a) { cudaEventCreate(&t.a); cudaEventCreate(&t.b); }
+    cudaEventRecord(t.a, E->stream);
+    t.used = false;
+}
+void timer_stop(Engine *E, int id)
+{
+    Timer &t = E->timers[id];
+    cudaEventRecord(t.b, E->stream);
+    t.used = true;
+}
+double timer_ms(Engine *E, int id)
+{
+    Timer &t = E->timers[id];
+    if(!t.used) return 0;
+    float ms = 0;
+    if(cudaEventSynchronize(t.b) != cudaSuccess) return 0;
+    if(cudaEventElapsedTime(&ms, t.a, t.b) != cudaSuccess) return 0;
+    return ms;
+}
+
+// ---- ingest kernels -------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_unpack_aos(const uint8_t *__restrict__ aos, int64_t n, b200_particle_layout L,
+             double *__restrict__ pos, float *__restrict__ mass, uint8_t *__restrict__ type,
+             uint8_t *__restrict__ flags, double *__restrict__ oldacc)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const uint8_t *r = aos + i * L.stride;
+    const double *p = (const double *) (r + L.off_pos);
+    pos[3 * i] = p[0]; pos[3 * i + 1] = p[1]; pos[3 * i + 2] = p[2];
+    mass[i] = *(const float *) (r + L.off_mass);
+    type[i] = r[L.off_type];
+    flags[i] = r[L.off_flags] & 3;
+    const double *ft = (const double *) (r + L.off_fulltreeacc);
+    const double *pm = (const double *) (r + L.off_gravpm);
+    double s = 0;                       // grav_get_abs_accel gravshort.h:69-86
+#pragma unroll
+    for(int j = 0; j < 3; j++) {
+        const double a = __dadd_rn(ft[j], pm[j]);
+        s = __dadd_rn(s, __dmul_rn(a, a));
+    }
+    oldacc[i] = sqrt(s);
+}
+
+__global__ void __launch_bounds__(256)
+k_set_soa(int64_t n, const uint8_t *__restrict__ type_in, const double *__restrict__ oldacc3,
+          uint8_t *__restrict__ type, uint8_t *__restrict__ flags, double *__restrict__ oldacc)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    type[i] = type_in ? type_in[i] : 1;
+    flags[i] = 0;
+    double s = 0;
+    if(oldacc3) {
+#pragma unroll
+        for(int j = 0; j < 3; j++) { const double a = oldacc3[3 * i + j]; s = __dadd_rn(s, __dmul_rn(a, a)); }
+    }
+    oldacc[i] = sqrt(s);
+}
+
+__global__ void __launch_bounds__(256)
+k_oldacc_from_last(int64_t n, const double *__restrict__ tr, const double *__restrict__ pm, double *__restrict__ oldacc)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    double s = 0;
+#pragma unroll
+    for(int j = 0; j < 3; j++) {
+        const double a = __dadd_rn(tr ? tr[3 * i + j] : 0.0, pm ? pm[3 * i + j] : 0.0);
+        s = __dadd_rn(s, __dmul_rn(a, a));
+    }
+    oldacc[i] = sqrt(s);
+}
+
+// Write GravPM, FullTreeGravAccel, Potential back into the AoS staging copy.
+__global__ void __launch_bounds__(256)
+k_pack_aos(uint8_t *__restrict__ aos, int64_t n, b200_particle_layout L,
+           const double *__restrict__ gravpm, const double *__restrict__ treeacc,
+           const double *__restrict__ pot, int full_tree)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    uint8_t *r = aos + i * L.stride;
+    double *pm = (double *) (r + L.off_gravpm);
+    pm[0] = gravpm[3 * i]; pm[1] = gravpm[3 * i + 1]; pm[2] = gravpm[3 * i + 2];
+    if(full_tree) {
+        double *ft = (double *) (r + L.off_fulltreeacc);
+        ft[0] = treeacc[3 * i]; ft[1] = treeacc[3 * i + 1]; ft[2] = treeacc[3 * i + 2];
+        // TREEWALK_REDUCE assigns in primary mode (treewalk.h:202), so the tree
+        // potential replaces the PM potential accumulated earlier in the step.
+        *(double *) (r + L.off_potential) = pot[i];
+    }
+}
+
+static int ensure_particles(Engine *E, int64_t n)
+{
+    const size_t m = (size_t) (n > 0 ? n : 1);
+    CK(E->pos.ensure(3 * m)); CK(E->mass.ensure(m)); CK(E->type.ensure(m));
+    CK(E->flags.ensure(m)); CK(E->oldacc.ensure(m));
+    E->n = n;
+    E->tree_valid = false;
+    E->potential_valid = false;
+    E->have_last_tree = E->have_last_pm = false;
+    return 0;
+}
+
+static int collect_timings(Engine *E)
+{
+    b200_timings &t = E->last;
+    t.pm_deposit = timer_ms(E, T_PM_DEPOSIT); t.pm_fft_forward = timer_ms(E, T_PM_FFT_FWD);
+    t.pm_transfer = timer_ms(E, T_PM_TRANSFER); t.pm_fft_inverse = timer_ms(E, T_PM_FFT_INV);
+    t.pm_gradient = timer_ms(E, T_PM_GRADIENT); t.pm_readout = timer_ms(E, T_PM_READOUT);
+    t.pm_total = t.pm_deposit + t.pm_fft_forward + t.pm_transfer + t.pm_fft_inverse + t.pm_gradient + t.pm_readout;
+    t.tree_keys = timer_ms(E, T_TREE_KEYS); t.tree_sort = timer_ms(E, T_TREE_SORT);
+    t.tree_nodes = timer_ms(E, T_TREE_NODES); t.tree_moments = timer_ms(E, T_TREE_MOMENTS);
+    t.tree_total = t.tree_keys + t.tree_sort + t.tree_nodes + t.tree_moments;
+    t.walk = timer_ms(E, T_WALK); t.walk_post = timer_ms(E, T_WALK_POST);
+    t.h2d = timer_ms(E, T_H2D); t.d2h = timer_ms(E, T_D2H);
+    return 0;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+void b200_default_particle_layout(b200_particle_layout *L)
+{
+    // struct particle_data, libgadget/partmanager.h:9-71 (no -DDEBUG): 160 bytes
+    L->stride = 160; L->off_pos = 0; L->off_mass = 28; L->off_pi = 32; L->off_flags = 36;
+    L->off_timebin_hydro = 37; L->off_timebin_gravity = 38; L->off_type = 39;
+    L->off_vel = 40; L->off_fulltreeacc = 64; L->off_gravpm = 88; L->off_hsml = 120; L->off_potential = 152;
+}
+
+int b200_abi_version(void) { return B200_ABI_VERSION; }
+
+int b200_ctx_create(b200_ctx **out, int device)
+{
+    if(!out) return 1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if(e != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "b200_ctx_create: no CUDA device (%s); this engine has no CPU fallback\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return 2;
+    }
+    if(device < 0 || device >= ndev) { fprintf(stderr, "b200_ctx_create: bad device %d of %d\n", device, ndev); return 3; }
+    if(cudaSetDevice(device) != cudaSuccess) return 4;
+    b200_ctx *c = new (std::nothrow) b200_ctx();
+    if(!c) return 5;
+    c->e.device = device;
+    if(cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 6; }
+    *out = c;
+    return 0;
+}
+
+void b200_ctx_destroy(b200_ctx *ctx)
+{
+    if(!ctx) return;
+    Engine *E = &ctx->e;
+    cudaSetDevice(E->device);
+    cudaStreamSynchronize(E->stream);
+    pm_destroy(E);
+    E->pos.release(); E->mass.release(); E->type.release(); E->flags.release(); E->oldacc.release();
+    E->last_tree_acc.release(); E->last_pm_acc.release(); E->aos.release();
+    E->keys.release(); E->keys_alt.release(); E->sidx.release(); E->sidx_alt.release(); E->cubtemp.release();
+    E->spart.release(); E->b_start.release(); E->b_count.release(); E->b_father.release(); E->b_sibling.release();
+    E->b_firstchild.release(); E->b_nchild.release(); E->b_level.release(); E->b_size.release(); E->b_dfs.release();
+    E->b_scan.release(); E->b_center.release(); E->nodeA.release(); E->nodeB.release(); E->nodeC.release();
+    E->nodeF.release(); E->nodeH.release(); E->scratch_i.release(); E->targets.release();
+    E->d_acc.release(); E->d_pot.release(); E->d_counts.release(); E->srtab.release();
+    for(int i = 0; i < T_COUNT; i++) if(E->timers[i].a) { cudaEventDestroy(E->timers[i].a); cudaEventDestroy(E->timers[i].b); }
+    cudaStreamDestroy(E->stream);
+    delete ctx;
+}
+
+const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->e.err.c_str() : "null context"; }
+int64_t b200_kernel_launches(const b200_ctx *ctx) { return ctx ? ctx->e.launches : 0; }
+void *b200_stream(const b200_ctx *ctx) { return ctx ? (void *) ctx->e.stream : nullptr; }
+
+#define ENTER(ctx) if(!(ctx)) return 1; Engine *E = &(ctx)->e; if(cudaSetDevice(E->device) != cudaSuccess) return failmsg(E, "cudaSetDevice failed");
+
+int b200_set_particles_aos(b200_ctx *ctx, const void *P, int64_t n, const b200_particle_layout *layout)
+{
+    ENTER(ctx);
+    if(n < 0 || (n > 0 && !P)) return failmsg(E, "b200_set_particles_aos: bad arguments");
+    b200_particle_layout L; if(layout) L = *layout; else b200_default_particle_layout(&L);
+    if(int rc = ensure_particles(E, n)) return rc;
+    if(n == 0) return 0;
+    CK(E->aos.ensure((size_t) n * L.stride));
+    timer_start(E, T_H2D);
+    CK(cudaMemcpyAsync(E->aos.p, P, (size_t) n * L.stride, cudaMemcpyHostToDevice, E->stream));
+    timer_stop(E, T_H2D);
+    k_unpack_aos<<<(unsigned) ((n + 255) / 256), 256, 0, E->stream>>>(E->aos.p, n, L, E->pos.p, E->mass.p, E->type.p, E->flags.p, E->oldacc.p);
+    CKL(E);
+    return 0;
+}
+
+static int set_soa_common(Engine *E, const double *pos, const float *mass, const uint8_t *type,
+                          const double *oldacc, int64_t n, cudaMemcpyKind kind)
+{
+    if(n < 0 || (n > 0 && (!pos || !mass))) return failmsg(E, "b200_set_particles_soa: bad arguments");
+    if(int rc = ensure_particles(E, n)) return rc;
+    if(n == 0) return 0;
+    timer_start(E, T_H2D);
+    CK(cudaMemcpyAsync(E->pos.p, pos, 3 * n * sizeof(double), kind, E->stream));
+    CK(cudaMemcpyAsync(E->mass.p, mass, n * sizeof(float), kind, E->stream));
+    const uint8_t *d_type = nullptr; const double *d_old = nullptr;
+    if(type) {
+        if(kind == cudaMemcpyHostToDevice) { CK(E->aos.ensure((size_t) n)); CK(cudaMemcpyAsync(E->aos.p, type, n, kind, E->stream)); d_type = E->aos.p; }
+        else d_type = type;
+    }
+    if(oldacc) {
+        if(kind == cudaMemcpyHostToDevice) {
+            CK(E->last_tree_acc.ensure(3 * (size_t) n));
+            CK(cudaMemcpyAsync(E->last_tree_acc.p, oldacc, 3 * n * sizeof(double), kind, E->stream));
+            d_old = E->last_tree_acc.p;
+        } else d_old = oldacc;
+    }
+    timer_stop(E, T_H2D);
+    k_set_soa<<<(unsigned) ((n + 255) / 256), 256, 0, E->stream>>>(n, d_type, d_old, E->type.p, E->flags.p, E->oldacc.p);
+    CKL(E);
+    return 0;
+}
+
+int b200_set_particles_soa(b200_ctx *ctx, const double *pos, const float *mass, const uint8_t *type, const double *oldacc, int64_t n)
+{
+    ENTER(ctx);
+    return set_soa_common(E, pos, mass, type, oldacc, n, cudaMemcpyHostToDevice);
+}
+
+int b200_set_particles_soa_dev(b200_ctx *ctx, const double *pos, const float *mass, const uint8_t *type, const double *oldacc, int64_t n)
+{
+    ENTER(ctx);
+    return set_soa_common(E, pos, mass, type, oldacc, n, cudaMemcpyDeviceToDevice);
+}
+
+int b200_oldacc_from_last_step(b200_ctx *ctx)
+{
+    ENTER(ctx);
+    if(!E->have_last_tree && !E->have_last_pm) return failmsg(E, "b200_oldacc_from_last_step: no previous accelerations");
+    if(E->n == 0) return 0;
+    k_oldacc_from_last<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->n, E->have_last_tree ? E->last_tree_acc.p : nullptr,
+                                                                          E->have_last_pm ? E->last_pm_acc.p : nullptr, E->oldacc.p);
+    CKL(E);
+    return 0;
+}
+
+int b200_pm_init(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G)
+{
+    ENTER(ctx);
+    return pm_init(E, BoxSize, Asmth, Nmesh, G);
+}
+
+static int pm_force_common(Engine *E, double *gravpm_out, double *potential_out, bool host)
+{
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->last_pm_acc.ensure(3 * n));
+    double *d_g = E->last_pm_acc.p, *d_p = nullptr;
+    if(potential_out) {
+        if(host) { CK(E->d_pot.ensure(n)); d_p = E->d_pot.p; } else d_p = potential_out;
+    }
+    if(int rc = pm_force(E, d_g, d_p)) return rc;
+    E->have_last_pm = true;
+    if(E->n > 0) {
+        timer_start(E, T_D2H);
+        if(gravpm_out) CK(cudaMemcpyAsync(gravpm_out, d_g, 3 * E->n * sizeof(double), host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, E->stream));
+        if(potential_out && host) CK(cudaMemcpyAsync(potential_out, d_p, E->n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+        timer_stop(E, T_D2H);
+    }
+    CK(cudaStreamSynchronize(E->stream));
+    return collect_timings(E);
+}
+
+int b200_pm_force(b200_ctx *ctx, double *gravpm_out, double *potential_out) { ENTER(ctx); return pm_force_common(E, gravpm_out, potential_out, true); }
+int b200_pm_force_dev(b200_ctx *ctx, double *gravpm_out, double *potential_out) { ENTER(ctx); return pm_force_common(E, gravpm_out, potential_out, false); }
+
+int b200_pm_cell_index(b200_ctx *ctx, int32_t *icell_out)
+{
+    ENTER(ctx);
+    if(E->n == 0) return 0;
+    CK(E->d_counts.ensure(3 * (size_t) E->n));
+    if(int rc = pm_cell_index(E, E->d_counts.p)) return rc;
+    CK(cudaMemcpyAsync(icell_out, E->d_counts.p, 3 * E->n * sizeof(int32_t), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
+int b200_pm_copy_mesh(b200_ctx *ctx, int which, double *mesh_out)
+{
+    ENTER(ctx);
+    if(E->Nmesh == 0) return failmsg(E, "b200_pm_copy_mesh: call b200_pm_init first");
+    const size_t N3 = (size_t) E->Nmesh * E->Nmesh * E->Nmesh;
+    const double *src = nullptr;
+    if(which == 0) { if(int rc = pm_deposit(E)) return rc; src = E->mesh.p; }
+    else if(which == 1) { if(!E->potential_valid) return failmsg(E, "b200_pm_copy_mesh: no potential (call b200_pm_force)"); src = E->mesh.p; }
+    else if(which >= 2 && which <= 4) { if(!E->potential_valid) return failmsg(E, "b200_pm_copy_mesh: no force mesh"); src = E->fmesh.p + (which - 2) * N3; }
+    else return failmsg(E, "b200_pm_copy_mesh: which must be 0..4");
+    CK(cudaMemcpyAsync(mesh_out, src, N3 * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
+int b200_tree_build(b200_ctx *ctx, double BoxSize, int mask, const int32_t *active, int64_t nactive,
+                    int toplevel_depth, b200_tree_info *info)
+{
+    ENTER(ctx);
+    const int32_t *d_active = nullptr;
+    if(active) {
+        CK(E->targets.ensure((size_t) (nactive > 0 ? nactive : 1)));
+        CK(cudaMemcpyAsync(E->targets.p, active, nactive * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
+        d_active = E->targets.p;
+    }
+    int rc = tree_build(E, BoxSize, mask, d_active, nactive, toplevel_depth, info);
+    if(rc) return rc;
+    CK(cudaStreamSynchronize(E->stream));
+    return collect_timings(E);
+}
+
+void b200_tree_free(b200_ctx *ctx) { if(ctx) ctx->e.tree_valid = false; }
+
+int b200_tree_export(b200_ctx *ctx, double *center, double *len, double *cofm, double *mass, double *hmax,
+                     int32_t *sibling, int32_t *firstchild, int32_t *nocc, int32_t *leafpart)
+{
+    ENTER(ctx);
+    return tree_export(E, center, len, cofm, mass, hmax, sibling, firstchild, nocc, leafpart);
+}
+
+static int grav_common(Engine *E, const b200_gravshort_params *par, const int32_t *active, int64_t nactive,
+                       double *accel_out, double *potential_out, b200_walk_counts *counts_out, bool host)
+{
+    if(!par) return failmsg(E, "b200_grav_short_tree: null params");
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    const int32_t *d_active = nullptr;
+    if(active) {
+        if(host) {
+            CK(E->targets.ensure((size_t) (nactive > 0 ? nactive : 1)));
+            CK(cudaMemcpyAsync(E->targets.p, active, nactive * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
+            d_active = E->targets.p;
+        } else d_active = active;
+    }
+    CK(E->last_tree_acc.ensure(3 * n));
+    double *d_a = E->last_tree_acc.p, *d_p = nullptr;
+    b200_walk_counts *d_c = nullptr;
+    if(potential_out) { if(host) { CK(E->d_pot.ensure(n)); d_p = E->d_pot.p; } else d_p = potential_out; }
+    if(counts_out) {
+        if(host) { CK(E->d_counts.ensure(4 * n)); CK(cudaMemsetAsync(E->d_counts.p, 0, 4 * n * sizeof(int), E->stream)); d_c = (b200_walk_counts *) E->d_counts.p; }
+        else d_c = counts_out;
+    }
+    if(int rc = grav_short_tree(E, par, d_active, nactive, d_a, d_p, d_c)) return rc;
+    E->have_last_tree = (active == nullptr);
+    if(E->n > 0) {
+        timer_start(E, T_D2H);
+        const cudaMemcpyKind k = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+        if(accel_out) {
+            if(active == nullptr) CK(cudaMemcpyAsync(accel_out, d_a, 3 * E->n * sizeof(double), k, E->stream));
+            else if(host) {
+                // only the active entries are defined (GravShortPriv.Accel semantics, gravshort.h:41)
+                std::vector<double> tmp(3 * (size_t) E->n);
+                CK(cudaMemcpyAsync(tmp.data(), d_a, 3 * E->n * sizeof(double), k, E->stream));
+                CK(cudaStreamSynchronize(E->stream));
+                for(int64_t q = 0; q < nactive; q++) { const int64_t i = active[q]; for(int j = 0; j < 3; j++) accel_out[3 * i + j] = tmp[3 * i + j]; }
+            } else CK(cudaMemcpyAsync(accel_out, d_a, 3 * E->n * sizeof(double), k, E->stream));
+        }
+        if(potential_out && host) CK(cudaMemcpyAsync(potential_out, d_p, E->n * sizeof(double), k, E->stream));
+        if(counts_out && host) CK(cudaMemcpyAsync(counts_out, d_c, E->n * sizeof(b200_walk_counts), k, E->stream));
+        timer_stop(E, T_D2H);
+    }
+    CK(cudaStreamSynchronize(E->stream));
+    return collect_timings(E);
+}
+
+int b200_grav_short_tree(b200_ctx *ctx, const b200_gravshort_params *par, const int32_t *active, int64_t nactive,
+                         double *accel_out, double *potential_out, b200_walk_counts *counts_out)
+{
+    ENTER(ctx);
+    return grav_common(E, par, active, nactive, accel_out, potential_out, counts_out, true);
+}
+
+int b200_grav_short_tree_dev(b200_ctx *ctx, const b200_gravshort_params *par, const int32_t *active, int64_t nactive,
+                             double *accel_out, double *potential_out, b200_walk_counts *counts_out)
+{
+    ENTER(ctx);
+    return grav_common(E, par, active, nactive, accel_out, potential_out, counts_out, false);
+}
+
+int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_layout *layout,
+                        const b200_gravshort_params *par)
+{
+    ENTER(ctx);
+    if(E->Nmesh == 0) return failmsg(E, "b200_force_step_aos: call b200_pm_init first");
+    if(!par) return failmsg(E, "b200_force_step_aos: null params");
+    b200_particle_layout L; if(layout) L = *layout; else b200_default_particle_layout(&L);
+    if(int rc = b200_set_particles_aos(ctx, P, n, &L)) return rc;
+    if(n == 0) return 0;
+    const size_t m = (size_t) n;
+    CK(E->last_pm_acc.ensure(3 * m)); CK(E->last_tree_acc.ensure(3 * m)); CK(E->d_pot.ensure(m));
+    // gravpm_force (run.c:519-523)
+    if(int rc = pm_force(E, E->last_pm_acc.p, nullptr)) return rc;
+    // force_tree_full + grav_short_tree (run.c:546-548)
+    if(int rc = tree_build(E, E->Box, 63, nullptr, 0, 0, nullptr)) return rc;
+    if(int rc = grav_short_tree(E, par, nullptr, 0, E->last_tree_acc.p, E->d_pot.p, nullptr)) return rc;
+    E->have_last_pm = E->have_last_tree = true;
+    k_pack_aos<<<(unsigned) ((n + 255) / 256), 256, 0, E->stream>>>(E->aos.p, n, L, E->last_pm_acc.p, E->last_tree_acc.p, E->d_pot.p, 1);
+    CKL(E);
+    timer_start(E, T_D2H);
+    CK(cudaMemcpyAsync(P, E->aos.p, m * L.stride, cudaMemcpyDeviceToHost, E->stream));
+    timer_stop(E, T_D2H);
+    CK(cudaStreamSynchronize(E->stream));
+    return collect_timings(E);
+}
+
+int b200_get_timings(const b200_ctx *ctx, b200_timings *t)
+{
+    if(!ctx || !t) return 1;
+    *t = ctx->e.last;
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,142 @@
+// engine.h -- internal state of the B200 force engine (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/b200force.h"
+
+namespace b200 {
+
+// Grow-only device buffer.
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t ensure(size_t n) {
+        if(n <= cap) return cudaSuccess;
+        if(p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 16 + 64;
+        cudaError_t e = cudaMalloc((void **) &p, want * sizeof(T));
+        if(e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if(p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    bool used = false;
+};
+
+enum TimerId {
+    T_PM_DEPOSIT, T_PM_FFT_FWD, T_PM_TRANSFER, T_PM_FFT_INV, T_PM_GRADIENT, T_PM_READOUT,
+    T_TREE_KEYS, T_TREE_SORT, T_TREE_NODES, T_TREE_MOMENTS,
+    T_WALK, T_WALK_POST, T_H2D, T_D2H, T_COUNT
+};
+
+// Node record used by the walk, DFS order.  A,B are 32-byte rows so that one
+// warp-uniform LDG.128 pair fetches each.
+struct NodeAux {           // int4
+    int sibling;           // DFS index of the next node when skipping the subtree, -1 at the end
+    int pstart;            // first particle (sorted order) of the subtree
+    int count;             // particles in the subtree
+    int leaf;              // 1: particle leaf, 0: internal (first child = self + 1)
+};
+
+struct Engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // ---- particles (original index order) ----
+    int64_t n = 0;
+    DevBuf<double> pos;        // [n][3]
+    DevBuf<float> mass;        // [n]
+    DevBuf<uint8_t> type;      // [n]
+    DevBuf<uint8_t> flags;     // [n] bit0 garbage bit1 swallowed
+    DevBuf<double> oldacc;     // [n] |FullTreeGravAccel + GravPM| (not divided by G)
+    DevBuf<double> last_tree_acc;  // [n][3]
+    DevBuf<double> last_pm_acc;    // [n][3]
+    bool have_last_tree = false, have_last_pm = false;
+    DevBuf<uint8_t> aos;       // staging for AoS ingest / write-back
+
+    // ---- PM ----
+    double Box = 0, Asmth = 0, G = 0;
+    int Nmesh = 0;
+    cufftHandle plan_fwd = 0, plan_inv = 0;
+    bool plans = false;
+    DevBuf<double> mesh;       // real mesh Nmesh^3 (density, then potential)
+    DevBuf<double> cplx;       // Nmesh^2 (Nmesh/2+1) complex, interleaved
+    DevBuf<double> fmesh;      // 3 force meshes
+    DevBuf<double> ktab;       // per-dimension deconvolution factor 1/sinc^2, [Nmesh]
+    DevBuf<uint8_t> fftwork;
+    bool potential_valid = false;
+
+    // ---- tree ----
+    bool tree_valid = false;
+    double tree_box = 0;
+    int64_t tree_np = 0;        // particles in the tree
+    int64_t tree_nn = 0;        // nodes
+    int tree_maxdepth = 0;
+    int tree_overfull = 0;
+    bool tree_full = false;     // contains every particle (full_particle_tree_flag)
+    DevBuf<unsigned long long> keys, keys_alt;
+    DevBuf<int> sidx, sidx_alt;   // sorted -> original index
+    DevBuf<uint8_t> cubtemp;
+    DevBuf<double> spart;       // [np] double4 {x,y,z,m} in sorted order
+    // build-time (BFS order) node fields
+    DevBuf<int> b_start, b_count, b_father, b_sibling, b_firstchild, b_nchild, b_level, b_size, b_dfs, b_scan;
+    DevBuf<double> b_center;    // [.][4] cx,cy,cz,len
+    // final (DFS order)
+    DevBuf<double> nodeA;       // [nn] double4 cofm.xyz, mass
+    DevBuf<double> nodeB;       // [nn] double4 center.xyz, len
+    DevBuf<int> nodeC;          // [nn] NodeAux
+    DevBuf<int> nodeF;          // [nn] father (DFS)
+    DevBuf<double> nodeH;       // [nn] hmax
+    DevBuf<int> scratch_i;      // small device scalars
+
+    // ---- walk ----
+    DevBuf<int> targets;        // walk target list (original indices)
+    DevBuf<double> d_acc, d_pot;  // outputs [n][3], [n]
+    DevBuf<int> d_counts;       // [n] b200_walk_counts
+    DevBuf<float> srtab;        // 2*512 short-range window tables
+
+    Timer timers[T_COUNT];
+    b200_timings last = {};
+};
+
+// error helpers -----------------------------------------------------------
+int fail(Engine *e, const char *what, cudaError_t err, const char *file, int line);
+int failmsg(Engine *e, const std::string &msg);
+#define CK(call) do { cudaError_t _e = (call); if(_e != cudaSuccess) return b200::fail(E, #call, _e, __FILE__, __LINE__); } while(0)
+#define CKL(E_) do { (E_)->launches++; cudaError_t _e = cudaGetLastError(); if(_e != cudaSuccess) return b200::fail((E_), "kernel launch", _e, __FILE__, __LINE__); } while(0)
+
+void timer_start(Engine *E, int id);
+void timer_stop(Engine *E, int id);
+double timer_ms(Engine *E, int id);
+
+// PM (pm.cu)
+int pm_init(Engine *E, double Box, double Asmth, int Nmesh, double G);
+void pm_destroy(Engine *E);
+int pm_deposit(Engine *E);
+int pm_force(Engine *E, double *d_gravpm, double *d_pot);   // device outputs, [n][3] / [n], may be null
+int pm_cell_index(Engine *E, int32_t *d_icell);
+
+// tree (tree_build.cu)
+int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t nactive,
+               int toplevel_depth, b200_tree_info *info);
+int tree_export(Engine *E, double *center, double *len, double *cofm, double *mass, double *hmax,
+                int32_t *sibling, int32_t *firstchild, int32_t *nocc, int32_t *leafpart);
+
+// walk (tree_walk.cu)
+int walk_init_tables(Engine *E);
+int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *d_active,
+                    int64_t nactive, double *d_acc, double *d_pot, b200_walk_counts *d_counts);
+
+} // namespace b200
+
+struct b200_ctx { b200::Engine e; };

@@ -1,0 +1,95 @@
+"""Synthetic initial conditions for tests and bench.
+
+Seeded, self-contained (no reference data files): a cubic lattice displaced by
+a Zel'dovich-like Gaussian displacement field with P(k) ~ k^-2, rms 3-D
+displacement `rms` lattice spacings ("z9" state), optionally with the
+reference's clustered recipe (tests/test_gravity.c:288-302) mixed in.
+Also the reference's unit-test particle distributions, restated.
+"""
+import numpy as np
+
+G_INTERNAL = 43.0071          # tests/test_gravity.c:35
+OMEGA0 = 0.288
+HUBBLE = 100.0                # km/s/(Mpc/h) with Mpc/h length units
+
+
+def rho_crit(G=G_INTERNAL):
+    return 3 * HUBBLE ** 2 / (8 * np.pi * G)
+
+
+def default_nmesh(ncbrt):
+    """run.c:211-212: Nmesh = 3 * 2^floor(log2(cbrt(N_dm)))."""
+    return 3 * 2 ** int(np.floor(np.log2(ncbrt) + 1e-9))
+
+
+def zeldovich_lattice(ng, box, seed=181170, rms=0.2):
+    """ng^3 particles; returns pos[n,3] (f64, in [0,box)), mass[n] (f32)."""
+    rng = np.random.default_rng(seed)
+    spacing = box / ng
+    noise = rng.standard_normal((ng, ng, ng)).astype(np.float32)
+    nk = np.fft.rfftn(noise)
+    del noise
+    kx = np.fft.fftfreq(ng) * ng
+    kz = np.fft.rfftfreq(ng) * ng
+    k2 = (kx[:, None, None] ** 2 + kx[None, :, None] ** 2 + kz[None, None, :] ** 2).astype(np.float32)
+    k2[0, 0, 0] = 1.0
+    # delta_k ~ noise / k ; psi_k = i k delta_k / k^2  -> noise * i k / k^3
+    amp = nk / (k2 ** 1.5)
+    amp[0, 0, 0] = 0
+    amp[k2 > (ng / 2) ** 2] = 0
+    del nk
+    disp = []
+    for kk in (kx[:, None, None], kx[None, :, None], kz[None, None, :]):
+        disp.append(np.fft.irfftn(1j * kk * amp, s=(ng, ng, ng)).astype(np.float64))
+    del amp
+    var = sum((x ** 2).mean() for x in disp)
+    scale = rms * spacing / np.sqrt(var)
+    g = (np.arange(ng) + 0.5) * spacing
+    pos = np.empty((ng ** 3, 3), dtype=np.float64)
+    pos[:, 0] = (g[:, None, None] + scale * disp[0]).ravel()
+    pos[:, 1] = (g[None, :, None] + scale * disp[1]).ravel()
+    pos[:, 2] = (g[None, None, :] + scale * disp[2]).ravel()
+    np.mod(pos, box, out=pos)
+    pos[pos >= box] = 0.0
+    mass = np.full(ng ** 3, OMEGA0 * rho_crit() * spacing ** 3, dtype=np.float32)
+    return pos, mass
+
+
+def clustered_mix(n, box, seed=0):
+    """tests/test_gravity.c:288-302 (do_random_test): 1/4 uniform, 1/2 in a
+    clump at box/2, 1/4 in a clump at 0.1 box.  With seed=0 the stream is the
+    one the reference test draws: gsl_rng_mt19937 seeded with 0 (= MT19937
+    init_genrand(4357)), gsl_rng_uniform = 32-bit draw / 2^32."""
+    bg = np.random.MT19937()
+    bg._legacy_seeding(4357 if seed == 0 else seed)
+    return clustered_mix_from(bg, n, box)
+
+
+def clustered_mix_from(bg, n, box):
+    u = bg.random_raw(3 * n).astype(np.float64) / 4294967296.0
+    u = u.reshape(n, 3)
+    pos = np.empty((n, 3))
+    a, b = n // 4, 3 * n // 4
+    pos[:a] = box * u[:a]
+    pos[a:b] = box / 2 + box / 8 * np.exp((u[a:b] - 0.5) ** 2)
+    pos[b:] = box * 0.1 + box / 32 * np.exp((u[b:] - 0.5) ** 2)
+    return pos
+
+
+def lattice(nc, box):
+    """tests/test_gravity.c:231-235 / test_forcetree.c lattice."""
+    i = np.arange(nc ** 3)
+    return np.stack([(box / nc) * (i // nc // nc), (box / nc) * ((i // nc) % nc), (box / nc) * (i % nc)], 1).astype(np.float64)
+
+
+def close_cluster(nc, close=5000.0):
+    """tests/test_gravity.c:270-276: tight clump at 4 + idx/close."""
+    i = np.arange(nc ** 3)
+    return np.stack([4. + (i // nc // nc) / close, 4. + ((i // nc) % nc) / close, 4. + (i % nc) / close], 1)
+
+
+def tree_params(box, n, treeusebh=0, errtol=0.002, rcut=6.0):
+    """Defaults of gadget/params.c:112-116,192 (ErrTolForceAcc, BHOpeningAngle,
+    MaxBHOpeningAngle, TreeRcut, GravitySoftening = 1/30 mean spacing)."""
+    return dict(ErrTolForceAcc=errtol, BHOpeningAngle=0.175, MaxBHOpeningAngle=0.9, TreeUseBH=treeusebh,
+                Rcut=rcut, GravitySoftening=(1 / 30.) * box / np.cbrt(n), rho0=OMEGA0 * rho_crit())

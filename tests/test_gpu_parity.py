@@ -1,0 +1,211 @@
+"""GPU parity tests: CUDA path (through the C-ABI) vs the CPU oracle.
+
+Bars (BASELINE.json north_star): PM cell indices, tree topology, tree opening
+and interaction counts bit-exact; fp64 accelerations within 1e-6 relative.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+G = 43.0071
+ACC_RTOL = 1e-6          # north_star tolerance for fp64 accelerations
+
+
+def _distributions(ics):
+    box = 8.0
+    rng = np.random.default_rng(42)
+    out = {
+        "lattice16": (ics.lattice(16, box), box),
+        "close16": (ics.close_cluster(16), box),
+        "gslrandom16": (ics.clustered_mix(16 ** 3, box, seed=0), box),
+        "uniform20k": (rng.random((20000, 3)) * box, box),
+    }
+    p, _ = ics.zeldovich_lattice(32, 32.0)
+    out["zeldovich32"] = (p, 32.0)
+    return out
+
+
+def _relerr(a, b):
+    scale = np.sqrt((b ** 2).sum(axis=1)).mean() + 1e-300
+    return np.abs(a - b).max() / scale
+
+
+@pytest.mark.parametrize("name", ["lattice16", "close16", "gslrandom16", "uniform20k", "zeldovich32"])
+def test_pm_parity(engine, ics, name):
+    pos, box = _distributions(ics)[name]
+    n = len(pos)
+    mass = np.ones(n, dtype=np.float32)
+    nmesh, asmth = 48, 1.5
+    engine.set_particles(pos, mass)
+    engine.gravpm_init_periodic(box, asmth, nmesh, G)
+    g, p = engine.gravpm_force()
+    og, op, oic, odens, opot = oracle.pm_force(pos, mass, box, nmesh, asmth, G, return_mesh=True)
+    # PM indexing bit-exact (petapm.c:976-980)
+    assert np.array_equal(engine.pm_cell_index(), oic)
+    # potential mesh and the readouts
+    potmesh = engine.pm_copy_mesh(1)
+    assert np.abs(potmesh - opot).max() <= 1e-11 * np.abs(opot).max()
+    dens = engine.pm_copy_mesh(0)
+    assert np.abs(dens - odens).max() <= 1e-13 * odens.max()
+    assert abs(dens.sum() - mass.sum(dtype=np.float64)) <= 1e-9 * n      # verify_density_field petapm.c:1059-1089
+    assert np.abs(p - op).max() <= 1e-10 * np.abs(op).max()
+    # forces: real-space 4-point difference vs the reference's k-space filter
+    scale = max(np.abs(og).max(), 1e-300)
+    assert np.abs(g - og).max() <= 1e-9 * scale, (np.abs(g - og).max(), scale)
+
+
+@pytest.mark.parametrize("name", ["lattice16", "close16", "gslrandom16", "uniform20k", "zeldovich32"])
+@pytest.mark.parametrize("topdepth", [0, 2])
+def test_tree_parity(engine, ics, name, topdepth):
+    pos, box = _distributions(ics)[name]
+    n = len(pos)
+    rng = np.random.default_rng(7)
+    mass = (1.0 + rng.random(n)).astype(np.float32)
+    engine.set_particles(pos, mass)
+    info = engine.force_tree_build(box, toplevel_depth=topdepth)
+    ot = oracle.OracleTree(pos, mass, box, toplevel_depth=topdepth)
+    assert info.numnodes == ot.t.numnodes
+    assert info.numparticles == n
+    assert info.overfull_leaves == 0
+    t = engine.tree_export()
+    on = ot.nodes
+    assert np.array_equal(t["len"], on["len"])
+    assert np.array_equal(t["center"], on["center"])
+    assert np.array_equal(t["sibling"], on["sibling"])
+    assert np.array_equal(t["firstchild"], on["firstchild"])
+    assert np.array_equal(t["nocc"], on["nocc"])
+    assert np.array_equal(t["part"], on["part"])
+    assert np.array_equal(t["mass"], on["mass"])
+    assert np.array_equal(t["cofm"], on["cofm"])
+    assert info.root_mass == on["mass"][0]
+
+
+def _walk_case(engine, ics, pos, box, nmesh, par, oldacc=None, active=None):
+    n = len(pos)
+    mass = np.ones(n, dtype=np.float32)
+    engine.set_particles(pos, mass, oldacc=oldacc)
+    engine.gravpm_init_periodic(box, 1.5, nmesh, G)
+    engine.force_tree_build(box, active=active)
+    acc, pot, cnt = engine.grav_short_tree(par, active=active, want_counts=True)
+    ot = oracle.OracleTree(pos, mass, box, active=active)
+    oacc, opot, ocnt = ot.grav_short_tree(par, G, nmesh, 1.5, oldacc=oldacc, active=active, full=active is None)
+    return acc, pot, cnt, oacc, opot, ocnt
+
+
+@pytest.mark.parametrize("name", ["lattice16", "close16", "gslrandom16", "uniform20k", "zeldovich32"])
+@pytest.mark.parametrize("usebh", [1, 0])
+def test_walk_parity(engine, ics, name, usebh):
+    pos, box = _distributions(ics)[name]
+    n = len(pos)
+    par = ics.tree_params(box, n, treeusebh=usebh, rcut=7.0)
+    oldacc = None
+    if usebh == 0:
+        rng = np.random.default_rng(3)
+        oldacc = rng.standard_normal((n, 3)) * 500.0
+    acc, pot, cnt, oacc, opot, ocnt = _walk_case(engine, ics, pos, box, 48, par, oldacc=oldacc)
+    for f in ("nodes_accepted", "nodes_opened", "nodes_discarded", "particles"):
+        assert np.array_equal(cnt[f], ocnt[f]), f
+    assert _relerr(acc, oacc) < ACC_RTOL
+    assert np.abs(pot - opot).max() <= ACC_RTOL * np.abs(opot).max()
+
+
+def test_walk_active_subset(engine, ics):
+    """Tree of active particles only, walked for the same subset
+    (force_tree_active_moments + grav_short_tree, timestep.c:282-290)."""
+    pos, box = _distributions(ics)["gslrandom16"]
+    n = len(pos)
+    rng = np.random.default_rng(11)
+    active = np.sort(rng.choice(n, size=n // 3, replace=False)).astype(np.int32)
+    par = ics.tree_params(box, n, treeusebh=1, rcut=7.0)
+    acc, pot, cnt, oacc, opot, ocnt = _walk_case(engine, ics, pos, box, 48, par, active=active)
+    assert np.array_equal(cnt["particles"][active], ocnt["particles"][active])
+    assert np.array_equal(cnt["nodes_accepted"][active], ocnt["nodes_accepted"][active])
+    assert _relerr(acc[active], oacc[active]) < ACC_RTOL
+    inactive = np.setdiff1d(np.arange(n), active)
+    assert np.all(acc[inactive] == 0)
+
+
+@pytest.mark.parametrize("name,direct", [("lattice16", False), ("close16", True), ("gslrandom16", True)])
+def test_reference_gravity_bounds(engine, ics, name, direct):
+    """The reference's own acceptance test for TreePM (tests/test_gravity.c:146-160,
+    222-318) run through the CUDA path: Nmesh 48, Asmth 1.5, BH angle 0.175,
+    Rcut 7, softening 1/30, two tree passes."""
+    pos, box = _distributions(ics)[name]
+    n = len(pos)
+    mass = np.ones(n, dtype=np.float32)
+    errtol = 0.002
+    par = dict(ErrTolForceAcc=errtol, BHOpeningAngle=0.175, MaxBHOpeningAngle=0.0, TreeUseBH=1, Rcut=7.0,
+               GravitySoftening=(1 / 30.) * box / np.cbrt(n), rho0=1.0)
+    engine.set_particles(pos, mass)
+    engine.gravpm_init_periodic(box, 1.5, 48, G)
+    gpm, _ = engine.gravpm_force()
+    engine.force_tree_full(box)
+    acc, _, _ = engine.grav_short_tree(par)
+    engine.oldacc_from_last_step()
+    acc, _, _ = engine.grav_short_tree(par)
+    tot = acc + gpm
+    if not direct:
+        assert np.abs(tot).max() < 0.015
+        assert np.abs(tot).mean() < 0.005
+        return
+    ds = oracle.direct_sum(pos, mass, box, G, 2.8 * par["GravitySoftening"], repeat=1)
+    meanacc = np.abs(ds).mean()
+    err = np.abs(ds - tot) / meanacc
+    assert err.max() < 3 * errtol
+    assert err.mean() < 0.8 * errtol
+
+
+def test_force_step_aos(engine, b200, ics):
+    """b200_force_step_aos on the reference's 160-byte particle records equals
+    the separate PM + tree calls and writes GravPM / FullTreeGravAccel / Potential in place."""
+    pos, box = _distributions(ics)["gslrandom16"]
+    n = len(pos)
+    P = np.zeros(n, dtype=b200.PARTICLE_DTYPE)
+    P["Pos"] = pos
+    P["Mass"] = 1.0
+    P["Type"] = 1
+    P["ID"] = np.arange(n)
+    rng = np.random.default_rng(5)
+    P["FullTreeGravAccel"] = rng.standard_normal((n, 3)) * 300
+    P["GravPM"] = rng.standard_normal((n, 3)) * 30
+    old = P["FullTreeGravAccel"] + P["GravPM"]
+    par = ics.tree_params(box, n, treeusebh=0, rcut=7.0)
+    engine.gravpm_init_periodic(box, 1.5, 48, G)
+    engine.force_step_aos(P, par)
+    engine.set_particles(pos, np.ones(n, np.float32), oldacc=old)
+    g, _ = engine.gravpm_force()
+    engine.force_tree_full(box)
+    acc, pot, _ = engine.grav_short_tree(par)
+    assert np.array_equal(P["GravPM"], g)
+    assert np.array_equal(P["FullTreeGravAccel"], acc)
+    assert np.array_equal(P["Potential"], pot)
+    assert np.array_equal(P["Pos"], pos) and np.all(P["ID"] == np.arange(n))
+
+
+def test_empty_and_tiny_inputs(engine, ics):
+    """Edge cases: no particles, one particle, particles exactly on the box edge
+    (Pos == BoxSize is legal, drift.c:77-78 -> iCell == Nmesh wraps, petapm.c:903-906)."""
+    box = 8.0
+    engine.gravpm_init_periodic(box, 1.5, 48, G)
+    par = ics.tree_params(box, 8, treeusebh=1)
+    engine.set_particles(np.zeros((0, 3)), np.zeros(0, np.float32))
+    g, p = engine.gravpm_force()
+    assert g.shape == (0, 3)
+    info = engine.force_tree_full(box)
+    assert info.numnodes == 1 and info.numparticles == 0
+    pos = np.array([[box, box, box], [0.0, 0.0, 0.0], [box, 0.0, 4.0], [3.999, 4.0, 4.001]])
+    mass = np.ones(len(pos), np.float32)
+    engine.set_particles(pos, mass)
+    g, p = engine.gravpm_force()
+    og, op, oic = oracle.pm_force(pos, mass, box, 48, 1.5, G)
+    assert np.array_equal(engine.pm_cell_index(), oic)
+    assert np.abs(g - og).max() <= 1e-9 * np.abs(og).max()
+    engine.force_tree_full(box)
+    acc, pot, cnt = engine.grav_short_tree(par, want_counts=True)
+    ot = oracle.OracleTree(pos, mass, box)
+    oacc, opot, ocnt = ot.grav_short_tree(par, G, 48, 1.5)
+    assert np.array_equal(cnt["particles"], ocnt["particles"])
+    assert np.abs(acc - oacc).max() <= ACC_RTOL * max(np.abs(oacc).max(), 1e-300)
