@@ -1,0 +1,340 @@
+#!/usr/bin/env python3
+"""bench.py -- force-step throughput of the B200 TreePM engine.
+
+One "step" = one full gravity force step on a PM step of the reference
+(run.c:519-548 with SplitGravityTimestepsOn=0): gravpm_force + force_tree_full
++ grav_short_tree over all particles of a synthetic 256^3 dark-matter box
+(BASELINE.json configs[1]: Nmesh 768, Asmth 1.5, TreeRcut 6, ErrTolForceAcc
+0.002, relative opening criterion fed by the previous step's accelerations).
+
+  value : particles / second, inputs resident in HBM, timed with CUDA events on
+          the engine's stream (max over ranks).
+  e2e   : the same step through b200_force_step_aos on the reference's 160-byte
+          particle records in pinned HOST memory, H2D + D2H inside the timed region.
+  --impl reference : the CPU path (the reference's own tree C from oracle/_ref when
+          built, else the oracle port; PM = oracle restatement + pocketfft) on all
+          host threads, on a bounded sample of the same workload.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+G = 43.0071
+METRIC = "particles/sec per force step (PM+tree)"
+UNIT = "particles/s"
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_force_step(ng, steps=1, warmup=0):
+    """The CPU path on an ng^3 Zel'dovich box with the bench's parameters.
+    Returns (particles_per_second, kind, seconds_per_step)."""
+    import numpy as np
+    import oracle
+    ics = importlib.import_module("mp-gadget_b200.ics")
+    box = float(ng)
+    nmesh = ics.default_nmesh(ng)
+    pos, mass = ics.zeldovich_lattice(ng, box)
+    n = len(mass)
+    par = ics.tree_params(box, n, treeusebh=0)
+    ref = None
+    try:
+        refmod = importlib.import_module("oracle.ref")
+        ref = refmod.load()
+    except Exception:
+        ref = None
+    kind = "reference" if ref is not None else "port"
+    nthr = host_threads()
+    os.environ.setdefault("OMP_NUM_THREADS", str(nthr))
+    oldacc = None
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        gpm, _, _ = oracle.pm_force(pos, mass, box, nmesh, 1.5, G, workers=nthr)
+        if ref is not None:
+            acc = ref.tree_gravity(pos, mass, box, nmesh, 1.5, G, par, oldacc)
+        else:
+            tr = oracle.OracleTree(pos, mass, box)
+            acc, _, _ = tr.grav_short_tree(par, G, nmesh, 1.5, oldacc=oldacc)
+        dt = time.perf_counter() - t0
+        oldacc = acc + gpm
+        if it >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    return n / t, kind, t, nmesh
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ng = args.cpu_ng
+    v, kind, t, nm = cpu_force_step(ng, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    sample = "%d^3 Zel'dovich box, Nmesh %d, full force step (PM + tree build + walk), one OMP process" % (ng, nm)
+    out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "impl": "reference",
+           "config": {"workload": "256^3 DM-only TreePM force step (sampled at %d^3 on CPU)" % ng, "Nmesh": 768,
+                      "Asmth": 1.5, "TreeRcut": 6.0, "ErrTolForceAcc": 0.002},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": host_threads(), "kind": kind, "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--ng", type=int, default=256, help="particles per dimension per GPU")
+    ap.add_argument("--cpu-ng", type=int, default=128, help="CPU-baseline sample size per dimension")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback")
+    pkg = importlib.import_module("mp-gadget_b200")
+    ics = importlib.import_module("mp-gadget_b200.ics")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    W = max(args.warmup, 3)
+    K = args.steps
+    ng = args.ng
+    box = float(ng)
+    nmesh = ics.default_nmesh(ng)
+    # weak scaling: every rank owns one ng^3 box (seed differs per rank)
+    pos, mass = ics.zeldovich_lattice(ng, box, seed=181170 + rank)
+    n = len(mass)
+    par = ics.tree_params(box, n, treeusebh=1)
+
+    e = pkg.Engine(local)
+    stream = torch.cuda.ExternalStream(e.stream(), device=torch.device("cuda", local))
+    e.gravpm_init_periodic(box, 1.5, nmesh, G)
+
+    # ---- device-resident arm ------------------------------------------------
+    d_pos = torch.from_numpy(pos).cuda()
+    d_mass = torch.from_numpy(mass).cuda()
+    d_acc = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    d_gpm = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    d_pot = torch.empty(n, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    e.set_particles_dev(d_pos.data_ptr(), d_mass.data_ptr(), n)
+
+    def step_dev():
+        e.gravpm_force_dev(d_gpm.data_ptr(), None)
+        e.force_tree_full(box)
+        e.grav_short_tree_dev(par, d_acc.data_ptr(), d_pot.data_ptr())
+        e.oldacc_from_last_step()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    step_dev()                      # first pass uses the Barnes-Hut angle (TreeUseBH=2 semantics, gravshort-tree.c:148-151)
+    par["TreeUseBH"] = 0
+    for _ in range(W):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = e.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase = {}
+    ev0.record(stream)
+    for _ in range(K):
+        step_dev()
+        for k, v in e.timings().items():
+            phase[k] = phase.get(k, 0.0) + v
+    ev1.record(stream)
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1)
+    launches = e.kernel_launches() - l0
+    info = e.tree_info
+    for k in phase:
+        phase[k] /= K
+
+    # ---- end-to-end arm: the reference's AoS in pinned host memory --------------
+    P = np.zeros(n, dtype=pkg.PARTICLE_DTYPE)
+    P["Pos"] = pos; P["Mass"] = mass; P["Type"] = 1; P["ID"] = np.arange(n)
+    acc_h = d_acc.cpu().numpy(); gpm_h = d_gpm.cpu().numpy()
+    P["FullTreeGravAccel"] = acc_h; P["GravPM"] = gpm_h
+    pinned = torch.empty(n * 160, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = P.view(np.uint8).reshape(-1)
+    del P, d_pos, d_mass
+    for _ in range(2):
+        e.force_step_aos(None, par, ptr=pinned.data_ptr(), n=n)
+    barrier()
+    t0 = time.perf_counter()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    Ke = max(2, min(K, 5))
+    for _ in range(Ke):
+        e.force_step_aos(None, par, ptr=pinned.data_ptr(), n=n)
+    ev3.record(stream)
+    barrier()
+    ms_e2e = ev2.elapsed_time(ev3)
+    wall_e2e = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    te2e = e.timings()
+    # check the AoS result against the device arm (same inputs up to the oldacc refresh)
+    Pout = pinned.numpy().view(pkg.PARTICLE_DTYPE)
+    chk = float(np.abs(Pout["GravPM"][:1000] - gpm_h[:1000]).max() / (np.abs(gpm_h[:1000]).max() + 1e-300))
+
+    if dist is not None:
+        tt = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    total = n * world
+    value = total * K / (ms_dev * 1e-3)
+    e2e_v = total * Ke / (ms_e2e * 1e-3)
+    hbm, how = peaks()
+    walk_ms = phase["walk"]
+    nn = int(info.numnodes)
+    # 40 B in + 32 B out per active particle + node rows read once (80 B here)
+    walk_bytes = 72.0 * n + 80.0 * nn
+    walk_gbs = walk_bytes / (walk_ms * 1e-3) / 1e9
+    N3 = float(nmesh) ** 3
+    Mc = float(nmesh) ** 2 * (nmesh // 2 + 1)
+    kern = {
+        "k_grav_walk": {"ms": walk_ms, "alg_bytes": walk_bytes},
+        "k_pm_deposit+clear": {"ms": phase["pm_deposit"], "alg_bytes": 156.0 * n + 8 * N3},
+        "cufft_d2z": {"ms": phase["pm_fft_forward"], "alg_bytes": 16 * N3},
+        "k_pm_potential_transfer": {"ms": phase["pm_transfer"], "alg_bytes": 32 * Mc},
+        "cufft_z2d": {"ms": phase["pm_fft_inverse"], "alg_bytes": 16 * N3},
+        "k_pm_gradient": {"ms": phase["pm_gradient"], "alg_bytes": 32 * N3},
+        "k_pm_readout": {"ms": phase["pm_readout"], "alg_bytes": 312.0 * n},
+        "tree_build": {"ms": phase["tree_total"], "alg_bytes": (96 + 28 + 32) * float(n) + 80.0 * nn},
+    }
+    for k in kern.values():
+        k["GBps"] = k["alg_bytes"] / (k["ms"] * 1e-3) / 1e9 if k["ms"] > 0 else None
+        k["frac"] = k["GBps"] / hbm if k["GBps"] else None
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%d^3 DM-only TreePM force step per GPU (gravpm_force + force_tree_full + grav_short_tree)" % ng,
+                   "particles_per_gpu": n, "Nmesh": nmesh, "Asmth": 1.5, "TreeRcut": 6.0, "ErrTolForceAcc": 0.002,
+                   "opening": "relative (TreeUseBH=0) after one BH pass", "ics": "Zel'dovich lattice rms 0.2 spacing",
+                   "l2": "inputs larger than L2 (particle arrays %.0f MB, mesh %.1f GB)" % (n * 28 / 1e6, N3 * 8 / 1e9),
+                   "parallelism": "single GPU" if world == 1 else "independent replicas, one box per GPU (no data-path collective yet)"},
+        "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": n * 160, "d2h_bytes_per_step": n * 160,
+                "ms_per_step": ms_e2e / Ke, "wall_ms_per_step": 1e3 * wall_e2e / Ke,
+                "h2d_ms": te2e["h2d"], "d2h_ms": te2e["d2h"], "api": "b200_force_step_aos (pinned host AoS, 160 B/particle)",
+                "check_vs_device_arm": chk},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "k_grav_walk", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
+                     "frac": walk_gbs / hbm, "traffic": None, "peak_source": how,
+                     "note": "latency/fp64-issue bound pair summation; compulsory bytes only (SURVEY 8d K8)"},
+        "phases_ms": phase,
+        "kernels": kern,
+        "tree": {"numnodes": nn, "maxdepth": int(info.maxdepth)},
+    }
+    if not args.no_cpu and world == 1:
+        try:
+            v, kind, t, nm = cpu_force_step(args.cpu_ng, steps=1, warmup=0)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": kind,
+                                   "sample": "%d^3 Zel'dovich box, Nmesh %d, one full force step (%.1f s)" % (args.cpu_ng, nm, t)}
+        except Exception as ex:      # the baseline is reported, never required
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": "failed: %r" % (ex,)}
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

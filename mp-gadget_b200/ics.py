@@ -40,7 +40,7 @@ def zeldovich_lattice(ng, box, seed=181170, rms=0.2):
     del nk
     disp = []
     for kk in (kx[:, None, None], kx[None, :, None], kz[None, None, :]):
-        disp.append(np.fft.irfftn(1j * kk * amp, s=(ng, ng, ng)).astype(np.float64))
+        disp.append(np.fft.irfftn(1j * kk * amp, s=(ng, ng, ng), axes=(0, 1, 2)).astype(np.float64))
     del amp
     var = sum((x ** 2).mean() for x in disp)
     scale = rms * spacing / np.sqrt(var)

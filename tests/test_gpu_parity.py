@@ -53,7 +53,8 @@ def test_pm_parity(engine, ics, name):
     assert abs(dens.sum() - mass.sum(dtype=np.float64)) <= 1e-9 * n      # verify_density_field petapm.c:1059-1089
     assert np.abs(p - op).max() <= 1e-10 * np.abs(op).max()
     # forces: real-space 4-point difference vs the reference's k-space filter
-    scale = max(np.abs(og).max(), 1e-300)
+    # (scale floor: on the exact lattice the true force is zero and both sides are rounding noise)
+    scale = max(np.abs(og).max(), 1e-3 * G * float(mass.max()) / (box / nmesh) ** 2)
     assert np.abs(g - og).max() <= 1e-9 * scale, (np.abs(g - og).max(), scale)
 
 
@@ -179,7 +180,8 @@ def test_force_step_aos(engine, b200, ics):
     g, _ = engine.gravpm_force()
     engine.force_tree_full(box)
     acc, pot, _ = engine.grav_short_tree(par)
-    assert np.array_equal(P["GravPM"], g)
+    # the CIC deposit uses fp64 atomics, so the mesh (hence GravPM) is reproducible only to rounding
+    assert np.abs(P["GravPM"] - g).max() <= 1e-11 * np.abs(g).max()
     assert np.array_equal(P["FullTreeGravAccel"], acc)
     assert np.array_equal(P["Potential"], pot)
     assert np.array_equal(P["Pos"], pos) and np.all(P["ID"] == np.arange(n))
