@@ -16,7 +16,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200force.so")
+LIB_PATH = os.environ.get("B200_LIB", os.path.join(_HERE, "libb200force.so"))   # B200_LIB: experiment builds only
 _lib = None
 
 ALLMASK = 63   # libgadget/forcetree.h:22
