@@ -33,7 +33,7 @@ namespace b200 {
 __global__ void __launch_bounds__(256)
 k_tree_keys(const double *__restrict__ pos, const uint8_t *__restrict__ type,
             const uint8_t *__restrict__ flags, const int *__restrict__ active, int64_t nin,
-            double c0, double len0, int mask, unsigned long long *__restrict__ keys,
+            double c0, double len0, double box, int topdepth, int mask, unsigned long long *__restrict__ keys,
             int *__restrict__ idx, int *__restrict__ nvalid)
 {
     const int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,10 +49,22 @@ k_tree_keys(const double *__restrict__ pos, const uint8_t *__restrict__ type,
             const double x = pos[3 * (int64_t) i], y = pos[3 * (int64_t) i + 1], z = pos[3 * (int64_t) i + 2];
             double cx = c0, cy = c0, cz = c0, len = len0;
             key = 0;
+            // Inside the forced top tree the reference places a particle below
+            // P[i].TopLeaf, which comes from the integer Peano-Hilbert lattice
+            // (PEANO, utils/peano.h:15-21; forcetree.c:819-823), not from position
+            // compares; the lattice is the tree's own, so this only matters within
+            // rounding of a cell boundary.
+            const double DomainFac = 1.0 / (box * 1.001) * (double) (1ull << 21);
+            const int ix = (int) ((x + box / 2000) * DomainFac);
+            const int iy = (int) ((y + box / 2000) * DomainFac);
+            const int iz = (int) ((z + box / 2000) * DomainFac);
 #pragma unroll 1
             for(int l = 0; l < KEY_LEVELS; l++) {
                 const double lenhalf = 0.25 * len;
-                const int bx = x > cx, by = y > cy, bz = z > cz;
+                int bx = x > cx, by = y > cy, bz = z > cz;
+                if(l < topdepth) {
+                    bx = (ix >> (20 - l)) & 1; by = (iy >> (20 - l)) & 1; bz = (iz >> (20 - l)) & 1;
+                }
                 key = (key << 3) | (unsigned long long) (bx | (by << 1) | (bz << 2));
                 cx = bx ? cx + lenhalf : cx - lenhalf;
                 cy = by ? cy + lenhalf : cy - lenhalf;
@@ -255,7 +267,7 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
     timer_start(E, T_TREE_KEYS);
     if(nin > 0) {
         k_tree_keys<<<(unsigned) ((nin + 255) / 256), 256, 0, E->stream>>>(E->pos.p, E->type.p, E->flags.p, d_active, nin,
-                                                                         c0, len0, mask, E->keys_alt.p, E->sidx_alt.p, d_cnt + 4);
+                                                                         c0, len0, Box, toplevel_depth, mask, E->keys_alt.p, E->sidx_alt.p, d_cnt + 4);
         CKL(E);
     }
     timer_stop(E, T_TREE_KEYS);

@@ -30,7 +30,30 @@ typedef struct {
     int32_t *scratch;
     int toplevel_depth;
     int failed;
+    double BoxSize;
 } builder;
+
+/* Octant of a particle below the cell at `level`.  Inside the forced top tree
+ * the reference does not compare positions: it drops the particle below
+ * P[i].TopLeaf (forcetree.c:819-823), which the domain code derived from the
+ * integer Peano-Hilbert lattice, PEANO() utils/peano.h:15-21.  The lattice is
+ * the tree's own (same 1.001*Box root, offset Box/2000), so the two agree
+ * except for positions within rounding of a cell boundary; to follow the
+ * reference there too, top-tree levels use the lattice bits.  Below the top
+ * leaves it is get_subnode, forcetree.c:278-284 (strict >). */
+static inline int octant_of(const builder *b, const double *x, const double c[3], int level)
+{
+    if(level < b->toplevel_depth) {
+        const double DomainFac = 1.0 / (b->BoxSize * 1.001) * (((uint64_t) 1) << 21);
+        int s = 0;
+        for(int j = 0; j < 3; j++) {
+            const int ix = (int) ((x[j] + b->BoxSize / 2000) * DomainFac);
+            s |= ((ix >> (21 - (level + 1))) & 1) << j;
+        }
+        return s;
+    }
+    return (x[0] > c[0]) + ((x[1] > c[1]) << 1) + ((x[2] > c[2]) << 2);
+}
 
 static int64_t new_node(builder *b)
 {
@@ -98,7 +121,7 @@ static int64_t build_cell(builder *b, int32_t *idx, int64_t cnt, const double c[
     int64_t count[8] = {0}, start[9];
     for(int64_t k = 0; k < cnt; k++) {
         const double *x = &b->pos[3 * (int64_t) idx[k]];
-        const int s = (x[0] > c[0]) + ((x[1] > c[1]) << 1) + ((x[2] > c[2]) << 2);
+        const int s = octant_of(b, x, c, level);
         count[s]++;
     }
     start[0] = 0;
@@ -108,7 +131,7 @@ static int64_t build_cell(builder *b, int32_t *idx, int64_t cnt, const double c[
         for(int s = 0; s < 8; s++) fill[s] = start[s];
         for(int64_t k = 0; k < cnt; k++) {
             const double *x = &b->pos[3 * (int64_t) idx[k]];
-            const int s = (x[0] > c[0]) + ((x[1] > c[1]) << 1) + ((x[2] > c[2]) << 2);
+            const int s = octant_of(b, x, c, level);
             b->scratch[fill[s]++] = idx[k];
         }
         memcpy(idx, b->scratch, cnt * sizeof(int32_t));
@@ -164,6 +187,7 @@ int oracle_tree_build(oracle_tree *t, const double *pos, const float *mass,
     memset(&b, 0, sizeof(b));
     b.pos = pos; b.mass = mass; b.type = type; b.hsml = hsml;
     b.toplevel_depth = toplevel_depth;
+    b.BoxSize = BoxSize;
     const int64_t nin = active ? nactive : n;
     int32_t *idx = (int32_t *) malloc((nin + 1) * sizeof(int32_t));
     b.scratch = (int32_t *) malloc((nin + 1) * sizeof(int32_t));

@@ -1,0 +1,83 @@
+"""ctypes front-end of oracle/_ref/libref_tree.so: the reference's OWN tree,
+treewalk and short-range gravity C compiled unmodified from /root/reference
+(oracle/Makefile.ref).  TEST INFRASTRUCTURE ONLY -- pins the oracle and serves
+as the CPU baseline.  load() returns None when the library was never built
+(e.g. on a box without /root/reference and without a prebuilt oracle/_ref)."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_ref", "libref_tree.so")
+_inst = None
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Ref:
+    def __init__(self, arena_gib=None, nthreads=0):
+        self.L = C.CDLL(SO)
+        self.L.ref_numnodes.restype = C.c_int64
+        self.L.ref_tree_export.restype = C.c_int64
+        if arena_gib is None:
+            try:
+                avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2.0 ** 30
+            except Exception:
+                avail = 16.0
+            arena_gib = max(2.0, min(24.0, 0.4 * avail))
+        self.L.ref_init(C.c_double(arena_gib), C.c_int(nthreads))
+        self.n = 0
+
+    def tree_build(self, pos, mass, box, type=None, oldacc=None, topdepth=0):
+        pos = np.ascontiguousarray(pos, np.float64)
+        mass = np.ascontiguousarray(mass, np.float32)
+        type = None if type is None else np.ascontiguousarray(type, np.uint8)
+        oldacc = None if oldacc is None else np.ascontiguousarray(oldacc, np.float64)
+        self.n = len(mass)
+        self.L.ref_tree_build(C.c_int64(self.n), _p(pos), _p(mass), _p(type), _p(oldacc), C.c_double(box), C.c_int(topdepth))
+        return int(self.L.ref_numnodes())
+
+    def grav_short_tree(self, par, G, nmesh, asmth):
+        acc = np.zeros((self.n, 3))
+        pot = np.zeros(self.n)
+        self.L.ref_grav_short_tree(C.c_double(G), C.c_int(nmesh), C.c_double(asmth), C.c_double(par["ErrTolForceAcc"]),
+                                   C.c_double(par["BHOpeningAngle"]), C.c_double(par["MaxBHOpeningAngle"]),
+                                   C.c_int(par["TreeUseBH"]), C.c_double(par["Rcut"]), C.c_double(par["GravitySoftening"]),
+                                   C.c_double(par["rho0"]), _p(acc), _p(pot))
+        return acc, pot
+
+    def tree_export(self):
+        nn = int(self.L.ref_numnodes())
+        out = dict(center=np.zeros((nn, 3)), len=np.zeros(nn), cofm=np.zeros((nn, 3)), mass=np.zeros(nn),
+                   nocc=np.zeros(nn, np.int32), part=np.zeros((nn, 8), np.int32), toplevel=np.zeros(nn, np.int32))
+        k = self.L.ref_tree_export(_p(out["center"]), _p(out["len"]), _p(out["cofm"]), _p(out["mass"]),
+                                   _p(out["nocc"]), _p(out["part"]), _p(out["toplevel"]))
+        return {a: v[:k] for a, v in out.items()}
+
+    def timings(self):
+        b, w = C.c_double(), C.c_double()
+        self.L.ref_timings(C.byref(b), C.byref(w))
+        return b.value, w.value
+
+    def tree_gravity(self, pos, mass, box, nmesh, asmth, G, par, oldacc=None, topdepth=None):
+        """force_tree_full + grav_short_tree as run.c:546-548."""
+        if topdepth is None:
+            topdepth = 2 if len(mass) >= 100000 else 0      # >= nthreads top leaves so the merge is parallel
+        self.tree_build(pos, mass, box, oldacc=oldacc, topdepth=topdepth)
+        acc, _ = self.grav_short_tree(par, G, nmesh, asmth)
+        return acc
+
+
+def available():
+    return os.path.exists(SO)
+
+
+def load(**kw):
+    global _inst
+    if not available():
+        return None
+    if _inst is None:
+        _inst = Ref(**kw)
+    return _inst

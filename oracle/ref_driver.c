@@ -1,0 +1,218 @@
+/* ref_driver.c -- drives the reference's OWN tree / treewalk / short-range
+ * gravity code (compiled unmodified from /root/reference by Makefile.ref) on
+ * caller-supplied particles, as one MPI "rank".  TEST INFRASTRUCTURE ONLY:
+ * used to pin the oracle restatement and as the CPU baseline
+ * (cpu_baseline.kind = "reference").
+ *
+ * It plays the role of the reference's test fixtures
+ * (libgadget/tests/test_gravity.c:162-220 do_force_test,
+ * tests/test_forcetree.c:410-430 trivial_domain, tests/stub.c:19-41).
+ */
+#include <mpi.h>
+#include <omp.h>
+#include <math.h>
+#include <string.h>
+#include <stdlib.h>
+#include <stdio.h>
+
+#include <libgadget/utils/endrun.h>
+#include <libgadget/utils/mymalloc.h>
+#include <libgadget/utils/system.h>
+#include <libgadget/utils/peano.h>
+#include <libgadget/partmanager.h>
+#include <libgadget/slotsmanager.h>
+#include <libgadget/domain.h>
+#include <libgadget/forcetree.h>
+#include <libgadget/treewalk.h>
+#include <libgadget/gravity.h>
+#include <libgadget/petapm.h>
+#include <libgadget/timestep.h>
+#include <libgadget/walltime.h>
+
+/* ---- stand-ins for functions that live in reference files we do not build
+ * (timestep.c needs cosmology/GSL; petaio needs bigfile) ------------------- */
+int is_timebin_active(int i, inttime_t current)          /* timestep.c:143-150 */
+{
+    if(i <= 0 || current <= 0) return 1;
+    if(current % dti_from_timebin(i) == 0) return 1;
+    return 0;
+}
+ActiveParticles init_empty_active_particles(struct part_manager_type *PartManager)   /* timestep.c */
+{
+    ActiveParticles act = {0};
+    act.ActiveParticle = NULL;
+    act.NumActiveParticle = PartManager->NumPart;
+    act.MaxActiveParticle = PartManager->NumPart;
+    act.Particles = PartManager->Base;
+    return act;
+}
+void dump_snapshot(const char *dump, const double Time, void *CP, const char *OutputDir) {}
+
+static struct ClockTable CT;
+static int initialised = 0;
+static DomainDecomp dd;
+static ForceTree Tree;
+static double t_build, t_walk;
+
+static void build_uniform_domain(DomainDecomp *d, int depth)
+{
+    /* A complete top tree of the given depth in Peano-Hilbert order: the shape
+     * domain_decompose_full produces for a uniform load (domain.c:154-256);
+     * depth 0 is trivial_domain of tests/test_forcetree.c:410-430. */
+    int ntop = 0, nleaf = 1;
+    for(int l = 0, c = 1; l <= depth; l++, c *= 8) { ntop += c; if(l == depth) nleaf = c; }
+    d->domain_allocated_flag = 1;
+    d->NTopNodes = ntop;
+    d->NTopLeaves = nleaf;
+    d->TopNodes = (struct topnode_data *) mymalloc("TopNodes", sizeof(struct topnode_data) * ntop);
+    d->TopLeaves = (struct topleaf_data *) mymalloc("TopLeaves", sizeof(struct topleaf_data) * nleaf);
+    d->Tasks = (struct task_data *) mymalloc("Tasks", sizeof(struct task_data));
+    d->Tasks[0].StartLeaf = 0;
+    d->Tasks[0].EndLeaf = nleaf;
+    d->DomainComm = MPI_COMM_WORLD;
+    /* breadth-first numbering: node t at level l has daughters at first(l+1) + 8*(t - first(l)) */
+    int first = 0, count = 1, nextleaf = 0;
+    d->TopNodes[0].StartKey = 0;
+    d->TopNodes[0].Shift = 3 * BITS_PER_DIMENSION;
+    for(int l = 0; l <= depth; l++) {
+        const int firstnext = first + count;
+        for(int t = first; t < first + count; t++) {
+            if(l == depth) {
+                d->TopNodes[t].Daughter = -1;
+                d->TopNodes[t].Leaf = -1;      /* assigned below in key order */
+            } else {
+                const int dau = firstnext + 8 * (t - first);
+                d->TopNodes[t].Daughter = dau;
+                d->TopNodes[t].Leaf = -1;
+                for(int j = 0; j < 8; j++) {
+                    d->TopNodes[dau + j].Shift = d->TopNodes[t].Shift - 3;
+                    d->TopNodes[dau + j].StartKey = d->TopNodes[t].StartKey + ((peano_t) j << d->TopNodes[dau + j].Shift);
+                }
+            }
+        }
+        first = firstnext; count *= 8;
+    }
+    /* leaves numbered along the curve: BFS order inside the last level is key order */
+    {
+        int lfirst = ntop - nleaf;
+        for(int t = lfirst; t < ntop; t++) {
+            d->TopNodes[t].Leaf = nextleaf;
+            d->TopLeaves[nextleaf].Task = 0;
+            d->TopLeaves[nextleaf].topnode = t;
+            d->TopLeaves[nextleaf].treenode = -1;
+            nextleaf++;
+        }
+    }
+}
+
+int ref_init(double arena_gib, int nthreads)
+{
+    if(initialised) return 0;
+    if(nthreads > 0) omp_set_num_threads(nthreads);
+    init_endrun(0);
+    tamalloc_init();
+    mymalloc_init(arena_gib * 1024.);       /* MiB */
+    walltime_init(&CT);
+    init_forcetree_params(0.7);            /* TreeAllocFactor default, gadget/params.c */
+    initialised = 1;
+    return 0;
+}
+
+static int have_particles = 0;
+static void free_all(void)
+{
+    if(force_tree_allocated(&Tree)) force_tree_free(&Tree);
+    if(dd.domain_allocated_flag) {
+        myfree(dd.Tasks); myfree(dd.TopLeaves); myfree(dd.TopNodes);
+        memset(&dd, 0, sizeof(dd));
+    }
+    if(have_particles) { myfree(P); have_particles = 0; }
+}
+
+/* Load particles (DM type 1 unless type given), build the domain and the full tree.
+ * oldacc[n][3] is stored in FullTreeGravAccel (GravPM = 0) for the relative criterion. */
+int ref_tree_build(int64_t n, const double *pos, const float *mass, const unsigned char *type,
+                   const double *oldacc, double BoxSize, int topdepth)
+{
+    free_all();
+    particle_alloc_memory(PartManager, BoxSize, n);
+    have_particles = 1;
+    PartManager->NumPart = n;
+    build_uniform_domain(&dd, topdepth);
+    #pragma omp parallel for
+    for(int64_t i = 0; i < n; i++) {
+        memset(&P[i], 0, sizeof(P[i]));
+        for(int k = 0; k < 3; k++) {
+            P[i].Pos[k] = pos[3 * i + k];
+            P[i].FullTreeGravAccel[k] = oldacc ? oldacc[3 * i + k] : 0;
+        }
+        P[i].Mass = mass[i];
+        P[i].Type = type ? type[i] : 1;
+        P[i].ID = i;
+        P[i].TopLeaf = domain_get_topleaf(PEANO(P[i].Pos, BoxSize), &dd);
+    }
+    const double t0 = omp_get_wtime();
+    force_tree_full(&Tree, &dd, 0, NULL);
+    t_build = omp_get_wtime() - t0;
+    return 0;
+}
+
+int ref_grav_short_tree(double G, int Nmesh, double Asmth, double ErrTolForceAcc, double BHOpeningAngle,
+                        double MaxBHOpeningAngle, int TreeUseBH, double Rcut, double GravitySoftening, double rho0,
+                        double *acc_out, double *pot_out)
+{
+    PetaPM pm;
+    memset(&pm, 0, sizeof(pm));
+    pm.BoxSize = PartManager->BoxSize; pm.Asmth = Asmth; pm.Nmesh = Nmesh; pm.G = G;
+    pm.CellSize = pm.BoxSize / Nmesh;
+    gravshort_fill_ntab(SHORTRANGE_FORCE_WINDOW_TYPE_EXACT, Asmth);
+    struct gravshort_tree_params tp = {0};
+    tp.ErrTolForceAcc = ErrTolForceAcc; tp.BHOpeningAngle = BHOpeningAngle; tp.MaxBHOpeningAngle = MaxBHOpeningAngle;
+    tp.TreeUseBH = TreeUseBH; tp.Rcut = Rcut; tp.FractionalGravitySoftening = GravitySoftening;
+    set_gravshort_treepar(tp);
+    gravshort_set_softenings(1.0);
+    ActiveParticles act = init_empty_active_particles(PartManager);
+    const double t0 = omp_get_wtime();
+    grav_short_tree(&act, &pm, &Tree, NULL, rho0, 0);
+    t_walk = omp_get_wtime() - t0;
+    const int64_t n = PartManager->NumPart;
+    #pragma omp parallel for
+    for(int64_t i = 0; i < n; i++) {
+        if(acc_out) for(int k = 0; k < 3; k++) acc_out[3 * i + k] = P[i].FullTreeGravAccel[k];
+        if(pot_out) pot_out[i] = P[i].Potential;
+    }
+    return 0;
+}
+
+void ref_timings(double *build_s, double *walk_s) { *build_s = t_build; *walk_s = t_walk; }
+int64_t ref_numnodes(void) { return Tree.numnodes; }
+
+/* Export the tree in walk order (sibling / suns[0]) for comparison with the oracle.
+ * Returns the number of nodes visited (all arrays sized ref_numnodes()). */
+int64_t ref_tree_export(double *center, double *len, double *cofm, double *mass, int *nocc, int *part, int *toplevel)
+{
+    int64_t k = 0;
+    int no = Tree.firstnode;
+    while(no >= 0) {
+        struct NODE *nop = &Tree.Nodes[no];
+        for(int j = 0; j < 3; j++) { center[3 * k + j] = nop->center[j]; cofm[3 * k + j] = nop->mom.cofm[j]; }
+        len[k] = nop->len; mass[k] = nop->mom.mass;
+        toplevel[k] = nop->f.TopLevel;
+        for(int j = 0; j < 8; j++) part[8 * k + j] = -1;
+        if(nop->f.ChildType == PARTICLE_NODE_TYPE) {
+            nocc[k] = nop->s.noccupied;
+            for(int j = 0; j < nop->s.noccupied; j++) part[8 * k + j] = nop->s.suns[j];
+            no = nop->sibling;
+        } else if(nop->f.ChildType == NODE_NODE_TYPE) {
+            nocc[k] = -1;
+            no = nop->s.suns[0];
+        } else {
+            nocc[k] = -2;
+            no = nop->sibling;
+        }
+        k++;
+    }
+    return k;
+}
+
+void ref_shutdown(void) { free_all(); }
