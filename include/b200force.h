@@ -71,7 +71,7 @@ int64_t b200_kernel_launches(const b200_ctx *ctx);
  * struct-of-arrays copy in HBM until the next call. */
 
 /* From the caller's AoS records (host memory). */
-int b200_set_particles_aos(b200_ctx *ctx, const void *P, int64_t n,
+int b200_set_particles_aos(b200_ctx *ctx, const void *particles, int64_t n,
                            const b200_particle_layout *layout);
 /* From separate arrays (host memory): pos[n][3] f64, mass[n] f32,
  * type[n] u8 (NULL = all type 1), oldacc[n][3] f64 = FullTreeGravAccel+GravPM
@@ -184,7 +184,7 @@ int b200_grav_short_tree_dev(b200_ctx *ctx, const b200_gravshort_params *par,
  * = gravpm_force + force_tree_full + grav_short_tree as run.c:519-548 does on a
  * PM step with SplitGravityTimestepsOn=0: reads P[], writes P[i].GravPM,
  * P[i].FullTreeGravAccel and P[i].Potential in place. */
-int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n,
+int b200_force_step_aos(b200_ctx *ctx, void *particles, int64_t n,
                         const b200_particle_layout *layout,
                         const b200_gravshort_params *par);
 

@@ -9,6 +9,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "libref_tree.so")
+# same driver + reference files, but gravshort-tree.c replaced by the B200 shim
+# (mp-gadget_b200/host/libgadget_shims.c): grav_short_tree() runs on the GPU.
+SO_DROPIN = os.path.join(_HERE, "_ref", "libref_dropin.so")
 _inst = None
 
 
@@ -17,8 +20,8 @@ def _p(a):
 
 
 class Ref:
-    def __init__(self, arena_gib=None, nthreads=0):
-        self.L = C.CDLL(SO)
+    def __init__(self, arena_gib=None, nthreads=0, so=SO):
+        self.L = C.CDLL(so)
         self.L.ref_numnodes.restype = C.c_int64
         self.L.ref_tree_export.restype = C.c_int64
         if arena_gib is None:
