@@ -96,6 +96,7 @@ struct Engine {
     DevBuf<double> nodeB;       // [nn] double4 center.xyz, len
     DevBuf<int> nodeC;          // [nn] NodeAux
     DevBuf<int> nodeF;          // [nn] father (DFS)
+    DevBuf<int> nodeK;          // [nn][8] DFS positions of the children (-1 = none)
     DevBuf<double> nodeH;       // [nn] hmax
     DevBuf<int> scratch_i;      // small device scalars
 

@@ -230,10 +230,10 @@ k_tree_dfs(int first, int last, const int *__restrict__ b_firstchild, const int 
 __global__ void __launch_bounds__(256)
 k_tree_scatter(int nn, const int *__restrict__ b_dfs, const int *__restrict__ b_size,
                const int *__restrict__ b_start, const int *__restrict__ b_count,
-               const int *__restrict__ b_nchild, const int *__restrict__ b_father,
+               const int *__restrict__ b_nchild, const int *__restrict__ b_firstchild, const int *__restrict__ b_father,
                const double4 *__restrict__ b_center, const double4 *__restrict__ b_mom,
                double4 *__restrict__ nodeA, double4 *__restrict__ nodeB, int4 *__restrict__ nodeC,
-               int *__restrict__ nodeF, double *__restrict__ nodeH)
+               int *__restrict__ nodeF, double *__restrict__ nodeH, int4 *__restrict__ nodeK)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if(b >= nn) return;
@@ -245,6 +245,14 @@ k_tree_scatter(int nn, const int *__restrict__ b_dfs, const int *__restrict__ b_
     const int f = b_father[b];
     nodeF[d] = f >= 0 ? b_dfs[f] : -1;
     nodeH[d] = 0.0;
+    // depth-first positions of the (up to 8) children, so a batched walk can
+    // push them without chasing sibling pointers
+    int kid[8];
+    const int nch = b_nchild[b], fc = b_firstchild[b];
+#pragma unroll
+    for(int k = 0; k < 8; k++) kid[k] = k < nch ? b_dfs[fc + k] : -1;
+    nodeK[2 * (size_t) d] = make_int4(kid[0], kid[1], kid[2], kid[3]);
+    nodeK[2 * (size_t) d + 1] = make_int4(kid[4], kid[5], kid[6], kid[7]);
 }
 
 int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t nactive,
@@ -333,6 +341,7 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
     // b_mom lives in nodeH's neighbour buffer: reuse keys_alt (np*8 bytes is too small) -> own buffer
     CK(E->nodeA.ensure(4 * (size_t) nn)); CK(E->nodeB.ensure(4 * (size_t) nn));
     CK(E->nodeC.ensure(4 * (size_t) nn)); CK(E->nodeF.ensure(nn)); CK(E->nodeH.ensure(nn));
+    CK(E->nodeK.ensure(8 * (size_t) nn));
     CK(E->b_scan.ensure(8 * (size_t) nn));       // used as double4 b_mom storage (32 B per node)
     double4 *b_mom = (double4 *) E->b_scan.p;
     for(int level = nlevels - 1; level >= 0; level--) {
@@ -349,9 +358,9 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
         CKL(E);
     }
     k_tree_scatter<<<(nn + 255) / 256, 256, 0, E->stream>>>(nn, E->b_dfs.p, E->b_size.p, E->b_start.p, E->b_count.p, E->b_nchild.p,
-                                                        E->b_father.p, (const double4 *) E->b_center.p, b_mom,
+                                                        E->b_firstchild.p, E->b_father.p, (const double4 *) E->b_center.p, b_mom,
                                                         (double4 *) E->nodeA.p, (double4 *) E->nodeB.p, (int4 *) E->nodeC.p,
-                                                        E->nodeF.p, E->nodeH.p);
+                                                        E->nodeF.p, E->nodeH.p, (int4 *) E->nodeK.p);
     CKL(E);
     timer_stop(E, T_TREE_MOMENTS);
 

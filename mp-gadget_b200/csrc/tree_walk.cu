@@ -86,10 +86,10 @@ __device__ __forceinline__ void monopole(double dx, double dy, double dz, double
     pot += facpot;
 }
 
-#define LIST_CAP 192          // opened leaves buffered per warp before a flush
+#define LIST_CAP 128          // opened leaves buffered per warp before a flush
 #define WALK_WARPS 4
 #ifndef WALK_MINB
-#define WALK_MINB 5
+#define WALK_MINB 4
 #endif
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -150,26 +150,71 @@ __device__ __forceinline__ int classify(const double4 &A, const double4 &B, doub
     return 1;
 }
 
+// Newtonian-regime pair with the window applied, branch-free (the caller
+// guarantees r2 >= h^2 or discards the result): two of these interleave in
+// straight-line code.
+__device__ __forceinline__ void pair_fast(double dx, double dy, double dz, double r2, double m,
+                                          const WalkPar &P, const double4 *__restrict__ tab,
+                                          double &ax, double &ay, double &az, double &pot)
+{
+    const double rinv = rsqrt(r2);
+    const double r = r2 * rinv;
+    const double mr = m * rinv;
+    const double ti = r * P.inv_cell_dx;
+    int t = (int) ti;
+    const bool beyond = t >= B200_SR_NTAB - 1;          // gravity.c:60-61: contribution dropped
+    t = beyond ? B200_SR_NTAB - 2 : t;
+    const double w1 = ti - (double) t;
+    const double4 e = tab[t];
+    double wf = fma(w1, e.y, e.x), wp = fma(w1, e.w, e.z);
+    wf = beyond ? 0.0 : wf; wp = beyond ? 0.0 : wp;
+    const double fac = mr * rinv * rinv * wf;
+    ax = fma(dx, fac, ax); ay = fma(dy, fac, ay); az = fma(dz, fac, az);
+    pot = fma(-mr, wp, pot);
+}
+
+template <bool WRAP>
+__device__ __forceinline__ void load_pair(const int2 *__restrict__ s_tl, int idx, int nt, int slot,
+                                          const double4 *__restrict__ spart, const WalkPar &P,
+                                          double tx, double ty, double tz,
+                                          double &qx, double &qy, double &qz, double &q2, double &qm)
+{
+    int2 lf = make_int2(0, 0);
+    if(idx < nt) lf = s_tl[idx];
+    const bool v = slot < lf.y;
+    double4 q = make_double4(0, 0, 0, 0);
+    if(v) q = spart[lf.x + slot];
+    qx = q.x - tx; qy = q.y - ty; qz = q.z - tz;
+    if(WRAP) {
+        qx = nearest(qx, P.box, P.halfbox); qy = nearest(qy, P.box, P.halfbox); qz = nearest(qz, P.box, P.halfbox);
+    }
+    qm = v ? q.w : 0.0;
+    qx = v ? qx : 1.0;            // a harmless massless dummy at unit distance
+    qy = v ? qy : 0.0; qz = v ? qz : 0.0;
+    q2 = fma(qz, qz, fma(qy, qy, qx * qx));
+}
+
+// s_tl holds the (pstart, count<=8) leaf pieces target t opened.  Each step the
+// four 8-lane groups take two leaves each (8 leaves per step), one particle per
+// lane per leaf, in branch-free interleaved code; pairs inside the softening
+// radius (the target itself among them) are rare and take the general path.
 template <bool WRAP>
 __device__ __forceinline__ void pair_sum(const int2 *__restrict__ s_tl, int nt, int g, int slot,
                                          const double4 *__restrict__ spart, const WalkPar &P,
                                          const double4 *__restrict__ tab, double tx, double ty, double tz,
                                          double &sx, double &sy, double &sz, double &sp)
 {
-#pragma unroll 2
-    for(int i = g; i < nt; i += 4) {
-        const int2 lf = s_tl[i];
-        for(int k = slot; k < lf.y; k += 8) {
-            const double4 q = spart[lf.x + k];
-            double qx = q.x - tx, qy = q.y - ty, qz = q.z - tz;
-            if(WRAP) {
-                qx = nearest(qx, P.box, P.halfbox);
-                qy = nearest(qy, P.box, P.halfbox);
-                qz = nearest(qz, P.box, P.halfbox);
-            }
-            const double q2 = fma(qz, qz, fma(qy, qy, qx * qx));
-            monopole(qx, qy, qz, q2, q.w, P, tab, sx, sy, sz, sp);
+    for(int i = 0; i < nt; i += 8) {
+        double ax_, ay_, az_, a2, am, bx_, by_, bz_, b2, bm;
+        load_pair<WRAP>(s_tl, i + g, nt, slot, spart, P, tx, ty, tz, ax_, ay_, az_, a2, am);
+        load_pair<WRAP>(s_tl, i + 4 + g, nt, slot, spart, P, tx, ty, tz, bx_, by_, bz_, b2, bm);
+        const bool softa = a2 < P.h2, softb = b2 < P.h2;
+        if(__any_sync(0xffffffffu, softa || softb)) {
+            if(softa) { monopole(ax_, ay_, az_, a2, am, P, tab, sx, sy, sz, sp); am = 0.0; a2 = 1.0; }
+            if(softb) { monopole(bx_, by_, bz_, b2, bm, P, tab, sx, sy, sz, sp); bm = 0.0; b2 = 1.0; }
         }
+        pair_fast(ax_, ay_, az_, a2, am, P, tab, sx, sy, sz, sp);
+        pair_fast(bx_, by_, bz_, b2, bm, P, tab, sx, sy, sz, sp);
     }
 }
 
@@ -214,10 +259,21 @@ __device__ __forceinline__ void eval_leaf_list(const int2 *__restrict__ s_leaf, 
     }
 }
 
+// Staged node rows of the current batch (one entry per lane).
+struct BatchEntry {
+    double4 A[32];    // cofm, mass
+    double4 B[32];    // center, len
+    int4 M[32];       // pstart, count, mask of lanes (targets) that opened every ancestor,
+                      // flags (bit0: leaf, bit1: rejected for all lanes by the bounding-box test)
+};
+
+#define WALK_STACK 384        // (node, mask) entries per warp
+#define WALK_RESERVE 154      // head-room so that single pops (<= 7 net pushes each, depth <= 21+) never overflow
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128, WALK_MINB)
 k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB,
-            const int4 *__restrict__ nodeC, const double4 *__restrict__ spart,
+            const int4 *__restrict__ nodeC, const int4 *__restrict__ nodeK, const double4 *__restrict__ spart,
             const int *__restrict__ targets,     // original indices of the walk targets
             const double *__restrict__ pos, const float *__restrict__ mass,
             const double *__restrict__ oldacc, const float *__restrict__ gtab,
@@ -228,17 +284,22 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
     __shared__ int2 s_leaf_all[WALK_WARPS][LIST_CAP];
     __shared__ int2 s_tl_all[WALK_WARPS][LIST_CAP];
     __shared__ unsigned s_mask_all[WALK_WARPS][LIST_CAP];
-    __shared__ double s_bb_all[WALK_WARPS][6];
+    __shared__ int s_stk_node_all[WALK_WARPS][WALK_STACK];
+    __shared__ unsigned s_stk_mask_all[WALK_WARPS][WALK_STACK];
+    __shared__ BatchEntry s_ent_all[WALK_WARPS];
     for(int k = threadIdx.x; k < B200_SR_NTAB; k += blockDim.x) {
         const int k1 = k + 1 < B200_SR_NTAB ? k + 1 : k;
         const double f0 = gtab[k], f1 = gtab[k1], p0 = gtab[B200_SR_NTAB + k], p1 = gtab[B200_SR_NTAB + k1];
         tab[k] = make_double4(f0, f1 - f0, p0, p1 - p0);
     }
     __syncthreads();
-    int2 *s_leaf = s_leaf_all[threadIdx.x >> 5];
-    int2 *s_tl = s_tl_all[threadIdx.x >> 5];
-    unsigned *s_mask = s_mask_all[threadIdx.x >> 5];
-    double *s_bb = s_bb_all[threadIdx.x >> 5];
+    const int wib = threadIdx.x >> 5;
+    int2 *s_leaf = s_leaf_all[wib];
+    int2 *s_tl = s_tl_all[wib];
+    unsigned *s_mask = s_mask_all[wib];
+    int *s_stk_node = s_stk_node_all[wib];
+    unsigned *s_stk_mask = s_stk_mask_all[wib];
+    BatchEntry &s_ent = s_ent_all[wib];
     int nlist = 0;
     unsigned anymask = 0;
 
@@ -256,85 +317,127 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
         // grav_get_abs_accel gravshort.h:69-86 (sqrt(..)/G), then * ErrTolForceAcc (gravshort-tree.c:264)
         aold = __dmul_rn(P.ErrTol, __ddiv_rn(oldacc[me], P.G));
     }
-    // bounding box (centre, half extent) of the warp's targets for the
-    // warp-uniform early discard; kept in shared memory, it is warp-uniform.
-    bool warp_central;
-    {
-        const double big = 1e300;
-        const double lox = warp_min(valid ? px : big), hix = warp_max(valid ? px : -big);
-        const double loy = warp_min(valid ? py : big), hiy = warp_max(valid ? py : -big);
-        const double loz = warp_min(valid ? pz : big), hiz = warp_max(valid ? pz : -big);
-        if(lane == 0) {
-            s_bb[0] = 0.5 * (lox + hix); s_bb[1] = 0.5 * (loy + hiy); s_bb[2] = 0.5 * (loz + hiz);
-            s_bb[3] = 0.5 * (hix - lox); s_bb[4] = 0.5 * (hiy - loy); s_bb[5] = 0.5 * (hiz - loz);
-        }
-        warp_central = lox >= P.wrap_lo && hix <= P.wrap_hi && loy >= P.wrap_lo && hiy <= P.wrap_hi &&
-                       loz >= P.wrap_lo && hiz <= P.wrap_hi;
-        __syncwarp();
-    }
+    // bounding box (centre, half extent) of the warp's targets
+    const double big = 1e300;
+    const double lox = warp_min(valid ? px : big), hix = warp_max(valid ? px : -big);
+    const double loy = warp_min(valid ? py : big), hiy = warp_max(valid ? py : -big);
+    const double loz = warp_min(valid ? pz : big), hiz = warp_max(valid ? pz : -big);
+    const double bcx = 0.5 * (lox + hix), bcy = 0.5 * (loy + hiy), bcz = 0.5 * (loz + hiz);
+    const double bhx = 0.5 * (hix - lox), bhy = 0.5 * (hiy - loy), bhz = 0.5 * (hiz - loz);
+    const bool warp_central = lox >= P.wrap_lo && hix <= P.wrap_hi && loy >= P.wrap_lo && hiy <= P.wrap_hi &&
+                              loz >= P.wrap_lo && hiz <= P.wrap_hi;
+    const unsigned validmask = __ballot_sync(0xffffffffu, valid);
 
     double ax = 0, ay = 0, az = 0, pot = 0;
     int n_acc = 0, n_open = 0, n_disc = 0, n_part = 0;
 
-    const int NONE = -2;
-    int resume = NONE;        // node at which this lane wakes up again
-    int cur = 0;
+    // The walk visits the same (target, node) pairs as the reference's depth-first
+    // walk: a target reaches a node iff it opened every ancestor (the mask).  Nodes
+    // are taken from a per-warp stack 32 at a time so that their rows are fetched
+    // in parallel (one node per lane) instead of one dependent load per step.
+    int sp = 1;
+    if(lane == 0) { s_stk_node[0] = 0; s_stk_mask[0] = validmask; }
+    __syncwarp();
     while(true) {
-        if(cur < 0 || nlist == LIST_CAP) {      // single flush site (warp-uniform)
-            __syncwarp();
+        if(sp == 0 || nlist > LIST_CAP - 32) {      // single flush site (warp-uniform)
             if(nlist > 0) eval_leaf_list(s_leaf, s_mask, s_tl, nlist, anymask, spart, P, tab, lane, px, py, pz, ax, ay, az, pot);
             __syncwarp();
             nlist = 0; anymask = 0;
-            if(cur < 0) break;
+            if(sp == 0) break;
         }
-        if(resume == cur) resume = NONE;
-        const bool awake = valid && (resume == NONE);
-        const double4 B = nodeB[cur];      // center, len
-        const int4 C = nodeC[cur];         // sibling, pstart, count, leaf
-        // Warp-uniform early discard: if along some axis the node centre is farther
-        // than rcut + len/2 (plus a rounding margin) from the whole bounding box of
-        // the targets, every lane's own test (gravshort-tree.c:198-215) discards it:
-        // the centre of mass lies inside the cell, so r2 > rcut^2 follows.
+        int nb = sp < 32 ? sp : 32;
         {
-            const double eff = P.rcut + 0.5 * B.w;
-            const double lim = eff + 1e-9 * (eff + B.w);
-            double ex = B.x - s_bb[0], ey = B.y - s_bb[1], ez = B.z - s_bb[2];
+            const int room = (WALK_STACK - WALK_RESERVE - sp) / 7;
+            if(nb > room) nb = room > 1 ? room : 1;
+        }
+        sp -= nb;
+        // ---- lane-parallel: lane l fetches entry sp + l, tests it against the warp's bounding box
+        int mynode = -1, mynch = 0;
+        if(lane < nb) {
+            mynode = s_stk_node[sp + lane];
+            const unsigned emask0 = s_stk_mask[sp + lane];
+            const double4 eB = nodeB[mynode];
+            const int4 C = nodeC[mynode];
+            int eflags0 = C.w ? 1 : 0;
+            // Early discard for all lanes (gravshort-tree.c:198-215): along some axis the
+            // node centre is farther than rcut + len/2 (+ rounding margin) from the whole
+            // bounding box; the centre of mass lies inside the cell, so r2 > rcut^2 follows.
+            const double eff = P.rcut + 0.5 * eB.w;
+            const double lim = eff + 1e-9 * (eff + eB.w);
+            double ex = eB.x - bcx, ey = eB.y - bcy, ez = eB.z - bcz;
             if(!warp_central) {
                 ex = nearest(ex, P.box, P.halfbox); ey = nearest(ey, P.box, P.halfbox); ez = nearest(ez, P.box, P.halfbox);
             }
-            if(fabs(ex) - s_bb[3] > lim || fabs(ey) - s_bb[4] > lim || fabs(ez) - s_bb[5] > lim) {
-                if(COUNT && awake) n_disc++;
-                cur = C.x;
-                continue;
+            if(fabs(ex) - bhx > lim || fabs(ey) - bhy > lim || fabs(ez) - bhz > lim) eflags0 |= 2;
+            else s_ent.A[lane] = nodeA[mynode];
+            s_ent.B[lane] = eB;
+            s_ent.M[lane] = make_int4(C.y, C.z, (int) emask0, eflags0);
+        }
+        __syncwarp();
+        // ---- per-target exact decisions, one staged node at a time
+        unsigned myopeners = 0;       // lane l keeps the openers of entry l
+        for(int k = 0; k < nb; k++) {
+            const int4 M = s_ent.M[k];
+            const unsigned emask = (unsigned) M.z;
+            const int eflags = M.w;
+            const bool awake = (emask >> lane) & 1u;
+            if(eflags & 2) { if(COUNT && awake) n_disc++; continue; }
+            const double4 A = s_ent.A[k];
+            const double4 B = s_ent.B[k];
+            int decision = 0;
+            double dx = 0, dy = 0, dz = 0, r2 = 0;
+            if(awake) {
+                if(warp_central) decision = classify<false>(A, B, px, py, pz, aold, P, dx, dy, dz, r2);
+                else decision = classify<true>(A, B, px, py, pz, aold, P, dx, dy, dz, r2);
+            }
+            const bool wantopen = awake && decision == 2;
+            const unsigned openmask = __ballot_sync(0xffffffffu, wantopen);
+            if(awake && decision == 1) {
+                monopole(dx, dy, dz, r2, A.w, P, tab, ax, ay, az, pot);
+                if(COUNT) n_acc++;
+            }
+            if(COUNT && awake && decision == 0) n_disc++;
+            if(openmask == 0) continue;
+            if(eflags & 1) {
+                // particle leaf: remember it with the lanes that opened it (gravshort-tree.c:344-352)
+                const int2 li = make_int2(M.x, M.y);
+                if(COUNT && wantopen) n_part += li.y;
+                anymask |= openmask;
+                // pieces of <= 8 particles (only leaves at the key-depth limit hold more)
+                for(int o = 0; o < li.y || o == 0; o += 8) {
+                    if(nlist == LIST_CAP) {          // only reachable through such oversized leaves
+                        eval_leaf_list(s_leaf, s_mask, s_tl, nlist, anymask, spart, P, tab, lane, px, py, pz, ax, ay, az, pot);
+                        __syncwarp();
+                        nlist = 0;
+                    }
+                    const int c = li.y - o < 8 ? li.y - o : 8;
+                    if(lane == 0) { s_leaf[nlist] = make_int2(li.x + o, c); s_mask[nlist] = openmask; }
+                    __syncwarp();
+                    nlist++;
+                }
+            } else {
+                if(COUNT && wantopen) n_open++;
+                if(lane == k) myopeners = openmask;
             }
         }
-        const double4 A = nodeA[cur];      // cofm, mass
-        int decision = 0;                   // 0 discard, 1 accept, 2 open
-        double dx = 0, dy = 0, dz = 0, r2 = 0;
-        if(awake) {
-            if(warp_central) decision = classify<false>(A, B, px, py, pz, aold, P, dx, dy, dz, r2);
-            else decision = classify<true>(A, B, px, py, pz, aold, P, dx, dy, dz, r2);
+        // ---- lane-parallel: push the children of opened internal nodes
+        int4 k0 = make_int4(-1, -1, -1, -1), k1 = k0;
+        if(myopeners) {
+            k0 = nodeK[2 * (size_t) mynode]; k1 = nodeK[2 * (size_t) mynode + 1];
+            mynch = (k0.x >= 0) + (k0.y >= 0) + (k0.z >= 0) + (k0.w >= 0) + (k1.x >= 0) + (k1.y >= 0) + (k1.z >= 0) + (k1.w >= 0);
         }
-        const bool wantopen = awake && decision == 2;
-        const unsigned openmask = __ballot_sync(0xffffffffu, wantopen);
-        if(awake && decision == 1) {
-            monopole(dx, dy, dz, r2, A.w, P, tab, ax, ay, az, pot);
-            if(COUNT) n_acc++;
+        int off = mynch;        // inclusive scan over lanes
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if(lane >= o) off += v; }
+        const int total = __shfl_sync(0xffffffffu, off, 31);
+        if(mynch) {
+            int w = sp + off - mynch;
+            const int kids[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+            for(int c = 0; c < 8; c++) if(kids[c] >= 0) { s_stk_node[w] = kids[c]; s_stk_mask[w] = myopeners; w++; }
         }
-        if(COUNT && awake && decision == 0) n_disc++;
-        if(openmask == 0) { cur = C.x; continue; }
-        if(C.w) {
-            // particle leaf: remember it with the lanes that opened it (gravshort-tree.c:344-352)
-            if(lane == 0) { s_leaf[nlist] = make_int2(C.y, C.z); s_mask[nlist] = openmask; }
-            if(COUNT && wantopen) n_part += C.z;
-            nlist++;
-            anymask |= openmask;
-            cur = C.x;
-        } else {
-            if(awake && !wantopen) resume = C.x;
-            if(COUNT && wantopen) n_open++;
-            cur = cur + 1;
-        }
+        sp += total;
+        __syncwarp();
     }
     if(valid) {
         // grav_short_postprocess gravshort.h:47-67
@@ -417,11 +520,11 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
     const unsigned nb = (unsigned) ((nwarps * 32 + bs - 1) / bs);
     if(d_counts)
         k_grav_walk<true><<<nb, bs, 0, E->stream>>>((const double4 *) E->nodeA.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p,
-                                                   (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p,
+                                                   (const int4 *) E->nodeK.p, (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p,
                                                    P, E->tree_full ? 1 : 0, cbrtrho0, d_acc, d_pot, (int4 *) d_counts);
     else
         k_grav_walk<false><<<nb, bs, 0, E->stream>>>((const double4 *) E->nodeA.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p,
-                                                    (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p,
+                                                    (const int4 *) E->nodeK.p, (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p,
                                                     P, E->tree_full ? 1 : 0, cbrtrho0, d_acc, d_pot, nullptr);
     CKL(E);
     timer_stop(E, T_WALK);
