@@ -188,6 +188,39 @@ int b200_force_step_aos(b200_ctx *ctx, void *particles, int64_t n,
                         const b200_particle_layout *layout,
                         const b200_gravshort_params *par);
 
+/* ---- multi-GPU building blocks (one process + one context per GPU; the host
+ * harness moves the buffers between ranks with NCCL) --------------------------
+ *
+ * Top-tree moments: the analogue of force_exchange_pseudodata (MPI_Allgatherv of
+ * struct topleaf_momentsdata, libgadget/forcetree.c:1145-1208) and
+ * force_treeupdate_pseudos (forcetree.c:1214-1284).  cells[8^level][4] =
+ * {cofm.x, cofm.y, cofm.z, mass} of the level-`level` cells of the forced top
+ * tree in Morton order (x bit 0, y bit 1, z bit 2 of each octal digit, root digit
+ * first); device pointers.  _set overwrites them and re-sums all higher levels. */
+int b200_tree_top_get_dev(b200_ctx *ctx, int level, double *cells_out);
+int b200_tree_top_set_dev(b200_ctx *ctx, int level, const double *cells_in);
+
+/* Slab-decomposed PM: replaces the 2-D pencil layout + PFFT transposes of
+ * petapm_init / petapm_force (libgadget/petapm.c:127-187,284-357,584-885).
+ * Rank r owns mesh planes [r*Nmesh/nranks, (r+1)*Nmesh/nranks).  The three
+ * device buffers are returned so the harness can exchange halo planes and do the
+ * all-to-all transpose:
+ *   real  [(nx+2*halo)][Nmesh][Nmesh] f64, plane 0 = global plane x0-halo
+ *   cplx  [nx][Nmesh][Nmesh/2+1] complex f64 (after the 2-D transforms)
+ *   cplxT [ny][Nmesh][Nmesh/2+1] complex f64 (y-slab, full x; 1-D transforms + Green's function)
+ * Sequence per PM step: deposit -> (halo planes added into the neighbours) ->
+ * fft2d(0) -> transpose -> fft1d(0) -> transfer -> fft1d(1) -> transpose back ->
+ * fft2d(1) -> (halo planes copied from the neighbours) -> readout. */
+int b200_pmslab_init(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G,
+                     int rank, int nranks, int halo,
+                     void **real_buf, void **cplx_buf, void **cplxT_buf);
+/* CIC deposit of the first n_own particles (the rank's own, ghosts follow them). */
+int b200_pmslab_deposit(b200_ctx *ctx, int64_t n_own);
+int b200_pmslab_fft2d(b200_ctx *ctx, int inverse);
+int b200_pmslab_fft1d(b200_ctx *ctx, int inverse);
+int b200_pmslab_transfer(b200_ctx *ctx);
+int b200_pmslab_readout_dev(b200_ctx *ctx, int64_t n_own, double *gravpm_out, double *potential_out);
+
 /* Device-side timing of the phases of the last call, milliseconds (CUDA
  * events on the engine's stream).  Names follow the reference's walltime
  * categories (libgadget/walltime.c, gravshort-tree.c:134-144, petapm.c:280-355). */

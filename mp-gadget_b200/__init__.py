@@ -70,6 +70,8 @@ EXPORTED = [
     "b200_pm_force_dev", "b200_pm_cell_index", "b200_pm_copy_mesh", "b200_tree_build", "b200_tree_free",
     "b200_tree_export", "b200_grav_short_tree", "b200_grav_short_tree_dev", "b200_force_step_aos",
     "b200_get_timings", "b200_stream",
+    "b200_tree_top_get_dev", "b200_tree_top_set_dev", "b200_pmslab_init", "b200_pmslab_deposit",
+    "b200_pmslab_fft2d", "b200_pmslab_fft1d", "b200_pmslab_transfer", "b200_pmslab_readout_dev",
 ]
 
 
@@ -218,11 +220,41 @@ class Engine:
         self._ck(self.L.b200_grav_short_tree(self.ctx, C.byref(p), _p(active), C.c_int64(na), _p(acc), _p(pot), _p(cnt)))
         return acc, pot, cnt
 
-    def grav_short_tree_dev(self, par, acc_ptr=None, pot_ptr=None):
+    def grav_short_tree_dev(self, par, acc_ptr=None, pot_ptr=None, active_ptr=None, nactive=0):
         p = GravShortParams(**par) if isinstance(par, dict) else par
-        self._ck(self.L.b200_grav_short_tree_dev(self.ctx, C.byref(p), None, C.c_int64(0),
+        self._ck(self.L.b200_grav_short_tree_dev(self.ctx, C.byref(p), C.c_void_p(active_ptr) if active_ptr else None, C.c_int64(nactive),
                                                  C.c_void_p(acc_ptr) if acc_ptr else None,
                                                  C.c_void_p(pot_ptr) if pot_ptr else None, None))
+
+    # -- multi-GPU building blocks ------------------------------------------------
+    def tree_top_get_dev(self, level, ptr):
+        self._ck(self.L.b200_tree_top_get_dev(self.ctx, C.c_int(level), C.c_void_p(ptr)))
+
+    def tree_top_set_dev(self, level, ptr):
+        self._ck(self.L.b200_tree_top_set_dev(self.ctx, C.c_int(level), C.c_void_p(ptr)))
+
+    def pmslab_init(self, BoxSize, Asmth, Nmesh, G, rank, nranks, halo):
+        r, c, t = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.b200_pmslab_init(self.ctx, C.c_double(BoxSize), C.c_double(Asmth), C.c_int(Nmesh), C.c_double(G),
+                                         C.c_int(rank), C.c_int(nranks), C.c_int(halo), C.byref(r), C.byref(c), C.byref(t)))
+        self.nmesh = int(Nmesh)
+        return r.value, c.value, t.value
+
+    def pmslab_deposit(self, n_own):
+        self._ck(self.L.b200_pmslab_deposit(self.ctx, C.c_int64(n_own)))
+
+    def pmslab_fft2d(self, inverse):
+        self._ck(self.L.b200_pmslab_fft2d(self.ctx, C.c_int(inverse)))
+
+    def pmslab_fft1d(self, inverse):
+        self._ck(self.L.b200_pmslab_fft1d(self.ctx, C.c_int(inverse)))
+
+    def pmslab_transfer(self):
+        self._ck(self.L.b200_pmslab_transfer(self.ctx))
+
+    def pmslab_readout_dev(self, n_own, gravpm_ptr, pot_ptr=None):
+        self._ck(self.L.b200_pmslab_readout_dev(self.ctx, C.c_int64(n_own), C.c_void_p(gravpm_ptr),
+                                                C.c_void_p(pot_ptr) if pot_ptr else None))
 
     # -- whole step on the reference's AoS -------------------------------------
     def force_step_aos(self, P, par, ptr=None, n=None):

@@ -184,6 +184,7 @@ void b200_ctx_destroy(b200_ctx *ctx)
     cudaSetDevice(E->device);
     cudaStreamSynchronize(E->stream);
     pm_destroy(E);
+    pmslab_destroy(E);
     E->pos.release(); E->mass.release(); E->type.release(); E->flags.release(); E->oldacc.release();
     E->last_tree_acc.release(); E->last_pm_acc.release(); E->aos.release();
     E->keys.release(); E->keys_alt.release(); E->sidx.release(); E->sidx_alt.release(); E->cubtemp.release();
@@ -429,6 +430,47 @@ int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_l
     timer_start(E, T_D2H);
     CK(cudaMemcpyAsync(P, E->aos.p, m * L.stride, cudaMemcpyDeviceToHost, E->stream));
     timer_stop(E, T_D2H);
+    CK(cudaStreamSynchronize(E->stream));
+    return collect_timings(E);
+}
+
+int b200_tree_top_get_dev(b200_ctx *ctx, int level, double *cells_out)
+{
+    ENTER(ctx);
+    if(int rc = tree_top_get(E, level, cells_out)) return rc;
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
+int b200_tree_top_set_dev(b200_ctx *ctx, int level, const double *cells_in)
+{
+    ENTER(ctx);
+    if(int rc = tree_top_set(E, level, cells_in)) return rc;
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
+int b200_pmslab_init(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G, int rank, int nranks, int halo,
+                     void **real_buf, void **cplx_buf, void **cplxT_buf)
+{
+    ENTER(ctx);
+    return pmslab_init(E, BoxSize, Asmth, Nmesh, G, rank, nranks, halo, real_buf, cplx_buf, cplxT_buf);
+}
+int b200_pmslab_deposit(b200_ctx *ctx, int64_t n_own) { ENTER(ctx); return pmslab_deposit(E, n_own); }
+int b200_pmslab_fft2d(b200_ctx *ctx, int inverse) { ENTER(ctx); if(int rc = pmslab_fft2d(E, inverse)) return rc; CK(cudaStreamSynchronize(E->stream)); return 0; }
+int b200_pmslab_fft1d(b200_ctx *ctx, int inverse) { ENTER(ctx); if(int rc = pmslab_fft1d(E, inverse)) return rc; CK(cudaStreamSynchronize(E->stream)); return 0; }
+int b200_pmslab_transfer(b200_ctx *ctx) { ENTER(ctx); if(int rc = pmslab_transfer(E)) return rc; CK(cudaStreamSynchronize(E->stream)); return 0; }
+int b200_pmslab_readout_dev(b200_ctx *ctx, int64_t n_own, double *gravpm_out, double *potential_out)
+{
+    ENTER(ctx);
+    if(int rc = pmslab_readout(E, n_own, gravpm_out, potential_out)) return rc;
+    // keep the PM accelerations of the own particles for b200_oldacc_from_last_step
+    if(gravpm_out && n_own > 0) {
+        CK(E->last_pm_acc.ensure(3 * (size_t) E->n));
+        CK(cudaMemsetAsync(E->last_pm_acc.p, 0, 3 * (size_t) E->n * sizeof(double), E->stream));
+        CK(cudaMemcpyAsync(E->last_pm_acc.p, gravpm_out, 3 * (size_t) n_own * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));
+        E->have_last_pm = true;
+    }
     CK(cudaStreamSynchronize(E->stream));
     return collect_timings(E);
 }

@@ -46,6 +46,8 @@ struct NodeAux {           // int4
     int leaf;              // 1: particle leaf, 0: internal (first child = self + 1)
 };
 
+struct SlabPM;
+
 struct Engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -67,6 +69,7 @@ struct Engine {
     // ---- PM ----
     double Box = 0, Asmth = 0, G = 0;
     int Nmesh = 0;
+    int NmeshWalk = 0;         // mesh size seen by the short-range walk (set by pm_init / pmslab_init)
     cufftHandle plan_fwd = 0, plan_inv = 0;
     bool plans = false;
     DevBuf<double> mesh;       // real mesh Nmesh^3 (density, then potential)
@@ -75,6 +78,7 @@ struct Engine {
     DevBuf<double> ktab;       // per-dimension deconvolution factor 1/sinc^2, [Nmesh]
     DevBuf<uint8_t> fftwork;
     bool potential_valid = false;
+    SlabPM *slab = nullptr;
 
     // ---- tree ----
     bool tree_valid = false;
@@ -83,6 +87,7 @@ struct Engine {
     int64_t tree_nn = 0;        // nodes
     int tree_maxdepth = 0;
     int tree_overfull = 0;
+    int tree_topdepth = 0;
     bool tree_full = false;     // contains every particle (full_particle_tree_flag)
     DevBuf<unsigned long long> keys, keys_alt;
     DevBuf<int> sidx, sidx_alt;   // sorted -> original index
@@ -132,6 +137,20 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
                int toplevel_depth, b200_tree_info *info);
 int tree_export(Engine *E, double *center, double *len, double *cofm, double *mass, double *hmax,
                 int32_t *sibling, int32_t *firstchild, int32_t *nocc, int32_t *leafpart);
+
+int tree_top_get(Engine *E, int level, double *d_out);
+int tree_top_set(Engine *E, int level, const double *d_in);
+
+// slab-decomposed PM for multi-GPU (pm_slab.cu)
+struct SlabPM;
+int pmslab_init(Engine *E, double Box, double Asmth, int Nmesh, double G, int rank, int nranks, int halo,
+                void **real_buf, void **cplx_buf, void **cplxT_buf);
+void pmslab_destroy(Engine *E);
+int pmslab_deposit(Engine *E, int64_t n_own);
+int pmslab_fft2d(Engine *E, int inverse);
+int pmslab_fft1d(Engine *E, int inverse);
+int pmslab_transfer(Engine *E);
+int pmslab_readout(Engine *E, int64_t n_own, double *d_gravpm, double *d_pot);
 
 // walk (tree_walk.cu)
 int walk_init_tables(Engine *E);

@@ -255,6 +255,7 @@ int pm_init(Engine *E, double Box, double Asmth, int Nmesh, double G)
     CK(cudaMemcpyAsync(E->ktab.p, tab.data(), Nmesh * sizeof(double), cudaMemcpyHostToDevice, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     E->potential_valid = false;
+    E->NmeshWalk = Nmesh;
     return 0;
 }
 

@@ -113,7 +113,16 @@ k_tree_split(const unsigned long long *__restrict__ keys, int first, int last, i
     const bool keep_empty = (level + 1) <= topdepth;
     int nch = 0;
     for(int d = 0; d < 8; d++) nch += (keep_empty || bound[d + 1] > bound[d]) ? 1 : 0;
-    const int base = atomicAdd(&counters[0], nch);
+    // Forced top-tree levels are complete (every cell has 8 children), so their
+    // children go to fixed slots: cell (level l, Morton index m) sits at
+    // (8^l - 1)/7 + m.  b200_tree_top_get/set rely on this.
+    int base;
+    if(forced) {
+        base = last + 8 * (node - first);
+        atomicMax(&counters[0], last + 8 * (last - first));
+    } else {
+        base = atomicAdd(&counters[0], nch);
+    }
     if(base + nch > cap) { counters[1] = 1; b_firstchild[node] = -1; b_nchild[node] = 0; return; }
     b_firstchild[node] = base;
     b_nchild[node] = nch;
@@ -260,7 +269,7 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
 {
     E->tree_valid = false;
     if(!(Box > 0)) return failmsg(E, "b200_tree_build: BoxSize must be positive");
-    if(toplevel_depth < 0 || toplevel_depth > 6) return failmsg(E, "b200_tree_build: toplevel_depth out of range [0,6]");
+    if(toplevel_depth < 0 || toplevel_depth > 8) return failmsg(E, "b200_tree_build: toplevel_depth out of range [0,8]");
     const int64_t nin = d_active ? nactive : E->n;
     if(nin >= (1ll << 30)) return failmsg(E, "b200_tree_build: too many particles for 32-bit node indices");
     const double c0 = Box / 2., len0 = Box * 1.001;       // forcetree.c:662-664
@@ -297,7 +306,7 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
 
     timer_start(E, T_TREE_NODES);
     int cap = (int) (np * 0.75) + 4096;
-    { int64_t top = 1; for(int l = 0; l < toplevel_depth; l++) top *= 8; cap += (int) (top * 2); }
+    { int64_t top = 1; for(int l = 0; l < toplevel_depth; l++) top *= 8; cap += (int) (top * 2.5); }
     std::vector<int> lvl;       // level offsets in BFS numbering
     int nn = 0, overfull = 0;
     for(int attempt = 0; attempt < 8; attempt++) {
@@ -371,6 +380,7 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
     E->tree_maxdepth = nlevels - 1;
     E->tree_overfull = overfull;
     E->tree_full = (d_active == nullptr);
+    E->tree_topdepth = toplevel_depth;
     if(info) {
         double root[4];
         CK(cudaMemcpyAsync(root, E->nodeA.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
@@ -380,6 +390,71 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
         info->maxdepth = nlevels - 1;
         info->overfull_leaves = overfull;
         info->root_mass = root[3];
+    }
+    return 0;
+}
+
+// ---- top-tree moments (multi-GPU): the analogue of force_exchange_pseudodata +
+// force_treeupdate_pseudos (forcetree.c:1156-1284).  Level-`level` cells of the
+// forced top tree are read out / overwritten as {cofm.xyz, mass}, indexed by
+// Morton cell index; the levels above are then re-summed from their 8 children in
+// octant order with the reference's arithmetic.
+__global__ void __launch_bounds__(256)
+k_top_get(int off, int ncell, const int *__restrict__ b_dfs, const double4 *__restrict__ nodeA, double4 *__restrict__ out)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if(m < ncell) out[m] = nodeA[b_dfs[off + m]];
+}
+__global__ void __launch_bounds__(256)
+k_top_set(int off, int ncell, const int *__restrict__ b_dfs, double4 *__restrict__ nodeA, const double4 *__restrict__ in)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if(m < ncell) nodeA[b_dfs[off + m]] = in[m];
+}
+__global__ void __launch_bounds__(256)
+k_top_resum(int off, int offchild, int ncell, const int *__restrict__ b_dfs, double4 *__restrict__ nodeA,
+            const double4 *__restrict__ nodeB)
+{
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if(m >= ncell) return;
+    double mass = 0, sx = 0, sy = 0, sz = 0;
+    for(int k = 0; k < 8; k++) {
+        const double4 c = nodeA[b_dfs[offchild + 8 * m + k]];
+        mass = __dadd_rn(mass, c.w);
+        sx = __dadd_rn(sx, __dmul_rn(c.w, c.x));
+        sy = __dadd_rn(sy, __dmul_rn(c.w, c.y));
+        sz = __dadd_rn(sz, __dmul_rn(c.w, c.z));
+    }
+    const int d = b_dfs[off + m];
+    double4 o;
+    if(mass > 0) { o.x = __ddiv_rn(sx, mass); o.y = __ddiv_rn(sy, mass); o.z = __ddiv_rn(sz, mass); }
+    else { const double4 b = nodeB[d]; o.x = b.x; o.y = b.y; o.z = b.z; }
+    o.w = mass;
+    nodeA[d] = o;
+}
+
+static int top_offset(int level) { int64_t o = 0, c = 1; for(int l = 0; l < level; l++) { o += c; c *= 8; } return (int) o; }
+
+int tree_top_get(Engine *E, int level, double *d_out)
+{
+    if(!E->tree_valid || level > E->tree_topdepth) return failmsg(E, "b200_tree_top_get: level is not inside the forced top tree");
+    int ncell = 1; for(int l = 0; l < level; l++) ncell *= 8;
+    k_top_get<<<(ncell + 255) / 256, 256, 0, E->stream>>>(top_offset(level), ncell, E->b_dfs.p, (const double4 *) E->nodeA.p, (double4 *) d_out);
+    CKL(E);
+    return 0;
+}
+
+int tree_top_set(Engine *E, int level, const double *d_in)
+{
+    if(!E->tree_valid || level > E->tree_topdepth) return failmsg(E, "b200_tree_top_set: level is not inside the forced top tree");
+    int ncell = 1; for(int l = 0; l < level; l++) ncell *= 8;
+    k_top_set<<<(ncell + 255) / 256, 256, 0, E->stream>>>(top_offset(level), ncell, E->b_dfs.p, (double4 *) E->nodeA.p, (const double4 *) d_in);
+    CKL(E);
+    for(int l = level - 1; l >= 0; l--) {
+        ncell /= 8;
+        k_top_resum<<<(ncell + 255) / 256, 256, 0, E->stream>>>(top_offset(l), top_offset(l + 1), ncell, E->b_dfs.p,
+                                                             (double4 *) E->nodeA.p, (const double4 *) E->nodeB.p);
+        CKL(E);
     }
     return 0;
 }

@@ -480,11 +480,11 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
                     int64_t nactive, double *d_acc, double *d_pot, b200_walk_counts *d_counts)
 {
     if(!E->tree_valid) return failmsg(E, "b200_grav_short_tree: tree moments not computed (call b200_tree_build)");   // gravshort-tree.c:113-114
-    if(E->Nmesh == 0) return failmsg(E, "b200_grav_short_tree: call b200_pm_init first (needs Nmesh, Asmth, G)");
+    if(E->NmeshWalk == 0) return failmsg(E, "b200_grav_short_tree: call b200_pm_init first (needs Nmesh, Asmth, G)");
     if(!E->srtab.p) if(int rc = walk_init_tables(E)) return rc;
     WalkPar P;
     P.box = E->tree_box; P.halfbox = 0.5 * E->tree_box;
-    const double cellsize = E->tree_box / E->Nmesh;                 // gravshort-tree.c:101
+    const double cellsize = E->tree_box / E->NmeshWalk;                 // gravshort-tree.c:101
     P.rcut = par->Rcut * E->Asmth * cellsize;                       // :102
     P.rcut2 = P.rcut * P.rcut;
     P.usebh = par->TreeUseBH;

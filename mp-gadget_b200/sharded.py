@@ -1,0 +1,301 @@
+"""Domain-sharded TreePM force step: one process + one engine per GPU.
+
+Host-side orchestration of the multi-GPU path.  The
+compute is the C-ABI engine; torch.distributed (NCCL on GPUs, gloo in the CPU
+tests) is the plumbing.  What the reference does with MPI:
+
+  * domain cut -> rank owns a contiguous set of top-level tree cells
+    (domain.c:154-256, domain.h:71-78).  Here: the cells of a uniform top tree
+    of depth `topdepth` on the reference's own lattice (root 1.001*Box,
+    peano.h:15-21), split into x-layers; rank r owns layers
+    [r*2^d/W, (r+1)*2^d/W).
+  * short-range tree: the reference exports *queries* to the ranks whose
+    top-leaves must be opened (treewalk.c:325-371,399-793).  Here (SURVEY 8e
+    option 2, "ghost import"): each rank imports the particles of the cell
+    layer adjacent to its domain from both neighbours, builds the same forced
+    top tree + complete subtrees for own and imported cells, and walks its own
+    particles only.  A cell that was not imported lies more than one cell width
+    (> Rcut) away from every own particle and is discarded by
+    shall_we_discard_node (gravshort-tree.c:198-215) whatever its content.
+    Top-cell moments are summed over ranks and the upper levels re-summed
+    (force_exchange_pseudodata + force_treeupdate_pseudos,
+    forcetree.c:1156-1284), so every node a target can see carries the same
+    moments as in a single-rank run with the same top tree.
+  * PM: x-slab decomposition of the mesh (the reference uses 2-D pencils,
+    petapm.c:127-150): halo planes of the deposit are added into the
+    neighbours (replaces layout_build_and_exchange_cells_to_pfft,
+    petapm.c:792-840), 2-D FFT per plane, all-to-all transpose, 1-D FFT along
+    x, Green's function, and back; halo planes of the potential are fetched
+    from the neighbours (replaces ..._to_local, petapm.c:848-885).
+
+The same class runs with world size 1 (self-neighbours), which is how the
+single-GPU tests check it against the unsharded engine path.
+"""
+import numpy as np
+import torch
+
+
+class _DevView:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def dev_tensor(ptr, shape, device):
+    return torch.as_tensor(_DevView(ptr, shape), device=device)
+
+
+class Comm:
+    """Neighbour / all-to-all exchanges over torch.distributed (or none for world 1)."""
+
+    def __init__(self, dist=None):
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.left = (self.rank - 1) % self.world
+        self.right = (self.rank + 1) % self.world
+
+    def neighbour_exchange(self, send_left, send_right, recv_from_right, recv_from_left):
+        """send_left goes to the left neighbour (who receives it as 'from its right')."""
+        if self.world == 1:
+            recv_from_right.copy_(send_left)
+            recv_from_left.copy_(send_right)
+            return
+        d = self.dist
+        ops = [d.P2POp(d.isend, send_left, self.left), d.P2POp(d.isend, send_right, self.right),
+               d.P2POp(d.irecv, recv_from_right, self.right), d.P2POp(d.irecv, recv_from_left, self.left)]
+        for r in d.batch_isend_irecv(ops):
+            r.wait()
+
+    def neighbour_exchange_var(self, send_left, send_right):
+        """Variable-length [k, C] tensors; returns (from_right, from_left)."""
+        if self.world == 1:
+            return send_left.clone(), send_right.clone()
+        dev, dt = send_left.device, send_left.dtype
+        cl = torch.tensor([send_left.shape[0]], dtype=torch.int64, device=dev)
+        cr = torch.tensor([send_right.shape[0]], dtype=torch.int64, device=dev)
+        nr, nl = torch.zeros_like(cl), torch.zeros_like(cl)
+        self.neighbour_exchange(cl, cr, nr, nl)
+        cols = send_left.shape[1]
+        fr = torch.empty((int(nr.item()), cols), dtype=dt, device=dev)
+        fl = torch.empty((int(nl.item()), cols), dtype=dt, device=dev)
+        self.neighbour_exchange(send_left.contiguous(), send_right.contiguous(), fr, fl)
+        return fr, fl
+
+    def all_to_all_equal(self, send, recv):
+        """send/recv: [world, ...] contiguous blocks of equal size."""
+        if self.world == 1:
+            recv.copy_(send)
+            return
+        d = self.dist
+        if d.get_backend() == "nccl":
+            d.all_to_all_single(recv.view(-1), send.view(-1))
+            return
+        ops = []
+        for p in range(self.world):        # gloo has no all_to_all: pairwise sends
+            if p == self.rank:
+                recv[p].copy_(send[p])
+            else:
+                ops.append(d.P2POp(d.isend, send[p], p))
+                ops.append(d.P2POp(d.irecv, recv[p], p))
+        if ops:
+            for r in d.batch_isend_irecv(ops):
+                r.wait()
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t)
+        return t
+
+
+class Domain:
+    """x-layers of the top-tree cells on the reference's Peano lattice."""
+
+    def __init__(self, box, topdepth, rank, world):
+        self.box, self.d, self.rank, self.world = float(box), int(topdepth), rank, world
+        self.ncell = 1 << self.d
+        if self.ncell % world:
+            raise ValueError("2^topdepth must be a multiple of the number of ranks")
+        self.per = self.ncell // world
+        self.lo, self.hi = rank * self.per, (rank + 1) * self.per
+        self.cellwidth = 1.001 * self.box / self.ncell
+        self.domainfac = 1.0 / (self.box * 1.001) * float(1 << 21)       # PEANO(), utils/peano.h:15-21
+
+    def layer_of(self, x):
+        """Top-cell x-index of positions x (torch f64)."""
+        ix = ((x + self.box / 2000) * self.domainfac).to(torch.int64)
+        return ix >> (21 - self.d)
+
+    def owner_of(self, x):
+        return torch.div(self.layer_of(x), self.per, rounding_mode="floor")
+
+    def own_cell_mask(self, device):
+        """[8^d] bool: Morton-indexed top cells owned by this rank (x bit = bit 0 of each octal digit)."""
+        m = torch.arange(8 ** self.d, dtype=torch.int64, device=device)
+        ix = torch.zeros_like(m)
+        for level in range(self.d):            # digit `level` counted from the least significant
+            ix |= ((m >> (3 * level)) & 1) << level
+        return (ix >= self.lo) & (ix < self.hi)
+
+    def ghost_sets(self, x):
+        """Boolean masks of own particles to send to the left / right neighbour."""
+        lay = self.layer_of(x)
+        to_left = lay == self.lo
+        to_right = lay == self.hi - 1
+        if self.world == 2:
+            # both neighbours are the same rank: it must receive each particle once
+            both = to_left | to_right
+            return both, torch.zeros_like(both)
+        if self.world == 1:
+            z = torch.zeros_like(to_left)
+            return z, z
+        return to_left, to_right
+
+
+def slab_transpose_forward(comm, cplx, cplxT, sendbuf, recvbuf, sync=None):
+    """[ix(local)][iy][kz] -> [jy(local)][ix][kz]: the all-to-all that PFFT does
+    between its 1-D stages (petapm.c:305, PFFT_TRANSPOSED_OUT)."""
+    W = comm.world
+    nx, nz = cplx.shape[0], cplx.shape[2]
+    if W == 1:
+        cplxT.copy_(cplx.permute(1, 0, 2, 3))
+        return
+    sendbuf.copy_(cplx.view(nx, W, nx, nz, 2).permute(1, 0, 2, 3, 4))      # [dest][ix][jy][kz]
+    if sync:
+        sync()
+    comm.all_to_all_equal(sendbuf, recvbuf)                                  # [src][ix][jy][kz]
+    cplxT.view(nx, W, nx, nz, 2).copy_(recvbuf.permute(2, 0, 1, 3, 4))      # [jy][src][ix][kz]
+
+
+def slab_transpose_backward(comm, cplx, cplxT, sendbuf, recvbuf, sync=None):
+    W = comm.world
+    nx, nz = cplx.shape[0], cplx.shape[2]
+    if W == 1:
+        cplx.copy_(cplxT.permute(1, 0, 2, 3))
+        return
+    sendbuf.copy_(cplxT.view(nx, W, nx, nz, 2).permute(1, 2, 0, 3, 4))     # [dest][ix][jy][kz]
+    if sync:
+        sync()
+    comm.all_to_all_equal(sendbuf, recvbuf)                                  # [src][ix][jy(src)][kz]
+    cplx.view(nx, W, nx, nz, 2).copy_(recvbuf.permute(1, 0, 2, 3, 4))       # [ix][src][jy][kz]
+
+
+def halo_add(comm, real, nx, h, buf_a, buf_b):
+    """Add the deposit that landed in my halo planes into the neighbours' edge planes."""
+    comm.neighbour_exchange(real[0:h].contiguous(), real[h + nx:].contiguous(), buf_a, buf_b)
+    real[nx:nx + h] += buf_a        # from my right neighbour: its left halo = my last owned planes
+    real[h:2 * h] += buf_b          # from my left neighbour: its right halo = my first owned planes
+
+
+def halo_fill(comm, real, nx, h, buf_a, buf_b):
+    """Fetch the neighbours' edge planes of the potential into my halo planes."""
+    comm.neighbour_exchange(real[h:2 * h].contiguous(), real[nx:nx + h].contiguous(), buf_a, buf_b)
+    real[h + nx:] = buf_a           # my right halo = right neighbour's first owned planes
+    real[0:h] = buf_b               # my left halo = left neighbour's last owned planes
+
+
+class ShardedTreePM:
+    def __init__(self, engine, box, nmesh, asmth, G, topdepth, dist=None, halo=6, device="cuda"):
+        self.e = engine
+        self.comm = Comm(dist)
+        self.rank, self.world = self.comm.rank, self.comm.world
+        self.box, self.nmesh, self.asmth, self.G = float(box), int(nmesh), float(asmth), float(G)
+        self.dom = Domain(box, topdepth, self.rank, self.world)
+        self.device = torch.device(device)
+        self.halo = halo
+        if nmesh % (2 * self.world):
+            raise ValueError("Nmesh must be a multiple of 2*world")
+        self.nx = nmesh // self.world
+        self.nz = nmesh // 2 + 1
+        r, c, t = engine.pmslab_init(box, asmth, nmesh, G, self.rank, self.world, halo)
+        N, nx, nz, h = nmesh, self.nx, self.nz, halo
+        self.real = dev_tensor(r, (nx + 2 * h, N, N), self.device)
+        self.cplx = dev_tensor(c, (nx, N, nz, 2), self.device)
+        self.cplxT = dev_tensor(t, (nx, N, nz, 2), self.device)          # [ny][x][kz], ny == nx
+        self.sendbuf = torch.empty((self.world, nx, nx, nz, 2), dtype=torch.float64, device=self.device) if self.world > 1 else None
+        self.recvbuf = torch.empty_like(self.sendbuf) if self.world > 1 else None
+        self.halo_a = torch.empty((h, N, N), dtype=torch.float64, device=self.device)
+        self.halo_b = torch.empty_like(self.halo_a)
+        self.own_cells = self.dom.own_cell_mask(self.device)
+        self.top = torch.empty((8 ** topdepth, 4), dtype=torch.float64, device=self.device)
+        self.timings = {}
+
+    # ---- particles ---------------------------------------------------------
+    def load(self, pos, mass, oldacc=None, rcut_cells=None):
+        """pos [n,3] f64, mass [n] f32 device tensors of the rank's OWN particles
+        (every x inside the rank's layers).  Imports the ghost layers and hands
+        own+ghost to the engine."""
+        if rcut_cells is not None:
+            rcut = rcut_cells * self.asmth * self.box / self.nmesh
+            if not self.dom.cellwidth > rcut * 1.0001:
+                raise ValueError("top-tree cells (%.4g) must be wider than Rcut (%.4g): lower topdepth" % (self.dom.cellwidth, rcut))
+        n_own = pos.shape[0]
+        to_l, to_r = self.dom.ghost_sets(pos[:, 0])
+        pm = torch.cat([pos, mass.to(torch.float64)[:, None]], dim=1)
+        fr, fl = self.comm.neighbour_exchange_var(pm[to_l], pm[to_r])
+        ghosts = torch.cat([fl, fr], dim=0)
+        self.n_own = n_own
+        self.pos = torch.cat([pos, ghosts[:, :3]], dim=0).contiguous()
+        self.mass = torch.cat([mass, ghosts[:, 3].to(torch.float32)], dim=0).contiguous()
+        self.n_tot = self.pos.shape[0]
+        self.oldacc = None
+        if oldacc is not None:
+            self.oldacc = torch.zeros((self.n_tot, 3), dtype=torch.float64, device=self.device)
+            self.oldacc[:n_own] = oldacc
+        torch.cuda.synchronize() if self.device.type == "cuda" else None
+        self.e.set_particles_dev(self.pos.data_ptr(), self.mass.data_ptr(), self.n_tot,
+                                 oldacc_ptr=self.oldacc.data_ptr() if self.oldacc is not None else None)
+        self.targets = torch.arange(n_own, dtype=torch.int32, device=self.device)
+        self.acc = torch.zeros((self.n_tot, 3), dtype=torch.float64, device=self.device)
+        self.pot = torch.zeros(self.n_tot, dtype=torch.float64, device=self.device)
+        self.gpm = torch.zeros((self.n_tot, 3), dtype=torch.float64, device=self.device)
+        return self.n_tot - n_own
+
+    # ---- PM ------------------------------------------------------------------
+    def _sync(self):
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+
+    def pm_force(self):
+        e, h, nx = self.e, self.halo, self.nx
+        e.pmslab_deposit(self.n_own)
+        # density halo planes -> add into the neighbours' edge planes (petapm.c:787-790)
+        halo_add(self.comm, self.real, nx, h, self.halo_a, self.halo_b)
+        self._sync()
+        e.pmslab_fft2d(0)
+        slab_transpose_forward(self.comm, self.cplx, self.cplxT, self.sendbuf, self.recvbuf, self._sync)
+        self._sync()
+        e.pmslab_fft1d(0)
+        e.pmslab_transfer()
+        e.pmslab_fft1d(1)
+        slab_transpose_backward(self.comm, self.cplx, self.cplxT, self.sendbuf, self.recvbuf, self._sync)
+        self._sync()
+        e.pmslab_fft2d(1)
+        # potential halo planes <- neighbours' edge planes (petapm.c:848-885)
+        halo_fill(self.comm, self.real, nx, h, self.halo_a, self.halo_b)
+        self._sync()
+        e.pmslab_readout_dev(self.n_own, self.gpm.data_ptr(), None)
+        return self.gpm[:self.n_own]
+
+    # ---- tree ------------------------------------------------------------------
+    def tree_force(self, par):
+        e, d = self.e, self.dom.d
+        info = e.force_tree_build(self.box, toplevel_depth=d)
+        self.tree_info = info
+        if self.world > 1:
+            e.tree_top_get_dev(d, self.top.data_ptr())
+            self.top[~self.own_cells] = 0.0
+            self._sync()
+            self.comm.all_reduce_sum(self.top)
+            self._sync()
+            e.tree_top_set_dev(d, self.top.data_ptr())
+        e.grav_short_tree_dev(par, self.acc.data_ptr(), self.pot.data_ptr(),
+                              active_ptr=self.targets.data_ptr(), nactive=self.n_own)
+        return self.acc[:self.n_own], self.pot[:self.n_own]
+
+    def force_step(self, par):
+        gpm = self.pm_force()
+        acc, pot = self.tree_force(par)
+        return gpm, acc, pot

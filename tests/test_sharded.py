@@ -1,0 +1,185 @@
+"""Multi-GPU host logic.  CPU: world_size-2 gloo processes exercise the domain
+cut, ghost import, halo-plane exchange and the slab-FFT transposes against
+single-process numpy.  GPU: the sharded driver with world size 1 against the
+unsharded engine path, and (when >= 2 GPUs are visible) 2 ranks under torchrun."""
+import importlib
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = 43.0071
+
+WORKER = r'''
+import os, sys, importlib
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+sh = importlib.import_module("mp-gadget_b200.sharded")
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+comm = sh.Comm(dist)
+rng = np.random.default_rng(5)                 # same stream on every rank
+box, d, N, h = 16.0, 3, 16, 4
+nx, nz = N // world, N // 2 + 1
+# ---- slab FFT: 2-D rfft per owned plane, transpose, 1-D fft along x == rfftn
+field = rng.standard_normal((N, N, N))
+mine = torch.from_numpy(field[rank * nx:(rank + 1) * nx].copy())
+c2 = torch.view_as_real(torch.fft.rfft2(mine)).contiguous()                 # [nx][N][nz][2]
+cT = torch.empty_like(c2)
+sb = torch.empty((world, nx, nx, nz, 2), dtype=torch.float64); rb = torch.empty_like(sb)
+sh.slab_transpose_forward(comm, c2, cT, sb, rb)
+full = np.fft.rfftn(field)                                                   # [x][y][kz]
+got = torch.fft.fft(torch.view_as_complex(cT), dim=1).numpy()                # [jy][kx][kz]
+want = np.transpose(full[:, rank * nx:(rank + 1) * nx, :], (1, 0, 2))
+assert np.abs(got - want).max() < 1e-10, "forward transpose"
+back = torch.empty_like(c2)
+sh.slab_transpose_backward(comm, back, cT, sb, rb)
+assert torch.equal(back, c2), "backward transpose"
+# ---- halo add / fill on planes labelled by their global index
+real = torch.zeros((nx + 2 * h, N, N), dtype=torch.float64)
+for l in range(nx + 2 * h):
+    real[l] = float((rank * nx - h + l) %% N) + 1.0                          # deposit "1 + global plane" everywhere
+a = torch.empty((h, N, N), dtype=torch.float64); b = torch.empty_like(a)
+sh.halo_add(comm, real, nx, h, a, b)
+for l in range(h, h + nx):                                                   # owned planes: own + what neighbours spilled
+    g = (rank * nx - h + l) %% N
+    extra = (1.0 + g) * ((1 if l < 2 * h else 0) + (1 if l >= nx else 0))
+    assert torch.all(real[l] == 1.0 + g + extra), ("halo_add", l)
+for l in range(h, h + nx):
+    real[l] = float((rank * nx - h + l) %% N)
+sh.halo_fill(comm, real, nx, h, a, b)
+for l in range(nx + 2 * h):
+    assert torch.all(real[l] == float((rank * nx - h + l) %% N)), ("halo_fill", l)
+# ---- domain + ghosts: every particle within rcut of an own particle is own or imported
+dom = sh.Domain(box, d, rank, world)
+pos = torch.from_numpy(rng.random((4000, 3)) * box)
+owner = dom.owner_of(pos[:, 0])
+own = pos[owner == rank]
+to_l, to_r = dom.ghost_sets(own[:, 0])
+pm = torch.cat([own, torch.ones(len(own), 1, dtype=torch.float64)], 1)
+fr, fl = comm.neighbour_exchange_var(pm[to_l], pm[to_r])
+have = torch.cat([own, fr[:, :3], fl[:, :3]], 0).numpy()
+rcut = 0.95 * dom.cellwidth
+allp = pos.numpy(); o = own.numpy()
+for p in o[::7]:
+    dd = allp - p; dd -= box * np.round(dd / box)
+    need = allp[(np.abs(dd) < rcut).all(1)]
+    for q in need:
+        assert (np.abs(have - q).sum(1) == 0).any(), "missing ghost"
+assert len(have) == len(np.unique(have, axis=0)), "duplicate ghosts"
+# ---- own-cell mask agrees with the layer of the cell centres
+mask = dom.own_cell_mask("cpu").numpy()
+m = np.arange(8 ** d); ix = np.zeros_like(m)
+for l in range(d): ix |= ((m >> (3 * l)) & 1) << l
+assert np.array_equal(mask, (ix // dom.per) == rank)
+cnt = torch.tensor([float(mask.sum())]); comm.all_reduce_sum(cnt)
+assert cnt.item() == 8 ** d
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def _torchrun(code, nproc, extra_env=None, timeout=600):
+    path = os.path.join(ROOT, "tests", "_worker_tmp_%d.py" % os.getpid())
+    with open(path, "w") as f:
+        f.write(code)
+    env = dict(os.environ)
+    env.update(extra_env or {})
+    try:
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+                            "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), path],
+                           capture_output=True, text=True, timeout=timeout, env=env)
+    finally:
+        os.unlink(path)
+    return r
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_host_logic_gloo(world):
+    r = _torchrun(WORKER % {"root": ROOT}, world)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == world
+
+
+def _setup(ics, ng=32, seed=3):
+    pos, mass = ics.zeldovich_lattice(ng, float(ng), seed=seed)
+    return pos, mass, float(ng), ics.default_nmesh(ng)
+
+
+@pytest.mark.gpu
+def test_sharded_world1_equals_unsharded(b200, ics):
+    """Slab PM (2-D FFT + transpose + 1-D FFT + fused difference/readout) and the
+    forced-top-tree walk over a target subset reproduce the single-GPU path."""
+    sh = importlib.import_module("mp-gadget_b200.sharded")
+    pos, mass, box, nmesh = _setup(ics)
+    n = len(mass)
+    par = ics.tree_params(box, n, treeusebh=1)
+    e0 = b200.Engine(0)
+    e0.set_particles(pos, mass)
+    e0.gravpm_init_periodic(box, 1.5, nmesh, G)
+    g0, _ = e0.gravpm_force()
+    e0.force_tree_build(box, toplevel_depth=2)
+    a0, p0, _ = e0.grav_short_tree(par)
+    e0.close()
+    e1 = b200.Engine(0)
+    s = sh.ShardedTreePM(e1, box, nmesh, 1.5, G, topdepth=2, dist=None)
+    s.load(torch.from_numpy(pos).cuda(), torch.from_numpy(mass).cuda(), rcut_cells=par["Rcut"])
+    g1, a1, p1 = s.force_step(par)
+    g1, a1, p1 = g1.cpu().numpy(), a1.cpu().numpy(), p1.cpu().numpy()
+    e1.close()
+    assert np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
+    assert np.abs(a1 - a0).max() <= 1e-12 * np.sqrt((a0 ** 2).sum(1)).mean()
+    assert np.abs(p1 - p0).max() <= 1e-12 * np.abs(p0).max()
+
+
+GPU_WORKER = r'''
+import os, sys, importlib
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+pkg = importlib.import_module("mp-gadget_b200"); ics = importlib.import_module("mp-gadget_b200.ics")
+sh = importlib.import_module("mp-gadget_b200.sharded")
+local = int(os.environ["LOCAL_RANK"]); torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+G = 43.0071
+pos, mass = ics.zeldovich_lattice(32, 32.0, seed=3); box, nmesh = 32.0, 96
+par = ics.tree_params(box, len(mass), treeusebh=1)
+e = pkg.Engine(local)
+s = sh.ShardedTreePM(e, box, nmesh, 1.5, G, topdepth=3, dist=dist, device="cuda:%%d" %% local)
+tp = torch.from_numpy(pos).cuda(); tm = torch.from_numpy(mass).cuda()
+sel = s.dom.owner_of(tp[:, 0]) == rank
+nghost = s.load(tp[sel].contiguous(), tm[sel].contiguous(), rcut_cells=par["Rcut"])
+g, a, p = s.force_step(par)
+idx = torch.nonzero(sel)[:, 0].cpu().numpy()
+np.savez(os.path.join(%(out)r, "shard_%%d.npz" %% rank), idx=idx, g=g.cpu().numpy(), a=a.cpu().numpy(), p=p.cpu().numpy(), nghost=nghost)
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_two_gpus_equal_one(b200, ics, tmp_path):
+    pos, mass, box, nmesh = _setup(ics)
+    par = ics.tree_params(box, len(mass), treeusebh=1)
+    e0 = b200.Engine(0)
+    e0.set_particles(pos, mass)
+    e0.gravpm_init_periodic(box, 1.5, nmesh, G)
+    g0, _ = e0.gravpm_force()
+    e0.force_tree_build(box, toplevel_depth=3)
+    a0, p0, _ = e0.grav_short_tree(par)
+    e0.close()
+    r = _torchrun(GPU_WORKER % {"root": ROOT, "out": str(tmp_path)}, 2)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    seen = np.zeros(len(mass), bool)
+    for rank in range(2):
+        d = np.load(os.path.join(str(tmp_path), "shard_%d.npz" % rank))
+        idx = d["idx"]
+        assert not seen[idx].any()
+        seen[idx] = True
+        assert np.abs(d["g"] - g0[idx]).max() <= 1e-10 * np.abs(g0).max()
+        assert np.abs(d["a"] - a0[idx]).max() <= 1e-11 * np.sqrt((a0 ** 2).sum(1)).mean()
+        assert np.abs(d["p"] - p0[idx]).max() <= 1e-11 * np.abs(p0).max()
+    assert seen.all()
