@@ -153,6 +153,145 @@ def run_reference(args, rank):
     print(json.dumps(out), flush=True)
 
 
+def sharded_config(world, ng_per_gpu):
+    """Global lattice, mesh and top-tree depth for `world` GPUs at ~ng_per_gpu^3 particles each."""
+    ng_tot = int(round(ng_per_gpu * world ** (1.0 / 3.0)))
+    ng_tot += (-ng_tot) % world                      # lattice planes split evenly over the ranks
+    # cell = spacing/3 as for 256^3/768; FFT-friendly (2^a 3^b 5^c) multiple of 2*world nearest to 3*ng_tot
+    cands = [2 ** a * 3 ** b * 5 ** c for a in range(1, 13) for b in range(0, 7) for c in range(0, 4)]
+    cands = [m for m in cands if m % (2 * world) == 0]
+    nmesh = min(cands, key=lambda m: abs(m - 3 * ng_tot))
+    rcut_spacings = 6.0 * 1.5 * ng_tot / nmesh
+    d = 1
+    while (1 << (d + 1)) * rcut_spacings * 1.02 < 1.001 * ng_tot and d < 8:
+        d += 1
+    while (1 << d) % world:
+        d -= 1
+    return ng_tot, nmesh, d
+
+
+def run_sharded(args, rank, world, local, dist, pkg, ics, W, K):
+    import numpy as np
+    import torch
+    sh = importlib.import_module("mp-gadget_b200.sharded")
+    dev = torch.device("cuda", local)
+    ng_tot, nmesh, topdepth = sharded_config(world, args.ng)
+    box = float(ng_tot)
+    par = ics.tree_params(box, ng_tot ** 3, treeusebh=1)
+    e = pkg.Engine(local)
+    stream = torch.cuda.ExternalStream(e.stream(), device=dev)
+    s = sh.ShardedTreePM(e, box, nmesh, 1.5, G, topdepth, dist=dist, device="cuda:%d" % local)
+    # own particles: lattice planes of my x-range (+3 planes margin), kept where the displaced x is mine
+    per = ng_tot // world
+    pos, mass = ics.planewave_lattice(ng_tot, box, xplanes=(rank * per - 3, (rank + 1) * per + 3), device="cuda:%d" % local)
+    keep = s.dom.owner_of(pos[:, 0]) == rank
+    pos, mass = pos[keep].contiguous(), mass[keep].contiguous()
+    n_own = pos.shape[0]
+    ntot = torch.tensor([n_own], dtype=torch.int64, device=dev)
+    dist.all_reduce(ntot)
+    total = int(ntot.item())
+    assert total == ng_tot ** 3, (total, ng_tot ** 3)
+    oldacc = None
+
+    def step_dev():
+        nonlocal oldacc
+        s.load(pos, mass, oldacc=oldacc, rcut_cells=par["Rcut"])     # ghost exchange is part of the step
+        gpm, acc, pot = s.force_step(par)
+        oldacc = (acc + gpm).contiguous()
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    step_dev()
+    par["TreeUseBH"] = 0
+    for _ in range(W):
+        step_dev()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = e.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase = {}
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_dev()
+        for k, v in e.timings().items():
+            phase[k] = phase.get(k, 0.0) + v / K
+    torch.cuda.synchronize()
+    wall_dev = (time.perf_counter() - t0) * 1e3
+    ev1.record(stream)
+    barrier()
+    # the harness interleaves torch (default stream) and engine (own stream) work with syncs in
+    # between, so wall-clock between device syncs is the honest per-rank step time
+    ms_dev = wall_dev
+    launches = e.kernel_launches() - l0
+    nghost = s.n_tot - s.n_own
+
+    # e2e: own particles from pinned host memory in, accelerations back to pinned host memory
+    hpos = torch.empty((n_own, 3), dtype=torch.float64).pin_memory(); hpos.copy_(pos)
+    hmass = torch.empty(n_own, dtype=torch.float32).pin_memory(); hmass.copy_(mass)
+    hacc = torch.empty((n_own, 3), dtype=torch.float64).pin_memory()
+    hgpm = torch.empty((n_own, 3), dtype=torch.float64).pin_memory()
+    hpot = torch.empty(n_own, dtype=torch.float64).pin_memory()
+    hold = torch.empty((n_own, 3), dtype=torch.float64).pin_memory(); hold.copy_(oldacc)
+
+    def step_e2e():
+        dp = hpos.to(dev, non_blocking=True); dm = hmass.to(dev, non_blocking=True); do = hold.to(dev, non_blocking=True)
+        s.load(dp, dm, oldacc=do, rcut_cells=par["Rcut"])
+        gpm, acc, pot = s.force_step(par)
+        hgpm.copy_(gpm, non_blocking=True); hacc.copy_(acc, non_blocking=True); hpot.copy_(pot, non_blocking=True)
+        torch.cuda.synchronize()
+
+    step_e2e()
+    barrier()
+    Ke = max(2, min(K, 5))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        step_e2e()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([ms_dev, ms_e2e, float(nghost), float(n_own)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e, max_ghost, max_own = [float(x) for x in tt]
+    tl = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tl)
+    if rank == 0:
+        hbm, how = peaks()
+        walk_ms = phase["walk"]
+        nn = int(s.tree_info.numnodes)
+        walk_bytes = 72.0 * n_own + 80.0 * nn
+        out = {
+            "metric": METRIC, "value": total * K / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%d^3 DM-only TreePM force step sharded over %d GPUs (~%d^3 per GPU)" % (ng_tot, world, args.ng),
+                       "particles_total": total, "particles_per_gpu_max": int(max_own), "ghosts_per_gpu_max": int(max_ghost),
+                       "Nmesh": nmesh, "Asmth": 1.5, "TreeRcut": 6.0, "ErrTolForceAcc": 0.002, "toptree_depth": topdepth,
+                       "opening": "relative (TreeUseBH=0) after one BH pass",
+                       "ics": "lattice + periodic plane-wave displacement field, rms 0.2 spacing",
+                       "l2": "inputs larger than L2",
+                       "parallelism": "x-slab domain of top-tree cell layers; ghost-layer import + top-moment all-reduce (tree), "
+                                      "slab FFT with NCCL all-to-all transposes + halo planes (PM)"},
+            "e2e": {"value": total * Ke / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_own * (24 + 4 + 24),
+                    "d2h_bytes_per_step": n_own * 56, "ms_per_step": ms_e2e / Ke,
+                    "api": "ShardedTreePM.load + force_step (pinned host pos/mass/oldacc in, acc/gpm/pot out), per rank"},
+            "gpu_launches": int(tl.item()),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_grav_walk", "bound": "hbm", "achieved": walk_bytes / (walk_ms * 1e-3) / 1e9, "peak": hbm,
+                         "unit": "GB/s", "frac": walk_bytes / (walk_ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": how,
+                         "note": "rank 0; latency/fp64-issue bound pair summation; compulsory bytes only (SURVEY 8d K8)"},
+            "phases_ms": phase,
+            "timing": "wall clock between device synchronisations, max over ranks (engine stream + torch stream interleave)",
+        }
+        print(json.dumps(out), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,6 +301,7 @@ def main():
     ap.add_argument("--ng", type=int, default=256, help="particles per dimension per GPU")
     ap.add_argument("--cpu-ng", type=int, default=128, help="CPU-baseline sample size per dimension")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ics", default="planewave", choices=["planewave", "fft"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,11 +325,18 @@ def main():
 
     W = max(args.warmup, 3)
     K = args.steps
+    if world > 1:
+        return run_sharded(args, rank, world, local, dist, pkg, ics, W, K)
     ng = args.ng
     box = float(ng)
     nmesh = ics.default_nmesh(ng)
-    # weak scaling: every rank owns one ng^3 box (seed differs per rank)
-    pos, mass = ics.zeldovich_lattice(ng, box, seed=181170 + rank)
+    # same generator as the multi-GPU arm: lattice + periodic plane-wave displacement field
+    if args.ics == "fft":
+        pos, mass = ics.zeldovich_lattice(ng, box)
+        d_pos, d_mass = torch.from_numpy(pos).cuda(), torch.from_numpy(mass).cuda()
+    else:
+        d_pos, d_mass = ics.planewave_lattice(ng, box, device="cuda")
+        pos = d_pos.cpu().numpy(); mass = d_mass.cpu().numpy()
     n = len(mass)
     par = ics.tree_params(box, n, treeusebh=1)
 
@@ -198,8 +345,6 @@ def main():
     e.gravpm_init_periodic(box, 1.5, nmesh, G)
 
     # ---- device-resident arm ------------------------------------------------
-    d_pos = torch.from_numpy(pos).cuda()
-    d_mass = torch.from_numpy(mass).cuda()
     d_acc = torch.empty((n, 3), dtype=torch.float64, device="cuda")
     d_gpm = torch.empty((n, 3), dtype=torch.float64, device="cuda")
     d_pot = torch.empty(n, dtype=torch.float64, device="cuda")
@@ -214,17 +359,13 @@ def main():
 
     def barrier():
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
 
     step_dev()                      # first pass uses the Barnes-Hut angle (TreeUseBH=2 semantics, gravshort-tree.c:148-151)
     par["TreeUseBH"] = 0
     for _ in range(W):
         step_dev()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()
     barrier()
     l0 = e.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -263,20 +404,11 @@ def main():
     barrier()
     ms_e2e = ev2.elapsed_time(ev3)
     wall_e2e = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     te2e = e.timings()
     # check the AoS result against the device arm (same inputs up to the oldacc refresh)
     Pout = pinned.numpy().view(pkg.PARTICLE_DTYPE)
     chk = float(np.abs(Pout["GravPM"][:1000] - gpm_h[:1000]).max() / (np.abs(gpm_h[:1000]).max() + 1e-300))
-
-    if dist is not None:
-        tt = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e = float(tt[0]), float(tt[1])
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
 
     total = n * world
     value = total * K / (ms_dev * 1e-3)
@@ -308,7 +440,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%d^3 DM-only TreePM force step per GPU (gravpm_force + force_tree_full + grav_short_tree)" % ng,
                    "particles_per_gpu": n, "Nmesh": nmesh, "Asmth": 1.5, "TreeRcut": 6.0, "ErrTolForceAcc": 0.002,
-                   "opening": "relative (TreeUseBH=0) after one BH pass", "ics": "Zel'dovich lattice rms 0.2 spacing",
+                   "opening": "relative (TreeUseBH=0) after one BH pass", "ics": "lattice + periodic plane-wave displacement field, rms 0.2 spacing",
                    "l2": "inputs larger than L2 (particle arrays %.0f MB, mesh %.1f GB)" % (n * 28 / 1e6, N3 * 8 / 1e9),
                    "parallelism": "single GPU" if world == 1 else "independent replicas, one box per GPU (no data-path collective yet)"},
         "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": n * 160, "d2h_bytes_per_step": n * 160,

@@ -191,7 +191,7 @@ void b200_ctx_destroy(b200_ctx *ctx)
     E->spart.release(); E->b_start.release(); E->b_count.release(); E->b_father.release(); E->b_sibling.release();
     E->b_firstchild.release(); E->b_nchild.release(); E->b_level.release(); E->b_size.release(); E->b_dfs.release();
     E->b_scan.release(); E->b_center.release(); E->nodeA.release(); E->nodeB.release(); E->nodeC.release();
-    E->nodeF.release(); E->nodeH.release(); E->nodeK.release(); E->scratch_i.release(); E->targets.release();
+    E->nodeF.release(); E->nodeH.release(); E->nodeK.release(); E->scratch_i.release(); E->targets.release(); E->targets_sorted.release(); E->walk_flags.release();
     E->d_acc.release(); E->d_pot.release(); E->d_counts.release(); E->srtab.release();
     for(int i = 0; i < T_COUNT; i++) if(E->timers[i].a) { cudaEventDestroy(E->timers[i].a); cudaEventDestroy(E->timers[i].b); }
     cudaStreamDestroy(E->stream);

@@ -107,6 +107,8 @@ struct Engine {
 
     // ---- walk ----
     DevBuf<int> targets;        // walk target list (original indices)
+    DevBuf<int> targets_sorted; // the same in tree (curve) order
+    DevBuf<uint8_t> walk_flags;
     DevBuf<double> d_acc, d_pot;  // outputs [n][3], [n]
     DevBuf<int> d_counts;       // [n] b200_walk_counts
     DevBuf<float> srtab;        // 2*512 short-range window tables

@@ -27,6 +27,7 @@
 #include "engine.h"
 #include "../data/shortrange_table.h"
 #include <math.h>
+#include <cub/device/device_select.cuh>
 
 namespace b200 {
 
@@ -466,6 +467,17 @@ __global__ void k_iota(int *p, int n)
     if(i < n) p[i] = i;
 }
 
+__global__ void k_mark(const int *__restrict__ list, int64_t n, uint8_t *__restrict__ flags)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) flags[list[i]] = 1;
+}
+__global__ void k_gather_flags(const int *__restrict__ sidx, int np, const uint8_t *__restrict__ flags, uint8_t *__restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if(j < np) out[j] = flags[sidx[j]];
+}
+
 int walk_init_tables(Engine *E)
 {
     CK(E->srtab.ensure(2 * B200_SR_NTAB));
@@ -510,7 +522,31 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
         CK(E->targets.ensure(E->n > 0 ? E->n : 1));
         if(E->n > 0) { k_iota<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->targets.p, (int) E->n); CKL(E); }
         tg = E->targets.p; nt = E->n;
-    } else { tg = d_active; nt = nactive; }
+    } else {
+        // Walk the caller's targets in the tree's curve order (a warp then holds 32
+        // neighbouring targets); falls back to the given order if some target is not
+        // in the tree.
+        tg = d_active; nt = nactive;
+        if(E->tree_np > 0 && nactive > 0) {
+            const size_t np = (size_t) E->tree_np;
+            CK(E->walk_flags.ensure((size_t) E->n + np + 64));
+            uint8_t *fl = E->walk_flags.p, *fs = fl + E->n;
+            CK(cudaMemsetAsync(fl, 0, (size_t) E->n, E->stream));
+            k_mark<<<(unsigned) ((nactive + 255) / 256), 256, 0, E->stream>>>(d_active, nactive, fl); CKL(E);
+            k_gather_flags<<<(unsigned) ((np + 255) / 256), 256, 0, E->stream>>>(E->sidx.p, (int) np, fl, fs); CKL(E);
+            CK(E->targets_sorted.ensure(np + 1));
+            CK(E->scratch_i.ensure(16));
+            size_t tb = 0;
+            cub::DeviceSelect::Flagged(nullptr, tb, E->sidx.p, fs, E->targets_sorted.p, E->scratch_i.p + 8, (int) np, E->stream);
+            CK(E->cubtemp.ensure(tb + 16));
+            CK(cub::DeviceSelect::Flagged(E->cubtemp.p, tb, E->sidx.p, fs, E->targets_sorted.p, E->scratch_i.p + 8, (int) np, E->stream));
+            E->launches += 2;
+            int got = 0;
+            CK(cudaMemcpyAsync(&got, E->scratch_i.p + 8, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+            CK(cudaStreamSynchronize(E->stream));
+            if(got == nactive) tg = E->targets_sorted.p;
+        }
+    }
     P.ntargets = (int) nt;
     if(nt == 0) return 0;
 

@@ -93,3 +93,44 @@ def tree_params(box, n, treeusebh=0, errtol=0.002, rcut=6.0):
     MaxBHOpeningAngle, TreeRcut, GravitySoftening = 1/30 mean spacing)."""
     return dict(ErrTolForceAcc=errtol, BHOpeningAngle=0.175, MaxBHOpeningAngle=0.9, TreeUseBH=treeusebh,
                 Rcut=rcut, GravitySoftening=(1 / 30.) * box / np.cbrt(n), rho0=OMEGA0 * rho_crit())
+
+
+def planewave_lattice(ng, box, xplanes=None, seed=181170, rms=0.2, nmodes=64, kmax=None, device="cpu"):
+    """Lattice displaced by a sum of random periodic plane waves (Zel'dovich-like,
+    amplitude ~ k^-2, 3-D rms displacement `rms` spacings).  The displacement is a
+    closed-form function of the lattice site, so any rank can generate any x-range
+    of the SAME global particle set without a global FFT: used by the multi-GPU
+    bench.  xplanes = (i0, i1) restricts to lattice planes i0 <= ix < i1 (may
+    extend beyond [0, ng): wrapped).  Returns torch tensors pos[n,3] f64, mass[n] f32."""
+    import torch
+    rng = np.random.default_rng(seed)
+    if kmax is None:
+        kmax = max(4, ng // 8)
+    nvec = rng.integers(-kmax, kmax + 1, size=(4 * nmodes, 3))
+    nvec = nvec[(nvec ** 2).sum(1) > 0][:nmodes]
+    kn = np.sqrt((nvec ** 2).sum(1))
+    amp = rng.standard_normal(len(nvec)) / kn ** 2
+    phase = rng.random(len(nvec)) * 2 * np.pi
+    # rms of sum_m a_m khat_m sin(.) : sum a_m^2 / 2 (3-D)
+    spacing = box / ng
+    scale = rms * spacing / np.sqrt((amp ** 2).sum() / 2)
+    i0, i1 = (0, ng) if xplanes is None else xplanes
+    dev = torch.device(device)
+    ix = torch.arange(i0, i1, dtype=torch.float64, device=dev)
+    iy = torch.arange(ng, dtype=torch.float64, device=dev)
+    qx = ((ix + 0.5) * spacing)[:, None, None].expand(len(ix), ng, ng)
+    qy = ((iy + 0.5) * spacing)[None, :, None].expand(len(ix), ng, ng)
+    qz = ((iy + 0.5) * spacing)[None, None, :].expand(len(ix), ng, ng)
+    dx = torch.zeros((len(ix), ng, ng), dtype=torch.float64, device=dev)
+    dy = torch.zeros_like(dx)
+    dz = torch.zeros_like(dx)
+    tw = 2 * np.pi / box
+    for m in range(len(nvec)):
+        arg = tw * (nvec[m, 0] * qx + nvec[m, 1] * qy + nvec[m, 2] * qz) + phase[m]
+        s = torch.sin(arg) * (scale * amp[m] / kn[m])
+        dx += s * float(nvec[m, 0]); dy += s * float(nvec[m, 1]); dz += s * float(nvec[m, 2])
+    pos = torch.stack([(qx + dx).reshape(-1), (qy + dy).reshape(-1), (qz + dz).reshape(-1)], dim=1)
+    pos = torch.remainder(pos, box)
+    pos[pos >= box] = 0.0
+    mass = torch.full((pos.shape[0],), OMEGA0 * rho_crit() * spacing ** 3, dtype=torch.float32, device=dev)
+    return pos.contiguous(), mass
