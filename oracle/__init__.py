@@ -43,7 +43,7 @@ COUNTS_DTYPE = np.dtype([("nodes_accepted", "i4"), ("nodes_opened", "i4"),
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_tree.c", "oracle_pm.c", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_tree.c", "oracle_pm.c", "oracle_sph.c", "oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -109,6 +109,66 @@ class OracleTree:
         if rc:
             raise MemoryError
         return acc, pot, cnt
+
+
+class SphParams(C.Structure):
+    _fields_ = [("KernelType", C.c_int32), ("DensityIndependentSphOn", C.c_int32),
+                ("DensityResolutionEta", C.c_double), ("MaxNumNgbDeviation", C.c_double), ("MinGasHsml", C.c_double),
+                ("ArtBulkViscConst", C.c_double), ("DensityContrastLimit", C.c_double),
+                ("gravkick", C.c_double), ("hydrokick", C.c_double), ("pmkick", C.c_double),
+                ("dloga_pred", C.c_double), ("drift", C.c_double), ("dloga_bin", C.c_double),
+                ("atime", C.c_double), ("hubble", C.c_double)]
+
+
+SPH_DEFAULTS = dict(KernelType=2, DensityIndependentSphOn=1, DensityResolutionEta=1.0, MaxNumNgbDeviation=2.0,
+                    MinGasHsml=0.0, ArtBulkViscConst=0.75, DensityContrastLimit=100.0, gravkick=0.0, hydrokick=0.0,
+                    pmkick=0.0, dloga_pred=0.0, drift=0.0, dloga_bin=0.0, atime=1.0, hubble=0.1)
+
+
+def sph_params(**kw):
+    d = dict(SPH_DEFAULTS)
+    d.update(kw)
+    return SphParams(**d)
+
+
+def set_init_hsml(tree, kerneltype, eta, mean_gas_separation):
+    h = np.zeros(tree.n)
+    lib().oracle_set_init_hsml(C.byref(tree.t), _p(tree.mass), _p(tree.type), C.c_int64(tree.n), C.c_int(kerneltype),
+                               C.c_double(eta), C.c_double(mean_gas_separation), _p(h))
+    return h
+
+
+def density(tree, sp, hsml, update_hsml=1, DoEgyDensity=0, vel=None, entropy=None, dtentropy=None,
+            fullacc=None, gravpm=None, hydroacc=None):
+    """oracle_density on the particles of an OracleTree (gas tree). Returns a dict."""
+    n = tree.n
+    f8 = lambda a: _c(a, np.float64)
+    out = dict(hsml=np.array(hsml, dtype=np.float64, copy=True), density=np.zeros(n), egywtdensity=np.zeros(n),
+               dhsmlfac=np.zeros(n), divvel=np.zeros(n), curlvel=np.zeros(n), dthsml=np.zeros(n), numngb=np.zeros(n),
+               ninteract=np.zeros(n, np.int32), niter=np.zeros(n, np.int32), entvarpred=np.zeros(n))
+    vel, entropy, dtentropy, fullacc, gravpm, hydroacc = map(f8, (vel, entropy, dtentropy, fullacc, gravpm, hydroacc))
+    lib().oracle_density.restype = C.c_int
+    rc = lib().oracle_density(C.byref(tree.t), _p(tree.pos), _p(tree.mass), _p(tree.type), C.c_int64(n), C.byref(sp),
+                              C.c_int(update_hsml), C.c_int(DoEgyDensity), _p(vel), _p(fullacc), _p(gravpm), _p(hydroacc),
+                              _p(entropy), _p(dtentropy), _p(out["hsml"]), _p(out["density"]), _p(out["egywtdensity"]),
+                              _p(out["dhsmlfac"]), _p(out["divvel"]), _p(out["curlvel"]), _p(out["dthsml"]), _p(out["numngb"]),
+                              _p(out["ninteract"]), _p(out["niter"]), _p(out["entvarpred"]))
+    out["rc"] = rc
+    return out
+
+
+def hydro(tree, sp, dens, vel=None, entropy=None, dtentropy=None, fullacc=None, gravpm=None, hydroacc=None):
+    """oracle_hydro after density(); dens is the dict density() returned."""
+    n = tree.n
+    f8 = lambda a: _c(a, np.float64)
+    vel, entropy, dtentropy, fullacc, gravpm, hydroacc = map(f8, (vel, entropy, dtentropy, fullacc, gravpm, hydroacc))
+    out = dict(acc=np.zeros((n, 3)), dtentropy=np.zeros(n), maxsignalvel=np.zeros(n), ninteract=np.zeros(n, np.int32))
+    lib().oracle_hydro(C.byref(tree.t), _p(tree.pos), _p(tree.mass), _p(tree.type), C.c_int64(n), C.byref(sp),
+                       _p(vel), _p(fullacc), _p(gravpm), _p(hydroacc), _p(entropy), _p(dtentropy),
+                       _p(dens["hsml"]), _p(dens["density"]), _p(dens["egywtdensity"]), _p(dens["dhsmlfac"]),
+                       _p(dens["divvel"]), _p(dens["curlvel"]),
+                       _p(out["acc"]), _p(out["dtentropy"]), _p(out["maxsignalvel"]), _p(out["ninteract"]))
+    return out
 
 
 def pm_force(pos, mass, box, nmesh, asmth, G, workers=-1, return_mesh=False):

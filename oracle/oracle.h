@@ -86,6 +86,37 @@ void oracle_pm_readout(const double *mesh, const double *pos, int64_t n, double 
 void oracle_direct_sum(const double *pos, const float *mass, int64_t n, double BoxSize, double G,
                        double softening_h, int repeat, double *accel_out);
 
+/* ---- SPH (synchronised step: all gas on one time bin) ---- */
+typedef struct oracle_sph_params {
+    int32_t KernelType;               /* 1 cubic, 2 quintic, 4 quartic: densitykernel.h:20-24 */
+    int32_t DensityIndependentSphOn;  /* hydra.c:37-53 */
+    double DensityResolutionEta, MaxNumNgbDeviation, MinGasHsml;     /* density.c:30-51,264-265 */
+    double ArtBulkViscConst, DensityContrastLimit;                   /* hydra.c:37-48 */
+    double gravkick, hydrokick, pmkick;   /* kick_factor_data of the common time bin, density.c:114-132 */
+    double dloga_pred;                    /* dloga of SPH_EntVarPred, density.c:74 */
+    double drift;                         /* drifts[bin], hydra.c:178-186 */
+    double dloga_bin;                     /* get_dloga_for_bin, hydra.c:271,463 */
+    double atime, hubble;                 /* hydra.c:219-223 */
+} oracle_sph_params;
+
+double oracle_sph_desnumngb(int kerneltype, double eta);
+void oracle_set_init_hsml(const oracle_tree *t, const float *mass, const uint8_t *type, int64_t n,
+                          int kerneltype, double eta, double MeanGasSeparation, double *hsml);
+int oracle_density(oracle_tree *t, const double *pos, const float *mass, const uint8_t *type, int64_t n,
+                   const oracle_sph_params *sp, int update_hsml, int DoEgyDensity,
+                   const double *vel, const double *fullacc, const double *gravpm, const double *hydroacc,
+                   const double *entropy, const double *dtentropy,
+                   double *hsml, double *density, double *egywtdensity, double *dhsmlfac,
+                   double *divvel, double *curlvel, double *dthsml, double *numngb_out, int32_t *ninteract, int32_t *niter_out,
+                   double *entvarpred_out);
+int oracle_hydro(const oracle_tree *t, const double *pos, const float *mass, const uint8_t *type, int64_t n,
+                 const oracle_sph_params *sp,
+                 const double *vel, const double *fullacc, const double *gravpm, const double *hydroacc_in,
+                 const double *entropy, const double *dtentropy_in,
+                 const double *hsml, const double *density, const double *egywtdensity, const double *dhsmlfac,
+                 const double *divvel, const double *curlvel,
+                 double *acc_out, double *dtentropy_out, double *maxsignalvel_out, int32_t *ninteract);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,33 @@ class Ref:
                                    _p(out["nocc"]), _p(out["part"]), _p(out["toplevel"]))
         return {a: v[:k] for a, v in out.items()}
 
+    def sph_density(self, pos, mass, box, hsml, vel=None, entropy=None, kerneltype=1, eta=1.0, maxdev=2.0,
+                    mingashsml_frac=0.006, softening=1.0, init_hsml=False, meansep=None, update_hsml=1, DoEgyDensity=0):
+        """density() as tests/test_density.c:55-107 drives it (gas only, time bin 0)."""
+        pos = np.ascontiguousarray(pos, np.float64); mass = np.ascontiguousarray(mass, np.float32)
+        n = len(mass)
+        vel = None if vel is None else np.ascontiguousarray(vel, np.float64)
+        entropy = None if entropy is None else np.ascontiguousarray(entropy, np.float64)
+        out = dict(hsml=np.array(hsml, dtype=np.float64, copy=True), density=np.zeros(n), egywtdensity=np.zeros(n),
+                   dhsmlfac=np.zeros(n), divvel=np.zeros(n), curlvel=np.zeros(n), dthsml=np.zeros(n))
+        self.n = n
+        self.L.ref_sph_density(C.c_int64(n), _p(pos), _p(mass), _p(vel), _p(entropy), C.c_double(box), C.c_int(kerneltype),
+                               C.c_double(eta), C.c_double(maxdev), C.c_double(mingashsml_frac), C.c_double(softening),
+                               C.c_int(1 if init_hsml else 0), C.c_double(box if meansep is None else meansep),
+                               C.c_int(update_hsml), C.c_int(DoEgyDensity), _p(out["hsml"]), _p(out["density"]),
+                               _p(out["egywtdensity"]), _p(out["dhsmlfac"]), _p(out["divvel"]), _p(out["curlvel"]), _p(out["dthsml"]))
+        return out
+
+    def sph_hydro(self, atime=1.0, hubble=0.1, dloga_bin=0.0, DensityIndependentSphOn=0, ArtBulkViscConst=0.75,
+                  DensityContrastLimit=100.0):
+        """force_tree_calc_moments + hydro_force right after sph_density (run.c:472-489)."""
+        n = self.n
+        out = dict(acc=np.zeros((n, 3)), dtentropy=np.zeros(n), maxsignalvel=np.zeros(n))
+        self.L.ref_sph_hydro(C.c_double(atime), C.c_double(hubble), C.c_double(dloga_bin), C.c_int(DensityIndependentSphOn),
+                             C.c_double(ArtBulkViscConst), C.c_double(DensityContrastLimit), _p(out["acc"]),
+                             _p(out["dtentropy"]), _p(out["maxsignalvel"]))
+        return out
+
     def timings(self):
         b, w = C.c_double(), C.c_double()
         self.L.ref_timings(C.byref(b), C.byref(w))

@@ -28,6 +28,9 @@
 #include <libgadget/petapm.h>
 #include <libgadget/timestep.h>
 #include <libgadget/walltime.h>
+#include <libgadget/density.h>
+#include <libgadget/hydra.h>
+#include <libgadget/cosmology.h>
 
 /* ---- stand-ins for functions that live in reference files we do not build
  * (timestep.c needs cosmology/GSL; petaio needs bigfile) ------------------- */
@@ -47,6 +50,37 @@ ActiveParticles init_empty_active_particles(struct part_manager_type *PartManage
     return act;
 }
 void dump_snapshot(const char *dump, const double Time, void *CP, const char *OutputDir) {}
+
+/* Time-integration helpers (timebinmgr.c, timefac.c need GSL; cosmology.c needs GSL;
+ * winds.c is sub-grid physics).  The SPH fixtures are synchronised: every particle
+ * sits on time bin 0 at Ti_Current = 0 with all kick times equal, for which the
+ * reference's own functions return exactly these values (timefac.c:44-45:
+ * t0 == t1 -> 0; timebinmgr.c:420-447 with dti = 0 / bin 0 -> 0). */
+static double sph_dloga_bin, sph_hubble;
+double dloga_from_dti(inttime_t dti, const inttime_t Ti_Current) { if(dti != 0) endrun(1, "ref_driver: unsynchronised fixture\n"); return 0; }
+double get_dloga_for_bin(int timebin, const inttime_t Ti_Current) { return sph_dloga_bin; }
+static double exact_factor(inttime_t t0, inttime_t t1) { if(t0 != t1) endrun(1, "ref_driver: unsynchronised fixture\n"); return 0; }
+double get_exact_drift_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return exact_factor(t0, t1); }
+double get_exact_gravkick_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return exact_factor(t0, t1); }
+double get_exact_hydrokick_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return exact_factor(t0, t1); }
+double hubble_function(const Cosmology *CP, double a) { return sph_hubble; }
+int winds_is_particle_decoupled(int i) { return 0; }
+void winds_decoupled_hydro(int i, double atime) {}
+/* set_hydro_params (hydra.c:37-48) reads its three keys through param_get_*; the
+ * driver supplies them from a table instead of a parsed parameter file. */
+static double hp_visc, hp_contrast; static int hp_di;
+double param_get_double(ParameterSet *ps, const char *name)
+{
+    if(!strcmp(name, "ArtBulkViscConst")) return hp_visc;
+    if(!strcmp(name, "DensityContrastLimit")) return hp_contrast;
+    endrun(1, "ref_driver: unexpected parameter %s\n", name); return 0;
+}
+int param_get_int(ParameterSet *ps, const char *name)
+{
+    if(!strcmp(name, "DensityIndependentSphOn")) return hp_di;
+    endrun(1, "ref_driver: unexpected parameter %s\n", name); return 0;
+}
+int param_get_enum(ParameterSet *ps, const char *name) { endrun(1, "ref_driver: unexpected enum %s\n", name); return 0; }
 
 static struct ClockTable CT;
 static int initialised = 0;
@@ -119,13 +153,18 @@ int ref_init(double arena_gib, int nthreads)
 }
 
 static int have_particles = 0;
+static int slots_ready = 0;
+static struct sph_pred_data sph_pred;
 static void free_all(void)
 {
+    /* the arena is a stack: release in reverse order of allocation (utils/mymalloc.h:15-19) */
+    if(sph_pred.EntVarPred) slots_free_sph_pred_data(&sph_pred);
     if(force_tree_allocated(&Tree)) force_tree_free(&Tree);
     if(dd.domain_allocated_flag) {
         myfree(dd.Tasks); myfree(dd.TopLeaves); myfree(dd.TopNodes);
         memset(&dd, 0, sizeof(dd));
     }
+    if(slots_ready) { slots_free(SlotsManager); slots_ready = 0; }
     if(have_particles) { myfree(P); have_particles = 0; }
 }
 
@@ -214,5 +253,88 @@ int64_t ref_tree_export(double *center, double *len, double *cofm, double *mass,
     }
     return k;
 }
+
+/* ---- SPH: the reference's density() and hydro_force() on a gas-only fixture, as
+ * tests/test_density.c:55-152 sets it up (all particles type 0, time bin 0). ---- */
+static double t_density, t_hydro;
+
+int ref_sph_density(int64_t n, const double *pos, const float *mass, const double *vel, const double *entropy,
+                    double BoxSize, int kerneltype, double eta, double maxdev, double mingashsml_frac, double softening,
+                    int init_hsml, double meansep, int update_hsml, int DoEgyDensity,
+                    double *hsml /*in/out*/, double *density_out, double *egy_out, double *dhsmlfac_out,
+                    double *divvel_out, double *curlvel_out, double *dthsml_out)
+{
+    free_all();
+    particle_alloc_memory(PartManager, BoxSize, n);
+    have_particles = 1;
+    PartManager->NumPart = n;
+    slots_init(0.01 * n, SlotsManager);
+    slots_set_enabled(0, sizeof(struct sph_particle_data), SlotsManager);
+    int64_t atleast[6] = {0};
+    atleast[0] = n;
+    slots_reserve(1, atleast, SlotsManager);
+    slots_ready = 1;
+    SlotsManager->info[0].size = n;
+    build_uniform_domain(&dd, 0);
+    for(int64_t i = 0; i < n; i++) {
+        memset(&P[i], 0, sizeof(P[i]));
+        for(int k = 0; k < 3; k++) { P[i].Pos[k] = pos[3 * i + k]; P[i].Vel[k] = vel ? vel[3 * i + k] : 0; }
+        P[i].Mass = mass[i]; P[i].Type = 0; P[i].PI = i; P[i].ID = i; P[i].Hsml = hsml[i];
+        P[i].TopLeaf = 0;
+        memset(&SPHP(i), 0, sizeof(struct sph_particle_data));
+        SPHP(i).Entropy = entropy ? entropy[i] : 1; SPHP(i).DtEntropy = 0; SPHP(i).Density = 1;
+    }
+    struct density_params dp = {0};
+    dp.DensityResolutionEta = eta; dp.MaxNumNgbDeviation = maxdev; dp.BlackHoleNgbFactor = 2;
+    dp.BlackHoleMaxAccretionRadius = 99999.; dp.DensityKernelType = (enum DensityKernelType) kerneltype;
+    dp.MinGasHsmlFractional = mingashsml_frac;
+    set_densitypar(dp);
+    struct gravshort_tree_params tp = {0};
+    tp.FractionalGravitySoftening = softening;
+    set_gravshort_treepar(tp);
+    gravshort_set_softenings(1);
+    ActiveParticles act = init_empty_active_particles(PartManager);
+    if(init_hsml) {      /* tests/test_density.c:84-86 */
+        force_tree_rebuild_mask(&Tree, &dd, GASMASK + BHMASK, NULL);
+        set_init_hsml(&Tree, &dd, meansep);
+    }
+    force_tree_rebuild_mask(&Tree, &dd, GASMASK, NULL);
+    DriftKickTimes kick = {0};
+    Cosmology CP = {0};
+    sph_pred.EntVarPred = NULL;
+    const double t0 = omp_get_wtime();
+    density(&act, update_hsml, DoEgyDensity, 0, kick, &CP, &sph_pred, NULL, &Tree);
+    t_density = omp_get_wtime() - t0;
+    for(int64_t i = 0; i < n; i++) {
+        hsml[i] = P[i].Hsml; density_out[i] = SPHP(i).Density; egy_out[i] = SPHP(i).EgyWtDensity;
+        dhsmlfac_out[i] = SPHP(i).DhsmlEgyDensityFactor; divvel_out[i] = SPHP(i).DivVel; curlvel_out[i] = SPHP(i).CurlVel;
+        dthsml_out[i] = P[i].DtHsml;
+    }
+    return 0;
+}
+
+/* hydro_force right after ref_sph_density (run.c:472-489: density, force_tree_calc_moments, hydro_force). */
+int ref_sph_hydro(double atime, double hubble, double dloga_bin, int DensityIndependentSphOn, double ArtBulkViscConst,
+                  double DensityContrastLimit, double *acc_out, double *dtentropy_out, double *maxsig_out)
+{
+    const int64_t n = PartManager->NumPart;
+    sph_hubble = hubble; sph_dloga_bin = dloga_bin;
+    hp_visc = ArtBulkViscConst; hp_contrast = DensityContrastLimit; hp_di = DensityIndependentSphOn;
+    set_hydro_params(NULL);
+    force_tree_calc_moments(&Tree, &dd);
+    ActiveParticles act = init_empty_active_particles(PartManager);
+    DriftKickTimes kick = {0};
+    Cosmology CP = {0};
+    const double t0 = omp_get_wtime();
+    hydro_force(&act, atime, &sph_pred, kick, &CP, &Tree);
+    t_hydro = omp_get_wtime() - t0;
+    for(int64_t i = 0; i < n; i++) {
+        for(int k = 0; k < 3; k++) acc_out[3 * i + k] = SPHP(i).HydroAccel[k];
+        dtentropy_out[i] = SPHP(i).DtEntropy; maxsig_out[i] = SPHP(i).MaxSignalVel;
+    }
+    slots_free_sph_pred_data(&sph_pred);
+    return 0;
+}
+void ref_sph_timings(double *dens_s, double *hydro_s) { *dens_s = t_density; *hydro_s = t_hydro; }
 
 void ref_shutdown(void) { free_all(); }

@@ -29,6 +29,8 @@ typedef ptrdiff_t MPI_Aint;
 #define MPI_UNSIGNED_LONG 8
 #define MPI_LONG_LONG 8
 #define MPI_DOUBLE 8
+#define MPI_INT64_T 8
+#define MPI_UINT64_T 8
 #define MPI_DATATYPE_NULL 0
 #define MPI_SUM 1
 #define MPI_MAX 2
