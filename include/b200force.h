@@ -188,6 +188,49 @@ int b200_force_step_aos(b200_ctx *ctx, void *particles, int64_t n,
                         const b200_particle_layout *layout,
                         const b200_gravshort_params *par);
 
+/* ---- SPH density and hydro force -----------------------------------------------
+ * b200_density     replaces density()     (libgadget/density.h:52, density.c:234-355)
+ * b200_hydro_force replaces hydro_force() (libgadget/hydra.h:10,  hydra.c:153-245)
+ * for a synchronised step: every gas particle on the same time bin, so the
+ * kick/drift factors of kick_factor_data (density.c:114-132) and drifts[]
+ * (hydra.c:178-186) are scalars.  Call order as run.c:466-489:
+ * b200_tree_build(mask = 1: gas) -> b200_sph_set_gas -> b200_density ->
+ * b200_hydro_force.  Parameters mirror struct density_params (density.h:10-28),
+ * struct hydro_params (hydra.c:26-35). */
+typedef struct b200_sph_params {
+    int32_t KernelType;               /* DensityKernelType: 1 cubic, 2 quintic, 4 quartic (densitykernel.h:20-24) */
+    int32_t DensityIndependentSphOn;
+    double DensityResolutionEta, MaxNumNgbDeviation;
+    double MinGasHsml;                /* absolute: MinGasHsmlFractional * softening (density.c:265) */
+    double ArtBulkViscConst, DensityContrastLimit;
+    double gravkick, hydrokick, pmkick;   /* gravkicks[bin], hydrokicks[bin], FgravkickB */
+    double dloga_pred;                    /* dloga in SPH_EntVarPred (density.c:74) */
+    double drift;                         /* drifts[bin] (hydra.c:185) */
+    double dloga_bin;                     /* get_dloga_for_bin (hydra.c:271,463) */
+    double atime, hubble;                 /* scale factor and hubble_function(CP, atime) (hydra.c:219-223) */
+} b200_sph_params;
+
+/* Per-particle gas state, host arrays indexed by particle index (entries of
+ * non-gas particles are ignored): Vel[n][3], Hsml[n] (required), Entropy[n],
+ * DtEntropy[n], FullTreeGravAccel[n][3], GravPM[n][3], HydroAccel[n][3]; NULL = 0
+ * (Entropy NULL = 1).  P[].Vel/Hsml, SphP[].Entropy/DtEntropy/HydroAccel of the
+ * reference (partmanager.h:40-120, slotsmanager.h:93-129). */
+int b200_sph_set_gas(b200_ctx *ctx, const double *vel, const double *hsml, const double *entropy,
+                     const double *dtentropy, const double *fulltreeacc, const double *gravpm,
+                     const double *hydroaccel);
+/* Outputs (host, [n], any may be NULL): Hsml, Density, EgyWtDensity,
+ * DhsmlEgyDensityFactor, DivVel, CurlVel, DtHsml, NumNgb (kernel-weighted),
+ * ninteract = particles with r^2 <= h^2 in the last pass (treewalk.c:1233-1240),
+ * niter = passes used. */
+int b200_density(b200_ctx *ctx, const b200_sph_params *par, int update_hsml, int DoEgyDensity,
+                 double *hsml, double *density, double *egywtdensity, double *dhsmlfac,
+                 double *divvel, double *curlvel, double *dthsml, double *numngb,
+                 int32_t *ninteract, int32_t *niter);
+/* HydroAccel[n][3], DtEntropy[n], MaxSignalVel[n], ninteract = candidates from
+ * opened leaves (treewalk.c:1056-1143). */
+int b200_hydro_force(b200_ctx *ctx, const b200_sph_params *par, double *hydroaccel, double *dtentropy,
+                     double *maxsignalvel, int32_t *ninteract);
+
 /* ---- multi-GPU building blocks (one process + one context per GPU; the host
  * harness moves the buffers between ranks with NCCL) --------------------------
  *
@@ -229,6 +272,7 @@ typedef struct b200_timings {
     double tree_keys, tree_sort, tree_nodes, tree_moments, tree_total;
     double walk, walk_post;
     double h2d, d2h;
+    double sph_density, sph_hydro;
 } b200_timings;
 int b200_get_timings(const b200_ctx *ctx, b200_timings *t);
 

@@ -42,10 +42,32 @@ class GravShortParams(C.Structure):
                 ("Rcut", C.c_double), ("GravitySoftening", C.c_double), ("rho0", C.c_double)]
 
 
+class SphParams(C.Structure):
+    """struct density_params (density.h:10-28) + struct hydro_params (hydra.c:26-35) + time factors."""
+    _fields_ = [("KernelType", C.c_int32), ("DensityIndependentSphOn", C.c_int32),
+                ("DensityResolutionEta", C.c_double), ("MaxNumNgbDeviation", C.c_double), ("MinGasHsml", C.c_double),
+                ("ArtBulkViscConst", C.c_double), ("DensityContrastLimit", C.c_double),
+                ("gravkick", C.c_double), ("hydrokick", C.c_double), ("pmkick", C.c_double),
+                ("dloga_pred", C.c_double), ("drift", C.c_double), ("dloga_bin", C.c_double),
+                ("atime", C.c_double), ("hubble", C.c_double)]
+
+
+SPH_DEFAULTS = dict(KernelType=2, DensityIndependentSphOn=1, DensityResolutionEta=1.0, MaxNumNgbDeviation=2.0,
+                    MinGasHsml=0.0, ArtBulkViscConst=0.75, DensityContrastLimit=100.0, gravkick=0.0, hydrokick=0.0,
+                    pmkick=0.0, dloga_pred=0.0, drift=0.0, dloga_bin=0.0, atime=1.0, hubble=0.1)
+
+
+def sph_params(**kw):
+    d = dict(SPH_DEFAULTS)
+    d.update(kw)
+    return SphParams(**d)
+
+
 class Timings(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "pm_deposit", "pm_fft_forward", "pm_transfer", "pm_fft_inverse", "pm_gradient", "pm_readout", "pm_total",
-        "tree_keys", "tree_sort", "tree_nodes", "tree_moments", "tree_total", "walk", "walk_post", "h2d", "d2h")]
+        "tree_keys", "tree_sort", "tree_nodes", "tree_moments", "tree_total", "walk", "walk_post", "h2d", "d2h",
+        "sph_density", "sph_hydro")]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -72,6 +94,7 @@ EXPORTED = [
     "b200_get_timings", "b200_stream",
     "b200_tree_top_get_dev", "b200_tree_top_set_dev", "b200_pmslab_init", "b200_pmslab_deposit",
     "b200_pmslab_fft2d", "b200_pmslab_fft1d", "b200_pmslab_transfer", "b200_pmslab_readout_dev",
+    "b200_sph_set_gas", "b200_density", "b200_hydro_force",
 ]
 
 
@@ -225,6 +248,30 @@ class Engine:
         self._ck(self.L.b200_grav_short_tree_dev(self.ctx, C.byref(p), C.c_void_p(active_ptr) if active_ptr else None, C.c_int64(nactive),
                                                  C.c_void_p(acc_ptr) if acc_ptr else None,
                                                  C.c_void_p(pot_ptr) if pot_ptr else None, None))
+
+    # -- SPH: density / hydro_force ------------------------------------------------
+    def sph_set_gas(self, hsml, vel=None, entropy=None, dtentropy=None, fullacc=None, gravpm=None, hydroacc=None):
+        f8 = lambda a: _c(a, np.float64)
+        arrs = [f8(vel), f8(hsml), f8(entropy), f8(dtentropy), f8(fullacc), f8(gravpm), f8(hydroacc)]
+        self._keep_sph = arrs
+        self._ck(self.L.b200_sph_set_gas(self.ctx, *[_p(a) for a in arrs]))
+
+    def density(self, sp, update_hsml=1, DoEgyDensity=0):
+        n = self.n
+        out = dict(hsml=np.zeros(n), density=np.zeros(n), egywtdensity=np.zeros(n), dhsmlfac=np.zeros(n), divvel=np.zeros(n),
+                   curlvel=np.zeros(n), dthsml=np.zeros(n), numngb=np.zeros(n), ninteract=np.zeros(n, np.int32),
+                   niter=np.zeros(n, np.int32))
+        self._ck(self.L.b200_density(self.ctx, C.byref(sp), C.c_int(update_hsml), C.c_int(DoEgyDensity),
+                                     *[_p(out[k]) for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel",
+                                                            "dthsml", "numngb", "ninteract", "niter")]))
+        return out
+
+    def hydro_force(self, sp):
+        n = self.n
+        out = dict(acc=np.zeros((n, 3)), dtentropy=np.zeros(n), maxsignalvel=np.zeros(n), ninteract=np.zeros(n, np.int32))
+        self._ck(self.L.b200_hydro_force(self.ctx, C.byref(sp), _p(out["acc"]), _p(out["dtentropy"]), _p(out["maxsignalvel"]),
+                                         _p(out["ninteract"])))
+        return out
 
     # -- multi-GPU building blocks ------------------------------------------------
     def tree_top_get_dev(self, level, ptr):

@@ -137,6 +137,7 @@ static int collect_timings(Engine *E)
     t.tree_total = t.tree_keys + t.tree_sort + t.tree_nodes + t.tree_moments;
     t.walk = timer_ms(E, T_WALK); t.walk_post = timer_ms(E, T_WALK_POST);
     t.h2d = timer_ms(E, T_H2D); t.d2h = timer_ms(E, T_D2H);
+    t.sph_density = timer_ms(E, T_SPH_DENSITY); t.sph_hydro = timer_ms(E, T_SPH_HYDRO);
     return 0;
 }
 
@@ -430,6 +431,58 @@ int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_l
     timer_start(E, T_D2H);
     CK(cudaMemcpyAsync(P, E->aos.p, m * L.stride, cudaMemcpyDeviceToHost, E->stream));
     timer_stop(E, T_D2H);
+    CK(cudaStreamSynchronize(E->stream));
+    return collect_timings(E);
+}
+
+int b200_sph_set_gas(b200_ctx *ctx, const double *vel, const double *hsml, const double *entropy, const double *dtentropy,
+                     const double *fulltreeacc, const double *gravpm, const double *hydroaccel)
+{
+    ENTER(ctx);
+    return sph_set_gas(E, vel, hsml, entropy, dtentropy, fulltreeacc, gravpm, hydroaccel);
+}
+
+static int d2h_opt(Engine *E, void *dst, const void *src, size_t bytes)
+{
+    if(dst && bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, E->stream));
+    return 0;
+}
+
+int b200_density(b200_ctx *ctx, const b200_sph_params *par, int update_hsml, int DoEgyDensity,
+                 double *hsml, double *density, double *egywtdensity, double *dhsmlfac, double *divvel, double *curlvel,
+                 double *dthsml, double *numngb, int32_t *ninteract, int32_t *niter)
+{
+    ENTER(ctx);
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->s_outi.ensure(n)); CK(E->s_outi2.ensure(n));
+    CK(cudaMemsetAsync(E->s_outi.p, 0, n * sizeof(int), E->stream));
+    CK(cudaMemsetAsync(E->s_outi2.p, 0, n * sizeof(int), E->stream));
+    if(int rc = sph_density(E, par, update_hsml, DoEgyDensity, E->s_outi.p, E->s_outi2.p)) return rc;
+    const size_t b = (size_t) E->n * sizeof(double);
+    if(d2h_opt(E, hsml, E->s_hsml.p, b) || d2h_opt(E, density, E->s_density.p, b) || d2h_opt(E, egywtdensity, E->s_egy.p, b) ||
+       d2h_opt(E, dhsmlfac, E->s_dhsmlfac.p, b) || d2h_opt(E, divvel, E->s_divvel.p, b) || d2h_opt(E, curlvel, E->s_curlvel.p, b) ||
+       d2h_opt(E, dthsml, E->s_dthsml.p, b) || d2h_opt(E, numngb, E->s_numngb.p, b) ||
+       d2h_opt(E, ninteract, E->s_outi.p, (size_t) E->n * sizeof(int)) || d2h_opt(E, niter, E->s_outi2.p, (size_t) E->n * sizeof(int)))
+        return 1;
+    CK(cudaStreamSynchronize(E->stream));
+    return collect_timings(E);
+}
+
+int b200_hydro_force(b200_ctx *ctx, const b200_sph_params *par, double *hydroaccel, double *dtentropy, double *maxsignalvel,
+                     int32_t *ninteract)
+{
+    ENTER(ctx);
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->s_out3.ensure(3 * n)); CK(E->s_out1a.ensure(n)); CK(E->s_out1b.ensure(n)); CK(E->s_outi.ensure(n));
+    CK(cudaMemsetAsync(E->s_out3.p, 0, 3 * n * sizeof(double), E->stream));
+    CK(cudaMemsetAsync(E->s_out1a.p, 0, n * sizeof(double), E->stream));
+    CK(cudaMemsetAsync(E->s_out1b.p, 0, n * sizeof(double), E->stream));
+    CK(cudaMemsetAsync(E->s_outi.p, 0, n * sizeof(int), E->stream));
+    if(int rc = sph_hydro(E, par, E->s_out3.p, E->s_out1a.p, E->s_out1b.p, E->s_outi.p)) return rc;
+    const size_t b = (size_t) E->n * sizeof(double);
+    if(d2h_opt(E, hydroaccel, E->s_out3.p, 3 * b) || d2h_opt(E, dtentropy, E->s_out1a.p, b) || d2h_opt(E, maxsignalvel, E->s_out1b.p, b) ||
+       d2h_opt(E, ninteract, E->s_outi.p, (size_t) E->n * sizeof(int)))
+        return 1;
     CK(cudaStreamSynchronize(E->stream));
     return collect_timings(E);
 }

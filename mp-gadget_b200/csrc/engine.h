@@ -34,7 +34,7 @@ struct Timer {
 enum TimerId {
     T_PM_DEPOSIT, T_PM_FFT_FWD, T_PM_TRANSFER, T_PM_FFT_INV, T_PM_GRADIENT, T_PM_READOUT,
     T_TREE_KEYS, T_TREE_SORT, T_TREE_NODES, T_TREE_MOMENTS,
-    T_WALK, T_WALK_POST, T_H2D, T_D2H, T_COUNT
+    T_WALK, T_WALK_POST, T_H2D, T_D2H, T_SPH_DENSITY, T_SPH_HYDRO, T_COUNT
 };
 
 // Node record used by the walk, DFS order.  A,B are 32-byte rows so that one
@@ -88,6 +88,7 @@ struct Engine {
     int tree_maxdepth = 0;
     int tree_overfull = 0;
     int tree_topdepth = 0;
+    std::vector<int> tree_lvl;  // BFS level offsets of the current tree
     bool tree_full = false;     // contains every particle (full_particle_tree_flag)
     DevBuf<unsigned long long> keys, keys_alt;
     DevBuf<int> sidx, sidx_alt;   // sorted -> original index
@@ -104,6 +105,16 @@ struct Engine {
     DevBuf<int> nodeK;          // [nn][8] DFS positions of the children (-1 = none)
     DevBuf<double> nodeH;       // [nn] hmax
     DevBuf<int> scratch_i;      // small device scalars
+
+    // ---- SPH (original index order unless noted) ----
+    DevBuf<double> s_vel, s_hsml, s_entropy, s_dtentropy, s_fullacc, s_gravpm, s_hydroacc;
+    bool s_have[7] = {false, false, false, false, false, false, false};
+    DevBuf<double> s_velpred, s_evp, s_density, s_egy, s_dhsmlfac, s_divvel, s_curlvel, s_dthsml, s_numngb;
+    DevBuf<double> s_svel, s_hA, s_hB;      // curve order: double4 rows
+    DevBuf<double> s_out3, s_out1a, s_out1b;
+    DevBuf<int> s_outi, s_outi2;
+    bool sph_density_done = false;
+    int sph_DoEgy = 0;
 
     // ---- walk ----
     DevBuf<int> targets;        // walk target list (original indices)
@@ -153,6 +164,12 @@ int pmslab_fft2d(Engine *E, int inverse);
 int pmslab_fft1d(Engine *E, int inverse);
 int pmslab_transfer(Engine *E);
 int pmslab_readout(Engine *E, int64_t n_own, double *d_gravpm, double *d_pot);
+
+// SPH (sph.cu)
+int sph_set_gas(Engine *E, const double *vel, const double *hsml, const double *entropy, const double *dtentropy,
+                const double *fullacc, const double *gravpm, const double *hydroacc);
+int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy, int *d_ninteract, int *d_niter);
+int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte, double *d_maxsig, int *d_ninteract);
 
 // walk (tree_walk.cu)
 int walk_init_tables(Engine *E);

@@ -381,6 +381,8 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
     E->tree_overfull = overfull;
     E->tree_full = (d_active == nullptr);
     E->tree_topdepth = toplevel_depth;
+    E->tree_lvl = lvl;
+    E->sph_density_done = false;
     if(info) {
         double root[4];
         CK(cudaMemcpyAsync(root, E->nodeA.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, E->stream));

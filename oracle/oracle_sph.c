@@ -377,8 +377,9 @@ int oracle_hydro(const oracle_tree *t, const double *pos, const float *mass, con
                     visc = 0.25 * sp->ArtBulkViscConst * vs * (-mu_ij) / rho_ij * (F1 + f2);
                     const double dloga = 2 * sp->dloga_bin;            /* 2*max(I->dloga, dloga_j), one bin */
                     if(dloga > 0 && (dwk_i + dwk_j) < 0) {
-                        if((mass[i] + mass[o]) > 0) {
-                            const double lim = 0.5 * fac_vsic_fix * vdotr2 / (0.5 * (mass[i] + mass[o]) * (dwk_i + dwk_j) * r * dloga);
+                        const double msum = (double) mass[i] + (double) mass[o];      /* I->Mass is MyFloat = double */
+                        if(msum > 0) {
+                            const double lim = 0.5 * fac_vsic_fix * vdotr2 / (0.5 * msum * (dwk_i + dwk_j) * r * dloga);
                             if(lim < visc) visc = lim;
                         }
                     }
