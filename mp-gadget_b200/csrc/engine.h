@@ -48,6 +48,8 @@ struct NodeAux {           // int4
 
 struct SlabPM;
 
+#define B200_SPART_PAD 16     // massless far-away rows behind spart[np) (tree_walk.cu pair loop)
+
 struct Engine {
     int device = 0;
     cudaStream_t stream = nullptr;

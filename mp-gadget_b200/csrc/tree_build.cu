@@ -171,10 +171,11 @@ k_tree_leaf_order(int nn, const int *__restrict__ b_start, const int *__restrict
 
 __global__ void __launch_bounds__(256)
 k_tree_gather(const double *__restrict__ pos, const float *__restrict__ mass,
-              const int *__restrict__ sidx, int np, double4 *__restrict__ spart)
+              const int *__restrict__ sidx, int np, double far, double4 *__restrict__ spart)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if(j >= np) return;
+    if(j >= np + B200_SPART_PAD) return;
+    if(j >= np) { spart[j] = make_double4(far, far, far, 0.0); return; }
     const int64_t i = sidx[j];
     spart[j] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], (double) mass[i]);
 }
@@ -342,11 +343,11 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
     timer_start(E, T_TREE_MOMENTS);
     k_tree_leaf_order<<<(nn + 127) / 128, 128, 0, E->stream>>>(nn, E->b_start.p, E->b_count.p, E->b_nchild.p, E->sidx.p);
     CKL(E);
-    CK(E->spart.ensure(4 * (size_t) (np > 0 ? np : 1)));
-    if(np > 0) {
-        k_tree_gather<<<(np + 255) / 256, 256, 0, E->stream>>>(E->pos.p, E->mass.p, E->sidx.p, np, (double4 *) E->spart.p);
-        CKL(E);
-    }
+    // 16 far-away massless rows follow the particles: the pair loop of the walk reads
+    // whole 8-row pieces and empty padding pieces without bounds checks.
+    CK(E->spart.ensure(4 * (size_t) (np + B200_SPART_PAD)));
+    k_tree_gather<<<(np + B200_SPART_PAD + 255) / 256, 256, 0, E->stream>>>(E->pos.p, E->mass.p, E->sidx.p, np, 1e3 * Box, (double4 *) E->spart.p);
+    CKL(E);
     // b_mom lives in nodeH's neighbour buffer: reuse keys_alt (np*8 bytes is too small) -> own buffer
     CK(E->nodeA.ensure(4 * (size_t) nn)); CK(E->nodeB.ensure(4 * (size_t) nn));
     CK(E->nodeC.ensure(4 * (size_t) nn)); CK(E->nodeF.ensure(nn)); CK(E->nodeH.ensure(nn));

@@ -27,6 +27,7 @@
 #include "engine.h"
 #include "../data/shortrange_table.h"
 #include <math.h>
+#include <stdlib.h>
 #include <cub/device/device_select.cuh>
 
 namespace b200 {
@@ -38,6 +39,8 @@ struct WalkPar {
     double wrap_lo, wrap_hi;    // targets inside [wrap_lo, wrap_hi]^3 never need the periodic wrap
     double ErrTol, G;
     double h, h2, hinv, h3inv;
+    double h2s;                 // max(h2, smallest normal): pairs with r2 < h2s take the general path
+    int sentinel;               // first of the >= 16 far-away massless rows behind spart[np)
     double inv_cell_dx;         // 1 / (cellsize * table spacing)
     int usebh;
     int ntargets;
@@ -51,8 +54,9 @@ __device__ __forceinline__ double nearest(double x, double box, double halfbox) 
 // apply_accn_to_output (gravshort-tree.c:158-193) with the tabulated window of
 // grav_apply_short_range_window (gravity.c:54-66).  tab[t] = {T[t], T[t+1]-T[t],
 // Tpot[t], Tpot[t+1]-Tpot[t]} so that the linear interpolation is one FMA.
+template <class PP>
 __device__ __forceinline__ void monopole(double dx, double dy, double dz, double r2, double m,
-                                         const WalkPar &P, const double4 *__restrict__ tab,
+                                         const PP &P, const double4 *__restrict__ tab,
                                          double &ax, double &ay, double &az, double &pot)
 {
     double r, fac, facpot;
@@ -151,71 +155,95 @@ __device__ __forceinline__ int classify(const double4 &A, const double4 &B, doub
     return 1;
 }
 
+// 1/sqrt(x) for normal positive x: the hardware seed (MUFU.RSQ64H, ~2^-22) followed by one
+// third-order correction y(1 + e/2 + 3e^2/8), e = 1 - x y^2; relative error < 2^-52.  Without
+// the zero/denormal/infinity fix-up branch of rsqrt(): the callers never pass those.
+__device__ __forceinline__ double rsqrt_pos(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(e, 0.375, 0.5), y);
+}
+
 // Newtonian-regime pair with the window applied, branch-free (the caller
-// guarantees r2 >= h^2 or discards the result): two of these interleave in
-// straight-line code.
+// guarantees r2 >= h^2 > 0 or passes m = 0, r2 = 1).  Row NTAB-1 of `tab` is all
+// zero, so a pair beyond the table (gravity.c:60-61: contribution dropped) needs
+// no select, only the index clamp.
 __device__ __forceinline__ void pair_fast(double dx, double dy, double dz, double r2, double m,
                                           const WalkPar &P, const double4 *__restrict__ tab,
                                           double &ax, double &ay, double &az, double &pot)
 {
-    const double rinv = rsqrt(r2);
+    const double rinv = rsqrt_pos(r2);
     const double r = r2 * rinv;
     const double mr = m * rinv;
     const double ti = r * P.inv_cell_dx;
-    int t = (int) ti;
-    const bool beyond = t >= B200_SR_NTAB - 1;          // gravity.c:60-61: contribution dropped
-    t = beyond ? B200_SR_NTAB - 2 : t;
+    const int t = min((int) ti, B200_SR_NTAB - 1);
     const double w1 = ti - (double) t;
     const double4 e = tab[t];
-    double wf = fma(w1, e.y, e.x), wp = fma(w1, e.w, e.z);
-    wf = beyond ? 0.0 : wf; wp = beyond ? 0.0 : wp;
+    const double wf = fma(w1, e.y, e.x), wp = fma(w1, e.w, e.z);
     const double fac = mr * rinv * rinv * wf;
     ax = fma(dx, fac, ax); ay = fma(dy, fac, ay); az = fma(dz, fac, az);
     pot = fma(-mr, wp, pot);
 }
 
+// One source row of a (pstart, count) leaf piece for this lane's slot.  Slots
+// past the count read the rows that follow (spart is padded with far-away
+// massless rows) and are neutralised through the mass.
+struct SrcRow { double4 q; int cnt; };
+
+__device__ __forceinline__ SrcRow fetch_row(const int2 *__restrict__ s_tl, int idx, int slot,
+                                            const double4 *__restrict__ spart)
+{
+    SrcRow r;
+    const int2 lf = s_tl[idx];
+    r.q = spart[lf.x + slot];
+    r.cnt = lf.y;
+    return r;
+}
+
 template <bool WRAP>
-__device__ __forceinline__ void load_pair(const int2 *__restrict__ s_tl, int idx, int nt, int slot,
-                                          const double4 *__restrict__ spart, const WalkPar &P,
-                                          double tx, double ty, double tz,
+__device__ __forceinline__ void row_delta(const SrcRow &s, int slot, const WalkPar &P, double tx, double ty, double tz,
                                           double &qx, double &qy, double &qz, double &q2, double &qm)
 {
-    int2 lf = make_int2(0, 0);
-    if(idx < nt) lf = s_tl[idx];
-    const bool v = slot < lf.y;
-    double4 q = make_double4(0, 0, 0, 0);
-    if(v) q = spart[lf.x + slot];
-    qx = q.x - tx; qy = q.y - ty; qz = q.z - tz;
+    qx = s.q.x - tx; qy = s.q.y - ty; qz = s.q.z - tz;
     if(WRAP) {
         qx = nearest(qx, P.box, P.halfbox); qy = nearest(qy, P.box, P.halfbox); qz = nearest(qz, P.box, P.halfbox);
     }
-    qm = v ? q.w : 0.0;
-    qx = v ? qx : 1.0;            // a harmless massless dummy at unit distance
-    qy = v ? qy : 0.0; qz = v ? qz : 0.0;
+    qm = slot < s.cnt ? s.q.w : 0.0;
     q2 = fma(qz, qz, fma(qy, qy, qx * qx));
 }
 
-// s_tl holds the (pstart, count<=8) leaf pieces target t opened.  Each step the
-// four 8-lane groups take two leaves each (8 leaves per step), one particle per
-// lane per leaf, in branch-free interleaved code; pairs inside the softening
-// radius (the target itself among them) are rare and take the general path.
+// s_tl holds the (pstart, count<=8) leaf pieces target t opened, padded with
+// empty pieces to a multiple of 8.  Each step the four 8-lane groups take two pieces each (8 per step),
+// one particle per lane per piece, in branch-free interleaved code; pairs inside the softening radius (the
+// target itself among them) are rare and take the general path.
 template <bool WRAP>
-__device__ __forceinline__ void pair_sum(const int2 *__restrict__ s_tl, int nt, int g, int slot,
+__device__ __forceinline__ void pair_step(const SrcRow &ca, const SrcRow &cb, int slot, const WalkPar &P,
+                                          const double4 *__restrict__ tab, double tx, double ty, double tz,
+                                          double &sx, double &sy, double &sz, double &sp)
+{
+    double ax_, ay_, az_, a2, am, bx_, by_, bz_, b2, bm;
+    row_delta<WRAP>(ca, slot, P, tx, ty, tz, ax_, ay_, az_, a2, am);
+    row_delta<WRAP>(cb, slot, P, tx, ty, tz, bx_, by_, bz_, b2, bm);
+    const bool softa = !(a2 >= P.h2s), softb = !(b2 >= P.h2s);
+    if(__any_sync(0xffffffffu, softa || softb)) {
+        if(softa) { monopole(ax_, ay_, az_, a2, am, P, tab, sx, sy, sz, sp); am = 0.0; a2 = 1.0; }
+        if(softb) { monopole(bx_, by_, bz_, b2, bm, P, tab, sx, sy, sz, sp); bm = 0.0; b2 = 1.0; }
+    }
+    pair_fast(ax_, ay_, az_, a2, am, P, tab, sx, sy, sz, sp);
+    pair_fast(bx_, by_, bz_, b2, bm, P, tab, sx, sy, sz, sp);
+}
+
+template <bool WRAP>
+__device__ __forceinline__ void pair_sum(const int2 *__restrict__ s_tl, int ntpad, int g, int slot,
                                          const double4 *__restrict__ spart, const WalkPar &P,
                                          const double4 *__restrict__ tab, double tx, double ty, double tz,
                                          double &sx, double &sy, double &sz, double &sp)
 {
-    for(int i = 0; i < nt; i += 8) {
-        double ax_, ay_, az_, a2, am, bx_, by_, bz_, b2, bm;
-        load_pair<WRAP>(s_tl, i + g, nt, slot, spart, P, tx, ty, tz, ax_, ay_, az_, a2, am);
-        load_pair<WRAP>(s_tl, i + 4 + g, nt, slot, spart, P, tx, ty, tz, bx_, by_, bz_, b2, bm);
-        const bool softa = a2 < P.h2, softb = b2 < P.h2;
-        if(__any_sync(0xffffffffu, softa || softb)) {
-            if(softa) { monopole(ax_, ay_, az_, a2, am, P, tab, sx, sy, sz, sp); am = 0.0; a2 = 1.0; }
-            if(softb) { monopole(bx_, by_, bz_, b2, bm, P, tab, sx, sy, sz, sp); bm = 0.0; b2 = 1.0; }
-        }
-        pair_fast(ax_, ay_, az_, a2, am, P, tab, sx, sy, sz, sp);
-        pair_fast(bx_, by_, bz_, b2, bm, P, tab, sx, sy, sz, sp);
+    for(int i = 0; i < ntpad; i += 8) {
+        const SrcRow ca = fetch_row(s_tl, i + g, slot, spart), cb = fetch_row(s_tl, i + 4 + g, slot, spart);
+        pair_step<WRAP>(ca, cb, slot, P, tab, tx, ty, tz, sx, sy, sz, sp);
     }
 }
 
@@ -223,13 +251,14 @@ __device__ __forceinline__ void pair_sum(const int2 *__restrict__ s_tl, int nt, 
 // warp, compact the leaves t opened into a dense list, then the lanes take
 // 4 leaves x 8 particle slots per step (gravshort-tree.c:364-374 sums the same
 // pairs) and one reduction hands the sums to lane t.
-__device__ __forceinline__ void eval_leaf_list(const int2 *__restrict__ s_leaf, const unsigned *__restrict__ s_mask,
+// Returns this lane's increments {ax, ay, az, pot}.
+__device__ __forceinline__ double4 eval_leaf_list(const int2 *__restrict__ s_leaf, const unsigned *__restrict__ s_mask,
                                                int2 *__restrict__ s_tl, int nlist, unsigned anymask,
                                                const double4 *__restrict__ spart,
                                                const WalkPar &P, const double4 *__restrict__ tab, int lane,
-                                               double px, double py, double pz,
-                                               double &ax, double &ay, double &az, double &pot)
+                                               double px, double py, double pz)
 {
+    double ax = 0, ay = 0, az = 0, pot = 0;
     const int g = lane >> 3, slot = lane & 7;
     const unsigned ltmask = (1u << lane) - 1u;
     for(int t = 0; t < 32; t++) {
@@ -245,6 +274,8 @@ __device__ __forceinline__ void eval_leaf_list(const int2 *__restrict__ s_leaf, 
             if(w) s_tl[nt + __popc(bal & ltmask)] = s_leaf[li];
             nt += __popc(bal);
         }
+        const int ntpad = (nt + 7) & ~7;
+        if(lane < ntpad - nt) s_tl[nt + lane] = make_int2(P.sentinel, 0);          // <= 7 empty pieces
         __syncwarp();
         double sx = 0, sy = 0, sz = 0, sp = 0;
         // No periodic wrap is needed when the target is farther than the reach of
@@ -252,12 +283,13 @@ __device__ __forceinline__ void eval_leaf_list(const int2 *__restrict__ s_leaf, 
         // beyond the table on both sides of the wrap and contributes nothing.
         const bool central = tx >= P.wrap_lo && tx <= P.wrap_hi && ty >= P.wrap_lo && ty <= P.wrap_hi &&
                              tz >= P.wrap_lo && tz <= P.wrap_hi;
-        if(central) pair_sum<false>(s_tl, nt, g, slot, spart, P, tab, tx, ty, tz, sx, sy, sz, sp);
-        else pair_sum<true>(s_tl, nt, g, slot, spart, P, tab, tx, ty, tz, sx, sy, sz, sp);
+        if(central) pair_sum<false>(s_tl, ntpad, g, slot, spart, P, tab, tx, ty, tz, sx, sy, sz, sp);
+        else pair_sum<true>(s_tl, ntpad, g, slot, spart, P, tab, tx, ty, tz, sx, sy, sz, sp);
         sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); sp = warp_sum(sp);
         if(lane == t) { ax += sx; ay += sy; az += sz; pot += sp; }
         __syncwarp();
     }
+    return make_double4(ax, ay, az, pot);
 }
 
 // Staged node rows of the current batch (one entry per lane).
@@ -268,7 +300,7 @@ struct BatchEntry {
                       // flags (bit0: leaf, bit1: rejected for all lanes by the bounding-box test)
 };
 
-#define WALK_STACK 384        // (node, mask) entries per warp
+#define WALK_STACK 344        // (node, mask) entries per warp
 #define WALK_RESERVE 154      // head-room so that single pops (<= 7 net pushes each, depth <= 21+) never overflow
 
 template <bool COUNT>
@@ -283,7 +315,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
 {
     __shared__ double4 tab[B200_SR_NTAB];
     __shared__ int2 s_leaf_all[WALK_WARPS][LIST_CAP];
-    __shared__ int2 s_tl_all[WALK_WARPS][LIST_CAP];
+    __shared__ int2 s_tl_all[WALK_WARPS][LIST_CAP + 16];
     __shared__ unsigned s_mask_all[WALK_WARPS][LIST_CAP];
     __shared__ int s_stk_node_all[WALK_WARPS][WALK_STACK];
     __shared__ unsigned s_stk_mask_all[WALK_WARPS][WALK_STACK];
@@ -291,7 +323,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
     for(int k = threadIdx.x; k < B200_SR_NTAB; k += blockDim.x) {
         const int k1 = k + 1 < B200_SR_NTAB ? k + 1 : k;
         const double f0 = gtab[k], f1 = gtab[k1], p0 = gtab[B200_SR_NTAB + k], p1 = gtab[B200_SR_NTAB + k1];
-        tab[k] = make_double4(f0, f1 - f0, p0, p1 - p0);
+        tab[k] = k + 1 < B200_SR_NTAB ? make_double4(f0, f1 - f0, p0, p1 - p0) : make_double4(0, 0, 0, 0);
     }
     __syncthreads();
     const int wib = threadIdx.x >> 5;
@@ -341,7 +373,10 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
     __syncwarp();
     while(true) {
         if(sp == 0 || nlist > LIST_CAP - 32) {      // single flush site (warp-uniform)
-            if(nlist > 0) eval_leaf_list(s_leaf, s_mask, s_tl, nlist, anymask, spart, P, tab, lane, px, py, pz, ax, ay, az, pot);
+            if(nlist > 0) {
+                const double4 d = eval_leaf_list(s_leaf, s_mask, s_tl, nlist, anymask, spart, P, tab, lane, px, py, pz);
+                ax += d.x; ay += d.y; az += d.z; pot += d.w;
+            }
             __syncwarp();
             nlist = 0; anymask = 0;
             if(sp == 0) break;
@@ -407,7 +442,8 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
                 // pieces of <= 8 particles (only leaves at the key-depth limit hold more)
                 for(int o = 0; o < li.y || o == 0; o += 8) {
                     if(nlist == LIST_CAP) {          // only reachable through such oversized leaves
-                        eval_leaf_list(s_leaf, s_mask, s_tl, nlist, anymask, spart, P, tab, lane, px, py, pz, ax, ay, az, pot);
+                        const double4 d = eval_leaf_list(s_leaf, s_mask, s_tl, nlist, anymask, spart, P, tab, lane, px, py, pz);
+                        ax += d.x; ay += d.y; az += d.z; pot += d.w;
                         __syncwarp();
                         nlist = 0;
                     }
@@ -505,6 +541,8 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
     P.ErrTol = par->ErrTolForceAcc; P.G = E->G;
     P.h = 2.8 * par->GravitySoftening;                              // FORCE_SOFTENING :37-41
     P.h2 = P.h * P.h; P.hinv = 1.0 / P.h; P.h3inv = 1.0 / P.h / P.h / P.h;
+    P.h2s = P.h2 > 2.3e-308 ? P.h2 : 2.3e-308;
+    P.sentinel = (int) E->tree_np;
     P.inv_cell_dx = 1.0 / (cellsize * (double) B200_SR_DX);
     {   // reach of the window table: index >= NTAB-1 <=> r >= (NTAB-1)*dx cells = 15 cells (gravity.c:57-61)
         const double reach = 1.001 * (B200_SR_NTAB - 1) * (double) B200_SR_DX * cellsize;
@@ -554,14 +592,12 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
     const int bs = 128;
     const int64_t nwarps = (nt + 31) / 32;
     const unsigned nb = (unsigned) ((nwarps * 32 + bs - 1) / bs);
-    if(d_counts)
-        k_grav_walk<true><<<nb, bs, 0, E->stream>>>((const double4 *) E->nodeA.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p,
-                                                   (const int4 *) E->nodeK.p, (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p,
-                                                   P, E->tree_full ? 1 : 0, cbrtrho0, d_acc, d_pot, (int4 *) d_counts);
-    else
-        k_grav_walk<false><<<nb, bs, 0, E->stream>>>((const double4 *) E->nodeA.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p,
-                                                    (const int4 *) E->nodeK.p, (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p,
-                                                    P, E->tree_full ? 1 : 0, cbrtrho0, d_acc, d_pot, nullptr);
+#define WALK_ARGS (const double4 *) E->nodeA.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, \
+                  (const int4 *) E->nodeK.p, (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p, \
+                  P, E->tree_full ? 1 : 0, cbrtrho0, d_acc, d_pot
+    if(d_counts) k_grav_walk<true><<<nb, bs, 0, E->stream>>>(WALK_ARGS, (int4 *) d_counts);
+    else k_grav_walk<false><<<nb, bs, 0, E->stream>>>(WALK_ARGS, nullptr);
+#undef WALK_ARGS
     CKL(E);
     timer_stop(E, T_WALK);
     return 0;

@@ -1,0 +1,12 @@
+#!/bin/bash
+# quick iteration: GPU parity tests, short bench, optional extra command
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+timeout 600 python bench.py --no-cpu --steps 3 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_quick.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_quick.json').read().strip().splitlines()[-1])
+print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],d['e2e']['ms_per_step'])
+print({k:round(v,2) for k,v in d['phases_ms'].items()})
+PY
+if [ -n "$1" ]; then bash -c "$1"; fi
