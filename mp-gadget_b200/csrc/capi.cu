@@ -2,6 +2,7 @@
 #include "engine.h"
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 
 namespace b200 {
@@ -97,10 +98,10 @@ k_oldacc_from_last(int64_t n, const double *__restrict__ tr, const double *__res
 __global__ void __launch_bounds__(256)
 k_pack_aos(uint8_t *__restrict__ aos, int64_t n, b200_particle_layout L,
            const double *__restrict__ gravpm, const double *__restrict__ treeacc,
-           const double *__restrict__ pot, int full_tree)
+           const double *__restrict__ pot, int full_tree, int64_t first)
 {
-    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= n) return;
+    const int64_t i = first + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= first + n) return;
     uint8_t *r = aos + i * L.stride;
     double *pm = (double *) (r + L.off_gravpm);
     pm[0] = gravpm[3 * i]; pm[1] = gravpm[3 * i + 1]; pm[2] = gravpm[3 * i + 2];
@@ -174,6 +175,7 @@ int b200_ctx_create(b200_ctx **out, int device)
     if(!c) return 5;
     c->e.device = device;
     if(cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 6; }
+    if(cudaStreamCreateWithFlags(&c->e.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->e.stream); delete c; return 6; }
     *out = c;
     return 0;
 }
@@ -195,6 +197,8 @@ void b200_ctx_destroy(b200_ctx *ctx)
     E->nodeF.release(); E->nodeH.release(); E->nodeK.release(); E->scratch_i.release(); E->targets.release(); E->targets_sorted.release(); E->walk_flags.release();
     E->d_acc.release(); E->d_pot.release(); E->d_counts.release(); E->srtab.release();
     for(int i = 0; i < T_COUNT; i++) if(E->timers[i].a) { cudaEventDestroy(E->timers[i].a); cudaEventDestroy(E->timers[i].b); }
+    for(int i = 0; i < 65; i++) if(E->chunk_ev[i]) cudaEventDestroy(E->chunk_ev[i]);
+    cudaStreamDestroy(E->copy_stream);
     cudaStreamDestroy(E->stream);
     delete ctx;
 }
@@ -424,13 +428,44 @@ int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_l
     if(int rc = pm_force(E, E->last_pm_acc.p, nullptr)) return rc;
     // force_tree_full + grav_short_tree (run.c:546-548)
     if(int rc = tree_build(E, E->Box, 63, nullptr, 0, 0, nullptr)) return rc;
-    if(int rc = grav_short_tree(E, par, nullptr, 0, E->last_tree_acc.p, E->d_pot.p, nullptr)) return rc;
     E->have_last_pm = E->have_last_tree = true;
-    k_pack_aos<<<(unsigned) ((n + 255) / 256), 256, 0, E->stream>>>(E->aos.p, n, L, E->last_pm_acc.p, E->last_tree_acc.p, E->d_pot.p, 1);
-    CKL(E);
-    timer_start(E, T_D2H);
-    CK(cudaMemcpyAsync(P, E->aos.p, m * L.stride, cudaMemcpyDeviceToHost, E->stream));
-    timer_stop(E, T_D2H);
+    // The walk is issued in groups of equal particle-index ranges (targets in curve
+    // order inside each group): as soon as a group is done its records are packed and
+    // copied back on the copy stream while the next group is walked, so the write-back
+    // (160 B/particle over PCIe) hides behind the walk.  B200_E2E_CHUNKS overrides.
+    int nchunks = n >= (1 << 20) ? 8 : 1;
+    if(const char *ev = getenv("B200_E2E_CHUNKS")) { nchunks = atoi(ev); if(nchunks < 1) nchunks = 1; if(nchunks > 64) nchunks = 64; }
+    if(nchunks == 1) {
+        if(int rc = grav_short_tree(E, par, nullptr, 0, E->last_tree_acc.p, E->d_pot.p, nullptr)) return rc;
+        k_pack_aos<<<(unsigned) ((n + 255) / 256), 256, 0, E->stream>>>(E->aos.p, n, L, E->last_pm_acc.p, E->last_tree_acc.p, E->d_pot.p, 1, 0);
+        CKL(E);
+        timer_start(E, T_D2H);
+        CK(cudaMemcpyAsync(P, E->aos.p, m * L.stride, cudaMemcpyDeviceToHost, E->stream));
+        timer_stop(E, T_D2H);
+    } else {
+        const int64_t chunk = (n + nchunks - 1) / nchunks;
+        int off[65];
+        if(int rc = walk_chunk_targets(E, nchunks, chunk, off)) return rc;
+        // particles outside the tree (garbage) keep their input record: pack only touches tree members' ranges
+        for(int c = 0; c < nchunks; c++) {
+            const int64_t lo = c * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+            if(hi <= lo) break;
+            const int64_t nc = off[c + 1] - off[c];
+            if(nc > 0)
+                if(int rc = grav_short_tree(E, par, E->targets_sorted.p + off[c], nc, E->last_tree_acc.p, E->d_pot.p, nullptr, true)) return rc;
+            k_pack_aos<<<(unsigned) ((hi - lo + 255) / 256), 256, 0, E->stream>>>(E->aos.p, hi - lo, L, E->last_pm_acc.p, E->last_tree_acc.p, E->d_pot.p, 1, lo);
+            CKL(E);
+            if(c == nchunks - 1 || hi == n) timer_start(E, T_D2H);      // the exposed tail of the write-back
+            if(!E->chunk_ev[c]) CK(cudaEventCreateWithFlags(&E->chunk_ev[c], cudaEventDisableTiming));
+            CK(cudaEventRecord(E->chunk_ev[c], E->stream));
+            CK(cudaStreamWaitEvent(E->copy_stream, E->chunk_ev[c], 0));
+            CK(cudaMemcpyAsync((uint8_t *) P + lo * L.stride, E->aos.p + lo * L.stride, (size_t) (hi - lo) * L.stride, cudaMemcpyDeviceToHost, E->copy_stream));
+        }
+        if(!E->chunk_ev[nchunks]) CK(cudaEventCreateWithFlags(&E->chunk_ev[nchunks], cudaEventDisableTiming));
+        CK(cudaEventRecord(E->chunk_ev[nchunks], E->copy_stream));
+        CK(cudaStreamWaitEvent(E->stream, E->chunk_ev[nchunks], 0));
+        timer_stop(E, T_D2H);
+    }
     CK(cudaStreamSynchronize(E->stream));
     return collect_timings(E);
 }

@@ -53,6 +53,8 @@ struct SlabPM;
 struct Engine {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;     // host<->device copies that overlap kernels on `stream`
+    cudaEvent_t chunk_ev[65] = {};
     std::string err;
     int64_t launches = 0;
 
@@ -175,8 +177,10 @@ int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte,
 
 // walk (tree_walk.cu)
 int walk_init_tables(Engine *E);
+// presorted: d_active is a device list already in tree (curve) order; it is walked as given
 int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *d_active,
-                    int64_t nactive, double *d_acc, double *d_pot, b200_walk_counts *d_counts);
+                    int64_t nactive, double *d_acc, double *d_pot, b200_walk_counts *d_counts, bool presorted = false);
+int walk_chunk_targets(Engine *E, int nchunks, int64_t chunk, int *offsets);
 
 } // namespace b200
 

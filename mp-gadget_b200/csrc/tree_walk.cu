@@ -29,6 +29,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace b200 {
 
@@ -524,8 +525,50 @@ int walk_init_tables(Engine *E)
     return 0;
 }
 
+// Split the tree's particles (curve order, E->sidx) into `nchunks` groups of equal
+// original-index ranges, keeping the curve order inside each group: a stable
+// 1-pass radix sort on the chunk number.  The e2e path walks one group at a time
+// so that the finished index range can travel back to the host while the next
+// group is walked.  offsets[nchunks+1] (host) delimit the groups in E->targets_sorted.
+__global__ void k_chunk_keys(const int *__restrict__ sidx, int np, int chunk, unsigned char *__restrict__ key)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if(j < np) key[j] = (unsigned char) (sidx[j] / chunk);
+}
+__global__ void k_chunk_offsets(const unsigned char *__restrict__ key, int np, int nchunks, int *__restrict__ off)
+{
+    const int c = threadIdx.x;
+    if(c > nchunks) return;
+    int lo = 0, hi = np;            // first position with key >= c
+    while(lo < hi) { const int mid = (lo + hi) >> 1; if((int) key[mid] < c) lo = mid + 1; else hi = mid; }
+    off[c] = lo;
+}
+
+int walk_chunk_targets(Engine *E, int nchunks, int64_t chunk, int *offsets)
+{
+    const int np = (int) E->tree_np;
+    if(nchunks < 1 || nchunks > 64) return failmsg(E, "walk_chunk_targets: bad chunk count");
+    CK(E->targets_sorted.ensure((size_t) np + 1));
+    CK(E->walk_flags.ensure(2 * (size_t) np + 64));
+    CK(E->scratch_i.ensure(128));
+    unsigned char *k0 = E->walk_flags.p, *k1 = k0 + np;
+    if(np > 0) {
+        k_chunk_keys<<<(np + 255) / 256, 256, 0, E->stream>>>(E->sidx.p, np, (int) chunk, k0); CKL(E);
+        int bits = 1; while((1 << bits) < nchunks) bits++;
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, k0, k1, E->sidx.p, E->targets_sorted.p, np, 0, bits, E->stream);
+        CK(E->cubtemp.ensure(tb + 16));
+        CK(cub::DeviceRadixSort::SortPairs(E->cubtemp.p, tb, k0, k1, E->sidx.p, E->targets_sorted.p, np, 0, bits, E->stream));
+        E->launches += 2;
+    }
+    k_chunk_offsets<<<1, 128, 0, E->stream>>>(k1, np, nchunks, E->scratch_i.p + 32); CKL(E);
+    CK(cudaMemcpyAsync(offsets, E->scratch_i.p + 32, (nchunks + 1) * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
 int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *d_active,
-                    int64_t nactive, double *d_acc, double *d_pot, b200_walk_counts *d_counts)
+                    int64_t nactive, double *d_acc, double *d_pot, b200_walk_counts *d_counts, bool presorted)
 {
     if(!E->tree_valid) return failmsg(E, "b200_grav_short_tree: tree moments not computed (call b200_tree_build)");   // gravshort-tree.c:113-114
     if(E->NmeshWalk == 0) return failmsg(E, "b200_grav_short_tree: call b200_pm_init first (needs Nmesh, Asmth, G)");
@@ -555,7 +598,8 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
     // tree set (the usual case); otherwise the caller's list as given.
     const int *tg = nullptr;
     int64_t nt = 0;
-    if(d_active == nullptr && E->tree_full) { tg = E->sidx.p; nt = E->tree_np; }
+    if(presorted) { tg = d_active; nt = nactive; }
+    else if(d_active == nullptr && E->tree_full) { tg = E->sidx.p; nt = E->tree_np; }
     else if(d_active == nullptr) {
         CK(E->targets.ensure(E->n > 0 ? E->n : 1));
         if(E->n > 0) { k_iota<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->targets.p, (int) E->n); CKL(E); }
