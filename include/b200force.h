@@ -187,6 +187,14 @@ int b200_grav_short_tree_dev(b200_ctx *ctx, const b200_gravshort_params *par,
 int b200_force_step_aos(b200_ctx *ctx, void *particles, int64_t n,
                         const b200_particle_layout *layout,
                         const b200_gravshort_params *par);
+/* The same three calls on particles already resident in HBM
+ * (b200_set_particles_*): outputs are DEVICE pointers [n][3] / [n], any may be
+ * NULL.  gravpm_force runs on a second stream concurrently with
+ * force_tree_full + grav_short_tree (the walk reads no PM result: its opening
+ * criterion uses the previous step's accelerations, gravshort.h:69-86). */
+int b200_force_step_dev(b200_ctx *ctx, const b200_gravshort_params *par,
+                        double *gravpm_out, double *pm_potential_out,
+                        double *accel_out, double *potential_out);
 
 /* ---- SPH density and hydro force -----------------------------------------------
  * b200_density     replaces density()     (libgadget/density.h:52, density.c:234-355)
@@ -226,6 +234,9 @@ int b200_density(b200_ctx *ctx, const b200_sph_params *par, int update_hsml, int
                  double *hsml, double *density, double *egywtdensity, double *dhsmlfac,
                  double *divvel, double *curlvel, double *dthsml, double *numngb,
                  int32_t *ninteract, int32_t *niter);
+/* GradRho[n][3] of the last b200_density pass (density.c:512-515; the reference
+ * returns its magnitude per gas slot in GradRho_mag, density.c:309-317). */
+int b200_density_gradrho(b200_ctx *ctx, double *gradrho);
 /* HydroAccel[n][3], DtEntropy[n], MaxSignalVel[n], ninteract = candidates from
  * opened leaves (treewalk.c:1056-1143). */
 int b200_hydro_force(b200_ctx *ctx, const b200_sph_params *par, double *hydroaccel, double *dtentropy,

@@ -90,11 +90,11 @@ EXPORTED = [
     "b200_abi_version", "b200_kernel_launches", "b200_set_particles_aos", "b200_set_particles_soa",
     "b200_set_particles_soa_dev", "b200_oldacc_from_last_step", "b200_pm_init", "b200_pm_force",
     "b200_pm_force_dev", "b200_pm_cell_index", "b200_pm_copy_mesh", "b200_tree_build", "b200_tree_free",
-    "b200_tree_export", "b200_grav_short_tree", "b200_grav_short_tree_dev", "b200_force_step_aos",
+    "b200_tree_export", "b200_grav_short_tree", "b200_grav_short_tree_dev", "b200_force_step_aos", "b200_force_step_dev",
     "b200_get_timings", "b200_stream",
     "b200_tree_top_get_dev", "b200_tree_top_set_dev", "b200_pmslab_init", "b200_pmslab_deposit",
     "b200_pmslab_fft2d", "b200_pmslab_fft1d", "b200_pmslab_transfer", "b200_pmslab_readout_dev",
-    "b200_sph_set_gas", "b200_density", "b200_hydro_force",
+    "b200_sph_set_gas", "b200_density", "b200_density_gradrho", "b200_hydro_force",
 ]
 
 
@@ -310,6 +310,11 @@ class Engine:
             ptr, n = P.ctypes.data, len(P)
         self.n = int(n)
         self._ck(self.L.b200_force_step_aos(self.ctx, C.c_void_p(ptr), C.c_int64(n), None, C.byref(p)))
+
+    def force_step_dev(self, par, gravpm_ptr=None, acc_ptr=None, pot_ptr=None, pmpot_ptr=None):
+        p = GravShortParams(**par) if isinstance(par, dict) else par
+        v = lambda x: C.c_void_p(x) if x else None
+        self._ck(self.L.b200_force_step_dev(self.ctx, C.byref(p), v(gravpm_ptr), v(pmpot_ptr), v(acc_ptr), v(pot_ptr)))
 
     def timings(self):
         t = Timings()

@@ -176,6 +176,8 @@ int b200_ctx_create(b200_ctx **out, int device)
     c->e.device = device;
     if(cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 6; }
     if(cudaStreamCreateWithFlags(&c->e.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->e.stream); delete c; return 6; }
+    if(cudaStreamCreateWithFlags(&c->e.side_stream, cudaStreamNonBlocking) != cudaSuccess) return 6;
+    if(cudaEventCreateWithFlags(&c->e.fork_ev, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->e.join_ev, cudaEventDisableTiming) != cudaSuccess) return 6;
     *out = c;
     return 0;
 }
@@ -199,6 +201,8 @@ void b200_ctx_destroy(b200_ctx *ctx)
     for(int i = 0; i < T_COUNT; i++) if(E->timers[i].a) { cudaEventDestroy(E->timers[i].a); cudaEventDestroy(E->timers[i].b); }
     for(int i = 0; i < 65; i++) if(E->chunk_ev[i]) cudaEventDestroy(E->chunk_ev[i]);
     cudaStreamDestroy(E->copy_stream);
+    cudaStreamDestroy(E->side_stream);
+    cudaEventDestroy(E->fork_ev); cudaEventDestroy(E->join_ev);
     cudaStreamDestroy(E->stream);
     delete ctx;
 }
@@ -413,6 +417,51 @@ int b200_grav_short_tree_dev(b200_ctx *ctx, const b200_gravshort_params *par, co
     return grav_common(E, par, active, nactive, accel_out, potential_out, counts_out, false);
 }
 
+// gravpm_force issued on the side stream, concurrent with whatever follows on the
+// main stream until pm_join(): the PM kernels are HBM-bound, the tree walk is
+// latency/issue-bound and reads none of the PM results, so the two overlap on the SMs.
+static int pm_force_forked(Engine *E, double *d_gravpm, double *d_pot)
+{
+    CK(cudaEventRecord(E->fork_ev, E->stream));
+    CK(cudaStreamWaitEvent(E->side_stream, E->fork_ev, 0));
+    cudaStream_t main_stream = E->stream;
+    E->stream = E->side_stream;
+    cufftSetStream(E->plan_fwd, E->stream); cufftSetStream(E->plan_inv, E->stream);
+    const int rc = pm_force(E, d_gravpm, d_pot);
+    cudaEventRecord(E->join_ev, E->stream);
+    E->stream = main_stream;
+    cufftSetStream(E->plan_fwd, E->stream); cufftSetStream(E->plan_inv, E->stream);
+    return rc;
+}
+static int pm_join(Engine *E)
+{
+    CK(cudaStreamWaitEvent(E->stream, E->join_ev, 0));
+    return 0;
+}
+
+/* Device-resident form of the same step: particles already set
+ * (b200_set_particles_*), outputs are device pointers (any may be NULL). */
+int b200_force_step_dev(b200_ctx *ctx, const b200_gravshort_params *par, double *gravpm_out, double *pm_potential_out,
+                        double *accel_out, double *potential_out)
+{
+    ENTER(ctx);
+    if(E->Nmesh == 0) return failmsg(E, "b200_force_step_dev: call b200_pm_init first");
+    if(!par) return failmsg(E, "b200_force_step_dev: null params");
+    const size_t m = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->last_pm_acc.ensure(3 * m)); CK(E->last_tree_acc.ensure(3 * m)); CK(E->d_pot.ensure(m));
+    if(int rc = pm_force_forked(E, E->last_pm_acc.p, pm_potential_out)) return rc;
+    if(int rc = tree_build(E, E->Box, 63, nullptr, 0, 0, nullptr)) return rc;
+    if(int rc = grav_short_tree(E, par, nullptr, 0, E->last_tree_acc.p, potential_out ? potential_out : E->d_pot.p, nullptr)) return rc;
+    if(int rc = pm_join(E)) return rc;
+    E->have_last_pm = E->have_last_tree = true;
+    if(E->n > 0) {
+        if(gravpm_out) CK(cudaMemcpyAsync(gravpm_out, E->last_pm_acc.p, 3 * E->n * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));
+        if(accel_out) CK(cudaMemcpyAsync(accel_out, E->last_tree_acc.p, 3 * E->n * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));
+    }
+    CK(cudaStreamSynchronize(E->stream));
+    return collect_timings(E);
+}
+
 int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_layout *layout,
                         const b200_gravshort_params *par)
 {
@@ -424,8 +473,8 @@ int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_l
     if(n == 0) return 0;
     const size_t m = (size_t) n;
     CK(E->last_pm_acc.ensure(3 * m)); CK(E->last_tree_acc.ensure(3 * m)); CK(E->d_pot.ensure(m));
-    // gravpm_force (run.c:519-523)
-    if(int rc = pm_force(E, E->last_pm_acc.p, nullptr)) return rc;
+    // gravpm_force (run.c:519-523), concurrent with the tree build and walk
+    if(int rc = pm_force_forked(E, E->last_pm_acc.p, nullptr)) return rc;
     // force_tree_full + grav_short_tree (run.c:546-548)
     if(int rc = tree_build(E, E->Box, 63, nullptr, 0, 0, nullptr)) return rc;
     E->have_last_pm = E->have_last_tree = true;
@@ -437,6 +486,7 @@ int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_l
     if(const char *ev = getenv("B200_E2E_CHUNKS")) { nchunks = atoi(ev); if(nchunks < 1) nchunks = 1; if(nchunks > 64) nchunks = 64; }
     if(nchunks == 1) {
         if(int rc = grav_short_tree(E, par, nullptr, 0, E->last_tree_acc.p, E->d_pot.p, nullptr)) return rc;
+        if(int rc = pm_join(E)) return rc;
         k_pack_aos<<<(unsigned) ((n + 255) / 256), 256, 0, E->stream>>>(E->aos.p, n, L, E->last_pm_acc.p, E->last_tree_acc.p, E->d_pot.p, 1, 0);
         CKL(E);
         timer_start(E, T_D2H);
@@ -453,6 +503,7 @@ int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_l
             const int64_t nc = off[c + 1] - off[c];
             if(nc > 0)
                 if(int rc = grav_short_tree(E, par, E->targets_sorted.p + off[c], nc, E->last_tree_acc.p, E->d_pot.p, nullptr, true)) return rc;
+            if(c == 0) if(int rc = pm_join(E)) return rc;       // GravPM is packed with the first group
             k_pack_aos<<<(unsigned) ((hi - lo + 255) / 256), 256, 0, E->stream>>>(E->aos.p, hi - lo, L, E->last_pm_acc.p, E->last_tree_acc.p, E->d_pot.p, 1, lo);
             CKL(E);
             if(c == nchunks - 1 || hi == n) timer_start(E, T_D2H);      // the exposed tail of the write-back
@@ -501,6 +552,15 @@ int b200_density(b200_ctx *ctx, const b200_sph_params *par, int update_hsml, int
         return 1;
     CK(cudaStreamSynchronize(E->stream));
     return collect_timings(E);
+}
+
+int b200_density_gradrho(b200_ctx *ctx, double *gradrho)
+{
+    ENTER(ctx);
+    if(!E->sph_density_done) return failmsg(E, "b200_density_gradrho: call b200_density first");
+    if(d2h_opt(E, gradrho, E->s_gradrho.p, 3 * (size_t) E->n * sizeof(double))) return 1;
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
 }
 
 int b200_hydro_force(b200_ctx *ctx, const b200_sph_params *par, double *hydroaccel, double *dtentropy, double *maxsignalvel,

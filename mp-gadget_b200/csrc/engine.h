@@ -55,6 +55,8 @@ struct Engine {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;     // host<->device copies that overlap kernels on `stream`
     cudaEvent_t chunk_ev[65] = {};
+    cudaStream_t side_stream = nullptr;     // PM long-range step when it runs concurrently with the tree walk
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     std::string err;
     int64_t launches = 0;
 
@@ -113,7 +115,7 @@ struct Engine {
     // ---- SPH (original index order unless noted) ----
     DevBuf<double> s_vel, s_hsml, s_entropy, s_dtentropy, s_fullacc, s_gravpm, s_hydroacc;
     bool s_have[7] = {false, false, false, false, false, false, false};
-    DevBuf<double> s_velpred, s_evp, s_density, s_egy, s_dhsmlfac, s_divvel, s_curlvel, s_dthsml, s_numngb;
+    DevBuf<double> s_velpred, s_evp, s_density, s_egy, s_dhsmlfac, s_divvel, s_curlvel, s_dthsml, s_numngb, s_gradrho;
     DevBuf<double> s_svel, s_hA, s_hB;      // curve order: double4 rows
     DevBuf<double> s_out3, s_out1a, s_out1b;
     DevBuf<int> s_outi, s_outi2;

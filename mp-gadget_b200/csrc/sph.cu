@@ -144,7 +144,7 @@ k_sph_density(int np, const int *__restrict__ sidx, const double4 *__restrict__ 
               SphDev S, int update_hsml, int DoEgy,
               double *__restrict__ hsml, double *__restrict__ density, double *__restrict__ egy, double *__restrict__ dhsmlfac,
               double *__restrict__ divvel, double *__restrict__ curlvel, double *__restrict__ dthsml, double *__restrict__ numngb,
-              int *__restrict__ ninteract, int *__restrict__ niter, int *__restrict__ err)
+              double *__restrict__ gradrho, int *__restrict__ ninteract, int *__restrict__ niter, int *__restrict__ err)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if(j >= np) return;
@@ -154,12 +154,13 @@ k_sph_density(int np, const int *__restrict__ sidx, const double4 *__restrict__ 
     const double4 vm = svel[j];
     double Left = 0, Right = S.box, h = hsml[me];
     double Ngb = 0, Rho = 0, Dh = 0, EgyRho = 0, DhEgy = 0, Div = 0, R0 = 0, R1 = 0, R2 = 0, DhsmlDens = 0;
+    double G0 = 0, G1 = 0, G2 = 0;
     int nint = 0, it = 0;
     for(it = 0; it < SPH_MAXITER + 2; it++) {
         Kern k; kern_init(k, h, S);
         const double vol = NORM_COEFF * pw3(k.H);
         const double h2 = h * h;
-        Ngb = Rho = Dh = EgyRho = DhEgy = Div = R0 = R1 = R2 = 0; nint = 0;
+        Ngb = Rho = Dh = EgyRho = DhEgy = Div = R0 = R1 = R2 = G0 = G1 = G2 = 0; nint = 0;
         int no = 0;
         while(no >= 0) {
             const double4 B = nodeB[no];
@@ -198,6 +199,7 @@ k_sph_density(int np, const int *__restrict__ sidx, const double4 *__restrict__ 
                         R0 += fac * (v1 * d2 - d1 * v2);
                         R1 += fac * (v2 * d0 - d2 * v0);
                         R2 += fac * (v0 * d1 - d0 * v1);
+                        G0 += fac * d0; G1 += fac * d1; G2 += fac * d2;         // density.c:512-515
                     }
                 }
             }
@@ -252,6 +254,7 @@ k_sph_density(int np, const int *__restrict__ sidx, const double4 *__restrict__ 
     divvel[me] = dv;
     dthsml[me] = (1.0 / 3) * dv * h;
     if(numngb) numngb[me] = Ngb;
+    gradrho[3 * (int64_t) me] = G0; gradrho[3 * (int64_t) me + 1] = G1; gradrho[3 * (int64_t) me + 2] = G2;
     if(ninteract) ninteract[me] = nint;
     if(niter) niter[me] = it + 1;
 }
@@ -466,7 +469,7 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
     const int np = (int) E->tree_np, nn = (int) E->tree_nn;
     CK(E->s_velpred.ensure(3 * n)); CK(E->s_evp.ensure(n));
     CK(E->s_density.ensure(n)); CK(E->s_egy.ensure(n)); CK(E->s_dhsmlfac.ensure(n)); CK(E->s_divvel.ensure(n));
-    CK(E->s_curlvel.ensure(n)); CK(E->s_dthsml.ensure(n)); CK(E->s_numngb.ensure(n));
+    CK(E->s_curlvel.ensure(n)); CK(E->s_dthsml.ensure(n)); CK(E->s_numngb.ensure(n)); CK(E->s_gradrho.ensure(3 * n));
     CK(E->s_svel.ensure(4 * (size_t) (np > 0 ? np : 1)));
     CK(E->scratch_i.ensure(16));
     CK(cudaMemsetAsync(E->scratch_i.p + 12, 0, sizeof(int), E->stream));
@@ -483,7 +486,7 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
         k_sph_density<<<(np + 127) / 128, 128, 0, E->stream>>>(np, E->sidx.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p,
             (const double4 *) E->spart.p, (const double4 *) E->s_svel.p, E->type.p, S, update_hsml, DoEgy,
             E->s_hsml.p, E->s_density.p, E->s_egy.p, E->s_dhsmlfac.p, E->s_divvel.p, E->s_curlvel.p, E->s_dthsml.p, E->s_numngb.p,
-            d_ninteract, d_niter, E->scratch_i.p + 12);
+            E->s_gradrho.p, d_ninteract, d_niter, E->scratch_i.p + 12);
         CKL(E);
         // hmax of the tree from the converged smoothing lengths (run.c:477 force_tree_calc_moments)
         k_sph_hmax_leaf<<<(nn + 255) / 256, 256, 0, E->stream>>>(nn, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p,

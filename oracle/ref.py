@@ -12,6 +12,8 @@ SO = os.path.join(_HERE, "_ref", "libref_tree.so")
 # same driver + reference files, but gravshort-tree.c replaced by the B200 shim
 # (mp-gadget_b200/host/libgadget_shims.c): grav_short_tree() runs on the GPU.
 SO_DROPIN = os.path.join(_HERE, "_ref", "libref_dropin.so")
+# same driver, but density.c + hydra.c replaced by libgadget_sph_shims.c: density() / hydro_force() run on the GPU
+SO_DROPIN_SPH = os.path.join(_HERE, "_ref", "libref_dropin_sph.so")
 _inst = None
 
 

@@ -31,3 +31,48 @@ def test_reference_driver_calls_gpu_grav_short_tree(name):
         scale = np.sqrt((racc ** 2).sum(1)).mean()
         assert np.abs(acc - racc).max() < 1e-6 * scale
         assert np.abs(pot - rpot).max() < 1e-6 * np.abs(rpot).max()
+
+
+GOLD_SPH = np.load(os.path.join(HERE, "golden", "ref_sph.npz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(R.SO_DROPIN_SPH), reason="oracle/_ref/libref_dropin_sph.so not built")
+@pytest.mark.parametrize("name", ["clustered16", "zeldovich16"])
+@pytest.mark.parametrize("kt,DI", [(1, 0), (2, 1)])
+def test_reference_driver_calls_gpu_density_and_hydro(name, kt, DI):
+    """The reference's fixture code (ref_driver.c, modelled on tests/test_density.c:55-152)
+    calls density() and hydro_force() with the reference signatures; the symbols come from
+    libgadget_sph_shims.c and run on the GPU.  Results land in P[]/SphP[] and must match the
+    stock density.c / hydra.c (golden fixture)."""
+    r = R.Ref(arena_gib=2.0, nthreads=2, so=R.SO_DROPIN_SPH)
+    g = lambda k: GOLD_SPH[name + "/" + k]
+    d = r.sph_density(g("pos"), g("mass"), float(g("box")), g("h0"), vel=g("vel"), entropy=g("entropy"), kerneltype=kt,
+                      init_hsml=False, DoEgyDensity=DI)
+    h = r.sph_hydro(atime=0.5, hubble=0.2, dloga_bin=0.01, DensityIndependentSphOn=DI)
+    key = "%s/k%d_di%d/" % (name, kt, DI)
+    close = lambda a, b, tol: np.abs(a - b).max() <= tol * (np.abs(b).max() + 1e-300)
+    for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel", "dthsml"):
+        if k == "egywtdensity" and not DI:
+            continue            # not written without DoEgyDensity (density.c:566-568)
+        assert close(d[k], GOLD_SPH[key + k], 1e-11), k
+    for k in ("acc", "dtentropy", "maxsignalvel"):
+        assert close(h[k], GOLD_SPH[key + "hydro_" + k], 1e-10), k
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(R.SO_DROPIN_SPH) or not os.path.exists(R.SO), reason="oracle/_ref not built")
+def test_shim_set_init_hsml_equals_reference():
+    """set_init_hsml of the shim (walks the caller's host ForceTree) against density.c:700-749,
+    through the converged smoothing lengths of tests/test_density.c's lattice case."""
+    n1 = 16
+    box = 8.0
+    x = (np.arange(n1) + 0.5) * box / n1
+    pos = np.stack(np.meshgrid(x, x, x, indexing="ij"), -1).reshape(-1, 3)
+    mass = np.ones(len(pos), np.float32)
+    out = []
+    for so in (R.SO, R.SO_DROPIN_SPH):
+        r = R.Ref(arena_gib=2.0, nthreads=2, so=so)
+        out.append(r.sph_density(pos, mass, box, np.ones(len(pos)), kerneltype=1, init_hsml=True, meansep=1.0))
+    assert np.abs(out[0]["hsml"] - out[1]["hsml"]).max() <= 1e-11 * out[0]["hsml"].max()
+    assert np.abs(out[0]["density"] - out[1]["density"]).max() <= 1e-11 * out[0]["density"].max()

@@ -195,6 +195,30 @@ def test_force_step_aos(engine, b200, ics, chunks, monkeypatch):
     assert np.array_equal(P["Pos"], pos) and np.all(P["ID"] == np.arange(n))
 
 
+def test_force_step_dev(engine, ics):
+    """b200_force_step_dev (PM on a second stream, concurrent with tree build + walk)
+    equals the three separate calls."""
+    import torch
+    pos, box = _distributions(ics)["gslrandom16"]
+    n = len(pos)
+    mass = np.ones(n, np.float32)
+    rng = np.random.default_rng(6)
+    old = rng.standard_normal((n, 3)) * 300
+    par = ics.tree_params(box, n, treeusebh=0, rcut=7.0)
+    engine.gravpm_init_periodic(box, 1.5, 48, G)
+    engine.set_particles(pos, mass, oldacc=old)
+    g, _ = engine.gravpm_force()
+    engine.force_tree_full(box)
+    acc, pot, _ = engine.grav_short_tree(par)
+    d = [torch.zeros(s, dtype=torch.float64, device="cuda") for s in ((n, 3), (n, 3), (n,))]
+    for _ in range(3):
+        engine.set_particles(pos, mass, oldacc=old)
+        engine.force_step_dev(par, d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr())
+        assert np.abs(d[0].cpu().numpy() - g).max() <= 1e-11 * np.abs(g).max()
+        assert np.array_equal(d[1].cpu().numpy(), acc)
+        assert np.array_equal(d[2].cpu().numpy(), pot)
+
+
 def test_empty_and_tiny_inputs(engine, ics):
     """Edge cases: no particles, one particle, particles exactly on the box edge
     (Pos == BoxSize is legal, drift.c:77-78 -> iCell == Nmesh wraps, petapm.c:903-906)."""
