@@ -193,11 +193,12 @@ void b200_ctx_destroy(b200_ctx *ctx)
     E->pos.release(); E->mass.release(); E->type.release(); E->flags.release(); E->oldacc.release();
     E->last_tree_acc.release(); E->last_pm_acc.release(); E->aos.release();
     E->keys.release(); E->keys_alt.release(); E->sidx.release(); E->sidx_alt.release(); E->cubtemp.release();
-    E->spart.release(); E->b_start.release(); E->b_count.release(); E->b_father.release(); E->b_sibling.release();
+    E->spart.release(); E->spart_xy.release(); E->spart_zm.release(); E->b_start.release(); E->b_count.release(); E->b_father.release(); E->b_sibling.release();
     E->b_firstchild.release(); E->b_nchild.release(); E->b_level.release(); E->b_size.release(); E->b_dfs.release();
     E->b_scan.release(); E->b_center.release(); E->nodeA.release(); E->nodeB.release(); E->nodeC.release();
     E->nodeF.release(); E->nodeH.release(); E->nodeK.release(); E->scratch_i.release(); E->targets.release(); E->targets_sorted.release(); E->walk_flags.release();
     E->d_acc.release(); E->d_pot.release(); E->d_counts.release(); E->srtab.release();
+    E->walk_pool.release(); E->walk_chunktab.release(); E->walk_cnt.release(); E->walk_partial.release();
     for(int i = 0; i < T_COUNT; i++) if(E->timers[i].a) { cudaEventDestroy(E->timers[i].a); cudaEventDestroy(E->timers[i].b); }
     for(int i = 0; i < 65; i++) if(E->chunk_ev[i]) cudaEventDestroy(E->chunk_ev[i]);
     cudaStreamDestroy(E->copy_stream);

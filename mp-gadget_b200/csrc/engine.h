@@ -100,6 +100,7 @@ struct Engine {
     DevBuf<int> sidx, sidx_alt;   // sorted -> original index
     DevBuf<uint8_t> cubtemp;
     DevBuf<double> spart;       // [np] double4 {x,y,z,m} in sorted order
+    DevBuf<double> spart_xy, spart_zm;   // the same as two double2 streams (pair kernel)
     // build-time (BFS order) node fields
     DevBuf<int> b_start, b_count, b_father, b_sibling, b_firstchild, b_nchild, b_level, b_size, b_dfs, b_scan;
     DevBuf<double> b_center;    // [.][4] cx,cy,cz,len
@@ -129,6 +130,10 @@ struct Engine {
     DevBuf<double> d_acc, d_pot;  // outputs [n][3], [n]
     DevBuf<int> d_counts;       // [n] b200_walk_counts
     DevBuf<float> srtab;        // 2*512 short-range window tables
+    DevBuf<unsigned> walk_pool; // chunk pool of the per-target leaf-piece lists (tree_walk.cu)
+    DevBuf<int> walk_chunktab, walk_cnt;
+    DevBuf<double> walk_partial;
+    double walk_chunks_per_warp = 6.0;
 
     Timer timers[T_COUNT];
     b200_timings last = {};

@@ -171,13 +171,19 @@ k_tree_leaf_order(int nn, const int *__restrict__ b_start, const int *__restrict
 
 __global__ void __launch_bounds__(256)
 k_tree_gather(const double *__restrict__ pos, const float *__restrict__ mass,
-              const int *__restrict__ sidx, int np, double far, double4 *__restrict__ spart)
+              const int *__restrict__ sidx, int np, double far, double4 *__restrict__ spart,
+              double2 *__restrict__ spart_xy, double2 *__restrict__ spart_zm)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if(j >= np + B200_SPART_PAD) return;
-    if(j >= np) { spart[j] = make_double4(far, far, far, 0.0); return; }
-    const int64_t i = sidx[j];
-    spart[j] = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], (double) mass[i]);
+    double4 q = make_double4(far, far, far, 0.0);
+    if(j < np) {
+        const int64_t i = sidx[j];
+        q = make_double4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], (double) mass[i]);
+    }
+    spart[j] = q;
+    spart_xy[j] = make_double2(q.x, q.y);       // the pair kernel's two 16-byte streams (tree_walk.cu)
+    spart_zm[j] = make_double2(q.z, q.w);
 }
 
 // Moments + subtree sizes for the cells of one level (children already done).
@@ -346,7 +352,9 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
     // 16 far-away massless rows follow the particles: the pair loop of the walk reads
     // whole 8-row pieces and empty padding pieces without bounds checks.
     CK(E->spart.ensure(4 * (size_t) (np + B200_SPART_PAD)));
-    k_tree_gather<<<(np + B200_SPART_PAD + 255) / 256, 256, 0, E->stream>>>(E->pos.p, E->mass.p, E->sidx.p, np, 1e3 * Box, (double4 *) E->spart.p);
+    CK(E->spart_xy.ensure(2 * (size_t) (np + B200_SPART_PAD))); CK(E->spart_zm.ensure(2 * (size_t) (np + B200_SPART_PAD)));
+    k_tree_gather<<<(np + B200_SPART_PAD + 255) / 256, 256, 0, E->stream>>>(E->pos.p, E->mass.p, E->sidx.p, np, 1e3 * Box, (double4 *) E->spart.p,
+                                                                            (double2 *) E->spart_xy.p, (double2 *) E->spart_zm.p);
     CKL(E);
     // b_mom lives in nodeH's neighbour buffer: reuse keys_alt (np*8 bytes is too small) -> own buffer
     CK(E->nodeA.ensure(4 * (size_t) nn)); CK(E->nodeB.ensure(4 * (size_t) nn));

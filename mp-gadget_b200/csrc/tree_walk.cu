@@ -3,31 +3,37 @@
 // (treewalk.c:266-310,801-902) with the visitor force_treeev_shortrange
 // (gravshort-tree.c:253-379)).
 //
-// One warp walks the tree for 32 targets that are adjacent on the space-filling
-// curve.  The warp follows the reference's depth-first sibling/first-child
-// order; every lane takes ITS OWN discard / accept / open decision with the
-// reference's criteria (gravshort-tree.c:198-241), so per-particle results and
-// interaction counts are those of the per-particle CPU walk.  A subtree is
-// entered when any lane opens the node (warp ballot); lanes that accepted or
-// discarded the node park until the walk reaches that node's sibling.  Node
-// rows are therefore fetched once per warp (uniform 128-bit loads), not once
-// per particle.
+// Two kernels.
 //
-// Pair sums are decoupled from the walk: an opened particle leaf is pushed to a
-// per-warp shared-memory list together with the ballot of lanes that opened it.
-// The list is then evaluated target-major with the lanes spread over SOURCE
-// particles (4 leaves x 8 particle slots per step) and one warp reduction per
-// target, so lanes whose target did not open a leaf do no work for it: the
-// pair loop runs at the number of pairs each target needs instead of the
-// union over the warp (measured 2.8x larger on a 256^3 box, see profiles/).
+// k_grav_walk: one warp walks the tree for 32 targets that are adjacent on the
+// space-filling curve.  The warp follows the reference's depth-first
+// sibling/first-child order through a batched frontier; every lane takes ITS OWN
+// discard / accept / open decision with the reference's criteria
+// (gravshort-tree.c:198-241), so per-particle results and interaction counts are
+// those of the per-particle CPU walk.  A subtree is entered when any lane opens
+// the node (warp ballot).  Node rows are fetched once per warp, not once per
+// particle.  Accepted nodes are applied at once; an opened particle leaf is NOT
+// evaluated here: every lane that opened it appends the leaf piece
+// (first particle, count <= 8) to its own list in a global chunk pool, laid out
+// [slot][lane] so that lanes with equal list lengths write one 128-byte line.
+//
+// k_grav_pairs: the same warp/target assignment.  For each of its 32 targets the
+// warp reads that target's piece list and sums the pairs with the lanes spread
+// over SOURCE particles (4 pieces x 8 particle slots, two sets interleaved and
+// the next two already in flight), then one warp reduction hands the sums to
+// the target's lane (gravshort-tree.c:364-374 sums the same pairs).  The pair
+// loop therefore runs at the number of pairs each target needs, not at the union
+// over the warp (2.8x larger on a 256^3 box), and it owns the whole register
+// file instead of sharing it with the walk state.
 //
 // Decisions are evaluated with un-fused IEEE fp64 mul/add so that they agree
 // bit-for-bit with a CPU evaluation; only the accepted-force arithmetic uses
-// FMA / rsqrt (accelerations are compared to 1e-6 relative, far above that).
+// FMA / a fix-up-free rsqrt (accelerations are compared to 1e-6 relative, far above that).
 #include "engine.h"
 #include "../data/shortrange_table.h"
 #include <math.h>
 #include <stdlib.h>
+#include <string>
 #include <cub/device/device_select.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -52,12 +58,34 @@ __device__ __forceinline__ double nearest(double x, double box, double halfbox) 
     return (x > halfbox) ? (x - box) : ((x < -halfbox) ? (x + box) : x);
 }
 
+// Window-table accessors.  row(t) = {T[t], T[t+1]-T[t], Tpot[t], Tpot[t+1]-Tpot[t]} so that the
+// linear interpolation of grav_apply_short_range_window (gravity.c:54-66) is one FMA.
+// TabD4: one double4 row per entry (walk kernel, few lookups).
+// TabF4x8: the pair kernel's layout.  The table values ARE floats (gravity.c:20), so a row
+// is stored as float4 {T[t], T[t+1], Tpot[t], Tpot[t+1]} and widened in registers (the
+// differences of two floats are exact in double: same values as TabD4).  Eight copies,
+// copy j in 16-byte bank group j: the eight lanes of a quarter warp (j = lane & 7) never
+// conflict however their rows differ.  One LDS.128 per pair instead of two conflicting ones.
+struct TabD4 {
+    const double4 *p;
+    __device__ __forceinline__ double4 row(int t) const { return p[t]; }
+};
+struct TabF4x8 {
+    const float4 *p;        // already offset by the lane's copy: p = base + (lane & 7)
+    __device__ __forceinline__ double4 row(int t) const
+    {
+        const float4 f = p[t * 8];
+        const double f0 = (double) f.x, p0 = (double) f.z;
+        return make_double4(f0, (double) f.y - f0, p0, (double) f.w - p0);
+    }
+};
+
 // apply_accn_to_output (gravshort-tree.c:158-193) with the tabulated window of
 // grav_apply_short_range_window (gravity.c:54-66).  tab[t] = {T[t], T[t+1]-T[t],
 // Tpot[t], Tpot[t+1]-Tpot[t]} so that the linear interpolation is one FMA.
-template <class PP>
+template <class TAB>
 __device__ __forceinline__ void monopole(double dx, double dy, double dz, double r2, double m,
-                                         const PP &P, const double4 *__restrict__ tab,
+                                         const WalkPar &P, const TAB &tab,
                                          double &ax, double &ay, double &az, double &pot)
 {
     double r, fac, facpot;
@@ -85,18 +113,29 @@ __device__ __forceinline__ void monopole(double dx, double dy, double dz, double
     const int t = (int) ti;                 // ti >= 0: truncation == floor
     if(t >= B200_SR_NTAB - 1) return;       // gravity.c:60-61: contribution dropped
     const double w1 = ti - (double) t;
-    const double4 e = tab[t];
+    const double4 e = tab.row(t);
     fac *= fma(w1, e.y, e.x);
     facpot *= fma(w1, e.w, e.z);
     ax = fma(dx, fac, ax); ay = fma(dy, fac, ay); az = fma(dz, fac, az);
     pot += facpot;
 }
 
-#define LIST_CAP 128          // opened leaves buffered per warp before a flush
 #define WALK_WARPS 4
+// Piece lists: chunk = CH_SLOTS list slots x 32 lanes x 4 bytes; a warp owns up to
+// WALK_MAXCH chunks (CH_SLOTS * WALK_MAXCH pieces = 8x that many pairs per target).
+#define CH_SHIFT 4
+#define CH_SLOTS (1 << CH_SHIFT)
+#define CH_WORDS (CH_SLOTS * 32)
+#define WALK_MAXCH 128
+// entry = first particle << 4 | count (0..8)
+#define PIECE(pstart, cnt) (((unsigned) (pstart) << 4) | (unsigned) (cnt))
 #ifndef WALK_MINB
-#define WALK_MINB 4
+#define WALK_MINB 5
 #endif
+#ifndef PAIR_MINB
+#define PAIR_MINB 2
+#endif
+#define PAIR_WARPS 8
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -172,7 +211,7 @@ __device__ __forceinline__ double rsqrt_pos(double x)
 // zero, so a pair beyond the table (gravity.c:60-61: contribution dropped) needs
 // no select, only the index clamp.
 __device__ __forceinline__ void pair_fast(double dx, double dy, double dz, double r2, double m,
-                                          const WalkPar &P, const double4 *__restrict__ tab,
+                                          const WalkPar &P, const TabF4x8 &tab,
                                           double &ax, double &ay, double &az, double &pot)
 {
     const double rinv = rsqrt_pos(r2);
@@ -181,25 +220,38 @@ __device__ __forceinline__ void pair_fast(double dx, double dy, double dz, doubl
     const double ti = r * P.inv_cell_dx;
     const int t = min((int) ti, B200_SR_NTAB - 1);
     const double w1 = ti - (double) t;
-    const double4 e = tab[t];
+    const double4 e = tab.row(t);
     const double wf = fma(w1, e.y, e.x), wp = fma(w1, e.w, e.z);
     const double fac = mr * rinv * rinv * wf;
     ax = fma(dx, fac, ax); ay = fma(dy, fac, ay); az = fma(dz, fac, az);
     pot = fma(-mr, wp, pot);
 }
 
-// One source row of a (pstart, count) leaf piece for this lane's slot.  Slots
-// past the count read the rows that follow (spart is padded with far-away
-// massless rows) and are neutralised through the mass.
+// One source row of a leaf piece for this lane's slot.  Slots past the count read
+// the rows that follow (spart is padded with far-away massless rows) and are
+// neutralised through the mass.
 struct SrcRow { double4 q; int cnt; };
 
-__device__ __forceinline__ SrcRow fetch_row(const int2 *__restrict__ s_tl, int idx, int slot,
-                                            const double4 *__restrict__ spart)
+struct PieceList {
+    const unsigned *__restrict__ pool;     // chunk pool
+    const int *__restrict__ ctab;          // this warp's chunk ids (shared memory)
+    unsigned empty;                        // PIECE(sentinel, 0)
+    int t;                                 // column = lane of the target in its warp
+    int nt;                                // pieces in the list
+};
+
+// The source rows are read from two 16-byte streams {x, y} and {z, m}: the eight lanes of a
+// group then read 128 contiguous bytes per load (whole sectors) instead of half of 8 x 32.
+struct SrcArrays { const double2 *__restrict__ xy; const double2 *__restrict__ zm; };
+
+__device__ __forceinline__ SrcRow fetch_row(const PieceList &L, int idx, int slot, const SrcArrays &S)
 {
+    unsigned e = L.empty;
+    if(idx < L.nt) e = L.pool[(size_t) L.ctab[idx >> CH_SHIFT] * CH_WORDS + (idx & (CH_SLOTS - 1)) * 32 + L.t];
     SrcRow r;
-    const int2 lf = s_tl[idx];
-    r.q = spart[lf.x + slot];
-    r.cnt = lf.y;
+    const double2 a = S.xy[(e >> 4) + slot], b = S.zm[(e >> 4) + slot];
+    r.q = make_double4(a.x, a.y, b.x, b.y);
+    r.cnt = (int) (e & 15u);
     return r;
 }
 
@@ -215,13 +267,9 @@ __device__ __forceinline__ void row_delta(const SrcRow &s, int slot, const WalkP
     q2 = fma(qz, qz, fma(qy, qy, qx * qx));
 }
 
-// s_tl holds the (pstart, count<=8) leaf pieces target t opened, padded with
-// empty pieces to a multiple of 8.  Each step the four 8-lane groups take two pieces each (8 per step),
-// one particle per lane per piece, in branch-free interleaved code; pairs inside the softening radius (the
-// target itself among them) are rare and take the general path.
 template <bool WRAP>
 __device__ __forceinline__ void pair_step(const SrcRow &ca, const SrcRow &cb, int slot, const WalkPar &P,
-                                          const double4 *__restrict__ tab, double tx, double ty, double tz,
+                                          const TabF4x8 &tab, double tx, double ty, double tz,
                                           double &sx, double &sy, double &sz, double &sp)
 {
     double ax_, ay_, az_, a2, am, bx_, by_, bz_, b2, bm;
@@ -236,61 +284,24 @@ __device__ __forceinline__ void pair_step(const SrcRow &ca, const SrcRow &cb, in
     pair_fast(bx_, by_, bz_, b2, bm, P, tab, sx, sy, sz, sp);
 }
 
+// Each step the four 8-lane groups take two pieces each (8 per step), one particle
+// per lane per piece, in branch-free interleaved code; the rows of the next step
+// are already in flight (two row sets swapped by unrolling).  Pairs inside the
+// softening radius (the target itself among them) are rare and take the general path.
 template <bool WRAP>
-__device__ __forceinline__ void pair_sum(const int2 *__restrict__ s_tl, int ntpad, int g, int slot,
-                                         const double4 *__restrict__ spart, const WalkPar &P,
-                                         const double4 *__restrict__ tab, double tx, double ty, double tz,
+__device__ __forceinline__ void pair_sum(const PieceList &L, int g, int slot,
+                                         const SrcArrays &spart, const WalkPar &P,
+                                         const TabF4x8 &tab, double tx, double ty, double tz,
                                          double &sx, double &sy, double &sz, double &sp)
 {
-    for(int i = 0; i < ntpad; i += 8) {
-        const SrcRow ca = fetch_row(s_tl, i + g, slot, spart), cb = fetch_row(s_tl, i + 4 + g, slot, spart);
-        pair_step<WRAP>(ca, cb, slot, P, tab, tx, ty, tz, sx, sy, sz, sp);
+    SrcRow na = fetch_row(L, g, slot, spart), nb = fetch_row(L, 4 + g, slot, spart);
+    for(int i = 0; i < L.nt; i += 16) {
+        const SrcRow ma = fetch_row(L, i + 8 + g, slot, spart), mb = fetch_row(L, i + 12 + g, slot, spart);
+        pair_step<WRAP>(na, nb, slot, P, tab, tx, ty, tz, sx, sy, sz, sp);
+        if(i + 8 >= L.nt) break;                       // warp-uniform
+        na = fetch_row(L, i + 16 + g, slot, spart); nb = fetch_row(L, i + 20 + g, slot, spart);
+        pair_step<WRAP>(ma, mb, slot, P, tab, tx, ty, tz, sx, sy, sz, sp);
     }
-}
-
-// Evaluate the buffered (leaf, wanting-lanes) list: for every target t of the
-// warp, compact the leaves t opened into a dense list, then the lanes take
-// 4 leaves x 8 particle slots per step (gravshort-tree.c:364-374 sums the same
-// pairs) and one reduction hands the sums to lane t.
-// Returns this lane's increments {ax, ay, az, pot}.
-__device__ __forceinline__ double4 eval_leaf_list(const int2 *__restrict__ s_leaf, const unsigned *__restrict__ s_mask,
-                                               int2 *__restrict__ s_tl, int nlist, unsigned anymask,
-                                               const double4 *__restrict__ spart,
-                                               const WalkPar &P, const double4 *__restrict__ tab, int lane,
-                                               double px, double py, double pz)
-{
-    double ax = 0, ay = 0, az = 0, pot = 0;
-    const int g = lane >> 3, slot = lane & 7;
-    const unsigned ltmask = (1u << lane) - 1u;
-    for(int t = 0; t < 32; t++) {
-        if(!((anymask >> t) & 1u)) continue;            // warp-uniform
-        const double tx = __shfl_sync(0xffffffffu, px, t);
-        const double ty = __shfl_sync(0xffffffffu, py, t);
-        const double tz = __shfl_sync(0xffffffffu, pz, t);
-        int nt = 0;
-        for(int base = 0; base < nlist; base += 32) {
-            const int li = base + lane;
-            const bool w = li < nlist && ((s_mask[li] >> t) & 1u);
-            const unsigned bal = __ballot_sync(0xffffffffu, w);
-            if(w) s_tl[nt + __popc(bal & ltmask)] = s_leaf[li];
-            nt += __popc(bal);
-        }
-        const int ntpad = (nt + 7) & ~7;
-        if(lane < ntpad - nt) s_tl[nt + lane] = make_int2(P.sentinel, 0);          // <= 7 empty pieces
-        __syncwarp();
-        double sx = 0, sy = 0, sz = 0, sp = 0;
-        // No periodic wrap is needed when the target is farther than the reach of
-        // the window table from every face: a pair that NEAREST would wrap is then
-        // beyond the table on both sides of the wrap and contributes nothing.
-        const bool central = tx >= P.wrap_lo && tx <= P.wrap_hi && ty >= P.wrap_lo && ty <= P.wrap_hi &&
-                             tz >= P.wrap_lo && tz <= P.wrap_hi;
-        if(central) pair_sum<false>(s_tl, ntpad, g, slot, spart, P, tab, tx, ty, tz, sx, sy, sz, sp);
-        else pair_sum<true>(s_tl, ntpad, g, slot, spart, P, tab, tx, ty, tz, sx, sy, sz, sp);
-        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); sp = warp_sum(sp);
-        if(lane == t) { ax += sx; ay += sy; az += sz; pot += sp; }
-        __syncwarp();
-    }
-    return make_double4(ax, ay, az, pot);
 }
 
 // Staged node rows of the current batch (one entry per lane).
@@ -311,13 +322,16 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             const int *__restrict__ targets,     // original indices of the walk targets
             const double *__restrict__ pos, const float *__restrict__ mass,
             const double *__restrict__ oldacc, const float *__restrict__ gtab,
-            WalkPar P, int full_tree, double cbrtrho0,
-            double *__restrict__ acc_out, double *__restrict__ pot_out, int4 *__restrict__ counts_out)
+            WalkPar P,
+            unsigned *__restrict__ pool, int pool_cap,      // chunk pool of the piece lists, capacity in chunks
+            int *__restrict__ pool_ctl,                     // [0] next free chunk, [1] error bits
+            int *__restrict__ chunk_tab,                    // [warp][WALK_MAXCH] chunk ids
+            int *__restrict__ piece_cnt,                    // [target slot] pieces in the list
+            double4 *__restrict__ partial,                  // [target slot] sums over accepted nodes {ax, ay, az, pot}
+            int4 *__restrict__ counts_out)
 {
     __shared__ double4 tab[B200_SR_NTAB];
-    __shared__ int2 s_leaf_all[WALK_WARPS][LIST_CAP];
-    __shared__ int2 s_tl_all[WALK_WARPS][LIST_CAP + 16];
-    __shared__ unsigned s_mask_all[WALK_WARPS][LIST_CAP];
+    __shared__ int s_ctab_all[WALK_WARPS][WALK_MAXCH];
     __shared__ int s_stk_node_all[WALK_WARPS][WALK_STACK];
     __shared__ unsigned s_stk_mask_all[WALK_WARPS][WALK_STACK];
     __shared__ BatchEntry s_ent_all[WALK_WARPS];
@@ -328,14 +342,12 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
     }
     __syncthreads();
     const int wib = threadIdx.x >> 5;
-    int2 *s_leaf = s_leaf_all[wib];
-    int2 *s_tl = s_tl_all[wib];
-    unsigned *s_mask = s_mask_all[wib];
+    int *s_ctab = s_ctab_all[wib];
     int *s_stk_node = s_stk_node_all[wib];
     unsigned *s_stk_mask = s_stk_mask_all[wib];
     BatchEntry &s_ent = s_ent_all[wib];
-    int nlist = 0;
-    unsigned anymask = 0;
+    int mycnt = 0;          // pieces in this lane's list
+    int nch_alloc = 0;      // chunks this warp owns (warp-uniform)
 
     const int lane = threadIdx.x & 31;
     const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -373,15 +385,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
     if(lane == 0) { s_stk_node[0] = 0; s_stk_mask[0] = validmask; }
     __syncwarp();
     while(true) {
-        if(sp == 0 || nlist > LIST_CAP - 32) {      // single flush site (warp-uniform)
-            if(nlist > 0) {
-                const double4 d = eval_leaf_list(s_leaf, s_mask, s_tl, nlist, anymask, spart, P, tab, lane, px, py, pz);
-                ax += d.x; ay += d.y; az += d.z; pot += d.w;
-            }
-            __syncwarp();
-            nlist = 0; anymask = 0;
-            if(sp == 0) break;
-        }
+        if(sp == 0) break;
         int nb = sp < 32 ? sp : 32;
         {
             const int room = (WALK_STACK - WALK_RESERVE - sp) / 7;
@@ -430,28 +434,40 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             const bool wantopen = awake && decision == 2;
             const unsigned openmask = __ballot_sync(0xffffffffu, wantopen);
             if(awake && decision == 1) {
-                monopole(dx, dy, dz, r2, A.w, P, tab, ax, ay, az, pot);
+                monopole(dx, dy, dz, r2, A.w, P, TabD4{tab}, ax, ay, az, pot);
                 if(COUNT) n_acc++;
             }
             if(COUNT && awake && decision == 0) n_disc++;
             if(openmask == 0) continue;
             if(eflags & 1) {
-                // particle leaf: remember it with the lanes that opened it (gravshort-tree.c:344-352)
-                const int2 li = make_int2(M.x, M.y);
-                if(COUNT && wantopen) n_part += li.y;
-                anymask |= openmask;
-                // pieces of <= 8 particles (only leaves at the key-depth limit hold more)
-                for(int o = 0; o < li.y || o == 0; o += 8) {
-                    if(nlist == LIST_CAP) {          // only reachable through such oversized leaves
-                        const double4 d = eval_leaf_list(s_leaf, s_mask, s_tl, nlist, anymask, spart, P, tab, lane, px, py, pz);
-                        ax += d.x; ay += d.y; az += d.z; pot += d.w;
+                // particle leaf (gravshort-tree.c:344-352): every lane that opened it appends the
+                // piece(s) to its own list; pieces of <= 8 particles (only leaves at the key-depth
+                // limit hold more)
+                if(COUNT && wantopen) n_part += M.y;
+                for(int o = 0; o < M.y; o += 8) {
+                    const int c = M.y - o < 8 ? M.y - o : 8;
+                    const int needch = (int) __reduce_max_sync(0xffffffffu, wantopen ? (unsigned) (mycnt >> CH_SHIFT) : 0u);
+                    if(needch >= nch_alloc) {               // warp-uniform; once per CH_SLOTS pieces of the longest list
+                        if(needch >= WALK_MAXCH) { if(lane == 0) atomicOr(pool_ctl + 1, 2); }
+                        else {
+                            if(lane == 0)
+                                for(int ch = nch_alloc; ch <= needch; ch++) {
+                                    const int id = atomicAdd(pool_ctl, 1);
+                                    s_ctab[ch] = id;
+                                    chunk_tab[(size_t) group * WALK_MAXCH + ch] = id;
+                                }
+                            nch_alloc = needch + 1;
+                        }
                         __syncwarp();
-                        nlist = 0;
                     }
-                    const int c = li.y - o < 8 ? li.y - o : 8;
-                    if(lane == 0) { s_leaf[nlist] = make_int2(li.x + o, c); s_mask[nlist] = openmask; }
-                    __syncwarp();
-                    nlist++;
+                    if(wantopen) {
+                        const int ch = mycnt >> CH_SHIFT;
+                        if(ch < nch_alloc) {
+                            const int id = s_ctab[ch];
+                            if(id < pool_cap) pool[(size_t) id * CH_WORDS + (mycnt & (CH_SLOTS - 1)) * 32 + lane] = PIECE(M.x + o, c);
+                        }
+                        mycnt++;
+                    }
                 }
             } else {
                 if(COUNT && wantopen) n_open++;
@@ -477,15 +493,84 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
         sp += total;
         __syncwarp();
     }
+    // hand over to k_grav_pairs (target-slot order: coalesced)
+    if(valid) {
+        partial[tslot] = make_double4(ax, ay, az, pot);
+        piece_cnt[tslot] = mycnt;
+        if(COUNT) counts_out[me] = make_int4(n_acc, n_open, n_disc, n_part);
+    }
+}
+
+// Pair sums over the piece lists written by k_grav_walk, then grav_short_postprocess
+// (gravshort.h:47-67).
+__global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_MINB)
+k_grav_pairs(const double2 *__restrict__ spart_xy, const double2 *__restrict__ spart_zm, const int *__restrict__ targets,
+             const double *__restrict__ pos, const float *__restrict__ mass, const float *__restrict__ gtab,
+             WalkPar P, int full_tree, double cbrtrho0,
+             const unsigned *__restrict__ pool, const int *__restrict__ chunk_tab, const int *__restrict__ piece_cnt,
+             const double4 *__restrict__ partial, double *__restrict__ acc_out, double *__restrict__ pot_out)
+{
+    extern __shared__ float4 s_tabx8[];                 // [B200_SR_NTAB][8], 64 KB
+    __shared__ int s_ctab_all[PAIR_WARPS][WALK_MAXCH];
+    for(int k = threadIdx.x; k < B200_SR_NTAB * 8; k += blockDim.x) {
+        const int t = k >> 3, t1 = t + 1 < B200_SR_NTAB ? t + 1 : t;
+        // row NTAB-1 all zero: pairs beyond the table (gravity.c:60-61) contribute nothing
+        s_tabx8[k] = t + 1 < B200_SR_NTAB ? make_float4(gtab[t], gtab[t1], gtab[B200_SR_NTAB + t], gtab[B200_SR_NTAB + t1])
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    int *s_ctab = s_ctab_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tslot = group * 32 + lane;
+    const bool valid = tslot < P.ntargets;
+    if(group * 32 >= P.ntargets) return;    // warp-uniform
+    int me = -1, mycnt = 0;
+    double px = 0, py = 0, pz = 0;
+    double4 acc = make_double4(0, 0, 0, 0);
+    if(valid) {
+        me = targets[tslot];
+        px = pos[3 * (int64_t) me]; py = pos[3 * (int64_t) me + 1]; pz = pos[3 * (int64_t) me + 2];
+        mycnt = piece_cnt[tslot];
+        acc = partial[tslot];
+    }
+    const int maxcnt = (int) __reduce_max_sync(0xffffffffu, (unsigned) mycnt);
+    const int nch = (maxcnt + CH_SLOTS - 1) >> CH_SHIFT;
+    for(int c = lane; c < nch; c += 32) s_ctab[c] = chunk_tab[(size_t) group * WALK_MAXCH + c];
+    __syncwarp();
+
+    PieceList L;
+    L.pool = pool; L.ctab = s_ctab; L.empty = PIECE(P.sentinel, 0);
+    const int g = lane >> 3, slot = lane & 7;
+    const TabF4x8 tab{s_tabx8 + slot};
+    const SrcArrays spart{spart_xy, spart_zm};
+    for(int t = 0; t < 32; t++) {
+        const int nt = __shfl_sync(0xffffffffu, mycnt, t);
+        if(nt == 0) continue;                           // warp-uniform
+        const double tx = __shfl_sync(0xffffffffu, px, t);
+        const double ty = __shfl_sync(0xffffffffu, py, t);
+        const double tz = __shfl_sync(0xffffffffu, pz, t);
+        L.t = t; L.nt = nt;
+        double sx = 0, sy = 0, sz = 0, sp = 0;
+        // No periodic wrap is needed when the target is farther than the reach of
+        // the window table from every face: a pair that NEAREST would wrap is then
+        // beyond the table on both sides of the wrap and contributes nothing.
+        const bool central = tx >= P.wrap_lo && tx <= P.wrap_hi && ty >= P.wrap_lo && ty <= P.wrap_hi &&
+                             tz >= P.wrap_lo && tz <= P.wrap_hi;
+        if(central) pair_sum<false>(L, g, slot, spart, P, tab, tx, ty, tz, sx, sy, sz, sp);
+        else pair_sum<true>(L, g, slot, spart, P, tab, tx, ty, tz, sx, sy, sz, sp);
+        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); sp = warp_sum(sp);
+        if(lane == t) { acc.x += sx; acc.y += sy; acc.z += sz; acc.w += sp; }
+    }
     if(valid) {
         // grav_short_postprocess gravshort.h:47-67
         if(acc_out) {
-            acc_out[3 * (int64_t) me] = ax * P.G;
-            acc_out[3 * (int64_t) me + 1] = ay * P.G;
-            acc_out[3 * (int64_t) me + 2] = az * P.G;
+            acc_out[3 * (int64_t) me] = acc.x * P.G;
+            acc_out[3 * (int64_t) me + 1] = acc.y * P.G;
+            acc_out[3 * (int64_t) me + 2] = acc.z * P.G;
         }
         if(pot_out) {
-            double p = pot;
+            double p = acc.w;
             if(full_tree) {
                 const double m = (double) mass[me];
                 p += m / (P.h / 2.8);
@@ -494,7 +579,6 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             }
             pot_out[me] = p;
         }
-        if(COUNT) counts_out[me] = make_int4(n_acc, n_open, n_disc, n_part);
     }
 }
 
@@ -632,19 +716,55 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
     P.ntargets = (int) nt;
     if(nt == 0) return 0;
 
-    timer_start(E, T_WALK);
+    if(E->tree_np + B200_SPART_PAD >= (1 << 28))
+        return failmsg(E, "b200_grav_short_tree: more than 2^28 particles in one tree (piece entries hold a 28-bit particle offset)");
     const int bs = 128;
     const int64_t nwarps = (nt + 31) / 32;
     const unsigned nb = (unsigned) ((nwarps * 32 + bs - 1) / bs);
+    // Piece-list storage.  The pool is sized from the last walk's use (first call: 3 chunks
+    // per warp) and grown when the walk reports that it ran out; the walk is then repeated.
+    CK(E->walk_chunktab.ensure((size_t) nwarps * WALK_MAXCH));
+    CK(E->walk_cnt.ensure((size_t) nwarps * 32));
+    CK(E->walk_partial.ensure((size_t) nwarps * 32 * 4));
+    CK(E->scratch_i.ensure(128));
+    int *ctl = E->scratch_i.p + 64;
+    size_t want = (size_t) (E->walk_chunks_per_warp * (double) nwarps) + 1024;
+    timer_start(E, T_WALK);
+    for(int attempt = 0;; attempt++) {
+        CK(E->walk_pool.ensure(want * CH_WORDS));
+        const size_t capz = E->walk_pool.cap / CH_WORDS;
+        const int cap = (int) (capz < (size_t) 0x7fffffff ? capz : (size_t) 0x7fffffff);
+        CK(cudaMemsetAsync(ctl, 0, 2 * sizeof(int), E->stream));
 #define WALK_ARGS (const double4 *) E->nodeA.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, \
                   (const int4 *) E->nodeK.p, (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p, \
-                  P, E->tree_full ? 1 : 0, cbrtrho0, d_acc, d_pot
-    if(d_counts) k_grav_walk<true><<<nb, bs, 0, E->stream>>>(WALK_ARGS, (int4 *) d_counts);
-    else k_grav_walk<false><<<nb, bs, 0, E->stream>>>(WALK_ARGS, nullptr);
+                  P, E->walk_pool.p, cap, ctl, E->walk_chunktab.p, E->walk_cnt.p, (double4 *) E->walk_partial.p
+        if(d_counts) k_grav_walk<true><<<nb, bs, 0, E->stream>>>(WALK_ARGS, (int4 *) d_counts);
+        else k_grav_walk<false><<<nb, bs, 0, E->stream>>>(WALK_ARGS, nullptr);
 #undef WALK_ARGS
-    CKL(E);
+        CKL(E);
+        int h[2] = {0, 0};
+        CK(cudaMemcpyAsync(h, ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+        CK(cudaStreamSynchronize(E->stream));
+        if(h[1] & 2)
+            return failmsg(E, "b200_grav_short_tree: a particle opened more than " + std::to_string(CH_SLOTS * WALK_MAXCH) +
+                              " leaf pieces (raise WALK_MAXCH)");
+        E->walk_chunks_per_warp = 1.15 * (double) h[0] / (double) nwarps + 0.05;
+        if(h[0] <= cap) break;
+        if(attempt >= 2) return failmsg(E, "b200_grav_short_tree: piece pool kept overflowing");
+        want = (size_t) h[0] + (size_t) h[0] / 8 + 1024;
+    }
     timer_stop(E, T_WALK);
+    timer_start(E, T_WALK_POST);
+    const size_t pair_smem = (size_t) B200_SR_NTAB * 8 * sizeof(float4);
+    static bool pair_attr = false;
+    if(!pair_attr) { CK(cudaFuncSetAttribute(k_grav_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pair_smem)); pair_attr = true; }
+    const unsigned nbp = (unsigned) ((nwarps + PAIR_WARPS - 1) / PAIR_WARPS);
+    k_grav_pairs<<<nbp, PAIR_WARPS * 32, pair_smem, E->stream>>>((const double2 *) E->spart_xy.p, (const double2 *) E->spart_zm.p, tg, E->pos.p, E->mass.p, E->srtab.p, P, E->tree_full ? 1 : 0, cbrtrho0,
+                                           E->walk_pool.p, E->walk_chunktab.p, E->walk_cnt.p, (const double4 *) E->walk_partial.p, d_acc, d_pot);
+    CKL(E);
+    timer_stop(E, T_WALK_POST);
     return 0;
 }
+
 
 } // namespace b200
