@@ -36,6 +36,11 @@ METRIC = "particles/sec per force step (PM+tree)"
 UNIT = "particles/s"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+# (profiles/r01_*_ncu_summary.txt), 256^3 workload
+NCU_TRAFFIC = {"k_grav_pairs": 6.84e9, "k_grav_walk": 6.22e9}
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -262,9 +267,8 @@ def run_sharded(args, rank, world, local, dist, pkg, ics, W, K):
     dist.all_reduce(tl)
     if rank == 0:
         hbm, how = peaks()
-        walk_ms = phase["walk"]
-        nn = int(s.tree_info.numnodes)
-        walk_bytes = 72.0 * n_own + 80.0 * nn
+        pairs_ms = phase["walk_post"]
+        pairs_bytes = 4.0 * phase["walk_pieces"] + 124.0 * n_own
         out = {
             "metric": METRIC, "value": total * K / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -282,9 +286,10 @@ def run_sharded(args, rank, world, local, dist, pkg, ics, W, K):
                     "api": "ShardedTreePM.load + force_step (pinned host pos/mass/oldacc in, acc/gpm/pot out), per rank"},
             "gpu_launches": int(tl.item()),
             "clocks": clocks,
-            "roofline": {"kernel": "k_grav_walk", "bound": "hbm", "achieved": walk_bytes / (walk_ms * 1e-3) / 1e9, "peak": hbm,
-                         "unit": "GB/s", "frac": walk_bytes / (walk_ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": how,
-                         "note": "rank 0; latency/fp64-issue bound pair summation; compulsory bytes only (SURVEY 8d K8)"},
+            "roofline": {"kernel": "k_grav_pairs", "bound": "hbm", "achieved": pairs_bytes / (pairs_ms * 1e-3) / 1e9, "peak": hbm,
+                         "unit": "GB/s", "frac": pairs_bytes / (pairs_ms * 1e-3) / 1e9 / hbm, "traffic": None, "peak_source": how,
+                         "note": "rank 0; pair summation bound by the fp64/conversion pipes and the L1 data path, not HBM; "
+                                 "compulsory bytes only (SURVEY 8d K8)"},
             "phases_ms": phase,
             "timing": "wall clock between device synchronisations, max over ranks (engine stream + torch stream interleave)",
         }
@@ -430,20 +435,30 @@ def main():
     e2e_v = total * Ke / (ms_e2e * 1e-3)
     hbm, how = peaks()
     walk_ms = phase["walk"]
+    pairs_ms = phase["walk_post"]
     nn = int(info.numnodes)
-    # 40 B in + 32 B out per active particle + node rows read once (80 B here)
-    walk_bytes = 72.0 * n + 80.0 * nn
-    walk_gbs = walk_bytes / (walk_ms * 1e-3) / 1e9
+    pieces = phase["walk_pieces"]
+    # SURVEY 8d K8 split over the two kernels.  k_grav_walk: 40 B in per target + node rows read once
+    # (80 B here) + its outputs (36 B partial sums/count per target, 4 B per queued leaf piece).
+    # k_grav_pairs: the same lists and partial sums in, the source rows read once (32 B), 24 B
+    # position in and 32 B result out per target.
+    walk_bytes = 40.0 * n + 80.0 * nn + 36.0 * n + 4.0 * pieces
+    pairs_bytes = 4.0 * pieces + 36.0 * n + 32.0 * n + 24.0 * n + 32.0 * n
+    pairs_gbs = pairs_bytes / (pairs_ms * 1e-3) / 1e9
+    pair_slots = 8.0 * pieces          # pair evaluations issued (one source slot per lane)
     N3 = float(nmesh) ** 3
     Mc = float(nmesh) ** 2 * (nmesh // 2 + 1)
     kern = {
         "k_grav_walk": {"ms": walk_ms, "alg_bytes": walk_bytes},
+        "k_grav_pairs": {"ms": pairs_ms, "alg_bytes": pairs_bytes, "pair_evaluations": pair_slots,
+                         "Gpairs_per_s": pair_slots / (pairs_ms * 1e-3) / 1e9},
         "k_pm_deposit+clear": {"ms": phase["pm_deposit"], "alg_bytes": 156.0 * n + 8 * N3},
         "cufft_d2z": {"ms": phase["pm_fft_forward"], "alg_bytes": 16 * N3},
         "k_pm_potential_transfer": {"ms": phase["pm_transfer"], "alg_bytes": 32 * Mc},
         "cufft_z2d": {"ms": phase["pm_fft_inverse"], "alg_bytes": 16 * N3},
-        "k_pm_gradient": {"ms": phase["pm_gradient"], "alg_bytes": 32 * N3},
-        "k_pm_readout": {"ms": phase["pm_readout"], "alg_bytes": 312.0 * n},
+        # difference + readout fused: the potential mesh is read once (8 B/cell) instead of the
+        # 32 B/cell of the three force meshes, plus the particle side of the gather
+        "k_pm_readout_fused": {"ms": phase["pm_gradient"] + phase["pm_readout"], "alg_bytes": 8 * N3 + (24.0 + 32.0) * n},
         "tree_build": {"ms": phase["tree_total"], "alg_bytes": (96 + 28 + 32) * float(n) + 80.0 * nn},
     }
     for k in kern.values():
@@ -464,9 +479,11 @@ def main():
                 "check_vs_device_arm": chk},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "k_grav_walk", "bound": "hbm", "achieved": walk_gbs, "peak": hbm, "unit": "GB/s",
-                     "frac": walk_gbs / hbm, "traffic": None, "peak_source": how,
-                     "note": "latency/fp64-issue bound pair summation; compulsory bytes only (SURVEY 8d K8)"},
+        "roofline": {"kernel": "k_grav_pairs", "bound": "hbm", "achieved": pairs_gbs, "peak": hbm, "unit": "GB/s",
+                     "frac": pairs_gbs / hbm, "traffic": NCU_TRAFFIC.get("k_grav_pairs"), "peak_source": how,
+                     "note": "dominant kernel of the step; a pair summation whose operands hit L1/L2, bound by the fp64 and "
+                             "conversion pipes and the L1 data path, not by HBM (ncu: profiles/); bytes = SURVEY 8d K8 compulsory "
+                             "traffic of this kernel; see kernels[] for the HBM-bound PM kernels"},
         "phases_ms": phase, "ms_per_step_serial": ms_serial,
         "kernels": kern,
         "tree": {"numnodes": nn, "maxdepth": int(info.maxdepth)},

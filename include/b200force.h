@@ -281,9 +281,12 @@ int b200_pmslab_readout_dev(b200_ctx *ctx, int64_t n_own, double *gravpm_out, do
 typedef struct b200_timings {
     double pm_deposit, pm_fft_forward, pm_transfer, pm_fft_inverse, pm_gradient, pm_readout, pm_total;
     double tree_keys, tree_sort, tree_nodes, tree_moments, tree_total;
-    double walk, walk_post;
+    double walk, walk_post;        /* k_grav_walk (traversal, node terms), k_grav_pairs (pair sums + postprocess) */
     double h2d, d2h;
     double sph_density, sph_hydro;
+    /* statistics of the last tree walk: leaf pieces (<= 8 source particles each) queued for the
+     * pair kernel = ninteractions / 8 rounded up per leaf, and the bytes of list storage used */
+    double walk_pieces, walk_list_bytes;
 } b200_timings;
 int b200_get_timings(const b200_ctx *ctx, b200_timings *t);
 

@@ -67,7 +67,7 @@ class Timings(C.Structure):
     _fields_ = [(k, C.c_double) for k in (
         "pm_deposit", "pm_fft_forward", "pm_transfer", "pm_fft_inverse", "pm_gradient", "pm_readout", "pm_total",
         "tree_keys", "tree_sort", "tree_nodes", "tree_moments", "tree_total", "walk", "walk_post", "h2d", "d2h",
-        "sph_density", "sph_hydro")]
+        "sph_density", "sph_hydro", "walk_pieces", "walk_list_bytes")]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

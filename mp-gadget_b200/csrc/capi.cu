@@ -139,6 +139,7 @@ static int collect_timings(Engine *E)
     t.walk = timer_ms(E, T_WALK); t.walk_post = timer_ms(E, T_WALK_POST);
     t.h2d = timer_ms(E, T_H2D); t.d2h = timer_ms(E, T_D2H);
     t.sph_density = timer_ms(E, T_SPH_DENSITY); t.sph_hydro = timer_ms(E, T_SPH_HYDRO);
+    t.walk_pieces = E->walk_pieces; t.walk_list_bytes = 4.0 * 32 * (1 << 4) * (double) E->walk_chunks;
     return 0;
 }
 
@@ -328,7 +329,11 @@ int b200_pm_copy_mesh(b200_ctx *ctx, int which, double *mesh_out)
     const double *src = nullptr;
     if(which == 0) { if(int rc = pm_deposit(E)) return rc; src = E->mesh.p; }
     else if(which == 1) { if(!E->potential_valid) return failmsg(E, "b200_pm_copy_mesh: no potential (call b200_pm_force)"); src = E->mesh.p; }
-    else if(which >= 2 && which <= 4) { if(!E->potential_valid) return failmsg(E, "b200_pm_copy_mesh: no force mesh"); src = E->fmesh.p + (which - 2) * N3; }
+    else if(which >= 2 && which <= 4) {
+        if(!E->potential_valid) return failmsg(E, "b200_pm_copy_mesh: no force mesh");
+        if(!E->fmesh_valid) if(int rc = pm_force_meshes(E)) return rc;
+        src = E->fmesh.p + (which - 2) * N3;
+    }
     else return failmsg(E, "b200_pm_copy_mesh: which must be 0..4");
     CK(cudaMemcpyAsync(mesh_out, src, N3 * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));

@@ -84,6 +84,8 @@ struct Engine {
     DevBuf<double> ktab;       // per-dimension deconvolution factor 1/sinc^2, [Nmesh]
     DevBuf<uint8_t> fftwork;
     bool potential_valid = false;
+    bool pm_fused = true;      // difference + readout in one kernel, no force meshes (B200_PM_FUSED=0: separate passes)
+    bool fmesh_valid = false;
     SlabPM *slab = nullptr;
 
     // ---- tree ----
@@ -134,6 +136,8 @@ struct Engine {
     DevBuf<int> walk_chunktab, walk_cnt;
     DevBuf<double> walk_partial;
     double walk_chunks_per_warp = 6.0;
+    double walk_pieces = 0;     // leaf pieces (<= 8 particles each) queued by the last walk
+    int walk_chunks = 0;        // pool chunks it used
 
     Timer timers[T_COUNT];
     b200_timings last = {};
@@ -154,6 +158,7 @@ int pm_init(Engine *E, double Box, double Asmth, int Nmesh, double G);
 void pm_destroy(Engine *E);
 int pm_deposit(Engine *E);
 int pm_force(Engine *E, double *d_gravpm, double *d_pot);   // device outputs, [n][3] / [n], may be null
+int pm_force_meshes(Engine *E);
 int pm_cell_index(Engine *E, int32_t *d_icell);
 
 // tree (tree_build.cu)

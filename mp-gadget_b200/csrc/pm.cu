@@ -23,6 +23,7 @@
 // meshes to rounding with 2 FFTs per step instead of 5.
 #include "engine.h"
 #include <math.h>
+#include <stdlib.h>
 #include <stdio.h>
 
 namespace b200 {
@@ -159,6 +160,53 @@ k_pm_gradient(const double *__restrict__ pot, int N, double inv12h,
     fz[base] = -gz * inv12h;
 }
 
+// readout_potential / readout_force_{x,y,z} (gravpm.c:499-510) in one pass with the 4-point
+// difference of the potential taken on the fly at each of the 8 CIC corners (the arithmetic of
+// k_pm_gradient followed by k_pm_readout, value for value): no force meshes are written or
+// read.  104 potential loads per particle; neighbouring particles share them through L1/L2.
+__global__ void __launch_bounds__(128)
+k_pm_readout_fused(const double *__restrict__ pos, const uint8_t *__restrict__ flags, int64_t n,
+                   double cellsize, int N, const double *__restrict__ pot, double inv12h,
+                   double *__restrict__ gravpm, double *__restrict__ potout)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    double a0 = 0, a1 = 0, a2 = 0, p = 0;
+    if(!(flags[i] & 3)) {
+        int ic[3]; double res[3];
+        cic_cell(pos + 3 * i, cellsize, ic, res);
+        const double wx[2] = {1 - res[0], res[0]};
+        const double wy[2] = {1 - res[1], res[1]};
+        const double wz[2] = {1 - res[2], res[2]};
+        const size_t NN = (size_t) N * N;
+        // the 6 planes / rows / columns the two corners per axis need
+        int xs[6], ys[6], zs[6];
+#pragma unroll
+        for(int k = 0; k < 6; k++) { xs[k] = wrapi(ic[0] - 2 + k, N); ys[k] = wrapi(ic[1] - 2 + k, N); zs[k] = wrapi(ic[2] - 2 + k, N); }
+#pragma unroll
+        for(int c = 0; c < 8; c++) {
+            const int ox = c & 1, oy = (c >> 1) & 1, oz = (c >> 2) & 1;
+            const int jx = 2 + ox, jy = 2 + oy, jz = 2 + oz;
+            const size_t rowyz = (size_t) ys[jy] * N + zs[jz];
+            const size_t rowxz = (size_t) xs[jx] * NN + zs[jz];
+            const size_t rowxy = (size_t) xs[jx] * NN + (size_t) ys[jy] * N;
+            const double gx = 8.0 * (__ldg(pot + xs[jx + 1] * NN + rowyz) - __ldg(pot + xs[jx - 1] * NN + rowyz))
+                            - (__ldg(pot + xs[jx + 2] * NN + rowyz) - __ldg(pot + xs[jx - 2] * NN + rowyz));
+            const double gy = 8.0 * (__ldg(pot + rowxz + (size_t) ys[jy + 1] * N) - __ldg(pot + rowxz + (size_t) ys[jy - 1] * N))
+                            - (__ldg(pot + rowxz + (size_t) ys[jy + 2] * N) - __ldg(pot + rowxz + (size_t) ys[jy - 2] * N));
+            const double gz = 8.0 * (__ldg(pot + rowxy + zs[jz + 1]) - __ldg(pot + rowxy + zs[jz - 1]))
+                            - (__ldg(pot + rowxy + zs[jz + 2]) - __ldg(pot + rowxy + zs[jz - 2]));
+            const double w = __dmul_rn(__dmul_rn(wx[ox], wy[oy]), wz[oz]);
+            a0 = __dadd_rn(a0, __dmul_rn(w, -gx * inv12h));
+            a1 = __dadd_rn(a1, __dmul_rn(w, -gy * inv12h));
+            a2 = __dadd_rn(a2, __dmul_rn(w, -gz * inv12h));
+            p  = __dadd_rn(p,  __dmul_rn(w, __ldg(pot + xs[jx] * NN + rowyz)));
+        }
+    }
+    if(gravpm) { gravpm[3 * i] = a0; gravpm[3 * i + 1] = a1; gravpm[3 * i + 2] = a2; }
+    if(potout) potout[i] = p;
+}
+
 // readout_potential / readout_force_{x,y,z} (gravpm.c:499-510) in one pass.
 __global__ void __launch_bounds__(256)
 k_pm_readout(const double *__restrict__ pos, const uint8_t *__restrict__ flags, int64_t n,
@@ -227,7 +275,8 @@ int pm_init(Engine *E, double Box, double Asmth, int Nmesh, double G)
         const size_t N = Nmesh, Nz = Nmesh / 2 + 1;
         CK(E->mesh.ensure(N * N * N));
         CK(E->cplx.ensure(2 * N * N * Nz));
-        CK(E->fmesh.ensure(3 * N * N * N));
+        E->pm_fused = !(getenv("B200_PM_FUSED") && atoi(getenv("B200_PM_FUSED")) == 0);
+        if(!E->pm_fused) CK(E->fmesh.ensure(3 * N * N * N));
         size_t ws_f = 0, ws_i = 0;
         CKF(cufftCreate(&E->plan_fwd));
         CKF(cufftCreate(&E->plan_inv));
@@ -284,6 +333,22 @@ int pm_cell_index(Engine *E, int32_t *d_icell)
     return 0;
 }
 
+// The three force meshes from the potential mesh (parity hook and the unfused path).
+int pm_force_meshes(Engine *E)
+{
+    const int N = E->Nmesh;
+    const size_t N3 = (size_t) N * N * N;
+    if(!E->potential_valid) return failmsg(E, "pm_force_meshes: no potential");
+    CK(E->fmesh.ensure(3 * N3));
+    double *fx = E->fmesh.p, *fy = fx + N3, *fz = fy + N3;
+    const double h = E->Box / N;
+    dim3 grid((N + 255) / 256, N, N);
+    k_pm_gradient<<<grid, 256, 0, E->stream>>>(E->mesh.p, N, 1.0 / (12.0 * h), fx, fy, fz);
+    CKL(E);
+    E->fmesh_valid = true;
+    return 0;
+}
+
 int pm_force(Engine *E, double *d_gravpm, double *d_pot)
 {
     if(E->Nmesh == 0) return failmsg(E, "b200_pm_force: call b200_pm_init first");
@@ -312,21 +377,29 @@ int pm_force(Engine *E, double *d_gravpm, double *d_pot)
     timer_stop(E, T_PM_FFT_INV);
     E->potential_valid = true;
 
+    E->fmesh_valid = false;
+    const double h = E->Box / N;
+    if(E->pm_fused) {
+        timer_start(E, T_PM_GRADIENT); timer_stop(E, T_PM_GRADIENT);
+        timer_start(E, T_PM_READOUT);
+        if(E->n > 0 && (d_gravpm || d_pot)) {
+            const int bs = 128;
+            k_pm_readout_fused<<<(unsigned) ((E->n + bs - 1) / bs), bs, 0, E->stream>>>(E->pos.p, E->flags.p, E->n, h, N, E->mesh.p,
+                                                                                    1.0 / (12.0 * h), d_gravpm, d_pot);
+            CKL(E);
+        }
+        timer_stop(E, T_PM_READOUT);
+        return 0;
+    }
+    timer_start(E, T_PM_GRADIENT);
+    if(int rc = pm_force_meshes(E)) return rc;
+    timer_stop(E, T_PM_GRADIENT);
     const size_t N3 = (size_t) N * N * N;
     double *fx = E->fmesh.p, *fy = fx + N3, *fz = fy + N3;
-    timer_start(E, T_PM_GRADIENT);
-    {
-        const double h = E->Box / N;
-        dim3 grid((N + 255) / 256, N, N);
-        k_pm_gradient<<<grid, 256, 0, E->stream>>>(E->mesh.p, N, 1.0 / (12.0 * h), fx, fy, fz);
-        CKL(E);
-    }
-    timer_stop(E, T_PM_GRADIENT);
-
     timer_start(E, T_PM_READOUT);
     if(E->n > 0 && (d_gravpm || d_pot)) {
         const int bs = 256;
-        k_pm_readout<<<(unsigned) ((E->n + bs - 1) / bs), bs, 0, E->stream>>>(E->pos.p, E->flags.p, E->n, E->Box / N, N,
+        k_pm_readout<<<(unsigned) ((E->n + bs - 1) / bs), bs, 0, E->stream>>>(E->pos.p, E->flags.p, E->n, h, N,
                                                                           E->mesh.p, fx, fy, fz, d_gravpm, d_pot);
         CKL(E);
     }

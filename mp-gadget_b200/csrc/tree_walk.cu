@@ -34,6 +34,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string>
+#include <string.h>
 #include <cub/device/device_select.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
@@ -166,6 +167,8 @@ template <bool WRAP>
 __device__ __forceinline__ int classify(const double4 &A, const double4 &B, double px, double py, double pz,
                                         double aold, const WalkPar &P, double &dx, double &dy, double &dz, double &r2)
 {
+    // Straight-line (two of these are interleaved by the caller); the same comparisons in the
+    // same arithmetic as the early-exit form of the reference.
     dx = A.x - px; dy = A.y - py; dz = A.z - pz;
     double cxd = B.x - px, cyd = B.y - py, czd = B.z - pz;
     if(WRAP) {
@@ -175,24 +178,19 @@ __device__ __forceinline__ int classify(const double4 &A, const double4 &B, doub
     cxd = fabs(cxd); cyd = fabs(cyd); czd = fabs(czd);
     r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     const double len = B.w;
-    if(r2 > P.rcut2) {
-        const double eff = __dadd_rn(P.rcut, __dmul_rn(0.5, len));
-        if((cxd > eff) || (cyd > eff) || (czd > eff)) return 0;
-    }
+    const double eff = __dadd_rn(P.rcut, __dmul_rn(0.5, len));
+    const bool disc = (r2 > P.rcut2) & ((cxd > eff) | (cyd > eff) | (czd > eff));          // shall_we_discard_node
     const double l2 = __dmul_rn(len, len);
-    if(P.usebh == 0) {
-        const double lhs = __dmul_rn(__dmul_rn(A.w, len), len);
-        const double rhs = __dmul_rn(__dmul_rn(r2, r2), aold);
-        if(lhs > rhs) return 2;
-    }
-    {   // len*len/r2 > theta2, evaluated without the division unless within rounding of the threshold
-        const double rhs = __dmul_rn(P.theta2, r2);
-        if(l2 > rhs * (1.0 + 1e-14)) return 2;
-        if(l2 >= rhs * (1.0 - 1e-14) && __ddiv_rn(l2, r2) > P.theta2) return 2;
-    }
+    const bool orel = (P.usebh == 0) & (__dmul_rn(__dmul_rn(A.w, len), len) > __dmul_rn(__dmul_rn(r2, r2), aold));
+    // len*len/r2 > theta2, evaluated without the division unless within rounding of the threshold
+    const double rhs = __dmul_rn(P.theta2, r2);
+    const bool obh = l2 > rhs * (1.0 + 1e-14);
+    const bool nearbh = (!obh) & (l2 >= rhs * (1.0 - 1e-14));
     const double inside = __dmul_rn(0.6, len);
-    if((cxd < inside) && (cyd < inside) && (czd < inside)) return 2;
-    return 1;
+    const bool oin = (cxd < inside) & (cyd < inside) & (czd < inside);
+    bool open = orel | obh | oin;
+    if(nearbh & !open & !disc) open = __ddiv_rn(l2, r2) > P.theta2;                          // practically never
+    return disc ? 0 : (open ? 2 : 1);
 }
 
 // 1/sqrt(x) for normal positive x: the hardware seed (MUFU.RSQ64H, ~2^-22) followed by one
@@ -244,15 +242,38 @@ struct PieceList {
 // group then read 128 contiguous bytes per load (whole sectors) instead of half of 8 x 32.
 struct SrcArrays { const double2 *__restrict__ xy; const double2 *__restrict__ zm; };
 
-__device__ __forceinline__ SrcRow fetch_row(const PieceList &L, int idx, int slot, const SrcArrays &S)
+// The pair loop advances 16 pieces (= one chunk row block) per step: group g takes the
+// pieces base + g + {0, 4, 8, 12}, one particle per lane per piece.  Three stages are in
+// flight: the 4 entries of the next step, the 2 source rows of the next half step, and the
+// arithmetic of the current half step.
+struct Ent4 { unsigned e[4]; };
+struct Rows2 { SrcRow r[2]; };
+
+__device__ __forceinline__ Ent4 fetch_ent(const PieceList &L, int base, int g)
 {
-    unsigned e = L.empty;
-    if(idx < L.nt) e = L.pool[(size_t) L.ctab[idx >> CH_SHIFT] * CH_WORDS + (idx & (CH_SLOTS - 1)) * 32 + L.t];
-    SrcRow r;
-    const double2 a = S.xy[(e >> 4) + slot], b = S.zm[(e >> 4) + slot];
-    r.q = make_double4(a.x, a.y, b.x, b.y);
-    r.cnt = (int) (e & 15u);
-    return r;
+    Ent4 E;
+#pragma unroll
+    for(int k = 0; k < 4; k++) E.e[k] = L.empty;
+    if(base < L.nt) {                       // warp-uniform; base is a multiple of CH_SLOTS = 16
+        const unsigned *row = L.pool + (size_t) L.ctab[base >> CH_SHIFT] * CH_WORDS + g * 32 + L.t;
+#pragma unroll
+        for(int k = 0; k < 4; k++) if(base + g + 4 * k < L.nt) E.e[k] = row[k * 128];
+    }
+    return E;
+}
+
+__device__ __forceinline__ Rows2 fetch_rows(const Ent4 &E, int first, int slot, const SrcArrays &S)
+{
+    Rows2 R;
+#pragma unroll
+    for(int k = 0; k < 2; k++) {
+        const unsigned e = E.e[first + k];
+        const unsigned j = (e >> 4) + slot;
+        const double2 a = S.xy[j], b = S.zm[j];
+        R.r[k].q = make_double4(a.x, a.y, b.x, b.y);
+        R.r[k].cnt = (int) (e & 15u);
+    }
+    return R;
 }
 
 template <bool WRAP>
@@ -284,23 +305,23 @@ __device__ __forceinline__ void pair_step(const SrcRow &ca, const SrcRow &cb, in
     pair_fast(bx_, by_, bz_, b2, bm, P, tab, sx, sy, sz, sp);
 }
 
-// Each step the four 8-lane groups take two pieces each (8 per step), one particle
-// per lane per piece, in branch-free interleaved code; the rows of the next step
-// are already in flight (two row sets swapped by unrolling).  Pairs inside the
-// softening radius (the target itself among them) are rare and take the general path.
+// Pairs inside the softening radius (the target itself among them) are rare and take the
+// general path; everything else is branch-free, two pieces interleaved.
 template <bool WRAP>
 __device__ __forceinline__ void pair_sum(const PieceList &L, int g, int slot,
                                          const SrcArrays &spart, const WalkPar &P,
                                          const TabF4x8 &tab, double tx, double ty, double tz,
                                          double &sx, double &sy, double &sz, double &sp)
 {
-    SrcRow na = fetch_row(L, g, slot, spart), nb = fetch_row(L, 4 + g, slot, spart);
-    for(int i = 0; i < L.nt; i += 16) {
-        const SrcRow ma = fetch_row(L, i + 8 + g, slot, spart), mb = fetch_row(L, i + 12 + g, slot, spart);
-        pair_step<WRAP>(na, nb, slot, P, tab, tx, ty, tz, sx, sy, sz, sp);
-        if(i + 8 >= L.nt) break;                       // warp-uniform
-        na = fetch_row(L, i + 16 + g, slot, spart); nb = fetch_row(L, i + 20 + g, slot, spart);
-        pair_step<WRAP>(ma, mb, slot, P, tab, tx, ty, tz, sx, sy, sz, sp);
+    Ent4 eC = fetch_ent(L, 0, g), eN = fetch_ent(L, 16, g);
+    Rows2 r01 = fetch_rows(eC, 0, slot, spart);
+    for(int base = 0; base < L.nt; base += 16) {
+        const Rows2 r23 = fetch_rows(eC, 2, slot, spart);
+        pair_step<WRAP>(r01.r[0], r01.r[1], slot, P, tab, tx, ty, tz, sx, sy, sz, sp);
+        eC = eN;
+        eN = fetch_ent(L, base + 32, g);
+        r01 = fetch_rows(eC, 0, slot, spart);
+        if(base + 8 < L.nt) pair_step<WRAP>(r23.r[0], r23.r[1], slot, P, tab, tx, ty, tz, sx, sy, sz, sp);
     }
 }
 
@@ -324,7 +345,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             const double *__restrict__ oldacc, const float *__restrict__ gtab,
             WalkPar P,
             unsigned *__restrict__ pool, int pool_cap,      // chunk pool of the piece lists, capacity in chunks
-            int *__restrict__ pool_ctl,                     // [0] next free chunk, [1] error bits
+            int *__restrict__ pool_ctl,                     // [0] next free chunk, [1] error bits, [2..3] pieces written (u64)
             int *__restrict__ chunk_tab,                    // [warp][WALK_MAXCH] chunk ids
             int *__restrict__ piece_cnt,                    // [target slot] pieces in the list
             double4 *__restrict__ partial,                  // [target slot] sums over accepted nodes {ax, ay, az, pot}
@@ -415,29 +436,50 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             s_ent.M[lane] = make_int4(C.y, C.z, (int) emask0, eflags0);
         }
         __syncwarp();
-        // ---- per-target exact decisions, one staged node at a time
+        // ---- per-target exact decisions: the staged nodes that survived the bounding-box test,
+        // two at a time (independent arithmetic chains)
         unsigned myopeners = 0;       // lane l keeps the openers of entry l
-        for(int k = 0; k < nb; k++) {
-            const int4 M = s_ent.M[k];
-            const unsigned emask = (unsigned) M.z;
-            const int eflags = M.w;
-            const bool awake = (emask >> lane) & 1u;
-            if(eflags & 2) { if(COUNT && awake) n_disc++; continue; }
-            const double4 A = s_ent.A[k];
-            const double4 B = s_ent.B[k];
-            int decision = 0;
-            double dx = 0, dy = 0, dz = 0, r2 = 0;
-            if(awake) {
-                if(warp_central) decision = classify<false>(A, B, px, py, pz, aold, P, dx, dy, dz, r2);
-                else decision = classify<true>(A, B, px, py, pz, aold, P, dx, dy, dz, r2);
+        const bool dead = lane < nb && (s_ent.M[lane].w & 2);
+        unsigned live = __ballot_sync(0xffffffffu, lane < nb && !dead);
+        if(COUNT) {
+            const unsigned myemask = lane < nb ? (unsigned) s_ent.M[lane].z : 0u;
+            for(unsigned m = __ballot_sync(0xffffffffu, dead); m; m &= m - 1) {
+                const unsigned e = __shfl_sync(0xffffffffu, myemask, __ffs(m) - 1);
+                if((e >> lane) & 1u) n_disc++;
             }
-            const bool wantopen = awake && decision == 2;
-            const unsigned openmask = __ballot_sync(0xffffffffu, wantopen);
-            if(awake && decision == 1) {
-                monopole(dx, dy, dz, r2, A.w, P, TabD4{tab}, ax, ay, az, pot);
+        }
+        while(live) {
+            const int kA = __ffs(live) - 1; live &= live - 1;
+            const bool haveB = live != 0;
+            const int kB = haveB ? __ffs(live) - 1 : kA; live &= live - 1;
+            const int4 MA = s_ent.M[kA], MB = s_ent.M[kB];
+            const bool awakeA = (((unsigned) MA.z) >> lane) & 1u, awakeB = haveB && ((((unsigned) MB.z) >> lane) & 1u);
+            const double4 AA = s_ent.A[kA], BA = s_ent.B[kA], AB = s_ent.A[kB], BB = s_ent.B[kB];
+            int decA = 0, decB = 0;
+            double dxA = 0, dyA = 0, dzA = 0, r2A = 0, dxB = 0, dyB = 0, dzB = 0, r2B = 0;
+            if(warp_central) {
+                decA = classify<false>(AA, BA, px, py, pz, aold, P, dxA, dyA, dzA, r2A);
+                decB = classify<false>(AB, BB, px, py, pz, aold, P, dxB, dyB, dzB, r2B);
+            } else {
+                decA = classify<true>(AA, BA, px, py, pz, aold, P, dxA, dyA, dzA, r2A);
+                decB = classify<true>(AB, BB, px, py, pz, aold, P, dxB, dyB, dzB, r2B);
+            }
+            decA = awakeA ? decA : -1; decB = awakeB ? decB : -1;
+            const unsigned openA = __ballot_sync(0xffffffffu, decA == 2), openB = __ballot_sync(0xffffffffu, decB == 2);
+#pragma unroll
+          for(int half = 0; half < 2; half++) {
+            const int k = half ? kB : kA;
+            const int4 M = half ? MB : MA;
+            const int decision = half ? decB : decA;
+            const unsigned openmask = half ? openB : openA;
+            const int eflags = M.w;
+            const bool wantopen = decision == 2;
+            if(decision == 1) {
+                if(half) monopole(dxB, dyB, dzB, r2B, AB.w, P, TabD4{tab}, ax, ay, az, pot);
+                else monopole(dxA, dyA, dzA, r2A, AA.w, P, TabD4{tab}, ax, ay, az, pot);
                 if(COUNT) n_acc++;
             }
-            if(COUNT && awake && decision == 0) n_disc++;
+            if(COUNT && decision == 0) n_disc++;
             if(openmask == 0) continue;
             if(eflags & 1) {
                 // particle leaf (gravshort-tree.c:344-352): every lane that opened it appends the
@@ -473,6 +515,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
                 if(COUNT && wantopen) n_open++;
                 if(lane == k) myopeners = openmask;
             }
+          }
         }
         // ---- lane-parallel: push the children of opened internal nodes
         int4 k0 = make_int4(-1, -1, -1, -1), k1 = k0;
@@ -494,6 +537,10 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
         __syncwarp();
     }
     // hand over to k_grav_pairs (target-slot order: coalesced)
+    {
+        const unsigned wsum = __reduce_add_sync(0xffffffffu, (unsigned) mycnt);
+        if(lane == 0) atomicAdd((unsigned long long *) (pool_ctl + 2), (unsigned long long) wsum);      // statistics
+    }
     if(valid) {
         partial[tslot] = make_double4(ax, ay, az, pot);
         piece_cnt[tslot] = mycnt;
@@ -734,7 +781,7 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
         CK(E->walk_pool.ensure(want * CH_WORDS));
         const size_t capz = E->walk_pool.cap / CH_WORDS;
         const int cap = (int) (capz < (size_t) 0x7fffffff ? capz : (size_t) 0x7fffffff);
-        CK(cudaMemsetAsync(ctl, 0, 2 * sizeof(int), E->stream));
+        CK(cudaMemsetAsync(ctl, 0, 4 * sizeof(int), E->stream));
 #define WALK_ARGS (const double4 *) E->nodeA.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, \
                   (const int4 *) E->nodeK.p, (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p, \
                   P, E->walk_pool.p, cap, ctl, E->walk_chunktab.p, E->walk_cnt.p, (double4 *) E->walk_partial.p
@@ -742,9 +789,11 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
         else k_grav_walk<false><<<nb, bs, 0, E->stream>>>(WALK_ARGS, nullptr);
 #undef WALK_ARGS
         CKL(E);
-        int h[2] = {0, 0};
-        CK(cudaMemcpyAsync(h, ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+        int h[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(h, ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
         CK(cudaStreamSynchronize(E->stream));
+        unsigned long long pieces; memcpy(&pieces, h + 2, sizeof(pieces));
+        E->walk_pieces = (double) pieces; E->walk_chunks = h[0];
         if(h[1] & 2)
             return failmsg(E, "b200_grav_short_tree: a particle opened more than " + std::to_string(CH_SLOTS * WALK_MAXCH) +
                               " leaf pieces (raise WALK_MAXCH)");
