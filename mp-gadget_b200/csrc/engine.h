@@ -121,7 +121,10 @@ struct Engine {
     DevBuf<double> s_velpred, s_evp, s_density, s_egy, s_dhsmlfac, s_divvel, s_curlvel, s_dthsml, s_numngb, s_gradrho;
     DevBuf<double> s_svel, s_hA, s_hB;      // curve order: double4 rows
     DevBuf<double> s_out3, s_out1a, s_out1b;
-    DevBuf<int> s_outi, s_outi2;
+    DevBuf<int> s_outi, s_outi2, s_niter, s_nint;
+    DevBuf<double> s_left, s_right;       // smoothing-length brackets of the density iteration
+    double sph_chunks_per_warp = 4.0;
+    int sph_passes = 0;
     bool sph_density_done = false;
     int sph_DoEgy = 0;
 
@@ -136,6 +139,8 @@ struct Engine {
     DevBuf<int> walk_chunktab, walk_cnt;
     DevBuf<double> walk_partial;
     double walk_chunks_per_warp = 6.0;
+    size_t walk_want = 0;       // chunks to allocate for the next walk (0: estimate)
+    int walk_maxch = 128;       // chunk-table entries per warp of the current call (piece_list.cuh)
     double walk_pieces = 0;     // leaf pieces (<= 8 particles each) queued by the last walk
     int walk_chunks = 0;        // pool chunks it used
 

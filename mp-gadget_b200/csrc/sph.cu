@@ -8,17 +8,29 @@
 // treewalk_visit_ngbiter (treewalk.c:930-1007) + ngb_treefind_threads
 // (:1056-1143) with hydro_ngbiter / hydro_postprocess (hydra.c:318-528).
 //
-// One thread owns one gas particle and walks the tree depth-first exactly like
-// the reference visitor (cull_node treewalk.c:1015-1042, leaf particles in
-// insertion order), so every sum is accumulated in the reference's order.  The
-// reference re-queues unconverged particles and re-runs the whole walk
-// (NPRedo, treewalk.c:1292-1364); here the bracket/Newton update of
-// density_check_neighbours is iterated inside the thread -- the update only
-// reads the particle's own sums, so the result is the same.  Targets are taken
-// in curve order, so the threads of a warp walk nearly the same nodes.
-// This file is compiled with -fmad=false: the arithmetic is the CPU's.
-#include "engine.h"
+// Both passes use the machinery of the tree-gravity kernels (tree_walk.cu, piece_list.cuh):
+//
+//  k_sph_walk: one warp searches the tree for 32 gas particles adjacent on the curve.  Every
+//    lane applies the reference's own node test (cull_node, treewalk.c:1015-1042) with ITS
+//    smoothing length; a node is entered when any lane keeps it, and every lane that keeps a
+//    particle leaf appends the leaf piece to its own list in the global chunk pool.  The set
+//    of leaves a particle sees is therefore exactly that of the reference visitor
+//    (treewalk_visit_nolist_ngbiter :1152-1265 / ngb_treefind_threads :1056-1143).
+//  k_sph_density_pairs / k_sph_hydro_pairs: for each target the lanes of the warp are spread
+//    over the SOURCE particles of its pieces (4 pieces x 8 slots per step), evaluate
+//    density_ngbiter (density.c:424-519) / hydro_ngbiter (hydra.c:318-506) and combine the
+//    partial sums with warp reductions; the target's lane then runs the post-processing
+//    (density_postprocess / density_check_neighbours, hydro_postprocess).
+//
+// The reference re-queues unconverged particles and re-runs the walk (treewalk_do_hsml_loop,
+// treewalk.c:1269-1367); so does sph_density(): each pass walks the still-unconverged
+// particles (compacted, still in curve order) with their updated smoothing lengths.
+// Sums are accumulated in a different order than on the CPU (lane-parallel, then a butterfly):
+// the integer neighbour counts are identical, the floating-point sums agree to rounding.
+// This file is compiled with -fmad=false: the per-term arithmetic is the CPU's.
+#include "piece_list.cuh"
 #include <math.h>
+#include <cub/device/device_select.cuh>
 
 namespace b200 {
 
@@ -138,81 +150,236 @@ __device__ __forceinline__ bool cull_keep(const double4 B, double hmaxnode, doub
     return !(r2 > dist * dist);
 }
 
-__global__ void __launch_bounds__(128)
-k_sph_density(int np, const int *__restrict__ sidx, const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC,
-              const double4 *__restrict__ spart, const double4 *__restrict__ svel, const uint8_t *__restrict__ type,
-              SphDev S, int update_hsml, int DoEgy,
-              double *__restrict__ hsml, double *__restrict__ density, double *__restrict__ egy, double *__restrict__ dhsmlfac,
-              double *__restrict__ divvel, double *__restrict__ curlvel, double *__restrict__ dthsml, double *__restrict__ numngb,
-              double *__restrict__ gradrho, int *__restrict__ ninteract, int *__restrict__ niter, int *__restrict__ err)
+// Staged node rows of the current batch (one entry per lane).
+struct SphBatch {
+    double4 B[32];    // center, len
+    int4 M[32];       // pstart, count, mask of lanes that kept every ancestor, flags (bit0 leaf, bit1 culled for all lanes)
+    double H[32];     // hmax of the node (symmetric search)
+};
+
+// Neighbour search for 32 targets.  targets: sorted (curve-order) particle indices, NULL = 0..nt-1.
+// SYM: symmetric search max(h_i, hmax(node)) of the hydro pass (NGB_TREEFIND_SYMMETRIC).
+template <bool SYM>
+__global__ void __launch_bounds__(128, 5)
+k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, const int4 *__restrict__ nodeK,
+           const double *__restrict__ nodeH, const double4 *__restrict__ spart, const int *__restrict__ sidx,
+           const int *__restrict__ targets, int nt, const double *__restrict__ hsml, SphDev S, PiecePool Q)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if(j >= np) return;
-    const int me = sidx[j];
-    if(type[me] != 0) return;                      // density_haswork density.c:521-530 (gas; black holes not modelled)
-    const double4 pm = spart[j];
-    const double4 vm = svel[j];
-    double Left = 0, Right = S.box, h = hsml[me];
-    double Ngb = 0, Rho = 0, Dh = 0, EgyRho = 0, DhEgy = 0, Div = 0, R0 = 0, R1 = 0, R2 = 0, DhsmlDens = 0;
-    double G0 = 0, G1 = 0, G2 = 0;
-    int nint = 0, it = 0;
-    for(it = 0; it < SPH_MAXITER + 2; it++) {
-        Kern k; kern_init(k, h, S);
+    extern __shared__ int s_ctab_dyn[];                 // [WALK_WARPS][Q.maxch]
+    __shared__ int s_stk_node_all[WALK_WARPS][WALK_STACK];
+    __shared__ unsigned s_stk_mask_all[WALK_WARPS][WALK_STACK];
+    __shared__ SphBatch s_ent_all[WALK_WARPS];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *s_ctab = s_ctab_dyn + wib * Q.maxch;
+    int *s_stk_node = s_stk_node_all[wib];
+    unsigned *s_stk_mask = s_stk_mask_all[wib];
+    SphBatch &s_ent = s_ent_all[wib];
+    const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tslot = group * 32 + lane;
+    const bool valid = tslot < nt;
+    if(group * 32 >= nt) return;            // warp-uniform
+    double px = 0, py = 0, pz = 0, h = 0;
+    if(valid) {
+        const int j = targets ? targets[tslot] : tslot;
+        const double4 pm = spart[j];
+        px = pm.x; py = pm.y; pz = pm.z;
+        h = hsml[sidx[j]];
+    }
+    const double big = 1e300;
+    const double lox = warp_min(valid ? px : big), hix = warp_max(valid ? px : -big);
+    const double loy = warp_min(valid ? py : big), hiy = warp_max(valid ? py : -big);
+    const double loz = warp_min(valid ? pz : big), hiz = warp_max(valid ? pz : -big);
+    const double bcx = 0.5 * (lox + hix), bcy = 0.5 * (loy + hiy), bcz = 0.5 * (loz + hiz);
+    const double bhx = 0.5 * (hix - lox), bhy = 0.5 * (hiy - loy), bhz = 0.5 * (hiz - loz);
+    const double hw = warp_max(h);
+    const unsigned validmask = __ballot_sync(0xffffffffu, valid);
+    int mycnt = 0, nch_alloc = 0;
+
+    int sp = 1;
+    if(lane == 0) { s_stk_node[0] = 0; s_stk_mask[0] = validmask; }
+    __syncwarp();
+    while(sp > 0) {
+        int nb = sp < 32 ? sp : 32;
+        {
+            const int room = (WALK_STACK - WALK_RESERVE - sp) / 7;
+            if(nb > room) nb = room > 1 ? room : 1;
+        }
+        sp -= nb;
+        // ---- lane-parallel: lane l fetches entry sp + l and tests it against the warp's bounding box
+        int mynode = -1, mynch = 0;
+        if(lane < nb) {
+            mynode = s_stk_node[sp + lane];
+            const unsigned emask0 = s_stk_mask[sp + lane];
+            const double4 eB = nodeB[mynode];
+            const int4 C = nodeC[mynode];
+            const double eH = SYM ? nodeH[mynode] : 0.0;
+            int eflags0 = C.w ? 1 : 0;
+            // cull_node's per-axis test (treewalk.c:1023-1036) for the whole warp: the largest search
+            // radius of the warp against the distance from the node centre to the bounding box
+            const double dist = ((SYM && eH > hw) ? eH : hw) + 0.5 * eB.w;
+            const double lim = dist + 1e-9 * (dist + eB.w);
+            const double ex = nearest_s(eB.x - bcx, S.box, S.halfbox), ey = nearest_s(eB.y - bcy, S.box, S.halfbox),
+                         ez = nearest_s(eB.z - bcz, S.box, S.halfbox);
+            if(fabs(ex) - bhx > lim || fabs(ey) - bhy > lim || fabs(ez) - bhz > lim) eflags0 |= 2;
+            s_ent.B[lane] = eB;
+            s_ent.H[lane] = eH;
+            s_ent.M[lane] = make_int4(C.y, C.z, (int) emask0, eflags0);
+        }
+        __syncwarp();
+        // ---- per-target exact decisions
+        unsigned myopeners = 0;
+        const bool dead = lane < nb && (s_ent.M[lane].w & 2);
+        unsigned live = __ballot_sync(0xffffffffu, lane < nb && !dead);
+        while(live) {
+            const int k = __ffs(live) - 1; live &= live - 1;
+            const int4 M = s_ent.M[k];
+            const bool awake = (((unsigned) M.z) >> lane) & 1u;
+            const bool keep = awake && cull_keep(s_ent.B[k], s_ent.H[k], px, py, pz, h, SYM, S);
+            const unsigned openmask = __ballot_sync(0xffffffffu, keep);
+            if(openmask == 0) continue;
+            if(M.w & 1) {
+                for(int o = 0; o < M.y; o += 8) {
+                    const int c = M.y - o < 8 ? M.y - o : 8;
+                    piece_push(keep, PIECE(M.x + o, c), mycnt, nch_alloc, s_ctab, Q, group, lane);
+                }
+            } else if(lane == k) myopeners = openmask;
+        }
+        // ---- lane-parallel: push the children of kept internal nodes
+        int4 k0 = make_int4(-1, -1, -1, -1), k1 = k0;
+        if(myopeners) {
+            k0 = nodeK[2 * (size_t) mynode]; k1 = nodeK[2 * (size_t) mynode + 1];
+            mynch = (k0.x >= 0) + (k0.y >= 0) + (k0.z >= 0) + (k0.w >= 0) + (k1.x >= 0) + (k1.y >= 0) + (k1.z >= 0) + (k1.w >= 0);
+        }
+        int off = mynch;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if(lane >= o) off += v; }
+        const int total = __shfl_sync(0xffffffffu, off, 31);
+        if(mynch) {
+            int w = sp + off - mynch;
+            const int kids[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+            for(int c = 0; c < 8; c++) if(kids[c] >= 0) { s_stk_node[w] = kids[c]; s_stk_mask[w] = myopeners; w++; }
+        }
+        sp += total;
+        __syncwarp();
+    }
+    piece_finish(valid, tslot, mycnt, Q, lane);
+}
+
+#define NSUM_DENS 12
+
+// density_ngbiter over the piece lists + density_postprocess + density_check_neighbours for the
+// targets of this pass.  State (Hsml, Left, Right, niter) is indexed by particle index.
+__global__ void __launch_bounds__(128, 4)
+k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restrict__ sidx,
+                    const double4 *__restrict__ spart, const double4 *__restrict__ svel, SphDev S, int update_hsml, int DoEgy,
+                    const unsigned *__restrict__ pool, const int *__restrict__ chunk_tab, int maxch, const int *__restrict__ piece_cnt, int sentinel,
+                    double *__restrict__ hsml, double *__restrict__ left, double *__restrict__ right,
+                    double *__restrict__ density, double *__restrict__ egy, double *__restrict__ dhsmlfac,
+                    double *__restrict__ divvel, double *__restrict__ curlvel, double *__restrict__ dthsml, double *__restrict__ numngb,
+                    double *__restrict__ gradrho, int *__restrict__ ninteract, int *__restrict__ niter,
+                    uint8_t *__restrict__ notdone, int *__restrict__ err)
+{
+    extern __shared__ int s_ctab_dyn[];                 // [WALK_WARPS][maxch]
+    int *s_ctab = s_ctab_dyn + (threadIdx.x >> 5) * maxch;
+    const int lane = threadIdx.x & 31;
+    const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tslot = group * 32 + lane;
+    const bool valid = tslot < nt;
+    if(group * 32 >= nt) return;            // warp-uniform
+    int me = -1, mycnt = 0;
+    double4 pm = make_double4(0, 0, 0, 0), vm = pm;
+    double h = 1;
+    if(valid) {
+        const int j = targets ? targets[tslot] : tslot;
+        me = sidx[j];
+        pm = spart[j]; vm = svel[j];
+        h = hsml[me];
+        mycnt = piece_cnt[tslot];
+    }
+    piece_load_ctab(s_ctab, chunk_tab, maxch, group, mycnt, lane);
+    PieceList L;
+    L.pool = pool; L.ctab = s_ctab; L.empty = PIECE(sentinel, 0);
+    const int g = lane >> 3, slot = lane & 7;
+    double acc[NSUM_DENS];
+#pragma unroll
+    for(int q = 0; q < NSUM_DENS; q++) acc[q] = 0;
+    int nint = 0;
+    for(int t = 0; t < 32; t++) {
+        const int ntp = __shfl_sync(0xffffffffu, mycnt, t);
+        if(ntp == 0) continue;                          // warp-uniform
+        const double tx = __shfl_sync(0xffffffffu, pm.x, t), ty = __shfl_sync(0xffffffffu, pm.y, t), tz = __shfl_sync(0xffffffffu, pm.z, t);
+        const double tvx = __shfl_sync(0xffffffffu, vm.x, t), tvy = __shfl_sync(0xffffffffu, vm.y, t), tvz = __shfl_sync(0xffffffffu, vm.z, t);
+        const double th = __shfl_sync(0xffffffffu, h, t);
+        Kern k; kern_init(k, th, S);
         const double vol = NORM_COEFF * pw3(k.H);
-        const double h2 = h * h;
-        Ngb = Rho = Dh = EgyRho = DhEgy = Div = R0 = R1 = R2 = G0 = G1 = G2 = 0; nint = 0;
-        int no = 0;
-        while(no >= 0) {
-            const double4 B = nodeB[no];
-            const int4 C = nodeC[no];
-            if(!cull_keep(B, 0.0, pm.x, pm.y, pm.z, h, false, S)) { no = C.x; continue; }
-            if(!C.w) { no = no + 1; continue; }
-            for(int c = 0; c < C.z; c++) {
-                const double4 q = spart[C.y + c];
+        const double h2 = th * th;
+        L.t = t; L.nt = ntp;
+        double s[NSUM_DENS];
+#pragma unroll
+        for(int q = 0; q < NSUM_DENS; q++) s[q] = 0;
+        int ni = 0;
+        Ent4 eN = fetch_ent(L, 0, g);
+        for(int base = 0; base < ntp; base += 16) {
+            const Ent4 eC = eN;
+            eN = fetch_ent(L, base + 16, g);
+#pragma unroll
+            for(int kk = 0; kk < 4; kk++) {
+                const unsigned e = eC.e[kk];
+                if(slot >= (int) (e & 15u)) continue;
+                const int o = (int) (e >> 4) + slot;
+                const double4 q = spart[o];
                 // treewalk.c:1223-1233
-                const double d0 = nearest_s(pm.x - q.x, S.box, S.halfbox);
-                double r2 = d0 * d0;
+                const double d0 = nearest_s(tx - q.x, S.box, S.halfbox);
+                const double d1 = nearest_s(ty - q.y, S.box, S.halfbox);
+                const double d2 = nearest_s(tz - q.z, S.box, S.halfbox);
+                double r2 = d0 * d0; r2 += d1 * d1; r2 += d2 * d2;
                 if(r2 > h2) continue;
-                const double d1 = nearest_s(pm.y - q.y, S.box, S.halfbox);
-                r2 += d1 * d1;
-                if(r2 > h2) continue;
-                const double d2 = nearest_s(pm.z - q.z, S.box, S.halfbox);
-                r2 += d2 * d2;
-                if(r2 > h2) continue;
-                nint++;
+                ni++;
                 if(r2 < k.HH) {                       // density_ngbiter density.c:451-518
                     const double r = sqrt(r2);
                     const double u = r * k.Hinv;
                     const double wk = kern_w(k, u, S);
-                    Ngb += wk * vol;
+                    s[0] += wk * vol;
                     const double dwk = kern_dw(k, u, S);
                     const double mj = q.w;
-                    Rho += mj * wk;
+                    s[1] += mj * wk;
                     const double dW = -(3 * k.Hinv * wk + u * dwk);
-                    Dh += mj * dW;
-                    const double4 vo = svel[C.y + c];
-                    if(DoEgy) { EgyRho += mj * vo.w * wk; DhEgy += mj * vo.w * dW; }
+                    s[2] += mj * dW;
+                    const double4 vo = svel[o];
+                    if(DoEgy) { s[3] += mj * vo.w * wk; s[4] += mj * vo.w * dW; }
                     if(r > 0) {
                         const double fac = mj * dwk / r;
-                        const double v0 = vm.x - vo.x, v1 = vm.y - vo.y, v2 = vm.z - vo.z;
-                        Div += -fac * (d0 * v0 + d1 * v1 + d2 * v2);
-                        R0 += fac * (v1 * d2 - d1 * v2);
-                        R1 += fac * (v2 * d0 - d2 * v0);
-                        R2 += fac * (v0 * d1 - d0 * v1);
-                        G0 += fac * d0; G1 += fac * d1; G2 += fac * d2;         // density.c:512-515
+                        const double v0 = tvx - vo.x, v1 = tvy - vo.y, v2 = tvz - vo.z;
+                        s[5] += -fac * (d0 * v0 + d1 * v1 + d2 * v2);
+                        s[6] += fac * (v1 * d2 - d1 * v2);
+                        s[7] += fac * (v2 * d0 - d2 * v0);
+                        s[8] += fac * (v0 * d1 - d0 * v1);
+                        s[9] += fac * d0; s[10] += fac * d1; s[11] += fac * d2;         // density.c:512-515
                     }
                 }
             }
-            no = C.x;
         }
-        // density_postprocess density.c:532-586
-        if(Rho <= 0 && Ngb > 0) atomicAdd(err, 1);
-        DhsmlDens = Dh * h / (3 * Rho);
-        DhsmlDens = 1 / (1 + DhsmlDens);
-        if(!update_hsml) break;
+#pragma unroll
+        for(int q = 0; q < NSUM_DENS; q++) s[q] = warp_sum(s[q]);
+        ni = (int) __reduce_add_sync(0xffffffffu, (unsigned) ni);
+        if(lane == t) {
+#pragma unroll
+            for(int q = 0; q < NSUM_DENS; q++) acc[q] = s[q];
+            nint = ni;
+        }
+    }
+    if(!valid) return;
+    const double Ngb = acc[0], Rho = acc[1], Dh = acc[2], EgyRho = acc[3], DhEgy = acc[4], Div = acc[5];
+    // density_postprocess density.c:532-586
+    if(Rho <= 0 && Ngb > 0) atomicAdd(err, 1);
+    double DhsmlDens = Dh * h / (3 * Rho);
+    DhsmlDens = 1 / (1 + DhsmlDens);
+    bool done = true;
+    if(update_hsml) {
         // density_check_neighbours density.c:589-689
+        double Left = left[me], Right = right[me];
         const double des = S.desnumngb, maxdev = S.p.MaxNumNgbDeviation;
-        bool done;
         if(Ngb < (des - maxdev) || Ngb > (des + maxdev)) {
             if((Right - Left) < 1.0e-5 * Left) { h = Right; done = true; }
             else {
@@ -235,10 +402,14 @@ k_sph_density(int np, const int *__restrict__ sidx, const double4 *__restrict__ 
             if(h < S.p.MinGasHsml) h = S.p.MinGasHsml;
             done = true;
         }
-        if(done) break;
-        if(it > SPH_MAXITER) { atomicAdd(err, 1); break; }
-    }
-    hsml[me] = h;
+        left[me] = Left; right[me] = Right;
+        hsml[me] = h;
+        const int it = niter[me] + 1;
+        niter[me] = it;
+        if(!done && it > SPH_MAXITER + 1) { atomicAdd(err, 1); done = true; }
+    } else niter[me] = 1;
+    notdone[tslot] = done ? 0 : 1;
+    if(!done) return;
     density[me] = Rho;
     if(DoEgy) {
         double f = DhEgy * h / (3 * EgyRho);
@@ -249,14 +420,26 @@ k_sph_density(int np, const int *__restrict__ sidx, const double4 *__restrict__ 
         dhsmlfac[me] = DhsmlDens;
         egy[me] = 0;
     }
-    curlvel[me] = sqrt(R0 * R0 + R1 * R1 + R2 * R2) / Rho;
+    curlvel[me] = sqrt(acc[6] * acc[6] + acc[7] * acc[7] + acc[8] * acc[8]) / Rho;
     const double dv = Div / Rho;
     divvel[me] = dv;
     dthsml[me] = (1.0 / 3) * dv * h;
-    if(numngb) numngb[me] = Ngb;
-    gradrho[3 * (int64_t) me] = G0; gradrho[3 * (int64_t) me + 1] = G1; gradrho[3 * (int64_t) me + 2] = G2;
-    if(ninteract) ninteract[me] = nint;
-    if(niter) niter[me] = it + 1;
+    numngb[me] = Ngb;
+    gradrho[3 * (int64_t) me] = acc[9]; gradrho[3 * (int64_t) me + 1] = acc[10]; gradrho[3 * (int64_t) me + 2] = acc[11];
+    ninteract[me] = nint;
+}
+
+__global__ void k_sph_iota(int *p, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) p[i] = i;
+}
+
+__global__ void k_sph_init_state(int64_t n, double box, double *__restrict__ left, double *__restrict__ right, int *__restrict__ niter,
+                                 int *__restrict__ nint)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) { left[i] = 0; right[i] = box; niter[i] = 0; nint[i] = 0; }
 }
 
 // update_tree_hmax_father forcetree.c:1287-1315 for every leaf, then bottom-up max (forcetree.c:1090-1091)
@@ -320,105 +503,130 @@ k_sph_gather_hydro(int np, const int *__restrict__ sidx, SphDev S, const double 
     hB[j] = make_double4(dvv, curlvel[i], dhsmlfac[i], eom0);
 }
 
-__global__ void __launch_bounds__(128)
-k_sph_hydro(int np, const int *__restrict__ sidx, const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC,
-            const double *__restrict__ nodeH, const double4 *__restrict__ spart, const double4 *__restrict__ svel,
-            const double4 *__restrict__ hA, const double4 *__restrict__ hB, const double *__restrict__ density,
-            const uint8_t *__restrict__ type, SphDev S,
-            double *__restrict__ acc_out, double *__restrict__ dte_out, double *__restrict__ maxsig_out, int *__restrict__ ninteract)
+// hydro_ngbiter (hydra.c:318-506) over the piece lists of the symmetric search, then
+// hydro_postprocess (hydra.c:514-528).  Candidates = particles of the kept leaves
+// (treewalk.c:962-999 filters them by r^2 <= max(h_i, h_j)^2).
+__global__ void __launch_bounds__(128, 3)
+k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict__ sidx,
+                  const double4 *__restrict__ spart, const double4 *__restrict__ svel,
+                  const double4 *__restrict__ hA, const double4 *__restrict__ hB, const double *__restrict__ density, SphDev S,
+                  const unsigned *__restrict__ pool, const int *__restrict__ chunk_tab, int maxch, const int *__restrict__ piece_cnt,
+                  double *__restrict__ acc_out, double *__restrict__ dte_out, double *__restrict__ maxsig_out, int *__restrict__ ninteract)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if(j >= np) return;
-    const int me = sidx[j];
-    if(type[me] != 0) return;                      // hydro_haswork hydra.c:508-512
-    const int DI = S.p.DensityIndependentSphOn;
-    const double4 pm = spart[j], vm = svel[j], a_i = hA[j], b_i = hB[j];
-    const double h_i = a_i.x, P_i = a_i.w, eom_i = b_i.w, dens_i = density[me];
-    // hydro_copy hydra.c:247-277
-    const double cs_i = sqrt(GAMMA * P_i / eom_i);
-    const double F1 = fabs(b_i.x) / (fabs(b_i.x) + b_i.y + 0.0001 * cs_i / h_i / S.fac_mu);
-    const double p_over_rho2_i = P_i / (eom_i * eom_i);
-    Kern ki; kern_init(ki, h_i, S);
-    double A0 = 0, A1 = 0, A2 = 0, DtE = 0, MaxSig = cs_i;
-    int ncand = 0;
-    int no = 0;
-    while(no >= 0) {                                // ngb_treefind_threads treewalk.c:1056-1143 (symmetric)
-        const double4 B = nodeB[no];
-        const int4 C = nodeC[no];
-        if(!cull_keep(B, nodeH[no], pm.x, pm.y, pm.z, h_i, true, S)) { no = C.x; continue; }
-        if(!C.w) { no = no + 1; continue; }
-        ncand += C.z;
-        for(int c = 0; c < C.z; c++) {              // treewalk.c:962-999, hydro_ngbiter hydra.c:350-505
-            const int o = C.y + c;
-            const double4 q = spart[o], a_j = hA[o];
-            const double hm = a_j.x > h_i ? a_j.x : h_i, h2 = hm * hm;
-            const double d0 = nearest_s(pm.x - q.x, S.box, S.halfbox);
-            double rsq = d0 * d0;
-            if(rsq > h2) continue;
-            const double d1 = nearest_s(pm.y - q.y, S.box, S.halfbox);
-            rsq += d1 * d1;
-            if(rsq > h2) continue;
-            const double d2 = nearest_s(pm.z - q.z, S.box, S.halfbox);
-            rsq += d2 * d2;
-            if(rsq > h2) continue;
-            Kern kj; kern_init(kj, a_j.x, S);
-            if(rsq <= 0 || !(rsq < ki.HH || rsq < kj.HH)) continue;
-            const double r = sqrt(rsq);
-            const double4 vo = svel[o], b_j = hB[o];
-            const double density_j = a_j.y, eom_j = a_j.z, P_j = a_j.w;
-            const double p_over_rho2_j = P_j / (eom_j * eom_j);
-            const double cs_j = sqrt(GAMMA * P_j / eom_j);
-            double vsig = cs_i + cs_j;
-            if(vsig > MaxSig) MaxSig = vsig;
-            const double v0 = vm.x - vo.x, v1 = vm.y - vo.y, v2 = vm.z - vo.z;
-            const double vdotr = d0 * v0 + d1 * v1 + d2 * v2;
-            const double vdotr2 = vdotr + S.hubble_a2 * rsq;
-            const double dwk_i = kern_dw(ki, r * ki.Hinv, S);
-            const double dwk_j = kern_dw(kj, r * kj.Hinv, S);
-            double visc = 0;
-            if(vdotr2 < 0) {
-                const double mu_ij = S.fac_mu * vdotr2 / r;
-                const double rho_ij = 0.5 * (dens_i + density_j);
-                double vs = cs_i + cs_j;
-                vs -= 3 * mu_ij;
-                if(vs > MaxSig) MaxSig = vs;
-                const double f2 = fabs(b_j.x) / (fabs(b_j.x) + b_j.y + 0.0001 * cs_j / S.fac_mu / a_j.x);
-                visc = 0.25 * S.p.ArtBulkViscConst * vs * (-mu_ij) / rho_ij * (F1 + f2);
-                const double dloga = 2 * S.p.dloga_bin;
-                if(dloga > 0 && (dwk_i + dwk_j) < 0) {
-                    const double msum = pm.w + q.w;
-                    if(msum > 0) {
-                        const double lim = 0.5 * S.fac_vsic_fix * vdotr2 / (0.5 * msum * (dwk_i + dwk_j) * r * dloga);
-                        if(lim < visc) visc = lim;
-                    }
-                }
-            }
-            const double hfc_visc = 0.5 * q.w * visc * (dwk_i + dwk_j) / r;
-            double hfc = hfc_visc, rr1 = 1, rr2 = 1;
-            if(DI) {
-                rr1 = 0; rr2 = 0;
-                hfc += q.w * (dwk_i * p_over_rho2_i * vo.w / vm.w + dwk_j * p_over_rho2_j * vm.w / vo.w) / r;
-                if(S.p.DensityContrastLimit >= 0) {
-                    rr1 = eom_i / dens_i;
-                    rr2 = eom_j / density_j;
-                    if(S.p.DensityContrastLimit > 0) {
-                        if(S.p.DensityContrastLimit < rr1) rr1 = S.p.DensityContrastLimit;
-                        if(S.p.DensityContrastLimit < rr2) rr2 = S.p.DensityContrastLimit;
-                    }
-                }
-            }
-            hfc += q.w * (p_over_rho2_i * b_i.z * dwk_i * rr1 + p_over_rho2_j * b_j.z * dwk_j * rr2) / r;
-            A0 += (-hfc * d0); A1 += (-hfc * d1); A2 += (-hfc * d2);
-            DtE += (0.5 * hfc_visc * vdotr2);
-        }
-        no = C.x;
+    extern __shared__ int s_ctab_dyn[];                 // [WALK_WARPS][maxch]
+    int *s_ctab = s_ctab_dyn + (threadIdx.x >> 5) * maxch;
+    const int lane = threadIdx.x & 31;
+    const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tslot = group * 32 + lane;
+    const bool valid = tslot < nt;
+    if(group * 32 >= nt) return;            // warp-uniform
+    int me = -1, mycnt = 0, myj = 0;
+    if(valid) {
+        myj = targets ? targets[tslot] : tslot;
+        me = sidx[myj];
+        mycnt = piece_cnt[tslot];
     }
+    piece_load_ctab(s_ctab, chunk_tab, maxch, group, mycnt, lane);
+    PieceList L;
+    L.pool = pool; L.ctab = s_ctab; L.empty = PIECE(0, 0);
+    const int g = lane >> 3, slot = lane & 7;
+    const int DI = S.p.DensityIndependentSphOn;
+    double rA0 = 0, rA1 = 0, rA2 = 0, rDtE = 0, rMaxSig = 0, rdens = 1;
+    int rncand = 0;
+    for(int t = 0; t < 32; t++) {
+        const int ntp = __shfl_sync(0xffffffffu, mycnt, t);
+        if(ntp == 0) continue;                          // warp-uniform
+        // the target's rows: one broadcast load each
+        const int jt = __shfl_sync(0xffffffffu, myj, t), met = __shfl_sync(0xffffffffu, me, t);
+        const double4 pm = spart[jt], vm = svel[jt], a_i = hA[jt], b_i = hB[jt];
+        const double h_i = a_i.x, P_i = a_i.w, eom_i = b_i.w, dens_i = density[met];
+        // hydro_copy hydra.c:247-277
+        const double cs_i = sqrt(GAMMA * P_i / eom_i);
+        const double F1 = fabs(b_i.x) / (fabs(b_i.x) + b_i.y + 0.0001 * cs_i / h_i / S.fac_mu);
+        const double p_over_rho2_i = P_i / (eom_i * eom_i);
+        Kern ki; kern_init(ki, h_i, S);
+        double A0 = 0, A1 = 0, A2 = 0, DtE = 0, MaxSig = cs_i;
+        int ncand = 0;
+        L.t = t; L.nt = ntp;
+        Ent4 eN = fetch_ent(L, 0, g);
+        for(int base = 0; base < ntp; base += 16) {
+            const Ent4 eC = eN;
+            eN = fetch_ent(L, base + 16, g);
+#pragma unroll
+            for(int kk = 0; kk < 4; kk++) {
+                const unsigned e = eC.e[kk];
+                if(slot == 0) ncand += (int) (e & 15u);
+                if(slot >= (int) (e & 15u)) continue;
+                const int o = (int) (e >> 4) + slot;
+                const double4 q = spart[o], a_j = hA[o];
+                const double hm = a_j.x > h_i ? a_j.x : h_i, h2 = hm * hm;
+                const double d0 = nearest_s(pm.x - q.x, S.box, S.halfbox);
+                const double d1 = nearest_s(pm.y - q.y, S.box, S.halfbox);
+                const double d2 = nearest_s(pm.z - q.z, S.box, S.halfbox);
+                double rsq = d0 * d0; rsq += d1 * d1; rsq += d2 * d2;
+                if(rsq > h2) continue;
+                Kern kj; kern_init(kj, a_j.x, S);
+                if(rsq <= 0 || !(rsq < ki.HH || rsq < kj.HH)) continue;
+                const double r = sqrt(rsq);
+                const double4 vo = svel[o], b_j = hB[o];
+                const double density_j = a_j.y, eom_j = a_j.z, P_j = a_j.w;
+                const double p_over_rho2_j = P_j / (eom_j * eom_j);
+                const double cs_j = sqrt(GAMMA * P_j / eom_j);
+                double vsig = cs_i + cs_j;
+                if(vsig > MaxSig) MaxSig = vsig;
+                const double v0 = vm.x - vo.x, v1 = vm.y - vo.y, v2 = vm.z - vo.z;
+                const double vdotr = d0 * v0 + d1 * v1 + d2 * v2;
+                const double vdotr2 = vdotr + S.hubble_a2 * rsq;
+                const double dwk_i = kern_dw(ki, r * ki.Hinv, S);
+                const double dwk_j = kern_dw(kj, r * kj.Hinv, S);
+                double visc = 0;
+                if(vdotr2 < 0) {
+                    const double mu_ij = S.fac_mu * vdotr2 / r;
+                    const double rho_ij = 0.5 * (dens_i + density_j);
+                    double vs = cs_i + cs_j;
+                    vs -= 3 * mu_ij;
+                    if(vs > MaxSig) MaxSig = vs;
+                    const double f2 = fabs(b_j.x) / (fabs(b_j.x) + b_j.y + 0.0001 * cs_j / S.fac_mu / a_j.x);
+                    visc = 0.25 * S.p.ArtBulkViscConst * vs * (-mu_ij) / rho_ij * (F1 + f2);
+                    const double dloga = 2 * S.p.dloga_bin;
+                    if(dloga > 0 && (dwk_i + dwk_j) < 0) {
+                        const double msum = pm.w + q.w;
+                        if(msum > 0) {
+                            const double lim = 0.5 * S.fac_vsic_fix * vdotr2 / (0.5 * msum * (dwk_i + dwk_j) * r * dloga);
+                            if(lim < visc) visc = lim;
+                        }
+                    }
+                }
+                const double hfc_visc = 0.5 * q.w * visc * (dwk_i + dwk_j) / r;
+                double hfc = hfc_visc, rr1 = 1, rr2 = 1;
+                if(DI) {
+                    rr1 = 0; rr2 = 0;
+                    hfc += q.w * (dwk_i * p_over_rho2_i * vo.w / vm.w + dwk_j * p_over_rho2_j * vm.w / vo.w) / r;
+                    if(S.p.DensityContrastLimit >= 0) {
+                        rr1 = eom_i / dens_i;
+                        rr2 = eom_j / density_j;
+                        if(S.p.DensityContrastLimit > 0) {
+                            if(S.p.DensityContrastLimit < rr1) rr1 = S.p.DensityContrastLimit;
+                            if(S.p.DensityContrastLimit < rr2) rr2 = S.p.DensityContrastLimit;
+                        }
+                    }
+                }
+                hfc += q.w * (p_over_rho2_i * b_i.z * dwk_i * rr1 + p_over_rho2_j * b_j.z * dwk_j * rr2) / r;
+                A0 += (-hfc * d0); A1 += (-hfc * d1); A2 += (-hfc * d2);
+                DtE += (0.5 * hfc_visc * vdotr2);
+            }
+        }
+        A0 = warp_sum(A0); A1 = warp_sum(A1); A2 = warp_sum(A2); DtE = warp_sum(DtE); MaxSig = warp_max(MaxSig);
+        ncand = (int) __reduce_add_sync(0xffffffffu, (unsigned) ncand);
+        if(lane == t) { rA0 = A0; rA1 = A1; rA2 = A2; rDtE = DtE; rMaxSig = MaxSig; rncand = ncand; rdens = dens_i; }
+    }
+    if(!valid) return;
     // hydro_postprocess hydra.c:514-528
-    DtE *= GAMMA_MINUS1 / (S.hubble_a2 * pow(dens_i, GAMMA_MINUS1));
-    acc_out[3 * (int64_t) me] = A0; acc_out[3 * (int64_t) me + 1] = A1; acc_out[3 * (int64_t) me + 2] = A2;
-    dte_out[me] = DtE;
-    maxsig_out[me] = MaxSig;
-    if(ninteract) ninteract[me] = ncand;
+    rDtE *= GAMMA_MINUS1 / (S.hubble_a2 * pow(rdens, GAMMA_MINUS1));
+    acc_out[3 * (int64_t) me] = rA0; acc_out[3 * (int64_t) me + 1] = rA1; acc_out[3 * (int64_t) me + 2] = rA2;
+    dte_out[me] = rDtE;
+    maxsig_out[me] = rMaxSig;
+    if(ninteract) ninteract[me] = rncand;
 }
 
 static int make_dev(Engine *E, const b200_sph_params *p, SphDev &S)
@@ -473,21 +681,72 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
     CK(E->s_svel.ensure(4 * (size_t) (np > 0 ? np : 1)));
     CK(E->scratch_i.ensure(16));
     CK(cudaMemsetAsync(E->scratch_i.p + 12, 0, sizeof(int), E->stream));
+    CK(E->s_left.ensure(n)); CK(E->s_right.ensure(n)); CK(E->s_niter.ensure(n)); CK(E->s_nint.ensure(n));
+    CK(E->targets.ensure((size_t) np + 1)); CK(E->targets_sorted.ensure((size_t) np + 1));
+    CK(E->walk_flags.ensure((size_t) np + 64));
     timer_start(E, T_SPH_DENSITY);
     if(E->n > 0) {
         k_sph_predict<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->n, E->s_have[0] ? E->s_vel.p : nullptr,
             E->s_have[4] ? E->s_fullacc.p : nullptr, E->s_have[5] ? E->s_gravpm.p : nullptr, E->s_have[6] ? E->s_hydroacc.p : nullptr,
             E->s_have[2] ? E->s_entropy.p : nullptr, E->s_have[3] ? E->s_dtentropy.p : nullptr, S, E->s_velpred.p, E->s_evp.p);
         CKL(E);
+        k_sph_init_state<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->n, S.box, E->s_left.p, E->s_right.p, E->s_niter.p, E->s_nint.p);
+        CKL(E);
     }
     if(np > 0) {
         k_sph_gather_vel<<<(np + 255) / 256, 256, 0, E->stream>>>(np, E->sidx.p, E->s_velpred.p, E->s_evp.p, (double4 *) E->s_svel.p);
         CKL(E);
-        k_sph_density<<<(np + 127) / 128, 128, 0, E->stream>>>(np, E->sidx.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p,
-            (const double4 *) E->spart.p, (const double4 *) E->s_svel.p, E->type.p, S, update_hsml, DoEgy,
-            E->s_hsml.p, E->s_density.p, E->s_egy.p, E->s_dhsmlfac.p, E->s_divvel.p, E->s_curlvel.p, E->s_dthsml.p, E->s_numngb.p,
-            E->s_gradrho.p, d_ninteract, d_niter, E->scratch_i.p + 12);
-        CKL(E);
+        // treewalk_do_hsml_loop (treewalk.c:1269-1367): walk, evaluate, re-queue the unconverged
+        const double keep_estimate = E->walk_chunks_per_warp;
+        E->walk_chunks_per_warp = E->sph_chunks_per_warp;
+        const int *tg = nullptr;            // pass 0: every tree particle, in curve order
+        int *tg_next = E->targets.p, *tg_other = E->targets_sorted.p;
+        int nt = np;
+        for(int pass = 0; nt > 0; pass++) {
+            const int64_t nwarps = (nt + 31) / 32;
+            const unsigned nb = (unsigned) ((nwarps * 32 + 127) / 128);
+            piece_pool_reset(E);
+            for(int attempt = 0;; attempt++) {
+                PiecePool Q;
+                if(int rc = piece_pool_begin(E, nwarps, &Q)) return rc;
+                CK(piece_set_smem(k_sph_walk<false>, piece_ctab_bytes(E, WALK_WARPS)));
+                k_sph_walk<false><<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>((const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, (const int4 *) E->nodeK.p,
+                    E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, tg, nt, E->s_hsml.p, S, Q);
+                CKL(E);
+                bool retry = false;
+                if(int rc = piece_pool_check(E, nwarps, &retry, attempt)) return rc;
+                if(!retry) break;
+            }
+            CK(piece_set_smem(k_sph_density_pairs, piece_ctab_bytes(E, WALK_WARPS)));
+            k_sph_density_pairs<<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>(tg, nt, E->sidx.p, (const double4 *) E->spart.p, (const double4 *) E->s_svel.p,
+                S, update_hsml, DoEgy, E->walk_pool.p, E->walk_chunktab.p, E->walk_maxch, E->walk_cnt.p, 0,
+                E->s_hsml.p, E->s_left.p, E->s_right.p, E->s_density.p, E->s_egy.p, E->s_dhsmlfac.p, E->s_divvel.p, E->s_curlvel.p,
+                E->s_dthsml.p, E->s_numngb.p, E->s_gradrho.p, E->s_nint.p, E->s_niter.p, E->walk_flags.p, E->scratch_i.p + 12);
+            CKL(E);
+            if(!update_hsml) break;
+            // the unconverged targets of this pass, still in curve order
+            size_t tb = 0;
+            int *d_num = E->scratch_i.p + 13;
+            if(!tg) {       // pass 0 walked the identity list
+                k_sph_iota<<<(nt + 255) / 256, 256, 0, E->stream>>>(tg_other, nt); CKL(E);
+                tg = tg_other;
+            }
+            cub::DeviceSelect::Flagged(nullptr, tb, tg, E->walk_flags.p, tg_next, d_num, nt, E->stream);
+            CK(E->cubtemp.ensure(tb + 16));
+            CK(cub::DeviceSelect::Flagged(E->cubtemp.p, tb, tg, E->walk_flags.p, tg_next, d_num, nt, E->stream));
+            E->launches += 1;
+            int left_over = 0;
+            CK(cudaMemcpyAsync(&left_over, d_num, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+            CK(cudaStreamSynchronize(E->stream));
+            E->sph_passes = pass + 1;
+            nt = left_over;
+            { int *sw = tg_next; tg_next = tg_other; tg_other = sw; }      // tg_other now holds the new list
+            tg = tg_other;
+        }
+        E->sph_chunks_per_warp = E->walk_chunks_per_warp;
+        E->walk_chunks_per_warp = keep_estimate;
+        if(d_ninteract) CK(cudaMemcpyAsync(d_ninteract, E->s_nint.p, (size_t) E->n * sizeof(int), cudaMemcpyDeviceToDevice, E->stream));
+        if(d_niter) CK(cudaMemcpyAsync(d_niter, E->s_niter.p, (size_t) E->n * sizeof(int), cudaMemcpyDeviceToDevice, E->stream));
         // hmax of the tree from the converged smoothing lengths (run.c:477 force_tree_calc_moments)
         k_sph_hmax_leaf<<<(nn + 255) / 256, 256, 0, E->stream>>>(nn, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p,
             (const double4 *) E->spart.p, E->sidx.p, E->s_hsml.p, E->type.p, E->nodeH.p);
@@ -521,9 +780,28 @@ int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte,
         k_sph_gather_hydro<<<(np + 255) / 256, 256, 0, E->stream>>>(np, E->sidx.p, S, E->s_hsml.p, E->s_density.p, E->s_egy.p, E->s_dhsmlfac.p,
             E->s_divvel.p, E->s_curlvel.p, (const double4 *) E->s_svel.p, (double4 *) E->s_hA.p, (double4 *) E->s_hB.p);
         CKL(E);
-        k_sph_hydro<<<(np + 127) / 128, 128, 0, E->stream>>>(np, E->sidx.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, E->nodeH.p,
-            (const double4 *) E->spart.p, (const double4 *) E->s_svel.p, (const double4 *) E->s_hA.p, (const double4 *) E->s_hB.p,
-            E->s_density.p, E->type.p, S, d_acc, d_dte, d_maxsig, d_ninteract);
+        const double keep_estimate = E->walk_chunks_per_warp;
+        E->walk_chunks_per_warp = E->sph_chunks_per_warp;
+        const int64_t nwarps = (np + 31) / 32;
+        const unsigned nb = (unsigned) ((nwarps * 32 + 127) / 128);
+        piece_pool_reset(E);
+        for(int attempt = 0;; attempt++) {
+            PiecePool Q;
+            if(int rc = piece_pool_begin(E, nwarps, &Q)) return rc;
+            CK(piece_set_smem(k_sph_walk<true>, piece_ctab_bytes(E, WALK_WARPS)));
+            k_sph_walk<true><<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>((const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, (const int4 *) E->nodeK.p,
+                E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, nullptr, np, E->s_hsml.p, S, Q);
+            CKL(E);
+            bool retry = false;
+            if(int rc = piece_pool_check(E, nwarps, &retry, attempt)) return rc;
+            if(!retry) break;
+        }
+        E->sph_chunks_per_warp = E->walk_chunks_per_warp;
+        E->walk_chunks_per_warp = keep_estimate;
+        CK(piece_set_smem(k_sph_hydro_pairs, piece_ctab_bytes(E, WALK_WARPS)));
+        k_sph_hydro_pairs<<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>(nullptr, np, E->sidx.p, (const double4 *) E->spart.p, (const double4 *) E->s_svel.p,
+            (const double4 *) E->s_hA.p, (const double4 *) E->s_hB.p, E->s_density.p, S,
+            E->walk_pool.p, E->walk_chunktab.p, E->walk_maxch, E->walk_cnt.p, d_acc, d_dte, d_maxsig, d_ninteract);
         CKL(E);
     }
     timer_stop(E, T_SPH_HYDRO);

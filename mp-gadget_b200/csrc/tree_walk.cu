@@ -29,7 +29,7 @@
 // Decisions are evaluated with un-fused IEEE fp64 mul/add so that they agree
 // bit-for-bit with a CPU evaluation; only the accepted-force arithmetic uses
 // FMA / a fix-up-free rsqrt (accelerations are compared to 1e-6 relative, far above that).
-#include "engine.h"
+#include "piece_list.cuh"
 #include "../data/shortrange_table.h"
 #include <math.h>
 #include <stdlib.h>
@@ -121,15 +121,6 @@ __device__ __forceinline__ void monopole(double dx, double dy, double dz, double
     pot += facpot;
 }
 
-#define WALK_WARPS 4
-// Piece lists: chunk = CH_SLOTS list slots x 32 lanes x 4 bytes; a warp owns up to
-// WALK_MAXCH chunks (CH_SLOTS * WALK_MAXCH pieces = 8x that many pairs per target).
-#define CH_SHIFT 4
-#define CH_SLOTS (1 << CH_SHIFT)
-#define CH_WORDS (CH_SLOTS * 32)
-#define WALK_MAXCH 128
-// entry = first particle << 4 | count (0..8)
-#define PIECE(pstart, cnt) (((unsigned) (pstart) << 4) | (unsigned) (cnt))
 #ifndef WALK_MINB
 #define WALK_MINB 5
 #endif
@@ -137,25 +128,6 @@ __device__ __forceinline__ void monopole(double dx, double dy, double dz, double
 #define PAIR_MINB 2
 #endif
 #define PAIR_WARPS 8
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_min(double v)
-{
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v)
-{
-#pragma unroll
-    for(int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
 
 // Per-lane decision on one node: 0 discard, 1 accept, 2 open
 // (shall_we_discard_node / shall_we_open_node, gravshort-tree.c:198-241).
@@ -230,37 +202,14 @@ __device__ __forceinline__ void pair_fast(double dx, double dy, double dz, doubl
 // neutralised through the mass.
 struct SrcRow { double4 q; int cnt; };
 
-struct PieceList {
-    const unsigned *__restrict__ pool;     // chunk pool
-    const int *__restrict__ ctab;          // this warp's chunk ids (shared memory)
-    unsigned empty;                        // PIECE(sentinel, 0)
-    int t;                                 // column = lane of the target in its warp
-    int nt;                                // pieces in the list
-};
-
 // The source rows are read from two 16-byte streams {x, y} and {z, m}: the eight lanes of a
 // group then read 128 contiguous bytes per load (whole sectors) instead of half of 8 x 32.
 struct SrcArrays { const double2 *__restrict__ xy; const double2 *__restrict__ zm; };
 
-// The pair loop advances 16 pieces (= one chunk row block) per step: group g takes the
-// pieces base + g + {0, 4, 8, 12}, one particle per lane per piece.  Three stages are in
-// flight: the 4 entries of the next step, the 2 source rows of the next half step, and the
-// arithmetic of the current half step.
-struct Ent4 { unsigned e[4]; };
+// The pair loop advances 16 pieces (= one chunk row block) per step (piece_list.cuh).  Three
+// stages are in flight: the 4 entries of the next step, the 2 source rows of the next half
+// step, and the arithmetic of the current half step.
 struct Rows2 { SrcRow r[2]; };
-
-__device__ __forceinline__ Ent4 fetch_ent(const PieceList &L, int base, int g)
-{
-    Ent4 E;
-#pragma unroll
-    for(int k = 0; k < 4; k++) E.e[k] = L.empty;
-    if(base < L.nt) {                       // warp-uniform; base is a multiple of CH_SLOTS = 16
-        const unsigned *row = L.pool + (size_t) L.ctab[base >> CH_SHIFT] * CH_WORDS + g * 32 + L.t;
-#pragma unroll
-        for(int k = 0; k < 4; k++) if(base + g + 4 * k < L.nt) E.e[k] = row[k * 128];
-    }
-    return E;
-}
 
 __device__ __forceinline__ Rows2 fetch_rows(const Ent4 &E, int first, int slot, const SrcArrays &S)
 {
@@ -333,9 +282,6 @@ struct BatchEntry {
                       // flags (bit0: leaf, bit1: rejected for all lanes by the bounding-box test)
 };
 
-#define WALK_STACK 344        // (node, mask) entries per warp
-#define WALK_RESERVE 154      // head-room so that single pops (<= 7 net pushes each, depth <= 21+) never overflow
-
 template <bool COUNT>
 __global__ void __launch_bounds__(128, WALK_MINB)
 k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB,
@@ -344,15 +290,12 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             const double *__restrict__ pos, const float *__restrict__ mass,
             const double *__restrict__ oldacc, const float *__restrict__ gtab,
             WalkPar P,
-            unsigned *__restrict__ pool, int pool_cap,      // chunk pool of the piece lists, capacity in chunks
-            int *__restrict__ pool_ctl,                     // [0] next free chunk, [1] error bits, [2..3] pieces written (u64)
-            int *__restrict__ chunk_tab,                    // [warp][WALK_MAXCH] chunk ids
-            int *__restrict__ piece_cnt,                    // [target slot] pieces in the list
+            PiecePool Q,                                    // piece lists (piece_list.cuh)
             double4 *__restrict__ partial,                  // [target slot] sums over accepted nodes {ax, ay, az, pot}
             int4 *__restrict__ counts_out)
 {
     __shared__ double4 tab[B200_SR_NTAB];
-    __shared__ int s_ctab_all[WALK_WARPS][WALK_MAXCH];
+    extern __shared__ int s_ctab_dyn[];                 // [WALK_WARPS][Q.maxch]
     __shared__ int s_stk_node_all[WALK_WARPS][WALK_STACK];
     __shared__ unsigned s_stk_mask_all[WALK_WARPS][WALK_STACK];
     __shared__ BatchEntry s_ent_all[WALK_WARPS];
@@ -363,7 +306,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
     }
     __syncthreads();
     const int wib = threadIdx.x >> 5;
-    int *s_ctab = s_ctab_all[wib];
+    int *s_ctab = s_ctab_dyn + wib * Q.maxch;
     int *s_stk_node = s_stk_node_all[wib];
     unsigned *s_stk_mask = s_stk_mask_all[wib];
     BatchEntry &s_ent = s_ent_all[wib];
@@ -488,28 +431,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
                 if(COUNT && wantopen) n_part += M.y;
                 for(int o = 0; o < M.y; o += 8) {
                     const int c = M.y - o < 8 ? M.y - o : 8;
-                    const int needch = (int) __reduce_max_sync(0xffffffffu, wantopen ? (unsigned) (mycnt >> CH_SHIFT) : 0u);
-                    if(needch >= nch_alloc) {               // warp-uniform; once per CH_SLOTS pieces of the longest list
-                        if(needch >= WALK_MAXCH) { if(lane == 0) atomicOr(pool_ctl + 1, 2); }
-                        else {
-                            if(lane == 0)
-                                for(int ch = nch_alloc; ch <= needch; ch++) {
-                                    const int id = atomicAdd(pool_ctl, 1);
-                                    s_ctab[ch] = id;
-                                    chunk_tab[(size_t) group * WALK_MAXCH + ch] = id;
-                                }
-                            nch_alloc = needch + 1;
-                        }
-                        __syncwarp();
-                    }
-                    if(wantopen) {
-                        const int ch = mycnt >> CH_SHIFT;
-                        if(ch < nch_alloc) {
-                            const int id = s_ctab[ch];
-                            if(id < pool_cap) pool[(size_t) id * CH_WORDS + (mycnt & (CH_SLOTS - 1)) * 32 + lane] = PIECE(M.x + o, c);
-                        }
-                        mycnt++;
-                    }
+                    piece_push(wantopen, PIECE(M.x + o, c), mycnt, nch_alloc, s_ctab, Q, group, lane);
                 }
             } else {
                 if(COUNT && wantopen) n_open++;
@@ -537,13 +459,9 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
         __syncwarp();
     }
     // hand over to k_grav_pairs (target-slot order: coalesced)
-    {
-        const unsigned wsum = __reduce_add_sync(0xffffffffu, (unsigned) mycnt);
-        if(lane == 0) atomicAdd((unsigned long long *) (pool_ctl + 2), (unsigned long long) wsum);      // statistics
-    }
+    piece_finish(valid, tslot, mycnt, Q, lane);
     if(valid) {
         partial[tslot] = make_double4(ax, ay, az, pot);
-        piece_cnt[tslot] = mycnt;
         if(COUNT) counts_out[me] = make_int4(n_acc, n_open, n_disc, n_part);
     }
 }
@@ -554,11 +472,10 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32, PAIR_MINB)
 k_grav_pairs(const double2 *__restrict__ spart_xy, const double2 *__restrict__ spart_zm, const int *__restrict__ targets,
              const double *__restrict__ pos, const float *__restrict__ mass, const float *__restrict__ gtab,
              WalkPar P, int full_tree, double cbrtrho0,
-             const unsigned *__restrict__ pool, const int *__restrict__ chunk_tab, const int *__restrict__ piece_cnt,
+             const unsigned *__restrict__ pool, const int *__restrict__ chunk_tab, int maxch, const int *__restrict__ piece_cnt,
              const double4 *__restrict__ partial, double *__restrict__ acc_out, double *__restrict__ pot_out)
 {
-    extern __shared__ float4 s_tabx8[];                 // [B200_SR_NTAB][8], 64 KB
-    __shared__ int s_ctab_all[PAIR_WARPS][WALK_MAXCH];
+    extern __shared__ float4 s_tabx8[];                 // [B200_SR_NTAB][8] (64 KB), then int [PAIR_WARPS][maxch]
     for(int k = threadIdx.x; k < B200_SR_NTAB * 8; k += blockDim.x) {
         const int t = k >> 3, t1 = t + 1 < B200_SR_NTAB ? t + 1 : t;
         // row NTAB-1 all zero: pairs beyond the table (gravity.c:60-61) contribute nothing
@@ -566,7 +483,7 @@ k_grav_pairs(const double2 *__restrict__ spart_xy, const double2 *__restrict__ s
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    int *s_ctab = s_ctab_all[threadIdx.x >> 5];
+    int *s_ctab = (int *) (s_tabx8 + B200_SR_NTAB * 8) + (threadIdx.x >> 5) * maxch;
     const int lane = threadIdx.x & 31;
     const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int tslot = group * 32 + lane;
@@ -581,10 +498,7 @@ k_grav_pairs(const double2 *__restrict__ spart_xy, const double2 *__restrict__ s
         mycnt = piece_cnt[tslot];
         acc = partial[tslot];
     }
-    const int maxcnt = (int) __reduce_max_sync(0xffffffffu, (unsigned) mycnt);
-    const int nch = (maxcnt + CH_SLOTS - 1) >> CH_SHIFT;
-    for(int c = lane; c < nch; c += 32) s_ctab[c] = chunk_tab[(size_t) group * WALK_MAXCH + c];
-    __syncwarp();
+    piece_load_ctab(s_ctab, chunk_tab, maxch, group, mycnt, lane);
 
     PieceList L;
     L.pool = pool; L.ctab = s_ctab; L.empty = PIECE(P.sentinel, 0);
@@ -653,6 +567,54 @@ int walk_init_tables(Engine *E)
     for(int i = 0; i < B200_SR_NTAB; i++) { t[i] = b200_sr_force[i]; t[B200_SR_NTAB + i] = b200_sr_pot[i]; }
     CK(cudaMemcpyAsync(E->srtab.p, t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice, E->stream));
     CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
+// Piece-list storage.  The pool is sized from the last walk's use (first call: 6 chunks per
+// warp) and grown when a walk reports that it ran out; the walk is then repeated.
+void piece_pool_reset(Engine *E) { E->walk_maxch = WALK_MAXCH0; }
+
+int piece_pool_begin(Engine *E, int64_t nwarps, PiecePool *Q)
+{
+    CK(E->walk_chunktab.ensure((size_t) nwarps * E->walk_maxch));
+    Q->maxch = E->walk_maxch;
+    CK(E->walk_cnt.ensure((size_t) nwarps * 32));
+    CK(E->scratch_i.ensure(128));
+    if(E->walk_want == 0) E->walk_want = (size_t) (E->walk_chunks_per_warp * (double) nwarps) + 1024;
+    CK(E->walk_pool.ensure(E->walk_want * CH_WORDS));
+    E->walk_want = 0;
+    const size_t capz = E->walk_pool.cap / CH_WORDS;
+    Q->pool = E->walk_pool.p;
+    Q->cap = (int) (capz < (size_t) 0x7fffffff ? capz : (size_t) 0x7fffffff);
+    Q->ctl = E->scratch_i.p + 64;
+    Q->chunk_tab = E->walk_chunktab.p;
+    Q->piece_cnt = E->walk_cnt.p;
+    CK(cudaMemsetAsync(Q->ctl, 0, 4 * sizeof(int), E->stream));
+    return 0;
+}
+
+int piece_pool_check(Engine *E, int64_t nwarps, bool *retry, int attempt)
+{
+    int h[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(h, E->scratch_i.p + 64, 4 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    *retry = false;
+    if(h[1] & 2) {      // a list outgrew the warp's chunk table: repeat with a table 8x as long
+        if(E->walk_maxch >= WALK_MAXCH_LIMIT)
+            return failmsg(E, "tree walk: a particle opened more than " + std::to_string(CH_SLOTS * WALK_MAXCH_LIMIT) + " leaf pieces");
+        E->walk_maxch *= 8;
+        E->walk_want = E->walk_pool.cap / CH_WORDS;
+        *retry = true;
+        return 0;
+    }
+    unsigned long long pieces; memcpy(&pieces, h + 2, sizeof(pieces));
+    E->walk_pieces = (double) pieces; E->walk_chunks = h[0];
+    E->walk_chunks_per_warp = 1.15 * (double) h[0] / (double) (nwarps > 0 ? nwarps : 1) + 0.05;
+    const size_t capz = E->walk_pool.cap / CH_WORDS;
+    if((size_t) h[0] <= capz) return 0;
+    if(attempt >= 2) return failmsg(E, "tree walk: piece pool kept overflowing");
+    E->walk_want = (size_t) h[0] + (size_t) h[0] / 8 + 1024;
+    *retry = true;
     return 0;
 }
 
@@ -768,48 +730,32 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
     const int bs = 128;
     const int64_t nwarps = (nt + 31) / 32;
     const unsigned nb = (unsigned) ((nwarps * 32 + bs - 1) / bs);
-    // Piece-list storage.  The pool is sized from the last walk's use (first call: 3 chunks
-    // per warp) and grown when the walk reports that it ran out; the walk is then repeated.
-    CK(E->walk_chunktab.ensure((size_t) nwarps * WALK_MAXCH));
-    CK(E->walk_cnt.ensure((size_t) nwarps * 32));
     CK(E->walk_partial.ensure((size_t) nwarps * 32 * 4));
-    CK(E->scratch_i.ensure(128));
-    int *ctl = E->scratch_i.p + 64;
-    size_t want = (size_t) (E->walk_chunks_per_warp * (double) nwarps) + 1024;
     timer_start(E, T_WALK);
+    piece_pool_reset(E);
     for(int attempt = 0;; attempt++) {
-        CK(E->walk_pool.ensure(want * CH_WORDS));
-        const size_t capz = E->walk_pool.cap / CH_WORDS;
-        const int cap = (int) (capz < (size_t) 0x7fffffff ? capz : (size_t) 0x7fffffff);
-        CK(cudaMemsetAsync(ctl, 0, 4 * sizeof(int), E->stream));
+        PiecePool Q;
+        if(int rc = piece_pool_begin(E, nwarps, &Q)) return rc;
+        const size_t wsm = piece_ctab_bytes(E, WALK_WARPS);
+        CK(piece_set_smem(k_grav_walk<true>, wsm)); CK(piece_set_smem(k_grav_walk<false>, wsm));
 #define WALK_ARGS (const double4 *) E->nodeA.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, \
                   (const int4 *) E->nodeK.p, (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p, \
-                  P, E->walk_pool.p, cap, ctl, E->walk_chunktab.p, E->walk_cnt.p, (double4 *) E->walk_partial.p
-        if(d_counts) k_grav_walk<true><<<nb, bs, 0, E->stream>>>(WALK_ARGS, (int4 *) d_counts);
-        else k_grav_walk<false><<<nb, bs, 0, E->stream>>>(WALK_ARGS, nullptr);
+                  P, Q, (double4 *) E->walk_partial.p
+        if(d_counts) k_grav_walk<true><<<nb, bs, wsm, E->stream>>>(WALK_ARGS, (int4 *) d_counts);
+        else k_grav_walk<false><<<nb, bs, wsm, E->stream>>>(WALK_ARGS, nullptr);
 #undef WALK_ARGS
         CKL(E);
-        int h[4] = {0, 0, 0, 0};
-        CK(cudaMemcpyAsync(h, ctl, 4 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
-        CK(cudaStreamSynchronize(E->stream));
-        unsigned long long pieces; memcpy(&pieces, h + 2, sizeof(pieces));
-        E->walk_pieces = (double) pieces; E->walk_chunks = h[0];
-        if(h[1] & 2)
-            return failmsg(E, "b200_grav_short_tree: a particle opened more than " + std::to_string(CH_SLOTS * WALK_MAXCH) +
-                              " leaf pieces (raise WALK_MAXCH)");
-        E->walk_chunks_per_warp = 1.15 * (double) h[0] / (double) nwarps + 0.05;
-        if(h[0] <= cap) break;
-        if(attempt >= 2) return failmsg(E, "b200_grav_short_tree: piece pool kept overflowing");
-        want = (size_t) h[0] + (size_t) h[0] / 8 + 1024;
+        bool retry = false;
+        if(int rc = piece_pool_check(E, nwarps, &retry, attempt)) return rc;
+        if(!retry) break;
     }
     timer_stop(E, T_WALK);
     timer_start(E, T_WALK_POST);
-    const size_t pair_smem = (size_t) B200_SR_NTAB * 8 * sizeof(float4);
-    static bool pair_attr = false;
-    if(!pair_attr) { CK(cudaFuncSetAttribute(k_grav_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) pair_smem)); pair_attr = true; }
+    const size_t pair_smem = (size_t) B200_SR_NTAB * 8 * sizeof(float4) + piece_ctab_bytes(E, PAIR_WARPS);
+    CK(piece_set_smem(k_grav_pairs, pair_smem));
     const unsigned nbp = (unsigned) ((nwarps + PAIR_WARPS - 1) / PAIR_WARPS);
     k_grav_pairs<<<nbp, PAIR_WARPS * 32, pair_smem, E->stream>>>((const double2 *) E->spart_xy.p, (const double2 *) E->spart_zm.p, tg, E->pos.p, E->mass.p, E->srtab.p, P, E->tree_full ? 1 : 0, cbrtrho0,
-                                           E->walk_pool.p, E->walk_chunktab.p, E->walk_cnt.p, (const double4 *) E->walk_partial.p, d_acc, d_pot);
+                                           E->walk_pool.p, E->walk_chunktab.p, E->walk_maxch, E->walk_cnt.p, (const double4 *) E->walk_partial.p, d_acc, d_pot);
     CKL(E);
     timer_stop(E, T_WALK_POST);
     return 0;
