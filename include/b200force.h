@@ -101,6 +101,17 @@ int b200_pm_init(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double 
  * added to P[i].Potential) for every particle; either may be NULL. */
 int b200_pm_force(b200_ctx *ctx, double *gravpm_out, double *potential_out);
 int b200_pm_force_dev(b200_ctx *ctx, double *gravpm_out, double *potential_out);
+/* Matter power spectrum side effect of gravpm_force: potential_transfer calls
+ * powerspectrum_add_mode on every density mode before scaling it
+ * (gravpm.c:330-361,440).  b200_pm_set_power(ctx, 1) makes the next b200_pm_force
+ * accumulate the same sums in the Green's-function pass; b200_pm_get_power
+ * returns the RAW sums of the nbins = Nmesh logarithmic bins
+ * (Power[] = sum w |rho_k|^2 / window^2, kk[] = sum w |k|, Nmodes[] = sum w,
+ * *norm = |rho_0|^2), i.e. the state of struct _powerspectrum
+ * (libgadget/powerspectrum.h:8-26) just before powerspectrum_sum
+ * (powerspectrum.c:56-92), which the caller applies. */
+int b200_pm_set_power(b200_ctx *ctx, int on);
+int b200_pm_get_power(b200_ctx *ctx, int nbins, double *power, double *kk, int64_t *nmodes, double *norm);
 /* Parity hooks: integer CIC cell of every particle (iCell of pm_iterate_one,
  * petapm.c:976-980) icell_out[n][3]; and a copy of the real-space mesh
  * (density after deposit if which==0, potential after the inverse FFT if

@@ -4,6 +4,8 @@
 #include <string.h>
 #include <stdlib.h>
 #include <new>
+#include <vector>
+#include <math.h>
 
 namespace b200 {
 
@@ -192,7 +194,7 @@ void b200_ctx_destroy(b200_ctx *ctx)
     pm_destroy(E);
     pmslab_destroy(E);
     E->pos.release(); E->mass.release(); E->type.release(); E->flags.release(); E->oldacc.release();
-    E->last_tree_acc.release(); E->last_pm_acc.release(); E->aos.release();
+    E->last_tree_acc.release(); E->last_pm_acc.release(); E->aos.release(); E->pm_ps.release();
     E->keys.release(); E->keys_alt.release(); E->sidx.release(); E->sidx_alt.release(); E->cubtemp.release();
     E->spart.release(); E->spart_xy.release(); E->spart_zm.release(); E->b_start.release(); E->b_count.release(); E->b_father.release(); E->b_sibling.release();
     E->b_firstchild.release(); E->b_nchild.release(); E->b_level.release(); E->b_size.release(); E->b_dfs.release();
@@ -309,6 +311,31 @@ static int pm_force_common(Engine *E, double *gravpm_out, double *potential_out,
 
 int b200_pm_force(b200_ctx *ctx, double *gravpm_out, double *potential_out) { ENTER(ctx); return pm_force_common(E, gravpm_out, potential_out, true); }
 int b200_pm_force_dev(b200_ctx *ctx, double *gravpm_out, double *potential_out) { ENTER(ctx); return pm_force_common(E, gravpm_out, potential_out, false); }
+
+int b200_pm_set_power(b200_ctx *ctx, int on)
+{
+    ENTER(ctx);
+    E->pm_power = on != 0;
+    if(!on) E->pm_ps_valid = false;
+    return 0;
+}
+
+int b200_pm_get_power(b200_ctx *ctx, int nbins, double *power, double *kk, int64_t *nmodes, double *norm)
+{
+    ENTER(ctx);
+    if(!E->pm_ps_valid) return failmsg(E, "b200_pm_get_power: no spectrum (b200_pm_set_power(1), then b200_pm_force)");
+    if(nbins != E->Nmesh) return failmsg(E, "b200_pm_get_power: nbins must equal Nmesh (powerspectrum_alloc, gravpm.c:207)");
+    std::vector<double> h(3 * (size_t) nbins + 1);
+    CK(cudaMemcpyAsync(h.data(), E->pm_ps.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    for(int b = 0; b < nbins; b++) {
+        if(power) power[b] = h[b];
+        if(kk) kk[b] = h[nbins + b];
+        if(nmodes) nmodes[b] = (int64_t) llround(h[2 * (size_t) nbins + b]);
+    }
+    if(norm) *norm = h[3 * (size_t) nbins];
+    return 0;
+}
 
 int b200_pm_cell_index(b200_ctx *ctx, int32_t *icell_out)
 {

@@ -86,6 +86,9 @@ struct Engine {
     bool potential_valid = false;
     bool pm_fused = true;      // difference + readout in one kernel, no force meshes (B200_PM_FUSED=0: separate passes)
     bool fmesh_valid = false;
+    bool pm_power = false;     // accumulate the matter power spectrum inside the Green's-function pass
+    bool pm_ps_valid = false;
+    DevBuf<double> pm_ps;      // [3][Nmesh] Power, kk, Nmodes sums + Norm
     SlabPM *slab = nullptr;
 
     // ---- tree ----

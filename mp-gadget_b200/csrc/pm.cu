@@ -104,10 +104,21 @@ k_pm_cell_index(const double *__restrict__ pos, int64_t n, double cellsize, int3
 
 // potential_transfer (gravpm.c:383-454) applied in place to the half spectrum,
 // layout [ix][iy][iz], iz in [0, N/2].  ktab[i] = 1/sinc^2(pi k_i / N).
+//
+// POWER: also powerspectrum_add_mode (gravpm.c:330-361) on the untouched density modes: bin
+// floor(binsperunit * log(k2) / 2) of N bins, weight 2 except in the planes kz = 0 and N/2,
+// value |rho_k|^2 deconvolved by f^2; the zero mode is the normalisation.  Bins are summed per
+// block in shared memory, then once per block into ps[3][N] = {Power, kk, Nmodes}, ps[3N] = Norm.
+template <bool POWER>
 __global__ void __launch_bounds__(256)
 k_pm_potential_transfer(double2 *__restrict__ v, int N, int Nz, const double *__restrict__ ktab,
-                        double asmth2, double pot_factor)
+                        double asmth2, double pot_factor, double binsperunit, double *__restrict__ ps)
 {
+    extern __shared__ double s_ps[];            // POWER: [3][N]
+    if(POWER) {
+        for(int b = threadIdx.x; b < 3 * N; b += blockDim.x) s_ps[b] = 0;
+        __syncthreads();
+    }
     const size_t total = (size_t) N * N * Nz;
     for(size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x; idx < total;
         idx += (size_t) gridDim.x * blockDim.x) {
@@ -121,14 +132,29 @@ k_pm_potential_transfer(double2 *__restrict__ v, int N, int Nz, const double *__
         const long long k2 = (long long) kx * kx + (long long) ky * ky + (long long) kz * kz;
         double2 val = v[idx];
         if(k2 == 0) {
+            if(POWER) ps[3 * N] = val.x * val.x + val.y * val.y;       // gravpm.c:332-336
             val.x = 0.0; val.y = 0.0;                   // gravpm.c:441-449
         } else {
             const double smth = exp((double) (-k2) * asmth2) / (double) k2;
             const double f = (ktab[ix] * ktab[iy]) * ktab[iz];
+            if(POWER) {
+                const int kint = (int) floor(binsperunit * log((double) k2) / 2.);
+                if(kint < N) {
+                    const double w = (kz == 0 || kz == N / 2) ? 1.0 : 2.0;
+                    const double m = val.x * val.x + val.y * val.y;
+                    atomicAdd(&s_ps[kint], w * m * f * f);
+                    atomicAdd(&s_ps[N + kint], w * sqrt((double) k2));
+                    atomicAdd(&s_ps[2 * N + kint], w);
+                }
+            }
             const double fac = ((pot_factor * smth) * f) * f;
             val.x *= fac; val.y *= fac;
         }
         v[idx] = val;
+    }
+    if(POWER) {
+        __syncthreads();
+        for(int b = threadIdx.x; b < 3 * N; b += blockDim.x) if(s_ps[b] != 0) atomicAdd(&ps[b], s_ps[b]);
     }
 }
 
@@ -366,7 +392,17 @@ int pm_force(Engine *E, double *d_gravpm, double *d_pot)
     {
         const double asmth2 = pow((2 * M_PI) * E->Asmth / N, 2);       // gravpm.c:386
         const double pot_factor = -E->G / (M_PI * E->Box);              // gravpm.c:392
-        k_pm_potential_transfer<<<148 * 16, 256, 0, E->stream>>>((double2 *) E->cplx.p, N, Nz, E->ktab.p, asmth2, pot_factor);
+        if(E->pm_power) {
+            CK(E->pm_ps.ensure(3 * (size_t) N + 1));
+            CK(cudaMemsetAsync(E->pm_ps.p, 0, (3 * (size_t) N + 1) * sizeof(double), E->stream));
+            const double binsperunit = (N - 1) / log(sqrt(3.) * N / 2.0);       // gravpm.c:341 with size = Nmesh (gravpm.c:207)
+            const size_t sm = 3 * (size_t) N * sizeof(double);
+            CK(cudaFuncSetAttribute(k_pm_potential_transfer<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+            k_pm_potential_transfer<true><<<148 * 4, 256, sm, E->stream>>>((double2 *) E->cplx.p, N, Nz, E->ktab.p, asmth2, pot_factor,
+                                                                          binsperunit, E->pm_ps.p);
+            E->pm_ps_valid = true;
+        } else
+            k_pm_potential_transfer<false><<<148 * 16, 256, 0, E->stream>>>((double2 *) E->cplx.p, N, Nz, E->ktab.p, asmth2, pot_factor, 0.0, nullptr);
         CKL(E);
     }
     timer_stop(E, T_PM_TRANSFER);

@@ -530,6 +530,9 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
     PieceList L;
     L.pool = pool; L.ctab = s_ctab; L.empty = PIECE(0, 0);
     const int g = lane >> 3, slot = lane & 7;
+    const unsigned ltmask = (1u << lane) - 1u;
+    __shared__ int s_q_all[WALK_WARPS][64];
+    int *s_q = s_q_all[threadIdx.x >> 5];
     const int DI = S.p.DensityIndependentSphOn;
     double rA0 = 0, rA1 = 0, rA2 = 0, rDtE = 0, rMaxSig = 0, rdens = 1;
     int rncand = 0;
@@ -548,6 +551,67 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
         double A0 = 0, A1 = 0, A2 = 0, DtE = 0, MaxSig = cs_i;
         int ncand = 0;
         L.t = t; L.nt = ntp;
+        // hydro_ngbiter (hydra.c:350-505) for one neighbour that passed r^2 <= max(h_i, h_j)^2
+        auto heavy = [&](int o) {
+            const double4 q = spart[o], a_j = hA[o];
+            const double d0 = nearest_s(pm.x - q.x, S.box, S.halfbox);
+            const double d1 = nearest_s(pm.y - q.y, S.box, S.halfbox);
+            const double d2 = nearest_s(pm.z - q.z, S.box, S.halfbox);
+            double rsq = d0 * d0; rsq += d1 * d1; rsq += d2 * d2;
+            Kern kj; kern_init(kj, a_j.x, S);
+            if(rsq <= 0 || !(rsq < ki.HH || rsq < kj.HH)) return;
+            const double r = sqrt(rsq);
+            const double4 vo = svel[o], b_j = hB[o];
+            const double density_j = a_j.y, eom_j = a_j.z, P_j = a_j.w;
+            const double p_over_rho2_j = P_j / (eom_j * eom_j);
+            const double cs_j = sqrt(GAMMA * P_j / eom_j);
+            double vsig = cs_i + cs_j;
+            if(vsig > MaxSig) MaxSig = vsig;
+            const double v0 = vm.x - vo.x, v1 = vm.y - vo.y, v2 = vm.z - vo.z;
+            const double vdotr = d0 * v0 + d1 * v1 + d2 * v2;
+            const double vdotr2 = vdotr + S.hubble_a2 * rsq;
+            const double dwk_i = kern_dw(ki, r * ki.Hinv, S);
+            const double dwk_j = kern_dw(kj, r * kj.Hinv, S);
+            double visc = 0;
+            if(vdotr2 < 0) {
+                const double mu_ij = S.fac_mu * vdotr2 / r;
+                const double rho_ij = 0.5 * (dens_i + density_j);
+                double vs = cs_i + cs_j;
+                vs -= 3 * mu_ij;
+                if(vs > MaxSig) MaxSig = vs;
+                const double f2 = fabs(b_j.x) / (fabs(b_j.x) + b_j.y + 0.0001 * cs_j / S.fac_mu / a_j.x);
+                visc = 0.25 * S.p.ArtBulkViscConst * vs * (-mu_ij) / rho_ij * (F1 + f2);
+                const double dloga = 2 * S.p.dloga_bin;
+                if(dloga > 0 && (dwk_i + dwk_j) < 0) {
+                    const double msum = pm.w + q.w;
+                    if(msum > 0) {
+                        const double lim = 0.5 * S.fac_vsic_fix * vdotr2 / (0.5 * msum * (dwk_i + dwk_j) * r * dloga);
+                        if(lim < visc) visc = lim;
+                    }
+                }
+            }
+            const double hfc_visc = 0.5 * q.w * visc * (dwk_i + dwk_j) / r;
+            double hfc = hfc_visc, rr1 = 1, rr2 = 1;
+            if(DI) {
+                rr1 = 0; rr2 = 0;
+                hfc += q.w * (dwk_i * p_over_rho2_i * vo.w / vm.w + dwk_j * p_over_rho2_j * vm.w / vo.w) / r;
+                if(S.p.DensityContrastLimit >= 0) {
+                    rr1 = eom_i / dens_i;
+                    rr2 = eom_j / density_j;
+                    if(S.p.DensityContrastLimit > 0) {
+                        if(S.p.DensityContrastLimit < rr1) rr1 = S.p.DensityContrastLimit;
+                        if(S.p.DensityContrastLimit < rr2) rr2 = S.p.DensityContrastLimit;
+                    }
+                }
+            }
+            hfc += q.w * (p_over_rho2_i * b_i.z * dwk_i * rr1 + p_over_rho2_j * b_j.z * dwk_j * rr2) / r;
+            A0 += (-hfc * d0); A1 += (-hfc * d1); A2 += (-hfc * d2);
+            DtE += (0.5 * hfc_visc * vdotr2);
+        };
+        // Candidates are screened 32 at a time (treewalk.c:962-999); the survivors (about 1/4 of the
+        // particles of the opened leaves) are queued in shared memory and evaluated 32 at a time,
+        // so the long pair arithmetic runs on full warps.
+        int qn = 0;
         Ent4 eN = fetch_ent(L, 0, g);
         for(int base = 0; base < ntp; base += 16) {
             const Ent4 eC = eN;
@@ -556,66 +620,34 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
             for(int kk = 0; kk < 4; kk++) {
                 const unsigned e = eC.e[kk];
                 if(slot == 0) ncand += (int) (e & 15u);
-                if(slot >= (int) (e & 15u)) continue;
                 const int o = (int) (e >> 4) + slot;
-                const double4 q = spart[o], a_j = hA[o];
-                const double hm = a_j.x > h_i ? a_j.x : h_i, h2 = hm * hm;
-                const double d0 = nearest_s(pm.x - q.x, S.box, S.halfbox);
-                const double d1 = nearest_s(pm.y - q.y, S.box, S.halfbox);
-                const double d2 = nearest_s(pm.z - q.z, S.box, S.halfbox);
-                double rsq = d0 * d0; rsq += d1 * d1; rsq += d2 * d2;
-                if(rsq > h2) continue;
-                Kern kj; kern_init(kj, a_j.x, S);
-                if(rsq <= 0 || !(rsq < ki.HH || rsq < kj.HH)) continue;
-                const double r = sqrt(rsq);
-                const double4 vo = svel[o], b_j = hB[o];
-                const double density_j = a_j.y, eom_j = a_j.z, P_j = a_j.w;
-                const double p_over_rho2_j = P_j / (eom_j * eom_j);
-                const double cs_j = sqrt(GAMMA * P_j / eom_j);
-                double vsig = cs_i + cs_j;
-                if(vsig > MaxSig) MaxSig = vsig;
-                const double v0 = vm.x - vo.x, v1 = vm.y - vo.y, v2 = vm.z - vo.z;
-                const double vdotr = d0 * v0 + d1 * v1 + d2 * v2;
-                const double vdotr2 = vdotr + S.hubble_a2 * rsq;
-                const double dwk_i = kern_dw(ki, r * ki.Hinv, S);
-                const double dwk_j = kern_dw(kj, r * kj.Hinv, S);
-                double visc = 0;
-                if(vdotr2 < 0) {
-                    const double mu_ij = S.fac_mu * vdotr2 / r;
-                    const double rho_ij = 0.5 * (dens_i + density_j);
-                    double vs = cs_i + cs_j;
-                    vs -= 3 * mu_ij;
-                    if(vs > MaxSig) MaxSig = vs;
-                    const double f2 = fabs(b_j.x) / (fabs(b_j.x) + b_j.y + 0.0001 * cs_j / S.fac_mu / a_j.x);
-                    visc = 0.25 * S.p.ArtBulkViscConst * vs * (-mu_ij) / rho_ij * (F1 + f2);
-                    const double dloga = 2 * S.p.dloga_bin;
-                    if(dloga > 0 && (dwk_i + dwk_j) < 0) {
-                        const double msum = pm.w + q.w;
-                        if(msum > 0) {
-                            const double lim = 0.5 * S.fac_vsic_fix * vdotr2 / (0.5 * msum * (dwk_i + dwk_j) * r * dloga);
-                            if(lim < visc) visc = lim;
-                        }
-                    }
+                bool pass = false;
+                if(slot < (int) (e & 15u)) {
+                    const double4 q = spart[o];
+                    const double hj = hA[o].x;
+                    const double hm = hj > h_i ? hj : h_i, h2 = hm * hm;
+                    const double d0 = nearest_s(pm.x - q.x, S.box, S.halfbox);
+                    const double d1 = nearest_s(pm.y - q.y, S.box, S.halfbox);
+                    const double d2 = nearest_s(pm.z - q.z, S.box, S.halfbox);
+                    double rsq = d0 * d0; rsq += d1 * d1; rsq += d2 * d2;
+                    pass = !(rsq > h2);
                 }
-                const double hfc_visc = 0.5 * q.w * visc * (dwk_i + dwk_j) / r;
-                double hfc = hfc_visc, rr1 = 1, rr2 = 1;
-                if(DI) {
-                    rr1 = 0; rr2 = 0;
-                    hfc += q.w * (dwk_i * p_over_rho2_i * vo.w / vm.w + dwk_j * p_over_rho2_j * vm.w / vo.w) / r;
-                    if(S.p.DensityContrastLimit >= 0) {
-                        rr1 = eom_i / dens_i;
-                        rr2 = eom_j / density_j;
-                        if(S.p.DensityContrastLimit > 0) {
-                            if(S.p.DensityContrastLimit < rr1) rr1 = S.p.DensityContrastLimit;
-                            if(S.p.DensityContrastLimit < rr2) rr2 = S.p.DensityContrastLimit;
-                        }
-                    }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if(pass) s_q[qn + __popc(bal & ltmask)] = o;
+                qn += __popc(bal);
+                __syncwarp();
+                if(qn >= 32) {
+                    heavy(s_q[lane]);
+                    const int mv = lane < qn - 32 ? s_q[32 + lane] : 0;
+                    __syncwarp();
+                    if(lane < qn - 32) s_q[lane] = mv;
+                    qn -= 32;
+                    __syncwarp();
                 }
-                hfc += q.w * (p_over_rho2_i * b_i.z * dwk_i * rr1 + p_over_rho2_j * b_j.z * dwk_j * rr2) / r;
-                A0 += (-hfc * d0); A1 += (-hfc * d1); A2 += (-hfc * d2);
-                DtE += (0.5 * hfc_visc * vdotr2);
             }
         }
+        if(lane < qn) heavy(s_q[lane]);
+        __syncwarp();
         A0 = warp_sum(A0); A1 = warp_sum(A1); A2 = warp_sum(A2); DtE = warp_sum(DtE); MaxSig = warp_max(MaxSig);
         ncand = (int) __reduce_add_sync(0xffffffffu, (unsigned) ncand);
         if(lane == t) { rA0 = A0; rA1 = A1; rA2 = A2; rDtE = DtE; rMaxSig = MaxSig; rncand = ncand; rdens = dens_i; }

@@ -31,23 +31,15 @@
 #include <libgadget/gravity.h>
 #include <libgadget/petapm.h>
 #include <libgadget/walltime.h>
+#include <libgadget/powerspectrum.h>
+#include <libgadget/cosmology.h>
 
 #include "../../include/b200force.h"
 
-static b200_ctx *Ctx;
-
-static b200_ctx *b200_shim_ctx(void)
-{
-    if(!Ctx) {
-        int dev = 0;
-        const char *e = getenv("B200_DEVICE");       /* one process per GPU: local rank */
-        if(e) dev = atoi(e);
-        if(b200_ctx_create(&Ctx, dev))
-            endrun(1, "b200: cannot create a CUDA context on device %d (no CPU fallback in this build)\n", dev);
-    }
-    return Ctx;
-}
-#define B200_CK(call) do { if((call) != 0) endrun(1, "b200: %s\n", b200_last_error(Ctx)); } while(0)
+/* the context shared by all shim files (libgadget_shim_ctx.c) */
+b200_ctx *b200_shim_context(void);
+#define b200_shim_ctx b200_shim_context
+#define B200_CK(call) do { if((call) != 0) endrun(1, "b200: %s\n", b200_last_error(b200_shim_context())); } while(0)
 
 /* ---- replaces libgadget/gravshort-tree.c -------------------------------- */
 
@@ -136,7 +128,9 @@ void grav_short_tree(const ActiveParticles *act, PetaPM *pm, ForceTree *tree, My
 }
 
 #ifdef B200_SHIM_GRAVPM
-/* ---- replaces libgadget/gravpm.c (power-spectrum side effect not produced) -- */
+/* ---- replaces libgadget/gravpm.c; the power-spectrum sums come from the GPU pass and go
+ * through the reference's own powerspectrum_sum / powerspectrum_save (powerspectrum.c). The
+ * massive-neutrino linear-response branch (gravpm.c:304-326,415-437) is not supported. */
 void gravpm_init_periodic(PetaPM *pm, double BoxSize, double Asmth, int Nmesh, double G)   /* gravpm.c:51-54 */
 {
     pm->BoxSize = BoxSize; pm->Asmth = Asmth; pm->Nmesh = Nmesh; pm->G = G;
@@ -154,6 +148,9 @@ void gravpm_force(PetaPM *pm, DomainDecomp *ddecomp, Cosmology *CP, double Time,
     B200_CK(b200_set_particles_aos(ctx, P, n, &lay));
     double *g = (double *) mymalloc2("B200GravPM", sizeof(double) * 3 * (n > 0 ? n : 1));
     double *pot = (double *) mymalloc2("B200PMPot", sizeof(double) * (n > 0 ? n : 1));
+    if(CP && CP->MassiveNuLinRespOn)
+        endrun(1, "b200 gravpm_force(): the linear-response neutrino branch is not supported by this build\n");
+    B200_CK(b200_pm_set_power(ctx, 1));
     B200_CK(b200_pm_force(ctx, g, pot));
     #pragma omp parallel for
     for(int64_t i = 0; i < n; i++) {
@@ -163,6 +160,12 @@ void gravpm_force(PetaPM *pm, DomainDecomp *ddecomp, Cosmology *CP, double Time,
     }
     myfree(pot);
     myfree(g);
+    /* gravpm.c:207 (allocation inside _prepare), :110-118 */
+    powerspectrum_alloc(pm->ps, pm->Nmesh, 1, 0, pm->BoxSize * UnitLength_in_cm);
+    B200_CK(b200_pm_get_power(ctx, pm->Nmesh, pm->ps->Power, pm->ps->kk, pm->ps->Nmodes, &pm->ps->Norm));
+    powerspectrum_sum(pm->ps);
+    powerspectrum_save(pm->ps, PowerOutputDir, "powerspectrum", Time, GrowthFactor(CP, Time, 1.0));
+    powerspectrum_free(pm->ps);
     walltime_measure("/PMgrav/B200");
 }
 #endif

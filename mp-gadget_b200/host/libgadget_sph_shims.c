@@ -40,20 +40,10 @@
 
 #include "../../include/b200force.h"
 
-static b200_ctx *SphCtx;
-
-static b200_ctx *sph_ctx(void)
-{
-    if(!SphCtx) {
-        int dev = 0;
-        const char *e = getenv("B200_DEVICE");       /* one process per GPU: local rank */
-        if(e) dev = atoi(e);
-        if(b200_ctx_create(&SphCtx, dev))
-            endrun(1, "b200: cannot create a CUDA context on device %d (no CPU fallback in this build)\n", dev);
-    }
-    return SphCtx;
-}
-#define B200_CK(call) do { if((call) != 0) endrun(1, "b200: %s\n", b200_last_error(SphCtx)); } while(0)
+/* the context shared by all shim files (libgadget_shim_ctx.c) */
+b200_ctx *b200_shim_context(void);
+#define sph_ctx b200_shim_context
+#define B200_CK(call) do { if((call) != 0) endrun(1, "b200: %s\n", b200_last_error(b200_shim_context())); } while(0)
 
 /* ---- module parameters: the setters of density.c:21-66 and hydra.c:26-54 ---- */
 static struct density_params DensityParams;

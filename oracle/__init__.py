@@ -171,6 +171,23 @@ def hydro(tree, sp, dens, vel=None, entropy=None, dtentropy=None, fullacc=None, 
     return out
 
 
+def pm_power(pos, mass, box, nmesh, workers=-1):
+    """Raw power-spectrum sums of gravpm_force's side effect (powerspectrum_add_mode,
+    gravpm.c:330-361) = (Power[nmesh], kk[nmesh], Nmodes[nmesh], Norm)."""
+    import scipy.fft as sfft
+    pos = _c(pos, np.float64)
+    mass = _c(mass, np.float32)
+    n = len(mass)
+    L = lib()
+    mesh = np.zeros((nmesh, nmesh, nmesh))
+    icell = np.zeros((n, 3), dtype=np.int32)
+    L.oracle_pm_deposit(_p(pos), _p(mass), C.c_int64(n), C.c_double(box), C.c_int(nmesh), _p(mesh), _p(icell))
+    rhok = np.ascontiguousarray(sfft.rfftn(mesh, workers=workers))
+    pw, kk, nm, norm = np.zeros(nmesh), np.zeros(nmesh), np.zeros(nmesh, np.int64), C.c_double()
+    L.oracle_pm_power(_p(rhok), C.c_int(nmesh), _p(pw), _p(kk), _p(nm), C.byref(norm))
+    return pw, kk, nm, norm.value
+
+
 def pm_force(pos, mass, box, nmesh, asmth, G, workers=-1, return_mesh=False):
     """gravpm_force restated: deposit -> rfftn -> potential_transfer ->
     {copy, force_transfer_d} -> irfftn (unnormalised) -> readout.

@@ -76,6 +76,7 @@ void oracle_pm_deposit(const double *pos, const float *mass, int64_t n, double B
 /* petapm.c:1092-1132 + gravpm.c:383-454.  rhok: complex [Nmesh][Nmesh][Nmesh/2+1]
  * interleaved re,im, index order (x, y, z). In place. */
 void oracle_pm_potential_transfer(double *rhok, int Nmesh, double BoxSize, double Asmth, double G);
+void oracle_pm_power(const double *rhok, int Nmesh, double *power, double *kk, int64_t *nmodes, double *norm);
 /* gravpm.c:458-489. dim 0/1/2 = x/y/z. out may alias nothing (copy then scale). */
 void oracle_pm_force_transfer(const double *potk, double *out, int Nmesh, double BoxSize, int dim);
 /* petapm.c:955-1006 + gravpm.c:499-510: out[i*ostride] += sum_c w_c mesh[c]. */

@@ -121,6 +121,39 @@ void oracle_pm_potential_transfer(double *rhok, int Nmesh, double BoxSize, doubl
             }
 }
 
+/* powerspectrum_add_mode over all modes of the untouched density spectrum
+ * (gravpm.c:330-361, called from potential_transfer gravpm.c:440): raw sums of the
+ * nbins = Nmesh logarithmic bins, before powerspectrum_sum (powerspectrum.c:56-92). */
+void oracle_pm_power(const double *rhok, int Nmesh, double *power, double *kk, int64_t *nmodes, double *norm)
+{
+    const int Nz = Nmesh / 2 + 1, size = Nmesh;
+    for(int b = 0; b < size; b++) { power[b] = 0; kk[b] = 0; nmodes[b] = 0; }
+    const double binsperunit = (size - 1) / log(sqrt(3) * Nmesh / 2.0);
+    for(int ix = 0; ix < Nmesh; ix++)
+        for(int iy = 0; iy < Nmesh; iy++)
+            for(int iz = 0; iz < Nz; iz++) {
+                const int kpos[3] = {mesh_to_k(ix, Nmesh), mesh_to_k(iy, Nmesh), mesh_to_k(iz, Nmesh)};
+                int64_t k2 = 0;
+                for(int k = 0; k < 3; k++) k2 += ((int64_t) kpos[k]) * kpos[k];
+                const double *v = &rhok[2 * (((int64_t) ix * Nmesh + iy) * Nz + iz)];
+                const double m = v[0] * v[0] + v[1] * v[1];
+                if(k2 == 0) { *norm = m; continue; }
+                double f = 1.0;
+                for(int k = 0; k < 3; k++) {
+                    double tmp = (kpos[k] * M_PI) / Nmesh;
+                    tmp = sinc_unnormed(tmp);
+                    f *= 1. / (tmp * tmp);
+                }
+                const int kint = floor(binsperunit * log(k2) / 2.);
+                if(kint >= size) continue;
+                const int w = (kpos[2] == 0 || kpos[2] == Nmesh / 2) ? 1 : 2;
+                const double keff = sqrt(kpos[0] * kpos[0] + kpos[1] * kpos[1] + kpos[2] * kpos[2]);
+                power[kint] += w * m * f * f;
+                nmodes[kint] += w;
+                kk[kint] += w * keff;
+            }
+}
+
 static double diff_kernel(double w)                       /* gravpm.c:458-466 */
 {
     return 1 / 6.0 * (8 * sin(w) - sin(2 * w));

@@ -14,6 +14,8 @@ SO = os.path.join(_HERE, "_ref", "libref_tree.so")
 SO_DROPIN = os.path.join(_HERE, "_ref", "libref_dropin.so")
 # same driver, but density.c + hydra.c replaced by libgadget_sph_shims.c: density() / hydro_force() run on the GPU
 SO_DROPIN_SPH = os.path.join(_HERE, "_ref", "libref_dropin_sph.so")
+# forcetree.c, gravshort-tree.c, density.c, hydra.c all replaced: no host octree at all
+SO_DROPIN_ALL = os.path.join(_HERE, "_ref", "libref_dropin_all.so")
 _inst = None
 
 

@@ -166,3 +166,19 @@ def test_no_cpu_fallback(b200):
         pytest.skip("GPU present")
     with pytest.raises(b200.B200Error):
         b200.Engine(0)
+
+
+def test_oracle_power_spectrum_sums(ics):
+    """powerspectrum_add_mode restated: every non-zero mode of the half spectrum lands in a bin
+    with weight 1 (kz = 0, N/2 planes) or 2, so sum(Nmodes) = N^3 - 1; Norm = (total mass)^2;
+    a single plane wave puts its power in the bin of its wavenumber."""
+    nmesh, box = 24, 24.0
+    pos, mass = ics.zeldovich_lattice(12, box, seed=3)
+    pw, kk, nm, norm = oracle.pm_power(pos, mass, box, nmesh)
+    assert nm.sum() == nmesh ** 3 - 1
+    assert abs(norm - float(mass.sum(dtype=np.float64)) ** 2) <= 1e-9 * norm
+    assert np.all(pw[nm > 0] >= 0) and np.all(kk[nm > 0] > 0)
+    # bin of a mode: floor(binsperunit * log(k2) / 2), binsperunit = (N-1)/log(sqrt(3) N/2)  (gravpm.c:341-342)
+    bpu = (nmesh - 1) / np.log(np.sqrt(3) * nmesh / 2.0)
+    assert nm[0] == 6          # k2 = 1: the six axis modes (+-x, +-y with weight 1 each... kz = +-1 folded with weight 2)
+    assert int(np.floor(bpu * np.log(3.0) / 2)) < nmesh

@@ -76,3 +76,29 @@ def test_shim_set_init_hsml_equals_reference():
         out.append(r.sph_density(pos, mass, box, np.ones(len(pos)), kerneltype=1, init_hsml=True, meansep=1.0))
     assert np.abs(out[0]["hsml"] - out[1]["hsml"]).max() <= 1e-11 * out[0]["hsml"].max()
     assert np.abs(out[0]["density"] - out[1]["density"]).max() <= 1e-11 * out[0]["density"].max()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(R.SO_DROPIN_ALL), reason="oracle/_ref/libref_dropin_all.so not built")
+def test_gpu_only_tree_mode():
+    """forcetree.c replaced too (libgadget_forcetree_shims.c): force_tree_full /
+    force_tree_rebuild_mask / force_tree_calc_moments only describe the tree, the octree exists
+    in HBM only; the reference fixture code still gets the stock results."""
+    r = R.Ref(arena_gib=2.0, nthreads=2, so=R.SO_DROPIN_ALL)
+    name = "gsl4096"
+    pos, mass, box = GOLD[name + "/pos"], GOLD[name + "/mass"], float(GOLD[name + "/box"])
+    v = GOLD["%s/bh0/par" % name]
+    par = dict(zip(PARKEYS, [float(x) for x in v])); par["TreeUseBH"] = int(par["TreeUseBH"])
+    r.tree_build(pos, mass, box, oldacc=GOLD[name + "/oldacc"], topdepth=0)
+    acc, pot = r.grav_short_tree(par, 43.0071, int(GOLD[name + "/nmesh"]), 1.5)
+    racc, rpot = GOLD["%s/bh0/acc" % name], GOLD["%s/bh0/pot" % name]
+    assert np.abs(acc - racc).max() < 1e-6 * np.sqrt((racc ** 2).sum(1)).mean()
+    assert np.abs(pot - rpot).max() < 1e-6 * np.abs(rpot).max()
+    g = lambda k: GOLD_SPH["zeldovich16/" + k]
+    d = r.sph_density(g("pos"), g("mass"), float(g("box")), g("h0"), vel=g("vel"), entropy=g("entropy"), kerneltype=2,
+                      init_hsml=False, DoEgyDensity=1)
+    h = r.sph_hydro(atime=0.5, hubble=0.2, dloga_bin=0.01, DensityIndependentSphOn=1)
+    close = lambda a, b, tol: np.abs(a - b).max() <= tol * (np.abs(b).max() + 1e-300)
+    assert close(d["hsml"], GOLD_SPH["zeldovich16/k2_di1/hsml"], 1e-11)
+    assert close(d["density"], GOLD_SPH["zeldovich16/k2_di1/density"], 1e-11)
+    assert close(h["acc"], GOLD_SPH["zeldovich16/k2_di1/hydro_acc"], 1e-10)

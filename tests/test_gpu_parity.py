@@ -219,6 +219,27 @@ def test_force_step_dev(engine, ics):
         assert np.array_equal(d[2].cpu().numpy(), pot)
 
 
+def test_pm_power_spectrum_side_effect(engine, ics):
+    """gravpm_force's power spectrum (powerspectrum_add_mode inside potential_transfer,
+    gravpm.c:330-361,440): mode counts bit-exact, sums to rounding; forces unchanged."""
+    pos, box = _distributions(ics)["gslrandom16"]
+    n = len(pos)
+    mass = np.ones(n, np.float32)
+    engine.gravpm_init_periodic(box, 1.5, 48, G)
+    engine.set_particles(pos, mass)
+    g0, _ = engine.gravpm_force()
+    engine.pm_set_power(True)
+    g1, _ = engine.gravpm_force()
+    pw, kk, nm, norm = engine.pm_power()
+    engine.pm_set_power(False)
+    opw, okk, onm, onorm = oracle.pm_power(pos, mass, box, 48)
+    assert np.array_equal(nm, onm)
+    assert abs(norm - onorm) <= 1e-12 * onorm
+    assert np.abs(kk - okk).max() <= 1e-11 * okk.max()
+    assert np.abs(pw - opw).max() <= 1e-9 * opw.max()
+    assert np.abs(g1 - g0).max() <= 1e-11 * np.abs(g0).max()
+
+
 def test_empty_and_tiny_inputs(engine, ics):
     """Edge cases: no particles, one particle, particles exactly on the box edge
     (Pos == BoxSize is legal, drift.c:77-78 -> iCell == Nmesh wraps, petapm.c:903-906)."""
