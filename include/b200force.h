@@ -210,11 +210,10 @@ int b200_force_step_dev(b200_ctx *ctx, const b200_gravshort_params *par,
 /* ---- SPH density and hydro force -----------------------------------------------
  * b200_density     replaces density()     (libgadget/density.h:52, density.c:234-355)
  * b200_hydro_force replaces hydro_force() (libgadget/hydra.h:10,  hydra.c:153-245)
- * for a synchronised step: every gas particle on the same time bin, so the
- * kick/drift factors of kick_factor_data (density.c:114-132) and drifts[]
- * (hydra.c:178-186) are scalars.  Call order as run.c:466-489:
- * b200_tree_build(mask = 1: gas) -> b200_sph_set_gas -> b200_density ->
- * b200_hydro_force.  Parameters mirror struct density_params (density.h:10-28),
+ * Call order as run.c:466-489: b200_tree_build(mask = 1: gas) -> b200_sph_set_gas
+ * [-> b200_sph_set_timebins / _set_active / _set_state] -> b200_density ->
+ * b200_hydro_force.  By default the step is synchronised (every gas particle on one
+ * time bin, all of them targets) and the kick/drift factors are the scalars below.  Parameters mirror struct density_params (density.h:10-28),
  * struct hydro_params (hydra.c:26-35). */
 typedef struct b200_sph_params {
     int32_t KernelType;               /* DensityKernelType: 1 cubic, 2 quintic, 4 quartic (densitykernel.h:20-24) */
@@ -228,6 +227,31 @@ typedef struct b200_sph_params {
     double dloga_bin;                     /* get_dloga_for_bin (hydra.c:271,463) */
     double atime, hubble;                 /* scale factor and hubble_function(CP, atime) (hydra.c:219-223) */
 } b200_sph_params;
+
+/* ---- mixed time bins and active sets (optional; call after b200_sph_set_gas) -------
+ * Without these calls every gas particle is a target and sits on one time bin whose
+ * factors are the scalar fields of b200_sph_params.
+ *
+ * b200_sph_set_timebins: P[].TimeBinGravity / P[].TimeBinHydro per particle (NULL = bin 0)
+ *   and, per bin, the factors the reference derives from DriftKickTimes:
+ *   gravkick/hydrokick = kick_factor_data.gravkicks/hydrokicks (init_kick_factor_data,
+ *   density.c:114-132), dloga_pred = dloga_from_dti(Ti_Current - Ti_kick[bin]) of
+ *   SPH_EntVarPred (density.c:69-85), drift = drifts[bin] of hydro_force (hydra.c:178-186,
+ *   0 for active bins), dloga_bin = get_dloga_for_bin(bin) (hydra.c:271,463).
+ * b200_sph_set_active: ActiveParticles.ActiveParticle (timestep.h:29-38): only these
+ *   particles are density / hydro targets; every gas particle of the tree stays a source.
+ * b200_sph_set_state: SphP[].{Density, EgyWtDensity, DhsmlEgyDensityFactor, DivVel,
+ *   CurlVel} of the particles that are NOT targets (the reference reads these stale values
+ *   of inactive neighbours in hydro_ngbiter, hydra.c:395-462).  NULL arrays are left as is. */
+#define B200_TIMEBINS 46        /* libgadget/timebinmgr.h:13 */
+typedef struct b200_sph_bins {
+    double gravkick[B200_TIMEBINS + 1], hydrokick[B200_TIMEBINS + 1], dloga_pred[B200_TIMEBINS + 1],
+           drift[B200_TIMEBINS + 1], dloga_bin[B200_TIMEBINS + 1];
+} b200_sph_bins;
+int b200_sph_set_timebins(b200_ctx *ctx, const uint8_t *timebin_gravity, const uint8_t *timebin_hydro, const b200_sph_bins *bins);
+int b200_sph_set_active(b200_ctx *ctx, const int32_t *active, int64_t nactive);
+int b200_sph_set_state(b200_ctx *ctx, const double *density, const double *egywtdensity, const double *dhsmlfac,
+                       const double *divvel, const double *curlvel);
 
 /* Per-particle gas state, host arrays indexed by particle index (entries of
  * non-gas particles are ignored): Vel[n][3], Hsml[n] (required), Entropy[n],

@@ -94,7 +94,7 @@ EXPORTED = [
     "b200_get_timings", "b200_stream",
     "b200_tree_top_get_dev", "b200_tree_top_set_dev", "b200_pmslab_init", "b200_pmslab_deposit",
     "b200_pmslab_fft2d", "b200_pmslab_fft1d", "b200_pmslab_transfer", "b200_pmslab_readout_dev",
-    "b200_sph_set_gas", "b200_density", "b200_density_gradrho", "b200_hydro_force",
+    "b200_sph_set_gas", "b200_sph_set_timebins", "b200_sph_set_active", "b200_sph_set_state", "b200_density", "b200_density_gradrho", "b200_hydro_force",
 ]
 
 
@@ -265,6 +265,23 @@ class Engine:
         arrs = [f8(vel), f8(hsml), f8(entropy), f8(dtentropy), f8(fullacc), f8(gravpm), f8(hydroacc)]
         self._keep_sph = arrs
         self._ck(self.L.b200_sph_set_gas(self.ctx, *[_p(a) for a in arrs]))
+
+    def sph_set_timebins(self, bin_gravity, bin_hydro, tables):
+        """tables: dict of per-bin arrays gravkick, hydrokick, dloga_pred, drift, dloga_bin (<= 47 entries)."""
+        t = np.zeros((5, 47))
+        for r, k in enumerate(("gravkick", "hydrokick", "dloga_pred", "drift", "dloga_bin")):
+            v = np.asarray(tables[k], dtype=np.float64)[:47]
+            t[r, :len(v)] = v
+        bg = _c(bin_gravity, np.uint8); bh = _c(bin_hydro, np.uint8)
+        self._ck(self.L.b200_sph_set_timebins(self.ctx, _p(bg), _p(bh), _p(t)))
+
+    def sph_set_active(self, active):
+        a = _c(active, np.int32)
+        self._ck(self.L.b200_sph_set_active(self.ctx, _p(a), C.c_int64(0 if a is None else len(a))))
+
+    def sph_set_state(self, density=None, egywtdensity=None, dhsmlfac=None, divvel=None, curlvel=None):
+        arr = [_c(x, np.float64) for x in (density, egywtdensity, dhsmlfac, divvel, curlvel)]
+        self._ck(self.L.b200_sph_set_state(self.ctx, *[_p(x) for x in arr]))
 
     def density(self, sp, update_hsml=1, DoEgyDensity=0):
         n = self.n

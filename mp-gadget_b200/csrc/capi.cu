@@ -195,6 +195,8 @@ void b200_ctx_destroy(b200_ctx *ctx)
     pmslab_destroy(E);
     E->pos.release(); E->mass.release(); E->type.release(); E->flags.release(); E->oldacc.release();
     E->last_tree_acc.release(); E->last_pm_acc.release(); E->aos.release(); E->pm_ps.release();
+    E->s_hD.release(); E->s_bins.release(); E->s_bin_grav.release(); E->s_bin_hydro.release(); E->s_active.release();
+    E->sph_list_a.release(); E->sph_list_b.release(); E->s_left.release(); E->s_right.release();
     E->keys.release(); E->keys_alt.release(); E->sidx.release(); E->sidx_alt.release(); E->cubtemp.release();
     E->spart.release(); E->spart_xy.release(); E->spart_zm.release(); E->b_start.release(); E->b_count.release(); E->b_father.release(); E->b_sibling.release();
     E->b_firstchild.release(); E->b_nchild.release(); E->b_level.release(); E->b_size.release(); E->b_dfs.release();
@@ -559,6 +561,19 @@ int b200_sph_set_gas(b200_ctx *ctx, const double *vel, const double *hsml, const
 {
     ENTER(ctx);
     return sph_set_gas(E, vel, hsml, entropy, dtentropy, fulltreeacc, gravpm, hydroaccel);
+}
+
+int b200_sph_set_timebins(b200_ctx *ctx, const uint8_t *timebin_gravity, const uint8_t *timebin_hydro, const b200_sph_bins *bins)
+{
+    ENTER(ctx);
+    return sph_set_timebins(E, timebin_gravity, timebin_hydro, bins);
+}
+int b200_sph_set_active(b200_ctx *ctx, const int32_t *active, int64_t nactive) { ENTER(ctx); return sph_set_active(E, active, nactive); }
+int b200_sph_set_state(b200_ctx *ctx, const double *density, const double *egywtdensity, const double *dhsmlfac,
+                       const double *divvel, const double *curlvel)
+{
+    ENTER(ctx);
+    return sph_set_state(E, density, egywtdensity, dhsmlfac, divvel, curlvel);
 }
 
 static int d2h_opt(Engine *E, void *dst, const void *src, size_t bytes)

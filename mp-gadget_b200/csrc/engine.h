@@ -116,7 +116,8 @@ struct Engine {
     DevBuf<int> nodeF;          // [nn] father (DFS)
     DevBuf<int> nodeK;          // [nn][8] DFS positions of the children (-1 = none)
     DevBuf<double> nodeH;       // [nn] hmax
-    DevBuf<int> scratch_i;      // small device scalars
+    DevBuf<int> scratch_i;      // small device scalars; always ensure(256): a later, larger ensure() would
+                                // reallocate and drop counters that are already in flight
 
     // ---- SPH (original index order unless noted) ----
     DevBuf<double> s_vel, s_hsml, s_entropy, s_dtentropy, s_fullacc, s_gravpm, s_hydroacc;
@@ -126,6 +127,11 @@ struct Engine {
     DevBuf<double> s_out3, s_out1a, s_out1b;
     DevBuf<int> s_outi, s_outi2, s_niter, s_nint;
     DevBuf<double> s_left, s_right;       // smoothing-length brackets of the density iteration
+    DevBuf<double> s_hD;                  // curve order: dloga of the particle's hydro bin
+    DevBuf<double> s_bins;                // [5][B200_TIMEBINS + 1] per-bin factors
+    DevBuf<uint8_t> s_bin_grav, s_bin_hydro, s_active;
+    DevBuf<int> sph_list_a, sph_list_b;   // target lists of the density passes
+    bool s_bins_set = false, s_active_set = false;
     double sph_chunks_per_warp = 4.0;
     int sph_passes = 0;
     bool sph_density_done = false;
@@ -194,6 +200,9 @@ int sph_set_gas(Engine *E, const double *vel, const double *hsml, const double *
                 const double *fullacc, const double *gravpm, const double *hydroacc);
 int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy, int *d_ninteract, int *d_niter);
 int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte, double *d_maxsig, int *d_ninteract);
+int sph_set_timebins(Engine *E, const uint8_t *bin_grav, const uint8_t *bin_hydro, const b200_sph_bins *bins);
+int sph_set_active(Engine *E, const int32_t *active, int64_t nactive);
+int sph_set_state(Engine *E, const double *density, const double *egy, const double *dhsmlfac, const double *divvel, const double *curlvel);
 
 // walk (tree_walk.cu)
 int walk_init_tables(Engine *E);

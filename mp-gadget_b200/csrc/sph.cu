@@ -46,7 +46,13 @@ struct SphDev {
     double fac_mu, fac_vsic_fix, hubble_a2;
     int ktype;          // 0 cubic, 1 quintic, 2 quartic
     double support, sigma;
+    // per-time-bin factors [5][B200_TIMEBINS + 1]: gravkick, hydrokick, dloga_pred, drift, dloga_bin
+    // (kick_factor_data density.c:114-132, SPH_EntVarPred :74, drifts[] hydra.c:178-186,
+    // get_dloga_for_bin hydra.c:271,463) and the particles' bins (TimeBinGravity, TimeBinHydro)
+    const double *bins;
+    const uint8_t *bg, *bh;
 };
+#define NB (B200_TIMEBINS + 1)
 
 __device__ __forceinline__ double nearest_s(double x, double box, double halfbox)
 {
@@ -112,11 +118,12 @@ k_sph_predict(int64_t n, const double *__restrict__ vel, const double *__restric
 {
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
+    const double gk = S.bins[S.bg[i]], hk = S.bins[NB + S.bh[i]], dlp = S.bins[2 * NB + S.bh[i]];
     for(int j = 0; j < 3; j++)
-        velpred[3 * i + j] = (vel ? vel[3 * i + j] : 0) + S.p.gravkick * (fullacc ? fullacc[3 * i + j] : 0)
-                           + (gravpm ? gravpm[3 * i + j] : 0) * S.p.pmkick + S.p.hydrokick * (hydroacc ? hydroacc[3 * i + j] : 0);
+        velpred[3 * i + j] = (vel ? vel[3 * i + j] : 0) + gk * (fullacc ? fullacc[3 * i + j] : 0)
+                           + (gravpm ? gravpm[3 * i + j] : 0) * S.p.pmkick + hk * (hydroacc ? hydroacc[3 * i + j] : 0);
     const double E = entropy ? entropy[i] : 1.0;
-    double e = E + (dtentropy ? dtentropy[i] : 0.0) * S.p.dloga_pred;
+    double e = E + (dtentropy ? dtentropy[i] : 0.0) * dlp;
     if(e < 0.05 * E) e = 0.05 * E;
     evp[i] = e <= 0 ? 0 : exp(1. / GAMMA * log(e));
 }
@@ -485,17 +492,19 @@ __global__ void __launch_bounds__(256)
 k_sph_gather_hydro(int np, const int *__restrict__ sidx, SphDev S, const double *__restrict__ hsml, const double *__restrict__ density,
                    const double *__restrict__ egy, const double *__restrict__ dhsmlfac, const double *__restrict__ divvel,
                    const double *__restrict__ curlvel, const double4 *__restrict__ svel,
-                   double4 *__restrict__ hA, double4 *__restrict__ hB)
+                   double4 *__restrict__ hA, double4 *__restrict__ hB, double *__restrict__ hD)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if(j >= np) return;
     const int64_t i = sidx[j];
     const int DI = S.p.DensityIndependentSphOn;
     const double dens = density[i], dvv = divvel[i];
+    const double drift = S.bins[3 * NB + S.bh[i]];
+    hD[j] = S.bins[4 * NB + S.bh[i]];
     // SPH_DensityPred hydra.c:300-312
-    double dj = dens - dvv * dens * S.p.drift; if(!(dj >= 1e-6 * dens)) dj = 1e-6 * dens;
+    double dj = dens - dvv * dens * drift; if(!(dj >= 1e-6 * dens)) dj = 1e-6 * dens;
     const double eom0 = DI ? egy[i] : dens;
-    double eom = eom0 - dvv * eom0 * S.p.drift; if(!(eom >= 1e-6 * eom0)) eom = 1e-6 * eom0;
+    double eom = eom0 - dvv * eom0 * drift; if(!(eom >= 1e-6 * eom0)) eom = 1e-6 * eom0;
     const double ev = svel[j].w;
     double P = 0;                                   // PressurePred hydra.c:67-77, cache hydra.c:195-214
     if(ev != 0 && ev * eom > 0) P = exp(GAMMA * log(ev * eom));
@@ -509,7 +518,8 @@ k_sph_gather_hydro(int np, const int *__restrict__ sidx, SphDev S, const double 
 __global__ void __launch_bounds__(128, 3)
 k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict__ sidx,
                   const double4 *__restrict__ spart, const double4 *__restrict__ svel,
-                  const double4 *__restrict__ hA, const double4 *__restrict__ hB, const double *__restrict__ density, SphDev S,
+                  const double4 *__restrict__ hA, const double4 *__restrict__ hB, const double *__restrict__ hD,
+                  const double *__restrict__ density, SphDev S,
                   const unsigned *__restrict__ pool, const int *__restrict__ chunk_tab, int maxch, const int *__restrict__ piece_cnt,
                   double *__restrict__ acc_out, double *__restrict__ dte_out, double *__restrict__ maxsig_out, int *__restrict__ ninteract)
 {
@@ -542,7 +552,7 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
         // the target's rows: one broadcast load each
         const int jt = __shfl_sync(0xffffffffu, myj, t), met = __shfl_sync(0xffffffffu, me, t);
         const double4 pm = spart[jt], vm = svel[jt], a_i = hA[jt], b_i = hB[jt];
-        const double h_i = a_i.x, P_i = a_i.w, eom_i = b_i.w, dens_i = density[met];
+        const double h_i = a_i.x, P_i = a_i.w, eom_i = b_i.w, dens_i = density[met], dloga_i = hD[jt];
         // hydro_copy hydra.c:247-277
         const double cs_i = sqrt(GAMMA * P_i / eom_i);
         const double F1 = fabs(b_i.x) / (fabs(b_i.x) + b_i.y + 0.0001 * cs_i / h_i / S.fac_mu);
@@ -581,7 +591,8 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
                 if(vs > MaxSig) MaxSig = vs;
                 const double f2 = fabs(b_j.x) / (fabs(b_j.x) + b_j.y + 0.0001 * cs_j / S.fac_mu / a_j.x);
                 visc = 0.25 * S.p.ArtBulkViscConst * vs * (-mu_ij) / rho_ij * (F1 + f2);
-                const double dloga = 2 * S.p.dloga_bin;
+                const double dlj = hD[o];
+                const double dloga = 2 * (dloga_i > dlj ? dloga_i : dlj);          // hydra.c:463
                 if(dloga > 0 && (dwk_i + dwk_j) < 0) {
                     const double msum = pm.w + q.w;
                     if(msum > 0) {
@@ -676,6 +687,98 @@ static int make_dev(Engine *E, const b200_sph_params *p, SphDev &S)
     S.fac_mu = pow(p->atime, 3 * (GAMMA - 1) / 2) / p->atime;                    // hydra.c:220-223
     S.fac_vsic_fix = p->hubble * pow(p->atime, 3 * GAMMA_MINUS1);
     S.hubble_a2 = p->hubble * p->atime * p->atime;
+    // Time bins: per-particle bins + per-bin tables when b200_sph_set_timebins was called, otherwise
+    // every particle on bin 0 with the scalar factors of b200_sph_params.
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    if(!E->s_bins_set) {
+        CK(E->s_bins.ensure(5 * NB)); CK(E->s_bin_grav.ensure(n)); CK(E->s_bin_hydro.ensure(n));
+        double t[5 * NB];
+        for(int b = 0; b < NB; b++) {
+            t[b] = p->gravkick; t[NB + b] = p->hydrokick; t[2 * NB + b] = p->dloga_pred; t[3 * NB + b] = p->drift; t[4 * NB + b] = p->dloga_bin;
+        }
+        CK(cudaMemcpyAsync(E->s_bins.p, t, sizeof(t), cudaMemcpyHostToDevice, E->stream));
+        CK(cudaStreamSynchronize(E->stream));       // t is a stack buffer
+        CK(cudaMemsetAsync(E->s_bin_grav.p, 0, n, E->stream)); CK(cudaMemsetAsync(E->s_bin_hydro.p, 0, n, E->stream));
+    }
+    S.bins = E->s_bins.p; S.bg = E->s_bin_grav.p; S.bh = E->s_bin_hydro.p;
+    return 0;
+}
+
+// Targets of a pass over the gas tree: the tree particles (curve order) that are in the caller's
+// active set, or all of them.  Returns the list (NULL = identity) and its length.
+__global__ void k_sph_active_flags(int np, const int *__restrict__ sidx, const uint8_t *__restrict__ active, uint8_t *__restrict__ out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if(j < np) out[j] = active[sidx[j]];
+}
+__global__ void k_sph_mark_active(int64_t na, const int *__restrict__ list, uint8_t *__restrict__ active)
+{
+    const int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(q < na) active[list[q]] = 1;
+}
+
+static int sph_first_targets(Engine *E, int np, int *list_buf, int *iota_buf, const int **tg, int *nt)
+{
+    *tg = nullptr; *nt = np;
+    if(!E->s_active_set || np == 0) return 0;
+    CK(E->walk_flags.ensure((size_t) np + 64));
+    k_sph_active_flags<<<(np + 255) / 256, 256, 0, E->stream>>>(np, E->sidx.p, E->s_active.p, E->walk_flags.p); CKL(E);
+    k_sph_iota<<<(np + 255) / 256, 256, 0, E->stream>>>(iota_buf, np); CKL(E);
+    CK(E->scratch_i.ensure(256));
+    int *d_num = E->scratch_i.p + 13;
+    size_t tb = 0;
+    cub::DeviceSelect::Flagged(nullptr, tb, iota_buf, E->walk_flags.p, list_buf, d_num, np, E->stream);
+    CK(E->cubtemp.ensure(tb + 16));
+    CK(cub::DeviceSelect::Flagged(E->cubtemp.p, tb, iota_buf, E->walk_flags.p, list_buf, d_num, np, E->stream));
+    E->launches += 1;
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, d_num, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    *tg = list_buf; *nt = cnt;
+    return 0;
+}
+
+int sph_set_timebins(Engine *E, const uint8_t *bin_grav, const uint8_t *bin_hydro, const b200_sph_bins *bins)
+{
+    if(!bins) return failmsg(E, "b200_sph_set_timebins: null factor tables");
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->s_bins.ensure(5 * NB)); CK(E->s_bin_grav.ensure(n)); CK(E->s_bin_hydro.ensure(n));
+    CK(cudaMemcpyAsync(E->s_bins.p, bins, 5 * NB * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    if(bin_grav) CK(cudaMemcpyAsync(E->s_bin_grav.p, bin_grav, E->n, cudaMemcpyHostToDevice, E->stream));
+    else CK(cudaMemsetAsync(E->s_bin_grav.p, 0, n, E->stream));
+    if(bin_hydro) CK(cudaMemcpyAsync(E->s_bin_hydro.p, bin_hydro, E->n, cudaMemcpyHostToDevice, E->stream));
+    else CK(cudaMemsetAsync(E->s_bin_hydro.p, 0, n, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    E->s_bins_set = true;
+    return 0;
+}
+
+int sph_set_active(Engine *E, const int32_t *active, int64_t nactive)
+{
+    E->s_active_set = false;
+    if(!active) return 0;
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->s_active.ensure(n)); CK(E->targets.ensure((size_t) (nactive > 0 ? nactive : 1)));
+    CK(cudaMemsetAsync(E->s_active.p, 0, n, E->stream));
+    if(nactive > 0) {
+        CK(cudaMemcpyAsync(E->targets.p, active, nactive * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
+        k_sph_mark_active<<<(unsigned) ((nactive + 255) / 256), 256, 0, E->stream>>>(nactive, E->targets.p, E->s_active.p); CKL(E);
+    }
+    CK(cudaStreamSynchronize(E->stream));
+    E->s_active_set = true;
+    return 0;
+}
+
+int sph_set_state(Engine *E, const double *density, const double *egy, const double *dhsmlfac, const double *divvel, const double *curlvel)
+{
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    struct { const double *src; DevBuf<double> *dst; } items[] = {
+        {density, &E->s_density}, {egy, &E->s_egy}, {dhsmlfac, &E->s_dhsmlfac}, {divvel, &E->s_divvel}, {curlvel, &E->s_curlvel}};
+    for(auto &it : items) {
+        CK(it.dst->ensure(n));
+        if(it.src) CK(cudaMemcpyAsync(it.dst->p, it.src, E->n * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    }
+    CK(cudaStreamSynchronize(E->stream));
     return 0;
 }
 
@@ -696,6 +799,8 @@ int sph_set_gas(Engine *E, const double *vel, const double *hsml, const double *
     if(!hsml) return failmsg(E, "b200_sph_set_gas: hsml is required");
     CK(cudaStreamSynchronize(E->stream));
     E->sph_density_done = false;
+    E->s_bins_set = false;
+    E->s_active_set = false;
     return 0;
 }
 
@@ -711,10 +816,9 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
     CK(E->s_density.ensure(n)); CK(E->s_egy.ensure(n)); CK(E->s_dhsmlfac.ensure(n)); CK(E->s_divvel.ensure(n));
     CK(E->s_curlvel.ensure(n)); CK(E->s_dthsml.ensure(n)); CK(E->s_numngb.ensure(n)); CK(E->s_gradrho.ensure(3 * n));
     CK(E->s_svel.ensure(4 * (size_t) (np > 0 ? np : 1)));
-    CK(E->scratch_i.ensure(16));
+    CK(E->scratch_i.ensure(256));
     CK(cudaMemsetAsync(E->scratch_i.p + 12, 0, sizeof(int), E->stream));
     CK(E->s_left.ensure(n)); CK(E->s_right.ensure(n)); CK(E->s_niter.ensure(n)); CK(E->s_nint.ensure(n));
-    CK(E->targets.ensure((size_t) np + 1)); CK(E->targets_sorted.ensure((size_t) np + 1));
     CK(E->walk_flags.ensure((size_t) np + 64));
     timer_start(E, T_SPH_DENSITY);
     if(E->n > 0) {
@@ -731,9 +835,12 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
         // treewalk_do_hsml_loop (treewalk.c:1269-1367): walk, evaluate, re-queue the unconverged
         const double keep_estimate = E->walk_chunks_per_warp;
         E->walk_chunks_per_warp = E->sph_chunks_per_warp;
-        const int *tg = nullptr;            // pass 0: every tree particle, in curve order
-        int *tg_next = E->targets.p, *tg_other = E->targets_sorted.p;
+        // pass 0: every tree particle (or the active ones), in curve order
+        CK(E->sph_list_a.ensure((size_t) np + 1)); CK(E->sph_list_b.ensure((size_t) np + 1));
+        int *tg_next = E->sph_list_a.p, *tg_other = E->sph_list_b.p;
+        const int *tg = nullptr;
         int nt = np;
+        if(int rc = sph_first_targets(E, np, tg_other, tg_next, &tg, &nt)) return rc;
         for(int pass = 0; nt > 0; pass++) {
             const int64_t nwarps = (nt + 31) / 32;
             const unsigned nb = (unsigned) ((nwarps * 32 + 127) / 128);
@@ -806,23 +913,27 @@ int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte,
     if(int rc = make_dev(E, p, S)) return rc;
     if(S.p.DensityIndependentSphOn && !E->sph_DoEgy) return failmsg(E, "b200_hydro_force: pressure-entropy SPH needs b200_density with DoEgyDensity=1");
     const int np = (int) E->tree_np;
-    CK(E->s_hA.ensure(4 * (size_t) (np > 0 ? np : 1))); CK(E->s_hB.ensure(4 * (size_t) (np > 0 ? np : 1)));
+    CK(E->s_hA.ensure(4 * (size_t) (np > 0 ? np : 1))); CK(E->s_hB.ensure(4 * (size_t) (np > 0 ? np : 1))); CK(E->s_hD.ensure((size_t) (np > 0 ? np : 1)));
     timer_start(E, T_SPH_HYDRO);
     if(np > 0) {
         k_sph_gather_hydro<<<(np + 255) / 256, 256, 0, E->stream>>>(np, E->sidx.p, S, E->s_hsml.p, E->s_density.p, E->s_egy.p, E->s_dhsmlfac.p,
-            E->s_divvel.p, E->s_curlvel.p, (const double4 *) E->s_svel.p, (double4 *) E->s_hA.p, (double4 *) E->s_hB.p);
+            E->s_divvel.p, E->s_curlvel.p, (const double4 *) E->s_svel.p, (double4 *) E->s_hA.p, (double4 *) E->s_hB.p, E->s_hD.p);
         CKL(E);
+        CK(E->sph_list_a.ensure((size_t) np + 1)); CK(E->sph_list_b.ensure((size_t) np + 1));
+        const int *tg = nullptr;
+        int nt = np;
+        if(int rc = sph_first_targets(E, np, E->sph_list_a.p, E->sph_list_b.p, &tg, &nt)) return rc;
         const double keep_estimate = E->walk_chunks_per_warp;
         E->walk_chunks_per_warp = E->sph_chunks_per_warp;
-        const int64_t nwarps = (np + 31) / 32;
+        const int64_t nwarps = (nt + 31) / 32;
         const unsigned nb = (unsigned) ((nwarps * 32 + 127) / 128);
         piece_pool_reset(E);
-        for(int attempt = 0;; attempt++) {
+        for(int attempt = 0; nt > 0; attempt++) {
             PiecePool Q;
             if(int rc = piece_pool_begin(E, nwarps, &Q)) return rc;
             CK(piece_set_smem(k_sph_walk<true>, piece_ctab_bytes(E, WALK_WARPS)));
             k_sph_walk<true><<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>((const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, (const int4 *) E->nodeK.p,
-                E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, nullptr, np, E->s_hsml.p, S, Q);
+                E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, tg, nt, E->s_hsml.p, S, Q);
             CKL(E);
             bool retry = false;
             if(int rc = piece_pool_check(E, nwarps, &retry, attempt)) return rc;
@@ -831,8 +942,9 @@ int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte,
         E->sph_chunks_per_warp = E->walk_chunks_per_warp;
         E->walk_chunks_per_warp = keep_estimate;
         CK(piece_set_smem(k_sph_hydro_pairs, piece_ctab_bytes(E, WALK_WARPS)));
-        k_sph_hydro_pairs<<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>(nullptr, np, E->sidx.p, (const double4 *) E->spart.p, (const double4 *) E->s_svel.p,
-            (const double4 *) E->s_hA.p, (const double4 *) E->s_hB.p, E->s_density.p, S,
+        if(nt > 0)
+        k_sph_hydro_pairs<<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>(tg, nt, E->sidx.p, (const double4 *) E->spart.p, (const double4 *) E->s_svel.p,
+            (const double4 *) E->s_hA.p, (const double4 *) E->s_hB.p, E->s_hD.p, E->s_density.p, S,
             E->walk_pool.p, E->walk_chunktab.p, E->walk_maxch, E->walk_cnt.p, d_acc, d_dte, d_maxsig, d_ninteract);
         CKL(E);
     }

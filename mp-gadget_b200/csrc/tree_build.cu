@@ -280,7 +280,7 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
     const int64_t nin = d_active ? nactive : E->n;
     if(nin >= (1ll << 30)) return failmsg(E, "b200_tree_build: too many particles for 32-bit node indices");
     const double c0 = Box / 2., len0 = Box * 1.001;       // forcetree.c:662-664
-    CK(E->scratch_i.ensure(16));
+    CK(E->scratch_i.ensure(256));
     int *d_cnt = E->scratch_i.p;            // [0..2] split counters, [4] nvalid
     CK(cudaMemsetAsync(d_cnt, 0, 16 * sizeof(int), E->stream));
 

@@ -579,7 +579,7 @@ int piece_pool_begin(Engine *E, int64_t nwarps, PiecePool *Q)
     CK(E->walk_chunktab.ensure((size_t) nwarps * E->walk_maxch));
     Q->maxch = E->walk_maxch;
     CK(E->walk_cnt.ensure((size_t) nwarps * 32));
-    CK(E->scratch_i.ensure(128));
+    CK(E->scratch_i.ensure(256));
     if(E->walk_want == 0) E->walk_want = (size_t) (E->walk_chunks_per_warp * (double) nwarps) + 1024;
     CK(E->walk_pool.ensure(E->walk_want * CH_WORDS));
     E->walk_want = 0;
@@ -643,7 +643,7 @@ int walk_chunk_targets(Engine *E, int nchunks, int64_t chunk, int *offsets)
     if(nchunks < 1 || nchunks > 64) return failmsg(E, "walk_chunk_targets: bad chunk count");
     CK(E->targets_sorted.ensure((size_t) np + 1));
     CK(E->walk_flags.ensure(2 * (size_t) np + 64));
-    CK(E->scratch_i.ensure(128));
+    CK(E->scratch_i.ensure(256));
     unsigned char *k0 = E->walk_flags.p, *k1 = k0 + np;
     if(np > 0) {
         k_chunk_keys<<<(np + 255) / 256, 256, 0, E->stream>>>(E->sidx.p, np, (int) chunk, k0); CKL(E);
@@ -710,7 +710,7 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
             k_mark<<<(unsigned) ((nactive + 255) / 256), 256, 0, E->stream>>>(d_active, nactive, fl); CKL(E);
             k_gather_flags<<<(unsigned) ((np + 255) / 256), 256, 0, E->stream>>>(E->sidx.p, (int) np, fl, fs); CKL(E);
             CK(E->targets_sorted.ensure(np + 1));
-            CK(E->scratch_i.ensure(16));
+            CK(E->scratch_i.ensure(256));
             size_t tb = 0;
             cub::DeviceSelect::Flagged(nullptr, tb, E->sidx.p, fs, E->targets_sorted.p, E->scratch_i.p + 8, (int) np, E->stream);
             CK(E->cubtemp.ensure(tb + 16));

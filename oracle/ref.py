@@ -90,6 +90,27 @@ class Ref:
                              _p(out["dtentropy"]), _p(out["maxsignalvel"]))
         return out
 
+    def sph_mixed(self, bins, Ti_Current, tables, atime, hubble, DoEgyDensity, vel=None, fullacc=None, hydroacc=None, dtentropy=None):
+        """A mixed-time-bin density + hydro step on the state left by sph_density + sph_hydro.
+        tables: dict of per-bin arrays (TIMEBINS + 2 = 48 entries) gravkick, hydrokick, drift,
+        dloga_pred, dloga_bin.  Returns (active indices, outputs of all particles)."""
+        n = self.n
+        NT = 48
+        tab = np.zeros((5, NT))
+        for r, k in enumerate(("gravkick", "hydrokick", "drift", "dloga_pred", "dloga_bin")):
+            tab[r, :len(tables[k])] = tables[k]
+        bins = np.ascontiguousarray(bins, np.uint8)
+        opt = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)
+        vel, fullacc, hydroacc, dtentropy = opt(vel), opt(fullacc), opt(hydroacc), opt(dtentropy)
+        out = dict(hsml=np.zeros(n), density=np.zeros(n), egywtdensity=np.zeros(n), dhsmlfac=np.zeros(n), divvel=np.zeros(n),
+                   curlvel=np.zeros(n), dthsml=np.zeros(n), acc=np.zeros((n, 3)), dtentropy=np.zeros(n), maxsignalvel=np.zeros(n))
+        act = np.zeros(n, np.int32); na = C.c_int64()
+        self.L.ref_sph_mixed(_p(bins), C.c_int64(Ti_Current), _p(tab), _p(vel), _p(fullacc), _p(hydroacc), _p(dtentropy),
+                             C.c_double(atime), C.c_double(hubble), C.c_int(DoEgyDensity), _p(act), C.byref(na),
+                             _p(out["hsml"]), _p(out["density"]), _p(out["egywtdensity"]), _p(out["dhsmlfac"]), _p(out["divvel"]),
+                             _p(out["curlvel"]), _p(out["dthsml"]), _p(out["acc"]), _p(out["dtentropy"]), _p(out["maxsignalvel"]))
+        return act[:na.value].copy(), out
+
     def timings(self):
         b, w = C.c_double(), C.c_double()
         self.L.ref_timings(C.byref(b), C.byref(w))

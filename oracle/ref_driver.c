@@ -57,12 +57,31 @@ void dump_snapshot(const char *dump, const double Time, void *CP, const char *Ou
  * reference's own functions return exactly these values (timefac.c:44-45:
  * t0 == t1 -> 0; timebinmgr.c:420-447 with dti = 0 / bin 0 -> 0). */
 static double sph_dloga_bin, sph_hubble;
-double dloga_from_dti(inttime_t dti, const inttime_t Ti_Current) { if(dti != 0) endrun(1, "ref_driver: unsynchronised fixture\n"); return 0; }
-double get_dloga_for_bin(int timebin, const inttime_t Ti_Current) { return sph_dloga_bin; }
+/* Mixed-bin fixtures (ref_sph_mixed below): the kick times are laid out so that the
+ * integer-time difference handed to each function IS the time bin (Ti_kick[b] =
+ * Ti_lastactivedrift[b] = Ti_Current - b, PM_kick = Ti_Current - MIXED_PM), and the value is read
+ * from a per-bin table supplied by the test -- the reference's integrals over the scale
+ * factor (timefac.c:12-73, GSL) are replaced by numbers, its SPH code is not touched. */
+#define MIXED_PM (TIMEBINS + 1)
+static int mixed_on;
+static double mx_gravkick[TIMEBINS + 2], mx_hydrokick[TIMEBINS + 2], mx_drift[TIMEBINS + 2], mx_dloga_pred[TIMEBINS + 2], mx_dloga_bin[TIMEBINS + 2];
+static int mixed_key(inttime_t t0, inttime_t t1)
+{
+    const int64_t d = (int64_t) t1 - (int64_t) t0;
+    if(d < 0 || d > TIMEBINS + 1) endrun(1, "ref_driver: unexpected kick-time difference %ld\n", (long) d);
+    return (int) d;
+}
+double dloga_from_dti(inttime_t dti, const inttime_t Ti_Current)
+{
+    if(mixed_on) return mx_dloga_pred[mixed_key(0, dti)];
+    if(dti != 0) endrun(1, "ref_driver: unsynchronised fixture\n");
+    return 0;
+}
+double get_dloga_for_bin(int timebin, const inttime_t Ti_Current) { return mixed_on ? mx_dloga_bin[timebin] : sph_dloga_bin; }
 static double exact_factor(inttime_t t0, inttime_t t1) { if(t0 != t1) endrun(1, "ref_driver: unsynchronised fixture\n"); return 0; }
-double get_exact_drift_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return exact_factor(t0, t1); }
-double get_exact_gravkick_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return exact_factor(t0, t1); }
-double get_exact_hydrokick_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return exact_factor(t0, t1); }
+double get_exact_drift_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return mixed_on ? mx_drift[mixed_key(t0, t1)] : exact_factor(t0, t1); }
+double get_exact_gravkick_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return mixed_on ? mx_gravkick[mixed_key(t0, t1)] : exact_factor(t0, t1); }
+double get_exact_hydrokick_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return mixed_on ? mx_hydrokick[mixed_key(t0, t1)] : exact_factor(t0, t1); }
 double hubble_function(const Cosmology *CP, double a) { return sph_hubble; }
 int winds_is_particle_decoupled(int i) { return 0; }
 void winds_decoupled_hydro(int i, double atime) {}
@@ -335,6 +354,70 @@ int ref_sph_hydro(double atime, double hubble, double dloga_bin, int DensityInde
     slots_free_sph_pred_data(&sph_pred);
     return 0;
 }
+/* A mixed-time-bin step on the state left by ref_sph_density + ref_sph_hydro (which this call
+ * needs first; pass keep_pred = 1 to ref_sph_hydro... the predictor array is re-made here):
+ * particle i sits on time bin bins[i] (hydro and gravity); the bins that divide Ti_Current are
+ * active (is_timebin_active, timestep.c:143-150) and form the ActiveParticles list, as
+ * build_active_particles does; density() and hydro_force() then run for the active particles
+ * only, with inactive neighbours contributing their stale SphP state.  tables[5][TIMEBINS+2]:
+ * gravkick, hydrokick, drift, dloga_pred, dloga_bin by bin (index TIMEBINS+1 of gravkick = the PM kick factor). */
+int ref_sph_mixed(const unsigned char *bins, int64_t Ti_Current, const double *tables, const double *vel_new,
+                  const double *fullacc, const double *hydroacc_in, const double *dtentropy_in,
+                  double atime, double hubble, int DoEgyDensity, int *active_out, int64_t *nactive_out,
+                  double *hsml, double *density_out, double *egy_out, double *dhsmlfac_out, double *divvel_out, double *curlvel_out,
+                  double *dthsml_out, double *acc_out, double *dtentropy_out, double *maxsig_out)
+{
+    const int64_t n = PartManager->NumPart;
+    const int NT = TIMEBINS + 2;
+    memcpy(mx_gravkick, tables, sizeof(double) * NT); memcpy(mx_hydrokick, tables + NT, sizeof(double) * NT);
+    memcpy(mx_drift, tables + 2 * NT, sizeof(double) * NT); memcpy(mx_dloga_pred, tables + 3 * NT, sizeof(double) * NT);
+    memcpy(mx_dloga_bin, tables + 4 * NT, sizeof(double) * NT);
+    mixed_on = 1; sph_hubble = hubble;
+    DriftKickTimes times;
+    memset(&times, 0, sizeof(times));
+    times.Ti_Current = Ti_Current;
+    times.mintimebin = 1; times.maxtimebin = TIMEBINS; times.mingravtimebin = 1;
+    for(int b = 0; b <= TIMEBINS; b++) { times.Ti_kick[b] = Ti_Current - b; times.Ti_lastactivedrift[b] = Ti_Current - b; }
+    times.PM_kick = Ti_Current - MIXED_PM;
+    for(int64_t i = 0; i < n; i++) {
+        P[i].TimeBinHydro = bins[i]; P[i].TimeBinGravity = bins[i];
+        P[i].Ti_drift = Ti_Current;             /* all particles are drifted to the current time (drift.c:17-102) */
+        for(int k = 0; k < 3; k++) {
+            if(vel_new) P[i].Vel[k] = vel_new[3 * i + k];
+            if(fullacc) P[i].FullTreeGravAccel[k] = fullacc[3 * i + k];
+            if(hydroacc_in) SPHP(i).HydroAccel[k] = hydroacc_in[3 * i + k];
+        }
+        if(dtentropy_in) SPHP(i).DtEntropy = dtentropy_in[i];
+    }
+    force_tree_rebuild_mask(&Tree, &dd, GASMASK, NULL);
+    /* the arena is a stack: the list goes on top of the rebuilt tree */
+    int *list = (int *) mymalloc("ActiveList", sizeof(int) * (n > 0 ? n : 1));
+    int64_t na = 0;
+    for(int64_t i = 0; i < n; i++)
+        if(is_timebin_active(bins[i], Ti_Current)) list[na++] = i;
+    ActiveParticles act = {0};
+    act.ActiveParticle = list; act.NumActiveParticle = na; act.MaxActiveParticle = n; act.NumActiveHydro = na; act.NumActiveGravity = na;
+    act.Particles = PartManager->Base;
+    Cosmology CP = {0};
+    sph_pred.EntVarPred = NULL;
+    density(&act, 1, DoEgyDensity, 0, times, &CP, &sph_pred, NULL, &Tree);
+    force_tree_calc_moments(&Tree, &dd);
+    hydro_force(&act, atime, &sph_pred, times, &CP, &Tree);
+    for(int64_t i = 0; i < n; i++) {
+        hsml[i] = P[i].Hsml; density_out[i] = SPHP(i).Density; egy_out[i] = SPHP(i).EgyWtDensity;
+        dhsmlfac_out[i] = SPHP(i).DhsmlEgyDensityFactor; divvel_out[i] = SPHP(i).DivVel; curlvel_out[i] = SPHP(i).CurlVel;
+        dthsml_out[i] = P[i].DtHsml;
+        for(int k = 0; k < 3; k++) acc_out[3 * i + k] = SPHP(i).HydroAccel[k];
+        dtentropy_out[i] = SPHP(i).DtEntropy; maxsig_out[i] = SPHP(i).MaxSignalVel;
+    }
+    for(int64_t q = 0; q < na; q++) active_out[q] = list[q];
+    *nactive_out = na;
+    slots_free_sph_pred_data(&sph_pred);
+    myfree(list);
+    mixed_on = 0;
+    return 0;
+}
+
 void ref_sph_timings(double *dens_s, double *hydro_s) { *dens_s = t_density; *hydro_s = t_hydro; }
 
 void ref_shutdown(void) { free_all(); }

@@ -122,3 +122,44 @@ def test_gpu_reference_test_density_goldens(b200, engine, ics):
         d = engine.density(sp)
         assert abs(d["hsml"].mean() - want) < tol
         assert np.all(d["density"] > 0) and d["hsml"].min() >= 0.006 and d["hsml"].max() <= box
+
+
+MIXED = np.load(os.path.join(HERE, "golden", "ref_sph_mixed.npz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["clustered16", "zeldovich16"])
+def test_gpu_sph_mixed_timebins_equal_reference(b200, engine, name):
+    """A mixed-time-bin step (bins 2,3 active, 4,5 not; tests/golden/make_golden_sph_mixed.py) against
+    the reference's own density.c / hydra.c: density + Hsml iteration and hydro force for the active
+    particles only, per-bin kick/drift factors, inactive neighbours contributing their stale state."""
+    pos, mass, vel, ent, box, h0 = _inputs(name)
+    n = len(mass)
+    m = lambda k: MIXED[name + "/" + k]
+    tb = {k: MIXED["tables/" + k] for k in ("gravkick", "hydrokick", "drift", "dloga_pred", "dloga_bin")}
+    bins, act = m("bins"), m("active")
+    Ti = int(MIXED["Ti_Current"])
+    active_bin = np.array([b <= 0 or Ti % (1 << b) == 0 for b in range(47)])
+    tabs = dict(gravkick=tb["gravkick"][:47], hydrokick=tb["hydrokick"][:47], dloga_pred=tb["dloga_pred"][:47],
+                drift=np.where(active_bin, 0.0, tb["drift"][:47]),          # hydra.c:178-186: no drift for active bins
+                dloga_bin=tb["dloga_bin"][:47])
+    engine.set_particles(pos, mass, type=np.zeros(n, np.uint8))
+    engine.force_tree_build(box, mask=1)
+    engine.sph_set_gas(m("sync_hsml"), vel=m("vel_new"), entropy=ent, dtentropy=m("sync_hydro_dtentropy"),
+                       fullacc=m("fullacc"), hydroacc=m("sync_hydro_acc"))
+    engine.sph_set_timebins(bins, bins, tabs)
+    engine.sph_set_active(act)
+    engine.sph_set_state(density=m("sync_density"), egywtdensity=m("sync_egywtdensity"), dhsmlfac=m("sync_dhsmlfac"),
+                         divvel=m("sync_divvel"), curlvel=m("sync_curlvel"))
+    sp = b200.sph_params(KernelType=2, MinGasHsml=0.006, DensityIndependentSphOn=1, atime=0.5, hubble=0.2,
+                         pmkick=float(tb["gravkick"][47]))
+    d = engine.density(sp, update_hsml=1, DoEgyDensity=1)
+    h = engine.hydro_force(sp)
+    for k in DENS_KEYS:
+        assert _close(d[k][act], m("mixed_" + k)[act], 1e-11), k
+    for k in ("acc", "dtentropy", "maxsignalvel"):
+        assert _close(h[k][act], m("mixed_" + k)[act], 1e-10), k
+    # inactive particles keep their state
+    inact = np.setdiff1d(np.arange(n), act)
+    assert np.array_equal(d["density"][inact], m("sync_density")[inact])
+    assert np.array_equal(d["hsml"][inact], m("sync_hsml")[inact])
