@@ -9,9 +9,9 @@
  * compiled against the reference's own headers (never copied here) and forwards to
  * the C-ABI of include/b200force.h.  densitykernel.c stays the reference's.
  *
- * Scope of this build: a synchronised hydro step -- every
- * live gas particle on one time bin and in the active set -- and no black-hole
- * density targets.  Anything else ends in endrun(): there is no CPU fallback.
+ * Scope of this build: gas targets on any mix of time bins and any
+ * active set; no black-hole density targets and no decoupled wind particles -- those end in
+ * endrun(): there is no CPU fallback.
  *
  * Exercised by tests/test_dropin.py through oracle/Makefile.ref (target
  * libref_dropin_sph.so): the reference's fixture code of ref_driver.c calls
@@ -162,32 +162,26 @@ void set_init_hsml(ForceTree *tree, DomainDecomp *ddecomp, const double MeanGasS
 static int64_t ShimNumPart = -1;         /* particle count the device gas tree was built for */
 static int ShimDoEgy;
 
-/* The one hydro time bin of the live gas, or -1 if there is more than one / the
- * active set does not cover the gas (then this build cannot run the pass). */
-static int common_gas_bin(const ActiveParticles *act, int *gravbin)
+/* Per-bin factors of this step, exactly as the reference derives them from DriftKickTimes:
+ * init_kick_factor_data (density.c:114-132), SPH_EntVarPred (density.c:74), drifts[] of
+ * hydro_force (hydra.c:178-186), get_dloga_for_bin (hydra.c:271,463). */
+static void fill_bins(b200_sph_bins *B, double *pmkick, const DriftKickTimes *times, Cosmology *CP)
 {
-    int bin = -1, gbin = -1, bad = 0;
-    for(int64_t i = 0; i < PartManager->NumPart; i++) {
-        if(P[i].Type != 0 || P[i].IsGarbage || P[i].Swallowed) continue;
-        if(bin < 0) { bin = P[i].TimeBinHydro; gbin = P[i].TimeBinGravity; }
-        else if(bin != P[i].TimeBinHydro || gbin != P[i].TimeBinGravity) bad = 1;
+    struct kick_factor_data kf;
+    init_kick_factor_data(&kf, times, CP);
+    memset(B, 0, sizeof(*B));
+    *pmkick = kf.FgravkickB;
+    for(int b = 0; b <= TIMEBINS; b++) {
+        B->gravkick[b] = kf.gravkicks[b]; B->hydrokick[b] = kf.hydrokicks[b];
+        if(b < times->mintimebin) continue;
+        B->dloga_pred[b] = dloga_from_dti(times->Ti_Current - times->Ti_kick[b], times->Ti_Current);
+        if(!is_timebin_active(b, times->Ti_Current))
+            B->drift[b] = get_exact_drift_factor(CP, times->Ti_lastactivedrift[b], times->Ti_Current);
+        B->dloga_bin[b] = get_dloga_for_bin(b, times->Ti_Current);
     }
-    if(act->ActiveParticle && act->NumActiveParticle < PartManager->NumPart) {
-        /* a list is fine as long as every live gas particle is on it */
-        int64_t ngas = 0, nact = 0;
-        for(int64_t i = 0; i < PartManager->NumPart; i++) ngas += (P[i].Type == 0 && !P[i].IsGarbage && !P[i].Swallowed);
-        for(int64_t q = 0; q < act->NumActiveParticle; q++) {
-            const int i = act->ActiveParticle[q];
-            nact += (P[i].Type == 0 && !P[i].IsGarbage && !P[i].Swallowed);
-        }
-        if(nact != ngas) bad = 1;
-    }
-    *gravbin = gbin < 0 ? 0 : gbin;
-    if(bad) return -1;
-    return bin < 0 ? 0 : bin;
 }
 
-static void fill_params(b200_sph_params *sp, const DriftKickTimes *times, Cosmology *CP, int bin, int gravbin)
+static void fill_params(b200_sph_params *sp, double pmkick)
 {
     memset(sp, 0, sizeof(*sp));
     sp->KernelType = (int) DensityParams.DensityKernelType;
@@ -197,20 +191,28 @@ static void fill_params(b200_sph_params *sp, const DriftKickTimes *times, Cosmol
     sp->MinGasHsml = DensityParams.MinGasHsmlFractional * (FORCE_SOFTENING() / 2.8);      /* density.c:265 */
     sp->ArtBulkViscConst = HydroParams.ArtBulkViscConst;
     sp->DensityContrastLimit = HydroParams.DensityContrastLimit;
-    struct kick_factor_data kf;
-    init_kick_factor_data(&kf, times, CP);
-    sp->gravkick = kf.gravkicks[gravbin]; sp->hydrokick = kf.hydrokicks[bin]; sp->pmkick = kf.FgravkickB;
-    sp->dloga_pred = dloga_from_dti(times->Ti_Current - times->Ti_kick[bin], times->Ti_Current);
+    sp->pmkick = pmkick;
 }
+
+/* time bins of every particle + the factor tables -> engine */
+static void push_bins(b200_ctx *ctx, const b200_sph_bins *B)
+{
+    const int64_t n = PartManager->NumPart;
+    const size_t m = (size_t) (n > 0 ? n : 1);
+    uint8_t *bg = (uint8_t *) mymalloc("B200Bins", 2 * m), *bh = bg + m;
+    #pragma omp parallel for
+    for(int64_t i = 0; i < n; i++) { bg[i] = P[i].TimeBinGravity; bh[i] = P[i].TimeBinHydro; }
+    B200_CK(b200_sph_set_timebins(ctx, bg, bh, B));
+    myfree(bg);
+}
+
+static int is_target(const int64_t i) { return P[i].Type == 0 && !P[i].IsGarbage && !P[i].Swallowed; }
 
 void density(const ActiveParticles *act, int update_hsml, int DoEgyDensity, int BlackHoleOn, const DriftKickTimes times,
              Cosmology *CP, struct sph_pred_data *SPH_predicted, MyFloat *GradRho_mag, const ForceTree *const tree)
 {
     b200_ctx *ctx = sph_ctx();
     const int64_t n = PartManager->NumPart;
-    int gravbin;
-    const int bin = common_gas_bin(act, &gravbin);
-    if(bin < 0) endrun(1, "b200 density(): gas on several time bins or a partial active set -- not supported by this build\n");
     if(BlackHoleOn && SlotsManager->info[5].size > 0)
         endrun(1, "b200 density(): black-hole density targets are not supported by this build\n");
     if(!(tree->mask & GASMASK)) endrun(1, "b200 density(): the tree holds no gas\n");
@@ -237,10 +239,24 @@ void density(const ActiveParticles *act, int update_hsml, int DoEgyDensity, int 
         ent[i] = gas ? SPHP(i).Entropy : 1; dte[i] = gas ? SPHP(i).DtEntropy : 0;
     }
     B200_CK(b200_sph_set_gas(ctx, vel, hsml, ent, dte, fa, gp, ha));
+    /* SphP state of the gas that is not a target of this call (stale neighbours in hydro) */
+    double *st_rho = buf, *st_egy = st_rho + m, *st_fac = st_egy + m, *st_div = st_fac + m, *st_curl = st_div + m;
+    #pragma omp parallel for
+    for(int64_t i = 0; i < n; i++) {
+        const int gas = P[i].Type == 0 && !P[i].IsGarbage;
+        st_rho[i] = gas ? SPHP(i).Density : 0; st_egy[i] = gas ? SPHP(i).EgyWtDensity : 0;
+        st_fac[i] = gas ? SPHP(i).DhsmlEgyDensityFactor : 0; st_div[i] = gas ? SPHP(i).DivVel : 0; st_curl[i] = gas ? SPHP(i).CurlVel : 0;
+    }
+    B200_CK(b200_sph_set_state(ctx, st_rho, st_egy, st_fac, st_div, st_curl));
     myfree(buf);
 
+    b200_sph_bins bins;
+    double pmkick;
+    fill_bins(&bins, &pmkick, &times, CP);
+    push_bins(ctx, &bins);
+    B200_CK(b200_sph_set_active(ctx, act->ActiveParticle, act->ActiveParticle ? act->NumActiveParticle : 0));
     b200_sph_params sp;
-    fill_params(&sp, &times, CP, bin, gravbin);
+    fill_params(&sp, pmkick);
     double *out = (double *) mymalloc("B200SphOut", sizeof(double) * 10 * m);
     double *o_h = out, *o_rho = o_h + m, *o_egy = o_rho + m, *o_fac = o_egy + m, *o_div = o_fac + m, *o_curl = o_div + m,
            *o_dth = o_curl + m, *o_grad = o_dth + m;
@@ -250,10 +266,13 @@ void density(const ActiveParticles *act, int update_hsml, int DoEgyDensity, int 
     /* EntVarPred for every gas slot (density.c:291-299; freed by the caller through slots_free_sph_pred_data) */
     SPH_predicted->EntVarPred = (MyFloat *) mymalloc2("EntVarPred", sizeof(MyFloat) * (SlotsManager->info[0].size > 0 ? SlotsManager->info[0].size : 1));
     #pragma omp parallel for
-    for(int64_t i = 0; i < n; i++) {
-        if(P[i].Type != 0 || P[i].IsGarbage) continue;
-        SPH_predicted->EntVarPred[P[i].PI] = SPH_EntVarPred(i, &times);
-        if(P[i].Swallowed) continue;
+    for(int64_t i = 0; i < n; i++)
+        if(P[i].Type == 0 && !P[i].IsGarbage) SPH_predicted->EntVarPred[P[i].PI] = SPH_EntVarPred(i, &times);
+    const int64_t nq = act->ActiveParticle ? act->NumActiveParticle : n;
+    #pragma omp parallel for
+    for(int64_t q = 0; q < nq; q++) {
+        const int64_t i = act->ActiveParticle ? act->ActiveParticle[q] : q;
+        if(!is_target(i)) continue;                                           /* density_haswork density.c:521-530 */
         if(update_hsml) P[i].Hsml = o_h[i];
         P[i].DtHsml = o_dth[i];                                               /* density.c:574-577 */
         struct sph_particle_data *s = &SPHP(i);
@@ -277,29 +296,30 @@ void hydro_force(const ActiveParticles *act, const double atime, struct sph_pred
     b200_ctx *ctx = sph_ctx();
     const int64_t n = PartManager->NumPart;
     if(ShimNumPart != n) endrun(5, "Hydro called before hmax computed\n");            /* hydra.c:174-175 */
-    int gravbin;
-    const int bin = common_gas_bin(act, &gravbin);
-    if(bin < 0) endrun(1, "b200 hydro_force(): gas on several time bins or a partial active set -- not supported by this build\n");
     if(HydroParams.DensityIndependentSphOn && !ShimDoEgy)
         endrun(1, "b200 hydro_force(): pressure-entropy SPH needs density() with DoEgyDensity\n");
     for(int64_t i = 0; i < n; i++)
         if(P[i].Type == 0 && !P[i].IsGarbage && winds_is_particle_decoupled(i))              /* hydra.c:362,523 */
             endrun(1, "b200 hydro_force(): decoupled wind particles are not supported by this build\n");
 
+    b200_sph_bins bins;
+    double pmkick;
+    fill_bins(&bins, &pmkick, &times, CP);
+    push_bins(ctx, &bins);
+    B200_CK(b200_sph_set_active(ctx, act->ActiveParticle, act->ActiveParticle ? act->NumActiveParticle : 0));
     b200_sph_params sp;
-    fill_params(&sp, &times, CP, bin, gravbin);
-    /* an active bin needs no density drift (hydra.c:178-186) */
-    sp.drift = is_timebin_active(bin, times.Ti_Current) ? 0 : get_exact_drift_factor(CP, times.Ti_lastactivedrift[bin], times.Ti_Current);
-    sp.dloga_bin = get_dloga_for_bin(bin, times.Ti_Current);
+    fill_params(&sp, pmkick);
     sp.atime = atime; sp.hubble = hubble_function(CP, atime);
 
     const size_t m = (size_t) (n > 0 ? n : 1);
     double *out = (double *) mymalloc("B200HydroOut", sizeof(double) * 5 * m);
     double *acc = out, *dte = acc + 3 * m, *sig = dte + m;
     B200_CK(b200_hydro_force(ctx, &sp, acc, dte, sig, NULL));
+    const int64_t nq = act->ActiveParticle ? act->NumActiveParticle : n;
     #pragma omp parallel for
-    for(int64_t i = 0; i < n; i++) {
-        if(P[i].Type != 0 || P[i].IsGarbage || P[i].Swallowed) continue;             /* hydro_haswork, treewalk.c:234 */
+    for(int64_t q = 0; q < nq; q++) {
+        const int64_t i = act->ActiveParticle ? act->ActiveParticle[q] : q;
+        if(!is_target(i)) continue;                                                  /* hydro_haswork, treewalk.c:234 */
         struct sph_particle_data *s = &SPHP(i);
         for(int k = 0; k < 3; k++) s->HydroAccel[k] = acc[3 * i + k];                /* hydro_reduce hydra.c:279-293 */
         s->DtEntropy = dte[i];

@@ -102,3 +102,30 @@ def test_gpu_only_tree_mode():
     assert close(d["hsml"], GOLD_SPH["zeldovich16/k2_di1/hsml"], 1e-11)
     assert close(d["density"], GOLD_SPH["zeldovich16/k2_di1/density"], 1e-11)
     assert close(h["acc"], GOLD_SPH["zeldovich16/k2_di1/hydro_acc"], 1e-10)
+
+
+GOLD_MIXED = np.load(os.path.join(HERE, "golden", "ref_sph_mixed.npz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(R.SO_DROPIN_SPH), reason="oracle/_ref/libref_dropin_sph.so not built")
+def test_reference_driver_mixed_timebin_step_through_shims():
+    """The mixed-time-bin fixture (ActiveParticles list, per-bin DriftKickTimes) driven through the
+    reference-signature density() / hydro_force() shims: the shim derives the per-bin factors with
+    the reference's own init_kick_factor_data / dloga_from_dti / get_exact_drift_factor calls."""
+    name = "zeldovich16"
+    r = R.Ref(arena_gib=2.0, nthreads=2, so=R.SO_DROPIN_SPH)
+    g = lambda k: GOLD_SPH[name + "/" + k]
+    m = lambda k: GOLD_MIXED[name + "/" + k]
+    r.sph_density(g("pos"), g("mass"), float(g("box")), g("h0"), vel=g("vel"), entropy=g("entropy"), kerneltype=2,
+                  init_hsml=False, DoEgyDensity=1)
+    h0 = r.sph_hydro(atime=0.5, hubble=0.2, dloga_bin=0.01, DensityIndependentSphOn=1)
+    tb = {k: GOLD_MIXED["tables/" + k] for k in ("gravkick", "hydrokick", "drift", "dloga_pred", "dloga_bin")}
+    act, out = r.sph_mixed(m("bins"), int(GOLD_MIXED["Ti_Current"]), tb, 0.5, 0.2, 1, vel=m("vel_new"), fullacc=m("fullacc"),
+                           hydroacc=h0["acc"], dtentropy=h0["dtentropy"])
+    assert np.array_equal(act, m("active"))
+    close = lambda a, b, tol: np.abs(a - b).max() <= tol * (np.abs(b).max() + 1e-300)
+    for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel", "dthsml"):
+        assert close(out[k], m("mixed_" + k), 1e-11), k          # active: new values; inactive: untouched state
+    for k in ("acc", "dtentropy", "maxsignalvel"):
+        assert close(out[k], m("mixed_" + k), 1e-10), k
