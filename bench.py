@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--ng", type=int, default=256, help="particles per dimension per GPU")
     ap.add_argument("--cpu-ng", type=int, default=128, help="CPU-baseline sample size per dimension")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-hydro", action="store_true", help="skip the SPH density + hydro timing (configs[2] gas part)")
     ap.add_argument("--ics", default="planewave", choices=["planewave", "fft"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -488,6 +489,30 @@ def main():
         "kernels": kern,
         "tree": {"numnodes": nn, "maxdepth": int(info.maxdepth)},
     }
+    if not args.no_hydro and world == 1:
+        # BASELINE.json configs[2], gas part: SPH density (with the smoothing-length iteration) and
+        # hydro force on ng^3 gas particles (gas-only tree = force_tree_rebuild_mask(GASMASK), run.c:466-489)
+        try:
+            rng = np.random.default_rng(1)
+            vel = rng.standard_normal((n, 3)) * 0.05
+            h0 = np.full(n, 3.0 * box / ng * 0.8)
+            sp = pkg.sph_params(KernelType=2, DensityIndependentSphOn=1, MinGasHsml=1e-4, atime=0.1, hubble=3.0, dloga_bin=0.01)
+            e.set_particles(pos, mass, type=np.zeros(n, np.uint8))
+            rec = {}
+            for rep in range(3):
+                e.force_tree_build(box, mask=1)
+                tree_ms = e.timings()["tree_total"]
+                e.sph_set_gas(h0, vel=vel, entropy=np.ones(n))
+                d = e.density(sp, update_hsml=1, DoEgyDensity=1); tm_d = e.timings()["sph_density"]
+                h = e.hydro_force(sp); tm_h = e.timings()["sph_hydro"]
+                rec = {"n_gas": n, "kernel": "quintic, 113 neighbours, pressure-entropy", "tree_ms": tree_ms, "density_ms": tm_d,
+                       "hydro_ms": tm_h, "density_passes_mean": float(d["niter"].mean()), "density_passes_max": int(d["niter"].max()),
+                       "neighbours_mean": float(d["ninteract"].mean()), "hydro_candidates_mean": float(h["ninteract"].mean()),
+                       "gas_per_s_density": n / (tm_d * 1e-3), "gas_per_s_hydro": n / (tm_h * 1e-3),
+                       "gas_per_s_sph_step": n / ((tree_ms + tm_d + tm_h) * 1e-3)}
+            out["hydro"] = rec
+        except Exception as ex:
+            out["hydro"] = {"failed": repr(ex)}
     if not args.no_cpu and world == 1:
         try:
             v, kind, t, nm = cpu_force_step(args.cpu_ng, steps=1, warmup=0)

@@ -38,11 +38,26 @@ struct PiecePool {
 };
 
 // Append `entry` to the list of every lane with want == true.  Must be called by all 32 lanes.
-// mycnt: this lane's list length; nch_alloc: chunks the warp owns (warp-uniform); s_ctab: the
-// warp's chunk ids in shared memory.
-__device__ __forceinline__ void piece_push(bool want, unsigned entry, int &mycnt, int &nch_alloc, int *s_ctab,
+// mycnt: this lane's list length; last: its last entry; nch_alloc: chunks the warp owns
+// (warp-uniform); s_ctab: the warp's chunk ids in shared memory.
+// A piece that continues the lane's last piece in particle order (the next leaf on the curve)
+// is merged into it while the sum stays <= 8: trees whose leaves hold 2-4 particles (anything
+// but a power-of-two lattice) would otherwise leave most of the 8 source slots of a piece idle.
+__device__ __forceinline__ void piece_push(bool want, unsigned entry, int &mycnt, unsigned &last, int &nch_alloc, int *s_ctab,
                                            const PiecePool &Q, int group, int lane)
 {
+    if((entry & 15u) < 8u) {                // warp-uniform (the entry is): a full piece can never be merged
+        const bool merge = want && mycnt > 0 && (entry >> 4) == (last >> 4) + (last & 15u) && (last & 15u) + (entry & 15u) <= 8u;
+        if(merge) {
+            last += entry & 15u;
+            const int at = mycnt - 1, ch = at >> CH_SHIFT;
+            if(ch < nch_alloc) {
+                const int id = s_ctab[ch];
+                if(id < Q.cap) Q.pool[(size_t) id * CH_WORDS + (at & (CH_SLOTS - 1)) * 32 + lane] = last;
+            }
+            want = false;
+        }
+    }
     const int needch = (int) __reduce_max_sync(0xffffffffu, want ? (unsigned) (mycnt >> CH_SHIFT) : 0u);
     if(needch >= nch_alloc) {               // warp-uniform; once per CH_SLOTS pieces of the longest list
         if(needch >= Q.maxch) { if(lane == 0) atomicOr(Q.ctl + 1, 2); }
@@ -64,6 +79,7 @@ __device__ __forceinline__ void piece_push(bool want, unsigned entry, int &mycnt
             if(id < Q.cap) Q.pool[(size_t) id * CH_WORDS + (mycnt & (CH_SLOTS - 1)) * 32 + lane] = entry;
         }
         mycnt++;
+        last = entry;
     }
 }
 

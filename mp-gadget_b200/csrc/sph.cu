@@ -201,6 +201,7 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
     const double hw = warp_max(h);
     const unsigned validmask = __ballot_sync(0xffffffffu, valid);
     int mycnt = 0, nch_alloc = 0;
+    unsigned mylast = 0;
 
     int sp = 1;
     if(lane == 0) { s_stk_node[0] = 0; s_stk_mask[0] = validmask; }
@@ -247,7 +248,7 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
             if(M.w & 1) {
                 for(int o = 0; o < M.y; o += 8) {
                     const int c = M.y - o < 8 ? M.y - o : 8;
-                    piece_push(keep, PIECE(M.x + o, c), mycnt, nch_alloc, s_ctab, Q, group, lane);
+                    piece_push(keep, PIECE(M.x + o, c), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
                 }
             } else if(lane == k) myopeners = openmask;
         }

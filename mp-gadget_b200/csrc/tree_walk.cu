@@ -311,6 +311,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
     unsigned *s_stk_mask = s_stk_mask_all[wib];
     BatchEntry &s_ent = s_ent_all[wib];
     int mycnt = 0;          // pieces in this lane's list
+    unsigned mylast = 0;    // its last entry (merged with the next piece when contiguous)
     int nch_alloc = 0;      // chunks this warp owns (warp-uniform)
 
     const int lane = threadIdx.x & 31;
@@ -431,7 +432,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
                 if(COUNT && wantopen) n_part += M.y;
                 for(int o = 0; o < M.y; o += 8) {
                     const int c = M.y - o < 8 ? M.y - o : 8;
-                    piece_push(wantopen, PIECE(M.x + o, c), mycnt, nch_alloc, s_ctab, Q, group, lane);
+                    piece_push(wantopen, PIECE(M.x + o, c), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
                 }
             } else {
                 if(COUNT && wantopen) n_open++;
