@@ -43,10 +43,12 @@ struct PiecePool {
 // A piece that continues the lane's last piece in particle order (the next leaf on the curve)
 // is merged into it while the sum stays <= 8: trees whose leaves hold 2-4 particles (anything
 // but a power-of-two lattice) would otherwise leave most of the 8 source slots of a piece idle.
+// MERGE is a compile-time switch: the host turns it off for trees whose leaves are mostly full.
+template <bool MERGE>
 __device__ __forceinline__ void piece_push(bool want, unsigned entry, int &mycnt, unsigned &last, int &nch_alloc, int *s_ctab,
                                            const PiecePool &Q, int group, int lane)
 {
-    if((entry & 15u) < 8u) {                // warp-uniform (the entry is): a full piece can never be merged
+    if(MERGE && (entry & 15u) < 8u) {       // a full piece can never be merged
         const bool merge = want && mycnt > 0 && (entry >> 4) == (last >> 4) + (last & 15u) && (last & 15u) + (entry & 15u) <= 8u;
         if(merge) {
             last += entry & 15u;

@@ -30,6 +30,7 @@
 // This file is compiled with -fmad=false: the per-term arithmetic is the CPU's.
 #include "piece_list.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <cub/device/device_select.cuh>
 
 namespace b200 {
@@ -170,7 +171,8 @@ template <bool SYM>
 __global__ void __launch_bounds__(128, 5)
 k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, const int4 *__restrict__ nodeK,
            const double *__restrict__ nodeH, const double4 *__restrict__ spart, const int *__restrict__ sidx,
-           const int *__restrict__ targets, int nt, const double *__restrict__ hsml, SphDev S, PiecePool Q)
+           const int *__restrict__ targets, int nt, const double *__restrict__ hsml, SphDev S, PiecePool Q,
+           double *__restrict__ reach)     // [target slot] bound on the distance to any candidate of the kept leaves
 {
     extern __shared__ int s_ctab_dyn[];                 // [WALK_WARPS][Q.maxch]
     __shared__ int s_stk_node_all[WALK_WARPS][WALK_STACK];
@@ -202,6 +204,7 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
     const unsigned validmask = __ballot_sync(0xffffffffu, valid);
     int mycnt = 0, nch_alloc = 0;
     unsigned mylast = 0;
+    double myreach = 0;
 
     int sp = 1;
     if(lane == 0) { s_stk_node[0] = 0; s_stk_mask[0] = validmask; }
@@ -246,9 +249,14 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
             const unsigned openmask = __ballot_sync(0xffffffffu, keep);
             if(openmask == 0) continue;
             if(M.w & 1) {
+                if(keep) {      // every particle of a kept leaf is within search distance + len of the target (cull_node)
+                    const double hn = s_ent.H[k], len = s_ent.B[k].w;
+                    const double r = ((SYM && hn > h) ? hn : h) + len;
+                    myreach = r > myreach ? r : myreach;
+                }
                 for(int o = 0; o < M.y; o += 8) {
                     const int c = M.y - o < 8 ? M.y - o : 8;
-                    piece_push(keep, PIECE(M.x + o, c), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
+                    piece_push<true>(keep, PIECE(M.x + o, c), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
                 }
             } else if(lane == k) myopeners = openmask;
         }
@@ -272,6 +280,7 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
         __syncwarp();
     }
     piece_finish(valid, tslot, mycnt, Q, lane);
+    if(valid) reach[tslot] = myreach;
 }
 
 #define NSUM_DENS 12
@@ -280,7 +289,9 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
 // targets of this pass.  State (Hsml, Left, Right, niter) is indexed by particle index.
 __global__ void __launch_bounds__(128, 4)
 k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restrict__ sidx,
-                    const double4 *__restrict__ spart, const double4 *__restrict__ svel, SphDev S, int update_hsml, int DoEgy,
+                    const double4 *__restrict__ spart, const double2 *__restrict__ spart_xy, const double2 *__restrict__ spart_zm,
+                    const double *__restrict__ reach,
+                    const double4 *__restrict__ svel, SphDev S, int update_hsml, int DoEgy,
                     const unsigned *__restrict__ pool, const int *__restrict__ chunk_tab, int maxch, const int *__restrict__ piece_cnt, int sentinel,
                     double *__restrict__ hsml, double *__restrict__ left, double *__restrict__ right,
                     double *__restrict__ density, double *__restrict__ egy, double *__restrict__ dhsmlfac,
@@ -297,13 +308,14 @@ k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restri
     if(group * 32 >= nt) return;            // warp-uniform
     int me = -1, mycnt = 0;
     double4 pm = make_double4(0, 0, 0, 0), vm = pm;
-    double h = 1;
+    double h = 1, myreach = 0;
     if(valid) {
         const int j = targets ? targets[tslot] : tslot;
         me = sidx[j];
         pm = spart[j]; vm = svel[j];
         h = hsml[me];
         mycnt = piece_cnt[tslot];
+        myreach = reach[tslot];
     }
     piece_load_ctab(s_ctab, chunk_tab, maxch, group, mycnt, lane);
     PieceList L;
@@ -327,6 +339,10 @@ k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restri
 #pragma unroll
         for(int q = 0; q < NSUM_DENS; q++) s[q] = 0;
         int ni = 0;
+        // A target farther than its search reach from every face needs no periodic wrap: every
+        // candidate of its kept leaves is its own nearest image (the reach bounds their distance).
+        const double tr = __shfl_sync(0xffffffffu, myreach, t);
+        const bool central = tx >= tr && tx + tr <= S.box && ty >= tr && ty + tr <= S.box && tz >= tr && tz + tr <= S.box;
         Ent4 eN = fetch_ent(L, 0, g);
         for(int base = 0; base < ntp; base += 16) {
             const Ent4 eC = eN;
@@ -336,11 +352,10 @@ k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restri
                 const unsigned e = eC.e[kk];
                 if(slot >= (int) (e & 15u)) continue;
                 const int o = (int) (e >> 4) + slot;
-                const double4 q = spart[o];
+                const double2 qa = spart_xy[o], qb = spart_zm[o];       // whole sectors per 8-lane group
                 // treewalk.c:1223-1233
-                const double d0 = nearest_s(tx - q.x, S.box, S.halfbox);
-                const double d1 = nearest_s(ty - q.y, S.box, S.halfbox);
-                const double d2 = nearest_s(tz - q.z, S.box, S.halfbox);
+                double d0 = tx - qa.x, d1 = ty - qa.y, d2 = tz - qb.x;
+                if(!central) { d0 = nearest_s(d0, S.box, S.halfbox); d1 = nearest_s(d1, S.box, S.halfbox); d2 = nearest_s(d2, S.box, S.halfbox); }
                 double r2 = d0 * d0; r2 += d1 * d1; r2 += d2 * d2;
                 if(r2 > h2) continue;
                 ni++;
@@ -350,7 +365,7 @@ k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restri
                     const double wk = kern_w(k, u, S);
                     s[0] += wk * vol;
                     const double dwk = kern_dw(k, u, S);
-                    const double mj = q.w;
+                    const double mj = qb.y;
                     s[1] += mj * wk;
                     const double dW = -(3 * k.Hinv * wk + u * dwk);
                     s[2] += mj * dW;
@@ -518,7 +533,8 @@ k_sph_gather_hydro(int np, const int *__restrict__ sidx, SphDev S, const double 
 // (treewalk.c:962-999 filters them by r^2 <= max(h_i, h_j)^2).
 __global__ void __launch_bounds__(128, 3)
 k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict__ sidx,
-                  const double4 *__restrict__ spart, const double4 *__restrict__ svel,
+                  const double4 *__restrict__ spart, const double2 *__restrict__ spart_xy, const double2 *__restrict__ spart_zm,
+                  const double *__restrict__ reach, const double4 *__restrict__ svel,
                   const double4 *__restrict__ hA, const double4 *__restrict__ hB, const double *__restrict__ hD,
                   const double *__restrict__ density, SphDev S,
                   const unsigned *__restrict__ pool, const int *__restrict__ chunk_tab, int maxch, const int *__restrict__ piece_cnt,
@@ -532,10 +548,12 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
     const bool valid = tslot < nt;
     if(group * 32 >= nt) return;            // warp-uniform
     int me = -1, mycnt = 0, myj = 0;
+    double myreach = 0;
     if(valid) {
         myj = targets ? targets[tslot] : tslot;
         me = sidx[myj];
         mycnt = piece_cnt[tslot];
+        myreach = reach[tslot];
     }
     piece_load_ctab(s_ctab, chunk_tab, maxch, group, mycnt, lane);
     PieceList L;
@@ -553,6 +571,9 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
         // the target's rows: one broadcast load each
         const int jt = __shfl_sync(0xffffffffu, myj, t), met = __shfl_sync(0xffffffffu, me, t);
         const double4 pm = spart[jt], vm = svel[jt], a_i = hA[jt], b_i = hB[jt];
+        // no periodic wrap for a target farther than its search reach from every face (see k_sph_density_pairs)
+        const double tr = __shfl_sync(0xffffffffu, myreach, t);
+        const bool wrap = !(pm.x >= tr && pm.x + tr <= S.box && pm.y >= tr && pm.y + tr <= S.box && pm.z >= tr && pm.z + tr <= S.box);
         const double h_i = a_i.x, P_i = a_i.w, eom_i = b_i.w, dens_i = density[met], dloga_i = hD[jt];
         // hydro_copy hydra.c:247-277
         const double cs_i = sqrt(GAMMA * P_i / eom_i);
@@ -564,10 +585,10 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
         L.t = t; L.nt = ntp;
         // hydro_ngbiter (hydra.c:350-505) for one neighbour that passed r^2 <= max(h_i, h_j)^2
         auto heavy = [&](int o) {
-            const double4 q = spart[o], a_j = hA[o];
-            const double d0 = nearest_s(pm.x - q.x, S.box, S.halfbox);
-            const double d1 = nearest_s(pm.y - q.y, S.box, S.halfbox);
-            const double d2 = nearest_s(pm.z - q.z, S.box, S.halfbox);
+            const double2 qa = spart_xy[o], qb = spart_zm[o];
+            const double4 q = make_double4(qa.x, qa.y, qb.x, qb.y), a_j = hA[o];
+            double d0 = pm.x - q.x, d1 = pm.y - q.y, d2 = pm.z - q.z;
+            if(wrap) { d0 = nearest_s(d0, S.box, S.halfbox); d1 = nearest_s(d1, S.box, S.halfbox); d2 = nearest_s(d2, S.box, S.halfbox); }
             double rsq = d0 * d0; rsq += d1 * d1; rsq += d2 * d2;
             Kern kj; kern_init(kj, a_j.x, S);
             if(rsq <= 0 || !(rsq < ki.HH || rsq < kj.HH)) return;
@@ -635,12 +656,11 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
                 const int o = (int) (e >> 4) + slot;
                 bool pass = false;
                 if(slot < (int) (e & 15u)) {
-                    const double4 q = spart[o];
+                    const double2 qa = spart_xy[o], qb = spart_zm[o];
                     const double hj = hA[o].x;
                     const double hm = hj > h_i ? hj : h_i, h2 = hm * hm;
-                    const double d0 = nearest_s(pm.x - q.x, S.box, S.halfbox);
-                    const double d1 = nearest_s(pm.y - q.y, S.box, S.halfbox);
-                    const double d2 = nearest_s(pm.z - q.z, S.box, S.halfbox);
+                    double d0 = pm.x - qa.x, d1 = pm.y - qa.y, d2 = pm.z - qb.x;
+                    if(wrap) { d0 = nearest_s(d0, S.box, S.halfbox); d1 = nearest_s(d1, S.box, S.halfbox); d2 = nearest_s(d2, S.box, S.halfbox); }
                     double rsq = d0 * d0; rsq += d1 * d1; rsq += d2 * d2;
                     pass = !(rsq > h2);
                 }
@@ -845,20 +865,22 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
         for(int pass = 0; nt > 0; pass++) {
             const int64_t nwarps = (nt + 31) / 32;
             const unsigned nb = (unsigned) ((nwarps * 32 + 127) / 128);
+            CK(E->walk_partial.ensure((size_t) nwarps * 32 * 4));
             piece_pool_reset(E);
             for(int attempt = 0;; attempt++) {
                 PiecePool Q;
                 if(int rc = piece_pool_begin(E, nwarps, &Q)) return rc;
                 CK(piece_set_smem(k_sph_walk<false>, piece_ctab_bytes(E, WALK_WARPS)));
                 k_sph_walk<false><<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>((const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, (const int4 *) E->nodeK.p,
-                    E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, tg, nt, E->s_hsml.p, S, Q);
+                    E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, tg, nt, E->s_hsml.p, S, Q, E->walk_partial.p);
                 CKL(E);
                 bool retry = false;
                 if(int rc = piece_pool_check(E, nwarps, &retry, attempt)) return rc;
                 if(!retry) break;
             }
             CK(piece_set_smem(k_sph_density_pairs, piece_ctab_bytes(E, WALK_WARPS)));
-            k_sph_density_pairs<<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>(tg, nt, E->sidx.p, (const double4 *) E->spart.p, (const double4 *) E->s_svel.p,
+            k_sph_density_pairs<<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>(tg, nt, E->sidx.p, (const double4 *) E->spart.p,
+                (const double2 *) E->spart_xy.p, (const double2 *) E->spart_zm.p, E->walk_partial.p, (const double4 *) E->s_svel.p,
                 S, update_hsml, DoEgy, E->walk_pool.p, E->walk_chunktab.p, E->walk_maxch, E->walk_cnt.p, 0,
                 E->s_hsml.p, E->s_left.p, E->s_right.p, E->s_density.p, E->s_egy.p, E->s_dhsmlfac.p, E->s_divvel.p, E->s_curlvel.p,
                 E->s_dthsml.p, E->s_numngb.p, E->s_gradrho.p, E->s_nint.p, E->s_niter.p, E->walk_flags.p, E->scratch_i.p + 12);
@@ -928,13 +950,14 @@ int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte,
         E->walk_chunks_per_warp = E->sph_chunks_per_warp;
         const int64_t nwarps = (nt + 31) / 32;
         const unsigned nb = (unsigned) ((nwarps * 32 + 127) / 128);
+        CK(E->walk_partial.ensure((size_t) (nwarps > 0 ? nwarps : 1) * 32 * 4));
         piece_pool_reset(E);
         for(int attempt = 0; nt > 0; attempt++) {
             PiecePool Q;
             if(int rc = piece_pool_begin(E, nwarps, &Q)) return rc;
             CK(piece_set_smem(k_sph_walk<true>, piece_ctab_bytes(E, WALK_WARPS)));
             k_sph_walk<true><<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>((const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, (const int4 *) E->nodeK.p,
-                E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, tg, nt, E->s_hsml.p, S, Q);
+                E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, tg, nt, E->s_hsml.p, S, Q, E->walk_partial.p);
             CKL(E);
             bool retry = false;
             if(int rc = piece_pool_check(E, nwarps, &retry, attempt)) return rc;
@@ -944,7 +967,8 @@ int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte,
         E->walk_chunks_per_warp = keep_estimate;
         CK(piece_set_smem(k_sph_hydro_pairs, piece_ctab_bytes(E, WALK_WARPS)));
         if(nt > 0)
-        k_sph_hydro_pairs<<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>(tg, nt, E->sidx.p, (const double4 *) E->spart.p, (const double4 *) E->s_svel.p,
+        k_sph_hydro_pairs<<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>(tg, nt, E->sidx.p, (const double4 *) E->spart.p,
+            (const double2 *) E->spart_xy.p, (const double2 *) E->spart_zm.p, E->walk_partial.p, (const double4 *) E->s_svel.p,
             (const double4 *) E->s_hA.p, (const double4 *) E->s_hB.p, E->s_hD.p, E->s_density.p, S,
             E->walk_pool.p, E->walk_chunktab.p, E->walk_maxch, E->walk_cnt.p, d_acc, d_dte, d_maxsig, d_ninteract);
         CKL(E);

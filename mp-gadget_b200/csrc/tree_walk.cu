@@ -282,7 +282,7 @@ struct BatchEntry {
                       // flags (bit0: leaf, bit1: rejected for all lanes by the bounding-box test)
 };
 
-template <bool COUNT>
+template <bool COUNT, bool MERGE>
 __global__ void __launch_bounds__(128, WALK_MINB)
 k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB,
             const int4 *__restrict__ nodeC, const int4 *__restrict__ nodeK, const double4 *__restrict__ spart,
@@ -432,7 +432,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
                 if(COUNT && wantopen) n_part += M.y;
                 for(int o = 0; o < M.y; o += 8) {
                     const int c = M.y - o < 8 ? M.y - o : 8;
-                    piece_push(wantopen, PIECE(M.x + o, c), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
+                    piece_push<MERGE>(wantopen, PIECE(M.x + o, c), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
                 }
             } else {
                 if(COUNT && wantopen) n_open++;
@@ -738,12 +738,16 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
         PiecePool Q;
         if(int rc = piece_pool_begin(E, nwarps, &Q)) return rc;
         const size_t wsm = piece_ctab_bytes(E, WALK_WARPS);
-        CK(piece_set_smem(k_grav_walk<true>, wsm)); CK(piece_set_smem(k_grav_walk<false>, wsm));
+        // merging of contiguous leaf pieces pays when the leaves are mostly not full (8 particles)
+        const bool merge = (double) E->tree_np < 5.0 * (double) E->tree_nn;
+        CK(piece_set_smem(k_grav_walk<true, true>, wsm)); CK(piece_set_smem(k_grav_walk<false, true>, wsm));
+        CK(piece_set_smem(k_grav_walk<false, false>, wsm));
 #define WALK_ARGS (const double4 *) E->nodeA.p, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, \
                   (const int4 *) E->nodeK.p, (const double4 *) E->spart.p, tg, E->pos.p, E->mass.p, E->oldacc.p, E->srtab.p, \
                   P, Q, (double4 *) E->walk_partial.p
-        if(d_counts) k_grav_walk<true><<<nb, bs, wsm, E->stream>>>(WALK_ARGS, (int4 *) d_counts);
-        else k_grav_walk<false><<<nb, bs, wsm, E->stream>>>(WALK_ARGS, nullptr);
+        if(d_counts) k_grav_walk<true, true><<<nb, bs, wsm, E->stream>>>(WALK_ARGS, (int4 *) d_counts);
+        else if(merge) k_grav_walk<false, true><<<nb, bs, wsm, E->stream>>>(WALK_ARGS, nullptr);
+        else k_grav_walk<false, false><<<nb, bs, wsm, E->stream>>>(WALK_ARGS, nullptr);
 #undef WALK_ARGS
         CKL(E);
         bool retry = false;
