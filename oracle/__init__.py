@@ -138,14 +138,43 @@ def set_init_hsml(tree, kerneltype, eta, mean_gas_separation):
     return h
 
 
+_mixed_keep = []
+
+
+def sph_set_mixed(bin_grav=None, bin_hydro=None, tables=None, active=None, n=None):
+    """Install (or with no arguments clear) the mixed-time-bin context of the following density() /
+    hydro() calls: per-particle bins, per-bin tables gravkick, hydrokick, dloga_pred, drift, dloga_bin
+    (<= 47 entries each) and the active particle indices."""
+    del _mixed_keep[:]
+    if bin_grav is None:
+        lib().oracle_sph_set_mixed(None, None, None, None)
+        return
+    bg = _c(bin_grav, np.uint8); bh = _c(bin_hydro, np.uint8)
+    tab = np.zeros((5, 47))
+    for r, k in enumerate(("gravkick", "hydrokick", "dloga_pred", "drift", "dloga_bin")):
+        v = np.asarray(tables[k], dtype=np.float64)[:47]
+        tab[r, :len(v)] = v
+    flags = None
+    if active is not None:
+        flags = np.zeros(len(bg) if n is None else n, np.uint8)
+        flags[np.asarray(active)] = 1
+    _mixed_keep.extend([bg, bh, tab, flags])        # the C side keeps the pointers
+    lib().oracle_sph_set_mixed(_p(bg), _p(bh), _p(tab), _p(flags))
+
+
 def density(tree, sp, hsml, update_hsml=1, DoEgyDensity=0, vel=None, entropy=None, dtentropy=None,
-            fullacc=None, gravpm=None, hydroacc=None):
-    """oracle_density on the particles of an OracleTree (gas tree). Returns a dict."""
+            fullacc=None, gravpm=None, hydroacc=None, state=None):
+    """oracle_density on the particles of an OracleTree (gas tree). Returns a dict.
+    state: dict of arrays the outputs start from (the values particles outside the active set keep)."""
     n = tree.n
     f8 = lambda a: _c(a, np.float64)
     out = dict(hsml=np.array(hsml, dtype=np.float64, copy=True), density=np.zeros(n), egywtdensity=np.zeros(n),
                dhsmlfac=np.zeros(n), divvel=np.zeros(n), curlvel=np.zeros(n), dthsml=np.zeros(n), numngb=np.zeros(n),
                ninteract=np.zeros(n, np.int32), niter=np.zeros(n, np.int32), entvarpred=np.zeros(n))
+    if state is not None:
+        for k in ("density", "egywtdensity", "dhsmlfac", "divvel", "curlvel", "dthsml"):
+            if k in state:
+                out[k] = np.array(state[k], dtype=np.float64, copy=True)
     vel, entropy, dtentropy, fullacc, gravpm, hydroacc = map(f8, (vel, entropy, dtentropy, fullacc, gravpm, hydroacc))
     lib().oracle_density.restype = C.c_int
     rc = lib().oracle_density(C.byref(tree.t), _p(tree.pos), _p(tree.mass), _p(tree.type), C.c_int64(n), C.byref(sp),

@@ -87,7 +87,7 @@ void oracle_pm_readout(const double *mesh, const double *pos, int64_t n, double 
 void oracle_direct_sum(const double *pos, const float *mass, int64_t n, double BoxSize, double G,
                        double softening_h, int repeat, double *accel_out);
 
-/* ---- SPH (synchronised step: all gas on one time bin) ---- */
+/* ---- SPH (synchronised step by default; mixed time bins / active sets via oracle_sph_set_mixed) ---- */
 typedef struct oracle_sph_params {
     int32_t KernelType;               /* 1 cubic, 2 quintic, 4 quartic: densitykernel.h:20-24 */
     int32_t DensityIndependentSphOn;  /* hydra.c:37-53 */
@@ -101,6 +101,8 @@ typedef struct oracle_sph_params {
 } oracle_sph_params;
 
 double oracle_sph_desnumngb(int kerneltype, double eta);
+#define ORACLE_NBINS 47          /* TIMEBINS + 1, timebinmgr.h:13 */
+void oracle_sph_set_mixed(const uint8_t *bin_grav, const uint8_t *bin_hydro, const double *tab, const uint8_t *active);
 void oracle_set_init_hsml(const oracle_tree *t, const float *mass, const uint8_t *type, int64_t n,
                           int kerneltype, double eta, double MeanGasSeparation, double *hsml);
 int oracle_density(oracle_tree *t, const double *pos, const float *mass, const uint8_t *type, int64_t n,

@@ -131,6 +131,25 @@ static int check_neighbours(double *Hsml, double *Left, double *Right, double Nu
 
 /* density() for gas targets; tree must hold the gas particles (GASMASK).
  * Arrays are indexed by particle index.  vel/acc inputs may be NULL (= 0). */
+/* ---- mixed time bins / active sets ------------------------------------------------------
+ * oracle_sph_set_mixed installs, for the following oracle_density / oracle_hydro calls, the
+ * particles' time bins (TimeBinGravity, TimeBinHydro), the per-bin factor tables
+ * tab[5][ORACLE_NBINS] = gravkick, hydrokick, dloga_pred, drift, dloga_bin (what the reference
+ * derives from DriftKickTimes: density.c:74,114-132, hydra.c:178-186,271,463) and the active
+ * flags (ActiveParticles, timestep.h:29-38): only flagged particles are targets, the others keep
+ * the state passed in and act as neighbours.  NULL bins resets to the synchronised mode. */
+static const uint8_t *mx_bg, *mx_bh, *mx_active;
+static const double *mx_tab;
+void oracle_sph_set_mixed(const uint8_t *bin_grav, const uint8_t *bin_hydro, const double *tab, const uint8_t *active)
+{
+    mx_bg = bin_grav; mx_bh = bin_hydro; mx_tab = tab; mx_active = active;
+}
+static inline double f_gravkick(const oracle_sph_params *sp, int64_t i) { return mx_tab ? mx_tab[mx_bg[i]] : sp->gravkick; }
+static inline double f_hydrokick(const oracle_sph_params *sp, int64_t i) { return mx_tab ? mx_tab[ORACLE_NBINS + mx_bh[i]] : sp->hydrokick; }
+static inline double f_dloga_pred(const oracle_sph_params *sp, int64_t i) { return mx_tab ? mx_tab[2 * ORACLE_NBINS + mx_bh[i]] : sp->dloga_pred; }
+static inline double f_drift(const oracle_sph_params *sp, int64_t i) { return mx_tab ? mx_tab[3 * ORACLE_NBINS + mx_bh[i]] : sp->drift; }
+static inline double f_dloga_bin(const oracle_sph_params *sp, int64_t i) { return mx_tab ? mx_tab[4 * ORACLE_NBINS + mx_bh[i]] : sp->dloga_bin; }
+
 int oracle_density(oracle_tree *t, const double *pos, const float *mass, const uint8_t *type, int64_t n,
                    const oracle_sph_params *sp, int update_hsml, int DoEgyDensity,
                    const double *vel, const double *fullacc, const double *gravpm, const double *hydroacc,
@@ -145,9 +164,9 @@ int oracle_density(oracle_tree *t, const double *pos, const float *mass, const u
     double *evp = (double *) malloc(sizeof(double) * n);
     for(int64_t i = 0; i < n; i++) {
         for(int j = 0; j < 3; j++)                    /* SPH_VelPred density.c:91-100 */
-            velpred[3 * i + j] = (vel ? vel[3 * i + j] : 0) + sp->gravkick * (fullacc ? fullacc[3 * i + j] : 0)
-                               + (gravpm ? gravpm[3 * i + j] : 0) * sp->pmkick + sp->hydrokick * (hydroacc ? hydroacc[3 * i + j] : 0);
-        evp[i] = entvarpred(entropy ? entropy[i] : 1.0, dtentropy ? dtentropy[i] : 0.0, sp->dloga_pred);
+            velpred[3 * i + j] = (vel ? vel[3 * i + j] : 0) + f_gravkick(sp, i) * (fullacc ? fullacc[3 * i + j] : 0)
+                               + (gravpm ? gravpm[3 * i + j] : 0) * sp->pmkick + f_hydrokick(sp, i) * (hydroacc ? hydroacc[3 * i + j] : 0);
+        evp[i] = entvarpred(entropy ? entropy[i] : 1.0, dtentropy ? dtentropy[i] : 0.0, f_dloga_pred(sp, i));
         if(entvarpred_out) entvarpred_out[i] = evp[i];
     }
     const oracle_node *N = t->nodes;
@@ -155,6 +174,7 @@ int oracle_density(oracle_tree *t, const double *pos, const float *mass, const u
 #pragma omp parallel for schedule(dynamic, 64)
     for(int64_t i = 0; i < n; i++) {
         if(type && type[i] != 0) continue;             /* density_haswork: gas (BH not modelled here) */
+        if(mx_active && !mx_active[i]) continue;       /* not in the active set: state untouched */
         double Left = 0, Right = box, h = hsml[i];
         double Ngb = 0, Rho = 0, Dh = 0, EgyRho = 0, DhEgy = 0, Div = 0, Rot[3] = {0, 0, 0}, DhsmlDens = 0;
         int nint = 0, it = 0;
@@ -306,10 +326,10 @@ int oracle_hydro(const oracle_tree *t, const double *pos, const float *mass, con
     double *press = (double *) malloc(sizeof(double) * n);
     for(int64_t i = 0; i < n; i++) {
         for(int j = 0; j < 3; j++)
-            velpred[3 * i + j] = (vel ? vel[3 * i + j] : 0) + sp->gravkick * (fullacc ? fullacc[3 * i + j] : 0)
-                               + (gravpm ? gravpm[3 * i + j] : 0) * sp->pmkick + sp->hydrokick * (hydroacc_in ? hydroacc_in[3 * i + j] : 0);
-        evp[i] = entvarpred(entropy ? entropy[i] : 1.0, dtentropy_in ? dtentropy_in[i] : 0.0, sp->dloga_pred);
-        const double eom = density_pred(DI ? egywtdensity[i] : density[i], divvel[i], sp->drift);   /* hydra.c:205-212 */
+            velpred[3 * i + j] = (vel ? vel[3 * i + j] : 0) + f_gravkick(sp, i) * (fullacc ? fullacc[3 * i + j] : 0)
+                               + (gravpm ? gravpm[3 * i + j] : 0) * sp->pmkick + f_hydrokick(sp, i) * (hydroacc_in ? hydroacc_in[3 * i + j] : 0);
+        evp[i] = entvarpred(entropy ? entropy[i] : 1.0, dtentropy_in ? dtentropy_in[i] : 0.0, f_dloga_pred(sp, i));
+        const double eom = density_pred(DI ? egywtdensity[i] : density[i], divvel[i], f_drift(sp, i));   /* hydra.c:205-212 */
         press[i] = evp[i] == 0 ? 0 : pressure_pred(eom, evp[i]);
     }
     const oracle_node *N = t->nodes;
@@ -319,6 +339,7 @@ int oracle_hydro(const oracle_tree *t, const double *pos, const float *mass, con
 #pragma omp for schedule(dynamic, 64)
         for(int64_t i = 0; i < n; i++) {
             if(type && type[i] != 0) continue;
+            if(mx_active && !mx_active[i]) continue;
             /* hydro_copy hydra.c:247-277 */
             const double eom_i = DI ? egywtdensity[i] : density[i];
             const double P_i = press[i];
@@ -353,8 +374,8 @@ int oracle_hydro(const oracle_tree *t, const double *pos, const float *mass, con
                 /* hydro_ngbiter hydra.c:350-505 */
                 kern kj; kern_init(&kj, hsml[o], sp->KernelType);
                 if(rsq <= 0 || !(rsq < ki.HH || rsq < kj.HH)) continue;
-                const double density_j = density_pred(density[o], divvel[o], sp->drift);
-                const double eom_j = density_pred(DI ? egywtdensity[o] : density[o], divvel[o], sp->drift);
+                const double density_j = density_pred(density[o], divvel[o], f_drift(sp, o));
+                const double eom_j = density_pred(DI ? egywtdensity[o] : density[o], divvel[o], f_drift(sp, o));
                 const double P_j = press[o];
                 const double p_over_rho2_j = P_j / (eom_j * eom_j);
                 const double cs_j = sqrt(GAMMA * P_j / eom_j);
@@ -375,7 +396,8 @@ int oracle_hydro(const oracle_tree *t, const double *pos, const float *mass, con
                     if(vs > MaxSig) MaxSig = vs;
                     const double f2 = fabs(divvel[o]) / (fabs(divvel[o]) + curlvel[o] + 0.0001 * cs_j / fac_mu / hsml[o]);
                     visc = 0.25 * sp->ArtBulkViscConst * vs * (-mu_ij) / rho_ij * (F1 + f2);
-                    const double dloga = 2 * sp->dloga_bin;            /* 2*max(I->dloga, dloga_j), one bin */
+                    const double dl_i = f_dloga_bin(sp, i), dl_o = f_dloga_bin(sp, o);
+                    const double dloga = 2 * (dl_i > dl_o ? dl_i : dl_o);      /* hydra.c:463 */
                     if(dloga > 0 && (dwk_i + dwk_j) < 0) {
                         const double msum = (double) mass[i] + (double) mass[o];      /* I->Mass is MyFloat = double */
                         if(msum > 0) {

@@ -163,3 +163,35 @@ def test_gpu_sph_mixed_timebins_equal_reference(b200, engine, name):
     inact = np.setdiff1d(np.arange(n), act)
     assert np.array_equal(d["density"][inact], m("sync_density")[inact])
     assert np.array_equal(d["hsml"][inact], m("sync_hsml")[inact])
+
+
+@pytest.mark.parametrize("name", ["clustered16", "zeldovich16"])
+def test_oracle_sph_mixed_timebins_equal_reference(name):
+    """The oracle's mixed-time-bin mode against the reference's own density.c / hydra.c on the
+    mixed fixture (bins 2,3 active, 4,5 not; per-bin factors; stale state of inactive neighbours)."""
+    pos, mass, vel, ent, box, h0 = _inputs(name)
+    n = len(mass)
+    m = lambda k: MIXED[name + "/" + k]
+    tb = {k: MIXED["tables/" + k] for k in ("gravkick", "hydrokick", "drift", "dloga_pred", "dloga_bin")}
+    bins, act = m("bins"), m("active")
+    Ti = int(MIXED["Ti_Current"])
+    active_bin = np.array([b <= 0 or Ti % (1 << b) == 0 for b in range(47)])
+    tabs = dict(gravkick=tb["gravkick"][:47], hydrokick=tb["hydrokick"][:47], dloga_pred=tb["dloga_pred"][:47],
+                drift=np.where(active_bin, 0.0, tb["drift"][:47]), dloga_bin=tb["dloga_bin"][:47])
+    t = oracle.OracleTree(pos, mass, box, type=np.zeros(n, np.uint8), mask=1)
+    sp = oracle.sph_params(KernelType=2, MinGasHsml=0.006, DensityIndependentSphOn=1, atime=0.5, hubble=0.2,
+                           pmkick=float(tb["gravkick"][47]))
+    state = {k: m("sync_" + k) for k in ("density", "egywtdensity", "dhsmlfac", "divvel", "curlvel", "dthsml")}
+    oracle.sph_set_mixed(bins, bins, tabs, act, n=n)
+    try:
+        d = oracle.density(t, sp, m("sync_hsml"), vel=m("vel_new"), entropy=ent, dtentropy=m("sync_hydro_dtentropy"),
+                           fullacc=m("fullacc"), hydroacc=m("sync_hydro_acc"), DoEgyDensity=1, state=state)
+        assert d["rc"] == 0
+        h = oracle.hydro(t, sp, d, vel=m("vel_new"), entropy=ent, dtentropy=m("sync_hydro_dtentropy"),
+                         fullacc=m("fullacc"), hydroacc=m("sync_hydro_acc"))
+    finally:
+        oracle.sph_set_mixed()
+    for k in DENS_KEYS:
+        assert _close(d[k], m("mixed_" + k), 1e-12), k          # inactive particles: untouched state
+    for k in ("acc", "dtentropy", "maxsignalvel"):
+        assert _close(h[k][act], m("mixed_" + k)[act], 1e-11), k
