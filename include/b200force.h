@@ -250,6 +250,10 @@ typedef struct b200_sph_bins {
 } b200_sph_bins;
 int b200_sph_set_timebins(b200_ctx *ctx, const uint8_t *timebin_gravity, const uint8_t *timebin_hydro, const b200_sph_bins *bins);
 int b200_sph_set_active(b200_ctx *ctx, const int32_t *active, int64_t nactive);
+/* Multi-GPU: overwrite P[].Hsml of the particles [first, first+count) -- imported ghosts whose
+ * owner rank has converged them -- and recompute the tree's hmax (update_tree_hmax_father,
+ * forcetree.c:1287-1315) before b200_hydro_force. */
+int b200_sph_set_hsml_range(b200_ctx *ctx, const double *hsml, int64_t first, int64_t count);
 int b200_sph_set_state(b200_ctx *ctx, const double *density, const double *egywtdensity, const double *dhsmlfac,
                        const double *divvel, const double *curlvel);
 

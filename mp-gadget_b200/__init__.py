@@ -94,7 +94,7 @@ EXPORTED = [
     "b200_get_timings", "b200_stream",
     "b200_tree_top_get_dev", "b200_tree_top_set_dev", "b200_pmslab_init", "b200_pmslab_deposit",
     "b200_pmslab_fft2d", "b200_pmslab_fft1d", "b200_pmslab_transfer", "b200_pmslab_readout_dev",
-    "b200_sph_set_gas", "b200_sph_set_timebins", "b200_sph_set_active", "b200_sph_set_state", "b200_density", "b200_density_gradrho", "b200_hydro_force",
+    "b200_sph_set_gas", "b200_sph_set_timebins", "b200_sph_set_active", "b200_sph_set_hsml_range", "b200_sph_set_state", "b200_density", "b200_density_gradrho", "b200_hydro_force",
 ]
 
 
@@ -278,6 +278,10 @@ class Engine:
     def sph_set_active(self, active):
         a = _c(active, np.int32)
         self._ck(self.L.b200_sph_set_active(self.ctx, _p(a), C.c_int64(0 if a is None else len(a))))
+
+    def sph_set_hsml_range(self, hsml, first):
+        h = _c(hsml, np.float64)
+        self._ck(self.L.b200_sph_set_hsml_range(self.ctx, _p(h), C.c_int64(first), C.c_int64(len(h))))
 
     def sph_set_state(self, density=None, egywtdensity=None, dhsmlfac=None, divvel=None, curlvel=None):
         arr = [_c(x, np.float64) for x in (density, egywtdensity, dhsmlfac, divvel, curlvel)]

@@ -568,6 +568,13 @@ int b200_sph_set_timebins(b200_ctx *ctx, const uint8_t *timebin_gravity, const u
     ENTER(ctx);
     return sph_set_timebins(E, timebin_gravity, timebin_hydro, bins);
 }
+int b200_sph_set_hsml_range(b200_ctx *ctx, const double *hsml, int64_t first, int64_t count)
+{
+    ENTER(ctx);
+    if(int rc = sph_set_hsml_range(E, hsml, first, count)) return rc;
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
 int b200_sph_set_active(b200_ctx *ctx, const int32_t *active, int64_t nactive) { ENTER(ctx); return sph_set_active(E, active, nactive); }
 int b200_sph_set_state(b200_ctx *ctx, const double *density, const double *egywtdensity, const double *dhsmlfac,
                        const double *divvel, const double *curlvel)

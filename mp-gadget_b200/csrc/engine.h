@@ -200,6 +200,8 @@ int sph_set_gas(Engine *E, const double *vel, const double *hsml, const double *
                 const double *fullacc, const double *gravpm, const double *hydroacc);
 int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy, int *d_ninteract, int *d_niter);
 int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte, double *d_maxsig, int *d_ninteract);
+int sph_update_hmax(Engine *E);
+int sph_set_hsml_range(Engine *E, const double *hsml, int64_t first, int64_t count);
 int sph_set_timebins(Engine *E, const uint8_t *bin_grav, const uint8_t *bin_hydro, const b200_sph_bins *bins);
 int sph_set_active(Engine *E, const int32_t *active, int64_t nactive);
 int sph_set_state(Engine *E, const double *density, const double *egy, const double *dhsmlfac, const double *divvel, const double *curlvel);

@@ -825,6 +825,35 @@ int sph_set_gas(Engine *E, const double *vel, const double *hsml, const double *
     return 0;
 }
 
+// hmax of the tree from the current smoothing lengths of all its gas particles
+// (update_tree_hmax_father forcetree.c:1287-1315, force_tree_calc_moments at run.c:477)
+int sph_update_hmax(Engine *E)
+{
+    if(!E->tree_valid) return failmsg(E, "b200_sph_update_hmax: no tree");
+    const int nn = (int) E->tree_nn;
+    if(E->tree_np == 0) return 0;
+    k_sph_hmax_leaf<<<(nn + 255) / 256, 256, 0, E->stream>>>(nn, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p,
+        (const double4 *) E->spart.p, E->sidx.p, E->s_hsml.p, E->type.p, E->nodeH.p);
+    CKL(E);
+    for(int level = (int) E->tree_lvl.size() - 2; level >= 0; level--) {
+        const int first = E->tree_lvl[level], last = E->tree_lvl[level + 1];
+        k_sph_hmax_up<<<(last - first + 127) / 128, 128, 0, E->stream>>>(first, last, E->b_firstchild.p, E->b_nchild.p, E->b_dfs.p, E->nodeH.p);
+        CKL(E);
+    }
+    return 0;
+}
+
+// Overwrite the smoothing lengths of the particles [first, first + count) (imported ghosts whose
+// owner has converged them) and refresh hmax.
+int sph_set_hsml_range(Engine *E, const double *hsml, int64_t first, int64_t count)
+{
+    if(!E->s_have[1]) return failmsg(E, "b200_sph_set_hsml_range: call b200_sph_set_gas first");
+    if(first < 0 || count < 0 || first + count > E->n) return failmsg(E, "b200_sph_set_hsml_range: bad range");
+    if(count > 0) CK(cudaMemcpyAsync(E->s_hsml.p + first, hsml, count * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return sph_update_hmax(E);
+}
+
 int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy, int *d_ninteract, int *d_niter)
 {
     if(!E->tree_valid) return failmsg(E, "b200_density: build the gas tree first (b200_tree_build with the gas mask)");
@@ -832,7 +861,7 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
     SphDev S;
     if(int rc = make_dev(E, p, S)) return rc;
     const size_t n = (size_t) (E->n > 0 ? E->n : 1);
-    const int np = (int) E->tree_np, nn = (int) E->tree_nn;
+    const int np = (int) E->tree_np;
     CK(E->s_velpred.ensure(3 * n)); CK(E->s_evp.ensure(n));
     CK(E->s_density.ensure(n)); CK(E->s_egy.ensure(n)); CK(E->s_dhsmlfac.ensure(n)); CK(E->s_divvel.ensure(n));
     CK(E->s_curlvel.ensure(n)); CK(E->s_dthsml.ensure(n)); CK(E->s_numngb.ensure(n)); CK(E->s_gradrho.ensure(3 * n));
@@ -909,15 +938,7 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
         E->walk_chunks_per_warp = keep_estimate;
         if(d_ninteract) CK(cudaMemcpyAsync(d_ninteract, E->s_nint.p, (size_t) E->n * sizeof(int), cudaMemcpyDeviceToDevice, E->stream));
         if(d_niter) CK(cudaMemcpyAsync(d_niter, E->s_niter.p, (size_t) E->n * sizeof(int), cudaMemcpyDeviceToDevice, E->stream));
-        // hmax of the tree from the converged smoothing lengths (run.c:477 force_tree_calc_moments)
-        k_sph_hmax_leaf<<<(nn + 255) / 256, 256, 0, E->stream>>>(nn, (const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p,
-            (const double4 *) E->spart.p, E->sidx.p, E->s_hsml.p, E->type.p, E->nodeH.p);
-        CKL(E);
-        for(int level = (int) E->tree_lvl.size() - 2; level >= 0; level--) {
-            const int first = E->tree_lvl[level], last = E->tree_lvl[level + 1];
-            k_sph_hmax_up<<<(last - first + 127) / 128, 128, 0, E->stream>>>(first, last, E->b_firstchild.p, E->b_nchild.p, E->b_dfs.p, E->nodeH.p);
-            CKL(E);
-        }
+        if(int rc = sph_update_hmax(E)) return rc;
     }
     timer_stop(E, T_SPH_DENSITY);
     int herr = 0;

@@ -299,3 +299,87 @@ class ShardedTreePM:
         gpm = self.pm_force()
         acc, pot = self.tree_force(par)
         return gpm, acc, pot
+
+
+class ShardedSPH:
+    """SPH density + hydro force on a domain-sharded gas distribution ("SPH hydro is
+    symmetric => halo width max(h) via hmax").  Same domain cut and ghost import as ShardedTreePM:
+
+      1. every rank imports the gas of the cell layer adjacent to its domain from both neighbours
+         (positions, masses and everything the velocity / entropy predictors read), builds the gas
+         tree over own + ghost particles and runs the density pass for its OWN particles only
+         (b200_sph_set_active): density is a gather over r < h_i, so it needs no neighbour
+         smoothing length and is exact as long as the ghost layer is wider than h_i;
+      2. the owners send the converged Hsml, Density, EgyWtDensity, DhsmlEgyDensityFactor, DivVel and
+         CurlVel of exactly those particles back along the same route (the reference gets them through
+         its result exchange, treewalk.c:560-793); the tree's hmax is refreshed;
+      3. the symmetric hydro pass runs for the own particles with the ghosts as sources.
+
+    A pair (i, j) interacts when r < max(h_i, h_j), so the ghost layer must be wider than the largest
+    smoothing length anywhere: checked after the density pass (all-reduce of max h), ValueError otherwise.
+    """
+
+    GHOST_COLS = 3 + 1 + 3 + 1 + 1 + 1 + 3 + 3 + 3      # pos, mass, vel, hsml, entropy, dtentropy, fullacc, gravpm, hydroacc
+    STATE_KEYS = ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel")
+
+    def __init__(self, engine, box, topdepth, dist=None, device="cuda"):
+        self.e = engine
+        self.comm = Comm(dist)
+        self.rank, self.world = self.comm.rank, self.comm.world
+        self.box = float(box)
+        self.dom = Domain(box, topdepth, self.rank, self.world)
+        self.device = torch.device(device)
+
+    def load(self, pos, mass, hsml, vel=None, entropy=None, dtentropy=None, fullacc=None, gravpm=None, hydroacc=None):
+        """Own gas particles (device tensors, every x inside the rank's layers)."""
+        n = pos.shape[0]
+        z3 = lambda a: torch.zeros((n, 3), dtype=torch.float64, device=self.device) if a is None else a
+        one = torch.ones(n, dtype=torch.float64, device=self.device)
+        cols = [pos, mass.to(torch.float64)[:, None], z3(vel), hsml[:, None], (one if entropy is None else entropy)[:, None],
+                (0 * one if dtentropy is None else dtentropy)[:, None], z3(fullacc), z3(gravpm), z3(hydroacc)]
+        own = torch.cat(cols, dim=1).contiguous()
+        self.to_l, self.to_r = self.dom.ghost_sets(pos[:, 0])
+        fr, fl = self.comm.neighbour_exchange_var(own[self.to_l], own[self.to_r])
+        self.n_from_left, self.n_from_right = fl.shape[0], fr.shape[0]
+        allp = torch.cat([own, fl, fr], dim=0)
+        self.n_own, self.n_tot = n, allp.shape[0]
+        a = allp.cpu().numpy()
+        self.host = dict(pos=np.ascontiguousarray(a[:, 0:3]), mass=np.ascontiguousarray(a[:, 3]).astype(np.float32),
+                         vel=np.ascontiguousarray(a[:, 4:7]), hsml=np.ascontiguousarray(a[:, 7]), entropy=np.ascontiguousarray(a[:, 8]),
+                         dtentropy=np.ascontiguousarray(a[:, 9]), fullacc=np.ascontiguousarray(a[:, 10:13]),
+                         gravpm=np.ascontiguousarray(a[:, 13:16]), hydroacc=np.ascontiguousarray(a[:, 16:19]))
+        h = self.host
+        self.e.set_particles(h["pos"], h["mass"], type=np.zeros(self.n_tot, np.uint8))
+        self.e.force_tree_build(self.box, mask=1)
+        self.e.sph_set_gas(h["hsml"], vel=h["vel"], entropy=h["entropy"], dtentropy=h["dtentropy"], fullacc=h["fullacc"],
+                           gravpm=h["gravpm"], hydroacc=h["hydroacc"])
+        self.e.sph_set_active(np.arange(n, dtype=np.int32))
+        return self.n_tot - n
+
+    def density(self, sp, DoEgyDensity=0):
+        d = self.e.density(sp, update_hsml=1, DoEgyDensity=DoEgyDensity)
+        n = self.n_own
+        # converged state of the particles I exported, back to the ranks that hold them as ghosts
+        st = torch.from_numpy(np.stack([d[k][:n] for k in self.STATE_KEYS], axis=1)).to(self.device)
+        fr, fl = self.comm.neighbour_exchange_var(st[self.to_l].contiguous(), st[self.to_r].contiguous())
+        assert fl.shape[0] == self.n_from_left and fr.shape[0] == self.n_from_right
+        g = torch.cat([fl, fr], dim=0).cpu().numpy()
+        full = {k: d[k].copy() for k in self.STATE_KEYS}
+        for c, k in enumerate(self.STATE_KEYS):
+            full[k][n:] = g[:, c]
+        hmax = torch.tensor([float(full["hsml"][:n].max()) if n else 0.0], dtype=torch.float64, device=self.device)
+        if self.world > 1:
+            self.comm.dist.all_reduce(hmax, op=self.comm.dist.ReduceOp.MAX)
+        if self.world > 1 and not self.dom.cellwidth > float(hmax.item()):
+            raise ValueError("top-tree cells (%.4g) must be wider than the largest smoothing length (%.4g): lower topdepth"
+                             % (self.dom.cellwidth, float(hmax.item())))
+        self.e.sph_set_state(density=full["density"], egywtdensity=full["egywtdensity"], dhsmlfac=full["dhsmlfac"],
+                             divvel=full["divvel"], curlvel=full["curlvel"])
+        if self.n_tot > n:
+            self.e.sph_set_hsml_range(full["hsml"][n:], n)
+        self.state = full
+        return {k: v[:n] for k, v in d.items() if hasattr(v, "__len__") and len(v) == self.n_tot}
+
+    def hydro_force(self, sp):
+        h = self.e.hydro_force(sp)
+        return {k: v[:self.n_own] for k, v in h.items()}

@@ -183,3 +183,99 @@ def test_sharded_two_gpus_equal_one(b200, ics, tmp_path):
         assert np.abs(d["a"] - a0[idx]).max() <= 1e-11 * np.sqrt((a0 ** 2).sum(1)).mean()
         assert np.abs(d["p"] - p0[idx]).max() <= 1e-11 * np.abs(p0).max()
     assert seen.all()
+
+
+def _gas_setup(ics, ng=24, seed=5):
+    pos, mass = ics.zeldovich_lattice(ng, float(ng), seed=seed, rms=0.3)
+    rng = np.random.default_rng(2)
+    n = len(mass)
+    return dict(pos=pos, mass=mass, box=float(ng), vel=rng.standard_normal((n, 3)) * 0.1, entropy=1 + 0.5 * rng.random(n),
+                h0=np.full(n, 1.3))
+
+
+def _sph_par(b200):
+    return b200.sph_params(KernelType=1, DensityIndependentSphOn=1, MinGasHsml=1e-4, atime=0.5, hubble=0.2, dloga_bin=0.01)
+
+
+def _sph_single(b200, gas):
+    e = b200.Engine(0)
+    n = len(gas["mass"])
+    e.set_particles(gas["pos"], gas["mass"], type=np.zeros(n, np.uint8))
+    e.force_tree_build(gas["box"], mask=1)
+    e.sph_set_gas(gas["h0"], vel=gas["vel"], entropy=gas["entropy"])
+    sp = _sph_par(b200)
+    d = e.density(sp, update_hsml=1, DoEgyDensity=1)
+    h = e.hydro_force(sp)
+    e.close()
+    return d, h
+
+
+@pytest.mark.gpu
+def test_sharded_sph_world1_equals_unsharded(b200, ics):
+    """ShardedSPH with one rank (no ghosts, active set = all) reproduces the plain engine calls."""
+    sh = importlib.import_module("mp-gadget_b200.sharded")
+    gas = _gas_setup(ics)
+    d0, h0 = _sph_single(b200, gas)
+    e = b200.Engine(0)
+    s = sh.ShardedSPH(e, gas["box"], topdepth=2, dist=None)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    s.load(t(gas["pos"]), t(gas["mass"]), t(gas["h0"]), vel=t(gas["vel"]), entropy=t(gas["entropy"]))
+    sp = _sph_par(b200)
+    d1 = s.density(sp, DoEgyDensity=1)
+    h1 = s.hydro_force(sp)
+    e.close()
+    for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel"):
+        assert np.array_equal(d1[k], d0[k]), k
+    for k in ("acc", "dtentropy", "maxsignalvel"):
+        assert np.array_equal(h1[k], h0[k]), k
+
+
+SPH_GPU_WORKER = r'''
+import os, sys, importlib
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+pkg = importlib.import_module("mp-gadget_b200"); ics = importlib.import_module("mp-gadget_b200.ics")
+sh = importlib.import_module("mp-gadget_b200.sharded")
+local = int(os.environ["LOCAL_RANK"]); torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+ng = 24
+pos, mass = ics.zeldovich_lattice(ng, float(ng), seed=5, rms=0.3)
+rng = np.random.default_rng(2); n = len(mass)
+vel = rng.standard_normal((n, 3)) * 0.1; ent = 1 + 0.5 * rng.random(n); h0 = np.full(n, 1.3)
+e = pkg.Engine(local)
+s = sh.ShardedSPH(e, float(ng), topdepth=2, dist=dist, device="cuda:%%d" %% local)
+t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+sel = (s.dom.owner_of(t(pos)[:, 0]) == rank).cpu().numpy()
+nghost = s.load(t(pos[sel]), t(mass[sel]), t(h0[sel]), vel=t(vel[sel]), entropy=t(ent[sel]))
+sp = pkg.sph_params(KernelType=1, DensityIndependentSphOn=1, MinGasHsml=1e-4, atime=0.5, hubble=0.2, dloga_bin=0.01)
+d = s.density(sp, DoEgyDensity=1)
+h = s.hydro_force(sp)
+np.savez(os.path.join(%(out)r, "sph_%%d.npz" %% rank), idx=np.nonzero(sel)[0], nghost=nghost,
+         **{"d_" + k: d[k] for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel")},
+         **{"h_" + k: h[k] for k in ("acc", "dtentropy", "maxsignalvel")})
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_sharded_sph_two_gpus_equal_one(b200, ics, tmp_path):
+    """Density + hydro on 2 GPUs (ghost import, converged ghost state sent back, hmax refresh) equal
+    the single-GPU result for every particle."""
+    gas = _gas_setup(ics)
+    d0, h0 = _sph_single(b200, gas)
+    r = _torchrun(SPH_GPU_WORKER % {"root": ROOT, "out": str(tmp_path)}, 2)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    seen = np.zeros(len(gas["mass"]), bool)
+    close = lambda a, b, tol: np.abs(a - b).max() <= tol * (np.abs(b).max() + 1e-300)
+    for rank in range(2):
+        z = np.load(os.path.join(str(tmp_path), "sph_%d.npz" % rank))
+        idx = z["idx"]
+        assert not seen[idx].any() and int(z["nghost"]) > 0
+        seen[idx] = True
+        for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel"):
+            assert close(z["d_" + k], d0[k][idx], 1e-11), k
+        for k in ("acc", "dtentropy", "maxsignalvel"):
+            assert close(z["h_" + k], h0[k][idx], 1e-10), k
+    assert seen.all()
