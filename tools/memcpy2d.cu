@@ -1,6 +1,6 @@
 // Microbenchmark: strided (2-D) DMA copies and zero-copy kernel access between a pinned
 // 160-byte AoS on the host and device SoA, to choose the e2e ingest/write-back path.
-// nvcc -O3 -gencode arch=compute_100a,code=sm_100a scripts_memcpy2d.cu -o /tmp/m2d && /tmp/m2d
+// nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/memcpy2d.cu -o /tmp/m2d && /tmp/m2d
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdint.h>
