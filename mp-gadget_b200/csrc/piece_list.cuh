@@ -60,8 +60,8 @@ __device__ __forceinline__ void piece_push(bool want, unsigned entry, int &mycnt
             want = false;
         }
     }
-    const int needch = (int) __reduce_max_sync(0xffffffffu, want ? (unsigned) (mycnt >> CH_SHIFT) : 0u);
-    if(needch >= nch_alloc) {               // warp-uniform; once per CH_SLOTS pieces of the longest list
+    if(__any_sync(0xffffffffu, want && (mycnt >> CH_SHIFT) >= nch_alloc)) {   // once per CH_SLOTS pieces of the longest list
+        const int needch = (int) __reduce_max_sync(0xffffffffu, want ? (unsigned) (mycnt >> CH_SHIFT) : 0u);
         if(needch >= Q.maxch) { if(lane == 0) atomicOr(Q.ctl + 1, 2); }
         else {
             if(lane == 0)

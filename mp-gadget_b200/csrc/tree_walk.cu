@@ -135,10 +135,20 @@ __device__ __forceinline__ void monopole(double dx, double dy, double dz, double
 // reach from all box faces: then NEAREST cannot change any decision (a node
 // whose wrapped and unwrapped distances differ is discarded either way) nor any
 // accepted distance, so the selects are skipped.
+// {rcut + len/2, len^2, (mass*len)*len, 0.6*len} (gravshort-tree.c:204,226,231,236)
+__device__ __forceinline__ double4 node_consts(const double4 &A, const double4 &B, const WalkPar &P)
+{
+    const double len = B.w;
+    return make_double4(__dadd_rn(P.rcut, __dmul_rn(0.5, len)), __dmul_rn(len, len), __dmul_rn(__dmul_rn(A.w, len), len),
+                        __dmul_rn(0.6, len));
+}
+
 template <bool WRAP>
-__device__ __forceinline__ int classify(const double4 &A, const double4 &B, double px, double py, double pz,
+__device__ __forceinline__ int classify(const double4 &A, const double4 &B, const double4 &D, double px, double py, double pz,
                                         double aold, const WalkPar &P, double &dx, double &dy, double &dz, double &r2)
 {
+    // D = node_consts(A, B): the per-node products of the criteria, formed once by the lane that
+    // fetched the node instead of by every lane (same un-fused operations, same values)
     // Straight-line (two of these are interleaved by the caller); the same comparisons in the
     // same arithmetic as the early-exit form of the reference.
     dx = A.x - px; dy = A.y - py; dz = A.z - pz;
@@ -149,16 +159,13 @@ __device__ __forceinline__ int classify(const double4 &A, const double4 &B, doub
     }
     cxd = fabs(cxd); cyd = fabs(cyd); czd = fabs(czd);
     r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    const double len = B.w;
-    const double eff = __dadd_rn(P.rcut, __dmul_rn(0.5, len));
+    const double eff = D.x, l2 = D.y, inside = D.w;
     const bool disc = (r2 > P.rcut2) & ((cxd > eff) | (cyd > eff) | (czd > eff));          // shall_we_discard_node
-    const double l2 = __dmul_rn(len, len);
-    const bool orel = (P.usebh == 0) & (__dmul_rn(__dmul_rn(A.w, len), len) > __dmul_rn(__dmul_rn(r2, r2), aold));
+    const bool orel = (P.usebh == 0) & (D.z > __dmul_rn(__dmul_rn(r2, r2), aold));
     // len*len/r2 > theta2, evaluated without the division unless within rounding of the threshold
     const double rhs = __dmul_rn(P.theta2, r2);
     const bool obh = l2 > rhs * (1.0 + 1e-14);
     const bool nearbh = (!obh) & (l2 >= rhs * (1.0 - 1e-14));
-    const double inside = __dmul_rn(0.6, len);
     const bool oin = (cxd < inside) & (cyd < inside) & (czd < inside);
     bool open = orel | obh | oin;
     if(nearbh & !open & !disc) open = __ddiv_rn(l2, r2) > P.theta2;                          // practically never
@@ -278,6 +285,7 @@ __device__ __forceinline__ void pair_sum(const PieceList &L, int g, int slot,
 struct BatchEntry {
     double4 A[32];    // cofm, mass
     double4 B[32];    // center, len
+    double4 D[32];    // node_consts
     int4 M[32];       // pstart, count, mask of lanes (targets) that opened every ancestor,
                       // flags (bit0: leaf, bit1: rejected for all lanes by the bounding-box test)
 };
@@ -375,7 +383,11 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
                 ex = nearest(ex, P.box, P.halfbox); ey = nearest(ey, P.box, P.halfbox); ez = nearest(ez, P.box, P.halfbox);
             }
             if(fabs(ex) - bhx > lim || fabs(ey) - bhy > lim || fabs(ez) - bhz > lim) eflags0 |= 2;
-            else s_ent.A[lane] = nodeA[mynode];
+            else {
+                const double4 eA = nodeA[mynode];
+                s_ent.A[lane] = eA;
+                s_ent.D[lane] = node_consts(eA, eB, P);
+            }
             s_ent.B[lane] = eB;
             s_ent.M[lane] = make_int4(C.y, C.z, (int) emask0, eflags0);
         }
@@ -399,14 +411,15 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             const int4 MA = s_ent.M[kA], MB = s_ent.M[kB];
             const bool awakeA = (((unsigned) MA.z) >> lane) & 1u, awakeB = haveB && ((((unsigned) MB.z) >> lane) & 1u);
             const double4 AA = s_ent.A[kA], BA = s_ent.B[kA], AB = s_ent.A[kB], BB = s_ent.B[kB];
+            const double4 DA = s_ent.D[kA], DB = s_ent.D[kB];
             int decA = 0, decB = 0;
             double dxA = 0, dyA = 0, dzA = 0, r2A = 0, dxB = 0, dyB = 0, dzB = 0, r2B = 0;
             if(warp_central) {
-                decA = classify<false>(AA, BA, px, py, pz, aold, P, dxA, dyA, dzA, r2A);
-                decB = classify<false>(AB, BB, px, py, pz, aold, P, dxB, dyB, dzB, r2B);
+                decA = classify<false>(AA, BA, DA, px, py, pz, aold, P, dxA, dyA, dzA, r2A);
+                decB = classify<false>(AB, BB, DB, px, py, pz, aold, P, dxB, dyB, dzB, r2B);
             } else {
-                decA = classify<true>(AA, BA, px, py, pz, aold, P, dxA, dyA, dzA, r2A);
-                decB = classify<true>(AB, BB, px, py, pz, aold, P, dxB, dyB, dzB, r2B);
+                decA = classify<true>(AA, BA, DA, px, py, pz, aold, P, dxA, dyA, dzA, r2A);
+                decB = classify<true>(AB, BB, DB, px, py, pz, aold, P, dxB, dyB, dzB, r2B);
             }
             decA = awakeA ? decA : -1; decB = awakeB ? decB : -1;
             const unsigned openA = __ballot_sync(0xffffffffu, decA == 2), openB = __ballot_sync(0xffffffffu, decB == 2);

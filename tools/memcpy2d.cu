@@ -75,6 +75,31 @@ int main()
         printf("zero-copy write 56 B/rec: %.2f ms  payload %.1f GB/s\n", ms, n * 56.0 / ms * 1e-6);
         CK(cudaGetLastError());
     }
+    // several strided copies at once on different streams (do the copy engines share the work?)
+    {
+        cudaStream_t st[4];
+        for(int q = 0; q < 4; q++) CK(cudaStreamCreateWithFlags(&st[q], cudaStreamNonBlocking));
+        for(int nsplit = 1; nsplit <= 4; nsplit *= 2) {
+            for(int dir = 0; dir < 2; dir++) {
+                CK(cudaDeviceSynchronize());
+                cudaEventRecord(e0, st[0]);
+                // two fields (40 B at 0, 48 B at 64), each split into nsplit row ranges -> 2*nsplit copies on up to 4 streams
+                int k = 0;
+                for(int f = 0; f < 2; f++) {
+                    const int w = f ? 48 : 40, off = f ? 64 : 0;
+                    for(int q = 0; q < nsplit; q++, k++) {
+                        const int64_t a = n / nsplit * q, cnt = n / nsplit;
+                        cudaStream_t s2 = st[k % 4];
+                        if(dir == 0) CK(cudaMemcpy2DAsync(soa + (size_t) f * n * 48 + a * w, w, h + a * 160 + off, 160, w, cnt, cudaMemcpyHostToDevice, s2));
+                        else CK(cudaMemcpy2DAsync(h + a * 160 + off, 160, soa + (size_t) f * n * 48 + a * w, w, w, cnt, cudaMemcpyDeviceToHost, s2));
+                    }
+                }
+                for(int q = 1; q < 4; q++) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, st[q]); cudaStreamWaitEvent(st[0], ev, 0); }
+                cudaEventRecord(e1, st[0]); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+                printf("%s 88 B/rec as %d strided copies on %d streams: %.2f ms  payload %.1f GB/s\n", dir ? "D2H" : "H2D", 2 * nsplit, 2 * nsplit < 4 ? 2 * nsplit : 4, ms, n * 88.0 / ms * 1e-6);
+            }
+        }
+    }
     // bidirectional overlap: bulk H2D and D2H on two streams
     cudaStream_t s2; CK(cudaStreamCreate(&s2));
     uint8_t *h2; CK(cudaMallocHost(&h2, n * 160));
