@@ -38,7 +38,7 @@ UNIT = "particles/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/r01_*_ncu_summary.txt), 256^3 workload
-NCU_TRAFFIC = {"k_grav_pairs": 6.84e9, "k_grav_walk": 6.22e9}
+NCU_TRAFFIC = {"k_grav_pairs": 6.85e9, "k_grav_walk": 6.26e9}
 
 
 def peaks():
