@@ -10,9 +10,13 @@
  *   - tree + short-range walk: PINNED against the reference's own C compiled
  *     from /root/reference (oracle/_ref, tests/test_oracle_vs_ref.py) and
  *     against committed outputs of it (tests/golden/);
- *   - PM: "parity unpinned" at the mesh level (the reference holds no golden
- *     PM value and PFFT is not buildable offline); pinned only through the
- *     reference's own TreePM-vs-direct-sum bounds (tests/test_gravity.c:146-160).
+ *   - SPH density / hydro (synchronised and mixed time bins): PINNED against the
+ *     reference's own density.c / hydra.c (tests/golden/ref_sph*.npz);
+ *   - PM: PINNED against the reference's own petapm.c / gravpm.c / powerspectrum.c
+ *     run on one rank (oracle/_ref/libref_pm.so, tests/golden/ref_pm.npz).  PFFT,
+ *     the one third-party piece (fetched at build time, absent offline), is
+ *     replaced there by plain DFTs in its single-rank layout
+ *     (oracle/pfft_standin.c); every other line that runs is the reference's.
  */
 #ifndef ORACLE_H
 #define ORACLE_H

@@ -16,6 +16,8 @@ SO_DROPIN = os.path.join(_HERE, "_ref", "libref_dropin.so")
 SO_DROPIN_SPH = os.path.join(_HERE, "_ref", "libref_dropin_sph.so")
 # forcetree.c, gravshort-tree.c, density.c, hydra.c all replaced: no host octree at all
 SO_DROPIN_ALL = os.path.join(_HERE, "_ref", "libref_dropin_all.so")
+# the reference's own petapm.c + gravpm.c + powerspectrum.c with the single-rank PFFT stand-in
+SO_PM = os.path.join(_HERE, "_ref", "libref_pm.so")
 _inst = None
 
 
@@ -110,6 +112,16 @@ class Ref:
                              _p(out["hsml"]), _p(out["density"]), _p(out["egywtdensity"]), _p(out["dhsmlfac"]), _p(out["divvel"]),
                              _p(out["curlvel"]), _p(out["dthsml"]), _p(out["acc"]), _p(out["dtentropy"]), _p(out["maxsignalvel"]))
         return act[:na.value].copy(), out
+
+    def gravpm_force(self, pos, mass, box, nmesh, asmth, G, outdir, time=1.0):
+        """gravpm_init_periodic + gravpm_force of the reference (needs so=SO_PM).  Returns
+        (GravPM[n,3], Potential[n]); the reference writes outdir/powerspectrum-<time>.txt."""
+        pos = np.ascontiguousarray(pos, np.float64); mass = np.ascontiguousarray(mass, np.float32)
+        n = len(mass)
+        g = np.zeros((n, 3)); p = np.zeros(n)
+        self.L.ref_gravpm_force(C.c_int64(n), _p(pos), _p(mass), C.c_double(box), C.c_int(nmesh), C.c_double(asmth), C.c_double(G),
+                                C.c_char_p(outdir.encode()), C.c_double(time), _p(g), _p(p))
+        return g, p
 
     def timings(self):
         b, w = C.c_double(), C.c_double()

@@ -420,4 +420,52 @@ int ref_sph_mixed(const unsigned char *bins, int64_t Ti_Current, const double *t
 
 void ref_sph_timings(double *dens_s, double *hydro_s) { *dens_s = t_density; *hydro_s = t_hydro; }
 
+#ifdef REF_WITH_PM
+/* ---- PM: the reference's own petapm.c + gravpm.c + powerspectrum.c on one rank, with the PFFT
+ * stand-in of oracle/pfft_standin.c (plain DFTs in PFFT's layout).  Stand-ins for the entry points
+ * of files that need GSL (cosmology.c, neutrinos_lra.c, omega_nu_single.c); none of them influences
+ * the forces with MassiveNuLinRespOn = HybridNeutrinosOn = 0. */
+#include <libgadget/powerspectrum.h>
+#include <libgadget/neutrinos_lra.h>
+double GrowthFactor(Cosmology *CP, double astart, double aend) { return 1.0; }       /* only scales a column of the P(k) file */
+int hybrid_nu_tracer(const Cosmology *CP, double atime) { return 0; }
+double get_omega_nu_nopart(const _omega_nu *const omnu, const double a) { return 0; }
+void delta_nu_from_power(struct _powerspectrum *PowerSpectrum, Cosmology *CP, const double Time, const double TimeIC) { endrun(1, "ref_driver: neutrino branch\n"); }
+void powerspectrum_nu_save(struct _powerspectrum *PowerSpectrum, const char *OutputDir, const char *filename, const double Time) {}
+
+/* gravpm_init_periodic + gravpm_force (gravpm.c:51-119) as run.c:330,522 call them: fills P[],
+ * builds the domain, runs the reference PM (region selection from its own tree, CIC, transfer
+ * functions, readout) and returns P[i].GravPM, P[i].Potential.  The power spectrum is written by
+ * the reference itself to outdir/powerspectrum-<Time>.txt. */
+int ref_gravpm_force(int64_t n, const double *pos, const float *mass, double BoxSize, int Nmesh, double Asmth, double G,
+                     const char *outdir, double Time, double *gravpm_out, double *pot_out)
+{
+    free_all();
+    particle_alloc_memory(PartManager, BoxSize, n);
+    have_particles = 1;
+    PartManager->NumPart = n;
+    build_uniform_domain(&dd, 0);
+    for(int64_t i = 0; i < n; i++) {
+        memset(&P[i], 0, sizeof(P[i]));
+        for(int k = 0; k < 3; k++) P[i].Pos[k] = pos[3 * i + k];
+        P[i].Mass = mass[i]; P[i].Type = 1; P[i].ID = i; P[i].TopLeaf = 0;
+    }
+    static PetaPM pm;
+    static int pm_module_ready = 0;
+    if(!pm_module_ready) { petapm_module_init(omp_get_max_threads()); pm_module_ready = 1; }     /* run.c / main.c start-up */
+    memset(&pm, 0, sizeof(pm));
+    Cosmology CP;
+    memset(&CP, 0, sizeof(CP));
+    CP.Omega0 = 0.3;
+    gravpm_init_periodic(&pm, BoxSize, Asmth, Nmesh, G);
+    gravpm_force(&pm, &dd, &CP, Time, 3.085678e21, outdir, 0.01);
+    for(int64_t i = 0; i < n; i++) {
+        for(int k = 0; k < 3; k++) gravpm_out[3 * i + k] = P[i].GravPM[k];
+        pot_out[i] = P[i].Potential;
+    }
+    petapm_destroy(&pm);
+    return 0;
+}
+#endif
+
 void ref_shutdown(void) { free_all(); }
