@@ -18,6 +18,8 @@ SO_DROPIN_SPH = os.path.join(_HERE, "_ref", "libref_dropin_sph.so")
 SO_DROPIN_ALL = os.path.join(_HERE, "_ref", "libref_dropin_all.so")
 # the reference's own petapm.c + gravpm.c + powerspectrum.c with the single-rank PFFT stand-in
 SO_PM = os.path.join(_HERE, "_ref", "libref_pm.so")
+# gravpm.c + petapm.c replaced by the shim (gravpm_force on the GPU, P(k) through the reference's powerspectrum.c)
+SO_DROPIN_PM = os.path.join(_HERE, "_ref", "libref_dropin_pm.so")
 _inst = None
 
 

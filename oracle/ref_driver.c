@@ -451,8 +451,10 @@ int ref_gravpm_force(int64_t n, const double *pos, const float *mass, double Box
         P[i].Mass = mass[i]; P[i].Type = 1; P[i].ID = i; P[i].TopLeaf = 0;
     }
     static PetaPM pm;
+#ifndef REF_PM_SHIM        /* with the gravpm shim (libref_dropin_pm.so) petapm.c is not linked at all */
     static int pm_module_ready = 0;
     if(!pm_module_ready) { petapm_module_init(omp_get_max_threads()); pm_module_ready = 1; }     /* run.c / main.c start-up */
+#endif
     memset(&pm, 0, sizeof(pm));
     Cosmology CP;
     memset(&CP, 0, sizeof(CP));
@@ -463,7 +465,9 @@ int ref_gravpm_force(int64_t n, const double *pos, const float *mass, double Box
         for(int k = 0; k < 3; k++) gravpm_out[3 * i + k] = P[i].GravPM[k];
         pot_out[i] = P[i].Potential;
     }
+#ifndef REF_PM_SHIM
     petapm_destroy(&pm);
+#endif
     return 0;
 }
 #endif

@@ -129,3 +129,24 @@ def test_reference_driver_mixed_timebin_step_through_shims():
         assert close(out[k], m("mixed_" + k), 1e-11), k          # active: new values; inactive: untouched state
     for k in ("acc", "dtentropy", "maxsignalvel"):
         assert close(out[k], m("mixed_" + k), 1e-10), k
+
+
+GOLD_PM = np.load(os.path.join(HERE, "golden", "ref_pm.npz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(R.SO_DROPIN_PM), reason="oracle/_ref/libref_dropin_pm.so not built")
+@pytest.mark.parametrize("name", ["zeldovich16_n32", "clustered16_n48"])
+def test_reference_driver_calls_gpu_gravpm_force(name, tmp_path):
+    """gravpm_init_periodic + gravpm_force with the reference signatures (run.c:330,522), provided by the
+    shim and run on the GPU: P[i].GravPM / P[i].Potential equal the reference's own PM (golden), and the
+    power-spectrum file the reference's powerspectrum_save writes from the GPU sums equals its own."""
+    g = lambda k: GOLD_PM[name + "/" + k]
+    r = R.Ref(arena_gib=2.0, nthreads=2, so=R.SO_DROPIN_PM)
+    gp, pot = r.gravpm_force(g("pos"), g("mass"), float(g("box")), int(g("nmesh")), float(g("asmth")), 43.0071, str(tmp_path))
+    assert np.abs(gp - g("gravpm")).max() <= 1e-9 * np.abs(g("gravpm")).max()
+    assert np.abs(pot - g("potential")).max() <= 1e-10 * np.abs(g("potential")).max()
+    ps = np.loadtxt(os.path.join(str(tmp_path), "powerspectrum-1.0000.txt"))
+    assert np.array_equal(ps[:, 2].astype(np.int64), g("ps_N"))
+    assert np.all(np.abs(ps[:, 1] - g("ps_P")) <= 2e-5 * np.abs(g("ps_P")))
+    assert np.all(np.abs(ps[:, 0] - g("ps_k")) <= 2e-5 * np.abs(g("ps_k")))
