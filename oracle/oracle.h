@@ -8,7 +8,7 @@
  * Every function cites the reference file:line whose arithmetic it restates
  * (paths relative to the MP-Gadget tree).  Parity status:
  *   - tree + short-range walk: PINNED against the reference's own C compiled
- *     from /root/reference (oracle/_ref, tests/test_oracle_vs_ref.py) and
+ *     from /root/reference (oracle/_ref, tests/test_golden.py) and
  *     against committed outputs of it (tests/golden/);
  *   - SPH density / hydro (synchronised and mixed time bins): PINNED against the
  *     reference's own density.c / hydra.c (tests/golden/ref_sph*.npz);
