@@ -43,7 +43,7 @@ COUNTS_DTYPE = np.dtype([("nodes_accepted", "i4"), ("nodes_opened", "i4"),
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_tree.c", "oracle_pm.c", "oracle_sph.c", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_tree.c", "oracle_pm.c", "oracle_sph.c", "oracle_step.c", "oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so

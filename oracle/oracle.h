@@ -124,6 +124,58 @@ int oracle_hydro(const oracle_tree *t, const double *pos, const float *mass, con
                  const double *divvel, const double *curlvel,
                  double *acc_out, double *dtentropy_out, double *maxsignalvel_out, int32_t *ninteract);
 
+/* ---- step loop (oracle_step.c): integer timeline, drift, active lists, kicks, hierarchical gravity ---- */
+#define ORACLE_TIMEBINS 46       /* timebinmgr.h:13 */
+typedef struct oracle_timeline { int64_t nsync; const double *loga; } oracle_timeline;     /* SyncPoints[].loga, timebinmgr.c:18 */
+typedef struct oracle_cosmo { double Omega0, OmegaBaryon, Hubble, G; } oracle_cosmo;        /* flat matter + Lambda */
+typedef struct oracle_times {                                                               /* DriftKickTimes timestep.h:10-26 */
+    int32_t mintimebin, maxtimebin, mingravtimebin, pad_;
+    int64_t Ti_kick[ORACLE_TIMEBINS + 1], Ti_lastactivedrift[ORACLE_TIMEBINS + 1];
+    int64_t Ti_Current, PM_length, PM_start, PM_kick;
+} oracle_times;
+typedef struct oracle_step_params {                                                         /* TimestepParams timestep.c:21-47 */
+    double ErrTolIntAccuracy, MaxGasVel, MaxSizeTimestep, MinSizeTimestep, MaxRMSDisplacementFac;
+    double softening;                                                                       /* FORCE_SOFTENING() */
+} oracle_step_params;
+double oracle_loga_from_ti(const oracle_timeline *tl, int64_t ti);
+int64_t oracle_ti_from_loga(const oracle_timeline *tl, double loga);
+int64_t oracle_dti_from_dloga(const oracle_timeline *tl, double dloga, int64_t Ti_Current);
+double oracle_dloga_from_dti(const oracle_timeline *tl, int64_t dti, int64_t Ti_Current);
+int oracle_is_timebin_active(int bin, int64_t ti);
+double oracle_step_factor(const oracle_cosmo *c, const oracle_timeline *tl, int kind, int64_t t0, int64_t t1);
+int64_t oracle_drift(int64_t n, double *pos, const double *vel, const uint8_t *type, const uint8_t *flags,
+                     double *hsml, const double *dthsml, double ddrift, const double *shift, double BoxSize);
+int64_t oracle_build_active(int64_t n, const uint8_t *type, const uint8_t *flags, const uint8_t *bin_grav, const uint8_t *bin_hydro,
+                            int64_t Ti_Current, int is_pm, int64_t nhydro_slots, int32_t *list_out, int64_t *counts, int64_t *bincounts);
+int64_t oracle_active_sublist(const int32_t *list, int64_t nlist, const uint8_t *flags, const uint8_t *bin_grav,
+                              int maxtimebin, int64_t Ti_Current, int32_t *out);
+void oracle_half_kick(const int32_t *list, int64_t nlist, const uint8_t *type, const uint8_t *flags, const uint8_t *bin_grav,
+                      const uint8_t *bin_hydro, double *vel, const double *fullacc, const double *hydroacc, double *entropy,
+                      const double *dtentropy, const double *gravkick, const double *hydrokick, const double *dt_entr,
+                      int64_t Ti_Current, double atime, double MaxGasVel, int hydro_only);
+void oracle_pm_kick(int64_t n, const uint8_t *flags, double *vel, const double *gravpm, double Fgravkick);
+void oracle_grav_kick(const int32_t *list, int64_t nlist, const uint8_t *flags, double *vel, const double *acc, double gravkick);
+void oracle_update_kick_times(oracle_times *t);
+void oracle_update_lastactive_drift(oracle_times *t);
+double oracle_gravity_dloga(const double *acc, const double *gravpm, double atime, double hubble, double ErrTolIntAccuracy, double softening);
+int64_t oracle_convert_timestep(const oracle_timeline *tl, double dloga, int64_t dti_max, int64_t Ti_Current, double MinSizeTimestep);
+int oracle_gravity_timebin(const oracle_timeline *tl, const double *acc, const double *gravpm, const oracle_step_params *sp,
+                           double atime, double hubble, int64_t dti_max, int64_t Ti_Current, int largest_active);
+int64_t oracle_pm_timestep_ti(const oracle_timeline *tl, const oracle_cosmo *c, const oracle_step_params *sp, const oracle_times *t,
+                              int64_t n, const double *vel, const float *mass, const uint8_t *type, const uint8_t *flags,
+                              double atime, int FastParticleType, double asmth);
+int oracle_hier_accelerations(const oracle_timeline *tl, const oracle_cosmo *c, const oracle_step_params *sp, oracle_gravshort_params *gp,
+                              oracle_times *t, int64_t n, const double *pos, const float *mass, const uint8_t *type, const uint8_t *flags,
+                              double *vel, double *fullacc, const double *gravpm, const uint8_t *bin_grav,
+                              const int32_t *act, int64_t nact, int64_t ngrav,
+                              double G, int Nmesh, double Asmth, double BoxSize, double *store);
+int oracle_hier_timesteps(const oracle_timeline *tl, const oracle_cosmo *c, const oracle_step_params *sp, oracle_gravshort_params *gp,
+                          oracle_times *t, int64_t n, const double *pos, const float *mass, const uint8_t *type, const uint8_t *flags,
+                          double *vel, double *fullacc, const double *gravpm, uint8_t *bin_grav,
+                          const int32_t *act, int64_t nact, int64_t ngrav, int is_pm,
+                          double G, int Nmesh, double Asmth, double BoxSize, double atime, int FastParticleType,
+                          const double *store, int64_t *info);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,3 +150,115 @@ def load(**kw):
     if _inst is None:
         _inst = Ref(**kw)
     return _inst
+
+
+# the reference's own drift.c + timestep.c + timebinmgr.c on top of its tree gravity (step loop)
+SO_STEP = os.path.join(_HERE, "_ref", "libref_step.so")
+NBINS = 47      # TIMEBINS + 1, timebinmgr.h:13
+
+
+class RefStep(Ref):
+    """Step loop of the reference (run.c:355-800 for collisionless particles with HierarchicalGravity):
+    drift, active lists, half kicks, hierarchical gravity + time-bin assignment.  One instance per
+    process (the sync-point table is set once)."""
+
+    def __init__(self, TimeIC, TimeMax, outtimes=(), Omega0=0.288, OmegaBaryon=0.0472, Hubble=0.1, G=43.0071,
+                 ErrTolIntAccuracy=0.02, MaxGasVel=3e5, MaxSizeTimestep=0.1, MinSizeTimestep=0.0,
+                 MaxRMSDisplacementFac=0.2, CourantFac=0.15, **kw):
+        super().__init__(so=SO_STEP, **kw)
+        L = self.L
+        L.ref_step_factor.restype = C.c_double
+        L.ref_loga_from_ti.restype = C.c_double
+        L.ref_dloga_from_dti.restype = C.c_double
+        L.ref_ti_from_loga.restype = C.c_int64
+        L.ref_dti_from_dloga.restype = C.c_int64
+        L.ref_step_drift.restype = C.c_double
+        L.ref_step_build_active.restype = C.c_int64
+        L.ref_step_sublist.restype = C.c_int64
+        L.ref_step_softening.restype = C.c_double
+        out = np.ascontiguousarray(outtimes, np.float64)
+        ts = np.array([ErrTolIntAccuracy, MaxGasVel, MaxSizeTimestep, MinSizeTimestep, MaxRMSDisplacementFac, CourantFac])
+        self.cosmo = dict(Omega0=Omega0, OmegaBaryon=OmegaBaryon, Hubble=Hubble, G=G)
+        self.tspar = dict(ErrTolIntAccuracy=ErrTolIntAccuracy, MaxGasVel=MaxGasVel, MaxSizeTimestep=MaxSizeTimestep,
+                          MinSizeTimestep=MinSizeTimestep, MaxRMSDisplacementFac=MaxRMSDisplacementFac)
+        self.sync_loga = np.log(np.unique(np.concatenate([[TimeIC, TimeMax], out[(out >= TimeIC) & (out <= TimeMax)]])))
+        rc = L.ref_step_init(C.c_double(TimeIC), C.c_double(TimeMax), C.c_int(len(out)), _p(out), C.c_double(Omega0),
+                             C.c_double(OmegaBaryon), C.c_double(Hubble), C.c_double(G), _p(ts))
+        if rc:
+            raise RuntimeError("RefStep: the reference timeline can be set only once per process")
+
+    # --- the integer timeline (timebinmgr.c:380-447) and the kick / drift integrals
+    def loga_from_ti(self, ti):
+        return self.L.ref_loga_from_ti(C.c_int64(ti))
+
+    def dti_from_dloga(self, dloga, ti):
+        return int(self.L.ref_dti_from_dloga(C.c_double(dloga), C.c_int64(ti)))
+
+    def dloga_from_dti(self, dti, ti):
+        return self.L.ref_dloga_from_dti(C.c_int64(dti), C.c_int64(ti))
+
+    def factor(self, kind, t0, t1):
+        """kind 0 drift, 1 gravkick, 2 hydrokick"""
+        return self.L.ref_step_factor(C.c_int(kind), C.c_int64(t0), C.c_int64(t1))
+
+    def set_times(self, scal, ti_kick, ti_last):
+        self.L.ref_step_set_times(_p(np.ascontiguousarray(scal, np.int64)), _p(np.ascontiguousarray(ti_kick, np.int64)),
+                                  _p(np.ascontiguousarray(ti_last, np.int64)))
+
+    def get_times(self):
+        scal = np.zeros(7, np.int64); kick = np.zeros(NBINS, np.int64); last = np.zeros(NBINS, np.int64)
+        self.L.ref_step_get_times(_p(scal), _p(kick), _p(last))
+        return scal, kick, last
+
+    def set_particles(self, pos, mass, type, box, vel=None, flags=None, fullacc=None, gravpm=None, bin_grav=None, bin_hydro=None,
+                      hsml=None, dthsml=None, hydroacc=None, entropy=None, dtentropy=None, topdepth=0, ti_drift=0):
+        f = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)
+        b = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8)
+        pos = f(pos); mass = np.ascontiguousarray(mass, np.float32); type = b(type)
+        self.n = len(mass)
+        keep = [f(vel), b(flags), f(fullacc), f(gravpm), b(bin_grav), b(bin_hydro), f(hsml), f(dthsml), f(hydroacc), f(entropy), f(dtentropy)]
+        self.L.ref_step_set_particles(C.c_int64(self.n), _p(pos), _p(keep[0]), _p(mass), _p(type), _p(keep[1]), _p(keep[2]), _p(keep[3]),
+                                      _p(keep[4]), _p(keep[5]), _p(keep[6]), _p(keep[7]), _p(keep[8]), _p(keep[9]), _p(keep[10]),
+                                      C.c_double(box), C.c_int(topdepth), C.c_int64(ti_drift))
+
+    def get(self):
+        n = self.n
+        out = dict(pos=np.zeros((n, 3)), vel=np.zeros((n, 3)), hsml=np.zeros(n), entropy=np.zeros(n), bin_grav=np.zeros(n, np.uint8),
+                   fullacc=np.zeros((n, 3)), ti_drift=np.zeros(n, np.int64))
+        self.L.ref_step_get(_p(out["pos"]), _p(out["vel"]), _p(out["hsml"]), _p(out["entropy"]), _p(out["bin_grav"]),
+                            _p(out["fullacc"]), _p(out["ti_drift"]))
+        return out
+
+    def drift(self, ti0, ti1, shift=(0.0, 0.0, 0.0)):
+        return self.L.ref_step_drift(C.c_int64(ti0), C.c_int64(ti1), _p(np.ascontiguousarray(shift, np.float64)))
+
+    def build_active(self):
+        """-> (list or None when implicit, [NumActiveParticle, NumActiveGravity, NumActiveHydro])"""
+        lst = np.zeros(self.n + 1, np.int32); counts = np.zeros(3, np.int64)
+        na = int(self.L.ref_step_build_active(_p(lst), _p(counts)))
+        return (None if na < 0 else lst[:na].copy()), counts
+
+    def sublist(self, maxtimebin):
+        lst = np.zeros(self.n + 1, np.int32)
+        na = int(self.L.ref_step_sublist(C.c_int(maxtimebin), _p(lst)))
+        return lst[:na].copy()
+
+    def kick(self, kind, atime=1.0):
+        """0 apply_half_kick, 1 apply_hydro_half_kick, 2 apply_PM_half_kick, 3 update_kick_times"""
+        self.L.ref_step_kick(C.c_int(kind), C.c_double(atime))
+
+    def set_gravity(self, par, G, nmesh, asmth):
+        self.L.ref_step_set_gravity(C.c_double(G), C.c_int(nmesh), C.c_double(asmth), C.c_double(par["ErrTolForceAcc"]),
+                                    C.c_double(par["BHOpeningAngle"]), C.c_double(par["MaxBHOpeningAngle"]), C.c_int(par["TreeUseBH"]),
+                                    C.c_double(par["Rcut"]), C.c_double(par["GravitySoftening"]))
+        return self.L.ref_step_softening()
+
+    def advance(self, first=False):
+        """One pass of the run.c loop -> (bad-timestep count, [NumActiveParticle, NumActiveGravity, is_PM])"""
+        info = np.zeros(3, np.int64)
+        bad = int(self.L.ref_step_advance(C.c_int(1 if first else 0), _p(info)))
+        return bad, info
+
+
+def step_available():
+    return os.path.exists(SO_STEP)

@@ -34,6 +34,7 @@
 
 /* ---- stand-ins for functions that live in reference files we do not build
  * (timestep.c needs cosmology/GSL; petaio needs bigfile) ------------------- */
+#ifndef REF_WITH_STEP      /* libref_step.so links the reference's own timestep.c / timebinmgr.c */
 int is_timebin_active(int i, inttime_t current)          /* timestep.c:143-150 */
 {
     if(i <= 0 || current <= 0) return 1;
@@ -49,6 +50,7 @@ ActiveParticles init_empty_active_particles(struct part_manager_type *PartManage
     act.Particles = PartManager->Base;
     return act;
 }
+#endif
 void dump_snapshot(const char *dump, const double Time, void *CP, const char *OutputDir) {}
 
 /* Time-integration helpers (timebinmgr.c, timefac.c need GSL; cosmology.c needs GSL;
@@ -71,6 +73,7 @@ static int mixed_key(inttime_t t0, inttime_t t1)
     if(d < 0 || d > TIMEBINS + 1) endrun(1, "ref_driver: unexpected kick-time difference %ld\n", (long) d);
     return (int) d;
 }
+#ifndef REF_WITH_STEP
 double dloga_from_dti(inttime_t dti, const inttime_t Ti_Current)
 {
     if(mixed_on) return mx_dloga_pred[mixed_key(0, dti)];
@@ -83,11 +86,13 @@ double get_exact_drift_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { retur
 double get_exact_gravkick_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return mixed_on ? mx_gravkick[mixed_key(t0, t1)] : exact_factor(t0, t1); }
 double get_exact_hydrokick_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return mixed_on ? mx_hydrokick[mixed_key(t0, t1)] : exact_factor(t0, t1); }
 double hubble_function(const Cosmology *CP, double a) { return sph_hubble; }
+#endif
 int winds_is_particle_decoupled(int i) { return 0; }
 void winds_decoupled_hydro(int i, double atime) {}
 /* set_hydro_params (hydra.c:37-48) reads its three keys through param_get_*; the
  * driver supplies them from a table instead of a parsed parameter file. */
 static double hp_visc, hp_contrast; static int hp_di;
+#ifndef REF_WITH_STEP
 double param_get_double(ParameterSet *ps, const char *name)
 {
     if(!strcmp(name, "ArtBulkViscConst")) return hp_visc;
@@ -99,6 +104,7 @@ int param_get_int(ParameterSet *ps, const char *name)
     if(!strcmp(name, "DensityIndependentSphOn")) return hp_di;
     endrun(1, "ref_driver: unexpected parameter %s\n", name); return 0;
 }
+#endif
 int param_get_enum(ParameterSet *ps, const char *name) { endrun(1, "ref_driver: unexpected enum %s\n", name); return 0; }
 
 static struct ClockTable CT;
@@ -469,6 +475,271 @@ int ref_gravpm_force(int64_t n, const double *pos, const float *mass, double Box
     petapm_destroy(&pm);
 #endif
     return 0;
+}
+#endif
+
+#ifdef REF_WITH_STEP
+/* ---- Step loop: the reference's own drift.c, timestep.c and timebinmgr.c (compiled unmodified) on
+ * one rank -- drift_all_particles, update_lastactive_drift, build_active_particles,
+ * build_active_sublist, apply_half_kick / apply_hydro_half_kick / apply_PM_half_kick,
+ * update_kick_times, hierarchical_gravity_accelerations and hierarchical_gravity_and_timesteps
+ * (with the reference's own force_tree_active_moments + grav_short_tree underneath), driven the way
+ * run.c:355-800 drives them.  Stand-ins only for what needs GSL: the background cosmology
+ * (cosmology.c:64-86 reduces to the flat matter + Lambda form below when radiation, curvature and
+ * neutrinos are off) and the kick/drift integrals of timefac.c:12-73, whose integrands are
+ * restated and integrated by Gauss-Legendre panels instead of gsl_integration_qag. */
+#include <libgadget/drift.h>
+#include <libgadget/timebinmgr.h>
+#include <libgadget/timefac.h>
+#include <libgadget/physconst.h>
+
+static Cosmology stepCP;
+static double ts_par[6];
+double hubble_function(const Cosmology *CP, double a)
+{
+    return CP->Hubble * sqrt(CP->Omega0 / (a * a * a) + CP->OmegaLambda);
+}
+static double step_integrand(int kind, double a)
+{
+    const double h = hubble_function(&stepCP, a);
+    if(kind == 0) return 1 / (h * a * a * a);                      /* drift_integ     timefac.c:12-17 */
+    if(kind == 1) return 1 / (h * a * a);                          /* gravkick_integ  timefac.c:20-26 */
+    return 1 / (h * pow(a, 3 * GAMMA_MINUS1) * a);                 /* hydrokick_integ timefac.c:30-38 */
+}
+static double step_factor(int kind, inttime_t t0, inttime_t t1)    /* get_exact_factor timefac.c:41-56 */
+{
+    if(t0 == t1) return 0;
+    static const double gx[4] = {0.1834346424956498, 0.5255324099163290, 0.7966664774136267, 0.9602898564975363};
+    static const double gw[4] = {0.3626837833783620, 0.3137066458778873, 0.2223810344533745, 0.1012285362903763};
+    const double a0 = exp(loga_from_ti(t0)), a1 = exp(loga_from_ti(t1));
+    const int NP = 64;
+    double sum = 0;
+    for(int p = 0; p < NP; p++) {
+        const double lo = a0 + (a1 - a0) * p / NP, hi = a0 + (a1 - a0) * (p + 1) / NP;
+        const double c = 0.5 * (lo + hi), hw = 0.5 * (hi - lo);
+        for(int k = 0; k < 4; k++) sum += gw[k] * hw * (step_integrand(kind, c - hw * gx[k]) + step_integrand(kind, c + hw * gx[k]));
+    }
+    return sum;
+}
+double get_exact_drift_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return step_factor(0, t0, t1); }
+double get_exact_gravkick_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return step_factor(1, t0, t1); }
+double get_exact_hydrokick_factor(Cosmology *CP, inttime_t t0, inttime_t t1) { return step_factor(2, t0, t1); }
+double ref_step_factor(int kind, int64_t t0, int64_t t1) { return step_factor(kind, t0, t1); }
+int BHGetRepositionEnabled(void) { return 0; }
+#ifndef REF_WITH_PM
+double get_omega_nu(const _omega_nu *const omnu, const double a) { return 0; }
+#endif
+double param_get_double(ParameterSet *ps, const char *name)
+{
+    static const char *keys[6] = {"ErrTolIntAccuracy", "MaxGasVel", "MaxSizeTimestep", "MinSizeTimestep", "MaxRMSDisplacementFac", "CourantFac"};
+    if(!strcmp(name, "ArtBulkViscConst")) return hp_visc;
+    if(!strcmp(name, "DensityContrastLimit")) return hp_contrast;
+    for(int k = 0; k < 6; k++) if(!strcmp(name, keys[k])) return ts_par[k];
+    endrun(1, "ref_driver: unexpected parameter %s\n", name); return 0;
+}
+int param_get_int(ParameterSet *ps, const char *name)
+{
+    if(!strcmp(name, "DensityIndependentSphOn")) return hp_di;
+    if(!strcmp(name, "ForceEqualTimesteps")) return 0;
+    endrun(1, "ref_driver: unexpected parameter %s\n", name); return 0;
+}
+char *param_get_string(ParameterSet *ps, const char *name) { return NULL; }
+
+/* Timeline and parameters: set_sync_params_test + setup_sync_points (timebinmgr.c:151-330) and
+ * set_timestep_params (timestep.c:51-67).  tspar = {ErrTolIntAccuracy, MaxGasVel, MaxSizeTimestep,
+ * MinSizeTimestep, MaxRMSDisplacementFac, CourantFac}.  Call once, before any particles. */
+int ref_step_init(double TimeIC, double TimeMax, int nout, double *outtimes, double Omega0, double OmegaBaryon,
+                  double Hubble, double G, const double *tspar)
+{
+    static int done = 0;
+    if(done) return 1;
+    free_all();
+    memset(&stepCP, 0, sizeof(stepCP));
+    stepCP.Omega0 = Omega0; stepCP.OmegaLambda = 1 - Omega0; stepCP.OmegaBaryon = OmegaBaryon; stepCP.OmegaCDM = Omega0 - OmegaBaryon;
+    stepCP.Hubble = Hubble; stepCP.GravInternal = G; stepCP.HubbleParam = 0.7;
+    stepCP.RhoCrit = 3 * Hubble * Hubble / (8 * M_PI * G);
+    memcpy(ts_par, tspar, sizeof(ts_par));
+    set_timestep_params(NULL);
+    set_sync_params_test(nout, outtimes);
+    setup_sync_points(&stepCP, TimeIC, TimeMax, 0.0, 0);
+    done = 1;
+    return 0;
+}
+/* the integer timeline as the reference computes it (timebinmgr.c:380-447) */
+double ref_loga_from_ti(int64_t ti) { return loga_from_ti(ti); }
+int64_t ref_ti_from_loga(double loga) { return ti_from_loga(loga); }
+int64_t ref_dti_from_dloga(double dloga, int64_t Ti_Current) { return dti_from_dloga(dloga, Ti_Current); }
+double ref_dloga_from_dti(int64_t dti, int64_t Ti_Current) { return dloga_from_dti(dti, Ti_Current); }
+
+static DriftKickTimes stepT;
+static ActiveParticles stepAct;
+static int step_act_built = 0;
+static PetaPM step_pm;
+static double step_rho0;
+
+/* scal = {mintimebin, maxtimebin, mingravtimebin, Ti_Current, PM_length, PM_start, PM_kick} */
+void ref_step_set_times(const int64_t *scal, const int64_t *ti_kick, const int64_t *ti_last)
+{
+    stepT.mintimebin = scal[0]; stepT.maxtimebin = scal[1]; stepT.mingravtimebin = scal[2];
+    stepT.Ti_Current = scal[3]; stepT.PM_length = scal[4]; stepT.PM_start = scal[5]; stepT.PM_kick = scal[6];
+    for(int b = 0; b <= TIMEBINS; b++) { stepT.Ti_kick[b] = ti_kick[b]; stepT.Ti_lastactivedrift[b] = ti_last[b]; }
+}
+void ref_step_get_times(int64_t *scal, int64_t *ti_kick, int64_t *ti_last)
+{
+    scal[0] = stepT.mintimebin; scal[1] = stepT.maxtimebin; scal[2] = stepT.mingravtimebin;
+    scal[3] = stepT.Ti_Current; scal[4] = stepT.PM_length; scal[5] = stepT.PM_start; scal[6] = stepT.PM_kick;
+    for(int b = 0; b <= TIMEBINS; b++) { ti_kick[b] = stepT.Ti_kick[b]; ti_last[b] = stepT.Ti_lastactivedrift[b]; }
+}
+
+/* Particles of any type; gas (type 0) gets an SPH slot in index order.  flags: bit 0 IsGarbage,
+ * bit 1 Swallowed.  Any of the optional arrays may be NULL (zeros). */
+int ref_step_set_particles(int64_t n, const double *pos, const double *vel, const float *mass, const unsigned char *type,
+                           const unsigned char *flags, const double *fullacc, const double *gravpm,
+                           const unsigned char *bin_grav, const unsigned char *bin_hydro, const double *hsml, const double *dthsml,
+                           const double *hydroacc, const double *entropy, const double *dtentropy,
+                           double BoxSize, int topdepth, int64_t ti_drift)
+{
+    if(step_act_built) { free_active_particles(&stepAct); step_act_built = 0; }
+    free_all();
+    particle_alloc_memory(PartManager, BoxSize, n);
+    have_particles = 1;
+    PartManager->NumPart = n;
+    int64_t ngas = 0;
+    for(int64_t i = 0; i < n; i++) ngas += (type[i] == 0);
+    slots_init(0.01 * n, SlotsManager);
+    slots_set_enabled(0, sizeof(struct sph_particle_data), SlotsManager);
+    int64_t atleast[6] = {0};
+    atleast[0] = ngas > 0 ? ngas : 1;
+    slots_reserve(1, atleast, SlotsManager);
+    slots_ready = 1;
+    SlotsManager->info[0].size = ngas;
+    build_uniform_domain(&dd, topdepth);
+    int64_t pi = 0;
+    for(int64_t i = 0; i < n; i++) {
+        memset(&P[i], 0, sizeof(P[i]));
+        for(int k = 0; k < 3; k++) {
+            P[i].Pos[k] = pos[3 * i + k];
+            P[i].Vel[k] = vel ? vel[3 * i + k] : 0;
+            P[i].FullTreeGravAccel[k] = fullacc ? fullacc[3 * i + k] : 0;
+            P[i].GravPM[k] = gravpm ? gravpm[3 * i + k] : 0;
+        }
+        P[i].Mass = mass[i]; P[i].Type = type[i]; P[i].ID = i;
+        P[i].IsGarbage = flags ? (flags[i] & 1) : 0; P[i].Swallowed = flags ? ((flags[i] >> 1) & 1) : 0;
+        P[i].TimeBinGravity = bin_grav ? bin_grav[i] : 0; P[i].TimeBinHydro = bin_hydro ? bin_hydro[i] : 0;
+        P[i].Ti_drift = ti_drift;
+        P[i].Hsml = hsml ? hsml[i] : 0; P[i].DtHsml = dthsml ? dthsml[i] : 0;
+        P[i].TopLeaf = domain_get_topleaf(PEANO(P[i].Pos, BoxSize), &dd);
+        if(type[i] == 0) {
+            P[i].PI = pi++;
+            memset(&SPHP(i), 0, sizeof(struct sph_particle_data));
+            for(int k = 0; k < 3; k++) SPHP(i).HydroAccel[k] = hydroacc ? hydroacc[3 * i + k] : 0;
+            SPHP(i).Entropy = entropy ? entropy[i] : 0; SPHP(i).DtEntropy = dtentropy ? dtentropy[i] : 0;
+        }
+    }
+    return 0;
+}
+void ref_step_get(double *pos, double *vel, double *hsml, double *entropy, unsigned char *bin_grav, double *fullacc, int64_t *ti_drift)
+{
+    const int64_t n = PartManager->NumPart;
+    for(int64_t i = 0; i < n; i++) {
+        for(int k = 0; k < 3; k++) {
+            if(pos) pos[3 * i + k] = P[i].Pos[k];
+            if(vel) vel[3 * i + k] = P[i].Vel[k];
+            if(fullacc) fullacc[3 * i + k] = P[i].FullTreeGravAccel[k];
+        }
+        if(hsml) hsml[i] = P[i].Hsml;
+        if(entropy) entropy[i] = P[i].Type == 0 ? SPHP(i).Entropy : 0;
+        if(bin_grav) bin_grav[i] = P[i].TimeBinGravity;
+        if(ti_drift) ti_drift[i] = P[i].Ti_drift;
+    }
+}
+/* drift_all_particles (drift.c:84-102): returns the drift factor it used */
+double ref_step_drift(int64_t ti0, int64_t ti1, const double *shift)
+{
+    drift_all_particles(ti0, ti1, &stepCP, shift);
+    /* the tree code needs the top leaf of the new position (domain_maintain would do this) */
+    for(int64_t i = 0; i < PartManager->NumPart; i++) P[i].TopLeaf = domain_get_topleaf(PEANO(P[i].Pos, PartManager->BoxSize), &dd);
+    return get_exact_drift_factor(&stepCP, ti0, ti1);
+}
+/* update_lastactive_drift + build_active_particles (timestep.c:860-871,1334-1431).  list_out (size
+ * NumPart) receives the list; returns NumActiveParticle, or -1 - NumPart when the list is implicit
+ * (PM step: ActiveParticle == NULL).  counts = {NumActiveParticle, NumActiveGravity, NumActiveHydro}. */
+int64_t ref_step_build_active(int *list_out, int64_t *counts)
+{
+    if(step_act_built) { free_active_particles(&stepAct); step_act_built = 0; }
+    update_lastactive_drift(&stepT);
+    stepAct = init_empty_active_particles(PartManager);
+    build_active_particles(&stepAct, &stepT, 0, get_atime(stepT.Ti_Current), PartManager);
+    step_act_built = 1;
+    counts[0] = stepAct.NumActiveParticle; counts[1] = stepAct.NumActiveGravity; counts[2] = stepAct.NumActiveHydro;
+    if(!stepAct.ActiveParticle) return -1 - stepAct.NumActiveParticle;
+    for(int64_t q = 0; q < stepAct.NumActiveParticle; q++) list_out[q] = stepAct.ActiveParticle[q];
+    return stepAct.NumActiveParticle;
+}
+/* build_active_sublist (timestep.c:1435-1478) of the current list */
+ActiveParticles build_active_sublist(const ActiveParticles *act, const int maxtimebin, const inttime_t Ti_Current);
+int64_t ref_step_sublist(int maxtimebin, int *list_out)
+{
+    ActiveParticles sub = build_active_sublist(&stepAct, maxtimebin, stepT.Ti_Current);
+    const int64_t na = sub.NumActiveParticle;
+    for(int64_t q = 0; q < na; q++) list_out[q] = sub.ActiveParticle[q];
+    myfree(sub.ActiveParticle);
+    return na;
+}
+/* kind 0 apply_half_kick, 1 apply_hydro_half_kick, 2 apply_PM_half_kick, 3 update_kick_times
+ * (timestep.c:874-994,215-235) on the current active list */
+void ref_step_kick(int kind, double atime)
+{
+    if(kind == 0) apply_half_kick(&stepAct, &stepCP, &stepT, atime);
+    else if(kind == 1) apply_hydro_half_kick(&stepAct, &stepCP, &stepT, atime);
+    else if(kind == 2) apply_PM_half_kick(&stepCP, &stepT);
+    else update_kick_times(&stepT);
+}
+/* Short-range gravity parameters of the hierarchy (as ref_grav_short_tree above) */
+void ref_step_set_gravity(double G, int Nmesh, double Asmth, double ErrTolForceAcc, double BHOpeningAngle,
+                          double MaxBHOpeningAngle, int TreeUseBH, double Rcut, double GravitySoftening)
+{
+    memset(&step_pm, 0, sizeof(step_pm));
+    step_pm.BoxSize = PartManager->BoxSize; step_pm.Asmth = Asmth; step_pm.Nmesh = Nmesh; step_pm.G = G;
+    step_pm.CellSize = step_pm.BoxSize / Nmesh;
+    gravshort_fill_ntab(SHORTRANGE_FORCE_WINDOW_TYPE_EXACT, Asmth);
+    struct gravshort_tree_params tp = {0};
+    tp.ErrTolForceAcc = ErrTolForceAcc; tp.BHOpeningAngle = BHOpeningAngle; tp.MaxBHOpeningAngle = MaxBHOpeningAngle;
+    tp.TreeUseBH = TreeUseBH; tp.Rcut = Rcut; tp.FractionalGravitySoftening = GravitySoftening;
+    set_gravshort_treepar(tp);
+    gravshort_set_softenings(1.0);
+}
+double ref_step_softening(void) { return FORCE_SOFTENING(); }
+/* One pass of run.c:441-795 for collisionless particles with HierarchicalGravity on, PM force held
+ * fixed (P[].GravPM as loaded): advance Ti_Current to the next kick, drift, active list,
+ * hierarchical_gravity_accelerations, update_kick_times, PM half kick, hierarchical_gravity_and_timesteps,
+ * update_kick_times, PM half kick.  first != 0 starts from the state as loaded (no advance, no drift),
+ * like NumCurrentTiStep == 0.  Returns the reference's bad-timestep count. */
+int ref_step_advance(int first, int64_t *nactive_out)
+{
+    const inttime_t Ti_Last = stepT.Ti_Current;
+    if(!first) stepT.Ti_Current = find_next_kick(stepT.Ti_Current, stepT.mintimebin);
+    const double atime = get_atime(stepT.Ti_Current);
+    const int is_PM = is_PM_timestep(&stepT);
+    const double zero[3] = {0, 0, 0};
+    if(!first) ref_step_drift(Ti_Last, stepT.Ti_Current, zero);
+    int64_t counts[3];
+    int *tmp = (int *) malloc(sizeof(int) * (PartManager->NumPart + 1));
+    ref_step_build_active(tmp, counts);
+    free(tmp);
+    if(nactive_out) { nactive_out[0] = counts[0]; nactive_out[1] = counts[1]; nactive_out[2] = is_PM; }
+    struct grav_accel_store GravAccel = {0};
+    GravAccel.nstore = PartManager->NumPart;
+    GravAccel.GravAccel = (MyFloat (*)[3]) mymalloc2("GravAccel", GravAccel.nstore * sizeof(GravAccel.GravAccel[0]));
+    hierarchical_gravity_accelerations(&stepAct, &step_pm, &dd, GravAccel, &stepT, 0, &stepCP, NULL);
+    update_kick_times(&stepT);
+    if(is_PM) apply_PM_half_kick(&stepCP, &stepT);
+    const int bad = hierarchical_gravity_and_timesteps(&stepAct, &step_pm, &dd, GravAccel, &stepT, atime, 0, 2, &stepCP, NULL);
+    update_kick_times(&stepT);
+    if(is_PM) apply_PM_half_kick(&stepCP, &stepT);
+    free_active_particles(&stepAct);
+    step_act_built = 0;
+    return bad;
 }
 #endif
 
