@@ -314,6 +314,82 @@ int b200_pmslab_fft1d(b200_ctx *ctx, int inverse);
 int b200_pmslab_transfer(b200_ctx *ctx);
 int b200_pmslab_readout_dev(b200_ctx *ctx, int64_t n_own, double *gravpm_out, double *potential_out);
 
+/* ---- Step loop around the force computation (device-resident particle state) -------------------
+ * Replaces, for collisionless and gas particles, drift_all_particles (libgadget/drift.c:84-102),
+ * build_active_particles / build_active_sublist (timestep.c:1334-1478), apply_half_kick /
+ * apply_hydro_half_kick / apply_PM_half_kick (timestep.c:874-994) and the hierarchical gravity drivers
+ * hierarchical_gravity_accelerations / hierarchical_gravity_and_timesteps (timestep.c:296-598), so
+ * that P[].Pos / Vel / TimeBinGravity live in HBM between force computations (run.c:355-800).  The
+ * host keeps DriftKickTimes, the cosmology and its integrals (get_exact_gravkick_factor & co.) and
+ * hands factors in; black-hole particles (drag terms, repositioning) are not supported.
+ * Status of this block in round 1: compiled for sm_100a and checked on the CPU side against the
+ * oracle restatement; not yet run on hardware (tests/test_step_gpu.py). */
+typedef struct b200_step_state {      /* host arrays in particle-index order, any may be NULL (= 0) */
+    const double *vel;                /* [n][3] P[].Vel */
+    const double *fullacc;            /* [n][3] P[].FullTreeGravAccel */
+    const double *gravpm;             /* [n][3] P[].GravPM */
+    const uint8_t *bin_grav;          /* [n] P[].TimeBinGravity */
+    const uint8_t *bin_hydro;         /* [n] P[].TimeBinHydro */
+    const uint8_t *flags;             /* [n] bit 0 IsGarbage, bit 1 Swallowed; NULL keeps what b200_set_particles_* set */
+    const double *hsml, *dthsml;      /* [n] P[].Hsml, P[].DtHsml (gas) */
+    const double *hydroacc;           /* [n][3] SphP[].HydroAccel */
+    const double *entropy, *dtentropy;/* [n] SphP[].Entropy, SphP[].DtEntropy */
+    double BoxSize;                   /* PartManager->BoxSize; 0 = the box b200_pm_init / b200_tree_build was given */
+} b200_step_state;
+typedef struct b200_step_state_out {  /* host outputs, any may be NULL */
+    double *pos, *vel, *fullacc, *hsml, *entropy;
+    uint8_t *bin_grav;
+} b200_step_state_out;
+typedef struct b200_step_times {      /* DriftKickTimes, timestep.h:10-26 */
+    int32_t mintimebin, maxtimebin, mingravtimebin, pad_;
+    int64_t Ti_kick[B200_TIMEBINS + 1], Ti_lastactivedrift[B200_TIMEBINS + 1];
+    int64_t Ti_Current, PM_length, PM_start, PM_kick;
+} b200_step_times;
+typedef struct b200_step_params {
+    double ErrTolIntAccuracy, MaxSizeTimestep, MinSizeTimestep, MaxRMSDisplacementFac;   /* TimestepParams, timestep.c:21-47 */
+    double softening;                 /* FORCE_SOFTENING(), gravshort-tree.c:37-41 */
+    double omega_type[6];             /* density parameter the mean spacing of each particle type is taken from
+                                       * (OmegaBaryon / OmegaCDM / get_omega_nu, timestep.c:1251-1263) */
+    double RhoCrit;                   /* CP->RhoCrit */
+    int32_t FastParticleType, pad_;
+    const double *sync_loga;          /* SyncPoints[].loga, timebinmgr.c:18 */
+    int64_t nsync;
+    double (*gravkick_factor)(void *user, int64_t ti0, int64_t ti1);   /* get_exact_gravkick_factor, timefac.c:65-68 */
+    void *user;
+} b200_step_params;
+
+/* Upload the state the step loop owns (after b200_set_particles_*). */
+int b200_step_set_state(b200_ctx *ctx, const b200_step_state *state);
+int b200_step_get_state(b200_ctx *ctx, b200_step_state_out *out);
+/* FullTreeGravAccel / GravPM of the state <- the device results of the last full-tree
+ * b200_grav_short_tree / b200_pm_force (no host round trip). */
+int b200_step_adopt_forces(b200_ctx *ctx, int tree, int pm);
+/* drift_all_particles with ddrift = get_exact_drift_factor(ti0, ti1); shift[3] may be NULL.
+ * *nbad = particles the reference would endrun on (Hsml <= 0, non-finite position); returns nonzero then. */
+int b200_step_drift(b200_ctx *ctx, double ddrift, const double *shift, int64_t *nbad);
+/* build_active_particles: the list stays on the device.  counts = {NumActiveParticle, NumActiveGravity,
+ * NumActiveHydro}; bincounts[6][B200_TIMEBINS + 1] = TimeBinCountType (may be NULL); nhydro_slots =
+ * SlotsManager->info[0].size + info[5].size (what the PM branch reports as NumActiveHydro). */
+int b200_step_build_active(b200_ctx *ctx, int64_t Ti_Current, int is_pm, int64_t nhydro_slots, int64_t *counts, int64_t *bincounts);
+/* build_active_sublist of the current active list */
+int b200_step_active_sublist(b200_ctx *ctx, int maxtimebin, int64_t Ti_Current, int64_t *nsub);
+/* which = 0: the active list (*nout = -1 - n when it is implicit), 1: the last sub-list */
+int b200_step_get_active(b200_ctx *ctx, int which, int32_t *out, int64_t *nout);
+/* apply_half_kick (hydro_only = 0) / apply_hydro_half_kick (1) on the current active list;
+ * gravkick / hydrokick / dt_entr [B200_TIMEBINS + 1] by bin as timestep.c:879-891,905-907 compute them */
+int b200_step_half_kick(b200_ctx *ctx, const double *gravkick, const double *hydrokick, const double *dt_entr,
+                        int64_t Ti_Current, double atime, double MaxGasVel, int hydro_only);
+/* apply_PM_half_kick: Vel += GravPM * Fgravkick (the caller advances PM_kick) */
+int b200_step_pm_kick(b200_ctx *ctx, double Fgravkick);
+/* hierarchical_gravity_accelerations on the current active list (ngrav = NumActiveGravity);
+ * gp->TreeUseBH > 1 is reset to 0 after the first walk like TreeParams.TreeUseBH */
+int b200_step_hier_accelerations(b200_ctx *ctx, const b200_step_params *sp, b200_gravshort_params *gp,
+                                 b200_step_times *times, int64_t ngrav);
+/* hierarchical_gravity_and_timesteps; hubble = hubble_function(CP, atime);
+ * info = {largest active bin, PM_length, bad-step count} */
+int b200_step_hier_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_gravshort_params *gp,
+                             b200_step_times *times, int64_t ngrav, int is_pm, double atime, double hubble, int64_t *info);
+
 /* Device-side timing of the phases of the last call, milliseconds (CUDA
  * events on the engine's stream).  Names follow the reference's walltime
  * categories (libgadget/walltime.c, gravshort-tree.c:134-144, petapm.c:280-355). */

@@ -153,6 +153,18 @@ struct Engine {
     double walk_pieces = 0;     // leaf pieces (<= 8 particles each) queued by the last walk
     int walk_chunks = 0;        // pool chunks it used
 
+    // ---- step loop (steploop.cu): lists and scratch of the device-resident drift / kick / time-bin code ----
+    bool st_state = false, st_have_gas = false;
+    double st_box = 0;                                 // PartManager->BoxSize when given with the state
+    DevBuf<int> st_iota, st_act, st_listA, st_listB;   // identity, the active list, two sub-list buffers
+    DevBuf<uint8_t> st_flag;
+    int64_t st_nact = 0, st_nsub = 0;
+    bool st_act_implicit = true;                       // PM step: every particle, no list (ActiveParticle == NULL)
+    DevBuf<double> st_store, st_lower;                 // [n][3] StoredGravAccel / accelerations of the lower levels
+    bool st_store_valid = false;
+    DevBuf<double> st_sync, st_part, st_tab;
+    DevBuf<unsigned long long> st_cnt;
+
     Timer timers[T_COUNT];
     b200_timings last = {};
 };
@@ -205,6 +217,9 @@ int sph_set_hsml_range(Engine *E, const double *hsml, int64_t first, int64_t cou
 int sph_set_timebins(Engine *E, const uint8_t *bin_grav, const uint8_t *bin_hydro, const b200_sph_bins *bins);
 int sph_set_active(Engine *E, const int32_t *active, int64_t nactive);
 int sph_set_state(Engine *E, const double *density, const double *egy, const double *dhsmlfac, const double *divvel, const double *curlvel);
+
+// step loop (steploop.cu)
+void step_release(Engine *E);
 
 // walk (tree_walk.cu)
 int walk_init_tables(Engine *E);

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "gpu_unverified: CUDA code compiled but not yet run on hardware; skips itself without a device")
 
 
 @pytest.fixture(scope="session")
