@@ -22,7 +22,9 @@ namespace b200 {
 
 #define TB B200_TIMEBINS
 #define NBIN (B200_TIMEBINS + 1)
+#ifndef STEP_BLOCKS
 #define STEP_BLOCKS 592          // 4 x 148 SMs: fixed grid of the per-type reductions (deterministic partial sums)
+#endif
 
 __device__ __forceinline__ long long dti_of_bin(int bin) { return bin > 0 ? (1ll << bin) : 0ll; }
 __device__ __forceinline__ bool bin_active(int bin, long long ti)          // timestep.c:143-150

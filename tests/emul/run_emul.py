@@ -1,0 +1,56 @@
+"""Run the step-loop scenarios of tests/step_scenarios.py through mp-gadget_b200/steploop.py's
+StepEngine on the CPU emulation build of csrc/steploop.cu (tests/emul/build.py) and check them
+against the reference's golden vectors.  TEST INFRASTRUCTURE ONLY.  Started by
+tests/test_step_emul.py in a subprocess with OMP_WAIT_POLICY=passive (256 OS threads per block)."""
+import ctypes as C
+import importlib
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, HERE)
+import build as EB                   # noqa: E402
+import step_scenarios as SC          # noqa: E402
+import test_step as TS               # noqa: E402
+
+
+class EmulEngine:
+    """The three calls StepEngine makes on a b200 Engine, bound to the emulation library."""
+
+    def __init__(self):
+        self.L = C.CDLL(EB.build())
+        self.L.b200_last_error.restype = C.c_char_p
+        self.L.b200_ctx_destroy.restype = None
+        self.ctx = C.c_void_p()
+        assert self.L.b200_ctx_create(C.byref(self.ctx), C.c_int(0)) == 0
+
+    def set_particles(self, pos, mass, type=None, oldacc=None):
+        pos = np.ascontiguousarray(pos, np.float64); mass = np.ascontiguousarray(mass, np.float32)
+        type = None if type is None else np.ascontiguousarray(type, np.uint8)
+        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        assert self.L.b200_set_particles_soa(self.ctx, p(pos), p(mass), p(type), None, C.c_int64(len(mass))) == 0
+
+    def gravpm_init_periodic(self, box, asmth, nmesh, G):
+        assert self.L.b200_pm_init(self.ctx, C.c_double(box), C.c_double(asmth), C.c_int(nmesh), C.c_double(G)) == 0
+
+
+def main(which):
+    SL = importlib.import_module("mp-gadget_b200.steploop")
+    O = TS.make_oracle()
+    cosmo = {k: float(TS.GOLD["cosmo/" + k]) for k in ("Omega0", "OmegaBaryon", "Hubble", "G")}
+    ts = {k: float(TS.GOLD["tspar/" + k]) for k in ("ErrTolIntAccuracy", "MaxGasVel", "MaxSizeTimestep", "MinSizeTimestep", "MaxRMSDisplacementFac")}
+    S = SL.StepEngine(EmulEngine(), TS.GOLD["sync_loga"], O.factor, O.hubble, **cosmo, **ts)
+    if which in ("primitives", "all"):
+        out = SC.run_primitives(S, SC.primitives_inputs())
+        TS.check_primitives(out)
+        print("primitives ok")
+    if which in ("hierarchy", "all"):
+        rec = SC.run_hierarchy(S, SC.hierarchy_inputs())
+        TS.check_hierarchy(rec)
+        print("hierarchy ok")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "all")

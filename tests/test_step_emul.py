@@ -1,0 +1,19 @@
+"""csrc/steploop.cu -- kernels and host drivers, source unchanged -- executed on the CPU under the CUDA
+stand-in of tests/emul (blocks serial, the threads of a block an OpenMP team; tree build and walk
+supplied by the oracle) and checked against the golden vectors of the reference's own drift.c /
+timestep.c / timebinmgr.c.  This is how the step-loop CUDA code, written in a round whose GPU budget was
+already spent, was checked before its first hardware run; tests/test_step_gpu.py is the hardware test."""
+import os
+import subprocess
+import sys
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("which", ["primitives", "hierarchy"])
+def test_steploop_source_under_emulation(which):
+    env = dict(os.environ, OMP_WAIT_POLICY="passive")          # 256 OS threads per emulated block: do not spin
+    r = subprocess.run([sys.executable, os.path.join(HERE, "emul", "run_emul.py"), which], env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert which + " ok" in r.stdout
