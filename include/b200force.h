@@ -338,7 +338,7 @@ typedef struct b200_step_state {      /* host arrays in particle-index order, an
 } b200_step_state;
 typedef struct b200_step_state_out {  /* host outputs, any may be NULL */
     double *pos, *vel, *fullacc, *hsml, *entropy;
-    uint8_t *bin_grav;
+    uint8_t *bin_grav, *bin_hydro;
 } b200_step_state_out;
 typedef struct b200_step_times {      /* DriftKickTimes, timestep.h:10-26 */
     int32_t mintimebin, maxtimebin, mingravtimebin, pad_;
@@ -346,7 +346,7 @@ typedef struct b200_step_times {      /* DriftKickTimes, timestep.h:10-26 */
     int64_t Ti_Current, PM_length, PM_start, PM_kick;
 } b200_step_times;
 typedef struct b200_step_params {
-    double ErrTolIntAccuracy, MaxSizeTimestep, MinSizeTimestep, MaxRMSDisplacementFac;   /* TimestepParams, timestep.c:21-47 */
+    double ErrTolIntAccuracy, MaxSizeTimestep, MinSizeTimestep, MaxRMSDisplacementFac, CourantFac;   /* TimestepParams, timestep.c:21-47 */
     double softening;                 /* FORCE_SOFTENING(), gravshort-tree.c:37-41 */
     double omega_type[6];             /* density parameter the mean spacing of each particle type is taken from
                                        * (OmegaBaryon / OmegaCDM / get_omega_nu, timestep.c:1251-1263) */
@@ -381,6 +381,10 @@ int b200_step_half_kick(b200_ctx *ctx, const double *gravkick, const double *hyd
                         int64_t Ti_Current, double atime, double MaxGasVel, int hydro_only);
 /* apply_PM_half_kick: Vel += GravPM * Fgravkick (the caller advances PM_kick) */
 int b200_step_pm_kick(b200_ctx *ctx, double Fgravkick);
+/* find_hydro_timesteps (timestep.c:617-738) for the gas on the current active list: new P[].TimeBinHydro on
+ * the device, times->mintimebin updated.  maxsignalvel[n] = SphP[].MaxSignalVel by particle index (host). */
+int b200_step_hydro_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel,
+                              double atime, double hubble, int64_t *nbad);
 /* hierarchical_gravity_accelerations on the current active list (ngrav = NumActiveGravity);
  * gp->TreeUseBH > 1 is reset to 0 after the first walk like TreeParams.TreeUseBH */
 int b200_step_hier_accelerations(b200_ctx *ctx, const b200_step_params *sp, b200_gravshort_params *gp,

@@ -162,7 +162,8 @@ struct Engine {
     bool st_act_implicit = true;                       // PM step: every particle, no list (ActiveParticle == NULL)
     DevBuf<double> st_store, st_lower;                 // [n][3] StoredGravAccel / accelerations of the lower levels
     bool st_store_valid = false;
-    DevBuf<double> st_sync, st_part, st_tab;
+    DevBuf<double> st_sync, st_part, st_tab, st_maxsig;  // st_maxsig: SphP[].MaxSignalVel by particle index
+    bool st_maxsig_valid = false;
     DevBuf<unsigned long long> st_cnt;
 
     Timer timers[T_COUNT];

@@ -260,6 +260,42 @@ k_step_reduce_bins(int64_t nlist, const int *__restrict__ list, const uint8_t *_
         if(ti == 1) atomicAdd(nbad, 1ull);
     }
 }
+// find_hydro_timesteps timestep.c:617-693 for gas: Courant and smoothing-length criteria
+// (get_timestep_hydro_dloga :1075-1117), get_timebin_from_dti :166-182, clamp to the gravity bin.
+// cnt[0] bad steps, cnt[1] smallest new bin (atomicMin).
+__global__ void __launch_bounds__(256)
+k_step_hydro_bins(int64_t nlist, const int *__restrict__ list, const uint8_t *__restrict__ type, const uint8_t *__restrict__ flags,
+                  const double *__restrict__ hsml, const double *__restrict__ dthsml, const double *__restrict__ maxsig,
+                  const uint8_t *__restrict__ bin_grav, uint8_t *__restrict__ bin_hydro, StepTimeline T, double atime, double hubble, double fac3,
+                  double CourantFac, double MinSizeTimestep, long long dti_max, long long Ti, unsigned long long *__restrict__ cnt)
+{
+    const int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(q >= nlist) return;
+    const int64_t i = list ? list[q] : q;
+    if((flags[i] & 3) || type[i] != 0) return;
+    double dt = 2 * CourantFac * atime * hsml[i] / (fac3 * maxsig[i]);
+    const double dt_hsml = CourantFac * atime * atime * fabs(hsml[i] / (dthsml[i] + 1e-20));
+    if(dt_hsml < dt) dt = dt_hsml;
+    double dloga = dt * hubble;
+    long long dti = 0;                                                     // convert_timestep_to_ti :1155-1173
+    if(dti_max != 0) {
+        if(dloga < MinSizeTimestep) dloga = MinSizeTimestep;
+        dti = dev_ti_from_loga(T, dloga + T.now) - T.ti_now;
+        if(dti > dti_max || dti < 0) dti = dti_max;
+    }
+    int bin = 0;
+    if(dti > 1) {
+        if(dti > (1ll << TB)) dti = 1ll << TB;
+        bin = 63 - __clzll(dti);
+    }
+    const int binold = bin_hydro[i];
+    if(bin > binold)
+        while(!bin_active(bin, Ti) && bin > binold && bin > 1) bin--;
+    if(bin > bin_grav[i]) bin = bin_grav[i];
+    if(bin < 1) atomicAdd(&cnt[0], 1ull);
+    if(bin_active(binold, Ti) && bin_active(bin, Ti)) bin_hydro[i] = (uint8_t) bin;
+    atomicMin(&cnt[1], (unsigned long long) bin);
+}
 // |FullTreeGravAccel + GravPM| for the relative opening criterion, gravshort.h:69-86
 __global__ void __launch_bounds__(256)
 k_step_oldacc(int64_t n, const double *__restrict__ fullacc, const double *__restrict__ gravpm, double *__restrict__ oldacc)
@@ -366,7 +402,7 @@ int step_set_state(Engine *E, const b200_step_state *s)
     if(s->flags) CK(cudaMemcpyAsync(E->flags.p, s->flags, E->n, cudaMemcpyHostToDevice, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     E->st_state = true;
-    E->st_store_valid = false;
+    E->st_store_valid = false; E->st_maxsig_valid = false;
     if(s->BoxSize > 0) E->st_box = s->BoxSize;
     E->st_have_gas = s->hsml != nullptr;
     E->st_nact = E->n; E->st_act_implicit = true; E->st_nsub = 0;
@@ -386,6 +422,7 @@ int step_get_state(Engine *E, b200_step_state_out *o)
     if(o->hsml) CK(cudaMemcpyAsync(o->hsml, E->s_hsml.p, n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
     if(o->entropy) CK(cudaMemcpyAsync(o->entropy, E->s_entropy.p, n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
     if(o->bin_grav) CK(cudaMemcpyAsync(o->bin_grav, E->s_bin_grav.p, n, cudaMemcpyDeviceToHost, E->stream));
+    if(o->bin_hydro) CK(cudaMemcpyAsync(o->bin_hydro, E->s_bin_hydro.p, n, cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     return 0;
 }
@@ -758,10 +795,49 @@ int step_hier_timesteps(Engine *E, const b200_step_params *sp, b200_gravshort_pa
     return 0;
 }
 
+// find_hydro_timesteps timestep.c:617-738 on the current active list (gas; black holes not supported).
+// maxsig: host array SphP[].MaxSignalVel by particle index, or NULL to use the one b200_hydro_force left on the device.
+int step_hydro_timesteps(Engine *E, const b200_step_params *sp, b200_step_times *t, const double *maxsig, double atime, double hubble, int64_t *nbad)
+{
+    if(int rc = step_need_state(E, "b200_step_hydro_timesteps")) return rc;
+    if(!sp || !t || !sp->sync_loga || sp->nsync < 2) return failmsg(E, "b200_step_hydro_timesteps: null argument / timeline missing");
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->st_sync.ensure((size_t) sp->nsync)); CK(E->st_cnt.ensure(1 + 6 * NBIN)); CK(E->st_maxsig.ensure(n));
+    CK(cudaMemcpyAsync(E->st_sync.p, sp->sync_loga, sp->nsync * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    if(maxsig) { CK(cudaMemcpyAsync(E->st_maxsig.p, maxsig, E->n * sizeof(double), cudaMemcpyHostToDevice, E->stream)); E->st_maxsig_valid = true; }
+    if(!E->st_maxsig_valid) return failmsg(E, "b200_step_hydro_timesteps: no MaxSignalVel (pass it, or run b200_hydro_force with the step state set)");
+    const unsigned long long init[2] = {0ull, (unsigned long long) TB};
+    CK(cudaMemcpyAsync(E->st_cnt.p, init, sizeof(init), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));           // init is a stack array
+    StepTimeline T;
+    T.sync = E->st_sync.p; T.nsync = (int) sp->nsync;
+    T.now = tl_loga_from_ti(sp, t->Ti_Current); T.ti_now = tl_ti_from_loga(sp, T.now);
+    const double fac3 = pow(atime, 3 * (1 - 5.0 / 3) / 2.0);              // GAMMA = 5/3, physconst.h
+    const int64_t nl = E->st_nact;
+    if(nl > 0) {
+        k_step_hydro_bins<<<grid_for(nl), 256, 0, E->stream>>>(nl, E->st_act_implicit ? nullptr : E->st_act.p, E->type.p, E->flags.p, E->s_hsml.p,
+            E->s_dthsml.p, E->st_maxsig.p, E->s_bin_grav.p, E->s_bin_hydro.p, T, atime, hubble, fac3, sp->CourantFac, sp->MinSizeTimestep,
+            (long long) t->PM_length, (long long) t->Ti_Current, E->st_cnt.p);
+        CKL(E);
+    }
+    unsigned long long h[2];
+    CK(cudaMemcpyAsync(h, E->st_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    int mTimeBin = (int) h[1];
+    if(!host_bin_active(mTimeBin, t->Ti_Current)) {                        // :713-719
+        mTimeBin = t->mintimebin;
+        if(host_bin_active(mTimeBin + 1, t->Ti_Current)) mTimeBin++;
+    }
+    t->mintimebin = mTimeBin;                                              // :727-731
+    if(t->mintimebin > t->mingravtimebin && t->mingravtimebin > 0) t->mintimebin = t->mingravtimebin;
+    if(nbad) *nbad = (int64_t) h[0];
+    return 0;
+}
+
 void step_release(Engine *E)
 {
     E->st_iota.release(); E->st_listA.release(); E->st_listB.release(); E->st_act.release(); E->st_flag.release();
-    E->st_store.release(); E->st_lower.release(); E->st_sync.release(); E->st_part.release(); E->st_tab.release(); E->st_cnt.release();
+    E->st_store.release(); E->st_lower.release(); E->st_sync.release(); E->st_part.release(); E->st_tab.release(); E->st_cnt.release(); E->st_maxsig.release();
 }
 
 } // namespace b200
@@ -793,6 +869,12 @@ int b200_step_half_kick(b200_ctx *ctx, const double *gravkick, const double *hyd
     return step_half_kick(E, gravkick, hydrokick, dt_entr, Ti_Current, atime, MaxGasVel, hydro_only);
 }
 int b200_step_pm_kick(b200_ctx *ctx, double Fgravkick) { STEP_ENTER(ctx); return step_pm_kick(E, Fgravkick); }
+int b200_step_hydro_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel, double atime,
+                              double hubble, int64_t *nbad)
+{
+    STEP_ENTER(ctx);
+    return step_hydro_timesteps(E, sp, times, maxsignalvel, atime, hubble, nbad);
+}
 int b200_step_hier_accelerations(b200_ctx *ctx, const b200_step_params *sp, b200_gravshort_params *gp, b200_step_times *times, int64_t ngrav)
 {
     STEP_ENTER(ctx);

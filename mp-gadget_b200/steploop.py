@@ -22,7 +22,7 @@ class StepState(C.Structure):
 
 
 class StepStateOut(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("pos", "vel", "fullacc", "hsml", "entropy", "bin_grav")]
+    _fields_ = [(k, C.c_void_p) for k in ("pos", "vel", "fullacc", "hsml", "entropy", "bin_grav", "bin_hydro")]
 
 
 class StepTimes(C.Structure):
@@ -37,7 +37,7 @@ KICKFN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int64, C.c_int64)
 
 class StepParams(C.Structure):
     _fields_ = [("ErrTolIntAccuracy", C.c_double), ("MaxSizeTimestep", C.c_double), ("MinSizeTimestep", C.c_double),
-                ("MaxRMSDisplacementFac", C.c_double), ("softening", C.c_double), ("omega_type", C.c_double * 6), ("RhoCrit", C.c_double),
+                ("MaxRMSDisplacementFac", C.c_double), ("CourantFac", C.c_double), ("softening", C.c_double), ("omega_type", C.c_double * 6), ("RhoCrit", C.c_double),
                 ("FastParticleType", C.c_int32), ("pad_", C.c_int32), ("sync_loga", C.c_void_p), ("nsync", C.c_int64),
                 ("gravkick_factor", KICKFN), ("user", C.c_void_p)]
 
@@ -54,7 +54,7 @@ class StepEngine:
     """Same interface as oracle.ref.RefStep / oracle.step.StepOracle, running on a b200 Engine."""
 
     def __init__(self, engine, sync_loga, factor, hubble, Omega0=0.288, OmegaBaryon=0.0472, Hubble=0.1, G=43.0071,
-                 ErrTolIntAccuracy=0.02, MaxGasVel=3e5, MaxSizeTimestep=0.1, MinSizeTimestep=0.0, MaxRMSDisplacementFac=0.2, **_):
+                 ErrTolIntAccuracy=0.02, MaxGasVel=3e5, MaxSizeTimestep=0.1, MinSizeTimestep=0.0, MaxRMSDisplacementFac=0.2, CourantFac=0.15, **_):
         self.e, self.L, self.ctx = engine, engine.L, engine.ctx
         self.sync = np.ascontiguousarray(sync_loga, np.float64)
         self.factor, self.hubble = factor, hubble
@@ -65,6 +65,7 @@ class StepEngine:
         om = [OmegaBaryon, Omega0 - OmegaBaryon, 0.0, Omega0 - OmegaBaryon, OmegaBaryon, OmegaBaryon]       # timestep.c:1251-1263
         for k in range(6):
             sp.omega_type[k] = om[k]
+        sp.CourantFac = CourantFac
         sp.RhoCrit = 3 * Hubble * Hubble / (8 * np.pi * G)
         sp.FastParticleType = 2
         sp.sync_loga = self.sync.ctypes.data; sp.nsync = len(self.sync)
@@ -125,7 +126,7 @@ class StepEngine:
     def get(self):
         n = self.n
         out = dict(pos=np.zeros((n, 3)), vel=np.zeros((n, 3)), fullacc=np.zeros((n, 3)), hsml=np.zeros(n), entropy=np.zeros(n),
-                   bin_grav=np.zeros(n, np.uint8))
+                   bin_grav=np.zeros(n, np.uint8), bin_hydro=np.zeros(n, np.uint8))
         so = StepStateOut(**{k: v.ctypes.data for k, v in out.items()})
         self._ck(self.L.b200_step_get_state(self.ctx, C.byref(so)))
         return out
@@ -192,6 +193,14 @@ class StepEngine:
                     t.Ti_kick[b] += dti_from_timebin(b) // 2
             for b in range(1, t.mintimebin):
                 t.Ti_kick[b] += dti_from_timebin(t.mintimebin) // 2
+
+    def hydro_timesteps(self, maxsig, atime, first=False):
+        """find_hydro_timesteps on the current active list -> (bad count, TimeBinHydro[n])"""
+        ms = _c(maxsig, np.float64)
+        nbad = C.c_int64()
+        self._ck(self.L.b200_step_hydro_timesteps(self.ctx, C.byref(self.sp), C.byref(self.t), _p(ms), C.c_double(atime),
+                                                  C.c_double(float(self.hubble(atime))), C.byref(nbad)))
+        return int(nbad.value), self.get()["bin_hydro"]
 
     # --- hierarchy
     def set_gravity(self, par, G, nmesh, asmth):

@@ -136,6 +136,7 @@ typedef struct oracle_times {                                                   
 typedef struct oracle_step_params {                                                         /* TimestepParams timestep.c:21-47 */
     double ErrTolIntAccuracy, MaxGasVel, MaxSizeTimestep, MinSizeTimestep, MaxRMSDisplacementFac;
     double softening;                                                                       /* FORCE_SOFTENING() */
+    double CourantFac;
 } oracle_step_params;
 double oracle_loga_from_ti(const oracle_timeline *tl, int64_t ti);
 int64_t oracle_ti_from_loga(const oracle_timeline *tl, double loga);
@@ -164,6 +165,9 @@ int oracle_gravity_timebin(const oracle_timeline *tl, const double *acc, const d
 int64_t oracle_pm_timestep_ti(const oracle_timeline *tl, const oracle_cosmo *c, const oracle_step_params *sp, const oracle_times *t,
                               int64_t n, const double *vel, const float *mass, const uint8_t *type, const uint8_t *flags,
                               double atime, int FastParticleType, double asmth);
+int oracle_hydro_timebins(const oracle_timeline *tl, const oracle_step_params *sp, oracle_times *t, const int32_t *list, int64_t nlist,
+                          const uint8_t *type, const uint8_t *flags, const double *hsml, const double *dthsml, const double *maxsig,
+                          const uint8_t *bin_grav, uint8_t *bin_hydro, double atime, double hubble);
 int oracle_hier_accelerations(const oracle_timeline *tl, const oracle_cosmo *c, const oracle_step_params *sp, oracle_gravshort_params *gp,
                               oracle_times *t, int64_t n, const double *pos, const float *mass, const uint8_t *type, const uint8_t *flags,
                               double *vel, double *fullacc, const double *gravpm, const uint8_t *bin_grav,

@@ -268,6 +268,42 @@ int oracle_gravity_timebin(const oracle_timeline *tl, const double *acc, const d
     return bin;
 }
 
+/* find_hydro_timesteps timestep.c:617-738 for gas (with get_timestep_hydro_dloga :1075-1117 and
+ * get_timebin_from_dti :166-182): Courant and smoothing-length criteria -> TimeBinHydro of the listed gas
+ * particles, then the new minimum time bin.  Returns the bad-step count. */
+int oracle_hydro_timebins(const oracle_timeline *tl, const oracle_step_params *sp, oracle_times *t, const int32_t *list, int64_t nlist,
+                          const uint8_t *type, const uint8_t *flags, const double *hsml, const double *dthsml, const double *maxsig,
+                          const uint8_t *bin_grav, uint8_t *bin_hydro, double atime, double hubble)
+{
+    const int64_t dti_max = t->PM_length;
+    const double fac3 = pow(atime, 3 * (1 - 5.0 / 3) / 2.0);
+    int bad = 0, mTimeBin = TB;
+    for(int64_t q = 0; q < nlist; q++) {
+        const int64_t i = list ? list[q] : q;
+        if(flags && (flags[i] & 3)) continue;
+        if(type[i] != 0) continue;                                         /* type 5 needs the black-hole slots: not supported */
+        double dt = 2 * sp->CourantFac * atime * hsml[i] / (fac3 * maxsig[i]);
+        const double dt_hsml = sp->CourantFac * atime * atime * fabs(hsml[i] / (dthsml[i] + 1e-20));
+        if(dt_hsml < dt) dt = dt_hsml;
+        const int64_t dti = round_down_pow2(oracle_convert_timestep(tl, dt * hubble, dti_max, t->Ti_Current, sp->MinSizeTimestep));
+        int bin = bin_of_dti(dti);
+        const int binold = bin_hydro[i];
+        if(bin > binold)
+            while(!oracle_is_timebin_active(bin, t->Ti_Current) && bin > binold && bin > 1) bin--;
+        if(bin > bin_grav[i]) bin = bin_grav[i];
+        if(bin < 1) bad++;
+        if(oracle_is_timebin_active(binold, t->Ti_Current) && oracle_is_timebin_active(bin, t->Ti_Current)) bin_hydro[i] = (uint8_t) bin;
+        if(bin < mTimeBin) mTimeBin = bin;
+    }
+    if(!oracle_is_timebin_active(mTimeBin, t->Ti_Current)) {               /* :713-719 */
+        mTimeBin = t->mintimebin;
+        if(oracle_is_timebin_active(mTimeBin + 1, t->Ti_Current)) mTimeBin++;
+    }
+    t->mintimebin = mTimeBin;                                              /* :727-731 */
+    if(t->mintimebin > t->mingravtimebin && t->mingravtimebin > 0) t->mintimebin = t->mingravtimebin;
+    return bad;
+}
+
 /* get_long_range_timestep_dloga + get_PM_timestep_ti timestep.c:1201-1298 (no neutrinos) */
 int64_t oracle_pm_timestep_ti(const oracle_timeline *tl, const oracle_cosmo *c, const oracle_step_params *sp, const oracle_times *t,
                               int64_t n, const double *vel, const float *mass, const uint8_t *type, const uint8_t *flags,

@@ -180,7 +180,7 @@ class RefStep(Ref):
         ts = np.array([ErrTolIntAccuracy, MaxGasVel, MaxSizeTimestep, MinSizeTimestep, MaxRMSDisplacementFac, CourantFac])
         self.cosmo = dict(Omega0=Omega0, OmegaBaryon=OmegaBaryon, Hubble=Hubble, G=G)
         self.tspar = dict(ErrTolIntAccuracy=ErrTolIntAccuracy, MaxGasVel=MaxGasVel, MaxSizeTimestep=MaxSizeTimestep,
-                          MinSizeTimestep=MinSizeTimestep, MaxRMSDisplacementFac=MaxRMSDisplacementFac)
+                          MinSizeTimestep=MinSizeTimestep, MaxRMSDisplacementFac=MaxRMSDisplacementFac, CourantFac=CourantFac)
         self.sync_loga = np.log(np.unique(np.concatenate([[TimeIC, TimeMax], out[(out >= TimeIC) & (out <= TimeMax)]])))
         rc = L.ref_step_init(C.c_double(TimeIC), C.c_double(TimeMax), C.c_int(len(out)), _p(out), C.c_double(Omega0),
                              C.c_double(OmegaBaryon), C.c_double(Hubble), C.c_double(G), _p(ts))
@@ -246,6 +246,12 @@ class RefStep(Ref):
     def kick(self, kind, atime=1.0):
         """0 apply_half_kick, 1 apply_hydro_half_kick, 2 apply_PM_half_kick, 3 update_kick_times"""
         self.L.ref_step_kick(C.c_int(kind), C.c_double(atime))
+
+    def hydro_timesteps(self, maxsig, atime, first=False):
+        """find_hydro_timesteps on the current active list -> (bad count, TimeBinHydro[n])"""
+        out = np.zeros(self.n, np.uint8)
+        bad = int(self.L.ref_step_hydro_timesteps(_p(np.ascontiguousarray(maxsig, np.float64)), C.c_double(atime), C.c_int(1 if first else 0), _p(out)))
+        return bad, out
 
     def set_gravity(self, par, G, nmesh, asmth):
         self.L.ref_step_set_gravity(C.c_double(G), C.c_int(nmesh), C.c_double(asmth), C.c_double(par["ErrTolForceAcc"]),

@@ -695,6 +695,16 @@ void ref_step_kick(int kind, double atime)
     else if(kind == 2) apply_PM_half_kick(&stepCP, &stepT);
     else update_kick_times(&stepT);
 }
+/* find_hydro_timesteps (timestep.c:617-738) on the current active list; maxsig[n] = SphP[].MaxSignalVel
+ * (entries of non-gas particles ignored).  Returns the bad-step count; bin_hydro_out[n] = P[].TimeBinHydro. */
+int ref_step_hydro_timesteps(const double *maxsig, double atime, int first, unsigned char *bin_hydro_out)
+{
+    const int64_t n = PartManager->NumPart;
+    for(int64_t i = 0; i < n; i++) if(P[i].Type == 0) SPHP(i).MaxSignalVel = maxsig[i];
+    const int bad = find_hydro_timesteps(&stepAct, &stepT, atime, &stepCP, first);
+    for(int64_t i = 0; i < n; i++) bin_hydro_out[i] = P[i].TimeBinHydro;
+    return bad;
+}
 /* Short-range gravity parameters of the hierarchy (as ref_grav_short_tree above) */
 void ref_step_set_gravity(double G, int Nmesh, double Asmth, double ErrTolForceAcc, double BHOpeningAngle,
                           double MaxBHOpeningAngle, int TreeUseBH, double Rcut, double GravitySoftening)

@@ -24,7 +24,8 @@ class Times(C.Structure):
 
 class StepParams(C.Structure):
     _fields_ = [("ErrTolIntAccuracy", C.c_double), ("MaxGasVel", C.c_double), ("MaxSizeTimestep", C.c_double),
-                ("MinSizeTimestep", C.c_double), ("MaxRMSDisplacementFac", C.c_double), ("softening", C.c_double)]
+                ("MinSizeTimestep", C.c_double), ("MaxRMSDisplacementFac", C.c_double), ("softening", C.c_double),
+                ("CourantFac", C.c_double)]
 
 
 def _p(a):
@@ -55,12 +56,12 @@ def dti_from_timebin(b):
 
 class StepOracle:
     def __init__(self, sync_loga, Omega0=0.288, OmegaBaryon=0.0472, Hubble=0.1, G=43.0071, ErrTolIntAccuracy=0.02, MaxGasVel=3e5,
-                 MaxSizeTimestep=0.1, MinSizeTimestep=0.0, MaxRMSDisplacementFac=0.2, **_):
+                 MaxSizeTimestep=0.1, MinSizeTimestep=0.0, MaxRMSDisplacementFac=0.2, CourantFac=0.15, **_):
         self.L = _lib()
         self.sync = np.ascontiguousarray(sync_loga, np.float64)
         self.tl = Timeline(len(self.sync), self.sync.ctypes.data_as(C.POINTER(C.c_double)))
         self.cosmo = Cosmo(Omega0, OmegaBaryon, Hubble, G)
-        self.sp = StepParams(ErrTolIntAccuracy, MaxGasVel, MaxSizeTimestep, MinSizeTimestep, MaxRMSDisplacementFac, 0.0)
+        self.sp = StepParams(ErrTolIntAccuracy, MaxGasVel, MaxSizeTimestep, MinSizeTimestep, MaxRMSDisplacementFac, 0.0, CourantFac)
         self.t = Times()
         self.act = None
         self.counts = None
@@ -170,6 +171,14 @@ class StepOracle:
             t.PM_kick = tiend
         else:
             self.L.oracle_update_kick_times(C.byref(t))
+
+    def hydro_timesteps(self, maxsig, atime, first=False):
+        ms = np.ascontiguousarray(maxsig, np.float64)
+        nl = self.n if self.act is None else len(self.act)
+        bad = self.L.oracle_hydro_timebins(C.byref(self.tl), C.byref(self.sp), C.byref(self.t), _p(self.act), C.c_int64(nl), _p(self.type),
+                                           _p(self.flags), _p(self.hsml), _p(self.dthsml), _p(ms), _p(self.bin_grav), _p(self.bin_hydro),
+                                           C.c_double(atime), C.c_double(float(self.hubble(atime))))
+        return int(bad), self.bin_hydro.copy()
 
     # --- hierarchy
     def set_gravity(self, par, G, nmesh, asmth):

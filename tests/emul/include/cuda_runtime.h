@@ -58,6 +58,12 @@ static inline void __syncthreads(void)
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long) v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while(v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 extern double emul_xchg[1024];
 static inline double __shfl_xor_sync(unsigned, double v, int o)      /* every thread of the block takes part */
 {

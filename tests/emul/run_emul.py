@@ -40,7 +40,7 @@ def main(which):
     SL = importlib.import_module("mp-gadget_b200.steploop")
     O = TS.make_oracle()
     cosmo = {k: float(TS.GOLD["cosmo/" + k]) for k in ("Omega0", "OmegaBaryon", "Hubble", "G")}
-    ts = {k: float(TS.GOLD["tspar/" + k]) for k in ("ErrTolIntAccuracy", "MaxGasVel", "MaxSizeTimestep", "MinSizeTimestep", "MaxRMSDisplacementFac")}
+    ts = {k: float(TS.GOLD["tspar/" + k]) for k in TS.TSKEYS}
     S = SL.StepEngine(EmulEngine(), TS.GOLD["sync_loga"], O.factor, O.hubble, **cosmo, **ts)
     if which in ("primitives", "all"):
         out = SC.run_primitives(S, SC.primitives_inputs())

@@ -40,7 +40,8 @@ def primitives_inputs(seed=7, n=1536, box=4000.0):
     return dict(pos=pos, vel=vel, type=typ, flags=flags, mass=mass, bin_grav=bin_grav, bin_hydro=bin_hydro, hsml=hsml, dthsml=dthsml,
                 fullacc=3.0 * rng.standard_normal((n, 3)), gravpm=2.0 * rng.standard_normal((n, 3)),
                 hydroacc=np.where(gas[:, None], 5.0 * rng.standard_normal((n, 3)), 0.0),
-                entropy=np.where(gas, 1.0 + rng.random(n), 0.0), dtentropy=np.where(gas, 0.3 * rng.standard_normal(n), 0.0), box=box)
+                entropy=np.where(gas, 1.0 + rng.random(n), 0.0), dtentropy=np.where(gas, 0.3 * rng.standard_normal(n), 0.0), box=box,
+                maxsig=np.where(gas, 50.0 * 2.0 ** rng.uniform(-3, 3, n), 0.0))
 
 
 def primitives_times(pm=False):
@@ -92,6 +93,11 @@ def run_primitives(S, d):
     out["pmkick_vel"] = S.get()["vel"].copy(); out["pmkick_times"] = S.get_times()[0].copy()
     S.kick(3)
     out["kick_times"] = S.get_times()[1].copy()
+    # hydro time bins of the active gas (find_hydro_timesteps)
+    scal, kick, last = primitives_times()
+    _load(S, d); S.set_times(scal, kick, last); S.build_active()
+    bad, bh = S.hydro_timesteps(d["maxsig"], atime)
+    out["hydro_bad"] = np.int64(bad); out["hydro_bins"] = np.array(bh, np.uint8); out["hydro_times"] = S.get_times()[0].copy()
     # PM step: implicit list
     scal, kick, last = primitives_times(pm=True)
     _load(S, d); S.set_times(scal, kick, last)

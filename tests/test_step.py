@@ -16,12 +16,13 @@ sys.path.insert(0, HERE)
 import step_scenarios as SC          # noqa: E402
 
 GOLD = np.load(os.path.join(HERE, "golden", "ref_step.npz"))
+TSKEYS = ("ErrTolIntAccuracy", "MaxGasVel", "MaxSizeTimestep", "MinSizeTimestep", "MaxRMSDisplacementFac", "CourantFac")
 RTOL = 2e-14          # the two sides differ only by the compiler's re-association (-ffast-math in the reference build)
 
 
 def make_oracle():
     cosmo = {k: float(GOLD["cosmo/" + k]) for k in ("Omega0", "OmegaBaryon", "Hubble", "G")}
-    ts = {k: float(GOLD["tspar/" + k]) for k in ("ErrTolIntAccuracy", "MaxGasVel", "MaxSizeTimestep", "MinSizeTimestep", "MaxRMSDisplacementFac")}
+    ts = {k: float(GOLD["tspar/" + k]) for k in TSKEYS}
     return OS.StepOracle(GOLD["sync_loga"], **cosmo, **ts)
 
 
@@ -33,7 +34,7 @@ def close(a, b, rtol=RTOL):
 
 def check_primitives(out, gold=GOLD, rtol=RTOL):
     for k in ("active", "active_counts", "last_drift", "sublist36", "sublist37", "sublist41", "pmkick_times", "kick_times",
-              "pm_active_counts", "pm_sublist38"):
+              "pm_active_counts", "pm_sublist38", "hydro_bad", "hydro_bins", "hydro_times"):
         assert np.array_equal(out[k], gold["prim/" + k]), k
     for k in ("ddrift", "drift_pos", "drift_hsml", "halfkick_vel", "halfkick_entropy", "hydrokick_vel", "hydrokick_entropy", "pmkick_vel"):
         assert close(out[k], gold["prim/" + k], rtol), k
@@ -70,6 +71,9 @@ def test_oracle_primitives_equal_reference():
     assert np.isclose(GOLD["prim/drift_hsml"][gas].max(), d["box"] / 2)                       # the Hsml cap
     cap = float(GOLD["tspar/MaxGasVel"]) * np.exp(make_oracle().loga_from_ti(int(SC.primitives_times()[0][3])))
     assert np.isclose(np.linalg.norm(GOLD["prim/halfkick_vel"][gas], axis=1), cap, rtol=1e-12).any()          # the velocity cap acted
+    hb = GOLD["prim/hydro_bins"]; act = GOLD["prim/active"]
+    changed = hb[act] != d["bin_hydro"][act]
+    assert changed.sum() > 50 and len(np.unique(hb[act][gas[act]])) >= 4                       # hydro bins really re-assigned
     assert 0 < len(GOLD["prim/sublist36"]) < len(GOLD["prim/sublist37"]) < len(GOLD["prim/active"]) < len(d["mass"])
 
 

@@ -29,7 +29,7 @@ def stepper(b200):
     SL = importlib.import_module("mp-gadget_b200.steploop")
     O = TS.make_oracle()             # the checker also supplies the cosmology callables (the reference host's cosmology.c / timefac.c)
     cosmo = {k: float(TS.GOLD["cosmo/" + k]) for k in ("Omega0", "OmegaBaryon", "Hubble", "G")}
-    ts = {k: float(TS.GOLD["tspar/" + k]) for k in ("ErrTolIntAccuracy", "MaxGasVel", "MaxSizeTimestep", "MinSizeTimestep", "MaxRMSDisplacementFac")}
+    ts = {k: float(TS.GOLD["tspar/" + k]) for k in TS.TSKEYS}
     S = SL.StepEngine(e, TS.GOLD["sync_loga"], O.factor, O.hubble, **cosmo, **ts)
     yield S
     e.close()
