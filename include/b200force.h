@@ -371,6 +371,8 @@ int b200_step_drift(b200_ctx *ctx, double ddrift, const double *shift, int64_t *
  * NumActiveHydro}; bincounts[6][B200_TIMEBINS + 1] = TimeBinCountType (may be NULL); nhydro_slots =
  * SlotsManager->info[0].size + info[5].size (what the PM branch reports as NumActiveHydro). */
 int b200_step_build_active(b200_ctx *ctx, int64_t Ti_Current, int is_pm, int64_t nhydro_slots, int64_t *counts, int64_t *bincounts);
+/* The host's own ActiveParticles list (ascending particle indices) as the current list; NULL = every particle. */
+int b200_step_set_active(b200_ctx *ctx, const int32_t *list, int64_t nlist);
 /* build_active_sublist of the current active list */
 int b200_step_active_sublist(b200_ctx *ctx, int maxtimebin, int64_t Ti_Current, int64_t *nsub);
 /* which = 0: the active list (*nout = -1 - n when it is implicit), 1: the last sub-list */
@@ -389,6 +391,11 @@ int b200_step_hydro_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_st
  * gp->TreeUseBH > 1 is reset to 0 after the first walk like TreeParams.TreeUseBH */
 int b200_step_hier_accelerations(b200_ctx *ctx, const b200_step_params *sp, b200_gravshort_params *gp,
                                  b200_step_times *times, int64_t ngrav);
+/* StoredGravAccel of the last b200_step_hier_accelerations -> host [n][3] (0 for particles it did not walk) */
+int b200_step_get_store(b200_ctx *ctx, double *out);
+/* ... and the way back: the host's StoredGravAccel.GravAccel (timestep.h:92-96) for b200_step_hier_timesteps
+ * after a new b200_step_set_state; NULL = none, the drivers then use FullTreeGravAccel as the reference does */
+int b200_step_set_store(b200_ctx *ctx, const double *in);
 /* hierarchical_gravity_and_timesteps; hubble = hubble_function(CP, atime);
  * info = {largest active bin, PM_length, bad-step count} */
 int b200_step_hier_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_gravshort_params *gp,

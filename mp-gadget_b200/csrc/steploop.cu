@@ -405,7 +405,7 @@ int step_set_state(Engine *E, const b200_step_state *s)
     E->st_store_valid = false; E->st_maxsig_valid = false;
     if(s->BoxSize > 0) E->st_box = s->BoxSize;
     E->st_have_gas = s->hsml != nullptr;
-    E->st_nact = E->n; E->st_act_implicit = true; E->st_nsub = 0;
+    E->st_nact = E->n; E->st_act_implicit = true; E->st_nsub = 0;      // the active list does not survive a new state
     E->sph_density_done = false;
     return 0;
 }
@@ -498,6 +498,44 @@ int step_active_sublist(Engine *E, int maxtimebin, int64_t Ti_Current, int64_t *
     if(int rc = step_sublist_of(E, E->st_act_implicit ? nullptr : E->st_act.p, E->st_nact, maxtimebin, Ti_Current, E->st_listA.p, &ns)) return rc;
     E->st_nsub = ns;
     if(nsub) *nsub = ns;
+    return 0;
+}
+
+// The host's ActiveParticles list (ascending particle indices) -> device; list == nullptr: every particle.
+int step_set_active(Engine *E, const int32_t *list, int64_t nlist)
+{
+    if(int rc = step_need_state(E, "b200_step_set_active")) return rc;
+    E->st_nsub = 0;
+    if(!list) { E->st_act_implicit = true; E->st_nact = E->n; return 0; }
+    if(nlist < 0 || nlist > E->n) return failmsg(E, "b200_step_set_active: bad list length");
+    CK(E->st_act.ensure((size_t) nlist + 1));
+    if(nlist > 0) CK(cudaMemcpyAsync(E->st_act.p, list, nlist * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    E->st_act_implicit = false; E->st_nact = nlist;
+    return 0;
+}
+
+// StoredGravAccel of the last b200_step_hier_accelerations, [n][3] (entries of particles it did not walk are 0)
+int step_get_store(Engine *E, double *out)
+{
+    if(int rc = step_need_state(E, "b200_step_get_store")) return rc;
+    if(!E->st_store_valid) return failmsg(E, "b200_step_get_store: no stored accelerations (run b200_step_hier_accelerations)");
+    if(!out || E->n == 0) return 0;
+    CK(cudaMemcpyAsync(out, E->st_store.p, 3 * (size_t) E->n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
+// StoredGravAccel from the host (struct grav_accel_store, timestep.h:92-96) for b200_step_hier_timesteps
+int step_set_store(Engine *E, const double *in)
+{
+    if(int rc = step_need_state(E, "b200_step_set_store")) return rc;
+    if(!in) { E->st_store_valid = false; return 0; }
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->st_store.ensure(3 * n));
+    CK(cudaMemcpyAsync(E->st_store.p, in, 3 * (size_t) E->n * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    E->st_store_valid = true;
     return 0;
 }
 
@@ -861,6 +899,9 @@ int b200_step_active_sublist(b200_ctx *ctx, int maxtimebin, int64_t Ti_Current, 
     STEP_ENTER(ctx);
     return step_active_sublist(E, maxtimebin, Ti_Current, nsub);
 }
+int b200_step_set_active(b200_ctx *ctx, const int32_t *list, int64_t nlist) { STEP_ENTER(ctx); return step_set_active(E, list, nlist); }
+int b200_step_set_store(b200_ctx *ctx, const double *in) { STEP_ENTER(ctx); return step_set_store(E, in); }
+int b200_step_get_store(b200_ctx *ctx, double *out) { STEP_ENTER(ctx); return step_get_store(E, out); }
 int b200_step_get_active(b200_ctx *ctx, int which, int32_t *out, int64_t *nout) { STEP_ENTER(ctx); return step_get_active(E, which, out, nout); }
 int b200_step_half_kick(b200_ctx *ctx, const double *gravkick, const double *hydrokick, const double *dt_entr, int64_t Ti_Current,
                         double atime, double MaxGasVel, int hydro_only)

@@ -154,6 +154,8 @@ def load(**kw):
 
 # the reference's own drift.c + timestep.c + timebinmgr.c on top of its tree gravity (step loop)
 SO_STEP = os.path.join(_HERE, "_ref", "libref_step.so")
+# the same, with the step-loop functions redirected (ld --wrap) to mp-gadget_b200/host/libgadget_step_shims.c -> GPU
+SO_DROPIN_STEP = os.path.join(_HERE, "_ref", "libref_dropin_step.so")
 NBINS = 47      # TIMEBINS + 1, timebinmgr.h:13
 
 
@@ -164,8 +166,8 @@ class RefStep(Ref):
 
     def __init__(self, TimeIC, TimeMax, outtimes=(), Omega0=0.288, OmegaBaryon=0.0472, Hubble=0.1, G=43.0071,
                  ErrTolIntAccuracy=0.02, MaxGasVel=3e5, MaxSizeTimestep=0.1, MinSizeTimestep=0.0,
-                 MaxRMSDisplacementFac=0.2, CourantFac=0.15, **kw):
-        super().__init__(so=SO_STEP, **kw)
+                 MaxRMSDisplacementFac=0.2, CourantFac=0.15, so=SO_STEP, **kw):
+        super().__init__(so=so, **kw)
         L = self.L
         L.ref_step_factor.restype = C.c_double
         L.ref_loga_from_ti.restype = C.c_double

@@ -54,5 +54,34 @@ def build(force=False):
     return SO
 
 
+DROPIN = os.path.join(OUT, "libref_dropin_step_emul.so")
+REF = "/root/reference"
+
+
+def build_dropin(force=False):
+    """The reference's own step-loop driver (oracle/ref_driver.c + its timestep.c, drift.c, tree gravity ...) with the
+    calls redirected by ld --wrap to mp-gadget_b200/host/libgadget_step_shims.c, linked against the EMULATION
+    library instead of libb200force.so.  Needs /root/reference; returns None without it."""
+    if not os.path.isdir(os.path.join(REF, "libgadget")):
+        return DROPIN if os.path.exists(DROPIN) else None
+    emul = build(force)
+    host = os.path.join(ROOT, "mp-gadget_b200", "host")
+    orc = os.path.join(ROOT, "oracle")
+    deps = [emul, os.path.join(host, "libgadget_step_shims.c"), os.path.join(host, "step_wrap.opts"), os.path.join(orc, "ref_driver.c")]
+    if not force and os.path.exists(DROPIN) and all(os.path.getmtime(d) <= os.path.getmtime(DROPIN) for d in deps):
+        return DROPIN
+    L = os.path.join(REF, "libgadget")
+    names = ["forcetree.c", "treewalk.c", "gravshort-tree.c", "gravity.c", "partmanager.c", "slotsmanager.c", "walltime.c", "utils/peano.c",
+             "utils/memory.c", "utils/mymalloc.c", "utils/openmpsort.c", "utils/endrun.c", "utils/system.c", "utils/string.c", "density.c",
+             "densitykernel.c", "hydra.c", "drift.c", "timestep.c", "timebinmgr.c"]         # SRCS_STEP of oracle/Makefile.ref
+    subprocess.check_call(["gcc", "-fopenmp", "-O3", "-g", "-ffast-math", "-fPIC", "-std=gnu11", "-w", "-Werror=implicit-function-declaration",
+                           "-I" + os.path.join(orc, "stubs"), "-I" + REF, "-I" + L, "-I" + os.path.join(REF, "depends", "bigfile", "src"),
+                           "-DREF_WITH_STEP", "-shared", "-o", DROPIN, os.path.join(orc, "ref_driver.c")] + [os.path.join(L, f) for f in names] +
+                          [os.path.join(host, "libgadget_step_shims.c"), os.path.join(host, "libgadget_shim_ctx.c"),
+                           "@" + os.path.join(host, "step_wrap.opts"), "-L" + OUT, "-lsteploop_emul", "-Wl,-rpath," + OUT, "-lm"])
+    return DROPIN
+
+
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_dropin(force=True))

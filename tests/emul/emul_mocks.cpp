@@ -69,6 +69,21 @@ int b200_set_particles_soa(b200_ctx *ctx, const double *pos, const float *mass, 
     for(int64_t i = 0; i < n; i++) { E->type.p[i] = type ? type[i] : 1; E->flags.p[i] = 0; E->oldacc.p[i] = 0; }
     return 0;
 }
+int b200_set_particles_aos(b200_ctx *ctx, const void *P, int64_t n, const b200_particle_layout *)
+{
+    // struct particle_data with the default layout (b200_default_particle_layout in csrc/capi.cu): stride 160,
+    // Pos 0, Mass 28, flag bits 36, Type 39
+    Engine *E = &ctx->e;
+    const size_t m = (size_t) (n > 0 ? n : 1);
+    E->n = n;
+    if(E->pos.ensure(3 * m) || E->mass.ensure(m) || E->type.ensure(m) || E->flags.ensure(m) || E->oldacc.ensure(m)) return failmsg(E, "emul: out of memory");
+    for(int64_t i = 0; i < n; i++) {
+        const uint8_t *r = (const uint8_t *) P + 160 * i;
+        memcpy(E->pos.p + 3 * i, r, 24); memcpy(E->mass.p + i, r + 28, 4);
+        E->flags.p[i] = r[36] & 3; E->type.p[i] = r[39]; E->oldacc.p[i] = 0;
+    }
+    return 0;
+}
 int b200_pm_init(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G)
 {
     Engine *E = &ctx->e;

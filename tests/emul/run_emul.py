@@ -36,7 +36,25 @@ class EmulEngine:
         assert self.L.b200_pm_init(self.ctx, C.c_double(box), C.c_double(asmth), C.c_int(nmesh), C.c_double(G)) == 0
 
 
+def dropin(which):
+    """The reference's own loop (oracle/ref_driver.c) with its step-loop calls redirected by ld --wrap to
+    mp-gadget_b200/host/libgadget_step_shims.c, which forwards to the emulated b200_step_*."""
+    from oracle import ref as R
+    so = EB.build_dropin()
+    if so is None:
+        print("skip: no /root/reference and no prebuilt drop-in library")
+        return
+    S = R.RefStep(nthreads=2, arena_gib=1.0, so=so, **SC.TIMELINE)
+    if which == "dropin_primitives":
+        TS.check_primitives(SC.run_primitives(S, SC.primitives_inputs()))
+    else:
+        TS.check_hierarchy(SC.run_hierarchy(S, SC.hierarchy_inputs()))
+    print(which + " ok")
+
+
 def main(which):
+    if which.startswith("dropin"):
+        return dropin(which)
     SL = importlib.import_module("mp-gadget_b200.steploop")
     O = TS.make_oracle()
     cosmo = {k: float(TS.GOLD["cosmo/" + k]) for k in ("Omega0", "OmegaBaryon", "Hubble", "G")}

@@ -11,9 +11,12 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("which", ["primitives", "hierarchy"])
+@pytest.mark.parametrize("which", ["primitives", "hierarchy", "dropin_primitives", "dropin_hierarchy"])
 def test_steploop_source_under_emulation(which):
+    """dropin_*: the reference's own loop with its calls redirected (ld --wrap) to host/libgadget_step_shims.c."""
     env = dict(os.environ, OMP_WAIT_POLICY="passive")          # 256 OS threads per emulated block: do not spin
     r = subprocess.run([sys.executable, os.path.join(HERE, "emul", "run_emul.py"), which], env=env, capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    if "skip:" in r.stdout:
+        pytest.skip(r.stdout.strip().splitlines()[-1])
     assert which + " ok" in r.stdout

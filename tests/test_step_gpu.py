@@ -47,3 +47,14 @@ def test_gpu_hierarchy_equals_reference(stepper):
     PM step bit-exact; positions / velocities to 1e-9 (GPU tree gravity agrees with the reference to ~1e-11)."""
     rec = SC.run_hierarchy(stepper, SC.hierarchy_inputs())
     TS.check_hierarchy(rec, rtol=1e-9)
+
+
+def test_gpu_dropin_step_shims(stepper):
+    """The reference's own loop with drift_all_particles, build_active_particles, the half kicks and the hierarchical
+    gravity drivers redirected (ld --wrap) to host/libgadget_step_shims.c -> GPU (oracle/_ref/libref_dropin_step.so)."""
+    from oracle import ref as R
+    if not os.path.exists(R.SO_DROPIN_STEP):
+        pytest.skip("oracle/_ref/libref_dropin_step.so not built")
+    S = R.RefStep(nthreads=2, arena_gib=1.0, so=R.SO_DROPIN_STEP, **SC.TIMELINE)
+    TS.check_primitives(SC.run_primitives(S, SC.primitives_inputs()))
+    TS.check_hierarchy(SC.run_hierarchy(S, SC.hierarchy_inputs()), rtol=1e-9)
