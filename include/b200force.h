@@ -383,6 +383,13 @@ int b200_step_half_kick(b200_ctx *ctx, const double *gravkick, const double *hyd
                         int64_t Ti_Current, double atime, double MaxGasVel, int hydro_only);
 /* apply_PM_half_kick: Vel += GravPM * Fgravkick (the caller advances PM_kick) */
 int b200_step_pm_kick(b200_ctx *ctx, double Fgravkick);
+/* Device-resident gas sub-step (run.c:466-495 between the active list and the kicks): b200_step_sph_prepare hands
+ * the current active list and the per-bin factor tables to the SPH module (the time bins are the ones already on the
+ * device), then b200_density / b200_hydro_force run as usual (output pointers may be NULL), then
+ * b200_step_adopt_hydro takes SphP[].HydroAccel / DtEntropy / MaxSignalVel of the listed gas from the device
+ * results, so that b200_step_half_kick and b200_step_hydro_timesteps (maxsignalvel = NULL) can follow. */
+int b200_step_sph_prepare(b200_ctx *ctx, const b200_sph_bins *tables);
+int b200_step_adopt_hydro(b200_ctx *ctx);
 /* find_hydro_timesteps (timestep.c:617-738) for the gas on the current active list: new P[].TimeBinHydro on
  * the device, times->mintimebin updated.  maxsignalvel[n] = SphP[].MaxSignalVel by particle index (host). */
 int b200_step_hydro_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel,

@@ -344,6 +344,29 @@ k_step_vel_stats(int64_t n, const double *__restrict__ vel, const float *__restr
     }
 }
 
+// ---- hand-over to / from the SPH module (sph.cu) without a host round trip ----
+__global__ void __launch_bounds__(256)
+k_step_mark_active(int64_t nlist, const int *__restrict__ list, uint8_t *__restrict__ active)
+{
+    const int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(q < nlist) active[list[q]] = 1;
+}
+// hydro_reduce / hydro_postprocess results (hydra.c:279-293,495-528) of the listed gas particles into the step state
+__global__ void __launch_bounds__(256)
+k_step_adopt_hydro(int64_t nlist, const int *__restrict__ list, const uint8_t *__restrict__ type, const uint8_t *__restrict__ flags,
+                   const double *__restrict__ acc, const double *__restrict__ dte, const double *__restrict__ maxsig,
+                   double *__restrict__ hydroacc, double *__restrict__ dtentropy, double *__restrict__ maxsig_out)
+{
+    const int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(q >= nlist) return;
+    const int64_t i = list ? list[q] : q;
+    if((flags[i] & 3) || type[i] != 0) return;
+#pragma unroll
+    for(int j = 0; j < 3; j++) hydroacc[3 * i + j] = acc[3 * i + j];
+    dtentropy[i] = dte[i];
+    maxsig_out[i] = maxsig[i];
+}
+
 // ---------------------------------------------------------------------------------------------
 static inline unsigned grid_for(int64_t n) { return (unsigned) ((n + 255) / 256); }
 static inline int64_t host_dti_of_bin(int bin) { return bin > 0 ? ((int64_t) 1 << bin) : 0; }
@@ -872,6 +895,44 @@ int step_hydro_timesteps(Engine *E, const b200_step_params *sp, b200_step_times 
     return 0;
 }
 
+// The current active list and the per-bin factor tables for b200_density / b200_hydro_force, the time bins being
+// the ones already on the device (what b200_sph_set_timebins + b200_sph_set_active do from host arrays).
+int step_sph_prepare(Engine *E, const b200_sph_bins *tables)
+{
+    if(int rc = step_need_state(E, "b200_step_sph_prepare")) return rc;
+    if(!tables) return failmsg(E, "b200_step_sph_prepare: null factor tables");
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->s_bins.ensure(5 * NBIN)); CK(E->s_active.ensure(n));
+    CK(cudaMemcpyAsync(E->s_bins.p, tables, 5 * NBIN * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    E->s_bins_set = true;
+    E->s_active_set = false;
+    if(!E->st_act_implicit) {
+        CK(cudaMemsetAsync(E->s_active.p, 0, n, E->stream));
+        if(E->st_nact > 0) { k_step_mark_active<<<grid_for(E->st_nact), 256, 0, E->stream>>>(E->st_nact, E->st_act.p, E->s_active.p); CKL(E); }
+        E->s_active_set = true;
+    }
+    CK(cudaStreamSynchronize(E->stream));      // `tables` may be a stack object of the caller
+    return 0;
+}
+// SphP[].HydroAccel / DtEntropy / MaxSignalVel of the listed gas <- the device results of the last b200_hydro_force
+int step_adopt_hydro(Engine *E)
+{
+    if(int rc = step_need_state(E, "b200_step_adopt_hydro")) return rc;
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    if(E->s_out3.cap < 3 * n || E->s_out1a.cap < n || E->s_out1b.cap < n) return failmsg(E, "b200_step_adopt_hydro: no hydro results on the device (run b200_hydro_force)");
+    CK(E->st_maxsig.ensure(n));
+    if(!E->st_maxsig_valid) CK(cudaMemsetAsync(E->st_maxsig.p, 0, n * sizeof(double), E->stream));
+    const int64_t nl = E->st_nact;
+    if(nl > 0) {
+        k_step_adopt_hydro<<<grid_for(nl), 256, 0, E->stream>>>(nl, E->st_act_implicit ? nullptr : E->st_act.p, E->type.p, E->flags.p,
+            E->s_out3.p, E->s_out1a.p, E->s_out1b.p, E->s_hydroacc.p, E->s_dtentropy.p, E->st_maxsig.p);
+        CKL(E);
+    }
+    CK(cudaStreamSynchronize(E->stream));
+    E->st_maxsig_valid = true;
+    return 0;
+}
+
 void step_release(Engine *E)
 {
     E->st_iota.release(); E->st_listA.release(); E->st_listB.release(); E->st_act.release(); E->st_flag.release();
@@ -910,6 +971,8 @@ int b200_step_half_kick(b200_ctx *ctx, const double *gravkick, const double *hyd
     return step_half_kick(E, gravkick, hydrokick, dt_entr, Ti_Current, atime, MaxGasVel, hydro_only);
 }
 int b200_step_pm_kick(b200_ctx *ctx, double Fgravkick) { STEP_ENTER(ctx); return step_pm_kick(E, Fgravkick); }
+int b200_step_sph_prepare(b200_ctx *ctx, const b200_sph_bins *tables) { STEP_ENTER(ctx); return step_sph_prepare(E, tables); }
+int b200_step_adopt_hydro(b200_ctx *ctx) { STEP_ENTER(ctx); return step_adopt_hydro(E); }
 int b200_step_hydro_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel, double atime,
                               double hubble, int64_t *nbad)
 {
