@@ -408,6 +408,17 @@ int b200_step_set_store(b200_ctx *ctx, const double *in);
 int b200_step_hier_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_gravshort_params *gp,
                              b200_step_times *times, int64_t ngrav, int is_pm, double atime, double hubble, int64_t *info);
 
+/* ---- Domain keys (first brick of the device-side domain decomposition) --------------------------------
+ * Status as the step loop above: compiled, emulation-checked against the reference's known-answer keys, hardware run pending. */
+/* PEANO(P[i].Pos, BoxSize) (libgadget/utils/peano.h:15-21, peano.c:108-129) of every particle set with
+ * b200_set_particles_*; keys stay on the device, keys_out (host, [n]) may be NULL. */
+int b200_domain_peano_keys(b200_ctx *ctx, double BoxSize, uint64_t *keys_out);
+/* DomainDecomp::TopNodes (libgadget/domain.h:20-33) as arrays: Daughter, StartKey, Shift, Leaf */
+int b200_domain_set_topnodes(b200_ctx *ctx, int32_t ntop, const int32_t *daughter, const uint64_t *startkey,
+                             const int32_t *shift, const int32_t *leaf);
+/* P[i].TopLeaf = domain_get_topleaf(key_i) (domain.h:71-78) from the keys of the last b200_domain_peano_keys */
+int b200_domain_topleaf(b200_ctx *ctx, int32_t *topleaf_out);
+
 /* Device-side timing of the phases of the last call, milliseconds (CUDA
  * events on the engine's stream).  Names follow the reference's walltime
  * categories (libgadget/walltime.c, gravshort-tree.c:134-144, petapm.c:280-355). */

@@ -98,6 +98,7 @@ EXPORTED = [
     "b200_step_set_state", "b200_step_get_state", "b200_step_adopt_forces", "b200_step_drift", "b200_step_build_active",
     "b200_step_active_sublist", "b200_step_get_active", "b200_step_half_kick", "b200_step_pm_kick",
     "b200_step_hier_accelerations", "b200_step_hier_timesteps", "b200_step_hydro_timesteps", "b200_step_set_active", "b200_step_get_store", "b200_step_set_store", "b200_step_sph_prepare", "b200_step_adopt_hydro",
+    "b200_domain_peano_keys", "b200_domain_set_topnodes", "b200_domain_topleaf",
 ]
 
 
@@ -354,6 +355,21 @@ class Engine:
         t = Timings()
         self.L.b200_get_timings(self.ctx, C.byref(t))
         return t.asdict()
+
+    # -- domain keys ---------------------------------------------------------
+    def peano_keys(self, box):
+        """PEANO(Pos, BoxSize) of every particle (utils/peano.h:15-21) -> uint64[n]"""
+        keys = np.zeros(max(self.n, 1), np.uint64)
+        self._ck(self.L.b200_domain_peano_keys(self.ctx, C.c_double(box), _p(keys)))
+        return keys[:self.n]
+
+    def topleaf(self, daughter, startkey, shift, leaf):
+        """domain_get_topleaf (domain.h:71-78) of every particle over TopNodes given as arrays (after peano_keys)"""
+        a = [_c(daughter, np.int32), _c(startkey, np.uint64), _c(shift, np.int32), _c(leaf, np.int32)]
+        self._ck(self.L.b200_domain_set_topnodes(self.ctx, C.c_int32(len(a[0])), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3])))
+        out = np.zeros(max(self.n, 1), np.int32)
+        self._ck(self.L.b200_domain_topleaf(self.ctx, _p(out)))
+        return out[:self.n]
 
     def kernel_launches(self):
         return int(self.L.b200_kernel_launches(self.ctx))

@@ -204,7 +204,7 @@ void b200_ctx_destroy(b200_ctx *ctx)
     E->nodeF.release(); E->nodeH.release(); E->nodeK.release(); E->scratch_i.release(); E->targets.release(); E->targets_sorted.release(); E->walk_flags.release();
     E->d_acc.release(); E->d_pot.release(); E->d_counts.release(); E->srtab.release();
     E->walk_pool.release(); E->walk_chunktab.release(); E->walk_cnt.release(); E->walk_partial.release();
-    step_release(E);
+    step_release(E); domain_release(E);
     for(int i = 0; i < T_COUNT; i++) if(E->timers[i].a) { cudaEventDestroy(E->timers[i].a); cudaEventDestroy(E->timers[i].b); }
     for(int i = 0; i < 65; i++) if(E->chunk_ev[i]) cudaEventDestroy(E->chunk_ev[i]);
     cudaStreamDestroy(E->copy_stream);

@@ -1,0 +1,156 @@
+// domain_keys.cu -- the keys of the reference's domain decomposition on the device (SURVEY.md 8f rank 2,
+// first brick): the Peano-Hilbert key of every particle (PEANO(), libgadget/utils/peano.h:15-21 over
+// peano_hilbert_key, utils/peano.c:108-129) and P[].TopLeaf = domain_get_topleaf(key) (libgadget/domain.h:71-78)
+// for a top tree handed in as arrays.  Integer work, bit-exact against the reference's own test vector
+// (tests/test_peano.c:107) and its compiled peano.c.
+//
+// The curve is stated geometrically and its state machine generated at first use (no stored tables): a state
+// is a symmetry of the cube applied to one base pattern -- octants in the Gray-code order
+// 000,010,110,100,101,111,011,001 (bits x,y,z) -- and the sub-cube visited r-th continues in the state composed
+// with the r-th of eight child symmetries (swap y,z | swap x,z twice | flip x,y twice | swap x,z + flip x,z twice |
+// swap y,z + flip y,z).  Both kernels are one thread per particle and HBM-bound (24 B in, 8 B out; 8 B in, 4 B out).
+#include <string.h>
+#include "engine.h"
+
+namespace b200 {
+
+#define PH_BITS 21               // BITS_PER_DIMENSION, peano.h:11
+
+struct CubeSym { int perm[3], flip[3]; };      // new bit k = old bit perm[k] ^ flip[k]
+static const int ph_base_order[8] = {0, 2, 6, 4, 5, 7, 3, 1};
+static const CubeSym ph_child[8] = {
+    {{0, 2, 1}, {0, 0, 0}}, {{2, 1, 0}, {0, 0, 0}}, {{2, 1, 0}, {0, 0, 0}}, {{0, 1, 2}, {1, 1, 0}},
+    {{0, 1, 2}, {1, 1, 0}}, {{2, 1, 0}, {1, 0, 1}}, {{2, 1, 0}, {1, 0, 1}}, {{0, 2, 1}, {0, 1, 1}}};
+
+static int ph_apply(const CubeSym &s, int pix)
+{
+    const int b[3] = {(pix >> 2) & 1, (pix >> 1) & 1, pix & 1};
+    return ((b[s.perm[0]] ^ s.flip[0]) << 2) | ((b[s.perm[1]] ^ s.flip[1]) << 1) | (b[s.perm[2]] ^ s.flip[2]);
+}
+// tab[0..383] = rank[state][octant], tab[384..767] = next[state][octant]; returns the number of states: 24, the
+// rotations reachable from the identity (the reference's tables also list their 24 mirror images, which the walk
+// from state 0 never enters)
+static int ph_tables(uint8_t *tab)
+{
+    CubeSym st[48];
+    int ns = 1;
+    st[0] = CubeSym{{0, 1, 2}, {0, 0, 0}};
+    for(int s = 0; s < ns; s++)
+        for(int r = 0; r < 8; r++) {
+            const int pix = ph_apply(st[s], ph_base_order[r]);
+            CubeSym c;
+            for(int k = 0; k < 3; k++) { c.perm[k] = ph_child[r].perm[st[s].perm[k]]; c.flip[k] = ph_child[r].flip[st[s].perm[k]] ^ st[s].flip[k]; }
+            int f = -1;
+            for(int q = 0; q < ns; q++) if(!memcmp(&st[q], &c, sizeof(c))) f = q;
+            if(f < 0) { if(ns == 48) return -1; st[ns] = c; f = ns++; }
+            tab[s * 8 + pix] = (uint8_t) r; tab[384 + s * 8 + pix] = (uint8_t) f;
+        }
+    return ns;
+}
+
+__global__ void __launch_bounds__(256)
+k_domain_keys(int64_t n, const double *__restrict__ pos, double Box, double fac, const uint8_t *__restrict__ tab,
+              unsigned long long *__restrict__ keys)
+{
+    __shared__ uint8_t s_tab[768];
+    for(int k = threadIdx.x; k < 768; k += blockDim.x) s_tab[k] = tab[k];
+    __syncthreads();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const double off = Box / 2000;                                         // peano.h:19
+    const int x = (int) ((pos[3 * i] + off) * fac), y = (int) ((pos[3 * i + 1] + off) * fac), z = (int) ((pos[3 * i + 2] + off) * fac);
+    unsigned long long key = 0;
+    int s = 0;
+#pragma unroll 1
+    for(int bit = PH_BITS - 1; bit >= 0; bit--) {                          // peano.c:114-124
+        const int pix = (((x >> bit) & 1) << 2) | (((y >> bit) & 1) << 1) | ((z >> bit) & 1);
+        key = (key << 3) | s_tab[s * 8 + pix];
+        s = s_tab[384 + s * 8 + pix];
+    }
+    keys[i] = key;
+}
+
+__global__ void __launch_bounds__(256)
+k_domain_topleaf(int64_t n, const unsigned long long *__restrict__ keys, const int *__restrict__ daughter,
+                 const unsigned long long *__restrict__ startkey, const int *__restrict__ shift, const int *__restrict__ leaf, int *__restrict__ out)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const unsigned long long key = keys[i];
+    int no = 0;
+    while(daughter[no] >= 0) no = daughter[no] + (int) ((key - startkey[no]) >> (shift[no] - 3));     // domain.h:74-76
+    out[i] = leaf[no];
+}
+
+int domain_peano_keys(Engine *E, double BoxSize, uint64_t *keys_out)
+{
+    if(!(BoxSize > 0)) return failmsg(E, "b200_domain_peano_keys: bad box size");
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->dk_keys.ensure(n));
+    if(!E->dk_tab.p) {
+        uint8_t tab[768];
+        if(ph_tables(tab) != 24) return failmsg(E, "b200_domain_peano_keys: state machine generation failed");
+        CK(E->dk_tab.ensure(768));
+        CK(cudaMemcpyAsync(E->dk_tab.p, tab, 768, cudaMemcpyHostToDevice, E->stream));
+        CK(cudaStreamSynchronize(E->stream));      // tab is a stack array
+    }
+    const double fac = 1.0 / (BoxSize * 1.001) * (double) (1ull << PH_BITS);      // peano.h:18
+    if(E->n > 0) {
+        k_domain_keys<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->n, E->pos.p, BoxSize, fac, E->dk_tab.p, E->dk_keys.p);
+        CKL(E);
+        if(keys_out) CK(cudaMemcpyAsync(keys_out, E->dk_keys.p, (size_t) E->n * sizeof(uint64_t), cudaMemcpyDeviceToHost, E->stream));
+    }
+    CK(cudaStreamSynchronize(E->stream));
+    E->dk_keys_n = E->n;
+    return 0;
+}
+
+int domain_set_topnodes(Engine *E, int32_t ntop, const int32_t *daughter, const uint64_t *startkey, const int32_t *shift, const int32_t *leaf)
+{
+    if(ntop < 1 || !daughter || !startkey || !shift || !leaf) return failmsg(E, "b200_domain_set_topnodes: bad arguments");
+    for(int t = 0; t < ntop; t++)      // the lookup must terminate: daughters lie behind their parent and inside the table
+        if(daughter[t] >= 0 && (daughter[t] <= t || daughter[t] + 8 > ntop || shift[t] < 3)) return failmsg(E, "b200_domain_set_topnodes: malformed top tree");
+    CK(E->dk_daughter.ensure(ntop)); CK(E->dk_startkey.ensure(ntop)); CK(E->dk_shift.ensure(ntop)); CK(E->dk_leaf.ensure(ntop));
+    CK(cudaMemcpyAsync(E->dk_daughter.p, daughter, ntop * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaMemcpyAsync(E->dk_startkey.p, startkey, ntop * sizeof(uint64_t), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaMemcpyAsync(E->dk_shift.p, shift, ntop * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaMemcpyAsync(E->dk_leaf.p, leaf, ntop * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    E->dk_ntop = ntop;
+    return 0;
+}
+
+int domain_topleaf(Engine *E, int32_t *topleaf_out)
+{
+    if(E->dk_ntop == 0) return failmsg(E, "b200_domain_topleaf: call b200_domain_set_topnodes first");
+    if(E->dk_keys_n != E->n) return failmsg(E, "b200_domain_topleaf: call b200_domain_peano_keys first");
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->dk_topleaf.ensure(n));
+    if(E->n > 0) {
+        k_domain_topleaf<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->n, E->dk_keys.p, E->dk_daughter.p, E->dk_startkey.p, E->dk_shift.p,
+                                                                               E->dk_leaf.p, E->dk_topleaf.p);
+        CKL(E);
+        if(topleaf_out) CK(cudaMemcpyAsync(topleaf_out, E->dk_topleaf.p, (size_t) E->n * sizeof(int32_t), cudaMemcpyDeviceToHost, E->stream));
+    }
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
+void domain_release(Engine *E)
+{
+    E->dk_keys.release(); E->dk_tab.release(); E->dk_daughter.release(); E->dk_startkey.release(); E->dk_shift.release(); E->dk_leaf.release(); E->dk_topleaf.release();
+}
+
+} // namespace b200
+
+using namespace b200;
+#define DK_ENTER(ctx) if(!(ctx)) return 1; Engine *E = &(ctx)->e; if(cudaSetDevice(E->device) != cudaSuccess) return failmsg(E, "cudaSetDevice failed")
+extern "C" {
+int b200_domain_peano_keys(b200_ctx *ctx, double BoxSize, uint64_t *keys_out) { DK_ENTER(ctx); return domain_peano_keys(E, BoxSize, keys_out); }
+int b200_domain_set_topnodes(b200_ctx *ctx, int32_t ntop, const int32_t *daughter, const uint64_t *startkey, const int32_t *shift, const int32_t *leaf)
+{
+    DK_ENTER(ctx);
+    return domain_set_topnodes(E, ntop, daughter, startkey, shift, leaf);
+}
+int b200_domain_topleaf(b200_ctx *ctx, int32_t *topleaf_out) { DK_ENTER(ctx); return domain_topleaf(E, topleaf_out); }
+}

@@ -166,6 +166,13 @@ struct Engine {
     bool st_maxsig_valid = false;
     DevBuf<unsigned long long> st_cnt;
 
+    // ---- domain keys (domain_keys.cu) ----
+    DevBuf<unsigned long long> dk_keys, dk_startkey;   // Peano-Hilbert key per particle; TopNodes[].StartKey
+    DevBuf<uint8_t> dk_tab;                            // generated state machine of the curve
+    DevBuf<int> dk_daughter, dk_shift, dk_leaf, dk_topleaf;
+    int dk_ntop = 0;
+    int64_t dk_keys_n = -1;
+
     Timer timers[T_COUNT];
     b200_timings last = {};
 };
@@ -219,8 +226,9 @@ int sph_set_timebins(Engine *E, const uint8_t *bin_grav, const uint8_t *bin_hydr
 int sph_set_active(Engine *E, const int32_t *active, int64_t nactive);
 int sph_set_state(Engine *E, const double *density, const double *egy, const double *dhsmlfac, const double *divvel, const double *curlvel);
 
-// step loop (steploop.cu)
+// step loop (steploop.cu), domain keys (domain_keys.cu)
 void step_release(Engine *E);
+void domain_release(Engine *E);
 
 // walk (tree_walk.cu)
 int walk_init_tables(Engine *E);

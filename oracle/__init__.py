@@ -43,7 +43,7 @@ COUNTS_DTYPE = np.dtype([("nodes_accepted", "i4"), ("nodes_opened", "i4"),
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_tree.c", "oracle_pm.c", "oracle_sph.c", "oracle_step.c", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_tree.c", "oracle_pm.c", "oracle_sph.c", "oracle_step.c", "oracle_domain.c", "oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -262,3 +262,24 @@ def direct_sum(pos, mass, box, G, softening_h, repeat=1):
     lib().oracle_direct_sum(_p(pos), _p(mass), C.c_int64(len(mass)), C.c_double(box), C.c_double(G),
                             C.c_double(softening_h), C.c_int(repeat), _p(acc))
     return acc
+
+
+def peano_keys(pos, box):
+    """PEANO(Pos, BoxSize) of utils/peano.h:15-21 for every row of pos -> uint64 keys."""
+    pos = _c(pos, np.float64)
+    keys = np.zeros(len(pos), np.uint64)
+    lib().oracle_peano_keys(_p(pos), C.c_int64(len(pos)), C.c_double(box), _p(keys))
+    return keys
+
+
+def peano_key(x, y, z, bits=21):
+    L = lib(); L.oracle_peano_key.restype = C.c_uint64
+    return int(L.oracle_peano_key(C.c_int(x), C.c_int(y), C.c_int(z), C.c_int(bits)))
+
+
+def topleaf(keys, daughter, startkey, shift, leaf):
+    """domain_get_topleaf (domain.h:71-78) over TopNodes given as arrays."""
+    keys = _c(keys, np.uint64); out = np.zeros(len(keys), np.int32)
+    lib().oracle_topleaf(_p(keys), C.c_int64(len(keys)), _p(_c(daughter, np.int32)), _p(_c(startkey, np.uint64)), _p(_c(shift, np.int32)),
+                         _p(_c(leaf, np.int32)), _p(out))
+    return out

@@ -180,6 +180,13 @@ int oracle_hier_timesteps(const oracle_timeline *tl, const oracle_cosmo *c, cons
                           double G, int Nmesh, double Asmth, double BoxSize, double atime, int FastParticleType,
                           const double *store, int64_t *info);
 
+/* ---- domain keys (oracle_domain.c): utils/peano.c:108-129, peano.h:15-21, domain.h:71-78 ---- */
+int oracle_peano_tables(uint8_t rank[48][8], uint8_t next[48][8]);
+uint64_t oracle_peano_key(int x, int y, int z, int bits);
+void oracle_peano_keys(const double *pos, int64_t n, double BoxSize, uint64_t *keys);
+void oracle_topleaf(const uint64_t *keys, int64_t n, const int32_t *daughter, const uint64_t *startkey, const int32_t *shift,
+                    const int32_t *leaf, int32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

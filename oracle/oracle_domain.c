@@ -1,0 +1,86 @@
+/* oracle_domain.c -- CPU restatement of the domain keys of the reference: the Peano-Hilbert key of a
+ * position (libgadget/utils/peano.c:108-129, peano.h:15-21) and the top-leaf lookup
+ * (libgadget/domain.h:71-78).  TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * PINNED against the 64 known-answer keys of the reference's own tests/test_peano.c:107-118
+ * (tests/golden/ref_peano.npz) and against the reference's compiled peano.c / domain.h on random input.
+ *
+ * The reference walks a state machine stored as two 48x8 tables.  Here the same curve is stated
+ * geometrically and the machine is generated: a state is a symmetry of the cube (axis permutation +
+ * flips) applied to one base pattern -- octants visited in the Gray-code order
+ * 000,010,110,100,101,111,011,001 (bits x,y,z) -- and the sub-cube visited r-th continues in the state
+ * composed with the r-th of eight fixed child symmetries:
+ *   r = 0: swap y,z | 1,2: swap x,z | 3,4: flip x,y | 5,6: swap x,z, flip x,z | 7: swap y,z, flip y,z.
+ * Closing the identity under these gives 24 states (the rotations); the reference's 48-row tables also hold their
+ * mirror images, which a walk from state 0 never enters. */
+#include <string.h>
+#include "oracle.h"
+
+typedef struct { int perm[3], flip[3]; } sym_t;                 /* new bit k = old bit perm[k] ^ flip[k] */
+static const int base_order[8] = {0, 2, 6, 4, 5, 7, 3, 1};      /* octant (4x+2y+z) visited at rank r */
+static const sym_t child[8] = {
+    {{0, 2, 1}, {0, 0, 0}}, {{2, 1, 0}, {0, 0, 0}}, {{2, 1, 0}, {0, 0, 0}}, {{0, 1, 2}, {1, 1, 0}},
+    {{0, 1, 2}, {1, 1, 0}}, {{2, 1, 0}, {1, 0, 1}}, {{2, 1, 0}, {1, 0, 1}}, {{0, 2, 1}, {0, 1, 1}}};
+
+static int apply(const sym_t *s, int pix)
+{
+    const int b[3] = {(pix >> 2) & 1, (pix >> 1) & 1, pix & 1};
+    return ((b[s->perm[0]] ^ s->flip[0]) << 2) | ((b[s->perm[1]] ^ s->flip[1]) << 1) | (b[s->perm[2]] ^ s->flip[2]);
+}
+static sym_t compose(const sym_t *a, const sym_t *b)            /* b first, then a */
+{
+    sym_t c;
+    for(int k = 0; k < 3; k++) { c.perm[k] = b->perm[a->perm[k]]; c.flip[k] = b->flip[a->perm[k]] ^ a->flip[k]; }
+    return c;
+}
+/* rank[state][octant] and next[state][octant], states numbered in order of discovery from the identity */
+int oracle_peano_tables(uint8_t rank[48][8], uint8_t next[48][8])
+{
+    sym_t st[48];
+    int ns = 1;
+    const sym_t id = {{0, 1, 2}, {0, 0, 0}};
+    st[0] = id;
+    for(int s = 0; s < ns; s++)
+        for(int r = 0; r < 8; r++) {
+            const int pix = apply(&st[s], base_order[r]);
+            const sym_t c = compose(&st[s], &child[r]);
+            int f = -1;
+            for(int q = 0; q < ns; q++) if(!memcmp(&st[q], &c, sizeof(c))) f = q;
+            if(f < 0) { if(ns == 48) return -1; st[ns] = c; f = ns++; }
+            rank[s][pix] = (uint8_t) r; next[s][pix] = (uint8_t) f;
+        }
+    return ns;
+}
+uint64_t oracle_peano_key(int x, int y, int z, int bits)        /* peano.c:108-129 */
+{
+    static uint8_t rank[48][8], next[48][8];
+    static int ready;
+    if(!ready) { oracle_peano_tables(rank, next); ready = 1; }
+    uint64_t key = 0;
+    int s = 0;
+    for(int bit = bits - 1; bit >= 0; bit--) {
+        const int pix = (((x >> bit) & 1) << 2) | (((y >> bit) & 1) << 1) | ((z >> bit) & 1);
+        key = (key << 3) | rank[s][pix];
+        s = next[s][pix];
+    }
+    return key;
+}
+/* PEANO(Pos, BoxSize) peano.h:15-21, BITS_PER_DIMENSION = 21 */
+void oracle_peano_keys(const double *pos, int64_t n, double BoxSize, uint64_t *keys)
+{
+    const double fac = 1.0 / (BoxSize * 1.001) * (double) (((uint64_t) 1) << 21);
+    for(int64_t i = 0; i < n; i++) {
+        const double sx = pos[3 * i] + BoxSize / 2000, sy = pos[3 * i + 1] + BoxSize / 2000, sz = pos[3 * i + 2] + BoxSize / 2000;
+        keys[i] = oracle_peano_key((int) (sx * fac), (int) (sy * fac), (int) (sz * fac), 21);
+    }
+}
+/* domain_get_topleaf domain.h:71-78 over TopNodes given as arrays */
+void oracle_topleaf(const uint64_t *keys, int64_t n, const int32_t *daughter, const uint64_t *startkey, const int32_t *shift,
+                    const int32_t *leaf, int32_t *out)
+{
+    for(int64_t i = 0; i < n; i++) {
+        int no = 0;
+        while(daughter[no] >= 0) no = daughter[no] + (int) ((keys[i] - startkey[no]) >> (shift[no] - 3));
+        out[i] = leaf[no];
+    }
+}

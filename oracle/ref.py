@@ -125,6 +125,18 @@ class Ref:
                                 C.c_char_p(outdir.encode()), C.c_double(time), _p(g), _p(p))
         return g, p
 
+    def peano_keys(self, pos, box):
+        pos = np.ascontiguousarray(pos, np.float64); keys = np.zeros(len(pos), np.uint64)
+        self.L.ref_peano_keys(C.c_int64(len(pos)), _p(pos), C.c_double(box), _p(keys))
+        return keys
+
+    def topleaf(self, keys, daughter, startkey, shift, leaf):
+        keys = np.ascontiguousarray(keys, np.uint64); out = np.zeros(len(keys), np.int32)
+        a = [np.ascontiguousarray(daughter, np.int32), np.ascontiguousarray(startkey, np.uint64), np.ascontiguousarray(shift, np.int32),
+             np.ascontiguousarray(leaf, np.int32)]
+        self.L.ref_topleaf(C.c_int64(len(keys)), _p(keys), C.c_int(len(a[0])), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(out))
+        return out
+
     def timings(self):
         b, w = C.c_double(), C.c_double()
         self.L.ref_timings(C.byref(b), C.byref(w))

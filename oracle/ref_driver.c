@@ -248,6 +248,26 @@ int ref_grav_short_tree(double G, int Nmesh, double Asmth, double ErrTolForceAcc
     return 0;
 }
 
+/* Domain keys: PEANO() (utils/peano.h:15-21 over peano.c:108-129) and domain_get_topleaf (domain.h:71-78) over a top
+ * tree handed in as arrays (TopNodes[].Daughter / StartKey / Shift / Leaf). */
+void ref_peano_keys(int64_t n, const double *pos, double BoxSize, uint64_t *keys)
+{
+    for(int64_t i = 0; i < n; i++) keys[i] = PEANO(&pos[3 * i], BoxSize);
+}
+void ref_topleaf(int64_t n, const uint64_t *keys, int ntop, const int *daughter, const uint64_t *startkey, const int *shift, const int *leaf, int *out)
+{
+    DomainDecomp d;
+    memset(&d, 0, sizeof(d));
+    d.TopNodes = (struct topnode_data *) malloc(sizeof(struct topnode_data) * ntop);
+    for(int t = 0; t < ntop; t++) {
+        memset(&d.TopNodes[t], 0, sizeof(d.TopNodes[t]));
+        d.TopNodes[t].Daughter = daughter[t]; d.TopNodes[t].StartKey = startkey[t]; d.TopNodes[t].Shift = shift[t]; d.TopNodes[t].Leaf = leaf[t];
+    }
+    d.NTopNodes = ntop;
+    for(int64_t i = 0; i < n; i++) out[i] = domain_get_topleaf(keys[i], &d);
+    free(d.TopNodes);
+}
+
 void ref_timings(double *build_s, double *walk_s) { *build_s = t_build; *walk_s = t_walk; }
 int64_t ref_numnodes(void) { return Tree.numnodes; }
 

@@ -1,0 +1,39 @@
+"""Inputs of the domain-key tests (Peano-Hilbert keys, top-leaf lookup), shared by the golden generator and the tests."""
+import numpy as np
+
+BITS = 21
+
+
+def peano_test_positions():
+    """tests/test_peano.c:107-118: the 4^3 integer lattice in a box of 4."""
+    B = 4
+    i = np.arange(B ** 3)
+    return np.stack([i % B, (i // B) % B, (i // B // B) % B], 1).astype(np.float64), float(B)
+
+
+def random_positions(seed=3, n=20000, box=25000.0):
+    rng = np.random.default_rng(seed)
+    pos = rng.random((n, 3)) * box
+    pos[:6] = [[0, 0, 0], [box, box, box], [box * (1 - 1e-12), 0, box / 2], [box / 2, box / 2, box / 2], [1e-9, box - 1e-9, 3.0], [box / 3, box / 7, box / 11]]
+    return pos, box
+
+
+def refined_toptree(seed=4, nrefine=40):
+    """A top tree as domain_decompose_full leaves it (domain.c): the root over the whole key range, nodes split into 8
+    daughters stored consecutively, leaves numbered along the curve; which nodes are split is random here."""
+    rng = np.random.default_rng(seed)
+    daughter = [-1]; startkey = [0]; shift = [3 * BITS]
+    leaves = [0]
+    for _ in range(nrefine):
+        t = leaves.pop(int(rng.integers(len(leaves))))
+        if shift[t] < 6:
+            leaves.append(t); continue
+        daughter[t] = len(daughter)
+        for j in range(8):
+            daughter.append(-1); shift.append(shift[t] - 3); startkey.append(startkey[t] + (j << (shift[t] - 3)))
+            leaves.append(len(daughter) - 1)
+    order = sorted(leaves, key=lambda t: startkey[t])
+    leaf = [-1] * len(daughter)
+    for k, t in enumerate(order):
+        leaf[t] = k
+    return (np.array(daughter, np.int32), np.array(startkey, np.uint64), np.array(shift, np.int32), np.array(leaf, np.int32))

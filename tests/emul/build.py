@@ -1,4 +1,4 @@
-"""Build tests/emul/_build/libsteploop_emul.so: mp-gadget_b200/csrc/steploop.cu compiled for the HOST
+"""Build tests/emul/_build/libsteploop_emul.so: mp-gadget_b200/csrc/steploop.cu and domain_keys.cu compiled for the HOST
 against the CUDA stand-in headers of tests/emul/include, kernels and host drivers unchanged except
 that the launch syntax  k<<<grid, block, smem, stream>>>(args);  is rewritten to a macro call.
 TEST INFRASTRUCTURE ONLY (see tests/emul/include/cuda_runtime.h)."""
@@ -8,7 +8,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SRC = os.path.join(ROOT, "mp-gadget_b200", "csrc", "steploop.cu")
+SRCS = [os.path.join(ROOT, "mp-gadget_b200", "csrc", f) for f in ("steploop.cu", "domain_keys.cu")]
+SRC = SRCS[0]
 OUT = os.path.join(HERE, "_build")
 SO = os.path.join(OUT, "libsteploop_emul.so")
 
@@ -37,19 +38,23 @@ def rewrite_launches(text):
 
 def build(force=False):
     os.makedirs(OUT, exist_ok=True)
-    deps = [SRC, os.path.join(HERE, "emul_mocks.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(HERE, "include", "cub", "cub.cuh"),
+    deps = SRCS + [os.path.join(HERE, "emul_mocks.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(HERE, "include", "cub", "cub.cuh"),
             os.path.join(ROOT, "mp-gadget_b200", "csrc", "engine.h"), os.path.join(ROOT, "include", "b200force.h"), __file__]
     if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return SO
-    text, n = rewrite_launches(open(SRC).read())
-    assert n >= 10, n
-    gen = os.path.join(OUT, "steploop_emul.cpp")
-    with open(gen, "w") as f:
-        f.write("// GENERATED from mp-gadget_b200/csrc/steploop.cu by tests/emul/build.py -- do not edit\n" + text)
+    gens, total = [], 0
+    for src in SRCS:
+        text, n = rewrite_launches(open(src).read())
+        total += n
+        gen = os.path.join(OUT, os.path.basename(src).replace(".cu", "_emul.cpp"))
+        with open(gen, "w") as f:
+            f.write("// GENERATED from mp-gadget_b200/csrc/%s by tests/emul/build.py -- do not edit\n" % os.path.basename(src) + text)
+        gens.append(gen)
+    assert total >= 12, total
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], stdout=subprocess.DEVNULL)
     inc = ["-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "mp-gadget_b200", "csrc")]
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
-                           "-Wno-unused-function", "-DSTEP_BLOCKS=4", "-o", SO, gen, os.path.join(HERE, "emul_mocks.cpp")] + inc +
+                           "-Wno-unused-function", "-DSTEP_BLOCKS=4", "-o", SO] + gens + [os.path.join(HERE, "emul_mocks.cpp")] + inc +
                           ["-L", os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     return SO
 

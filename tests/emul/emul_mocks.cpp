@@ -57,7 +57,7 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
 using namespace b200;
 extern "C" {
 int b200_ctx_create(b200_ctx **out, int device) { *out = new (std::nothrow) b200_ctx(); return *out ? 0 : 5; }
-void b200_ctx_destroy(b200_ctx *ctx) { if(ctx) { step_release(&ctx->e); delete ctx; } }
+void b200_ctx_destroy(b200_ctx *ctx) { if(ctx) { step_release(&ctx->e); domain_release(&ctx->e); delete ctx; } }
 const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->e.err.c_str() : "null context"; }
 int b200_set_particles_soa(b200_ctx *ctx, const double *pos, const float *mass, const uint8_t *type, const double *, int64_t n)
 {

@@ -52,7 +52,37 @@ def dropin(which):
     print(which + " ok")
 
 
+def domain():
+    """csrc/domain_keys.cu under emulation against the reference's known-answer keys and compiled peano.c / domain.h."""
+    import domain_scenarios as DS
+    G = np.load(os.path.join(ROOT, "tests", "golden", "ref_peano.npz"))
+    e = EmulEngine()
+    L, ctx = e.L, e.ctx
+    p = lambda a: C.c_void_p(a.ctypes.data)
+
+    def keys_of(pos, box):
+        pos = np.ascontiguousarray(pos, np.float64)
+        e.set_particles(pos, np.ones(len(pos), np.float32))
+        k = np.zeros(len(pos), np.uint64)
+        assert L.b200_domain_peano_keys(ctx, C.c_double(box), p(k)) == 0, L.b200_last_error(ctx)
+        return k
+    pos4, box4 = DS.peano_test_positions()
+    assert np.array_equal(keys_of(pos4, box4), G["known_keys"])
+    pos, box = DS.random_positions()
+    assert np.array_equal(keys_of(pos, box), G["random_keys"])
+    top = [np.ascontiguousarray(a) for a in DS.refined_toptree()]
+    assert L.b200_domain_set_topnodes(ctx, C.c_int32(len(top[0])), p(top[0]), p(top[1]), p(top[2]), p(top[3])) == 0
+    leaf = np.zeros(len(pos), np.int32)
+    assert L.b200_domain_topleaf(ctx, p(leaf)) == 0, L.b200_last_error(ctx)
+    assert np.array_equal(leaf, G["topleaf"])
+    bad = top[0].copy(); bad[0] = 0          # a daughter pointing at its parent must be refused, not loop
+    assert L.b200_domain_set_topnodes(ctx, C.c_int32(len(bad)), p(bad), p(top[1]), p(top[2]), p(top[3])) != 0
+    print("domain ok")
+
+
 def main(which):
+    if which == "domain":
+        return domain()
     if which.startswith("dropin"):
         return dropin(which)
     SL = importlib.import_module("mp-gadget_b200.steploop")

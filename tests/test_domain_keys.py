@@ -1,0 +1,69 @@
+"""Domain keys: Peano-Hilbert keys (utils/peano.c:108-129, peano.h:15-21) and the top-leaf lookup (domain.h:71-78).
+Golden tests/golden/ref_peano.npz (generator make_golden_peano.py): the 64 known-answer keys of the reference's own
+tests/test_peano.c:107, its compiled peano.c on random positions, domain_get_topleaf over a refined top tree.
+CPU: the oracle (a generated state machine, no stored tables).  The CUDA kernels run under emulation in
+tests/test_step_emul.py[domain]; the hardware test below carries the `gpu_unverified` marker (see test_step_gpu.py)."""
+import os
+import sys
+import numpy as np
+import pytest
+
+import oracle
+from oracle import ref as R
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import domain_scenarios as DS        # noqa: E402
+
+GOLD = np.load(os.path.join(HERE, "golden", "ref_peano.npz"))
+
+
+def test_oracle_reproduces_test_peano_known_answers():
+    pos, box = DS.peano_test_positions()
+    assert np.array_equal(oracle.peano_keys(pos, box), GOLD["known_keys"])
+    # test_peano.c:120-128 compares the table walk with the older bit-twiddling routine on single-bit coordinates;
+    # here: keys of a complete 8^3 grid are a permutation of 0..511 and consecutive keys are face neighbours
+    g = np.arange(8)
+    x, y, z = np.meshgrid(g, g, g, indexing="ij")
+    k = np.array([oracle.peano_key(int(a), int(b), int(c), 3) for a, b, c in zip(x.ravel(), y.ravel(), z.ravel())])
+    assert sorted(k) == list(range(512))
+    order = np.argsort(k)
+    steps = np.abs(np.diff(np.stack([x.ravel()[order], y.ravel()[order], z.ravel()[order]], 1), axis=0)).sum(1)
+    assert (steps == 1).all()
+
+
+def test_oracle_keys_and_topleaf_equal_reference():
+    pos, box = DS.random_positions()
+    keys = oracle.peano_keys(pos, box)
+    assert np.array_equal(keys, GOLD["random_keys"])
+    top = DS.refined_toptree()
+    assert len(top[0]) == int(GOLD["ntop"])
+    assert np.array_equal(oracle.topleaf(keys, *top), GOLD["topleaf"])
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref_tree.so not built")
+def test_oracle_equals_reference_live():
+    r = R.load()
+    if not hasattr(r.L, "ref_peano_keys"):
+        pytest.skip("prebuilt libref_tree.so predates ref_peano_keys")
+    pos, box = DS.random_positions(seed=17, n=5000, box=731.5)
+    keys = oracle.peano_keys(pos, box)
+    assert np.array_equal(keys, r.peano_keys(pos, box))
+    top = DS.refined_toptree(seed=9, nrefine=25)
+    assert np.array_equal(oracle.topleaf(keys, *top), r.topleaf(keys, *top))
+
+
+@pytest.mark.gpu_unverified
+def test_gpu_domain_keys(b200):
+    try:
+        e = b200.Engine(0)
+    except Exception as ex:
+        pytest.skip("no CUDA device (%s)" % ex)
+    pos, box = DS.peano_test_positions()
+    e.set_particles(pos, np.ones(len(pos), np.float32))
+    assert np.array_equal(e.peano_keys(box), GOLD["known_keys"])
+    pos, box = DS.random_positions()
+    e.set_particles(pos, np.ones(len(pos), np.float32))
+    assert np.array_equal(e.peano_keys(box), GOLD["random_keys"])
+    assert np.array_equal(e.topleaf(*DS.refined_toptree()), GOLD["topleaf"])
+    e.close()
