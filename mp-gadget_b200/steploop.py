@@ -209,8 +209,15 @@ class StepEngine:
         self.sp.softening = 2.8 * par["GravitySoftening"]           # FORCE_SOFTENING gravshort-tree.c:37-41
         return self.sp.softening
 
-    def advance(self, first=False):
-        """One pass of run.c:355-800 (collisionless, HierarchicalGravity, PM force held fixed)."""
+    def pm_force(self):
+        """gravpm_force on a PM step (run.c:519-523) without leaving the device: b200_pm_force_dev, then P[].GravPM of
+        the step state <- its result."""
+        self.e.gravpm_force_dev()
+        self._ck(self.L.b200_step_adopt_forces(self.ctx, C.c_int(0), C.c_int(1)))
+
+    def advance(self, first=False, pm=False):
+        """One pass of run.c:355-800 (collisionless, HierarchicalGravity).  pm = False holds the PM force fixed (the
+        parity scenarios); pm = True recomputes it on PM steps."""
         t = self.t
         last = t.Ti_Current
         if not first:
@@ -220,6 +227,8 @@ class StepEngine:
         if not first:
             self.drift(last, t.Ti_Current)
         _, counts = self.build_active()
+        if pm and is_pm:
+            self.pm_force()
         self._ck(self.L.b200_step_hier_accelerations(self.ctx, C.byref(self.sp), C.byref(self.gp), C.byref(t), C.c_int64(int(counts[1]))))
         self.kick(3)
         if is_pm:

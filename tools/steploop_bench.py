@@ -61,7 +61,7 @@ for ng in [int(a) for a in sys.argv[1:]] or [128, 256]:
     for s in range(9):
         l0 = e.kernel_launches() if hasattr(e, "kernel_launches") else 0
         t0 = time.perf_counter()
-        bad, info = S.advance(first=(s == 0))
+        bad, info = S.advance(first=(s == 0), pm=True)
         dt = time.perf_counter() - t0
         scal = S.get_times()[0]
         steps.append(dict(step=s, wall_ms=1e3 * dt, active=int(info[1]), is_pm=int(info[2]), mintimebin=int(scal[0]), maxtimebin=int(scal[1]), bad=bad))
