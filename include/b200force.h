@@ -394,6 +394,10 @@ int b200_step_adopt_hydro(b200_ctx *ctx);
  * the device, times->mintimebin updated.  maxsignalvel[n] = SphP[].MaxSignalVel by particle index (host). */
 int b200_step_hydro_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel,
                               double atime, double hubble, int64_t *nbad);
+/* find_timesteps (timestep.c:739-853), the SplitGravityTimestepsOn = 0 loop: one bin for TimeBinGravity and
+ * TimeBinHydro from the gravity and (gas) hydro criteria, PM step length on PM steps, times->mintimebin / maxtimebin. */
+int b200_step_find_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel,
+                             int is_pm, double atime, double hubble, int64_t *nbad);
 /* hierarchical_gravity_accelerations on the current active list (ngrav = NumActiveGravity);
  * gp->TreeUseBH > 1 is reset to 0 after the first walk like TreeParams.TreeUseBH */
 int b200_step_hier_accelerations(b200_ctx *ctx, const b200_step_params *sp, b200_gravshort_params *gp,

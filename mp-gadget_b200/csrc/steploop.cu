@@ -296,6 +296,46 @@ k_step_hydro_bins(int64_t nlist, const int *__restrict__ list, const uint8_t *__
     if(bin_active(binold, Ti) && bin_active(bin, Ti)) bin_hydro[i] = (uint8_t) bin;
     atomicMin(&cnt[1], (unsigned long long) bin);
 }
+// find_timesteps timestep.c:739-853 (SplitGravityTimestepsOn = 0): the smaller of the gravity and (gas) hydro steps -> one
+// bin for TimeBinGravity and TimeBinHydro.  cnt[0] bad steps, cnt[1] smallest, cnt[2] largest new bin.
+__global__ void __launch_bounds__(256)
+k_step_find_bins(int64_t nlist, const int *__restrict__ list, const uint8_t *__restrict__ type, const uint8_t *__restrict__ flags,
+                 const double *__restrict__ fullacc, const double *__restrict__ gravpm, const double *__restrict__ hsml,
+                 const double *__restrict__ dthsml, const double *__restrict__ maxsig, uint8_t *__restrict__ bin_grav, uint8_t *__restrict__ bin_hydro,
+                 StepTimeline T, double atime, double hubble, double fac3, double ErrTolIntAccuracy, double softening, double CourantFac,
+                 double MinSizeTimestep, long long dti_max, long long Ti, unsigned long long *__restrict__ cnt)
+{
+    const int64_t q = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(q >= nlist) return;
+    const int64_t i = list ? list[q] : q;
+    if(flags[i] & 3) return;
+    long long dti = dev_gravity_dti(T, fullacc + 3 * i, gravpm + 3 * i, atime, hubble, ErrTolIntAccuracy, softening, MinSizeTimestep, dti_max);
+    if(type[i] == 0) {                                                     // :783-791
+        double dt = 2 * CourantFac * atime * hsml[i] / (fac3 * maxsig[i]);
+        const double dt_hsml = CourantFac * atime * atime * fabs(hsml[i] / (dthsml[i] + 1e-20));
+        if(dt_hsml < dt) dt = dt_hsml;
+        double dloga = dt * hubble;
+        long long dti_hydro = 0;
+        if(dti_max != 0) {
+            if(dloga < MinSizeTimestep) dloga = MinSizeTimestep;
+            dti_hydro = dev_ti_from_loga(T, dloga + T.now) - T.ti_now;
+            if(dti_hydro > dti_max || dti_hydro < 0) dti_hydro = dti_max;
+        }
+        if(dti_hydro < dti) dti = dti_hydro;
+    }
+    int bin = 0;                                                           // get_timebin_from_dti :166-182
+    if(dti > 1) {
+        if(dti > (1ll << TB)) dti = 1ll << TB;
+        bin = 63 - __clzll(dti);
+    }
+    const int binold = bin_hydro[i];
+    if(bin > binold)
+        while(!bin_active(bin, Ti) && bin > binold && bin > 1) bin--;
+    if(bin < 1) atomicAdd(&cnt[0], 1ull);
+    if(bin_active(binold, Ti) && bin_active(bin, Ti)) { bin_hydro[i] = (uint8_t) bin; bin_grav[i] = (uint8_t) bin; }
+    atomicMin(&cnt[1], (unsigned long long) bin);
+    atomicMax(&cnt[2], (unsigned long long) bin);
+}
 // |FullTreeGravAccel + GravPM| for the relative opening criterion, gravshort.h:69-86
 __global__ void __launch_bounds__(256)
 k_step_oldacc(int64_t n, const double *__restrict__ fullacc, const double *__restrict__ gravpm, double *__restrict__ oldacc)
@@ -933,6 +973,50 @@ int step_adopt_hydro(Engine *E)
     return 0;
 }
 
+// find_timesteps timestep.c:739-853 on the current active list (the SplitGravityTimestepsOn = 0 loop: followed by
+// b200_step_half_kick with hydro_only = 0).  maxsig as in b200_step_hydro_timesteps (ignored without gas).
+int step_find_timesteps(Engine *E, const b200_step_params *sp, b200_step_times *t, const double *maxsig, int is_pm, double atime, double hubble,
+                        int64_t *nbad)
+{
+    if(int rc = step_need_state(E, "b200_step_find_timesteps")) return rc;
+    if(!sp || !t || !sp->sync_loga || sp->nsync < 2) return failmsg(E, "b200_step_find_timesteps: null argument / timeline missing");
+    if(E->Nmesh == 0 && E->NmeshWalk == 0) return failmsg(E, "b200_step_find_timesteps: call b200_pm_init first (PM smoothing scale)");
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->st_sync.ensure((size_t) sp->nsync)); CK(E->st_cnt.ensure(1 + 6 * NBIN)); CK(E->st_maxsig.ensure(n));
+    CK(cudaMemcpyAsync(E->st_sync.p, sp->sync_loga, sp->nsync * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    if(maxsig) { CK(cudaMemcpyAsync(E->st_maxsig.p, maxsig, E->n * sizeof(double), cudaMemcpyHostToDevice, E->stream)); E->st_maxsig_valid = true; }
+    if(E->st_have_gas && !E->st_maxsig_valid) return failmsg(E, "b200_step_find_timesteps: no MaxSignalVel for the gas");
+    Hier H;
+    H.E = E; H.sp = sp; H.gp = nullptr; H.t = t;
+    H.T.sync = E->st_sync.p; H.T.nsync = (int) sp->nsync;
+    H.T.now = tl_loga_from_ti(sp, t->Ti_Current); H.T.ti_now = tl_ti_from_loga(sp, H.T.now);
+    int64_t dti_max = t->PM_length;
+    if(is_pm) {                                                            // :751-755
+        if(int rc = hier_pm_timestep(H, atime, hubble, &dti_max)) return rc;
+        t->PM_length = dti_max;
+        t->PM_start = t->PM_kick;
+    }
+    const unsigned long long init[3] = {0ull, (unsigned long long) TB, 0ull};
+    CK(cudaMemcpyAsync(E->st_cnt.p, init, sizeof(init), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));           // init is a stack array
+    const double fac3 = pow(atime, 3 * (1 - 5.0 / 3) / 2.0);
+    const int64_t nl = E->st_nact;
+    if(nl > 0) {
+        k_step_find_bins<<<grid_for(nl), 256, 0, E->stream>>>(nl, E->st_act_implicit ? nullptr : E->st_act.p, E->type.p, E->flags.p, E->s_fullacc.p,
+            E->s_gravpm.p, E->s_hsml.p, E->s_dthsml.p, E->st_maxsig.p, E->s_bin_grav.p, E->s_bin_hydro.p, H.T, atime, hubble, fac3,
+            sp->ErrTolIntAccuracy, sp->softening, sp->CourantFac, sp->MinSizeTimestep, (long long) dti_max, (long long) t->Ti_Current, E->st_cnt.p);
+        CKL(E);
+    }
+    unsigned long long h[3];
+    CK(cudaMemcpyAsync(h, E->st_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    const int maxTimeBin = (int) h[2];
+    if(is_pm && t->PM_length > host_dti_of_bin(maxTimeBin)) t->PM_length = host_dti_of_bin(maxTimeBin);       // :835-836
+    t->mintimebin = (int) h[1]; t->maxtimebin = maxTimeBin;
+    if(nbad) *nbad = (int64_t) h[0];
+    return 0;
+}
+
 void step_release(Engine *E)
 {
     E->st_iota.release(); E->st_listA.release(); E->st_listB.release(); E->st_act.release(); E->st_flag.release();
@@ -973,6 +1057,12 @@ int b200_step_half_kick(b200_ctx *ctx, const double *gravkick, const double *hyd
 int b200_step_pm_kick(b200_ctx *ctx, double Fgravkick) { STEP_ENTER(ctx); return step_pm_kick(E, Fgravkick); }
 int b200_step_sph_prepare(b200_ctx *ctx, const b200_sph_bins *tables) { STEP_ENTER(ctx); return step_sph_prepare(E, tables); }
 int b200_step_adopt_hydro(b200_ctx *ctx) { STEP_ENTER(ctx); return step_adopt_hydro(E); }
+int b200_step_find_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel, int is_pm,
+                             double atime, double hubble, int64_t *nbad)
+{
+    STEP_ENTER(ctx);
+    return step_find_timesteps(E, sp, times, maxsignalvel, is_pm, atime, hubble, nbad);
+}
 int b200_step_hydro_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel, double atime,
                               double hubble, int64_t *nbad)
 {

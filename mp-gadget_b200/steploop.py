@@ -202,6 +202,16 @@ class StepEngine:
                                                   C.c_double(float(self.hubble(atime))), C.byref(nbad)))
         return int(nbad.value), self.get()["bin_hydro"]
 
+    def find_timesteps(self, maxsig, atime, asmth=None, first=False):
+        """find_timesteps (SplitGravityTimestepsOn = 0) on the current active list -> (bad, TimeBinGravity[n], TimeBinHydro[n]);
+        the PM smoothing scale comes from gravpm_init_periodic (set_gravity)."""
+        ms = _c(maxsig, np.float64)
+        nbad = C.c_int64()
+        self._ck(self.L.b200_step_find_timesteps(self.ctx, C.byref(self.sp), C.byref(self.t), _p(ms), C.c_int(1 if self.is_pm() else 0),
+                                                 C.c_double(atime), C.c_double(float(self.hubble(atime))), C.byref(nbad)))
+        g = self.get()
+        return int(nbad.value), g["bin_grav"], g["bin_hydro"]
+
     # --- hierarchy
     def set_gravity(self, par, G, nmesh, asmth):
         self.e.gravpm_init_periodic(self.box, asmth, nmesh, G)

@@ -168,6 +168,10 @@ int64_t oracle_pm_timestep_ti(const oracle_timeline *tl, const oracle_cosmo *c, 
 int oracle_hydro_timebins(const oracle_timeline *tl, const oracle_step_params *sp, oracle_times *t, const int32_t *list, int64_t nlist,
                           const uint8_t *type, const uint8_t *flags, const double *hsml, const double *dthsml, const double *maxsig,
                           const uint8_t *bin_grav, uint8_t *bin_hydro, double atime, double hubble);
+int oracle_find_timesteps(const oracle_timeline *tl, const oracle_cosmo *c, const oracle_step_params *sp, oracle_times *t, int64_t n,
+                          const int32_t *list, int64_t nlist, const uint8_t *type, const uint8_t *flags, const float *mass, const double *vel,
+                          const double *fullacc, const double *gravpm, const double *hsml, const double *dthsml, const double *maxsig,
+                          uint8_t *bin_grav, uint8_t *bin_hydro, int is_pm, double atime, int FastParticleType, double asmth);
 int oracle_hier_accelerations(const oracle_timeline *tl, const oracle_cosmo *c, const oracle_step_params *sp, oracle_gravshort_params *gp,
                               oracle_times *t, int64_t n, const double *pos, const float *mass, const uint8_t *type, const uint8_t *flags,
                               double *vel, double *fullacc, const double *gravpm, const uint8_t *bin_grav,

@@ -343,6 +343,48 @@ int64_t oracle_pm_timestep_ti(const oracle_timeline *tl, const oracle_cosmo *c, 
     return dti;
 }
 
+/* find_timesteps timestep.c:739-853 (ForceEqualTimesteps = 0, no black holes): the smaller of the gravity and (gas)
+ * hydro steps -> one bin for TimeBinGravity and TimeBinHydro; PM step length, min / max bin.  Returns the bad-step count. */
+int oracle_find_timesteps(const oracle_timeline *tl, const oracle_cosmo *c, const oracle_step_params *sp, oracle_times *t, int64_t n,
+                          const int32_t *list, int64_t nlist, const uint8_t *type, const uint8_t *flags, const float *mass, const double *vel,
+                          const double *fullacc, const double *gravpm, const double *hsml, const double *dthsml, const double *maxsig,
+                          uint8_t *bin_grav, uint8_t *bin_hydro, int is_pm, double atime, int FastParticleType, double asmth)
+{
+    int64_t dti_max = t->PM_length;
+    if(is_pm) {                                                            /* :751-755 */
+        dti_max = oracle_pm_timestep_ti(tl, c, sp, t, n, vel, mass, type, flags, atime, FastParticleType, asmth);
+        t->PM_length = dti_max;
+        t->PM_start = t->PM_kick;
+    }
+    const double hubble = hubble_of(c, atime);
+    const double fac3 = pow(atime, 3 * (1 - 5.0 / 3) / 2.0);
+    int bad = 0, mTimeBin = TB, maxTimeBin = 0;
+    for(int64_t q = 0; q < nlist; q++) {
+        const int64_t i = list ? list[q] : q;
+        if(flags && (flags[i] & 3)) continue;
+        const double dloga = oracle_gravity_dloga(fullacc + 3 * i, gravpm + 3 * i, atime, hubble, sp->ErrTolIntAccuracy, sp->softening);
+        int64_t dti = oracle_convert_timestep(tl, dloga, dti_max, t->Ti_Current, sp->MinSizeTimestep);
+        if(type[i] == 0) {                                                 /* :783-791 */
+            double dt = 2 * sp->CourantFac * atime * hsml[i] / (fac3 * maxsig[i]);
+            const double dt_hsml = sp->CourantFac * atime * atime * fabs(hsml[i] / (dthsml[i] + 1e-20));
+            if(dt_hsml < dt) dt = dt_hsml;
+            const int64_t dti_hydro = oracle_convert_timestep(tl, dt * hubble, dti_max, t->Ti_Current, sp->MinSizeTimestep);
+            if(dti_hydro < dti) dti = dti_hydro;
+        }
+        int bin = bin_of_dti(round_down_pow2(dti));                        /* get_timebin_from_dti :166-182 */
+        const int binold = bin_hydro[i];
+        if(bin > binold)
+            while(!oracle_is_timebin_active(bin, t->Ti_Current) && bin > binold && bin > 1) bin--;
+        if(bin < 1) bad++;
+        if(oracle_is_timebin_active(binold, t->Ti_Current) && oracle_is_timebin_active(bin, t->Ti_Current)) { bin_hydro[i] = (uint8_t) bin; bin_grav[i] = (uint8_t) bin; }
+        if(bin < mTimeBin) mTimeBin = bin;
+        if(bin > maxTimeBin) maxTimeBin = bin;
+    }
+    if(is_pm && t->PM_length > dti_of_bin(maxTimeBin)) t->PM_length = dti_of_bin(maxTimeBin);      /* :835-836 */
+    t->mintimebin = mTimeBin; t->maxtimebin = maxTimeBin;
+    return bad;
+}
+
 /* ---- the hierarchical gravity drivers (collisionless particles, one rank) ---- */
 typedef struct {
     const oracle_timeline *tl; const oracle_cosmo *c; const oracle_step_params *sp; oracle_gravshort_params *gp;

@@ -267,6 +267,13 @@ class RefStep(Ref):
         bad = int(self.L.ref_step_hydro_timesteps(_p(np.ascontiguousarray(maxsig, np.float64)), C.c_double(atime), C.c_int(1 if first else 0), _p(out)))
         return bad, out
 
+    def find_timesteps(self, maxsig, atime, asmth, first=False):
+        """find_timesteps (SplitGravityTimestepsOn = 0) on the current active list -> (bad, TimeBinGravity[n], TimeBinHydro[n])"""
+        bg = np.zeros(self.n, np.uint8); bh = np.zeros(self.n, np.uint8)
+        bad = int(self.L.ref_step_find_timesteps(_p(np.ascontiguousarray(maxsig, np.float64)), C.c_double(atime), C.c_double(asmth),
+                                                 C.c_int(1 if first else 0), _p(bg), _p(bh)))
+        return bad, bg, bh
+
     def set_gravity(self, par, G, nmesh, asmth):
         self.L.ref_step_set_gravity(C.c_double(G), C.c_int(nmesh), C.c_double(asmth), C.c_double(par["ErrTolForceAcc"]),
                                     C.c_double(par["BHOpeningAngle"]), C.c_double(par["MaxBHOpeningAngle"]), C.c_int(par["TreeUseBH"]),

@@ -725,6 +725,16 @@ int ref_step_hydro_timesteps(const double *maxsig, double atime, int first, unsi
     for(int64_t i = 0; i < n; i++) bin_hydro_out[i] = P[i].TimeBinHydro;
     return bad;
 }
+/* find_timesteps (timestep.c:739-853), the SplitGravityTimestepsOn = 0 path: one bin per particle from the gravity
+ * and (gas) hydro criteria.  Returns the bad-step count; both bin arrays [n] out. */
+int ref_step_find_timesteps(const double *maxsig, double atime, double asmth, int first, unsigned char *bin_grav_out, unsigned char *bin_hydro_out)
+{
+    const int64_t n = PartManager->NumPart;
+    for(int64_t i = 0; i < n; i++) if(P[i].Type == 0) SPHP(i).MaxSignalVel = maxsig[i];
+    const int bad = find_timesteps(&stepAct, &stepT, atime, 2, &stepCP, asmth, first);
+    for(int64_t i = 0; i < n; i++) { bin_grav_out[i] = P[i].TimeBinGravity; bin_hydro_out[i] = P[i].TimeBinHydro; }
+    return bad;
+}
 /* Short-range gravity parameters of the hierarchy (as ref_grav_short_tree above) */
 void ref_step_set_gravity(double G, int Nmesh, double Asmth, double ErrTolForceAcc, double BHOpeningAngle,
                           double MaxBHOpeningAngle, int TreeUseBH, double Rcut, double GravitySoftening)

@@ -180,6 +180,15 @@ class StepOracle:
                                            C.c_double(atime), C.c_double(float(self.hubble(atime))))
         return int(bad), self.bin_hydro.copy()
 
+    def find_timesteps(self, maxsig, atime, asmth, first=False):
+        ms = np.ascontiguousarray(maxsig, np.float64)
+        nl = self.n if self.act is None else len(self.act)
+        bad = self.L.oracle_find_timesteps(C.byref(self.tl), C.byref(self.cosmo), C.byref(self.sp), C.byref(self.t), C.c_int64(self.n), _p(self.act),
+                                           C.c_int64(nl), _p(self.type), _p(self.flags), _p(self.mass), _p(self.vel), _p(self.fullacc), _p(self.gravpm),
+                                           _p(self.hsml), _p(self.dthsml), _p(ms), _p(self.bin_grav), _p(self.bin_hydro),
+                                           C.c_int(1 if self.is_pm() else 0), C.c_double(atime), C.c_int(2), C.c_double(asmth))
+        return int(bad), self.bin_grav.copy(), self.bin_hydro.copy()
+
     # --- hierarchy
     def set_gravity(self, par, G, nmesh, asmth):
         self.gp = GravShortParams(**par); self.G, self.nmesh, self.asmth = G, nmesh, asmth

@@ -64,6 +64,12 @@ static inline unsigned long long atomicMin(unsigned long long *p, unsigned long 
     while(v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     return old;
 }
+static inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v)
+{
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while(v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 extern double emul_xchg[1024];
 static inline double __shfl_xor_sync(unsigned, double v, int o)      /* every thread of the block takes part */
 {

@@ -98,6 +98,15 @@ def run_primitives(S, d):
     _load(S, d); S.set_times(scal, kick, last); S.build_active()
     bad, bh = S.hydro_timesteps(d["maxsig"], atime)
     out["hydro_bad"] = np.int64(bad); out["hydro_bins"] = np.array(bh, np.uint8); out["hydro_times"] = S.get_times()[0].copy()
+    # the SplitGravityTimestepsOn = 0 assignment (find_timesteps), off and on a PM step
+    S.set_gravity(importlib.import_module("mp-gadget_b200.ics").tree_params(d["box"], len(d["mass"])), G, 64, 1.5)
+    for tag, pm in (("find", False), ("findpm", True)):
+        scal, kick, last = primitives_times(pm=pm)
+        _load(S, d); S.set_times(scal, kick, last); S.build_active()
+        at = float(np.exp(S.loga_from_ti(int(scal[3]))))
+        bad, bg, bh = S.find_timesteps(d["maxsig"], at, 1.5 * d["box"] / 64)
+        out[tag + "_bad"] = np.int64(bad); out[tag + "_bin_grav"] = np.array(bg, np.uint8); out[tag + "_bin_hydro"] = np.array(bh, np.uint8)
+        out[tag + "_times"] = S.get_times()[0].copy()
     # PM step: implicit list
     scal, kick, last = primitives_times(pm=True)
     _load(S, d); S.set_times(scal, kick, last)

@@ -34,7 +34,8 @@ def close(a, b, rtol=RTOL):
 
 def check_primitives(out, gold=GOLD, rtol=RTOL):
     for k in ("active", "active_counts", "last_drift", "sublist36", "sublist37", "sublist41", "pmkick_times", "kick_times",
-              "pm_active_counts", "pm_sublist38", "hydro_bad", "hydro_bins", "hydro_times"):
+              "pm_active_counts", "pm_sublist38", "hydro_bad", "hydro_bins", "hydro_times", "find_bad", "find_bin_grav", "find_bin_hydro",
+              "find_times", "findpm_bad", "findpm_bin_grav", "findpm_bin_hydro", "findpm_times"):
         assert np.array_equal(out[k], gold["prim/" + k]), k
     for k in ("ddrift", "drift_pos", "drift_hsml", "halfkick_vel", "halfkick_entropy", "hydrokick_vel", "hydrokick_entropy", "pmkick_vel"):
         assert close(out[k], gold["prim/" + k], rtol), k
