@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRCS = [os.path.join(ROOT, "mp-gadget_b200", "csrc", f) for f in ("steploop.cu", "domain_keys.cu")]
 SRC = SRCS[0]
-OUT = os.path.join(HERE, "_build")
+ASAN = os.environ.get("EMUL_ASAN") == "1"     # address-sanitised build: run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+OUT = os.path.join(HERE, "_build_asan" if ASAN else "_build")
 SO = os.path.join(OUT, "libsteploop_emul.so")
 
 
@@ -53,7 +54,7 @@ def build(force=False):
     assert total >= 12, total
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], stdout=subprocess.DEVNULL)
     inc = ["-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "mp-gadget_b200", "csrc")]
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas",
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off"] + (["-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else []) + [ "-Wall", "-Wno-unknown-pragmas",
                            "-Wno-unused-function", "-DSTEP_BLOCKS=4", "-o", SO] + gens + [os.path.join(HERE, "emul_mocks.cpp")] + inc +
                           ["-L", os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     return SO

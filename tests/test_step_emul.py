@@ -20,3 +20,15 @@ def test_steploop_source_under_emulation(which):
     if "skip:" in r.stdout:
         pytest.skip(r.stdout.strip().splitlines()[-1])
     assert which + " ok" in r.stdout
+
+
+def test_steploop_emulation_under_address_sanitizer():
+    """The same runs with the emulated CUDA sources compiled -fsanitize=address: every `device` buffer is a red-zoned heap
+    block, so an out-of-range index in a kernel or a host driver aborts here instead of corrupting memory on the GPU."""
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    env = dict(os.environ, OMP_WAIT_POLICY="passive", EMUL_ASAN="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    for which in ("primitives", "hierarchy", "domain"):
+        r = subprocess.run([sys.executable, os.path.join(HERE, "emul", "run_emul.py"), which], env=env, capture_output=True, text=True, timeout=1800)
+        assert r.returncode == 0 and which + " ok" in r.stdout, r.stdout[-2000:] + r.stderr[-6000:]
