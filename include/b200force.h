@@ -339,6 +339,7 @@ typedef struct b200_step_state {      /* host arrays in particle-index order, an
 typedef struct b200_step_state_out {  /* host outputs, any may be NULL */
     double *pos, *vel, *fullacc, *hsml, *entropy;
     uint8_t *bin_grav, *bin_hydro;
+    double *hydroacc, *dtentropy, *maxsignalvel;   /* SphP[].HydroAccel [n][3], DtEntropy [n], MaxSignalVel [n] */
 } b200_step_state_out;
 typedef struct b200_step_times {      /* DriftKickTimes, timestep.h:10-26 */
     int32_t mintimebin, maxtimebin, mingravtimebin, pad_;

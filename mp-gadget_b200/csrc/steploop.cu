@@ -486,6 +486,12 @@ int step_get_state(Engine *E, b200_step_state_out *o)
     if(o->entropy) CK(cudaMemcpyAsync(o->entropy, E->s_entropy.p, n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
     if(o->bin_grav) CK(cudaMemcpyAsync(o->bin_grav, E->s_bin_grav.p, n, cudaMemcpyDeviceToHost, E->stream));
     if(o->bin_hydro) CK(cudaMemcpyAsync(o->bin_hydro, E->s_bin_hydro.p, n, cudaMemcpyDeviceToHost, E->stream));
+    if(o->hydroacc) CK(cudaMemcpyAsync(o->hydroacc, E->s_hydroacc.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    if(o->dtentropy) CK(cudaMemcpyAsync(o->dtentropy, E->s_dtentropy.p, n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    if(o->maxsignalvel) {
+        if(!E->st_maxsig_valid) return failmsg(E, "b200_step_get_state: no MaxSignalVel on the device");
+        CK(cudaMemcpyAsync(o->maxsignalvel, E->st_maxsig.p, n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+    }
     CK(cudaStreamSynchronize(E->stream));
     return 0;
 }

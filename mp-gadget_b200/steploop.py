@@ -22,7 +22,8 @@ class StepState(C.Structure):
 
 
 class StepStateOut(C.Structure):
-    _fields_ = [(k, C.c_void_p) for k in ("pos", "vel", "fullacc", "hsml", "entropy", "bin_grav", "bin_hydro")]
+    _fields_ = [(k, C.c_void_p) for k in ("pos", "vel", "fullacc", "hsml", "entropy", "bin_grav", "bin_hydro", "hydroacc", "dtentropy",
+                                          "maxsignalvel")]
 
 
 class StepTimes(C.Structure):
@@ -193,6 +194,24 @@ class StepEngine:
                     t.Ti_kick[b] += dti_from_timebin(b) // 2
             for b in range(1, t.mintimebin):
                 t.Ti_kick[b] += dti_from_timebin(t.mintimebin) // 2
+
+    # --- gas sub-step on the device (run.c:466-495): active list + tables to the SPH module, hydro results back
+    def sph_prepare(self, tables):
+        """tables: dict of per-bin arrays gravkick, hydrokick, dloga_pred, drift, dloga_bin (b200_sph_bins)"""
+        t = np.zeros((5, NBINS))
+        for r, k in enumerate(("gravkick", "hydrokick", "dloga_pred", "drift", "dloga_bin")):
+            v = np.asarray(tables[k], dtype=np.float64)[:NBINS]
+            t[r, :len(v)] = v
+        self._ck(self.L.b200_step_sph_prepare(self.ctx, _p(t)))
+
+    def adopt_hydro(self):
+        """-> dict(hydroacc, dtentropy, maxsignalvel) as now held in the step state"""
+        self._ck(self.L.b200_step_adopt_hydro(self.ctx))
+        n = self.n
+        out = dict(hydroacc=np.zeros((n, 3)), dtentropy=np.zeros(n), maxsignalvel=np.zeros(n))
+        so = StepStateOut(**{k: v.ctypes.data for k, v in out.items()})
+        self._ck(self.L.b200_step_get_state(self.ctx, C.byref(so)))
+        return out
 
     def hydro_timesteps(self, maxsig, atime, first=False):
         """find_hydro_timesteps on the current active list -> (bad count, TimeBinHydro[n])"""

@@ -58,3 +58,53 @@ def test_gpu_dropin_step_shims(stepper):
     S = R.RefStep(nthreads=2, arena_gib=1.0, so=R.SO_DROPIN_STEP, **SC.TIMELINE)
     TS.check_primitives(SC.run_primitives(S, SC.primitives_inputs()))
     TS.check_hierarchy(SC.run_hierarchy(S, SC.hierarchy_inputs()), rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["clustered16", "zeldovich16"])
+def test_gpu_gas_substep_device_resident(b200, name):
+    """The mixed-time-bin density + hydro step of tests/test_sph.py (golden of the reference's own density.c / hydra.c,
+    tests/golden/ref_sph_mixed.npz), but fed from the step state on the device: b200_step_set_state ->
+    b200_step_build_active (must find the reference's active list) -> b200_step_sph_prepare -> b200_density ->
+    b200_hydro_force -> b200_step_adopt_hydro, no per-particle host array in between."""
+    import importlib
+    import test_sph as SPH
+    try:
+        e = b200.Engine(0)
+    except Exception as ex:
+        pytest.skip("no CUDA device (%s)" % ex)
+    SL = importlib.import_module("mp-gadget_b200.steploop")
+    M = SPH.MIXED
+    pos, mass, vel, ent, box, h0 = SPH._inputs(name)
+    n = len(mass)
+    m = lambda k: M[name + "/" + k]
+    tb = {k: M["tables/" + k] for k in ("gravkick", "hydrokick", "drift", "dloga_pred", "dloga_bin")}
+    bins, act = m("bins"), m("active")
+    Ti = int(M["Ti_Current"])
+    active_bin = np.array([b <= 0 or Ti % (1 << b) == 0 for b in range(47)])
+    tabs = dict(gravkick=tb["gravkick"][:47], hydrokick=tb["hydrokick"][:47], dloga_pred=tb["dloga_pred"][:47],
+                drift=np.where(active_bin, 0.0, tb["drift"][:47]), dloga_bin=tb["dloga_bin"][:47])
+    S = SL.StepEngine(e, np.log([0.1, 1.0]), lambda k, a, b: 0.0, lambda a: 0.2)
+    S.set_particles(pos, mass, np.zeros(n, np.uint8), box, vel=m("vel_new"), fullacc=m("fullacc"), bin_grav=bins, bin_hydro=bins,
+                    hsml=m("sync_hsml"), hydroacc=m("sync_hydro_acc"), entropy=ent, dtentropy=m("sync_hydro_dtentropy"))
+    scal = np.zeros(7, np.int64); scal[3] = Ti; scal[4] = 1 << 40; scal[0] = 1; scal[1] = 46          # not a PM step
+    S.set_times(scal, np.zeros(47, np.int64), np.zeros(47, np.int64))
+    lst, counts = S.build_active()
+    assert np.array_equal(lst, act)
+    e.force_tree_build(box, mask=1)
+    S.sph_prepare(tabs)
+    e.sph_set_state(density=m("sync_density"), egywtdensity=m("sync_egywtdensity"), dhsmlfac=m("sync_dhsmlfac"),
+                    divvel=m("sync_divvel"), curlvel=m("sync_curlvel"))
+    sp = b200.sph_params(KernelType=2, MinGasHsml=0.006, DensityIndependentSphOn=1, atime=0.5, hubble=0.2, pmkick=float(tb["gravkick"][47]))
+    d = e.density(sp, update_hsml=1, DoEgyDensity=1)
+    h = e.hydro_force(sp)
+    for k in SPH.DENS_KEYS:
+        assert SPH._close(d[k][act], m("mixed_" + k)[act], 1e-11), k
+    for k in ("acc", "dtentropy", "maxsignalvel"):
+        assert SPH._close(h[k][act], m("mixed_" + k)[act], 1e-10), k
+    a = S.adopt_hydro()
+    inact = np.setdiff1d(np.arange(n), act)
+    assert np.array_equal(a["hydroacc"][act], h["acc"][act]) and np.array_equal(a["dtentropy"][act], h["dtentropy"][act])
+    assert np.array_equal(a["maxsignalvel"][act], h["maxsignalvel"][act])
+    assert np.array_equal(a["hydroacc"][inact], m("sync_hydro_acc")[inact])          # inactive gas keeps its stale state
+    assert np.array_equal(S.get()["hsml"][act], d["hsml"][act])                      # the converged Hsml is the state's Hsml
+    e.close()
