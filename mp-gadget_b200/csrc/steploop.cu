@@ -455,7 +455,7 @@ int step_set_state(Engine *E, const b200_step_state *s)
         CK(it.dst->ensure(it.k * n));
         if(it.src) CK(cudaMemcpyAsync(it.dst->p, it.src, it.k * E->n * sizeof(double), cudaMemcpyHostToDevice, E->stream));
         else CK(cudaMemsetAsync(it.dst->p, 0, it.k * n * sizeof(double), E->stream));
-        if(it.have >= 0) E->s_have[it.have] = true;
+        if(it.have >= 0) E->s_have[it.have] = it.src != nullptr;      // the SPH module's "NULL = default" rules stay in force
     }
     CK(E->s_bin_grav.ensure(n)); CK(E->s_bin_hydro.ensure(n));
     if(s->bin_grav) CK(cudaMemcpyAsync(E->s_bin_grav.p, s->bin_grav, E->n, cudaMemcpyHostToDevice, E->stream));
