@@ -307,6 +307,8 @@ def main():
     ap.add_argument("--cpu-ng", type=int, default=128, help="CPU-baseline sample size per dimension")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hydro", action="store_true", help="skip the SPH density + hydro timing (configs[2] gas part)")
+    ap.add_argument("--steploop", action="store_true", help="also time hierarchical KDK sub-steps with the particle state resident "
+                    "in HBM (b200_step_*; off by default until its first hardware run)")
     ap.add_argument("--ics", default="planewave", choices=["planewave", "fft"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -513,6 +515,23 @@ def main():
             out["hydro"] = rec
         except Exception as ex:
             out["hydro"] = {"failed": repr(ex)}
+    if args.steploop and world == 1:
+        # sub-steps of the hierarchical integrator (run.c:355-800) without the 160-byte record round trip
+        try:
+            SL = importlib.import_module("mp-gadget_b200.steploop")
+            cosmo = ics.FlatLCDM()
+            rng = np.random.default_rng(2)
+            S = SL.StepEngine(e, cosmo.sync, cosmo.factor, cosmo.hubble, Omega0=cosmo.Omega0, Hubble=cosmo.Hubble, G=G)
+            S.set_particles(pos, mass, np.ones(n, np.uint8), box, vel=0.05 * rng.standard_normal((n, 3)))
+            S.set_gravity(ics.tree_params(box, n, treeusebh=2), G, nmesh, 1.5)
+            S.set_times(np.zeros(7, np.int64), np.zeros(47, np.int64), np.zeros(47, np.int64))
+            sub = []
+            for k in range(9):
+                t0 = time.perf_counter(); bad, info = S.advance(first=(k == 0), pm=True); dt = time.perf_counter() - t0
+                sub.append({"wall_ms": 1e3 * dt, "active": int(info[1]), "is_pm": int(info[2]), "bad": bad})
+            out["steploop"] = {"substeps": sub, "host_bytes_per_substep": "scalars only", "aos_roundtrip_bytes_per_force_call": 2 * 160 * n}
+        except Exception as ex:
+            out["steploop"] = {"failed": repr(ex)}
     if not args.no_cpu and world == 1:
         try:
             v, kind, t, nm = cpu_force_step(args.cpu_ng, steps=1, warmup=0)

@@ -134,3 +134,34 @@ def planewave_lattice(ng, box, xplanes=None, seed=181170, rms=0.2, nmodes=64, km
     pos[pos >= box] = 0.0
     mass = torch.full((pos.shape[0],), OMEGA0 * rho_crit() * spacing ** 3, dtype=torch.float32, device=dev)
     return pos.contiguous(), mass
+
+
+class FlatLCDM:
+    """What the reference's host takes from cosmology.c / timefac.c / timebinmgr.c, for bench and tool runs of the step
+    loop: hubble_function for a flat matter + Lambda background, the drift / kick integrals of timefac.c:12-73
+    (Gauss-Legendre instead of gsl_integration_qag) and loga_from_ti over a sync-point table."""
+    TIMEBINS = 46
+
+    def __init__(self, sync_a=(0.1, 0.2, 0.5, 1.0), Omega0=OMEGA0, Hubble=0.1):
+        self.sync = np.log(np.asarray(sync_a, np.float64)); self.Omega0 = Omega0; self.Hubble = Hubble
+        self.gx, self.gw = np.polynomial.legendre.leggauss(16)
+
+    def hubble(self, a):
+        return self.Hubble * np.sqrt(self.Omega0 / a ** 3 + 1 - self.Omega0)
+
+    def loga_from_ti(self, ti):
+        s = ti >> self.TIMEBINS
+        step = 0.0 if s >= len(self.sync) - 1 else (self.sync[s + 1] - self.sync[s]) / (1 << self.TIMEBINS)
+        return self.sync[s] + (ti & ((1 << self.TIMEBINS) - 1)) * step
+
+    def factor(self, kind, t0, t1):
+        """kind 0 drift, 1 gravkick, 2 hydrokick between two integer times"""
+        if t0 == t1:
+            return 0.0
+        a0, a1 = np.exp(self.loga_from_ti(t0)), np.exp(self.loga_from_ti(t1))
+        e = np.linspace(a0, a1, 17)
+        a = 0.5 * (e[1:] + e[:-1])[:, None] + 0.5 * (e[1:] - e[:-1])[:, None] * self.gx[None, :]
+        w = 0.5 * (e[1:] - e[:-1])[:, None] * self.gw[None, :]
+        h = self.hubble(a)
+        f = (1 / (h * a ** 3), 1 / (h * a ** 2), 1 / (h * a ** (3 * (5.0 / 3 - 1)) * a))[kind]
+        return float((w * f).sum())

@@ -3,8 +3,7 @@ Hierarchical KDK sub-steps with the particle state resident in HBM (mp-gadget_b2
 plane-wave-displaced 128^3 / 256^3 DM box: wall time per sub-step against the number of
 gravitationally active particles, the host<->device bytes per sub-step (scalars only), and for comparison
 the 160-byte-record round trip the host-resident loop would pay per force call (b200_force_step_aos).
-The cosmology callables (what the reference host takes from cosmology.c / timefac.c) are a flat matter + Lambda
-background and Gauss-Legendre integrals of the timefac.c:12-38 integrands, written out here.
+The cosmology callables (what the reference host takes from cosmology.c / timefac.c) are ics.FlatLCDM.
 usage: python tools/steploop_bench.py [ng ...]   -> gpurun_out/steploop_bench.json"""
 import importlib
 import json
@@ -17,33 +16,8 @@ sys.path.insert(0, "."); sys.path.insert(0, "tests")
 pkg = importlib.import_module("mp-gadget_b200"); ics = importlib.import_module("mp-gadget_b200.ics")
 SL = importlib.import_module("mp-gadget_b200.steploop")
 G = 43.0071
-OM, H0 = 0.288, 0.1
-sync = np.log(np.array([0.1, 0.2, 0.5, 1.0]))
-TB = 46
-GX, GW = np.polynomial.legendre.leggauss(16)
-
-
-def hubble(a):
-    return H0 * np.sqrt(OM / a ** 3 + 1 - OM)
-
-
-def loga_from_ti(ti):
-    s = ti >> TB
-    step = 0.0 if s >= len(sync) - 1 else (sync[s + 1] - sync[s]) / (1 << TB)
-    return sync[s] + (ti & ((1 << TB) - 1)) * step
-
-
-def factor(kind, t0, t1):
-    if t0 == t1:
-        return 0.0
-    a0, a1 = np.exp(loga_from_ti(t0)), np.exp(loga_from_ti(t1))
-    edges = np.linspace(a0, a1, 17)
-    a = (0.5 * (edges[1:] + edges[:-1])[:, None] + 0.5 * (edges[1:] - edges[:-1])[:, None] * GX[None, :])
-    w = 0.5 * (edges[1:] - edges[:-1])[:, None] * GW[None, :]
-    f = {0: 1 / (hubble(a) * a ** 3), 1: 1 / (hubble(a) * a ** 2), 2: 1 / (hubble(a) * a ** (3 * (5.0 / 3 - 1)) * a)}[kind]
-    return float((w * f).sum())
-
-
+cosmo = ics.FlatLCDM()
+sync = cosmo.sync
 out = {}
 for ng in [int(a) for a in sys.argv[1:]] or [128, 256]:
     box = 1000.0 * ng
@@ -53,7 +27,7 @@ for ng in [int(a) for a in sys.argv[1:]] or [128, 256]:
     rng = np.random.default_rng(2)
     vel = 30.0 * rng.standard_normal((n, 3))
     e = pkg.Engine(0)
-    S = SL.StepEngine(e, sync, factor, hubble, Omega0=OM, Hubble=H0, G=G)
+    S = SL.StepEngine(e, sync, cosmo.factor, cosmo.hubble, Omega0=cosmo.Omega0, Hubble=cosmo.Hubble, G=G)
     S.set_particles(pos, mass, np.ones(n, np.uint8), box, vel=vel)
     S.set_gravity(ics.tree_params(box, n, treeusebh=2), G, 3 * ng, 1.5)
     S.set_times(np.zeros(7, np.int64), np.zeros(47, np.int64), np.zeros(47, np.int64))
