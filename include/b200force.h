@@ -423,6 +423,12 @@ int b200_domain_set_topnodes(b200_ctx *ctx, int32_t ntop, const int32_t *daughte
                              const int32_t *shift, const int32_t *leaf);
 /* P[i].TopLeaf = domain_get_topleaf(key_i) (domain.h:71-78) from the keys of the last b200_domain_peano_keys */
 int b200_domain_topleaf(b200_ctx *ctx, int32_t *topleaf_out);
+/* TopLeafCount of domain_compute_costs (domain.c:1396-1451): particles per top leaf from the last b200_domain_topleaf,
+ * garbage skipped */
+int b200_domain_leaf_counts(b200_ctx *ctx, int32_t nleaf, int64_t *counts_out);
+/* domain_assign_topleaves_balanced (domain.c:610-755): task of every top leaf (leaves in key order) from the per-leaf
+ * cost; host arithmetic, no context.  Non-zero where the reference would endrun. */
+int b200_domain_assign_balanced(int32_t ntask, int32_t nleaf, const int64_t *cost, int32_t nseg_per_task, int32_t *task_out);
 
 /* Device-side timing of the phases of the last call, milliseconds (CUDA
  * events on the engine's stream).  Names follow the reference's walltime

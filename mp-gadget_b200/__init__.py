@@ -98,7 +98,7 @@ EXPORTED = [
     "b200_step_set_state", "b200_step_get_state", "b200_step_adopt_forces", "b200_step_drift", "b200_step_build_active",
     "b200_step_active_sublist", "b200_step_get_active", "b200_step_half_kick", "b200_step_pm_kick",
     "b200_step_hier_accelerations", "b200_step_hier_timesteps", "b200_step_hydro_timesteps", "b200_step_find_timesteps", "b200_step_set_active", "b200_step_get_store", "b200_step_set_store", "b200_step_sph_prepare", "b200_step_adopt_hydro",
-    "b200_domain_peano_keys", "b200_domain_set_topnodes", "b200_domain_topleaf",
+    "b200_domain_peano_keys", "b200_domain_set_topnodes", "b200_domain_topleaf", "b200_domain_leaf_counts", "b200_domain_assign_balanced",
 ]
 
 
@@ -371,8 +371,22 @@ class Engine:
         self._ck(self.L.b200_domain_topleaf(self.ctx, _p(out)))
         return out[:self.n]
 
+    def leaf_counts(self, nleaf):
+        """TopLeafCount (domain.c:1396-1451) of the last topleaf() -> int64[nleaf]"""
+        out = np.zeros(nleaf, np.int64)
+        self._ck(self.L.b200_domain_leaf_counts(self.ctx, C.c_int32(nleaf), _p(out)))
+        return out
+
     def kernel_launches(self):
         return int(self.L.b200_kernel_launches(self.ctx))
 
     def stream(self):
         return self.L.b200_stream(self.ctx)
+
+
+def domain_assign_balanced(ntask, cost, nseg_per_task=1):
+    """domain_assign_topleaves_balanced (domain.c:610-755) over leaves in key order -> task per leaf"""
+    cost = _c(cost, np.int64); task = np.zeros(len(cost), np.int32)
+    if lib().b200_domain_assign_balanced(C.c_int32(ntask), C.c_int32(len(cost)), _p(cost), C.c_int32(nseg_per_task), _p(task)) != 0:
+        raise B200Error("b200_domain_assign_balanced: the leaves cannot be dealt out to %d tasks" % ntask)
+    return task

@@ -82,6 +82,16 @@ k_domain_topleaf(int64_t n, const unsigned long long *__restrict__ keys, const i
     out[i] = leaf[no];
 }
 
+// TopLeafCount of domain_compute_costs (domain.c:1396-1451): particles per top leaf, garbage skipped
+__global__ void __launch_bounds__(256)
+k_domain_leaf_counts(int64_t n, const int *__restrict__ topleaf, const uint8_t *__restrict__ flags, int nleaf, unsigned long long *__restrict__ counts)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n || (flags[i] & 1)) return;
+    const int l = topleaf[i];
+    if(l >= 0 && l < nleaf) atomicAdd(&counts[l], 1ull);
+}
+
 int domain_peano_keys(Engine *E, double BoxSize, uint64_t *keys_out)
 {
     if(!(BoxSize > 0)) return failmsg(E, "b200_domain_peano_keys: bad box size");
@@ -133,12 +143,68 @@ int domain_topleaf(Engine *E, int32_t *topleaf_out)
         if(topleaf_out) CK(cudaMemcpyAsync(topleaf_out, E->dk_topleaf.p, (size_t) E->n * sizeof(int32_t), cudaMemcpyDeviceToHost, E->stream));
     }
     CK(cudaStreamSynchronize(E->stream));
+    E->dk_topleaf_n = E->n;
     return 0;
+}
+
+int domain_leaf_counts(Engine *E, int32_t nleaf, int64_t *counts_out)
+{
+    if(nleaf < 1 || !counts_out) return failmsg(E, "b200_domain_leaf_counts: bad arguments");
+    if(E->dk_topleaf_n != E->n) return failmsg(E, "b200_domain_leaf_counts: call b200_domain_topleaf first");
+    CK(E->dk_counts.ensure((size_t) nleaf));
+    CK(cudaMemsetAsync(E->dk_counts.p, 0, (size_t) nleaf * sizeof(unsigned long long), E->stream));
+    if(E->n > 0) {
+        k_domain_leaf_counts<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->n, E->dk_topleaf.p, E->flags.p, nleaf, E->dk_counts.p);
+        CKL(E);
+    }
+    CK(cudaMemcpyAsync(counts_out, E->dk_counts.p, (size_t) nleaf * sizeof(int64_t), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
+// domain_assign_topleaves_balanced (domain.c:610-755) over leaves in key order: host arithmetic on NTopLeaves numbers.
+// Returns 0, or 1 where the reference would endrun (fewer segments than asked for, cost not fully assigned).
+int domain_assign_balanced(int ntask, int32_t nleaf, const int64_t *cost, int nseg_per_task, int32_t *task)
+{
+    if(ntask < 1 || nseg_per_task < 1 || nleaf < ntask * nseg_per_task || !cost || !task) return 1;
+    const int nsegment = ntask * nseg_per_task;
+    int64_t total = 0;
+    for(int32_t i = 0; i < nleaf; i++) { total += cost[i]; task[i] = -1; }
+    int64_t left = total;
+    double mean_expected = 1.0 * total / nsegment, mean_task = 1.0 * total / ntask;
+    int curleaf = 0, curseg = 0, curtask = 0, nrounds = 0;
+    int64_t curload = 0, curtaskload = 0;
+    while(nrounds < nleaf) {
+        bool append = false, advance = false;
+        if(curleaf == nleaf) advance = true;
+        else if(nleaf - curleaf == nsegment - curseg) append = advance = true;       // one leaf per remaining segment
+        else {
+            const int64_t assigned = (total - left) + curload;
+            if(mean_expected * (curseg + 1) - assigned > 0.5 * cost[curleaf] || curload == 0) append = true;
+            else advance = true;
+        }
+        if(append) { curload += cost[curleaf]; task[curleaf] = curtask; curleaf++; }
+        if(advance) {
+            curtaskload += curload;
+            if(mean_task - curtaskload < 0.5 * mean_expected || nsegment - curseg <= ntask - curtask) { curtaskload = 0; curtask++; }
+            left -= curload;
+            curload = 0;
+            curseg++;
+            if(curtask == ntask) {
+                curtask = 0;
+                mean_expected = 1.0 * left / nsegment;
+                mean_task = 1.0 * left / ntask;
+                nrounds++;
+            }
+            if(curleaf == nleaf) break;
+        }
+    }
+    return (curseg < nsegment || left != 0) ? 1 : 0;
 }
 
 void domain_release(Engine *E)
 {
-    E->dk_keys.release(); E->dk_tab.release(); E->dk_daughter.release(); E->dk_startkey.release(); E->dk_shift.release(); E->dk_leaf.release(); E->dk_topleaf.release();
+    E->dk_keys.release(); E->dk_tab.release(); E->dk_daughter.release(); E->dk_startkey.release(); E->dk_shift.release(); E->dk_leaf.release(); E->dk_topleaf.release(); E->dk_counts.release();
 }
 
 } // namespace b200
@@ -153,4 +219,9 @@ int b200_domain_set_topnodes(b200_ctx *ctx, int32_t ntop, const int32_t *daughte
     return domain_set_topnodes(E, ntop, daughter, startkey, shift, leaf);
 }
 int b200_domain_topleaf(b200_ctx *ctx, int32_t *topleaf_out) { DK_ENTER(ctx); return domain_topleaf(E, topleaf_out); }
+int b200_domain_leaf_counts(b200_ctx *ctx, int32_t nleaf, int64_t *counts_out) { DK_ENTER(ctx); return domain_leaf_counts(E, nleaf, counts_out); }
+int b200_domain_assign_balanced(int32_t ntask, int32_t nleaf, const int64_t *cost, int32_t nseg_per_task, int32_t *task_out)
+{
+    return domain_assign_balanced(ntask, nleaf, cost, nseg_per_task, task_out);
+}
 }

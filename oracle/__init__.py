@@ -283,3 +283,18 @@ def topleaf(keys, daughter, startkey, shift, leaf):
     lib().oracle_topleaf(_p(keys), C.c_int64(len(keys)), _p(_c(daughter, np.int32)), _p(_c(startkey, np.uint64)), _p(_c(shift, np.int32)),
                          _p(_c(leaf, np.int32)), _p(out))
     return out
+
+
+def leaf_counts(topleaf, nleaf, flags=None):
+    """TopLeafCount of domain_compute_costs (domain.c:1398-1470)"""
+    tl = _c(topleaf, np.int32); out = np.zeros(nleaf, np.int64)
+    lib().oracle_leaf_counts(_p(tl), _p(_c(flags, np.uint8)), C.c_int64(len(tl)), C.c_int32(nleaf), _p(out))
+    return out
+
+
+def domain_assign_balanced(ntask, cost, nseg_per_task=1):
+    """domain_assign_topleaves_balanced (domain.c:610-755) over leaves in key order -> task per leaf (None where the
+    reference would stop with an error)."""
+    cost = _c(cost, np.int64); task = np.zeros(len(cost), np.int32)
+    rc = lib().oracle_domain_assign_balanced(C.c_int(ntask), C.c_int32(len(cost)), _p(cost), C.c_int(nseg_per_task), _p(task))
+    return None if rc < 0 else task

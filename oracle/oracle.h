@@ -188,6 +188,8 @@ int oracle_hier_timesteps(const oracle_timeline *tl, const oracle_cosmo *c, cons
 int oracle_peano_tables(uint8_t rank[48][8], uint8_t next[48][8]);
 uint64_t oracle_peano_key(int x, int y, int z, int bits);
 void oracle_peano_keys(const double *pos, int64_t n, double BoxSize, uint64_t *keys);
+void oracle_leaf_counts(const int32_t *topleaf, const uint8_t *flags, int64_t n, int32_t nleaf, int64_t *counts);
+int oracle_domain_assign_balanced(int ntask, int32_t nleaf, const int64_t *cost, int nseg_per_task, int32_t *task);
 void oracle_topleaf(const uint64_t *keys, int64_t n, const int32_t *daughter, const uint64_t *startkey, const int32_t *shift,
                     const int32_t *leaf, int32_t *out);
 

@@ -84,3 +84,56 @@ void oracle_topleaf(const uint64_t *keys, int64_t n, const int32_t *daughter, co
         out[i] = leaf[no];
     }
 }
+
+/* domain_compute_costs domain.c:1398-1470, the count part: particles per top leaf (garbage skipped) */
+void oracle_leaf_counts(const int32_t *topleaf, const uint8_t *flags, int64_t n, int32_t nleaf, int64_t *counts)
+{
+    for(int32_t l = 0; l < nleaf; l++) counts[l] = 0;
+    for(int64_t i = 0; i < n; i++) {
+        if(flags && (flags[i] & 1)) continue;                   /* IsGarbage, domain.c:1426-1428 */
+        counts[topleaf[i]]++;
+    }
+}
+
+/* domain_assign_topleaves_balanced domain.c:610-755 for leaves already in key order: contiguous runs of leaves
+ * (segments) of about the mean cost, handed to the tasks in order so that neighbours on the curve share a task;
+ * when every task has its share and leaves remain, a further round deals out the rest.  task[nleaf] out.
+ * Returns the number of segments made, or -1 where the reference would stop (fewer segments than tasks x
+ * nseg_per_task, cost not fully assigned). */
+int oracle_domain_assign_balanced(int ntask, int32_t nleaf, const int64_t *cost, int nseg_per_task, int32_t *task)
+{
+    const int nsegment = ntask * nseg_per_task;
+    int64_t total = 0;
+    for(int32_t i = 0; i < nleaf; i++) { total += cost[i]; task[i] = -1; }
+    int64_t left = total;
+    double mean_expected = 1.0 * total / nsegment, mean_task = 1.0 * total / ntask;
+    int curleaf = 0, curseg = 0, curtask = 0, nrounds = 0;
+    int64_t curload = 0, curtaskload = 0;
+    while(nrounds < nleaf) {
+        int append = 0, advance = 0;
+        if(curleaf == nleaf) advance = 1;
+        else if(nleaf - curleaf == nsegment - curseg) { append = 1; advance = 1; }        /* one leaf per remaining segment */
+        else {
+            const int64_t assigned = (total - left) + curload;
+            if(mean_expected * (curseg + 1) - assigned > 0.5 * cost[curleaf] || curload == 0) append = 1;
+            else advance = 1;
+        }
+        if(append) { curload += cost[curleaf]; task[curleaf] = curtask; curleaf++; }
+        if(advance) {
+            curtaskload += curload;
+            if(mean_task - curtaskload < 0.5 * mean_expected || nsegment - curseg <= ntask - curtask) { curtaskload = 0; curtask++; }
+            left -= curload;
+            curload = 0;
+            curseg++;
+            if(curtask == ntask) {
+                curtask = 0;
+                mean_expected = 1.0 * left / nsegment;
+                mean_task = 1.0 * left / ntask;
+                nrounds++;
+            }
+            if(curleaf == nleaf) break;
+        }
+    }
+    if(curseg < nsegment || left != 0) return -1;
+    return curseg;
+}

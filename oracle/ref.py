@@ -289,3 +289,36 @@ class RefStep(Ref):
 
 def step_available():
     return os.path.exists(SO_STEP)
+
+
+# file-static routines of the reference's domain.c (oracle/ref_domain_driver.c includes the file where it lies)
+SO_DOMAIN = os.path.join(_HERE, "_ref", "libref_domain.so")
+
+
+class RefDomain(Ref):
+    def __init__(self, **kw):
+        super().__init__(so=SO_DOMAIN, **kw)
+
+    # method order: leaf_counts is defined below assign_balanced
+    def assign_balanced(self, ntask, startkey, cost, nseg_per_task=1):
+        """domain_assign_topleaves_balanced for `ntask` tasks -> (task per leaf in the final order, input leaf at each position)"""
+        sk = np.ascontiguousarray(startkey, np.uint64); cost = np.ascontiguousarray(cost, np.int64)
+        task = np.zeros(len(cost), np.int32); order = np.zeros(len(cost), np.int32)
+        self.L.ref_domain_assign(C.c_int(ntask), C.c_int(len(cost)), _p(sk), _p(cost), C.c_int(nseg_per_task), _p(task), _p(order))
+        return task, order
+
+
+    def leaf_counts(self, pos, box, top, nleaf, flags=None):
+        """domain_compute_costs -> TopLeafCount[nleaf]; top = (daughter, startkey, shift, leaf)"""
+        pos = np.ascontiguousarray(pos, np.float64)
+        flags = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+        a = [np.ascontiguousarray(top[0], np.int32), np.ascontiguousarray(top[1], np.uint64), np.ascontiguousarray(top[2], np.int32),
+             np.ascontiguousarray(top[3], np.int32)]
+        out = np.zeros(nleaf, np.int64)
+        self.L.ref_domain_counts(C.c_int64(len(pos)), _p(pos), _p(flags), C.c_double(box), C.c_int(len(a[0])), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]),
+                                 C.c_int(nleaf), _p(out))
+        return out
+
+
+def domain_available():
+    return os.path.exists(SO_DOMAIN)

@@ -1,0 +1,69 @@
+/* ref_domain_driver.c -- drives file-static routines of the reference's domain.c by including that file where it
+ * lies (nothing is copied): the balanced assignment of top leaves to tasks (domain_assign_topleaves_balanced,
+ * domain.c:610-755) for any task count.  TEST INFRASTRUCTURE ONLY; pins oracle_domain_assign_balanced.
+ * The routine is pure computation; the one MPI call it makes, MPI_Comm_size, is answered by the stand-in header with
+ * the task count set here. */
+#include <libgadget/domain.c>
+
+extern int ref_stub_ntask;
+
+/* entry points of files that are not built (exchange.c, utils/mpsort.c need a real MPI; blackhole.c is sub-grid
+ * physics): domain.c links to them, the routines driven here never reach them */
+static void unreachable(const char *what) { endrun(1, "ref_domain_driver: %s reached\n", what); }
+int domain_exchange(ExchangeLayoutFunc layoutfunc, const void *layout_userdata, PreExchangeList *preexch, struct part_manager_type *pman,
+                    struct slots_manager_type *sman, int maxiter, MPI_Comm Comm) { unreachable("domain_exchange"); return 0; }
+void mpsort_mpi_impl(void *base, size_t nmemb, size_t size, void (*radix)(const void *ptr, void *radix, void *arg), size_t rsize, void *arg,
+                     MPI_Comm comm, const int line, const char *file) { unreachable("mpsort_mpi"); }
+int blackhole_dynfric_treemask(void) { return 0; }
+
+/* leaves in key order: startkey[nleaf], cost[nleaf] -> task[nleaf] (TopLeaves[].Task in the final leaf order) and
+ * order[nleaf] (which input leaf ended up at each position).  Returns 0. */
+int ref_domain_assign(int ntask, int nleaf, const uint64_t *startkey, const int64_t *cost, int nseg_per_task, int *task_out, int *order_out)
+{
+    DomainDecomp d;
+    memset(&d, 0, sizeof(d));
+    d.DomainComm = MPI_COMM_WORLD;
+    d.NTopLeaves = nleaf; d.NTopNodes = nleaf;
+    d.TopNodes = (struct topnode_data *) mymalloc("TopNodes", sizeof(struct topnode_data) * nleaf);
+    d.TopLeaves = (struct topleaf_data *) mymalloc("TopLeaves", sizeof(struct topleaf_data) * (nleaf + 1));
+    for(int i = 0; i < nleaf; i++) {
+        memset(&d.TopNodes[i], 0, sizeof(d.TopNodes[i]));
+        d.TopNodes[i].StartKey = startkey[i]; d.TopNodes[i].Daughter = -1; d.TopNodes[i].Leaf = i;
+        d.TopLeaves[i].topnode = i; d.TopLeaves[i].Task = -1;
+    }
+    int64_t *c = (int64_t *) mymalloc("cost", sizeof(int64_t) * nleaf);
+    memcpy(c, cost, sizeof(int64_t) * nleaf);
+    ref_stub_ntask = ntask;
+    domain_assign_topleaves_balanced(&d, c, nseg_per_task);
+    ref_stub_ntask = 1;
+    for(int i = 0; i < nleaf; i++) { task_out[i] = d.TopLeaves[i].Task; order_out[i] = d.TopLeaves[i].topnode; }
+    myfree(c); myfree(d.TopLeaves); myfree(d.TopNodes);
+    return 0;
+}
+
+/* domain_compute_costs (domain.c:1396-1451) over a top tree given as arrays: TopLeafCount[nleaf] of the particles
+ * (garbage skipped), leaf = domain_get_topleaf(PEANO(Pos)).  flags bit 0 = IsGarbage. */
+int ref_domain_counts(int64_t n, const double *pos, const unsigned char *flags, double BoxSize, int ntop, const int *daughter,
+                      const uint64_t *startkey, const int *shift, const int *leaf, int nleaf, int64_t *counts_out)
+{
+    particle_alloc_memory(PartManager, BoxSize, n);
+    PartManager->NumPart = n;
+    for(int64_t i = 0; i < n; i++) {
+        memset(&P[i], 0, sizeof(P[i]));
+        for(int k = 0; k < 3; k++) P[i].Pos[k] = pos[3 * i + k];
+        P[i].IsGarbage = flags ? (flags[i] & 1) : 0;
+    }
+    DomainDecomp d;
+    memset(&d, 0, sizeof(d));
+    d.DomainComm = MPI_COMM_WORLD;
+    d.NTopLeaves = nleaf; d.NTopNodes = ntop;
+    d.TopNodes = (struct topnode_data *) mymalloc("TopNodes", sizeof(struct topnode_data) * ntop);
+    for(int t = 0; t < ntop; t++) {
+        memset(&d.TopNodes[t], 0, sizeof(d.TopNodes[t]));
+        d.TopNodes[t].Daughter = daughter[t]; d.TopNodes[t].StartKey = startkey[t]; d.TopNodes[t].Shift = shift[t]; d.TopNodes[t].Leaf = leaf[t];
+    }
+    domain_compute_costs(&d, NULL, counts_out);
+    myfree(d.TopNodes);
+    myfree(P);
+    return 0;
+}

@@ -107,6 +107,7 @@ int param_get_int(ParameterSet *ps, const char *name)
 #endif
 int param_get_enum(ParameterSet *ps, const char *name) { endrun(1, "ref_driver: unexpected enum %s\n", name); return 0; }
 
+int ref_stub_ntask = 1;          /* what the stand-in MPI_Comm_size reports (oracle/stubs/mpi.h) */
 static struct ClockTable CT;
 static int initialised = 0;
 static DomainDecomp dd;

@@ -51,7 +51,10 @@ static inline int MPI_Init(int *a, char ***b) { return 0; }
 static inline int MPI_Init_thread(int *a, char ***b, int req, int *prov) { if(prov) *prov = req; return 0; }
 static inline int MPI_Finalize(void) { return 0; }
 static inline int MPI_Comm_rank(MPI_Comm c, int *r) { *r = 0; return 0; }
-static inline int MPI_Comm_size(MPI_Comm c, int *s) { *s = 1; return 0; }
+/* 1 everywhere, except while a fixture drives a pure-computation routine of the reference for several tasks
+ * (oracle/ref_domain_driver.c sets ref_stub_ntask around the call) */
+extern int ref_stub_ntask;
+static inline int MPI_Comm_size(MPI_Comm c, int *s) { *s = ref_stub_ntask; return 0; }
 static inline int MPI_Barrier(MPI_Comm c) { return 0; }
 static inline int MPI_Abort(MPI_Comm c, int e) { fprintf(stderr, "MPI_Abort(%d)\n", e); abort(); return 0; }
 static inline double MPI_Wtime(void) { return omp_get_wtime(); }
@@ -71,6 +74,8 @@ static inline int MPI_Type_free(MPI_Datatype *t) { return 0; }
 static inline int MPI_Type_get_extent(MPI_Datatype t, MPI_Aint *lb, MPI_Aint *ext) { *lb = 0; *ext = t; return 0; }
 static inline int MPI_Isend(const void *b, int n, MPI_Datatype t, int d, int tag, MPI_Comm c, MPI_Request *r) { fprintf(stderr, "stub MPI_Isend reached\n"); abort(); return 0; }
 static inline int MPI_Irecv(void *b, int n, MPI_Datatype t, int s, int tag, MPI_Comm c, MPI_Request *r) { fprintf(stderr, "stub MPI_Irecv reached\n"); abort(); return 0; }
+static inline int MPI_Send(const void *b, int n, MPI_Datatype t, int d, int tag, MPI_Comm c) { fprintf(stderr, "stub MPI_Send reached\n"); abort(); return 0; }
+static inline int MPI_Recv(void *b, int n, MPI_Datatype t, int s, int tag, MPI_Comm c, MPI_Status *st) { fprintf(stderr, "stub MPI_Recv reached\n"); abort(); return 0; }
 static inline int MPI_Waitall(int n, MPI_Request *r, MPI_Status *s) { return 0; }
 static inline int MPI_Waitsome(int n, MPI_Request *r, int *outcount, int *idx, MPI_Status *s) { *outcount = MPI_UNDEFINED; return 0; }
 static inline int MPI_Wait(MPI_Request *r, MPI_Status *s) { return 0; }

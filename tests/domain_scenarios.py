@@ -37,3 +37,32 @@ def refined_toptree(seed=4, nrefine=40):
     for k, t in enumerate(order):
         leaf[t] = k
     return (np.array(daughter, np.int32), np.array(startkey, np.uint64), np.array(shift, np.int32), np.array(leaf, np.int32))
+
+
+def garbage_flags(n, seed=6):
+    rng = np.random.default_rng(seed)
+    return (rng.random(n) < 0.02).astype(np.uint8)
+
+
+def assign_cases(seed=3, ncase=120):
+    """(ntask, cost[nleaf]) pairs for the balanced top-leaf assignment: flat, heavy-tailed, many empty leaves, equal costs,
+    as few leaves as tasks."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for trial in range(ncase):
+        ntask = int(rng.choice([1, 2, 3, 4, 8, 16]))
+        nleaf = ntask if trial % 15 == 14 else int(rng.integers(ntask, 40 * ntask))
+        kind = trial % 4
+        if kind == 0:
+            cost = rng.integers(0, 1000, nleaf)
+        elif kind == 1:
+            cost = (rng.pareto(1.2, nleaf) * 100).astype(np.int64)
+        elif kind == 2:
+            cost = np.where(rng.random(nleaf) < 0.3, 0, rng.integers(1, 50, nleaf))
+        else:
+            cost = np.full(nleaf, 17)
+        cost = cost.astype(np.int64)
+        if cost.sum() == 0:
+            cost[0] = 1
+        out.append((ntask, cost))
+    return out

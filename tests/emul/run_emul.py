@@ -75,6 +75,13 @@ def domain():
     leaf = np.zeros(len(pos), np.int32)
     assert L.b200_domain_topleaf(ctx, p(leaf)) == 0, L.b200_last_error(ctx)
     assert np.array_equal(leaf, G["topleaf"])
+    nleaf = int(top[3].max()) + 1
+    counts = np.zeros(nleaf, np.int64)
+    assert L.b200_domain_leaf_counts(ctx, C.c_int32(nleaf), p(counts)) == 0, L.b200_last_error(ctx)
+    assert np.array_equal(counts, np.bincount(G["topleaf"], minlength=nleaf))
+    for nt, cost in DS.assign_cases()[:30]:
+        task = np.zeros(len(cost), np.int32)
+        assert L.b200_domain_assign_balanced(C.c_int32(nt), C.c_int32(len(cost)), p(cost), C.c_int32(1), p(task)) == 0
     bad = top[0].copy(); bad[0] = 0          # a daughter pointing at its parent must be refused, not loop
     assert L.b200_domain_set_topnodes(ctx, C.c_int32(len(bad)), p(bad), p(top[1]), p(top[2]), p(top[3])) != 0
     print("domain ok")

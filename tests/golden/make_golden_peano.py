@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """Generate tests/golden/ref_peano.npz: (1) the 64 known-answer Peano-Hilbert keys of the reference's own
 libgadget/tests/test_peano.c:107 (read from that file), (2) PEANO() of its compiled utils/peano.c on random
-positions incl. the box faces, (3) domain_get_topleaf (domain.h:71-78) over a randomly refined top tree.
+positions incl. the box faces, (3) domain_get_topleaf (domain.h:71-78) over a randomly refined top tree, (4) the per-leaf particle counts of
+domain_compute_costs and (5) domain_assign_topleaves_balanced for 120 cost distributions and 1-16 tasks, both
+file-static in domain.c and reached by including that file in oracle/ref_domain_driver.c.
 Run in the build container:  make -C oracle ref && python tests/golden/make_golden_peano.py"""
 import os
 import re
@@ -25,6 +27,16 @@ def main():
     top = DS.refined_toptree()
     leaf = r.topleaf(keys, *top)
     out = dict(known_keys=known, random_keys=keys, topleaf=leaf, ntop=np.int64(len(top[0])), nleaf=np.int64(leaf.max() + 1))
+    # domain_compute_costs and domain_assign_topleaves_balanced, file-static in domain.c (oracle/ref_domain_driver.c)
+    D = R.RefDomain(arena_gib=1.0, nthreads=2)
+    nleaf = int(top[3].max()) + 1
+    out["leaf_counts"] = D.leaf_counts(pos, box, top, nleaf, flags=DS.garbage_flags(len(pos)))
+    tasks = []
+    for ntask, cost in DS.assign_cases():
+        t, order = D.assign_balanced(ntask, np.arange(len(cost), dtype=np.uint64) * 8, cost)
+        per_leaf = np.zeros(len(cost), np.int32); per_leaf[order] = t
+        tasks.append(per_leaf)
+    out["assign_tasks"] = np.concatenate(tasks)
     path = os.path.join(ROOT, "tests", "golden", "ref_peano.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; top nodes", len(top[0]), "leaves used", len(np.unique(leaf)))

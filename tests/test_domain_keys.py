@@ -41,6 +41,29 @@ def test_oracle_keys_and_topleaf_equal_reference():
     assert np.array_equal(oracle.topleaf(keys, *top), GOLD["topleaf"])
 
 
+def test_oracle_leaf_counts_and_balanced_assignment_equal_reference():
+    pos, box = DS.random_positions()
+    top = DS.refined_toptree()
+    nleaf = int(top[3].max()) + 1
+    leaf = oracle.topleaf(oracle.peano_keys(pos, box), *top)
+    counts = oracle.leaf_counts(leaf, nleaf, flags=DS.garbage_flags(len(pos)))
+    assert np.array_equal(counts, GOLD["leaf_counts"]) and counts.sum() == len(pos) - DS.garbage_flags(len(pos)).sum()
+    got = np.concatenate([oracle.domain_assign_balanced(nt, cost) for nt, cost in DS.assign_cases()])
+    assert np.array_equal(got, GOLD["assign_tasks"])
+    # properties: tasks non-decreasing along the curve within a round, every task used, loads near the mean for flat costs
+    for nt, cost in DS.assign_cases()[:40]:
+        t = oracle.domain_assign_balanced(nt, cost)
+        assert set(t) == set(range(nt))
+
+
+def test_product_host_assignment_equals_reference(b200):
+    """b200_domain_assign_balanced is host arithmetic inside libb200force.so: callable without a GPU."""
+    got = np.concatenate([b200.domain_assign_balanced(nt, cost) for nt, cost in DS.assign_cases()])
+    assert np.array_equal(got, GOLD["assign_tasks"])
+    with pytest.raises(b200.B200Error):
+        b200.domain_assign_balanced(8, np.ones(3, np.int64))            # fewer leaves than tasks
+
+
 @pytest.mark.skipif(not R.available(), reason="oracle/_ref/libref_tree.so not built")
 def test_oracle_equals_reference_live():
     r = R.load()
@@ -65,5 +88,10 @@ def test_gpu_domain_keys(b200):
     pos, box = DS.random_positions()
     e.set_particles(pos, np.ones(len(pos), np.float32))
     assert np.array_equal(e.peano_keys(box), GOLD["random_keys"])
-    assert np.array_equal(e.topleaf(*DS.refined_toptree()), GOLD["topleaf"])
+    top = DS.refined_toptree()
+    assert np.array_equal(e.topleaf(*top), GOLD["topleaf"])
+    counts = e.leaf_counts(int(top[3].max()) + 1)
+    assert counts.sum() == len(pos)
+    leaf = GOLD["topleaf"]
+    assert np.array_equal(counts, np.bincount(leaf, minlength=len(counts)))
     e.close()
