@@ -423,6 +423,23 @@ int b200_domain_set_topnodes(b200_ctx *ctx, int32_t ntop, const int32_t *daughte
                              const int32_t *shift, const int32_t *leaf);
 /* P[i].TopLeaf = domain_get_topleaf(key_i) (domain.h:71-78) from the keys of the last b200_domain_peano_keys */
 int b200_domain_topleaf(b200_ctx *ctx, int32_t *topleaf_out);
+/* The top tree (domain_determine_global_toptree, domain.c:1281-1340) stage by stage.  The device supplies the keys of
+ * the subsample (every `subsample`-th particle, domain.c:1066-1074: 8 N / subsample bytes cross PCIe); the tree itself --
+ * hundreds to thousands of nodes -- is sequential integer work on the host, as in the reference:
+ *   local (domain_check_for_local_refine_subsample, sorts the keys in place) -> truncate with the limits from the
+ *   summed root counts -> pairwise merge of the ranks' trees (domain_nonrecursively_combine_topTree) ->
+ *   global_refine -> leaves (domain_create_topleaves; TopNodes[] = StartKey / Shift / Daughter of the nodes + leaf_out).
+ * Status: 0 ok, 1 out of nodes (retry with a larger maxnodes, domain.c:186-193), 2 the samples are too clustered,
+ * 3 bad arguments. */
+typedef struct b200_topnode {         /* struct local_topnode_data, domain.c:60-70 */
+    uint64_t StartKey; int32_t Shift, Daughter, Parent, pad_; int64_t Count, Cost;
+} b200_topnode;
+int b200_domain_sample_keys(b200_ctx *ctx, double BoxSize, int32_t subsample, uint64_t *keys_out, int64_t *nsample);
+int b200_domain_toptree_local(uint64_t *sample_keys, int64_t nsample, b200_topnode *tree, int32_t *size, int32_t maxnodes);
+int b200_domain_toptree_truncate(b200_topnode *tree, int32_t *size, int64_t countlimit, int64_t costlimit);
+int b200_domain_toptree_merge(b200_topnode *treeA, int32_t *sizeA, const b200_topnode *treeB, int32_t maxnodes);
+int b200_domain_toptree_global_refine(b200_topnode *tree, int32_t *size, int32_t maxnodes, int64_t countlimit, int64_t costlimit);
+int b200_domain_toptree_leaves(const b200_topnode *tree, int32_t size, int32_t *leaf_out, int32_t *nleaf);
 /* TopLeafCount of domain_compute_costs (domain.c:1396-1451): particles per top leaf from the last b200_domain_topleaf,
  * garbage skipped */
 int b200_domain_leaf_counts(b200_ctx *ctx, int32_t nleaf, int64_t *counts_out);

@@ -99,6 +99,8 @@ EXPORTED = [
     "b200_step_active_sublist", "b200_step_get_active", "b200_step_half_kick", "b200_step_pm_kick",
     "b200_step_hier_accelerations", "b200_step_hier_timesteps", "b200_step_hydro_timesteps", "b200_step_find_timesteps", "b200_step_set_active", "b200_step_get_store", "b200_step_set_store", "b200_step_sph_prepare", "b200_step_adopt_hydro",
     "b200_domain_peano_keys", "b200_domain_set_topnodes", "b200_domain_topleaf", "b200_domain_leaf_counts", "b200_domain_assign_balanced",
+    "b200_domain_sample_keys", "b200_domain_toptree_local", "b200_domain_toptree_truncate", "b200_domain_toptree_merge",
+    "b200_domain_toptree_global_refine", "b200_domain_toptree_leaves",
 ]
 
 
@@ -371,6 +373,12 @@ class Engine:
         self._ck(self.L.b200_domain_topleaf(self.ctx, _p(out)))
         return out[:self.n]
 
+    def sample_keys(self, box, subsample):
+        """keys of every subsample-th particle (domain.c:1066-1074) -> uint64[n // subsample]"""
+        keys = np.zeros(max(self.n // subsample, 1), np.uint64); ns = C.c_int64()
+        self._ck(self.L.b200_domain_sample_keys(self.ctx, C.c_double(box), C.c_int32(subsample), _p(keys), C.byref(ns)))
+        return keys[:ns.value]
+
     def leaf_counts(self, nleaf):
         """TopLeafCount (domain.c:1396-1451) of the last topleaf() -> int64[nleaf]"""
         out = np.zeros(nleaf, np.int64)
@@ -390,3 +398,35 @@ def domain_assign_balanced(ntask, cost, nseg_per_task=1):
     if lib().b200_domain_assign_balanced(C.c_int32(ntask), C.c_int32(len(cost)), _p(cost), C.c_int32(nseg_per_task), _p(task)) != 0:
         raise B200Error("b200_domain_assign_balanced: the leaves cannot be dealt out to %d tasks" % ntask)
     return task
+
+
+TOPNODE_DTYPE = np.dtype([("StartKey", "u8"), ("Shift", "i4"), ("Daughter", "i4"), ("Parent", "i4"), ("pad_", "i4"), ("Count", "i8"), ("Cost", "i8")])
+
+
+class TopTree:
+    """b200_domain_toptree_* (host side of the domain decomposition, domain.c:826-1395); .tree is the node array."""
+
+    def __init__(self, maxnodes):
+        self.nodes = np.zeros(maxnodes, TOPNODE_DTYPE); self.size = C.c_int32(0); self.maxnodes = maxnodes
+
+    @property
+    def tree(self):
+        return self.nodes[:self.size.value]
+
+    def local(self, sample_keys):
+        k = np.array(sample_keys, np.uint64, copy=True)
+        return lib().b200_domain_toptree_local(_p(k), C.c_int64(len(k)), _p(self.nodes), C.byref(self.size), C.c_int32(self.maxnodes))
+
+    def truncate(self, countlimit, costlimit):
+        return lib().b200_domain_toptree_truncate(_p(self.nodes), C.byref(self.size), C.c_int64(countlimit), C.c_int64(costlimit))
+
+    def merge(self, other):
+        return lib().b200_domain_toptree_merge(_p(self.nodes), C.byref(self.size), _p(other.nodes), C.c_int32(self.maxnodes))
+
+    def global_refine(self, countlimit, costlimit):
+        return lib().b200_domain_toptree_global_refine(_p(self.nodes), C.byref(self.size), C.c_int32(self.maxnodes), C.c_int64(countlimit), C.c_int64(costlimit))
+
+    def leaves(self):
+        leaf = np.zeros(self.size.value, np.int32); nl = C.c_int32()
+        lib().b200_domain_toptree_leaves(_p(self.nodes), self.size, _p(leaf), C.byref(nl))
+        return nl.value, leaf

@@ -10,6 +10,7 @@
 // with the r-th of eight child symmetries (swap y,z | swap x,z twice | flip x,y twice | swap x,z + flip x,z twice |
 // swap y,z + flip y,z).  Both kernels are one thread per particle and HBM-bound (24 B in, 8 B out; 8 B in, 4 B out).
 #include <string.h>
+#include <algorithm>
 #include "engine.h"
 
 namespace b200 {
@@ -49,8 +50,8 @@ static int ph_tables(uint8_t *tab)
 }
 
 __global__ void __launch_bounds__(256)
-k_domain_keys(int64_t n, const double *__restrict__ pos, double Box, double fac, const uint8_t *__restrict__ tab,
-              unsigned long long *__restrict__ keys)
+k_domain_keys(int64_t n, int64_t stride, const double *__restrict__ pos, double Box, double fac, const uint8_t *__restrict__ tab,
+              unsigned long long *__restrict__ keys)      // keys[i] = key of particle i * stride
 {
     __shared__ uint8_t s_tab[768];
     for(int k = threadIdx.x; k < 768; k += blockDim.x) s_tab[k] = tab[k];
@@ -58,7 +59,8 @@ k_domain_keys(int64_t n, const double *__restrict__ pos, double Box, double fac,
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) return;
     const double off = Box / 2000;                                         // peano.h:19
-    const int x = (int) ((pos[3 * i] + off) * fac), y = (int) ((pos[3 * i + 1] + off) * fac), z = (int) ((pos[3 * i + 2] + off) * fac);
+    const double *p = pos + 3 * i * stride;
+    const int x = (int) ((p[0] + off) * fac), y = (int) ((p[1] + off) * fac), z = (int) ((p[2] + off) * fac);
     unsigned long long key = 0;
     int s = 0;
 #pragma unroll 1
@@ -92,21 +94,45 @@ k_domain_leaf_counts(int64_t n, const int *__restrict__ topleaf, const uint8_t *
     if(l >= 0 && l < nleaf) atomicAdd(&counts[l], 1ull);
 }
 
+static int domain_need_tables(Engine *E)
+{
+    if(E->dk_tab.p) return 0;
+    uint8_t tab[768];
+    if(ph_tables(tab) != 24) return failmsg(E, "b200_domain_peano_keys: state machine generation failed");
+    CK(E->dk_tab.ensure(768));
+    CK(cudaMemcpyAsync(E->dk_tab.p, tab, 768, cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));      // tab is a stack array
+    return 0;
+}
+
+// The subsample domain_check_for_local_refine_subsample builds its skeleton from (PreSort = 0, domain.c:1066-1074):
+// the key of every `subsample`-th particle in memory order; only these 8 N / subsample bytes go to the host.
+int domain_sample_keys(Engine *E, double BoxSize, int32_t subsample, uint64_t *keys_out, int64_t *nsample_out)
+{
+    if(!(BoxSize > 0) || subsample < 1 || !keys_out || !nsample_out) return failmsg(E, "b200_domain_sample_keys: bad arguments");
+    int64_t ns = E->n / subsample;
+    if(ns == 0 && E->n != 0) ns = 1;                                       // :1033-1035
+    *nsample_out = ns;
+    if(ns == 0) return 0;
+    if(int rc = domain_need_tables(E)) return rc;
+    CK(E->dk_sample.ensure((size_t) ns));
+    const double fac = 1.0 / (BoxSize * 1.001) * (double) (1ull << PH_BITS);
+    k_domain_keys<<<(unsigned) ((ns + 255) / 256), 256, 0, E->stream>>>(ns, subsample, E->pos.p, BoxSize, fac, E->dk_tab.p, E->dk_sample.p);
+    CKL(E);
+    CK(cudaMemcpyAsync(keys_out, E->dk_sample.p, (size_t) ns * sizeof(uint64_t), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
 int domain_peano_keys(Engine *E, double BoxSize, uint64_t *keys_out)
 {
     if(!(BoxSize > 0)) return failmsg(E, "b200_domain_peano_keys: bad box size");
     const size_t n = (size_t) (E->n > 0 ? E->n : 1);
     CK(E->dk_keys.ensure(n));
-    if(!E->dk_tab.p) {
-        uint8_t tab[768];
-        if(ph_tables(tab) != 24) return failmsg(E, "b200_domain_peano_keys: state machine generation failed");
-        CK(E->dk_tab.ensure(768));
-        CK(cudaMemcpyAsync(E->dk_tab.p, tab, 768, cudaMemcpyHostToDevice, E->stream));
-        CK(cudaStreamSynchronize(E->stream));      // tab is a stack array
-    }
+    if(int rc = domain_need_tables(E)) return rc;
     const double fac = 1.0 / (BoxSize * 1.001) * (double) (1ull << PH_BITS);      // peano.h:18
     if(E->n > 0) {
-        k_domain_keys<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->n, E->pos.p, BoxSize, fac, E->dk_tab.p, E->dk_keys.p);
+        k_domain_keys<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->n, 1, E->pos.p, BoxSize, fac, E->dk_tab.p, E->dk_keys.p);
         CKL(E);
         if(keys_out) CK(cudaMemcpyAsync(keys_out, E->dk_keys.p, (size_t) E->n * sizeof(uint64_t), cudaMemcpyDeviceToHost, E->stream));
     }
@@ -202,9 +228,115 @@ int domain_assign_balanced(int ntask, int32_t nleaf, const int64_t *cost, int ns
     return (curseg < nsegment || left != 0) ? 1 : 0;
 }
 
+// ---- the top tree (domain.c:826-1395) on the host: it has a few hundred to a few thousand nodes and is built from the
+// N / 256 subsample keys, so the device's part is the keys; the stages below are sequential integer work. ----
+namespace toptree {
+using Node = b200_topnode;
+
+static int locate(const Node *t, uint64_t key)                            // domain_toptree_get_subnode :826-835
+{
+    int no = 0;
+    while(t[no].Daughter >= 0) no = t[no].Daughter + (int) ((key - t[no].StartKey) >> (t[no].Shift - 3));
+    return no;
+}
+static void make_children(Node *t, int parent, int first, int64_t count8, int64_t cost8, bool divide)
+{
+    for(int j = 0; j < 8; j++) {
+        Node &c = t[first + j];
+        c.Shift = t[parent].Shift - 3; c.pad_ = 0; c.Daughter = -1; c.Parent = parent;
+        c.StartKey = t[parent].StartKey + (uint64_t) j * (1ull << c.Shift);
+        c.Count = divide ? (j + 1) * count8 / 8 - j * count8 / 8 : count8;
+        c.Cost = divide ? (j + 1) * cost8 / 8 - j * cost8 / 8 : cost8;
+    }
+}
+static void accumulate(Node *t, int no)                                   // domain_toptree_update_cost :885-897
+{
+    if(t[no].Daughter < 0) return;
+    for(int j = 0; j < 8; j++) {
+        const int c = t[no].Daughter + j;
+        accumulate(t, c);
+        t[no].Count += t[c].Count; t[no].Cost += t[c].Cost;
+    }
+}
+// domain_check_for_local_refine_subsample :1084-1187 from the sorted keys on.  0 ok, 1 out of nodes, 2 too clustered / unsorted
+static int local(const uint64_t *keys, int64_t ns, Node *t, int32_t *size, int32_t maxnodes)
+{
+    *size = 1;
+    memset(&t[0], 0, sizeof(Node));
+    t[0].Daughter = -1; t[0].Parent = -1; t[0].Shift = 3 * PH_BITS;
+    uint64_t prev_key = ~0ull;
+    int prev_leaf = -1;
+    for(int64_t i = 0; i < ns;) {
+        const int leaf = locate(t, keys[i]);
+        if(leaf == prev_leaf && t[leaf].Shift >= 3) {                     // two samples in one leaf: refine it, re-seat the previous one
+            if(*size + 8 > maxnodes) return 1;
+            t[leaf].Daughter = *size;
+            make_children(t, leaf, *size, 0, 0, false);
+            *size += 8;
+            t[leaf].Count = 0;
+            prev_leaf = locate(t, prev_key);
+            t[prev_leaf].Count++;
+            continue;
+        }
+        if(t[leaf].Count != 0 && leaf != prev_leaf) return 2;
+        prev_key = keys[i]; prev_leaf = leaf;
+        t[leaf].Count++;
+        i++;
+    }
+    for(int k = 0; k < *size; k++) t[k].Count = 0;
+    for(int64_t i = 0; i < ns; i++) { Node &l = t[locate(t, keys[i])]; l.Count++; l.Cost++; }
+    accumulate(t, 0);
+    return 0;
+}
+static void prune(Node *t, int no, int64_t countlimit, int64_t costlimit)  // domain_toptree_truncate_r :899-916
+{
+    if(t[no].Daughter < 0) return;
+    if(t[no].Count < countlimit && t[no].Cost < costlimit) { t[no].Daughter = -1; return; }
+    for(int j = 0; j < 8; j++) prune(t, t[no].Daughter + j, countlimit, costlimit);
+}
+static void repack(Node *t, int no, int32_t *next)                         // domain_toptree_garbage_collection :927-951
+{
+    if(t[no].Daughter < 0) return;
+    const int from = t[no].Daughter, to = *next;
+    t[no].Daughter = to;
+    *next += 8;
+    for(int j = 0; j < 8; j++) { t[to + j] = t[from + j]; t[to + j].Parent = no; }
+    for(int j = 0; j < 8; j++) repack(t, to + j, next);
+}
+static int merge(Node *A, const Node *B, int a, int b, int32_t *sizeA, int32_t maxnodes)       // domain_toptree_merge :1473-1577
+{
+    if(B[b].Shift < A[a].Shift) {
+        if(A[a].Daughter < 0) {
+            if(*sizeA + 8 >= maxnodes) return 1;
+            A[a].Daughter = *sizeA;
+            make_children(A, a, *sizeA, A[a].Count - B[B[b].Parent].Count, A[a].Cost - B[B[b].Parent].Cost, true);
+            *sizeA += 8;
+        }
+        return merge(A, B, A[a].Daughter + (int) ((B[b].StartKey - A[a].StartKey) >> (A[a].Shift - 3)), b, sizeA, maxnodes);
+    }
+    if(B[b].Shift == A[a].Shift) {
+        A[a].Count += B[b].Count; A[a].Cost += B[b].Cost;
+        if(B[b].Daughter >= 0) { for(int j = 0; j < 8; j++) if(merge(A, B, a, B[b].Daughter + j, sizeA, maxnodes)) return 1; }
+        else if(A[a].Daughter >= 0) { for(int j = 0; j < 8; j++) if(merge(A, B, A[a].Daughter + j, b, sizeA, maxnodes)) return 1; }
+        return 0;
+    }
+    const int up = B[b].Shift - A[a].Shift;                                // B's node covers 2^up cells of A's size
+    if(up > 60) return 0;
+    const uint64_t cells = 1ull << up;                                     // the reference divides in unsigned arithmetic (peano_t n)
+    A[a].Count += (int64_t) ((uint64_t) B[b].Count / cells); A[a].Cost += (int64_t) ((uint64_t) B[b].Cost / cells);
+    if(A[a].Daughter >= 0) for(int j = 0; j < 8; j++) if(merge(A, B, A[a].Daughter + j, b, sizeA, maxnodes)) return 1;
+    return 0;
+}
+static void number_leaves(const Node *t, int no, int32_t *next, int32_t *leaf)   // domain_create_topleaves :810-824
+{
+    if(t[no].Daughter < 0) { leaf[no] = (*next)++; return; }
+    for(int j = 0; j < 8; j++) number_leaves(t, t[no].Daughter + j, next, leaf);
+}
+} // namespace toptree
+
 void domain_release(Engine *E)
 {
-    E->dk_keys.release(); E->dk_tab.release(); E->dk_daughter.release(); E->dk_startkey.release(); E->dk_shift.release(); E->dk_leaf.release(); E->dk_topleaf.release(); E->dk_counts.release();
+    E->dk_keys.release(); E->dk_tab.release(); E->dk_daughter.release(); E->dk_startkey.release(); E->dk_shift.release(); E->dk_leaf.release(); E->dk_topleaf.release(); E->dk_counts.release(); E->dk_sample.release();
 }
 
 } // namespace b200
@@ -220,6 +352,51 @@ int b200_domain_set_topnodes(b200_ctx *ctx, int32_t ntop, const int32_t *daughte
 }
 int b200_domain_topleaf(b200_ctx *ctx, int32_t *topleaf_out) { DK_ENTER(ctx); return domain_topleaf(E, topleaf_out); }
 int b200_domain_leaf_counts(b200_ctx *ctx, int32_t nleaf, int64_t *counts_out) { DK_ENTER(ctx); return domain_leaf_counts(E, nleaf, counts_out); }
+int b200_domain_sample_keys(b200_ctx *ctx, double BoxSize, int32_t subsample, uint64_t *keys_out, int64_t *nsample)
+{
+    DK_ENTER(ctx);
+    return domain_sample_keys(E, BoxSize, subsample, keys_out, nsample);
+}
+int b200_domain_toptree_local(uint64_t *sample_keys, int64_t nsample, b200_topnode *tree, int32_t *size, int32_t maxnodes)
+{
+    if(!tree || !size || maxnodes < 1 || nsample < 0 || (nsample > 0 && !sample_keys)) return 3;
+    std::sort(sample_keys, sample_keys + nsample);                         // qsort_openmp(LP, ..., order_by_key), domain.c:1079
+    return toptree::local(sample_keys, nsample, tree, size, maxnodes);
+}
+int b200_domain_toptree_truncate(b200_topnode *tree, int32_t *size, int64_t countlimit, int64_t costlimit)   // :953-966
+{
+    if(!tree || !size || *size < 1) return 3;
+    toptree::prune(tree, 0, countlimit, costlimit);
+    *size = 1;
+    toptree::repack(tree, 0, size);
+    return 0;
+}
+int b200_domain_toptree_merge(b200_topnode *treeA, int32_t *sizeA, const b200_topnode *treeB, int32_t maxnodes)
+{
+    if(!treeA || !sizeA || !treeB) return 3;
+    return toptree::merge(treeA, treeB, 0, 0, sizeA, maxnodes);
+}
+int b200_domain_toptree_global_refine(b200_topnode *t, int32_t *size, int32_t maxnodes, int64_t countlimit, int64_t costlimit)   // :1343-1393
+{
+    if(!t || !size) return 3;
+    for(int i = 0; i < *size; i++) {
+        if(t[i].Daughter >= 0 || t[i].Shift <= 0) continue;
+        if(t[i].Count < countlimit && t[i].Cost < costlimit) continue;
+        if(*size + 8 > maxnodes) return 1;
+        t[i].Daughter = *size;
+        toptree::make_children(t, i, *size, t[i].Count / 8, t[i].Cost / 8, false);
+        *size += 8;
+    }
+    return 0;
+}
+int b200_domain_toptree_leaves(const b200_topnode *tree, int32_t size, int32_t *leaf_out, int32_t *nleaf)
+{
+    if(!tree || size < 1 || !leaf_out || !nleaf) return 3;
+    for(int i = 0; i < size; i++) leaf_out[i] = -1;
+    *nleaf = 0;
+    toptree::number_leaves(tree, 0, nleaf, leaf_out);
+    return 0;
+}
 int b200_domain_assign_balanced(int32_t ntask, int32_t nleaf, const int64_t *cost, int32_t nseg_per_task, int32_t *task_out)
 {
     return domain_assign_balanced(ntask, nleaf, cost, nseg_per_task, task_out);

@@ -298,3 +298,35 @@ def domain_assign_balanced(ntask, cost, nseg_per_task=1):
     cost = _c(cost, np.int64); task = np.zeros(len(cost), np.int32)
     rc = lib().oracle_domain_assign_balanced(C.c_int(ntask), C.c_int32(len(cost)), _p(cost), C.c_int(nseg_per_task), _p(task))
     return None if rc < 0 else task
+
+
+TOPNODE_DTYPE = np.dtype([("StartKey", "u8"), ("Shift", "i4"), ("Daughter", "i4"), ("Parent", "i4"), ("pad_", "i4"), ("Count", "i8"), ("Cost", "i8")])
+
+
+class TopTree:
+    """The top tree of the domain decomposition stage by stage (domain.c:826-1395); .nodes[:size] is the tree."""
+
+    def __init__(self, maxnodes):
+        self.nodes = np.zeros(maxnodes, TOPNODE_DTYPE); self.size = C.c_int32(0); self.maxnodes = maxnodes
+
+    @property
+    def tree(self):
+        return self.nodes[:self.size.value]
+
+    def local(self, sample_keys):
+        k = np.sort(_c(sample_keys, np.uint64))
+        return lib().oracle_toptree_local(_p(k), None, C.c_int64(len(k)), _p(self.nodes), C.byref(self.size), C.c_int32(self.maxnodes))
+
+    def truncate(self, countlimit, costlimit):
+        lib().oracle_toptree_truncate(_p(self.nodes), C.byref(self.size), C.c_int64(countlimit), C.c_int64(costlimit))
+
+    def merge(self, other):
+        return lib().oracle_toptree_merge(_p(self.nodes), C.byref(self.size), _p(other.nodes), C.c_int32(self.maxnodes))
+
+    def global_refine(self, countlimit, costlimit):
+        return lib().oracle_toptree_global_refine(_p(self.nodes), C.byref(self.size), C.c_int32(self.maxnodes), C.c_int64(countlimit), C.c_int64(costlimit))
+
+    def leaves(self):
+        leaf = np.zeros(self.size.value, np.int32)
+        nl = lib().oracle_toptree_leaves(_p(self.nodes), self.size, _p(leaf))
+        return nl, leaf

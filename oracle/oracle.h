@@ -188,6 +188,13 @@ int oracle_hier_timesteps(const oracle_timeline *tl, const oracle_cosmo *c, cons
 int oracle_peano_tables(uint8_t rank[48][8], uint8_t next[48][8]);
 uint64_t oracle_peano_key(int x, int y, int z, int bits);
 void oracle_peano_keys(const double *pos, int64_t n, double BoxSize, uint64_t *keys);
+/* the top tree, domain.c:826-1395; node layout = struct local_topnode_data (domain.c:60-70) */
+typedef struct oracle_topnode { uint64_t StartKey; int32_t Shift, Daughter, Parent, pad_; int64_t Count, Cost; } oracle_topnode;
+int oracle_toptree_local(const uint64_t *sorted_keys, const int64_t *cost, int64_t nsample, oracle_topnode *tree, int32_t *size, int32_t maxnodes);
+void oracle_toptree_truncate(oracle_topnode *tree, int32_t *size, int64_t countlimit, int64_t costlimit);
+int oracle_toptree_merge(oracle_topnode *treeA, int32_t *sizeA, const oracle_topnode *treeB, int32_t maxnodes);
+int oracle_toptree_global_refine(oracle_topnode *tree, int32_t *size, int32_t maxnodes, int64_t countlimit, int64_t costlimit);
+int32_t oracle_toptree_leaves(const oracle_topnode *tree, int32_t size, int32_t *leaf_out);
 void oracle_leaf_counts(const int32_t *topleaf, const uint8_t *flags, int64_t n, int32_t nleaf, int64_t *counts);
 int oracle_domain_assign_balanced(int ntask, int32_t nleaf, const int64_t *cost, int nseg_per_task, int32_t *task);
 void oracle_topleaf(const uint64_t *keys, int64_t n, const int32_t *daughter, const uint64_t *startkey, const int32_t *shift,

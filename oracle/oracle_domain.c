@@ -137,3 +137,161 @@ int oracle_domain_assign_balanced(int ntask, int32_t nleaf, const int64_t *cost,
     if(curseg < nsegment || left != 0) return -1;
     return curseg;
 }
+
+/* ---- the top tree: domain.c:826-1395 ---- */
+static int32_t tt_find(const oracle_topnode *t, uint64_t key)              /* domain_toptree_get_subnode :826-835 */
+{
+    int32_t no = 0;
+    while(t[no].Daughter >= 0) no = t[no].Daughter + (int32_t) ((key - t[no].StartKey) >> (t[no].Shift - 3));
+    return no;
+}
+static int tt_split(oracle_topnode *t, int32_t *size, int32_t maxnodes, int32_t i)      /* domain_toptree_split :849-883 */
+{
+    if(*size + 8 > maxnodes) return 1;
+    if(t[i].Shift < 3) return -1;                                           /* the reference stops: particles overly clustered */
+    t[i].Daughter = *size;
+    *size += 8;
+    for(int j = 0; j < 8; j++) {
+        oracle_topnode *s = &t[t[i].Daughter + j];
+        s->Daughter = -1; s->Parent = i; s->Shift = t[i].Shift - 3; s->pad_ = 0;
+        s->StartKey = t[i].StartKey + (uint64_t) j * (((uint64_t) 1) << s->Shift);
+        s->Count = 0; s->Cost = 0;
+    }
+    return 0;
+}
+static void tt_sum(oracle_topnode *t, int32_t no)                           /* domain_toptree_update_cost :885-897 */
+{
+    if(t[no].Daughter == -1) return;
+    for(int j = 0; j < 8; j++) {
+        const int32_t sub = t[no].Daughter + j;
+        tt_sum(t, sub);
+        t[no].Count += t[sub].Count; t[no].Cost += t[sub].Cost;
+    }
+}
+/* domain_check_for_local_refine_subsample :1084-1187 from the sorted subsample keys on: the skeleton in which no two
+ * samples share a leaf (scanning sorted keys, either the leaf of the previous sample is refined or a fresh leaf is
+ * entered), then counts and costs.  cost == NULL: 1 per sample.  Returns 0, 1 out of nodes, -1 where the reference stops. */
+int oracle_toptree_local(const uint64_t *keys, const int64_t *cost, int64_t nsample, oracle_topnode *t, int32_t *size, int32_t maxnodes)
+{
+    *size = 1;
+    memset(&t[0], 0, sizeof(t[0]));
+    t[0].Daughter = -1; t[0].Parent = -1; t[0].Shift = 21 * 3;
+    uint64_t last_key = UINT64_MAX;
+    int32_t last_leaf = -1;
+    int64_t i = 0;
+    while(i < nsample) {
+        const int32_t leaf = tt_find(t, keys[i]);
+        if(leaf == last_leaf && t[leaf].Shift >= 3) {
+            const int rc = tt_split(t, size, maxnodes, leaf);
+            if(rc) return rc;
+            t[leaf].Count = 0;
+            last_leaf = tt_find(t, last_key);
+            t[last_leaf].Count++;
+            continue;
+        }
+        if(t[leaf].Count != 0 && leaf != last_leaf) return -1;
+        last_key = keys[i];
+        last_leaf = leaf;
+        t[leaf].Count++;
+        i++;
+    }
+    for(int32_t k = 0; k < *size; k++) t[k].Count = 0;
+    for(i = 0; i < nsample; i++) {
+        const int32_t leaf = tt_find(t, keys[i]);
+        t[leaf].Count++; t[leaf].Cost += cost ? cost[i] : 1;
+    }
+    tt_sum(t, 0);
+    return 0;
+}
+static void tt_cut(oracle_topnode *t, int32_t no, int64_t countlimit, int64_t costlimit)   /* domain_toptree_truncate_r :899-916 */
+{
+    if(t[no].Daughter == -1) return;
+    if(t[no].Count < countlimit && t[no].Cost < costlimit) { t[no].Daughter = -1; return; }
+    for(int j = 0; j < 8; j++) tt_cut(t, t[no].Daughter + j, countlimit, costlimit);
+}
+static void tt_compact(oracle_topnode *t, int32_t no, int32_t *next)        /* domain_toptree_garbage_collection :927-951 */
+{
+    if(t[no].Daughter == -1) return;
+    const int32_t from = t[no].Daughter, to = *next;
+    t[no].Daughter = to;
+    *next += 8;
+    for(int j = 0; j < 8; j++) { t[to + j] = t[from + j]; t[to + j].Parent = no; }
+    for(int j = 0; j < 8; j++) tt_compact(t, to + j, next);
+}
+void oracle_toptree_truncate(oracle_topnode *t, int32_t *size, int64_t countlimit, int64_t costlimit)      /* :953-966 */
+{
+    tt_cut(t, 0, countlimit, costlimit);
+    *size = 1;
+    tt_compact(t, 0, size);
+}
+/* domain_toptree_merge :1473-1577: B's counts and refinement into A */
+static int tt_merge(oracle_topnode *A, const oracle_topnode *B, int32_t a, int32_t b, int32_t *sizeA, int32_t maxnodes)
+{
+    if(B[b].Shift < A[a].Shift) {
+        if(A[a].Daughter < 0) {
+            if(*sizeA + 8 >= maxnodes) return 1;
+            const int64_t count = A[a].Count - B[B[b].Parent].Count, cost = A[a].Cost - B[B[b].Parent].Cost;
+            A[a].Daughter = *sizeA;
+            for(int j = 0; j < 8; j++) {
+                oracle_topnode *s = &A[A[a].Daughter + j];
+                s->Shift = A[a].Shift - 3; s->pad_ = 0;
+                s->Count = (j + 1) * count / 8 - j * count / 8;
+                s->Cost = (j + 1) * cost / 8 - j * cost / 8;
+                s->Daughter = -1; s->Parent = a;
+                s->StartKey = A[a].StartKey + (uint64_t) j * (((uint64_t) 1) << s->Shift);
+            }
+            *sizeA += 8;
+        }
+        const int32_t sub = A[a].Daughter + (int32_t) ((B[b].StartKey - A[a].StartKey) >> (A[a].Shift - 3));
+        return tt_merge(A, B, sub, b, sizeA, maxnodes);
+    }
+    if(B[b].Shift == A[a].Shift) {
+        A[a].Count += B[b].Count; A[a].Cost += B[b].Cost;
+        if(B[b].Daughter >= 0) {
+            for(int j = 0; j < 8; j++) if(tt_merge(A, B, a, B[b].Daughter + j, sizeA, maxnodes)) return 1;
+        } else if(A[a].Daughter >= 0) {
+            for(int j = 0; j < 8; j++) if(tt_merge(A, B, A[a].Daughter + j, b, sizeA, maxnodes)) return 1;
+        }
+        return 0;
+    }
+    /* B's node is the larger one: spread its counts evenly over the A cells it covers */
+    uint64_t nn = ((uint64_t) 1) << (B[b].Shift - A[a].Shift);
+    if(B[b].Shift - A[a].Shift > 60) nn = 0;
+    if(nn > 0) {
+        A[a].Count += (int64_t) ((uint64_t) B[b].Count / nn); A[a].Cost += (int64_t) ((uint64_t) B[b].Cost / nn);   /* unsigned, as peano_t n */
+        if(A[a].Daughter >= 0)
+            for(int j = 0; j < 8; j++) if(tt_merge(A, B, A[a].Daughter + j, b, sizeA, maxnodes)) return 1;
+    }
+    return 0;
+}
+int oracle_toptree_merge(oracle_topnode *A, int32_t *sizeA, const oracle_topnode *B, int32_t maxnodes) { return tt_merge(A, B, 0, 0, sizeA, maxnodes); }
+/* domain_global_refine :1343-1393 */
+int oracle_toptree_global_refine(oracle_topnode *t, int32_t *size, int32_t maxnodes, int64_t countlimit, int64_t costlimit)
+{
+    for(int32_t i = 0; i < *size; i++) {
+        if(t[i].Daughter >= 0 || t[i].Shift <= 0) continue;
+        if(t[i].Count < countlimit && t[i].Cost < costlimit) continue;
+        if(*size + 8 > maxnodes) return 1;
+        t[i].Daughter = *size;
+        for(int j = 0; j < 8; j++) {
+            oracle_topnode *s = &t[t[i].Daughter + j];
+            s->Shift = t[i].Shift - 3; s->pad_ = 0; s->Count = t[i].Count / 8; s->Cost = t[i].Cost / 8; s->Daughter = -1; s->Parent = i;
+            s->StartKey = t[i].StartKey + (uint64_t) j * (((uint64_t) 1) << s->Shift);
+        }
+        *size += 8;
+    }
+    return 0;
+}
+/* domain_create_topleaves :810-824: leaves numbered along the curve */
+static void tt_leaves(const oracle_topnode *t, int32_t no, int32_t *next, int32_t *leaf)
+{
+    if(t[no].Daughter == -1) { leaf[no] = (*next)++; return; }
+    for(int j = 0; j < 8; j++) tt_leaves(t, t[no].Daughter + j, next, leaf);
+}
+int32_t oracle_toptree_leaves(const oracle_topnode *t, int32_t size, int32_t *leaf)
+{
+    for(int32_t i = 0; i < size; i++) leaf[i] = -1;
+    int32_t next = 0;
+    tt_leaves(t, 0, &next, leaf);
+    return next;
+}

@@ -320,5 +320,37 @@ class RefDomain(Ref):
         return out
 
 
+    # --- the top tree, stage by stage (ref_domain_driver.c); trees are numpy arrays of oracle.TOPNODE_DTYPE
+    def toptree_local(self, pos, box, subsample, maxnodes, flags=None, presort=0):
+        from . import TOPNODE_DTYPE
+        assert self.L.ref_toptree_node_size() == TOPNODE_DTYPE.itemsize
+        pos = np.ascontiguousarray(pos, np.float64)
+        flags = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+        tree = np.zeros(maxnodes, TOPNODE_DTYPE); size = C.c_int(0)
+        rc = self.L.ref_toptree_local(C.c_int64(len(pos)), _p(pos), _p(flags), C.c_double(box), C.c_int(subsample), C.c_int(presort),
+                                      C.c_int(maxnodes), _p(tree), C.byref(size))
+        return rc, tree, size.value
+
+    def toptree_truncate(self, tree, size, countlimit, costlimit):
+        s = C.c_int(size)
+        self.L.ref_toptree_truncate(_p(tree), C.byref(s), C.c_int64(countlimit), C.c_int64(costlimit))
+        return s.value
+
+    def toptree_merge(self, treeA, sizeA, treeB):
+        s = C.c_int(sizeA)
+        self.L.ref_toptree_merge(_p(treeA), C.byref(s), _p(treeB), C.c_int(len(treeA)))
+        return s.value
+
+    def toptree_global_refine(self, tree, size, countlimit, costlimit):
+        s = C.c_int(size)
+        rc = self.L.ref_toptree_global_refine(_p(tree), C.byref(s), C.c_int(len(tree)), C.c_int64(countlimit), C.c_int64(costlimit))
+        return rc, s.value
+
+    def toptree_leaves(self, tree, size):
+        leaf = np.zeros(size, np.int32)
+        nl = self.L.ref_toptree_leaves(_p(tree), C.c_int(size), _p(leaf))
+        return nl, leaf
+
+
 def domain_available():
     return os.path.exists(SO_DOMAIN)

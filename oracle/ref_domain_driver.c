@@ -67,3 +67,57 @@ int ref_domain_counts(int64_t n, const double *pos, const unsigned char *flags, 
     myfree(P);
     return 0;
 }
+
+/* ---- the top tree (domain.c:826-1395), stage by stage on struct local_topnode_data arrays (domain.c:60-70: StartKey,
+ * Shift, Daughter, Parent, Count, Cost; 40 bytes) handed in and out as raw memory ---- */
+int ref_toptree_node_size(void) { return (int) sizeof(struct local_topnode_data); }
+
+/* domain_check_for_local_refine_subsample (domain.c:1006-1187): skeleton from every `subsample`-th particle, then counts */
+int ref_toptree_local(int64_t n, const double *pos, const unsigned char *flags, double BoxSize, int subsample, int presort, int maxnodes,
+                      void *tree, int *size)
+{
+    particle_alloc_memory(PartManager, BoxSize, n);
+    PartManager->NumPart = n;
+    for(int64_t i = 0; i < n; i++) {
+        memset(&P[i], 0, sizeof(P[i]));
+        for(int k = 0; k < 3; k++) P[i].Pos[k] = pos[3 * i + k];
+        P[i].IsGarbage = flags ? (flags[i] & 1) : 0;
+    }
+    DomainDecompositionPolicy pol;
+    pol.SubSampleDistance = subsample; pol.PreSort = presort; pol.NTopLeaves = 0;
+    domain_params.DomainUseGlobalSorting = 0;
+    memset(tree, 0, sizeof(struct local_topnode_data) * maxnodes);
+    const int rc = domain_check_for_local_refine_subsample(&pol, (struct local_topnode_data *) tree, size, maxnodes, MPI_COMM_WORLD);
+    myfree(P);
+    return rc;
+}
+void ref_toptree_truncate(void *tree, int *size, int64_t countlimit, int64_t costlimit)
+{
+    domain_toptree_truncate((struct local_topnode_data *) tree, size, countlimit, costlimit);
+}
+void ref_toptree_merge(void *treeA, int *sizeA, void *treeB, int maxnodes)
+{
+    domain_toptree_merge((struct local_topnode_data *) treeA, (struct local_topnode_data *) treeB, 0, 0, sizeA, maxnodes);
+}
+int ref_toptree_global_refine(void *tree, int *size, int maxnodes, int64_t countlimit, int64_t costlimit)
+{
+    return domain_global_refine((struct local_topnode_data *) tree, size, maxnodes, countlimit, costlimit);
+}
+/* domain_attempt_decompose's copy + domain_create_topleaves (domain.c:445-459,810-824): Leaf of every node (-1 inside) */
+int ref_toptree_leaves(const void *tree, int size, int *leaf_out)
+{
+    const struct local_topnode_data *t = (const struct local_topnode_data *) tree;
+    DomainDecomp d;
+    memset(&d, 0, sizeof(d));
+    d.TopNodes = (struct topnode_data *) mymalloc("TopNodes", sizeof(struct topnode_data) * size);
+    d.TopLeaves = (struct topleaf_data *) mymalloc("TopLeaves", sizeof(struct topleaf_data) * (size + 1));
+    for(int i = 0; i < size; i++) {
+        d.TopNodes[i].StartKey = t[i].StartKey; d.TopNodes[i].Shift = t[i].Shift; d.TopNodes[i].Daughter = t[i].Daughter; d.TopNodes[i].Leaf = -1;
+    }
+    d.NTopNodes = size; d.NTopLeaves = 0;
+    domain_create_topleaves(&d, 0, &d.NTopLeaves);
+    for(int i = 0; i < size; i++) leaf_out[i] = d.TopNodes[i].Leaf;
+    const int nl = d.NTopLeaves;
+    myfree(d.TopLeaves); myfree(d.TopNodes);
+    return nl;
+}

@@ -66,3 +66,37 @@ def assign_cases(seed=3, ncase=120):
             cost[0] = 1
         out.append((ntask, cost))
     return out
+
+
+def clustered(n, box, seed):
+    r = np.random.default_rng(seed)
+    pos = r.random((n, 3)) * box
+    pos[: n // 2] = box * r.random(3) + box / 20 * r.standard_normal((n // 2, 3))
+    return np.mod(pos, box)
+
+
+TOPTREE_CASES = [dict(n=(40000, 17000), box=1000.0, subsample=16, ntopleaves=32, seeds=(1, 2)),
+                 dict(n=(9000, 30000), box=250.0, subsample=4, ntopleaves=64, seeds=(3, 4)),
+                 dict(n=(25000, 25000), box=5000.0, subsample=64, ntopleaves=8, seeds=(5, 6))]
+TOPTREE_FIELDS = ("StartKey", "Shift", "Daughter", "Parent", "Count", "Cost")
+
+
+def toptree_pipeline(make_tree, sample_keys_of, case):
+    """The two-rank top tree of domain_determine_global_toptree: each rank's local tree from its subsample, truncation
+    with the limits from the summed root counts, merge of rank 1 into rank 0, global refinement, leaf numbering.
+    make_tree(maxnodes) -> object with local/truncate/merge/global_refine/leaves/.tree; sample_keys_of(pos, box, sub) -> keys.
+    Returns (tree fields dict, leaf array, nleaf, sizes after each stage)."""
+    trees, sizes = [], []
+    maxn = 8 * max(case["n"]) // case["subsample"] + 64
+    for n, seed in zip(case["n"], case["seeds"]):
+        T = make_tree(maxn)
+        assert T.local(sample_keys_of(clustered(n, case["box"], seed), case["box"], case["subsample"])) == 0
+        trees.append(T); sizes.append(len(T.tree))
+    lim = int(trees[0].tree["Count"][0] + trees[1].tree["Count"][0]) // case["ntopleaves"]
+    for T in trees:
+        T.truncate(lim, lim); sizes.append(len(T.tree))
+    A, B = trees
+    assert A.merge(B) == 0; sizes.append(len(A.tree))
+    assert A.global_refine(lim, lim) == 0; sizes.append(len(A.tree))
+    nl, leaf = A.leaves()
+    return {f: A.tree[f].copy() for f in TOPTREE_FIELDS}, leaf, nl, np.array(sizes, np.int64)

@@ -82,6 +82,11 @@ def domain():
     for nt, cost in DS.assign_cases()[:30]:
         task = np.zeros(len(cost), np.int32)
         assert L.b200_domain_assign_balanced(C.c_int32(nt), C.c_int32(len(cost)), p(cost), C.c_int32(1), p(task)) == 0
+    import oracle
+    for sub in (1, 7, 256):                  # the strided subsample keys of the top-tree build
+        ks = np.zeros(max(len(pos) // sub, 1), np.uint64); ns = C.c_int64()
+        assert L.b200_domain_sample_keys(ctx, C.c_double(box), C.c_int32(sub), p(ks), C.byref(ns)) == 0, L.b200_last_error(ctx)
+        assert ns.value == len(pos) // sub and np.array_equal(ks[:ns.value], oracle.peano_keys(pos[::sub][: len(pos) // sub], box))
     bad = top[0].copy(); bad[0] = 0          # a daughter pointing at its parent must be refused, not loop
     assert L.b200_domain_set_topnodes(ctx, C.c_int32(len(bad)), p(bad), p(top[1]), p(top[2]), p(top[3])) != 0
     print("domain ok")

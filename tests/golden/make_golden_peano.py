@@ -3,7 +3,8 @@
 libgadget/tests/test_peano.c:107 (read from that file), (2) PEANO() of its compiled utils/peano.c on random
 positions incl. the box faces, (3) domain_get_topleaf (domain.h:71-78) over a randomly refined top tree, (4) the per-leaf particle counts of
 domain_compute_costs and (5) domain_assign_topleaves_balanced for 120 cost distributions and 1-16 tasks, both
-file-static in domain.c and reached by including that file in oracle/ref_domain_driver.c.
+file-static in domain.c and reached by including that file in oracle/ref_domain_driver.c, (6) the top tree of two ranks
+through the reference's static stages (local refinement of a subsample, truncation, merge, global refinement, leaves).
 Run in the build container:  make -C oracle ref && python tests/golden/make_golden_peano.py"""
 import os
 import re
@@ -37,6 +38,27 @@ def main():
         per_leaf = np.zeros(len(cost), np.int32); per_leaf[order] = t
         tasks.append(per_leaf)
     out["assign_tasks"] = np.concatenate(tasks)
+    # the top tree of two ranks through the reference's own static stages
+    import oracle
+
+    class RefTree:
+        def __init__(self, maxnodes):
+            self.maxnodes = maxnodes; self.nodes = None; self.size = 0
+        tree = property(lambda self: self.nodes[:self.size])
+        def local(self, arg):
+            pos, bx, sub = arg
+            rc, self.nodes, self.size = D.toptree_local(pos, bx, sub, self.maxnodes)
+            return rc
+        def truncate(self, a, b): self.size = D.toptree_truncate(self.nodes, self.size, a, b)
+        def merge(self, other): self.size = D.toptree_merge(self.nodes, self.size, other.nodes); return 0
+        def global_refine(self, a, b):
+            rc, self.size = D.toptree_global_refine(self.nodes, self.size, a, b); return rc
+        def leaves(self): return D.toptree_leaves(self.nodes, self.size)
+    for k, case in enumerate(DS.TOPTREE_CASES):
+        fields, lf, nl, sizes = DS.toptree_pipeline(RefTree, lambda p_, b_, s_: (p_, b_, s_), case)
+        for f, v in fields.items():
+            out["toptree/%d/%s" % (k, f)] = v
+        out["toptree/%d/leaf" % k] = lf; out["toptree/%d/nleaf" % k] = np.int64(nl); out["toptree/%d/sizes" % k] = sizes
     path = os.path.join(ROOT, "tests", "golden", "ref_peano.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; top nodes", len(top[0]), "leaves used", len(np.unique(leaf)))

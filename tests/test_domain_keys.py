@@ -56,6 +56,31 @@ def test_oracle_leaf_counts_and_balanced_assignment_equal_reference():
         assert set(t) == set(range(nt))
 
 
+def _check_toptree(make_tree, keys_of):
+    for k, case in enumerate(DS.TOPTREE_CASES):
+        fields, leaf, nl, sizes = DS.toptree_pipeline(make_tree, keys_of, case)
+        assert np.array_equal(sizes, GOLD["toptree/%d/sizes" % k]), (k, sizes)
+        for f in DS.TOPTREE_FIELDS:
+            assert np.array_equal(fields[f], GOLD["toptree/%d/%s" % (k, f)]), (k, f)
+        assert nl == int(GOLD["toptree/%d/nleaf" % k]) and np.array_equal(leaf, GOLD["toptree/%d/leaf" % k])
+        assert nl >= case["ntopleaves"] // 2                                # a real refinement
+
+
+def _subsample_keys(pos, box, sub):
+    return oracle.peano_keys(pos[::sub][: len(pos) // sub], box)           # domain.c:1066-1074
+
+
+def test_oracle_toptree_equals_reference():
+    """Local refinement, truncation, two-rank merge, global refinement and leaf numbering, node for node."""
+    _check_toptree(oracle.TopTree, _subsample_keys)
+
+
+def test_product_host_toptree_equals_reference(b200):
+    """b200_domain_toptree_* are host functions of libb200force.so (the tree has ~10^2-10^3 nodes): checked without a GPU;
+    the subsample keys come from the oracle here and from k_domain_keys on the device (emulation / hardware tests)."""
+    _check_toptree(b200.TopTree, _subsample_keys)
+
+
 def test_product_host_assignment_equals_reference(b200):
     """b200_domain_assign_balanced is host arithmetic inside libb200force.so: callable without a GPU."""
     got = np.concatenate([b200.domain_assign_balanced(nt, cost) for nt, cost in DS.assign_cases()])
