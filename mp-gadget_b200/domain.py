@@ -1,0 +1,78 @@
+"""Host orchestration of the domain decomposition over torch.distributed (one process per GPU):
+domain_determine_global_toptree (libgadget/domain.c:1281-1340) and domain_balance (domain.c:482-502) on top of the
+C-ABI stages (b200_domain_sample_keys on the device, b200_domain_toptree_* / b200_domain_assign_balanced on the host).
+The exchanges are the reference's own -- two all-reduces, the pairwise tree merge of
+domain_nonrecursively_combine_topTree (domain.c:1190-1278), one broadcast -- carried by torch.distributed (gloo on CPU
+tests, NCCL on GPUs; the messages are a few kilobytes).  The particle exchange itself (exchange.c) is not built."""
+import numpy as np
+import torch
+
+from . import TopTree, TOPNODE_DTYPE, B200Error, domain_assign_balanced
+
+
+def _as_tensor(a):
+    return torch.from_numpy(a.view(np.uint8).reshape(-1))
+
+
+def global_toptree(sample_keys, ntopleaves, dist=None, maxnodes=None):
+    """sample_keys: this rank's subsample keys (Engine.sample_keys).  -> (TopTree, leaf number per node, nleaf), identical on
+    every rank.  ntopleaves = policy->NTopLeaves (DomainOverDecompositionFactor * NTask * (attempt + 1), domain.c:369-371)."""
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
+    if maxnodes is None:
+        maxnodes = 8 * max(len(sample_keys), 1) * world + 64 * ntopleaves
+    T = TopTree(maxnodes)
+    rc = T.local(sample_keys)
+    if rc:
+        raise B200Error("top tree: local refinement failed (%d)" % rc)
+    tot = torch.tensor([int(T.tree["Count"][0]), int(T.tree["Cost"][0])], dtype=torch.int64)
+    if dist is not None:
+        dist.all_reduce(tot)
+    countlimit, costlimit = int(tot[0]) // ntopleaves, int(tot[1]) // ntopleaves          # :1301-1302
+    T.truncate(countlimit, costlimit)
+    # domain_nonrecursively_combine_topTree: at separation sep the leaders of odd groups hand their tree to the leader of
+    # the even group on their left and drop out, until rank 0 holds the merge of all
+    alive = True
+    sep = 1
+    while sep < world:
+        if alive and rank % sep == 0:
+            if (rank // sep) % 2 == 0:
+                src = rank + sep
+                if src < world:
+                    n = torch.zeros(1, dtype=torch.int64)
+                    dist.recv(n, src=src)
+                    other = TopTree(max(int(n), T.size.value, 1))
+                    dist.recv(_as_tensor(other.nodes)[: int(n) * TOPNODE_DTYPE.itemsize], src=src)
+                    other.size.value = int(n)
+                    if T.size.value + int(n) > maxnodes or (int(n) > 0 and T.merge(other)):
+                        raise B200Error("top tree: out of nodes while merging")
+            else:
+                dist.send(torch.tensor([T.size.value], dtype=torch.int64), dst=rank - sep)
+                dist.send(_as_tensor(T.nodes)[: T.size.value * TOPNODE_DTYPE.itemsize].clone(), dst=rank - sep)
+                alive = False
+        sep *= 2
+    if dist is not None and world > 1:
+        n = torch.tensor([T.size.value if rank == 0 else 0], dtype=torch.int64)
+        dist.broadcast(n, src=0)
+        T.size.value = int(n)
+        buf = _as_tensor(T.nodes)[: int(n) * TOPNODE_DTYPE.itemsize]
+        dist.broadcast(buf, src=0)
+    if T.global_refine(countlimit, costlimit):
+        raise B200Error("top tree: out of nodes in the global refinement")
+    nleaf, leaf = T.leaves()
+    return T, leaf, nleaf
+
+
+def topnode_arrays(T, leaf):
+    """(Daughter, StartKey, Shift, Leaf) of the tree: the arguments of b200_domain_set_topnodes / Engine.topleaf"""
+    t = T.tree
+    return t["Daughter"].astype(np.int32), t["StartKey"].astype(np.uint64), t["Shift"].astype(np.int32), leaf.astype(np.int32)
+
+
+def balance(local_leaf_counts, dist=None, nseg_per_task=1):
+    """domain_balance (domain.c:482-502): summed per-leaf particle counts -> task of every top leaf (leaves in key order)."""
+    world = dist.get_world_size() if dist is not None else 1
+    c = torch.from_numpy(np.ascontiguousarray(local_leaf_counts, np.int64).copy())
+    if dist is not None:
+        dist.all_reduce(c)
+    return domain_assign_balanced(world, c.numpy(), nseg_per_task), c.numpy()

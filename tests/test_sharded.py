@@ -279,3 +279,51 @@ def test_sharded_sph_two_gpus_equal_one(b200, ics, tmp_path):
         for k in ("acc", "dtentropy", "maxsignalvel"):
             assert close(z["h_" + k], h0[k][idx], 1e-10), k
     assert seen.all()
+
+
+DOMAIN_WORKER = r'''
+import os, sys, importlib
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import oracle                                   # test side: keys / leaf lookup of a box without a GPU
+import domain_scenarios as DS
+dom = importlib.import_module("mp-gadget_b200.domain")
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+GOLD = np.load(os.path.join(%(root)r, "tests", "golden", "ref_peano.npz"))
+for k, case in enumerate(DS.TOPTREE_CASES):
+    # rank r holds the particles the reference fixture gave to rank r (world 2); with more ranks the extra ones hold few
+    if rank < 2:
+        pos = DS.clustered(case["n"][rank], case["box"], case["seeds"][rank])
+    else:
+        pos = DS.clustered(300 * rank, case["box"], 50 + rank)
+    sub = case["subsample"]
+    keys = oracle.peano_keys(pos[::sub][: len(pos) // sub], case["box"])
+    T, leaf, nleaf = dom.global_toptree(keys, case["ntopleaves"], dist)
+    if world == 2:                              # the reference's own two-rank tree, node for node
+        for f in DS.TOPTREE_FIELDS:
+            assert np.array_equal(T.tree[f], GOLD["toptree/%%d/%%s" %% (k, f)]), (k, f)
+        assert nleaf == int(GOLD["toptree/%%d/nleaf" %% k]) and np.array_equal(leaf, GOLD["toptree/%%d/leaf" %% k])
+    # every rank ends with the same tree
+    sig = torch.tensor([int(T.tree["StartKey"].sum() %% (1 << 62)), int(T.tree["Count"].sum()), nleaf], dtype=torch.int64)
+    lo, hi = sig.clone(), sig.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "trees differ between ranks"
+    # balance: counts per leaf of all particles -> tasks
+    tl = oracle.topleaf(oracle.peano_keys(pos, case["box"]), *dom.topnode_arrays(T, leaf))
+    task, counts = dom.balance(np.bincount(tl, minlength=nleaf), dist)
+    assert counts.sum() >= sum(case["n"]) and np.array_equal(task, oracle.domain_assign_balanced(world, counts))
+    load = np.bincount(task, weights=counts, minlength=world)
+    assert set(task) == set(range(world)) and load.max() <= 1.6 * load.mean(), load
+print("ok", flush=True)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_domain_toptree_and_balance_gloo(world):
+    """domain_determine_global_toptree + domain_balance over torch.distributed: world 2 reproduces the reference's own
+    two-rank top tree node for node; 3 and 4 ranks exercise the pairwise merge schedule with an odd rank count."""
+    r = _torchrun(DOMAIN_WORKER % {"root": ROOT}, world)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == world
