@@ -54,7 +54,7 @@ def build(force=False):
     assert total >= 12, total
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liboracle.so"], stdout=subprocess.DEVNULL)
     inc = ["-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "mp-gadget_b200", "csrc")]
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off"] + (["-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else []) + [ "-Wall", "-Wno-unknown-pragmas",
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off"] + (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if ASAN else []) + [ "-Wall", "-Wno-unknown-pragmas",
                            "-Wno-unused-function", "-DSTEP_BLOCKS=4", "-o", SO] + gens + [os.path.join(HERE, "emul_mocks.cpp")] + inc +
                           ["-L", os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     return SO

@@ -23,12 +23,13 @@ def test_steploop_source_under_emulation(which):
 
 
 def test_steploop_emulation_under_address_sanitizer():
-    """The same runs with the emulated CUDA sources compiled -fsanitize=address: every `device` buffer is a red-zoned heap
-    block, so an out-of-range index in a kernel or a host driver aborts here instead of corrupting memory on the GPU."""
-    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
-    if not os.path.isabs(asan) or not os.path.exists(asan):
-        pytest.skip("libasan not available")
-    env = dict(os.environ, OMP_WAIT_POLICY="passive", EMUL_ASAN="1", LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    """The same runs with the emulated CUDA sources compiled -fsanitize=address,undefined: every `device` buffer is a
+    red-zoned heap block, so an out-of-range index in a kernel or a host driver aborts here instead of corrupting memory on
+    the GPU, and so do shifts / conversions with undefined results."""
+    libs = [subprocess.run(["gcc", "-print-file-name=" + l], capture_output=True, text=True).stdout.strip() for l in ("libasan.so", "libubsan.so")]
+    if not all(os.path.isabs(l) and os.path.exists(l) for l in libs):
+        pytest.skip("libasan / libubsan not available")
+    env = dict(os.environ, OMP_WAIT_POLICY="passive", EMUL_ASAN="1", LD_PRELOAD=" ".join(libs), ASAN_OPTIONS="detect_leaks=0")
     for which in ("primitives", "hierarchy", "domain"):
         r = subprocess.run([sys.executable, os.path.join(HERE, "emul", "run_emul.py"), which], env=env, capture_output=True, text=True, timeout=1800)
         assert r.returncode == 0 and which + " ok" in r.stdout, r.stdout[-2000:] + r.stderr[-6000:]
