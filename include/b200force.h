@@ -443,6 +443,13 @@ int b200_domain_toptree_leaves(const b200_topnode *tree, int32_t size, int32_t *
 /* TopLeafCount of domain_compute_costs (domain.c:1396-1451): particles per top leaf from the last b200_domain_topleaf,
  * garbage skipped */
 int b200_domain_leaf_counts(b200_ctx *ctx, int32_t nleaf, int64_t *counts_out);
+/* The exchange plan of this rank (domain_build_exchange_list + domain_build_plan, exchange.c:408-444,505-530, with
+ * domain_layoutfunc, domain.c:794-803) from the last b200_domain_topleaf and the leaf -> task table: the particles that
+ * leave (ascending index; the list stays on the device, list_out may be NULL), the garbage count, and
+ * togo[ntask][7] = {base, slots[0..5]}: how many go to every task in total and per particle type.  Moving the records
+ * (exchange.c:211-405) is not part of this library yet. */
+int b200_domain_exchange_plan(b200_ctx *ctx, const int32_t *task_of_leaf, int32_t nleaf, int32_t ntask, int32_t thistask,
+                              int64_t *nexchange, int64_t *ngarbage, int64_t *togo, int32_t *list_out);
 /* domain_assign_topleaves_balanced (domain.c:610-755): task of every top leaf (leaves in key order) from the per-leaf
  * cost; host arithmetic, no context.  Non-zero where the reference would endrun. */
 int b200_domain_assign_balanced(int32_t ntask, int32_t nleaf, const int64_t *cost, int32_t nseg_per_task, int32_t *task_out);

@@ -98,7 +98,7 @@ EXPORTED = [
     "b200_step_set_state", "b200_step_get_state", "b200_step_adopt_forces", "b200_step_drift", "b200_step_build_active",
     "b200_step_active_sublist", "b200_step_get_active", "b200_step_half_kick", "b200_step_pm_kick",
     "b200_step_hier_accelerations", "b200_step_hier_timesteps", "b200_step_hydro_timesteps", "b200_step_find_timesteps", "b200_step_set_active", "b200_step_get_store", "b200_step_set_store", "b200_step_sph_prepare", "b200_step_adopt_hydro",
-    "b200_domain_peano_keys", "b200_domain_set_topnodes", "b200_domain_topleaf", "b200_domain_leaf_counts", "b200_domain_assign_balanced",
+    "b200_domain_peano_keys", "b200_domain_set_topnodes", "b200_domain_topleaf", "b200_domain_leaf_counts", "b200_domain_assign_balanced", "b200_domain_exchange_plan",
     "b200_domain_sample_keys", "b200_domain_toptree_local", "b200_domain_toptree_truncate", "b200_domain_toptree_merge",
     "b200_domain_toptree_global_refine", "b200_domain_toptree_leaves",
 ]
@@ -378,6 +378,14 @@ class Engine:
         keys = np.zeros(max(self.n // subsample, 1), np.uint64); ns = C.c_int64()
         self._ck(self.L.b200_domain_sample_keys(self.ctx, C.c_double(box), C.c_int32(subsample), _p(keys), C.byref(ns)))
         return keys[:ns.value]
+
+    def exchange_plan(self, task_of_leaf, ntask, thistask):
+        """exchange.c:408-444,505-530 after topleaf() -> (exchange list, togo[ntask][7], ngarbage)"""
+        tk = _c(task_of_leaf, np.int32)
+        lst = np.zeros(self.n + 1, np.int32); togo = np.zeros((ntask, 7), np.int64); nex = C.c_int64(); ng = C.c_int64()
+        self._ck(self.L.b200_domain_exchange_plan(self.ctx, _p(tk), C.c_int32(len(tk)), C.c_int32(ntask), C.c_int32(thistask),
+                                                  C.byref(nex), C.byref(ng), _p(togo), _p(lst)))
+        return lst[:nex.value].copy(), togo, int(ng.value)
 
     def leaf_counts(self, nleaf):
         """TopLeafCount (domain.c:1396-1451) of the last topleaf() -> int64[nleaf]"""

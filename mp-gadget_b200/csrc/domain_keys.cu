@@ -9,6 +9,7 @@
 // 000,010,110,100,101,111,011,001 (bits x,y,z) -- and the sub-cube visited r-th continues in the state composed
 // with the r-th of eight child symmetries (swap y,z | swap x,z twice | flip x,y twice | swap x,z + flip x,z twice |
 // swap y,z + flip y,z).  Both kernels are one thread per particle and HBM-bound (24 B in, 8 B out; 8 B in, 4 B out).
+#include <cub/cub.cuh>
 #include <string.h>
 #include <algorithm>
 #include "engine.h"
@@ -124,6 +125,35 @@ int domain_sample_keys(Engine *E, double BoxSize, int32_t subsample, uint64_t *k
     return 0;
 }
 
+// domain_build_exchange_list + domain_build_plan (exchange.c:408-444,505-530) with domain_layoutfunc (domain.c:794-803):
+// flag[i] = particle i leaves this task; cnt[0] garbage, cnt[1] bad leaf / task, cnt[2 + 7 * target + {0, 1 + type}] = toGo
+__global__ void __launch_bounds__(256)
+k_domain_exchange_flags(int64_t n, const uint8_t *__restrict__ type, const uint8_t *__restrict__ flags, const int *__restrict__ topleaf,
+                        const int *__restrict__ task_of_leaf, int nleaf, int ntask, int thistask, uint8_t *__restrict__ flag,
+                        unsigned long long *__restrict__ cnt)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    uint8_t f = 0;
+    if(flags[i] & 1) atomicAdd(&cnt[0], 1ull);
+    else {
+        const int l = topleaf[i];
+        const int target = (l >= 0 && l < nleaf) ? task_of_leaf[l] : -1;
+        if(target < 0 || target >= ntask) atomicAdd(&cnt[1], 1ull);
+        else if(target != thistask) {
+            f = 1;
+            atomicAdd(&cnt[2 + 7 * target], 1ull);
+            atomicAdd(&cnt[2 + 7 * target + 1 + (type[i] < 6 ? type[i] : 5)], 1ull);
+        }
+    }
+    flag[i] = f;
+}
+__global__ void k_domain_iota(int *p, int64_t n)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) p[i] = (int) i;
+}
+
 int domain_peano_keys(Engine *E, double BoxSize, uint64_t *keys_out)
 {
     if(!(BoxSize > 0)) return failmsg(E, "b200_domain_peano_keys: bad box size");
@@ -185,6 +215,51 @@ int domain_leaf_counts(Engine *E, int32_t nleaf, int64_t *counts_out)
     }
     CK(cudaMemcpyAsync(counts_out, E->dk_counts.p, (size_t) nleaf * sizeof(int64_t), cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
+// The exchange plan of this rank from the last b200_domain_topleaf: which particles leave (the list stays on the device in
+// dk_xlist, ascending index) and how many go to every task in total and per type.
+int domain_exchange_plan(Engine *E, const int32_t *task_of_leaf, int32_t nleaf, int32_t ntask, int32_t thistask, int64_t *nexchange,
+                         int64_t *ngarbage, int64_t *togo, int32_t *list_out)
+{
+    if(!task_of_leaf || nleaf < 1 || ntask < 1 || thistask < 0 || thistask >= ntask || !nexchange || !togo)
+        return failmsg(E, "b200_domain_exchange_plan: bad arguments");
+    if(E->dk_topleaf_n != E->n) return failmsg(E, "b200_domain_exchange_plan: call b200_domain_topleaf first");
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1), nc = 2 + 7 * (size_t) ntask;
+    CK(E->dk_task.ensure((size_t) nleaf)); CK(E->dk_counts.ensure(nc)); CK(E->dk_xflag.ensure(n + 64)); CK(E->dk_xlist.ensure(n + 1));
+    CK(E->dk_iota.ensure(n));
+    CK(cudaMemcpyAsync(E->dk_task.p, task_of_leaf, (size_t) nleaf * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaMemsetAsync(E->dk_counts.p, 0, nc * sizeof(unsigned long long), E->stream));
+    *nexchange = 0;
+    if(ngarbage) *ngarbage = 0;
+    for(size_t k = 0; k < 7 * (size_t) ntask; k++) togo[k] = 0;
+    if(E->n == 0) { CK(cudaStreamSynchronize(E->stream)); return 0; }
+    const unsigned grid = (unsigned) ((E->n + 255) / 256);
+    k_domain_exchange_flags<<<grid, 256, 0, E->stream>>>(E->n, E->type.p, E->flags.p, E->dk_topleaf.p, E->dk_task.p, nleaf, ntask, thistask,
+                                                        E->dk_xflag.p, E->dk_counts.p);
+    CKL(E);
+    k_domain_iota<<<grid, 256, 0, E->stream>>>(E->dk_iota.p, E->n); CKL(E);
+    CK(E->scratch_i.ensure(256));
+    int *d_num = E->scratch_i.p + 24;
+    size_t tb = 0;
+    cub::DeviceSelect::Flagged(nullptr, tb, E->dk_iota.p, E->dk_xflag.p, E->dk_xlist.p, d_num, (int) E->n, E->stream);
+    CK(E->cubtemp.ensure(tb + 16));
+    CK(cub::DeviceSelect::Flagged(E->cubtemp.p, tb, E->dk_iota.p, E->dk_xflag.p, E->dk_xlist.p, d_num, (int) E->n, E->stream));
+    E->launches += 1;
+    std::vector<unsigned long long> h(nc);
+    int cnt = 0;
+    CK(cudaMemcpyAsync(h.data(), E->dk_counts.p, nc * sizeof(unsigned long long), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaMemcpyAsync(&cnt, d_num, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    if(h[1]) return failmsg(E, "b200_domain_exchange_plan: " + std::to_string(h[1]) + " particles with a top leaf or task out of range (domain.c:797-799)");
+    *nexchange = cnt;
+    if(ngarbage) *ngarbage = (int64_t) h[0];
+    for(size_t k = 0; k < 7 * (size_t) ntask; k++) togo[k] = (int64_t) h[2 + k];
+    if(list_out && cnt > 0) {
+        CK(cudaMemcpyAsync(list_out, E->dk_xlist.p, (size_t) cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, E->stream));
+        CK(cudaStreamSynchronize(E->stream));
+    }
     return 0;
 }
 
@@ -336,7 +411,7 @@ static void number_leaves(const Node *t, int no, int32_t *next, int32_t *leaf)  
 
 void domain_release(Engine *E)
 {
-    E->dk_keys.release(); E->dk_tab.release(); E->dk_daughter.release(); E->dk_startkey.release(); E->dk_shift.release(); E->dk_leaf.release(); E->dk_topleaf.release(); E->dk_counts.release(); E->dk_sample.release();
+    E->dk_keys.release(); E->dk_tab.release(); E->dk_daughter.release(); E->dk_startkey.release(); E->dk_shift.release(); E->dk_leaf.release(); E->dk_topleaf.release(); E->dk_counts.release(); E->dk_sample.release(); E->dk_xflag.release(); E->dk_xlist.release(); E->dk_iota.release(); E->dk_task.release();
 }
 
 } // namespace b200
@@ -352,6 +427,12 @@ int b200_domain_set_topnodes(b200_ctx *ctx, int32_t ntop, const int32_t *daughte
 }
 int b200_domain_topleaf(b200_ctx *ctx, int32_t *topleaf_out) { DK_ENTER(ctx); return domain_topleaf(E, topleaf_out); }
 int b200_domain_leaf_counts(b200_ctx *ctx, int32_t nleaf, int64_t *counts_out) { DK_ENTER(ctx); return domain_leaf_counts(E, nleaf, counts_out); }
+int b200_domain_exchange_plan(b200_ctx *ctx, const int32_t *task_of_leaf, int32_t nleaf, int32_t ntask, int32_t thistask, int64_t *nexchange,
+                              int64_t *ngarbage, int64_t *togo, int32_t *list_out)
+{
+    DK_ENTER(ctx);
+    return domain_exchange_plan(E, task_of_leaf, nleaf, ntask, thistask, nexchange, ngarbage, togo, list_out);
+}
 int b200_domain_sample_keys(b200_ctx *ctx, double BoxSize, int32_t subsample, uint64_t *keys_out, int64_t *nsample)
 {
     DK_ENTER(ctx);

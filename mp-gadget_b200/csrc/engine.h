@@ -169,7 +169,8 @@ struct Engine {
     // ---- domain keys (domain_keys.cu) ----
     DevBuf<unsigned long long> dk_keys, dk_startkey;   // Peano-Hilbert key per particle; TopNodes[].StartKey
     DevBuf<uint8_t> dk_tab;                            // generated state machine of the curve
-    DevBuf<int> dk_daughter, dk_shift, dk_leaf, dk_topleaf;
+    DevBuf<int> dk_daughter, dk_shift, dk_leaf, dk_topleaf, dk_xlist, dk_iota, dk_task;   // dk_xlist: particles leaving this task
+    DevBuf<uint8_t> dk_xflag;
     DevBuf<unsigned long long> dk_counts, dk_sample;
     int dk_ntop = 0;
     int64_t dk_keys_n = -1, dk_topleaf_n = -1;

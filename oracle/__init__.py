@@ -330,3 +330,15 @@ class TopTree:
         leaf = np.zeros(self.size.value, np.int32)
         nl = lib().oracle_toptree_leaves(_p(self.nodes), self.size, _p(leaf))
         return nl, leaf
+
+
+def exchange_plan(type, flags, topleaf, task_of_leaf, ntask, thistask):
+    """exchange.c:408-444,505-530 -> (exchange list, togo[ntask][7], ngarbage)"""
+    type = _c(type, np.uint8); flags = _c(flags, np.uint8); tl = _c(topleaf, np.int32); tk = _c(task_of_leaf, np.int32)
+    lst = np.zeros(len(tl) + 1, np.int32); togo = np.zeros((ntask, 7), np.int64); ng = C.c_int64()
+    L = lib(); L.oracle_exchange_plan.restype = C.c_int64
+    nex = L.oracle_exchange_plan(C.c_int64(len(tl)), _p(type), _p(flags), _p(tl), C.c_int32(len(tk)), _p(tk), C.c_int32(ntask),
+                                 C.c_int32(thistask), _p(lst), _p(togo), C.byref(ng))
+    if nex < 0:
+        raise ValueError("exchange_plan: leaf or task out of range")
+    return lst[:nex].copy(), togo, int(ng.value)

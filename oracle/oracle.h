@@ -195,6 +195,8 @@ void oracle_toptree_truncate(oracle_topnode *tree, int32_t *size, int64_t countl
 int oracle_toptree_merge(oracle_topnode *treeA, int32_t *sizeA, const oracle_topnode *treeB, int32_t maxnodes);
 int oracle_toptree_global_refine(oracle_topnode *tree, int32_t *size, int32_t maxnodes, int64_t countlimit, int64_t costlimit);
 int32_t oracle_toptree_leaves(const oracle_topnode *tree, int32_t size, int32_t *leaf_out);
+int64_t oracle_exchange_plan(int64_t n, const uint8_t *type, const uint8_t *flags, const int32_t *topleaf, int32_t nleaf,
+                             const int32_t *task_of_leaf, int32_t ntask, int32_t thistask, int32_t *list_out, int64_t *togo, int64_t *ngarbage);
 void oracle_leaf_counts(const int32_t *topleaf, const uint8_t *flags, int64_t n, int32_t nleaf, int64_t *counts);
 int oracle_domain_assign_balanced(int ntask, int32_t nleaf, const int64_t *cost, int nseg_per_task, int32_t *task);
 void oracle_topleaf(const uint64_t *keys, int64_t n, const int32_t *daughter, const uint64_t *startkey, const int32_t *shift,

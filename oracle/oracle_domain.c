@@ -295,3 +295,26 @@ int32_t oracle_toptree_leaves(const oracle_topnode *t, int32_t size, int32_t *le
     tt_leaves(t, 0, &next, leaf);
     return next;
 }
+
+/* domain_build_exchange_list + domain_build_plan, exchange.c:408-444,505-530 with domain_layoutfunc (domain.c:794-803):
+ * the particles that leave this task (ascending index, garbage skipped and counted) and, per target task, how many go
+ * there in total and per particle type: togo[ntask][7] = {base, slots[0..5]}.  Returns the list length, -1 on a leaf or
+ * task out of range (where the reference stops). */
+int64_t oracle_exchange_plan(int64_t n, const uint8_t *type, const uint8_t *flags, const int32_t *topleaf, int32_t nleaf,
+                             const int32_t *task_of_leaf, int32_t ntask, int32_t thistask, int32_t *list_out, int64_t *togo, int64_t *ngarbage)
+{
+    memset(togo, 0, sizeof(int64_t) * 7 * ntask);
+    int64_t nex = 0, ng = 0;
+    for(int64_t i = 0; i < n; i++) {
+        if(flags && (flags[i] & 1)) { ng++; continue; }
+        if(topleaf[i] < 0 || topleaf[i] >= nleaf) return -1;
+        const int32_t target = task_of_leaf[topleaf[i]];
+        if(target < 0 || target >= ntask) return -1;
+        if(target == thistask) continue;
+        list_out[nex++] = (int32_t) i;
+        togo[7 * target]++;
+        togo[7 * target + 1 + type[i]]++;
+    }
+    *ngarbage = ng;
+    return nex;
+}

@@ -352,5 +352,16 @@ class RefDomain(Ref):
         return nl, leaf
 
 
+    def exchange_plan(self, type, flags, topleaf, task_of_leaf, ntask, thistask):
+        """domain_build_exchange_list + domain_build_plan (exchange.c, static) -> (list, togo[ntask][7], ngarbage)"""
+        type = np.ascontiguousarray(type, np.uint8); flags = np.ascontiguousarray(flags, np.uint8)
+        tl = np.ascontiguousarray(topleaf, np.int32); tk = np.ascontiguousarray(task_of_leaf, np.int32)
+        lst = np.zeros(len(tl) + 1, np.int32); togo = np.zeros((ntask, 7), np.int64); ng = C.c_int64()
+        self.L.ref_exchange_plan.restype = C.c_int64
+        nex = self.L.ref_exchange_plan(C.c_int64(len(tl)), _p(type), _p(flags), _p(tl), C.c_int(len(tk)), _p(tk), C.c_int(ntask), C.c_int(thistask),
+                                       _p(lst), _p(togo), C.byref(ng))
+        return lst[:nex].copy(), togo, int(ng.value)
+
+
 def domain_available():
     return os.path.exists(SO_DOMAIN)

@@ -10,8 +10,7 @@ extern int ref_stub_ntask;
 /* entry points of files that are not built (exchange.c, utils/mpsort.c need a real MPI; blackhole.c is sub-grid
  * physics): domain.c links to them, the routines driven here never reach them */
 static void unreachable(const char *what) { endrun(1, "ref_domain_driver: %s reached\n", what); }
-int domain_exchange(ExchangeLayoutFunc layoutfunc, const void *layout_userdata, PreExchangeList *preexch, struct part_manager_type *pman,
-                    struct slots_manager_type *sman, int maxiter, MPI_Comm Comm) { unreachable("domain_exchange"); return 0; }
+/* domain_exchange itself comes from exchange.c, included by ref_exchange_driver.c for its static planning routines */
 void mpsort_mpi_impl(void *base, size_t nmemb, size_t size, void (*radix)(const void *ptr, void *radix, void *arg), size_t rsize, void *arg,
                      MPI_Comm comm, const int line, const char *file) { unreachable("mpsort_mpi"); }
 int blackhole_dynfric_treemask(void) { return 0; }

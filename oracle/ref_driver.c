@@ -108,6 +108,7 @@ int param_get_int(ParameterSet *ps, const char *name)
 int param_get_enum(ParameterSet *ps, const char *name) { endrun(1, "ref_driver: unexpected enum %s\n", name); return 0; }
 
 int ref_stub_ntask = 1;          /* what the stand-in MPI_Comm_size reports (oracle/stubs/mpi.h) */
+int ref_stub_thistask = 0;       /* ... and MPI_Comm_rank */
 static struct ClockTable CT;
 static int initialised = 0;
 static DomainDecomp dd;

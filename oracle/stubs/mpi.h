@@ -50,7 +50,8 @@ static inline int stub_mpi_copy(const void *s, void *r, int count, MPI_Datatype 
 static inline int MPI_Init(int *a, char ***b) { return 0; }
 static inline int MPI_Init_thread(int *a, char ***b, int req, int *prov) { if(prov) *prov = req; return 0; }
 static inline int MPI_Finalize(void) { return 0; }
-static inline int MPI_Comm_rank(MPI_Comm c, int *r) { *r = 0; return 0; }
+extern int ref_stub_thistask;      /* 0 unless a fixture plays another rank, see ref_stub_ntask below */
+static inline int MPI_Comm_rank(MPI_Comm c, int *r) { *r = ref_stub_thistask; return 0; }
 /* 1 everywhere, except while a fixture drives a pure-computation routine of the reference for several tasks
  * (oracle/ref_domain_driver.c sets ref_stub_ntask around the call) */
 extern int ref_stub_ntask;
@@ -76,6 +77,8 @@ static inline int MPI_Isend(const void *b, int n, MPI_Datatype t, int d, int tag
 static inline int MPI_Irecv(void *b, int n, MPI_Datatype t, int s, int tag, MPI_Comm c, MPI_Request *r) { fprintf(stderr, "stub MPI_Irecv reached\n"); abort(); return 0; }
 static inline int MPI_Send(const void *b, int n, MPI_Datatype t, int d, int tag, MPI_Comm c) { fprintf(stderr, "stub MPI_Send reached\n"); abort(); return 0; }
 static inline int MPI_Recv(void *b, int n, MPI_Datatype t, int s, int tag, MPI_Comm c, MPI_Status *st) { fprintf(stderr, "stub MPI_Recv reached\n"); abort(); return 0; }
+static inline int MPI_Sendrecv(const void *sb, int sn, MPI_Datatype st, int d, int stag, void *rb, int rn, MPI_Datatype rt, int s, int rtag,
+                               MPI_Comm c, MPI_Status *status) { fprintf(stderr, "stub MPI_Sendrecv reached\n"); abort(); return 0; }
 static inline int MPI_Waitall(int n, MPI_Request *r, MPI_Status *s) { return 0; }
 static inline int MPI_Waitsome(int n, MPI_Request *r, int *outcount, int *idx, MPI_Status *s) { *outcount = MPI_UNDEFINED; return 0; }
 static inline int MPI_Wait(MPI_Request *r, MPI_Status *s) { return 0; }

@@ -100,3 +100,14 @@ def toptree_pipeline(make_tree, sample_keys_of, case):
     assert A.global_refine(lim, lim) == 0; sizes.append(len(A.tree))
     nl, leaf = A.leaves()
     return {f: A.tree[f].copy() for f in TOPTREE_FIELDS}, leaf, nl, np.array(sizes, np.int64)
+
+
+def exchange_case(seed=8, n=30000, nleaf=97, ntask=5):
+    """Particles of all types with garbage, random top leaves, a leaf -> task table in curve order (contiguous runs)."""
+    rng = np.random.default_rng(seed)
+    typ = rng.choice([0, 1, 1, 1, 4, 5], n).astype(np.uint8)
+    flags = (rng.random(n) < 0.03).astype(np.uint8)
+    topleaf = rng.integers(0, nleaf, n).astype(np.int32)
+    cuts = np.sort(rng.choice(np.arange(1, nleaf), ntask - 1, replace=False))
+    task_of_leaf = np.searchsorted(cuts, np.arange(nleaf), side="right").astype(np.int32)
+    return typ, flags, topleaf, task_of_leaf, ntask

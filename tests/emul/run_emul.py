@@ -83,6 +83,13 @@ def domain():
         task = np.zeros(len(cost), np.int32)
         assert L.b200_domain_assign_balanced(C.c_int32(nt), C.c_int32(len(cost)), p(cost), C.c_int32(1), p(task)) == 0
     import oracle
+    tasks = np.zeros(nleaf, np.int32)
+    assert L.b200_domain_assign_balanced(C.c_int32(4), C.c_int32(nleaf), p(counts), C.c_int32(1), p(tasks)) == 0
+    for r in range(4):                       # the exchange plan of every rank against the oracle (itself pinned by exchange.c)
+        lst = np.zeros(len(pos) + 1, np.int32); togo = np.zeros((4, 7), np.int64); nex = C.c_int64(); ng = C.c_int64()
+        assert L.b200_domain_exchange_plan(ctx, p(tasks), C.c_int32(nleaf), C.c_int32(4), C.c_int32(r), C.byref(nex), C.byref(ng), p(togo), p(lst)) == 0, L.b200_last_error(ctx)
+        olst, otogo, ong = oracle.exchange_plan(np.ones(len(pos), np.uint8), np.zeros(len(pos), np.uint8), G["topleaf"], tasks, 4, r)
+        assert nex.value == len(olst) and np.array_equal(lst[:nex.value], olst) and np.array_equal(togo, otogo) and ng.value == ong
     for sub in (1, 7, 256):                  # the strided subsample keys of the top-tree build
         ks = np.zeros(max(len(pos) // sub, 1), np.uint64); ns = C.c_int64()
         assert L.b200_domain_sample_keys(ctx, C.c_double(box), C.c_int32(sub), p(ks), C.byref(ns)) == 0, L.b200_last_error(ctx)

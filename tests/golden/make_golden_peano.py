@@ -4,7 +4,8 @@ libgadget/tests/test_peano.c:107 (read from that file), (2) PEANO() of its compi
 positions incl. the box faces, (3) domain_get_topleaf (domain.h:71-78) over a randomly refined top tree, (4) the per-leaf particle counts of
 domain_compute_costs and (5) domain_assign_topleaves_balanced for 120 cost distributions and 1-16 tasks, both
 file-static in domain.c and reached by including that file in oracle/ref_domain_driver.c, (6) the top tree of two ranks
-through the reference's static stages (local refinement of a subsample, truncation, merge, global refinement, leaves).
+through the reference's static stages (local refinement of a subsample, truncation, merge, global refinement, leaves), (7) the exchange list and plan of
+every rank of a five-task case (exchange.c statics through oracle/ref_exchange_driver.c).
 Run in the build container:  make -C oracle ref && python tests/golden/make_golden_peano.py"""
 import os
 import re
@@ -54,6 +55,11 @@ def main():
         def global_refine(self, a, b):
             rc, self.size = D.toptree_global_refine(self.nodes, self.size, a, b); return rc
         def leaves(self): return D.toptree_leaves(self.nodes, self.size)
+    # the exchange plan of every rank (exchange.c statics through oracle/ref_exchange_driver.c)
+    typ, fl, tl, tk, ntask = DS.exchange_case()
+    for r in range(ntask):
+        lst, togo, ng = D.exchange_plan(typ, fl, tl, tk, ntask, r)
+        out["xplan/%d/list" % r] = lst; out["xplan/%d/togo" % r] = togo; out["xplan/%d/ngarbage" % r] = np.int64(ng)
     for k, case in enumerate(DS.TOPTREE_CASES):
         fields, lf, nl, sizes = DS.toptree_pipeline(RefTree, lambda p_, b_, s_: (p_, b_, s_), case)
         for f, v in fields.items():

@@ -81,6 +81,20 @@ def test_product_host_toptree_equals_reference(b200):
     _check_toptree(b200.TopTree, _subsample_keys)
 
 
+def test_oracle_exchange_plan_equals_reference():
+    typ, fl, tl, tk, ntask = DS.exchange_case()
+    total = np.zeros((ntask, 7), np.int64)
+    for r in range(ntask):
+        lst, togo, ng = oracle.exchange_plan(typ, fl, tl, tk, ntask, r)
+        assert np.array_equal(lst, GOLD["xplan/%d/list" % r]) and np.array_equal(togo, GOLD["xplan/%d/togo" % r])
+        assert ng == int(GOLD["xplan/%d/ngarbage" % r]) == int(fl.sum())
+        assert togo[r].sum() == 0 and togo[:, 0].sum() == len(lst) and (togo[:, 1:].sum(1) == togo[:, 0]).all()
+        total += togo
+    # what all ranks send to task t is what t's own particles elsewhere would be: every live particle is kept or sent once
+    live = fl == 0
+    assert total[:, 0].sum() == sum(int((live & (tk[tl] != r)).sum()) for r in range(ntask))
+
+
 def test_product_host_assignment_equals_reference(b200):
     """b200_domain_assign_balanced is host arithmetic inside libb200force.so: callable without a GPU."""
     got = np.concatenate([b200.domain_assign_balanced(nt, cost) for nt, cost in DS.assign_cases()])
@@ -119,4 +133,10 @@ def test_gpu_domain_keys(b200):
     assert counts.sum() == len(pos)
     leaf = GOLD["topleaf"]
     assert np.array_equal(counts, np.bincount(leaf, minlength=len(counts)))
+    # exchange plan: leaves dealt to 4 tasks by the balanced assignment
+    tasks = b200.domain_assign_balanced(4, counts)
+    for r in range(4):
+        lst, togo, ng = e.exchange_plan(tasks, 4, r)
+        olst, otogo, ong = oracle.exchange_plan(np.ones(len(pos), np.uint8), np.zeros(len(pos), np.uint8), leaf, tasks, 4, r)
+        assert np.array_equal(lst, olst) and np.array_equal(togo, otogo) and ng == ong == 0
     e.close()
