@@ -37,7 +37,7 @@ class Ref:
                 avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2.0 ** 30
             except Exception:
                 avail = 16.0
-            arena_gib = max(2.0, min(24.0, 0.4 * avail))
+            arena_gib = max(2.0, min(8.0, 0.4 * avail))      # the arena is touched on creation: 24 GiB cost ~25 s of page faults per process
         self.L.ref_init(C.c_double(arena_gib), C.c_int(nthreads))
         self.n = 0
 
