@@ -205,6 +205,12 @@ void b200_ctx_destroy(b200_ctx *ctx)
     E->d_acc.release(); E->d_pot.release(); E->d_counts.release(); E->srtab.release();
     E->walk_pool.release(); E->walk_chunktab.release(); E->walk_cnt.release(); E->walk_partial.release();
     step_release(E); domain_release(E);
+    // the SPH state and scratch (grow-only buffers have no destructor: everything is released here)
+    E->s_vel.release(); E->s_hsml.release(); E->s_entropy.release(); E->s_dtentropy.release(); E->s_fullacc.release(); E->s_gravpm.release();
+    E->s_hydroacc.release(); E->s_velpred.release(); E->s_evp.release(); E->s_density.release(); E->s_egy.release(); E->s_dhsmlfac.release();
+    E->s_divvel.release(); E->s_curlvel.release(); E->s_dthsml.release(); E->s_numngb.release(); E->s_gradrho.release(); E->s_svel.release();
+    E->s_hA.release(); E->s_hB.release(); E->s_out3.release(); E->s_out1a.release(); E->s_out1b.release(); E->s_outi.release(); E->s_outi2.release();
+    E->s_niter.release(); E->s_nint.release();
     for(int i = 0; i < T_COUNT; i++) if(E->timers[i].a) { cudaEventDestroy(E->timers[i].a); cudaEventDestroy(E->timers[i].b); }
     for(int i = 0; i < 65; i++) if(E->chunk_ev[i]) cudaEventDestroy(E->chunk_ev[i]);
     cudaStreamDestroy(E->copy_stream);

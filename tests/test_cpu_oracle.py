@@ -182,3 +182,13 @@ def test_oracle_power_spectrum_sums(ics):
     bpu = (nmesh - 1) / np.log(np.sqrt(3) * nmesh / 2.0)
     assert nm[0] == 6          # k2 = 1: the six axis modes (+-x, +-y with weight 1 each... kz = +-1 folded with weight 2)
     assert int(np.floor(bpu * np.log(3.0) / 2)) < nmesh
+
+
+def test_every_device_buffer_is_released():
+    """Engine's grow-only device buffers have no destructor: each must be released by a destroy / release function."""
+    src_dir = os.path.join(ROOT, "mp-gadget_b200", "csrc")
+    hdr = open(os.path.join(src_dir, "engine.h")).read()
+    names = [n.strip() for m in re.finditer(r"DevBuf<[^>]+>\s+([^;]+);", hdr) for n in m.group(1).split(",")]
+    src = "".join(open(os.path.join(src_dir, f)).read() for f in os.listdir(src_dir) if f.endswith(".cu"))
+    missing = [n for n in names if not re.search(r"\b%s\.release\(\)" % re.escape(n), src)]
+    assert len(names) > 100 and not missing, missing
