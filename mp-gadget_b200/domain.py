@@ -76,3 +76,63 @@ def balance(local_leaf_counts, dist=None, nseg_per_task=1):
     if dist is not None:
         dist.all_reduce(c)
     return domain_assign_balanced(world, c.numpy(), nseg_per_task), c.numpy()
+
+
+def exchange(tensors, leaving, target, dist=None):
+    """domain_exchange_once (exchange.c:211-405) for particle state held as torch tensors (first dimension = particle):
+    the particles `leaving` (indices, ascending: the exchange list of b200_domain_exchange_plan) go to the tasks `target`
+    (one per leaving particle); everything else stays, in order, and what arrives is appended by source rank.  The
+    counts go round first (MPI_Alltoall of toGo, exchange.c:530), then one variable-size all-to-all per tensor
+    (NCCL all_to_all_single; pairwise sends on gloo).  Returns the new tensors (same keys)."""
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    first = next(iter(tensors.values()))
+    dev = first.device
+    n = first.shape[0]
+    leaving = torch.as_tensor(leaving, dtype=torch.int64, device=dev)
+    target = torch.as_tensor(target, dtype=torch.int64, device=dev)
+    if world == 1 or dist is None:
+        if leaving.numel():
+            raise B200Error("exchange: particles leave the only task")
+        return dict(tensors)
+    if target.numel() and (int(target.min()) < 0 or int(target.max()) >= world or bool((target == rank).any())):
+        raise B200Error("exchange: bad target task")
+    order = torch.argsort(target, stable=True)                 # by destination, ascending particle index inside one
+    send_idx = leaving[order]
+    togo = torch.bincount(target, minlength=world).to(torch.int64)
+    toget = torch.zeros_like(togo)
+    nccl = dist.get_backend() == "nccl"
+
+    def pairwise(send_parts, recv_parts):
+        ops = []
+        for p in range(world):
+            if p == rank:
+                continue
+            if send_parts[p].numel():
+                ops.append(dist.P2POp(dist.isend, send_parts[p], p))
+            if recv_parts[p].numel():
+                ops.append(dist.P2POp(dist.irecv, recv_parts[p], p))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+
+    if nccl:
+        dist.all_to_all_single(toget, togo)
+    else:
+        sp = [togo[p:p + 1].clone() for p in range(world)]
+        rp = [toget[p:p + 1] for p in range(world)]
+        pairwise(sp, rp)
+    send_counts = [int(c) for c in togo.tolist()]
+    recv_counts = [int(c) for c in toget.tolist()]
+    keep = torch.ones(n, dtype=torch.bool, device=dev)
+    keep[leaving] = False
+    out = {}
+    for name, t in tensors.items():
+        send = t[send_idx].contiguous()
+        recv = torch.empty((sum(recv_counts),) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        if nccl:
+            dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts)
+        else:
+            pairwise(list(torch.split(send, send_counts)), list(torch.split(recv, recv_counts)))
+        out[name] = torch.cat([t[keep], recv])
+    return out

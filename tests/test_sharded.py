@@ -327,3 +327,56 @@ def test_domain_toptree_and_balance_gloo(world):
     r = _torchrun(DOMAIN_WORKER % {"root": ROOT}, world)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == world
+
+
+EXCHANGE_WORKER = r'''
+import os, sys, importlib
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import oracle
+import domain_scenarios as DS
+dom = importlib.import_module("mp-gadget_b200.domain")
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+box = 1000.0
+n = 4000 + 1500 * rank
+pos = DS.clustered(n, box, 20 + rank)
+ids = (np.arange(n, dtype=np.int64) + (rank << 32))
+vel = np.random.default_rng(rank).standard_normal((n, 3))
+# decomposition: keys -> global top tree -> top leaf -> counts -> balanced tasks -> plan (device kernels stood in by the oracle here)
+keys = oracle.peano_keys(pos, box)
+T, leaf, nleaf = dom.global_toptree(keys[::8][: n // 8], 8 * world, dist)
+top = dom.topnode_arrays(T, leaf)
+tl = oracle.topleaf(keys, *top)
+task, counts = dom.balance(np.bincount(tl, minlength=nleaf), dist)
+lst, togo, ng = oracle.exchange_plan(np.ones(n, np.uint8), np.zeros(n, np.uint8), tl, task, world, rank)
+new = dom.exchange(dict(pos=torch.from_numpy(pos), vel=torch.from_numpy(vel), id=torch.from_numpy(ids)), lst, task[tl[lst]], dist)
+# every particle now lives on the task that owns its top leaf, with its own payload
+npos = new["pos"].numpy(); nid = new["id"].numpy()
+assert len(npos) == len(nid) == len(new["vel"]) == counts[task == rank].sum(), (len(npos), counts[task == rank].sum())
+assert (task[oracle.topleaf(oracle.peano_keys(npos, box), *top)] == rank).all()
+src = nid >> 32; loc = nid & 0xffffffff
+for r in range(world):
+    m = src == r
+    assert np.array_equal(npos[m], DS.clustered(4000 + 1500 * r, box, 20 + r)[loc[m]])
+    assert np.array_equal(new["vel"].numpy()[m], np.random.default_rng(r).standard_normal((4000 + 1500 * r, 3))[loc[m]])
+# nothing lost, nothing doubled
+tot = torch.tensor([len(nid), int(nid.sum() %% (1 << 40))], dtype=torch.int64); dist.all_reduce(tot)
+want_n = sum(4000 + 1500 * r for r in range(world))
+want_s = sum(int((np.arange(4000 + 1500 * r, dtype=np.int64) + (r << 32)).sum() %% (1 << 40)) for r in range(world))
+assert int(tot[0]) == want_n and len(np.unique(nid)) == len(nid)
+# kept particles stay in order in front, arrivals follow by source rank
+kept = src == rank
+assert kept[: kept.sum()].all() and (np.diff(loc[kept]) > 0).all() and (np.diff(src[~kept]) >= 0).all()
+print("ok", flush=True)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_domain_exchange_gloo(world):
+    """The whole decomposition on CPU ranks: keys, global top tree, balanced leaf assignment, exchange plan, and the
+    variable-size all-to-all of the particle state; afterwards every particle sits on the task owning its top leaf."""
+    r = _torchrun(EXCHANGE_WORKER % {"root": ROOT}, world)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == world
