@@ -136,3 +136,21 @@ def exchange(tensors, leaving, target, dist=None):
             pairwise(list(torch.split(send, send_counts)), list(torch.split(recv, recv_counts)))
         out[name] = torch.cat([t[keep], recv])
     return out
+
+
+def decompose(engine, box, dist=None, overdecomposition=4, subsample=256, attempt=0):
+    """domain_decompose_full (domain.c:154-256) for the particles held by `engine`, first policy: the subsample keys,
+    per-leaf counts, top-leaf lookup and exchange plan run on the device, the top tree and the leaf assignment on the
+    host, the reductions over `dist`.  -> dict(tree, leaf, nleaf, topnodes, topleaf (int32[n]), task_of_leaf, counts,
+    leaving (indices), target (task per leaving particle), togo, ngarbage)."""
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    ntopleaves = overdecomposition * world * (attempt + 1)                 # domain_policies_init, domain.c:369-371
+    T, leaf, nleaf = global_toptree(engine.sample_keys(box, subsample), ntopleaves, dist)
+    top = topnode_arrays(T, leaf)
+    engine.peano_keys(box)
+    topleaf = engine.topleaf(*top)
+    task, counts = balance(engine.leaf_counts(nleaf), dist)
+    leaving, togo, ngarbage = engine.exchange_plan(task, world, rank)
+    return dict(tree=T, leaf=leaf, nleaf=nleaf, topnodes=top, topleaf=topleaf, task_of_leaf=task, counts=counts, leaving=leaving,
+                target=task[topleaf[leaving]], togo=togo, ngarbage=ngarbage)

@@ -140,3 +140,32 @@ def test_gpu_domain_keys(b200):
         olst, otogo, ong = oracle.exchange_plan(np.ones(len(pos), np.uint8), np.zeros(len(pos), np.uint8), leaf, tasks, 4, r)
         assert np.array_equal(lst, olst) and np.array_equal(togo, otogo) and ng == ong == 0
     e.close()
+
+
+@pytest.mark.gpu_unverified
+def test_gpu_domain_decompose_chain(b200):
+    """domain.decompose on one GPU: device keys / lookup / counts / plan around the host top tree; checked against the
+    oracle for the same particles (the tree from the oracle's stages, fed with the oracle's subsample keys)."""
+    import importlib
+    try:
+        e = b200.Engine(0)
+    except Exception as ex:
+        pytest.skip("no CUDA device (%s)" % ex)
+    dom = importlib.import_module("mp-gadget_b200.domain")
+    box = 1000.0
+    pos = DS.clustered(60000, box, 31)
+    e.set_particles(pos, np.ones(len(pos), np.float32))
+    d = dom.decompose(e, box, None, overdecomposition=16, subsample=16)
+    keys = oracle.peano_keys(pos, box)
+    O = oracle.TopTree(d["tree"].maxnodes)
+    assert O.local(keys[::16][: len(pos) // 16]) == 0
+    lim = int(O.tree["Count"][0]) // 16
+    O.truncate(lim, lim); O.global_refine(lim, lim)
+    for f in DS.TOPTREE_FIELDS:
+        assert np.array_equal(O.tree[f], d["tree"].tree[f]), f
+    nl, leaf = O.leaves()
+    assert nl == d["nleaf"] and np.array_equal(leaf, d["leaf"])
+    tl = oracle.topleaf(keys, *d["topnodes"])
+    assert np.array_equal(tl, d["topleaf"]) and np.array_equal(d["counts"], np.bincount(tl, minlength=nl))
+    assert (d["task_of_leaf"] == 0).all() and len(d["leaving"]) == 0 and d["ngarbage"] == 0
+    e.close()

@@ -3,7 +3,7 @@
 # 1. hardware parity of csrc/steploop.cu against the reference goldens, 2. the usual GPU suite,
 # 3. step-loop timings.  Outputs under gpurun_out/.
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_step_gpu.py tests/test_domain_keys.py -q 2>&1 | tail -15 | tee gpurun_out/step_gpu.log
+timeout 900 python -m pytest tests/test_step_gpu.py tests/test_domain_keys.py -q 2>&1 | tail -15 | tee gpurun_out/step_gpu.log
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/gpu_tests.log
 timeout 900 python tools/steploop_bench.py 128 256 2>&1 | tail -30 | tee gpurun_out/steploop_bench.log
 # memcheck of the new kernels on the hardware (the emulation ran them under AddressSanitizer only on the CPU)
