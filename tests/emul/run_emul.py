@@ -16,8 +16,12 @@ import step_scenarios as SC          # noqa: E402
 import test_step as TS               # noqa: E402
 
 
-class EmulEngine:
-    """The three calls StepEngine makes on a b200 Engine, bound to the emulation library."""
+PKG = importlib.import_module("mp-gadget_b200")
+
+
+class EmulEngine(PKG.Engine):
+    """The harness Engine with its methods bound to the emulation library instead of libb200force.so: every method
+    whose entry point the emulation exports (particles, pm_init, step loop, domain keys) works unchanged."""
 
     def __init__(self):
         self.L = C.CDLL(EB.build())
@@ -25,15 +29,8 @@ class EmulEngine:
         self.L.b200_ctx_destroy.restype = None
         self.ctx = C.c_void_p()
         assert self.L.b200_ctx_create(C.byref(self.ctx), C.c_int(0)) == 0
-
-    def set_particles(self, pos, mass, type=None, oldacc=None):
-        pos = np.ascontiguousarray(pos, np.float64); mass = np.ascontiguousarray(mass, np.float32)
-        type = None if type is None else np.ascontiguousarray(type, np.uint8)
-        p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
-        assert self.L.b200_set_particles_soa(self.ctx, p(pos), p(mass), p(type), None, C.c_int64(len(mass))) == 0
-
-    def gravpm_init_periodic(self, box, asmth, nmesh, G):
-        assert self.L.b200_pm_init(self.ctx, C.c_double(box), C.c_double(asmth), C.c_int(nmesh), C.c_double(G)) == 0
+        self.n = 0
+        self.nmesh = 0
 
 
 def dropin(which):
@@ -99,9 +96,54 @@ def domain():
     print("domain ok")
 
 
+def decompose():
+    """mp-gadget_b200/domain.py::decompose -- device keys / lookup / counts / plan (emulated kernels) around the host top
+    tree, over torch.distributed when started under torchrun -- against the oracle; with several ranks the exchange follows
+    and every particle must end on the task owning its top leaf."""
+    import oracle
+    import torch
+    import domain_scenarios as DS
+    dom = importlib.import_module("mp-gadget_b200.domain")
+    dist = None
+    if "RANK" in os.environ:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    box = 1000.0
+    n = 20000 + 7000 * rank
+    pos = DS.clustered(n, box, 31 + rank)
+    e = EmulEngine()
+    e.set_particles(pos, np.ones(n, np.float32))
+    d = dom.decompose(e, box, dist, overdecomposition=8, subsample=16)
+    keys = oracle.peano_keys(pos, box)
+    tl = oracle.topleaf(keys, *d["topnodes"])
+    assert np.array_equal(tl, d["topleaf"])
+    lst, togo, ng = oracle.exchange_plan(np.ones(n, np.uint8), np.zeros(n, np.uint8), tl, d["task_of_leaf"], world, rank)
+    assert np.array_equal(lst, d["leaving"]) and np.array_equal(togo, d["togo"]) and ng == d["ngarbage"] == 0
+    if world == 1:
+        O = oracle.TopTree(d["tree"].maxnodes)
+        assert O.local(keys[::16][: n // 16]) == 0
+        lim = int(O.tree["Count"][0]) // 8
+        O.truncate(lim, lim); O.global_refine(lim, lim)
+        for f in DS.TOPTREE_FIELDS:
+            assert np.array_equal(O.tree[f], d["tree"].tree[f]), f
+        assert (d["task_of_leaf"] == 0).all() and len(d["leaving"]) == 0
+    else:
+        new = dom.exchange(dict(pos=torch.from_numpy(pos)), d["leaving"], d["target"], dist)
+        npos = new["pos"].numpy()
+        assert (d["task_of_leaf"][oracle.topleaf(oracle.peano_keys(npos, box), *d["topnodes"])] == rank).all()
+        tot = torch.tensor([len(npos)], dtype=torch.int64); dist.all_reduce(tot)
+        assert int(tot) == sum(20000 + 7000 * r for r in range(world)) and len(npos) == d["counts"][d["task_of_leaf"] == rank].sum()
+        dist.destroy_process_group()
+    print("decompose ok", flush=True)
+
+
 def main(which):
     if which == "domain":
         return domain()
+    if which == "decompose":
+        return decompose()
     if which.startswith("dropin"):
         return dropin(which)
     SL = importlib.import_module("mp-gadget_b200.steploop")

@@ -11,7 +11,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("which", ["primitives", "hierarchy", "dropin_primitives", "dropin_hierarchy", "domain"])
+@pytest.mark.parametrize("which", ["primitives", "hierarchy", "dropin_primitives", "dropin_hierarchy", "domain", "decompose"])
 def test_steploop_source_under_emulation(which):
     """dropin_*: the reference's own loop with its calls redirected (ld --wrap) to host/libgadget_step_shims.c."""
     env = dict(os.environ, OMP_WAIT_POLICY="passive")          # 256 OS threads per emulated block: do not spin
@@ -33,3 +33,15 @@ def test_steploop_emulation_under_address_sanitizer():
     for which in ("primitives", "hierarchy", "domain"):
         r = subprocess.run([sys.executable, os.path.join(HERE, "emul", "run_emul.py"), which], env=env, capture_output=True, text=True, timeout=1800)
         assert r.returncode == 0 and which + " ok" in r.stdout, r.stdout[-2000:] + r.stderr[-6000:]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_domain_decompose_emulated_ranks(world):
+    """mp-gadget_b200/domain.py::decompose + exchange with one emulated engine per gloo rank: the device side of the chain
+    (subsample keys, keys, top-leaf lookup, counts, exchange plan) is the CUDA source under emulation."""
+    env = dict(os.environ, OMP_WAIT_POLICY="passive")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", str(31500 + os.getpid() % 2000), os.path.join(HERE, "emul", "run_emul.py"), "decompose"],
+                       env=env, capture_output=True, text=True, timeout=1800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("decompose ok") == world
