@@ -68,6 +68,15 @@ k_step_drift(int64_t n, double *__restrict__ pos, const double *__restrict__ vel
     }
 }
 
+// black holes carry drag / dynamic-friction kicks and repositioning (timestep.c:1006-1012, drift.c:32-53) that this module
+// does not have: count them so that b200_step_set_state can refuse instead of integrating them wrongly
+__global__ void __launch_bounds__(256)
+k_step_count_bh(int64_t n, const uint8_t *__restrict__ type, const uint8_t *__restrict__ flags, unsigned long long *__restrict__ cnt)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n && type[i] == 5 && !(flags[i] & 3)) atomicAdd(cnt, 1ull);
+}
+
 // ---- active lists: timestep.c:1334-1478 ----
 __global__ void k_step_iota(int *p, int64_t n)
 {
@@ -463,7 +472,13 @@ int step_set_state(Engine *E, const b200_step_state *s)
     if(s->bin_hydro) CK(cudaMemcpyAsync(E->s_bin_hydro.p, s->bin_hydro, E->n, cudaMemcpyHostToDevice, E->stream));
     else CK(cudaMemsetAsync(E->s_bin_hydro.p, 0, n, E->stream));
     if(s->flags) CK(cudaMemcpyAsync(E->flags.p, s->flags, E->n, cudaMemcpyHostToDevice, E->stream));
+    CK(E->st_cnt.ensure(1 + 6 * NBIN));
+    CK(cudaMemsetAsync(E->st_cnt.p, 0, sizeof(unsigned long long), E->stream));
+    if(E->n > 0) { k_step_count_bh<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->n, E->type.p, E->flags.p, E->st_cnt.p); CKL(E); }
+    unsigned long long nbh = 0;
+    CK(cudaMemcpyAsync(&nbh, E->st_cnt.p, sizeof(nbh), cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
+    if(nbh) { E->st_state = false; return failmsg(E, "b200_step_set_state: " + std::to_string(nbh) + " black-hole particles; their kicks and repositioning are not supported by the step loop"); }
     E->st_state = true;
     E->st_store_valid = false; E->st_maxsig_valid = false;
     if(s->BoxSize > 0) E->st_box = s->BoxSize;

@@ -154,6 +154,12 @@ def main(which):
     if which in ("primitives", "all"):
         out = SC.run_primitives(S, SC.primitives_inputs())
         TS.check_primitives(out)
+        d = SC.primitives_inputs(); d["type"] = d["type"].copy(); d["type"][100] = 5       # a live black hole is refused, loudly
+        try:
+            SC._load(S, d)
+            raise AssertionError("black-hole particle accepted")
+        except PKG.B200Error as ex:
+            assert "black-hole" in str(ex)
         print("primitives ok")
     if which in ("hierarchy", "all"):
         rec = SC.run_hierarchy(S, SC.hierarchy_inputs())

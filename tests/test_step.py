@@ -103,3 +103,13 @@ def test_oracle_equals_reference_live():
             assert np.array_equal(x[k], y[k]), (s, k)
         for k in ("pos", "vel", "fullacc"):
             assert close(y[k], x[k], 1e-12), (s, k)
+
+
+def test_bench_cosmology_helper_matches_oracle(ics):
+    """ics.FlatLCDM (the bench / tool stand-in for the reference host's cosmology.c + timefac.c) against the oracle's."""
+    c = ics.FlatLCDM()
+    O = OS.StepOracle(c.sync, Omega0=c.Omega0, Hubble=c.Hubble)
+    for kind, t0, t1 in [(0, 0, 1 << 40), (1, (1 << 46) + 5, (1 << 46) + (1 << 42)), (2, 3 << 44, (3 << 44) + (1 << 30)), (1, 7, 7)]:
+        a, b = c.factor(kind, t0, t1), O.factor(kind, t0, t1)
+        assert abs(a - b) <= 1e-12 * max(abs(b), 1e-300)
+    assert abs(c.hubble(0.37) - O.hubble(0.37)) < 1e-15 and c.loga_from_ti((1 << 46) + 12345) == O.loga_from_ti((1 << 46) + 12345)
