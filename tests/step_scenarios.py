@@ -29,9 +29,11 @@ def primitives_inputs(seed=7, n=1536, box=4000.0):
                [box - 0.5, box - 0.5, box - 0.5], [12.5, 7.25, box - 3.0], [box - 12.5, 7.25, 3.0], [2000.0, 2000.0, 2000.0]]
     vel = 40.0 * rng.standard_normal((n, 3))
     typ = np.ones(n, np.uint8); typ[n // 3: 2 * n // 3] = 0; typ[-3:] = 4
+    typ[-40:-3] = 2                                  # fast (neutrino) particles: excluded from the PM step criterion, timestep.c:1272
     flags = np.zeros(n, np.uint8); flags[[5, n // 3 + 7, n - 20]] = 1; flags[[6, n // 3 + 11]] = 2
     gas = typ == 0
     vel[np.flatnonzero(gas)[:5]] *= 3e4
+    vel[typ == 2] *= 1e6
     mass = (1.0 + rng.random(n)).astype(np.float32)
     bin_grav = rng.integers(36, 42, n).astype(np.uint8)
     bin_hydro = np.zeros(n, np.uint8); bin_hydro[gas] = np.minimum(bin_grav[gas], rng.integers(35, 41, gas.sum())).astype(np.uint8)
