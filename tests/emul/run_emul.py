@@ -152,6 +152,15 @@ def main(which):
     ts = {k: float(TS.GOLD["tspar/" + k]) for k in TS.TSKEYS}
     S = SL.StepEngine(EmulEngine(), TS.GOLD["sync_loga"], O.factor, O.hubble, **cosmo, **ts)
     if which in ("primitives", "all"):
+        # error behaviour: every entry point refuses to run without its prerequisites and says which one is missing
+        S.n, S.box = 0, 1.0
+        for call, word in ((lambda: S.drift(0, 1 << 30), "b200_step_set_state"), (lambda: S.build_active(), "b200_step_set_state"),
+                           (lambda: S.kick(2), "b200_step_set_state"), (lambda: S.adopt_hydro(), "b200_step_set_state")):
+            try:
+                call()
+                raise AssertionError("call without state accepted")
+            except PKG.B200Error as ex:
+                assert word in str(ex), str(ex)
         out = SC.run_primitives(S, SC.primitives_inputs())
         TS.check_primitives(out)
         d = SC.primitives_inputs(); d["type"] = d["type"].copy(); d["type"][100] = 5       # a live black hole is refused, loudly
