@@ -113,3 +113,45 @@ def test_bench_cosmology_helper_matches_oracle(ics):
         a, b = c.factor(kind, t0, t1), O.factor(kind, t0, t1)
         assert abs(a - b) <= 1e-12 * max(abs(b), 1e-300)
     assert abs(c.hubble(0.37) - O.hubble(0.37)) < 1e-15 and c.loga_from_ti((1 << 46) + 12345) == O.loga_from_ti((1 << 46) + 12345)
+
+
+def test_reference_test_timebinmgr_known_answers():
+    """libgadget/tests/test_timebinmgr.c:24-90 (sync points 0.1, 0.2, 0.8, 1.0) on the oracle's integer timeline."""
+    outs = np.log([0.1, 0.2, 0.8, 1.0])
+    O = OS.StepOracle(outs)
+    TB = 1 << 46
+    assert abs(O.loga_from_ti(0) - outs[0]) < 1e-6 and abs(O.loga_from_ti(TB) - outs[1]) < 1e-6
+    assert abs(O.loga_from_ti(TB - 1) - (outs[0] + (outs[1] - outs[0]) * (TB - 1) / TB)) < 1e-6
+    assert abs(O.loga_from_ti(TB + 1) - (outs[1] + (outs[2] - outs[1]) / TB)) < 1e-6
+    assert abs(O.loga_from_ti(2 * TB) - outs[2]) < 1e-6
+    ti = lambda la: int(O.L.oracle_ti_from_loga(OS.C.byref(O.tl), OS.C.c_double(la)))
+    assert ti(outs[0]) == 0 and ti(outs[1]) == TB and ti(outs[2]) == 2 * TB
+    mid = (outs[2] + outs[1]) / 2
+    assert ti(mid) == TB + TB // 2 and abs(O.loga_from_ti(TB + TB // 2) - mid) < 1e-6
+    assert ti(0.0) == 3 * TB
+    assert abs(O.loga_from_ti(ti(np.log(0.1))) - np.log(0.1)) < 1e-6
+    # test_dloga: get_dloga_for_bin = dloga_from_dti(dti_from_timebin(bin))
+    Ti = ti(np.log(0.55))
+    assert abs(O.dloga_from_dti(0, Ti)) < 1e-6
+    assert abs(O.dloga_from_dti(1 << 46, Ti) - (outs[2] - outs[1])) < 1e-6
+    assert abs(O.dloga_from_dti(1 << 44, Ti) - (outs[2] - outs[1]) / 4) < 1e-6
+
+
+def test_reference_test_timefac_known_answers():
+    """libgadget/tests/test_timefac.c:78-106: matter-dominated closed forms of the drift / kick factors (Omega0 = 1,
+    H0 = 0.1) and the identity hydrokick = drift, on the Gauss-Legendre stand-in both sides of the step fixtures use."""
+    amin, amax = 0.005, 1.0
+    O = OS.StepOracle(np.log([amin, amax]), Omega0=1.0, Hubble=0.1)
+    logdt = (np.log(amax) - np.log(amin)) / (1 << 46)
+    ti = lambda a: int((np.log(a) - np.log(amin)) / logdt)
+    assert abs(O.factor(0, ti(0.8), ti(0.85)) + 2 / 0.1 * (1 / np.sqrt(0.85) - 1 / np.sqrt(0.8))) < 5e-5
+    assert abs(O.factor(1, ti(0.8), ti(0.85)) - 2 / 0.1 * (np.sqrt(0.85) - np.sqrt(0.8))) < 5e-5
+    assert abs(O.factor(0, ti(0.8), ti(0.8003)) + 2 / 0.1 * (1 / np.sqrt(0.8003) - 1 / np.sqrt(0.8))) < 5e-6
+    assert abs(O.factor(2, ti(0.8), ti(0.85)) - O.factor(0, ti(0.8), ti(0.85))) < 5e-5
+    # a more realistic cosmology against an independent quadrature of the same integrands (test_timefac.c:88-102)
+    from scipy.integrate import quad
+    O2 = OS.StepOracle(np.log([amin, amax]), Omega0=0.25, Hubble=0.1)
+    H = lambda a: 0.1 * np.sqrt(0.25 / a ** 3 + 0.75)
+    for kind, p, lo, hi in ((0, 3, 0.95, 0.98), (0, 3, 0.05, 0.06), (1, 2, 0.8, 0.85), (1, 2, 0.05, 0.06)):
+        want = quad(lambda a: 1 / (H(a) * a ** p), lo, hi, epsrel=1e-10)[0]
+        assert abs(O2.factor(kind, ti(lo), ti(hi)) - want) < 5e-5 * max(1.0, abs(want))
