@@ -368,6 +368,26 @@ assert int(tot[0]) == want_n and len(np.unique(nid)) == len(nid)
 # kept particles stay in order in front, arrivals follow by source rank
 kept = src == rank
 assert kept[: kept.sum()].all() and (np.diff(loc[kept]) > 0).all() and (np.diff(src[~kept]) >= 0).all()
+# ---- the reference's own exchange tests (libgadget/tests/test_exchange.c): layout ID %% NTask
+def by_id(nlocal, garbage_every=0):
+    ids = torch.arange(nlocal, dtype=torch.int64) + nlocal * rank if nlocal else torch.zeros(0, dtype=torch.int64)
+    live = torch.ones(nlocal, dtype=torch.bool)
+    if garbage_every:
+        live[::garbage_every] = False                              # garbage is never on the exchange list (exchange.c:427-430)
+    tgt = ids %% world
+    leaving = torch.nonzero(live & (tgt != rank)).flatten()
+    new = dom.exchange(dict(id=ids, live=live), leaving.numpy(), tgt[leaving].numpy(), dist)
+    nid, nlive = new["id"], new["live"]
+    assert bool(((nid[nlive] %% world) == rank).all())            # test_exchange.c:78
+    tot = torch.tensor([int(nlive.sum())]); dist.all_reduce(tot)
+    return int(tot), nid[nlive]
+tot, mine = by_id(48)                                              # test_exchange
+assert tot == 48 * world and len(torch.unique(mine)) == len(mine)
+live_before = torch.tensor([48 - len(range(0, 48, 5))]); dist.all_reduce(live_before)
+tot, mine = by_id(48, garbage_every=5)                             # test_exchange_with_garbage
+assert tot == int(live_before)
+tot, mine = by_id(48 * world if rank == 0 else 0)                 # test_exchange_uneven: everything starts on task 0
+assert tot == 48 * world and len(mine) == 48
 print("ok", flush=True)
 dist.destroy_process_group()
 '''
@@ -376,7 +396,8 @@ dist.destroy_process_group()
 @pytest.mark.parametrize("world", [2, 3])
 def test_domain_exchange_gloo(world):
     """The whole decomposition on CPU ranks: keys, global top tree, balanced leaf assignment, exchange plan, and the
-    variable-size all-to-all of the particle state; afterwards every particle sits on the task owning its top leaf."""
+    variable-size all-to-all of the particle state; afterwards every particle sits on the task owning its top leaf.
+    Then the reference's own exchange tests (tests/test_exchange.c: layout ID mod NTask, with garbage, everything on task 0)."""
     r = _torchrun(EXCHANGE_WORKER % {"root": ROOT}, world)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == world
