@@ -395,6 +395,9 @@ int b200_step_adopt_hydro(b200_ctx *ctx);
  * the device, times->mintimebin updated.  maxsignalvel[n] = SphP[].MaxSignalVel by particle index (host). */
 int b200_step_hydro_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel,
                               double atime, double hubble, int64_t *nbad);
+/* force_tree_full + grav_short_tree for the current active list (run.c:541-548, SplitGravityTimestepsOn = 0): the
+ * FullTreeGravAccel of the listed particles in the step state is replaced; gp->TreeUseBH > 1 -> 0 afterwards */
+int b200_step_grav_short_tree(b200_ctx *ctx, b200_gravshort_params *gp);
 /* find_timesteps (timestep.c:739-853), the SplitGravityTimestepsOn = 0 loop: one bin for TimeBinGravity and
  * TimeBinHydro from the gravity and (gas) hydro criteria, PM step length on PM steps, times->mintimebin / maxtimebin. */
 int b200_step_find_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel,

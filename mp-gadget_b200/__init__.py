@@ -97,7 +97,7 @@ EXPORTED = [
     "b200_sph_set_gas", "b200_sph_set_timebins", "b200_sph_set_active", "b200_sph_set_hsml_range", "b200_sph_set_state", "b200_density", "b200_density_gradrho", "b200_hydro_force",
     "b200_step_set_state", "b200_step_get_state", "b200_step_adopt_forces", "b200_step_drift", "b200_step_build_active",
     "b200_step_active_sublist", "b200_step_get_active", "b200_step_half_kick", "b200_step_pm_kick",
-    "b200_step_hier_accelerations", "b200_step_hier_timesteps", "b200_step_hydro_timesteps", "b200_step_find_timesteps", "b200_step_set_active", "b200_step_get_store", "b200_step_set_store", "b200_step_sph_prepare", "b200_step_adopt_hydro",
+    "b200_step_hier_accelerations", "b200_step_hier_timesteps", "b200_step_hydro_timesteps", "b200_step_find_timesteps", "b200_step_grav_short_tree", "b200_step_set_active", "b200_step_get_store", "b200_step_set_store", "b200_step_sph_prepare", "b200_step_adopt_hydro",
     "b200_domain_peano_keys", "b200_domain_set_topnodes", "b200_domain_topleaf", "b200_domain_leaf_counts", "b200_domain_assign_balanced", "b200_domain_exchange_plan",
     "b200_domain_sample_keys", "b200_domain_toptree_local", "b200_domain_toptree_truncate", "b200_domain_toptree_merge",
     "b200_domain_toptree_global_refine", "b200_domain_toptree_leaves",

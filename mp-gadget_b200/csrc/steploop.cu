@@ -994,6 +994,24 @@ int step_adopt_hydro(Engine *E)
     return 0;
 }
 
+// force_tree_full + grav_short_tree for the current active list (run.c:541-548, the SplitGravityTimestepsOn = 0 loop): a tree
+// over every particle, the walk for the listed ones, their FullTreeGravAccel in the step state replaced (the walk reads the
+// old modulus from Engine::oldacc, so writing into s_fullacc in place is safe).
+int step_grav_short_tree(Engine *E, b200_gravshort_params *gp)
+{
+    if(int rc = step_need_state(E, "b200_step_grav_short_tree")) return rc;
+    if(!gp) return failmsg(E, "b200_step_grav_short_tree: null parameters");
+    if(E->Nmesh == 0 && E->NmeshWalk == 0) return failmsg(E, "b200_step_grav_short_tree: call b200_pm_init first");
+    if(E->n == 0) return 0;
+    k_step_oldacc<<<grid_for(E->n), 256, 0, E->stream>>>(E->n, E->s_fullacc.p, E->s_gravpm.p, E->oldacc.p); CKL(E);
+    if(int rc = tree_build(E, step_box(E), 63, nullptr, 0, 0, nullptr)) return rc;
+    if(E->st_act_implicit) { if(int rc = grav_short_tree(E, gp, nullptr, 0, E->s_fullacc.p, nullptr, nullptr)) return rc; }
+    else if(E->st_nact > 0) { if(int rc = grav_short_tree(E, gp, E->st_act.p, E->st_nact, E->s_fullacc.p, nullptr, nullptr)) return rc; }
+    if(gp->TreeUseBH > 1) gp->TreeUseBH = 0;                               // gravshort-tree.c:150-151
+    CK(cudaStreamSynchronize(E->stream));
+    return 0;
+}
+
 // find_timesteps timestep.c:739-853 on the current active list (the SplitGravityTimestepsOn = 0 loop: followed by
 // b200_step_half_kick with hydro_only = 0).  maxsig as in b200_step_hydro_timesteps (ignored without gas).
 int step_find_timesteps(Engine *E, const b200_step_params *sp, b200_step_times *t, const double *maxsig, int is_pm, double atime, double hubble,
@@ -1078,6 +1096,7 @@ int b200_step_half_kick(b200_ctx *ctx, const double *gravkick, const double *hyd
 int b200_step_pm_kick(b200_ctx *ctx, double Fgravkick) { STEP_ENTER(ctx); return step_pm_kick(E, Fgravkick); }
 int b200_step_sph_prepare(b200_ctx *ctx, const b200_sph_bins *tables) { STEP_ENTER(ctx); return step_sph_prepare(E, tables); }
 int b200_step_adopt_hydro(b200_ctx *ctx) { STEP_ENTER(ctx); return step_adopt_hydro(E); }
+int b200_step_grav_short_tree(b200_ctx *ctx, b200_gravshort_params *gp) { STEP_ENTER(ctx); return step_grav_short_tree(E, gp); }
 int b200_step_find_timesteps(b200_ctx *ctx, const b200_step_params *sp, b200_step_times *times, const double *maxsignalvel, int is_pm,
                              double atime, double hubble, int64_t *nbad)
 {

@@ -269,3 +269,27 @@ class StepEngine:
         if is_pm:
             self.kick(2)
         return int(info[2]), np.array([counts[0], counts[1], 1 if is_pm else 0], np.int64)
+
+    def advance_nonsplit(self, asmth=None, first=False, pm=False):
+        """One pass of run.c:355-800 with SplitGravityTimestepsOn = 0: one full tree, the walk for the active particles,
+        closing half kick, find_timesteps, opening half kick."""
+        t = self.t
+        last = t.Ti_Current
+        if not first:
+            t.Ti_Current = t.Ti_Current + dti_from_timebin(t.mintimebin)
+        atime = self.atime()
+        is_pm = self.is_pm()
+        if not first:
+            self.drift(last, t.Ti_Current)
+        _, counts = self.build_active()
+        if pm and is_pm:
+            self.pm_force()
+        self._ck(self.L.b200_step_grav_short_tree(self.ctx, C.byref(self.gp)))
+        self.kick(0, atime); self.kick(3)
+        if is_pm:
+            self.kick(2)
+        bad, _, _ = self.find_timesteps(np.zeros(self.n), atime, first=first)
+        self.kick(0, atime); self.kick(3)
+        if is_pm:
+            self.kick(2)
+        return bad, np.array([counts[0], counts[1], 1 if is_pm else 0], np.int64)

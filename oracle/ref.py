@@ -287,6 +287,13 @@ class RefStep(Ref):
         return bad, info
 
 
+    def advance_nonsplit(self, asmth, first=False):
+        """The same pass with SplitGravityTimestepsOn = 0 -> (bad, [NumActiveParticle, NumActiveGravity, is_PM])"""
+        info = np.zeros(3, np.int64)
+        bad = int(self.L.ref_step_advance_nonsplit(C.c_int(1 if first else 0), C.c_double(asmth), _p(info)))
+        return bad, info
+
+
 def step_available():
     return os.path.exists(SO_STEP)
 

@@ -750,6 +750,7 @@ void ref_step_set_gravity(double G, int Nmesh, double Asmth, double ErrTolForceA
     tp.TreeUseBH = TreeUseBH; tp.Rcut = Rcut; tp.FractionalGravitySoftening = GravitySoftening;
     set_gravshort_treepar(tp);
     gravshort_set_softenings(1.0);
+    step_rho0 = stepCP.Omega0 * 3 * stepCP.Hubble * stepCP.Hubble / (8 * M_PI * stepCP.GravInternal);      /* run.c:544 */
 }
 double ref_step_softening(void) { return FORCE_SOFTENING(); }
 /* One pass of run.c:441-795 for collisionless particles with HierarchicalGravity on, PM force held
@@ -777,6 +778,36 @@ int ref_step_advance(int first, int64_t *nactive_out)
     update_kick_times(&stepT);
     if(is_PM) apply_PM_half_kick(&stepCP, &stepT);
     const int bad = hierarchical_gravity_and_timesteps(&stepAct, &step_pm, &dd, GravAccel, &stepT, atime, 0, 2, &stepCP, NULL);
+    update_kick_times(&stepT);
+    if(is_PM) apply_PM_half_kick(&stepCP, &stepT);
+    free_active_particles(&stepAct);
+    step_act_built = 0;
+    return bad;
+}
+/* The same pass with SplitGravityTimestepsOn = 0 (run.c:541-560,749-793): one full tree, grav_short_tree for the active
+ * particles, closing half kick, find_timesteps, opening half kick. */
+int ref_step_advance_nonsplit(int first, double asmth, int64_t *nactive_out)
+{
+    const inttime_t Ti_Last = stepT.Ti_Current;
+    if(!first) stepT.Ti_Current = find_next_kick(stepT.Ti_Current, stepT.mintimebin);
+    const double atime = get_atime(stepT.Ti_Current);
+    const int is_PM = is_PM_timestep(&stepT);
+    const double zero[3] = {0, 0, 0};
+    if(!first) ref_step_drift(Ti_Last, stepT.Ti_Current, zero);
+    int64_t counts[3];
+    int *tmp = (int *) malloc(sizeof(int) * (PartManager->NumPart + 1));
+    ref_step_build_active(tmp, counts);
+    free(tmp);
+    if(nactive_out) { nactive_out[0] = counts[0]; nactive_out[1] = counts[1]; nactive_out[2] = is_PM; }
+    ForceTree T = {0};
+    force_tree_full(&T, &dd, 0, NULL);
+    grav_short_tree(&stepAct, &step_pm, &T, NULL, step_rho0, stepT.Ti_Current);
+    force_tree_free(&T);
+    apply_half_kick(&stepAct, &stepCP, &stepT, atime);
+    update_kick_times(&stepT);
+    if(is_PM) apply_PM_half_kick(&stepCP, &stepT);
+    const int bad = find_timesteps(&stepAct, &stepT, atime, 2, &stepCP, asmth, first);
+    apply_half_kick(&stepAct, &stepCP, &stepT, atime);
     update_kick_times(&stepT);
     if(is_PM) apply_PM_half_kick(&stepCP, &stepT);
     free_active_particles(&stepAct);

@@ -3,7 +3,7 @@ TEST INFRASTRUCTURE ONLY.  StepOracle mirrors oracle.ref.RefStep call for call s
 tests read the same on both sides."""
 import ctypes as C
 import numpy as np
-from . import lib, GravShortParams, _c
+from . import lib, GravShortParams, OracleTree, _c
 
 NBINS = 47      # TIMEBINS + 1
 
@@ -227,3 +227,37 @@ class StepOracle:
             self.kick(2)
         self.act = None
         return int(bad), np.array([counts[0], counts[1], 1 if is_pm else 0], np.int64)
+
+    def grav_short_tree_active(self):
+        """force_tree_full + grav_short_tree for the current active list (run.c:541-548): FullTreeGravAccel of the walked particles"""
+        old = self.fullacc + self.gravpm
+        t = OracleTree(self.pos, self.mass, self.box, type=self.type, mask=63)
+        par = {k: getattr(self.gp, k) for k in ("ErrTolForceAcc", "BHOpeningAngle", "MaxBHOpeningAngle", "TreeUseBH", "Rcut", "GravitySoftening", "rho0")}
+        res = t.grav_short_tree(par, self.G, self.nmesh, self.asmth, oldacc=old, active=self.act, full=True)
+        acc = res[0]
+        idx = np.arange(self.n) if self.act is None else self.act
+        self.fullacc[idx] = acc[idx]
+        if self.gp.TreeUseBH > 1:
+            self.gp.TreeUseBH = 0                                           # gravshort-tree.c:150-151
+
+    def advance_nonsplit(self, asmth, first=False):
+        """run.c:355-800 with SplitGravityTimestepsOn = 0, PM force held fixed: see RefStep.advance_nonsplit"""
+        t = self.t
+        last = t.Ti_Current
+        if not first:
+            t.Ti_Current = t.Ti_Current + dti_from_timebin(t.mintimebin)
+        atime = self.atime()
+        is_pm = self.is_pm()
+        if not first:
+            self.drift(last, t.Ti_Current)
+        act, counts = self.build_active()
+        self.grav_short_tree_active()
+        self.kick(0, atime); self.kick(3)
+        if is_pm:
+            self.kick(2)
+        bad, _, _ = self.find_timesteps(np.zeros(self.n), atime, asmth, first)
+        self.kick(0, atime); self.kick(3)
+        if is_pm:
+            self.kick(2)
+        self.act = None
+        return bad, np.array([counts[0], counts[1], 1 if is_pm else 0], np.int64)

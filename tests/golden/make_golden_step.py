@@ -4,7 +4,8 @@
 gravity): the integer timeline, drift_all_particles, build_active_particles / build_active_sublist,
 apply_half_kick / apply_hydro_half_kick / apply_PM_half_kick / update_kick_times on a mixed
 DM + gas set with garbage, and eight passes of the hierarchical KDK loop of run.c:355-800
-(hierarchical_gravity_accelerations + hierarchical_gravity_and_timesteps) from the initial step.
+(hierarchical_gravity_accelerations + hierarchical_gravity_and_timesteps) from the initial step, and six passes of
+the SplitGravityTimestepsOn = 0 loop (force_tree_full + grav_short_tree for the active particles, find_timesteps).
 Stand-ins only for what needs GSL (flat matter + Lambda H(a), Gauss-Legendre kick integrals;
 oracle/ref_driver.c).  Run in the build container:
     make -C oracle ref && python tests/golden/make_golden_step.py"""
@@ -41,10 +42,17 @@ def main():
         if s in SC.HIER_KEEP:
             for k in ("pos", "vel", "fullacc"):
                 out["hier/%d/%s" % (s, k)] = r[k]
+    rec2 = SC.run_nonsplit(S, SC.hierarchy_inputs(seed=15, n=1536))
+    for s, r in enumerate(rec2):
+        for k in ("bad", "info", "scal", "kick", "last", "bin_grav"):
+            out["nonsplit/%d/%s" % (s, k)] = r[k]
+        if s in SC.NONSPLIT_KEEP:
+            for k in ("pos", "vel", "fullacc"):
+                out["nonsplit/%d/%s" % (s, k)] = r[k]
     path = os.path.join(ROOT, "tests", "golden", "ref_step.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", "bins per step:", [np.bincount(r["bin_grav"])[24:].tolist() for r in rec][-1],
-          "active:", [int(r["info"][0]) for r in rec])
+          "active:", [int(r["info"][0]) for r in rec], "nonsplit active:", [int(r["info"][0]) for r in rec2])
 
 
 if __name__ == "__main__":

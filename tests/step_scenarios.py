@@ -147,3 +147,21 @@ def run_hierarchy(S, d, steps=HIER_STEPS):
         rec.append(dict(bad=bad, info=info.copy(), scal=t[0].copy(), kick=t[1].copy(), last=t[2].copy(), bin_grav=g["bin_grav"].copy(),
                         pos=g["pos"].copy(), vel=g["vel"].copy(), fullacc=g["fullacc"].copy()))
     return rec
+
+
+NONSPLIT_STEPS = 6
+NONSPLIT_KEEP = (0, 5)
+
+
+def run_nonsplit(S, d, steps=NONSPLIT_STEPS):
+    """The same loop with SplitGravityTimestepsOn = 0 (one tree over all particles per step, find_timesteps)."""
+    S.set_particles(d["pos"], d["mass"], d["type"], d["box"], vel=d["vel"], gravpm=d["gravpm"])
+    S.set_gravity(d["par"], G, d["nmesh"], d["asmth"])
+    S.set_times(np.zeros(7, np.int64), np.zeros(NB, np.int64), np.zeros(NB, np.int64))
+    rec = []
+    for s in range(steps):
+        bad, info = S.advance_nonsplit(d["asmth"] * d["box"] / d["nmesh"], first=(s == 0))
+        g = S.get(); t = S.get_times()
+        rec.append(dict(bad=bad, info=info.copy(), scal=t[0].copy(), kick=t[1].copy(), last=t[2].copy(), bin_grav=g["bin_grav"].copy(),
+                        pos=g["pos"].copy(), vel=g["vel"].copy(), fullacc=g["fullacc"].copy()))
+    return rec

@@ -51,6 +51,23 @@ def check_hierarchy(rec, gold=GOLD, rtol=1e-12):
                 assert close(r[k], gold["hier/%d/%s" % (s, k)], rtol), (s, k)
 
 
+def check_nonsplit(rec, gold=GOLD, rtol=1e-12):
+    for s, r in enumerate(rec):
+        for k in ("info", "scal", "kick", "last", "bin_grav"):
+            assert np.array_equal(r[k], gold["nonsplit/%d/%s" % (s, k)]), (s, k)
+        assert r["bad"] == int(gold["nonsplit/%d/bad" % s])
+        if s in SC.NONSPLIT_KEEP:
+            for k in ("pos", "vel", "fullacc"):
+                assert close(r[k], gold["nonsplit/%d/%s" % (s, k)], rtol), (s, k)
+
+
+def test_oracle_nonsplit_loop_equals_reference():
+    """Six passes with SplitGravityTimestepsOn = 0: one full tree per pass, the walk for the active particles only."""
+    rec = SC.run_nonsplit(make_oracle(), SC.hierarchy_inputs(seed=15, n=1536))
+    check_nonsplit(rec)
+    assert len({int(r["info"][0]) for r in rec}) >= 3                       # sub-steps with different active sets
+
+
 def test_oracle_timeline_equals_reference():
     O = make_oracle()
     ti, dloga, span = SC.timeline_samples()

@@ -49,6 +49,11 @@ def test_gpu_hierarchy_equals_reference(stepper):
     TS.check_hierarchy(rec, rtol=1e-9)
 
 
+def test_gpu_nonsplit_loop_equals_reference(stepper):
+    """Six passes with SplitGravityTimestepsOn = 0: b200_step_grav_short_tree + half kicks + b200_step_find_timesteps."""
+    TS.check_nonsplit(SC.run_nonsplit(stepper, SC.hierarchy_inputs(seed=15, n=1536)), rtol=1e-9)
+
+
 def test_gpu_dropin_step_shims(stepper):
     """The reference's own loop with drift_all_particles, build_active_particles, the half kicks and the hierarchical
     gravity drivers redirected (ld --wrap) to host/libgadget_step_shims.c -> GPU (oracle/_ref/libref_dropin_step.so)."""
