@@ -17,7 +17,13 @@
  *    non-zero status to endrun(1, "%s", b200_last_error(ctx));
  *  - particle arrays are indexed by the caller's particle index (the index into
  *    the reference's global P[] array, libgadget/partmanager.h:73-85);
- *  - there is NO CPU fallback: without a CUDA device b200_ctx_create fails.
+ *  - there is NO CPU fallback: without a CUDA device b200_ctx_create fails.  The b200_domain_toptree_* and
+ *    b200_domain_assign_balanced functions take no context: they are the host part of the domain decomposition
+ *    (sequential integer work on a tree of a few hundred nodes, as in the reference) and run anywhere.
+ *
+ * Sections: particles and context; PM (gravpm.c, petapm.c); tree build and short-range walk (forcetree.c,
+ * gravshort-tree.c); whole force step; SPH density and hydro (density.c, hydra.c); multi-GPU building blocks; step loop
+ * (drift.c, timestep.c); domain decomposition (peano.c, domain.c, exchange.c); timings.
  */
 #ifndef B200FORCE_H
 #define B200FORCE_H
