@@ -117,7 +117,10 @@ struct Engine {
     DevBuf<int> nodeK;          // [nn][8] DFS positions of the children (-1 = none)
     DevBuf<double> nodeH;       // [nn] hmax
     DevBuf<int> scratch_i;      // small device scalars; always ensure(256): a later, larger ensure() would
-                                // reallocate and drop counters that are already in flight
+                                // reallocate and drop counters that are already in flight.  Slots: [0..15] tree build
+                                // (cleared by every build), [8] walk target select, [12..13] SPH pass counters,
+                                // [20] step-loop list select, [24] exchange-list select, [32..63] walk chunk offsets,
+                                // [64..67] piece-pool control
 
     // ---- SPH (original index order unless noted) ----
     DevBuf<double> s_vel, s_hsml, s_entropy, s_dtentropy, s_fullacc, s_gravpm, s_hydroacc;
