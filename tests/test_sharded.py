@@ -320,10 +320,11 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("world", [2, 3])
 def test_domain_toptree_and_balance_gloo(world):
     """domain_determine_global_toptree + domain_balance over torch.distributed: world 2 reproduces the reference's own
-    two-rank top tree node for node; 3 and 4 ranks exercise the pairwise merge schedule with an odd rank count."""
+    two-rank top tree node for node; 3 ranks exercise the pairwise merge schedule with an odd rank count (rank 2 merges
+    into rank 0 at separation 2)."""
     r = _torchrun(DOMAIN_WORKER % {"root": ROOT}, world)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == world
