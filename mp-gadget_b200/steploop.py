@@ -244,7 +244,7 @@ class StepEngine:
         self.e.gravpm_force_dev()
         self._ck(self.L.b200_step_adopt_forces(self.ctx, C.c_int(0), C.c_int(1)))
 
-    def advance(self, first=False, pm=False):
+    def advance(self, first=False, pm=False, maxsig=None):
         """One pass of run.c:355-800 (collisionless, HierarchicalGravity).  pm = False holds the PM force fixed (the
         parity scenarios); pm = True recomputes it on PM steps."""
         t = self.t
@@ -256,15 +256,23 @@ class StepEngine:
         if not first:
             self.drift(last, t.Ti_Current)
         _, counts = self.build_active()
+        if maxsig is not None:          # gas takes part with its hydro accelerations held fixed: closing hydro kick, run.c:498-499
+            self.kick(1, atime)
         if pm and is_pm:
             self.pm_force()
-        self._ck(self.L.b200_step_hier_accelerations(self.ctx, C.byref(self.sp), C.byref(self.gp), C.byref(t), C.c_int64(int(counts[1]))))
+        if counts[1] > 0:               # run.c:533
+            self._ck(self.L.b200_step_hier_accelerations(self.ctx, C.byref(self.sp), C.byref(self.gp), C.byref(t), C.c_int64(int(counts[1]))))
         self.kick(3)
         if is_pm:
             self.kick(2)
         info = np.zeros(3, np.int64)
-        self._ck(self.L.b200_step_hier_timesteps(self.ctx, C.byref(self.sp), C.byref(self.gp), C.byref(t), C.c_int64(int(counts[1])),
-                                                 C.c_int(1 if is_pm else 0), C.c_double(atime), C.c_double(float(self.hubble(atime))), _p(info)))
+        if counts[1] > 0:
+            self._ck(self.L.b200_step_hier_timesteps(self.ctx, C.byref(self.sp), C.byref(self.gp), C.byref(t), C.c_int64(int(counts[1])),
+                                                     C.c_int(1 if is_pm else 0), C.c_double(atime), C.c_double(float(self.hubble(atime))), _p(info)))
+        if maxsig is not None:          # run.c:767-773
+            b2, _ = self.hydro_timesteps(maxsig, atime, first)
+            info[2] += b2
+            self.kick(1, atime)
         self.kick(3)
         if is_pm:
             self.kick(2)

@@ -280,8 +280,12 @@ class RefStep(Ref):
                                     C.c_double(par["Rcut"]), C.c_double(par["GravitySoftening"]))
         return self.L.ref_step_softening()
 
-    def advance(self, first=False):
-        """One pass of the run.c loop -> (bad-timestep count, [NumActiveParticle, NumActiveGravity, is_PM])"""
+    def advance(self, first=False, maxsig=None):
+        """One pass of the run.c loop -> (bad-timestep count, [NumActiveParticle, NumActiveGravity, is_PM]).  maxsig
+        (SphP[].MaxSignalVel by particle index): gas takes part -- hydro half kicks and find_hydro_timesteps with the hydro
+        accelerations held fixed."""
+        self._maxsig = None if maxsig is None else np.ascontiguousarray(maxsig, np.float64)
+        self.L.ref_step_set_maxsig(_p(self._maxsig))
         info = np.zeros(3, np.int64)
         bad = int(self.L.ref_step_advance(C.c_int(1 if first else 0), _p(info)))
         return bad, info

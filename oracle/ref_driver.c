@@ -758,6 +758,8 @@ double ref_step_softening(void) { return FORCE_SOFTENING(); }
  * hierarchical_gravity_accelerations, update_kick_times, PM half kick, hierarchical_gravity_and_timesteps,
  * update_kick_times, PM half kick.  first != 0 starts from the state as loaded (no advance, no drift),
  * like NumCurrentTiStep == 0.  Returns the reference's bad-timestep count. */
+static const double *step_maxsig;      /* non-NULL: gas takes part, hydro accelerations and signal velocities held fixed */
+void ref_step_set_maxsig(const double *maxsig) { step_maxsig = maxsig; }
 int ref_step_advance(int first, int64_t *nactive_out)
 {
     const inttime_t Ti_Last = stepT.Ti_Current;
@@ -771,13 +773,21 @@ int ref_step_advance(int first, int64_t *nactive_out)
     ref_step_build_active(tmp, counts);
     free(tmp);
     if(nactive_out) { nactive_out[0] = counts[0]; nactive_out[1] = counts[1]; nactive_out[2] = is_PM; }
+    if(step_maxsig) apply_hydro_half_kick(&stepAct, &stepCP, &stepT, atime);       /* run.c:498-499, after density + hydro_force */
     struct grav_accel_store GravAccel = {0};
     GravAccel.nstore = PartManager->NumPart;
     GravAccel.GravAccel = (MyFloat (*)[3]) mymalloc2("GravAccel", GravAccel.nstore * sizeof(GravAccel.GravAccel[0]));
-    hierarchical_gravity_accelerations(&stepAct, &step_pm, &dd, GravAccel, &stepT, 0, &stepCP, NULL);
+    if(counts[1] > 0) hierarchical_gravity_accelerations(&stepAct, &step_pm, &dd, GravAccel, &stepT, 0, &stepCP, NULL);     /* run.c:533 */
     update_kick_times(&stepT);
     if(is_PM) apply_PM_half_kick(&stepCP, &stepT);
-    const int bad = hierarchical_gravity_and_timesteps(&stepAct, &step_pm, &dd, GravAccel, &stepT, atime, 0, 2, &stepCP, NULL);
+    int bad = 0;
+    if(counts[1] > 0) bad = hierarchical_gravity_and_timesteps(&stepAct, &step_pm, &dd, GravAccel, &stepT, atime, 0, 2, &stepCP, NULL);
+    else if(GravAccel.GravAccel) myfree(GravAccel.GravAccel);
+    if(step_maxsig) {                                                               /* run.c:767-773 */
+        for(int64_t i = 0; i < PartManager->NumPart; i++) if(P[i].Type == 0) SPHP(i).MaxSignalVel = step_maxsig[i];
+        bad += find_hydro_timesteps(&stepAct, &stepT, atime, &stepCP, first);
+        apply_hydro_half_kick(&stepAct, &stepCP, &stepT, atime);
+    }
     update_kick_times(&stepT);
     if(is_PM) apply_PM_half_kick(&stepCP, &stepT);
     free_active_particles(&stepAct);

@@ -195,8 +195,8 @@ class StepOracle:
         self.sp.softening = 2.8 * par["GravitySoftening"]       # FORCE_SOFTENING gravshort-tree.c:37-41
         return self.sp.softening
 
-    def advance(self, first=False):
-        """One pass of run.c:355-800 (collisionless, HierarchicalGravity, PM force held fixed): see RefStep.advance."""
+    def advance(self, first=False, maxsig=None):
+        """One pass of run.c:355-800 (HierarchicalGravity, PM force and hydro accelerations held fixed): see RefStep.advance."""
         L, t = self.L, self.t
         last = t.Ti_Current
         if not first:
@@ -206,22 +206,32 @@ class StepOracle:
         if not first:
             self.drift(last, t.Ti_Current)
         act, counts = self.build_active()
+        if maxsig is not None:
+            self.kick(1, atime)                     # run.c:498-499
         nact = self.n if act is None else len(act)
         store = np.zeros((self.n, 3))
         common = (C.byref(self.tl), C.byref(self.cosmo), C.byref(self.sp), C.byref(self.gp), C.byref(t), C.c_int64(self.n),
                   _p(self.pos), _p(self.mass), _p(self.type), _p(self.flags), _p(self.vel), _p(self.fullacc), _p(self.gravpm), _p(self.bin_grav),
                   _p(act), C.c_int64(nact), C.c_int64(int(counts[1])))
-        rc = L.oracle_hier_accelerations(*common, C.c_double(self.G), C.c_int(self.nmesh), C.c_double(self.asmth), C.c_double(self.box), _p(store))
+        rc = 0
+        if counts[1] > 0:                           # run.c:533
+            rc = L.oracle_hier_accelerations(*common, C.c_double(self.G), C.c_int(self.nmesh), C.c_double(self.asmth), C.c_double(self.box), _p(store))
         if rc:
             raise RuntimeError("oracle_hier_accelerations failed")
         self.kick(3)
         if is_pm:
             self.kick(2)
         info = np.zeros(2, np.int64)
-        bad = L.oracle_hier_timesteps(*common, C.c_int(1 if is_pm else 0), C.c_double(self.G), C.c_int(self.nmesh), C.c_double(self.asmth),
-                                      C.c_double(self.box), C.c_double(atime), C.c_int(2), _p(store), _p(info))
+        bad = 0
+        if counts[1] > 0:
+            bad = L.oracle_hier_timesteps(*common, C.c_int(1 if is_pm else 0), C.c_double(self.G), C.c_int(self.nmesh), C.c_double(self.asmth),
+                                          C.c_double(self.box), C.c_double(atime), C.c_int(2), _p(store), _p(info))
         if bad < 0:
             raise RuntimeError("oracle_hier_timesteps failed (%d)" % bad)
+        if maxsig is not None:                      # run.c:767-773
+            b2, _ = self.hydro_timesteps(maxsig, atime, first)
+            bad += b2
+            self.kick(1, atime)
         self.kick(3)
         if is_pm:
             self.kick(2)

@@ -174,6 +174,10 @@ def main(which):
         rec = SC.run_hierarchy(S, SC.hierarchy_inputs())
         TS.check_hierarchy(rec)
         print("hierarchy ok")
+    if which in ("gas", "all"):
+        rec = SC.run_gas_hierarchy(S, SC.gas_hierarchy_inputs())
+        TS.check_gas(rec)
+        print("gas ok")
     if which in ("nonsplit", "all"):
         rec = SC.run_nonsplit(S, SC.hierarchy_inputs(seed=15, n=1536))
         TS.check_nonsplit(rec)

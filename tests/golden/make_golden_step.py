@@ -5,7 +5,10 @@ gravity): the integer timeline, drift_all_particles, build_active_particles / bu
 apply_half_kick / apply_hydro_half_kick / apply_PM_half_kick / update_kick_times on a mixed
 DM + gas set with garbage, and eight passes of the hierarchical KDK loop of run.c:355-800
 (hierarchical_gravity_accelerations + hierarchical_gravity_and_timesteps) from the initial step, and six passes of
-the SplitGravityTimestepsOn = 0 loop (force_tree_full + grav_short_tree for the active particles, find_timesteps).
+the SplitGravityTimestepsOn = 0 loop (force_tree_full + grav_short_tree for the active particles, find_timesteps), and ten
+passes of the hierarchical loop with gas taking part (hydro half kicks, find_hydro_timesteps, Hsml prediction; hydro
+accelerations and signal velocities held fixed), including hydro-only sub-steps and one where 5 of 174 active particles are
+gravitationally active.
 Stand-ins only for what needs GSL (flat matter + Lambda H(a), Gauss-Legendre kick integrals;
 oracle/ref_driver.c).  Run in the build container:
     make -C oracle ref && python tests/golden/make_golden_step.py"""
@@ -49,6 +52,13 @@ def main():
         if s in SC.NONSPLIT_KEEP:
             for k in ("pos", "vel", "fullacc"):
                 out["nonsplit/%d/%s" % (s, k)] = r[k]
+    rec3 = SC.run_gas_hierarchy(S, SC.gas_hierarchy_inputs())
+    for s, r in enumerate(rec3):
+        for k in ("bad", "info", "scal", "kick", "last", "bin_grav"):
+            out["gas/%d/%s" % (s, k)] = r[k]
+        if s in SC.GAS_KEEP:
+            for k in ("pos", "vel", "fullacc", "hsml", "entropy"):
+                out["gas/%d/%s" % (s, k)] = r[k]
     path = os.path.join(ROOT, "tests", "golden", "ref_step.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", "bins per step:", [np.bincount(r["bin_grav"])[24:].tolist() for r in rec][-1],

@@ -165,3 +165,35 @@ def run_nonsplit(S, d, steps=NONSPLIT_STEPS):
         rec.append(dict(bad=bad, info=info.copy(), scal=t[0].copy(), kick=t[1].copy(), last=t[2].copy(), bin_grav=g["bin_grav"].copy(),
                         pos=g["pos"].copy(), vel=g["vel"].copy(), fullacc=g["fullacc"].copy()))
     return rec
+
+
+GAS_STEPS = 10
+GAS_KEEP = (0, 9)
+
+
+def gas_hierarchy_inputs(seed=25, n=1536, box=9000.0):
+    """DM + gas (every third particle) for the hierarchical loop with the hydro accelerations, DtEntropy, DtHsml and signal
+    velocities held fixed: exercises the hydro kicks / hydro time bins inside the loop and, because gas can be hydro-active
+    while gravitationally inactive, the sub-list branches at the top of both hierarchical drivers."""
+    d = hierarchy_inputs(seed=seed, n=n, box=box)
+    rng = np.random.default_rng(seed + 1)
+    typ = np.ones(n, np.uint8); typ[::3] = 0
+    gas = typ == 0
+    d.update(type=typ, hsml=np.where(gas, 0.03 * box * (0.5 + rng.random(n)), 0.0), dthsml=np.where(gas, 0.5 * rng.standard_normal(n), 0.0),
+             hydroacc=np.where(gas[:, None], 2.0 * rng.standard_normal((n, 3)), 0.0), entropy=np.where(gas, 1.0 + rng.random(n), 0.0),
+             dtentropy=np.where(gas, 0.05 * rng.standard_normal(n), 0.0), maxsig=np.where(gas, 400.0 * 2.0 ** rng.uniform(4, 12, n), 0.0))
+    return d
+
+
+def run_gas_hierarchy(S, d, steps=GAS_STEPS):
+    S.set_particles(d["pos"], d["mass"], d["type"], d["box"], vel=d["vel"], gravpm=d["gravpm"], hsml=d["hsml"], dthsml=d["dthsml"],
+                    hydroacc=d["hydroacc"], entropy=d["entropy"], dtentropy=d["dtentropy"])
+    S.set_gravity(d["par"], G, d["nmesh"], d["asmth"])
+    S.set_times(np.zeros(7, np.int64), np.zeros(NB, np.int64), np.zeros(NB, np.int64))
+    rec = []
+    for s in range(steps):
+        bad, info = S.advance(first=(s == 0), maxsig=d["maxsig"])
+        g = S.get(); t = S.get_times()
+        rec.append(dict(bad=bad, info=info.copy(), scal=t[0].copy(), kick=t[1].copy(), last=t[2].copy(), bin_grav=g["bin_grav"].copy(),
+                        pos=g["pos"].copy(), vel=g["vel"].copy(), fullacc=g["fullacc"].copy(), hsml=g["hsml"].copy(), entropy=g["entropy"].copy()))
+    return rec

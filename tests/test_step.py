@@ -68,6 +68,25 @@ def test_oracle_nonsplit_loop_equals_reference():
     assert len({int(r["info"][0]) for r in rec}) >= 3                       # sub-steps with different active sets
 
 
+def check_gas(rec, gold=GOLD, rtol=1e-12):
+    for s, r in enumerate(rec):
+        for k in ("info", "scal", "kick", "last", "bin_grav"):
+            assert np.array_equal(r[k], gold["gas/%d/%s" % (s, k)]), (s, k)
+        assert r["bad"] == int(gold["gas/%d/bad" % s])
+        if s in SC.GAS_KEEP:
+            for k in ("pos", "vel", "fullacc", "hsml", "entropy"):
+                assert close(r[k], gold["gas/%d/%s" % (s, k)], rtol), (s, k)
+
+
+def test_oracle_gas_hierarchy_equals_reference():
+    """Ten passes of the hierarchical loop with gas: hydro-only sub-steps (no gravitationally active particle) and a mixed
+    one, where the hierarchical drivers start from a sub-list of the active list."""
+    rec = SC.run_gas_hierarchy(make_oracle(), SC.gas_hierarchy_inputs())
+    check_gas(rec)
+    infos = np.array([r["info"] for r in rec])
+    assert (infos[:, 1] == 0).any() and ((infos[:, 1] > 0) & (infos[:, 1] < infos[:, 0])).any()
+
+
 def test_oracle_timeline_equals_reference():
     O = make_oracle()
     ti, dloga, span = SC.timeline_samples()

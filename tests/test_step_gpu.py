@@ -49,6 +49,11 @@ def test_gpu_hierarchy_equals_reference(stepper):
     TS.check_hierarchy(rec, rtol=1e-9)
 
 
+def test_gpu_gas_hierarchy_equals_reference(stepper):
+    """Ten passes of the hierarchical loop with gas (hydro kicks, hydro time bins, Hsml prediction; hydro-only sub-steps)."""
+    TS.check_gas(SC.run_gas_hierarchy(stepper, SC.gas_hierarchy_inputs()), rtol=1e-9)
+
+
 def test_gpu_nonsplit_loop_equals_reference(stepper):
     """Six passes with SplitGravityTimestepsOn = 0: b200_step_grav_short_tree + half kicks + b200_step_find_timesteps."""
     TS.check_nonsplit(SC.run_nonsplit(stepper, SC.hierarchy_inputs(seed=15, n=1536)), rtol=1e-9)
