@@ -44,6 +44,8 @@ def dropin(which):
     S = R.RefStep(nthreads=2, arena_gib=1.0, so=so, **SC.TIMELINE)
     if which == "dropin_primitives":
         TS.check_primitives(SC.run_primitives(S, SC.primitives_inputs()))
+    elif which == "dropin_gas":
+        TS.check_gas(SC.run_gas_hierarchy(S, SC.gas_hierarchy_inputs()))
     else:
         TS.check_hierarchy(SC.run_hierarchy(S, SC.hierarchy_inputs()))
     print(which + " ok")

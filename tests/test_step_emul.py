@@ -11,7 +11,7 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("which", ["primitives", "hierarchy", "gas", "nonsplit", "dropin_primitives", "dropin_hierarchy", "domain", "decompose"])
+@pytest.mark.parametrize("which", ["primitives", "hierarchy", "gas", "nonsplit", "dropin_primitives", "dropin_hierarchy", "dropin_gas", "domain", "decompose"])
 def test_steploop_source_under_emulation(which):
     """dropin_*: the reference's own loop with its calls redirected (ld --wrap) to host/libgadget_step_shims.c."""
     env = dict(os.environ, OMP_WAIT_POLICY="passive")          # 256 OS threads per emulated block: do not spin

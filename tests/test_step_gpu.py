@@ -68,6 +68,7 @@ def test_gpu_dropin_step_shims(stepper):
     S = R.RefStep(nthreads=2, arena_gib=1.0, so=R.SO_DROPIN_STEP, **SC.TIMELINE)
     TS.check_primitives(SC.run_primitives(S, SC.primitives_inputs()))
     TS.check_hierarchy(SC.run_hierarchy(S, SC.hierarchy_inputs()), rtol=1e-9)
+    TS.check_gas(SC.run_gas_hierarchy(S, SC.gas_hierarchy_inputs()), rtol=1e-9)
 
 
 @pytest.mark.parametrize("name", ["clustered16", "zeldovich16"])
