@@ -154,3 +154,17 @@ def decompose(engine, box, dist=None, overdecomposition=4, subsample=256, attemp
     leaving, togo, ngarbage = engine.exchange_plan(task, world, rank)
     return dict(tree=T, leaf=leaf, nleaf=nleaf, topnodes=top, topleaf=topleaf, task_of_leaf=task, counts=counts, leaving=leaving,
                 target=task[topleaf[leaving]], togo=togo, ngarbage=ngarbage)
+
+
+def maintain(engine, box, topnodes, task_of_leaf, dist=None):
+    """domain_maintain (domain.c:282-347) after a drift on the device (b200_step_drift): the top tree and the leaf -> task
+    table stay, every particle's top leaf is looked up again and those whose task changed form the exchange list.
+    The reference additionally leaves gravitationally inactive dark matter where it is until its next active step
+    (domain.c:315-317, an optimisation tied to its host tree); here every particle follows its leaf at once.
+    -> dict(topleaf, leaving, target, togo, ngarbage)"""
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    engine.peano_keys(box)
+    topleaf = engine.topleaf(*topnodes)
+    leaving, togo, ngarbage = engine.exchange_plan(task_of_leaf, world, rank)
+    return dict(topleaf=topleaf, leaving=leaving, target=np.asarray(task_of_leaf)[topleaf[leaving]], togo=togo, ngarbage=ngarbage)

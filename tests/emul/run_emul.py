@@ -137,6 +137,26 @@ def decompose():
         assert (d["task_of_leaf"][oracle.topleaf(oracle.peano_keys(npos, box), *d["topnodes"])] == rank).all()
         tot = torch.tensor([len(npos)], dtype=torch.int64); dist.all_reduce(tot)
         assert int(tot) == sum(20000 + 7000 * r for r in range(world)) and len(npos) == d["counts"][d["task_of_leaf"] == rank].sum()
+        # domain_maintain: drift the new local set on the (emulated) device, look the leaves up again, exchange the movers
+        SL = importlib.import_module("mp-gadget_b200.steploop")
+        n2 = len(npos)
+        vel = np.random.default_rng(100 + rank).standard_normal((n2, 3)) * 40.0
+        e.set_particles(npos, np.ones(n2, np.float32))
+        S = SL.StepEngine(e, np.log([0.1, 1.0]), lambda k, a, b: 0.5, lambda a: 0.1)
+        S.n, S.box = n2, box
+        st = SL.StepState(vel=vel.ctypes.data, BoxSize=box)
+        assert e.L.b200_step_set_state(e.ctx, C.byref(st)) == 0
+        S.drift(0, 1 << 40)                                             # ddrift = 0.5: displacements of ~20 in a box of 1000
+        moved = S.get()["pos"]
+        want = np.mod(npos + 0.5 * vel, box); want[want <= 0] += box
+        assert np.abs(moved - want).max() < 1e-9
+        m = dom.maintain(e, box, d["topnodes"], d["task_of_leaf"], dist)
+        assert len(m["leaving"]) > 0 and len(m["leaving"]) < n2 // 2
+        new2 = dom.exchange(dict(pos=torch.from_numpy(moved)), m["leaving"], m["target"], dist)
+        p2 = new2["pos"].numpy()
+        assert (d["task_of_leaf"][oracle.topleaf(oracle.peano_keys(p2, box), *d["topnodes"])] == rank).all()
+        tot = torch.tensor([len(p2)], dtype=torch.int64); dist.all_reduce(tot)
+        assert int(tot) == sum(20000 + 7000 * r for r in range(world))
         dist.destroy_process_group()
     print("decompose ok", flush=True)
 
