@@ -3,7 +3,7 @@ TEST INFRASTRUCTURE ONLY.  StepOracle mirrors oracle.ref.RefStep call for call s
 tests read the same on both sides."""
 import ctypes as C
 import numpy as np
-from . import lib, GravShortParams, OracleTree, _c
+from . import lib, GravShortParams, OracleTree
 
 NBINS = 47      # TIMEBINS + 1
 
