@@ -43,7 +43,7 @@ COUNTS_DTYPE = np.dtype([("nodes_accepted", "i4"), ("nodes_opened", "i4"),
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_tree.c", "oracle_pm.c", "oracle_sph.c", "oracle_step.c", "oracle_domain.c", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_tree.c", "oracle_pm.c", "oracle_sph.c", "oracle_step.c", "oracle_domain.c", "oracle_fof.c", "oracle.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     return so
@@ -342,3 +342,13 @@ def exchange_plan(type, flags, topleaf, task_of_leaf, ntask, thistask):
     if nex < 0:
         raise ValueError("exchange_plan: leaf or task out of range")
     return lst[:nex].copy(), togo, int(ng.value)
+
+
+def fof_primary(pos, ids, type, box, ll, mask=2):
+    """fof_label_primary (fof.c:366-470): MinID of every particle for linking length ll over the types in mask"""
+    pos = _c(pos, np.float64); ids = _c(ids, np.int64); type = _c(type, np.uint8)
+    out = np.zeros(len(ids), np.int64)
+    rc = lib().oracle_fof_primary(C.c_int64(len(ids)), _p(pos), _p(ids), _p(type), C.c_int(mask), C.c_double(box), C.c_double(ll), _p(out))
+    if rc:
+        raise MemoryError
+    return out

@@ -202,6 +202,10 @@ int oracle_domain_assign_balanced(int ntask, int32_t nleaf, const int64_t *cost,
 void oracle_topleaf(const uint64_t *keys, int64_t n, const int32_t *daughter, const uint64_t *startkey, const int32_t *shift,
                     const int32_t *leaf, int32_t *out);
 
+/* ---- friends-of-friends, primary linking (oracle_fof.c): fof.c:366-470,540-579 ---- */
+int oracle_fof_primary(int64_t n, const double *pos, const int64_t *ids, const uint8_t *type, int mask, double BoxSize, double ll,
+                       int64_t *minid);
+
 #ifdef __cplusplus
 }
 #endif

@@ -374,5 +374,13 @@ class RefDomain(Ref):
         return lst[:nex].copy(), togo, int(ng.value)
 
 
+    def fof_primary(self, pos, ids, type, box, ll):
+        """fof_label_primary of the reference's own fof.c (FOFPrimaryLinkTypes = 2: dark matter) -> MinID[n]"""
+        pos = np.ascontiguousarray(pos, np.float64); ids = np.ascontiguousarray(ids, np.int64); type = np.ascontiguousarray(type, np.uint8)
+        out = np.zeros(len(ids), np.int64)
+        self.L.ref_fof_primary(C.c_int64(len(ids)), _p(pos), _p(ids), _p(type), C.c_double(box), C.c_double(ll), _p(out))
+        return out
+
+
 def domain_available():
     return os.path.exists(SO_DOMAIN)

@@ -166,6 +166,8 @@ static void build_uniform_domain(DomainDecomp *d, int depth)
     }
 }
 
+void ref_build_uniform_domain(DomainDecomp *d, int depth) { build_uniform_domain(d, depth); }     /* for the other fixture files */
+
 int ref_init(double arena_gib, int nthreads)
 {
     if(initialised) return 0;

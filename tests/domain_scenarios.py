@@ -111,3 +111,22 @@ def exchange_case(seed=8, n=30000, nleaf=97, ntask=5):
     cuts = np.sort(rng.choice(np.arange(1, nleaf), ntask - 1, replace=False))
     task_of_leaf = np.searchsorted(cuts, np.arange(nleaf), side="right").astype(np.int32)
     return typ, flags, topleaf, task_of_leaf, ntask
+
+
+def fof_cases():
+    """(pos, ids, type, box, ll): clustered dark matter with gas mixed in (not a primary link type), shuffled IDs, a close
+    pair across the periodic faces; a uniform box where most groups are single particles."""
+    out = []
+    for seed, n, box in ((2, 6000, 100.0), (3, 4000, 40.0)):
+        rng = np.random.default_rng(seed)
+        pos = rng.random((n, 3)) * box
+        if seed == 2:
+            pos[: n // 3] = 0.5 * box + 0.02 * box * rng.standard_normal((n // 3, 3))
+            pos[n // 3: n // 2] = 0.98 * box + 0.015 * box * rng.standard_normal((n // 2 - n // 3, 3))     # a clump over the corner
+        pos = np.mod(pos, box)
+        ll = 0.2 * box / n ** (1 / 3)
+        pos[-1] = [box - 0.2 * ll, 1.0, 1.0]; pos[-2] = [0.2 * ll, 1.0, 1.0]                                # linked through the face
+        ids = rng.permutation(n).astype(np.int64) + 10
+        typ = np.ones(n, np.uint8); typ[::7] = 0; typ[-2:] = 1
+        out.append((pos, ids, typ, box, ll))
+    return out
