@@ -96,7 +96,10 @@ k_step_active_flags(int64_t n, const uint8_t *__restrict__ type, const uint8_t *
         uint8_t f = 0;
         if(!(flags[i] & 3)) {
             const int ty = type[i] < 6 ? type[i] : 5;
-            const bool hydro_particle = ty == 0 || ty == 5;
+            // gas and black holes carry a hydro bin.  Taken from a bit table, not from `ty == 0 || ty == 5`: for that form
+            // ptxas 12.9 (sm_100a) emits VIMNMX.U16x2 R, P4, P4, type, 0x5 -- one predicate for both 16-bit halves -- and the
+            // hardware then reports every type as a hydro particle (first hardware run of this kernel, round 2).
+            const bool hydro_particle = (0x21u >> ty) & 1u;
             const int bg = bin_grav[i], bh = bin_hydro[i];
             const int b = hydro_particle ? bh : bg;
             atomicAdd(&s_cnt[1 + ty * NBIN + (b < NBIN ? b : TB)], 1u);

@@ -10,16 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    config.addinivalue_line("markers", "gpu_unverified: CUDA code compiled but not yet run on hardware; skips itself without a device")
-
-
-def pytest_collection_modifyitems(config, items):
-    """B200_RUN_UNVERIFIED=1 puts the hardware-pending tests (marker gpu_unverified) under `-m gpu` as well, so that one
-    `pytest -m gpu` run on a GPU box covers them before their markers are switched in the source."""
-    if os.environ.get("B200_RUN_UNVERIFIED") == "1":
-        for it in items:
-            if it.get_closest_marker("gpu_unverified"):
-                it.add_marker(pytest.mark.gpu)
 
 
 @pytest.fixture(scope="session")

@@ -2,7 +2,7 @@
 Golden tests/golden/ref_peano.npz (generator make_golden_peano.py): the 64 known-answer keys of the reference's own
 tests/test_peano.c:107, its compiled peano.c on random positions, domain_get_topleaf over a refined top tree.
 CPU: the oracle (a generated state machine, no stored tables).  The CUDA kernels run under emulation in
-tests/test_step_emul.py[domain]; the hardware test below carries the `gpu_unverified` marker (see test_step_gpu.py)."""
+tests/test_step_emul.py[domain]; the hardware tests below (marker `gpu`) first ran green in round 2."""
 import os
 import sys
 import numpy as np
@@ -115,7 +115,7 @@ def test_oracle_equals_reference_live():
     assert np.array_equal(oracle.topleaf(keys, *top), r.topleaf(keys, *top))
 
 
-@pytest.mark.gpu_unverified
+@pytest.mark.gpu
 def test_gpu_domain_keys(b200):
     try:
         e = b200.Engine(0)
@@ -142,7 +142,7 @@ def test_gpu_domain_keys(b200):
     e.close()
 
 
-@pytest.mark.gpu_unverified
+@pytest.mark.gpu
 def test_gpu_domain_decompose_chain(b200):
     """domain.decompose on one GPU: device keys / lookup / counts / plan around the host top tree; checked against the
     oracle for the same particles (the tree from the oracle's stages, fed with the oracle's subsample keys)."""

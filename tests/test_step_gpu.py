@@ -1,11 +1,8 @@
 """The device-resident step loop (csrc/steploop.cu, b200_step_*) against the golden vectors of the
 reference's own drift.c / timestep.c / timebinmgr.c (tests/golden/ref_step.npz) and the oracle.
 
-STATUS (round 1): the CUDA side is compiled for sm_100a but has NOT yet run on hardware -- the round's
-GPU budget was spent before it was written.  The tests therefore carry their own marker
-(`gpu_unverified`, not `gpu`) and skip themselves when no CUDA device is present; run them first
-thing on a GPU box with  python -m pytest tests/test_step_gpu.py -q  and move them under `gpu`
-once green."""
+First hardware run: round 2 (all green after working round a ptxas 12.9 miscompile in k_step_active_flags,
+see the comment there).  Marker `gpu`."""
 import os
 import sys
 import numpy as np
@@ -16,7 +13,7 @@ sys.path.insert(0, HERE)
 import step_scenarios as SC          # noqa: E402
 import test_step as TS               # noqa: E402
 
-pytestmark = pytest.mark.gpu_unverified
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
