@@ -310,6 +310,7 @@ def main():
     ap.add_argument("--steploop", action="store_true", help="also time hierarchical KDK sub-steps with the particle state resident "
                     "in HBM (b200_step_*; off by default until its first hardware run)")
     ap.add_argument("--ics", default="planewave", choices=["planewave", "fft"])
+    ap.add_argument("--rms", type=float, default=0.2)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -343,7 +344,7 @@ def main():
         pos, mass = ics.zeldovich_lattice(ng, box)
         d_pos, d_mass = torch.from_numpy(pos).cuda(), torch.from_numpy(mass).cuda()
     else:
-        d_pos, d_mass = ics.planewave_lattice(ng, box, device="cuda")
+        d_pos, d_mass = ics.planewave_lattice(ng, box, device="cuda", rms=args.rms)
         pos = d_pos.cpu().numpy(); mass = d_mass.cpu().numpy()
     n = len(mass)
     par = ics.tree_params(box, n, treeusebh=1)

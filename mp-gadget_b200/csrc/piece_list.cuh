@@ -44,21 +44,15 @@ struct PiecePool {
 // is merged into it while the sum stays <= 8: trees whose leaves hold 2-4 particles (anything
 // but a power-of-two lattice) would otherwise leave most of the 8 source slots of a piece idle.
 // MERGE is a compile-time switch: the host turns it off for trees whose leaves are mostly full.
+// The lane's newest entry stays in the register `last` while later pieces can still be merged into it and is
+// stored when the next entry starts (or by piece_finish): one store per entry, none per merge.
 template <bool MERGE>
 __device__ __forceinline__ void piece_push(bool want, unsigned entry, int &mycnt, unsigned &last, int &nch_alloc, int *s_ctab,
                                            const PiecePool &Q, int group, int lane)
 {
-    if(MERGE && (entry & 15u) < 8u) {       // a full piece can never be merged
+    if(MERGE) {
         const bool merge = want && mycnt > 0 && (entry >> 4) == (last >> 4) + (last & 15u) && (last & 15u) + (entry & 15u) <= 8u;
-        if(merge) {
-            last += entry & 15u;
-            const int at = mycnt - 1, ch = at >> CH_SHIFT;
-            if(ch < nch_alloc) {
-                const int id = s_ctab[ch];
-                if(id < Q.cap) Q.pool[(size_t) id * CH_WORDS + (at & (CH_SLOTS - 1)) * 32 + lane] = last;
-            }
-            want = false;
-        }
+        if(merge) { last += entry & 15u; want = false; }
     }
     if(__any_sync(0xffffffffu, want && (mycnt >> CH_SHIFT) >= nch_alloc)) {   // once per CH_SLOTS pieces of the longest list
         const int needch = (int) __reduce_max_sync(0xffffffffu, want ? (unsigned) (mycnt >> CH_SHIFT) : 0u);
@@ -75,19 +69,38 @@ __device__ __forceinline__ void piece_push(bool want, unsigned entry, int &mycnt
         __syncwarp();
     }
     if(want) {
-        const int ch = mycnt >> CH_SHIFT;
-        if(ch < nch_alloc) {
-            const int id = s_ctab[ch];
-            if(id < Q.cap) Q.pool[(size_t) id * CH_WORDS + (mycnt & (CH_SLOTS - 1)) * 32 + lane] = entry;
+        if(MERGE) {
+            if(mycnt > 0) {                                     // the previous entry is final now
+                const int at = mycnt - 1, ch = at >> CH_SHIFT;
+                if(ch < nch_alloc) {
+                    const int id = s_ctab[ch];
+                    if(id < Q.cap) Q.pool[(size_t) id * CH_WORDS + (at & (CH_SLOTS - 1)) * 32 + lane] = last;
+                }
+            }
+        } else {
+            const int ch = mycnt >> CH_SHIFT;
+            if(ch < nch_alloc) {
+                const int id = s_ctab[ch];
+                if(id < Q.cap) Q.pool[(size_t) id * CH_WORDS + (mycnt & (CH_SLOTS - 1)) * 32 + lane] = entry;
+            }
         }
         mycnt++;
         last = entry;
     }
 }
 
-// End of a walk: list lengths in target-slot order + statistics.
-__device__ __forceinline__ void piece_finish(bool valid, int tslot, int mycnt, const PiecePool &Q, int lane)
+// End of a walk: the pending entry (MERGE), list lengths in target-slot order + statistics.
+template <bool MERGE = true>
+__device__ __forceinline__ void piece_finish(bool valid, int tslot, int mycnt, unsigned last, int nch_alloc, const int *s_ctab,
+                                             const PiecePool &Q, int lane)
 {
+    if(MERGE && mycnt > 0) {
+        const int at = mycnt - 1, ch = at >> CH_SHIFT;
+        if(ch < nch_alloc) {
+            const int id = s_ctab[ch];
+            if(id < Q.cap) Q.pool[(size_t) id * CH_WORDS + (at & (CH_SLOTS - 1)) * 32 + lane] = last;
+        }
+    }
     const unsigned wsum = __reduce_add_sync(0xffffffffu, (unsigned) mycnt);
     if(lane == 0) atomicAdd((unsigned long long *) (Q.ctl + 2), (unsigned long long) wsum);
     if(valid) Q.piece_cnt[tslot] = mycnt;

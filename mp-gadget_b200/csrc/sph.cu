@@ -279,7 +279,7 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
         sp += total;
         __syncwarp();
     }
-    piece_finish(valid, tslot, mycnt, Q, lane);
+    piece_finish<true>(valid, tslot, mycnt, mylast, nch_alloc, s_ctab, Q, lane);
     if(valid) reach[tslot] = myreach;
 }
 

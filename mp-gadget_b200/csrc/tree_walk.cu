@@ -52,6 +52,7 @@ struct WalkPar {
     double inv_cell_dx;         // 1 / (cellsize * table spacing)
     int usebh;
     int ntargets;
+    int f32ok;                  // the fp32 pre-classification of the walk may be used (box within float range)
 };
 
 __device__ __forceinline__ double nearest(double x, double box, double halfbox)   // NEAREST partmanager.h:99
@@ -70,6 +71,15 @@ __device__ __forceinline__ double nearest(double x, double box, double halfbox) 
 struct TabD4 {
     const double4 *p;
     __device__ __forceinline__ double4 row(int t) const { return p[t]; }
+};
+struct TabF2 {            // walk kernel: {T, Tpot} floats, two rows per lookup
+    const float2 *p;
+    __device__ __forceinline__ double4 row(int t) const
+    {
+        const float2 a = p[t], b = p[t + 1 < B200_SR_NTAB ? t + 1 : t];
+        const double f0 = (double) a.x, p0 = (double) a.y;
+        return make_double4(f0, (double) b.x - f0, p0, (double) b.y - p0);
+    }
 };
 struct TabF4x8 {
     const float4 *p;        // already offset by the lane's copy: p = base + (lane & 7)
@@ -281,14 +291,61 @@ __device__ __forceinline__ void pair_sum(const PieceList &L, int g, int slot,
     }
 }
 
-// Staged node rows of the current batch (one entry per lane).
+// Staged node rows of the current batch (one entry per lane).  The fp64 rows are the reference's
+// operands; the fp32 rows are the same vectors taken relative to the centre of the warp's bounding box
+// (after NEAREST), which is what the per-lane pre-classification reads.
 struct BatchEntry {
     double4 A[32];    // cofm, mass
-    double4 B[32];    // center, len
-    double4 D[32];    // node_consts
+    float4 C[32];     // centre - bbox centre, len
+    float4 F[32];     // cofm - bbox centre, (mass*len)*len
+    float4 T[32];     // error bounds {tau2 on r2, mu on |centre - p|}, rcut + len/2, 0.6 len
     int4 M[32];       // pstart, count, mask of lanes (targets) that opened every ancestor,
-                      // flags (bit0: leaf, bit1: rejected for all lanes by the bounding-box test)
+                      // flags (bit0: leaf, bit1: rejected for all lanes by the bounding-box test,
+                      //        bit2: fp32 rows unusable (box seam, underflow): exact classification only)
+    int N[32];        // node index
 };
+
+// Per-lane constants of the fp32 pre-classification.
+struct Lane32 {
+    float px, py, pz;       // position - bbox centre
+    float alo, ahi;         // bounds of ErrTolForceAcc * |a_old| / G
+};
+struct Walk32 {
+    float rcut2, th2lo, th2hi;
+    bool rel;
+};
+
+// Interval version of classify(): every comparison of shall_we_discard_node / shall_we_open_node
+// (gravshort-tree.c:198-241) is evaluated at both ends of the rounding-error interval of its fp32
+// operands (r2 in [r2 - tau2, r2 + tau2], max |centre - p| in [c - mu, c + mu], the thresholds widened by
+// 1e-6 relative).  `discard` increases with both, `open` decreases with both, so when the two ends agree the
+// fp64 decision is known; otherwise 3 = undecided and the caller repeats the node in fp64.  The bounds:
+// operands are fp32 roundings (u = 2^-24) of fp64 vectors relative to the bbox centre, |p'| <= hb, hence
+// |err(dx)| <= u (2|dx| + 2 hb), |err(r2)| <= u (10.5 r2 + 3.5 hb^2) <= tau2 := 1e-6 ((|m'| + hb)^2 + hb^2) + ...,
+// |err(c)| <= u (2 |c'| + 4 hb) <= mu (hb = half diagonal of the box).
+__device__ __forceinline__ int classify32(const float4 C, const float4 F, const float4 T, const Lane32 &L, const Walk32 &W)
+{
+    const float dx = F.x - L.px, dy = F.y - L.py, dz = F.z - L.pz;
+    const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const float cm = fmaxf(fmaxf(fabsf(C.x - L.px), fabsf(C.y - L.py)), fabsf(C.z - L.pz));
+    const float r2lo = fmaxf(r2 - T.x, 0.f), r2hi = r2 + T.x;
+    const float clo = cm - T.y, chi = cm + T.y;
+    const bool dlo = (r2lo > W.rcut2) & (clo > T.z), dhi = (r2hi > W.rcut2) & (chi > T.z);
+    const float l2 = C.w * C.w;
+    const bool oup = (W.rel & (F.w > r2lo * r2lo * L.alo)) | (l2 > W.th2lo * r2lo) | (clo < T.w);   // open => oup
+    const bool odn = (W.rel & (F.w > r2hi * r2hi * L.ahi)) | (l2 > W.th2hi * r2hi) | (chi < T.w);   // odn => open
+    const bool undecided = (dlo != dhi) | ((!dhi) & (oup != odn));
+    return undecided ? 3 : (dhi ? 0 : (oup ? 2 : 1));
+}
+
+// The fp64 decision for one node, out of line: taken only when the fp32 intervals straddle a threshold.
+__device__ __noinline__ int classify_exact(const double4 A, const double4 B, double px, double py, double pz, double aold,
+                                           const WalkPar &P, bool wrap)
+{
+    double dx, dy, dz, r2;
+    const double4 D = node_consts(A, B, P);
+    return wrap ? classify<true>(A, B, D, px, py, pz, aold, P, dx, dy, dz, r2) : classify<false>(A, B, D, px, py, pz, aold, P, dx, dy, dz, r2);
+}
 
 template <bool COUNT, bool MERGE>
 __global__ void __launch_bounds__(128, WALK_MINB)
@@ -302,24 +359,23 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             double4 *__restrict__ partial,                  // [target slot] sums over accepted nodes {ax, ay, az, pot}
             int4 *__restrict__ counts_out)
 {
-    __shared__ double4 tab[B200_SR_NTAB];
+    __shared__ float2 tab[B200_SR_NTAB];                // {T, Tpot} (gravity.c:20: the table IS float)
     extern __shared__ int s_ctab_dyn[];                 // [WALK_WARPS][Q.maxch]
     __shared__ int s_stk_node_all[WALK_WARPS][WALK_STACK];
     __shared__ unsigned s_stk_mask_all[WALK_WARPS][WALK_STACK];
     __shared__ BatchEntry s_ent_all[WALK_WARPS];
-    for(int k = threadIdx.x; k < B200_SR_NTAB; k += blockDim.x) {
-        const int k1 = k + 1 < B200_SR_NTAB ? k + 1 : k;
-        const double f0 = gtab[k], f1 = gtab[k1], p0 = gtab[B200_SR_NTAB + k], p1 = gtab[B200_SR_NTAB + k1];
-        tab[k] = k + 1 < B200_SR_NTAB ? make_double4(f0, f1 - f0, p0, p1 - p0) : make_double4(0, 0, 0, 0);
-    }
+    __shared__ double s_bbox_all[WALK_WARPS][8];        // bbox centre, half extents, half diagonal of the warp's targets
+    for(int k = threadIdx.x; k < B200_SR_NTAB; k += blockDim.x)
+        tab[k] = make_float2(gtab[k], gtab[B200_SR_NTAB + k]);       // monopole() never takes t >= NTAB-1 as the base row
     __syncthreads();
     const int wib = threadIdx.x >> 5;
     int *s_ctab = s_ctab_dyn + wib * Q.maxch;
     int *s_stk_node = s_stk_node_all[wib];
     unsigned *s_stk_mask = s_stk_mask_all[wib];
     BatchEntry &s_ent = s_ent_all[wib];
+    double *s_bbox = s_bbox_all[wib];
     int mycnt = 0;          // pieces in this lane's list
-    unsigned mylast = 0;    // its last entry (merged with the next piece when contiguous)
+    unsigned mylast = 0;    // its last entry (merged with the next piece when contiguous; stored when the next one starts)
     int nch_alloc = 0;      // chunks this warp owns (warp-uniform)
 
     const int lane = threadIdx.x & 31;
@@ -336,16 +392,35 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
         // grav_get_abs_accel gravshort.h:69-86 (sqrt(..)/G), then * ErrTolForceAcc (gravshort-tree.c:264)
         aold = __dmul_rn(P.ErrTol, __ddiv_rn(oldacc[me], P.G));
     }
-    // bounding box (centre, half extent) of the warp's targets
-    const double big = 1e300;
-    const double lox = warp_min(valid ? px : big), hix = warp_max(valid ? px : -big);
-    const double loy = warp_min(valid ? py : big), hiy = warp_max(valid ? py : -big);
-    const double loz = warp_min(valid ? pz : big), hiz = warp_max(valid ? pz : -big);
-    const double bcx = 0.5 * (lox + hix), bcy = 0.5 * (loy + hiy), bcz = 0.5 * (loz + hiz);
-    const double bhx = 0.5 * (hix - lox), bhy = 0.5 * (hiy - loy), bhz = 0.5 * (hiz - loz);
-    const bool warp_central = lox >= P.wrap_lo && hix <= P.wrap_hi && loy >= P.wrap_lo && hiy <= P.wrap_hi &&
-                              loz >= P.wrap_lo && hiz <= P.wrap_hi;
+    Lane32 L32;
+    bool warp_central;
     const unsigned validmask = __ballot_sync(0xffffffffu, valid);
+    {
+        // bounding box (centre, half extent) of the warp's targets, kept in shared memory
+        const double big = 1e300;
+        const double lox = warp_min(valid ? px : big), hix = warp_max(valid ? px : -big);
+        const double loy = warp_min(valid ? py : big), hiy = warp_max(valid ? py : -big);
+        const double loz = warp_min(valid ? pz : big), hiz = warp_max(valid ? pz : -big);
+        const double bcx = 0.5 * (lox + hix), bcy = 0.5 * (loy + hiy), bcz = 0.5 * (loz + hiz);
+        const double bhx = 0.5 * (hix - lox), bhy = 0.5 * (hiy - loy), bhz = 0.5 * (hiz - loz);
+        warp_central = lox >= P.wrap_lo && hix <= P.wrap_hi && loy >= P.wrap_lo && hiy <= P.wrap_hi &&
+                       loz >= P.wrap_lo && hiz <= P.wrap_hi;
+        if(lane == 0) {
+            s_bbox[0] = bcx; s_bbox[1] = bcy; s_bbox[2] = bcz; s_bbox[3] = bhx; s_bbox[4] = bhy; s_bbox[5] = bhz;
+            // bounds |p - bc| of every lane (plus a rounding allowance)
+            s_bbox[6] = 1.0000001 * sqrt(bhx * bhx + bhy * bhy + bhz * bhz) + 1e-30;
+        }
+        // fp32 side: everything relative to the bbox centre
+        L32.px = valid ? (float) (px - bcx) : 0.f; L32.py = valid ? (float) (py - bcy) : 0.f; L32.pz = valid ? (float) (pz - bcz) : 0.f;
+        const float a32 = (float) aold;
+        const bool tiny = !(a32 >= 1e-30f);
+        L32.alo = tiny ? 0.f : a32 * (1.f - 2e-6f);
+        L32.ahi = (tiny ? 1e-30f : a32) * (1.f + 2e-6f);
+    }
+    Walk32 W32;
+    W32.rcut2 = (float) P.rcut2;
+    W32.th2lo = (float) P.theta2 * (1.f - 2e-6f); W32.th2hi = (float) P.theta2 * (1.f + 2e-6f);
+    W32.rel = P.usebh == 0;
 
     double ax = 0, ay = 0, az = 0, pot = 0;
     int n_acc = 0, n_open = 0, n_disc = 0, n_part = 0;
@@ -367,12 +442,15 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
         sp -= nb;
         // ---- lane-parallel: lane l fetches entry sp + l, tests it against the warp's bounding box
         int mynode = -1, mynch = 0;
+        bool dead = false, isleaf = false;
         if(lane < nb) {
             mynode = s_stk_node[sp + lane];
             const unsigned emask0 = s_stk_mask[sp + lane];
             const double4 eB = nodeB[mynode];
             const int4 C = nodeC[mynode];
             int eflags0 = C.w ? 1 : 0;
+            isleaf = C.w != 0;
+            const double bcx = s_bbox[0], bcy = s_bbox[1], bcz = s_bbox[2], hbd = s_bbox[6];
             // Early discard for all lanes (gravshort-tree.c:198-215): along some axis the
             // node centre is farther than rcut + len/2 (+ rounding margin) from the whole
             // bounding box; the centre of mass lies inside the cell, so r2 > rcut^2 follows.
@@ -382,24 +460,42 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             if(!warp_central) {
                 ex = nearest(ex, P.box, P.halfbox); ey = nearest(ey, P.box, P.halfbox); ez = nearest(ez, P.box, P.halfbox);
             }
-            if(fabs(ex) - bhx > lim || fabs(ey) - bhy > lim || fabs(ez) - bhz > lim) eflags0 |= 2;
+            if(fabs(ex) - s_bbox[3] > lim || fabs(ey) - s_bbox[4] > lim || fabs(ez) - s_bbox[5] > lim) { eflags0 |= 2; dead = true; }
             else {
                 const double4 eA = nodeA[mynode];
                 s_ent.A[lane] = eA;
-                s_ent.D[lane] = node_consts(eA, eB, P);
+                double mx = eA.x - bcx, my = eA.y - bcy, mz = eA.z - bcz;
+                if(!warp_central) {
+                    mx = nearest(mx, P.box, P.halfbox); my = nearest(my, P.box, P.halfbox); mz = nearest(mz, P.box, P.halfbox);
+                }
+                const double ml2 = __dmul_rn(__dmul_rn(eA.w, eB.w), eB.w);
+                const double cinf = fmax(fmax(fabs(ex), fabs(ey)), fabs(ez));
+                const double minf = fmax(fmax(fabs(mx), fabs(my)), fabs(mz));
+                const double rmax = sqrt(mx * mx + my * my + mz * mz) + hbd;
+                // a lane's NEAREST(node - p) equals (node - bc wrapped) - (p - bc) only away from the +-box/2 seam
+                const bool seam = !warp_central && (fmax(cinf, minf) + hbd >= 0.999999 * P.halfbox);
+                if(!P.f32ok || seam || (ml2 > 0.0 && ml2 < 1e-30)) eflags0 |= 4;
+                s_ent.C[lane] = make_float4((float) ex, (float) ey, (float) ez, (float) eB.w);
+                s_ent.F[lane] = make_float4((float) mx, (float) my, (float) mz, (float) ml2);
+                s_ent.T[lane] = make_float4((float) (1e-6 * (rmax * rmax + hbd * hbd) + 4e-7 * P.rcut2),
+                                            (float) (4e-7 * (cinf + hbd + eff + eB.w)),
+                                            (float) eff, (float) __dmul_rn(0.6, eB.w));
             }
-            s_ent.B[lane] = eB;
             s_ent.M[lane] = make_int4(C.y, C.z, (int) emask0, eflags0);
+            s_ent.N[lane] = mynode;
         }
         __syncwarp();
-        // ---- per-target exact decisions: the staged nodes that survived the bounding-box test,
-        // two at a time (independent arithmetic chains)
+        // ---- phase 1, per-target decisions on the staged nodes that survived the bounding-box test, two at a
+        // time (independent arithmetic chains).  Results stay in per-lane bit sets over the batch slots; only
+        // an internal node needs the warp's vote (who descends).
         unsigned myopeners = 0;       // lane l keeps the openers of entry l
-        const bool dead = lane < nb && (s_ent.M[lane].w & 2);
+        unsigned accbits = 0, openbits = 0;     // batch slots this lane accepted / opened
+        const unsigned deadmask = __ballot_sync(0xffffffffu, dead);
+        const unsigned leafmask = __ballot_sync(0xffffffffu, isleaf);
         unsigned live = __ballot_sync(0xffffffffu, lane < nb && !dead);
         if(COUNT) {
             const unsigned myemask = lane < nb ? (unsigned) s_ent.M[lane].z : 0u;
-            for(unsigned m = __ballot_sync(0xffffffffu, dead); m; m &= m - 1) {
+            for(unsigned m = deadmask; m; m &= m - 1) {
                 const unsigned e = __shfl_sync(0xffffffffu, myemask, __ffs(m) - 1);
                 if((e >> lane) & 1u) n_disc++;
             }
@@ -410,48 +506,57 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             const int kB = haveB ? __ffs(live) - 1 : kA; live &= live - 1;
             const int4 MA = s_ent.M[kA], MB = s_ent.M[kB];
             const bool awakeA = (((unsigned) MA.z) >> lane) & 1u, awakeB = haveB && ((((unsigned) MB.z) >> lane) & 1u);
-            const double4 AA = s_ent.A[kA], BA = s_ent.B[kA], AB = s_ent.A[kB], BB = s_ent.B[kB];
-            const double4 DA = s_ent.D[kA], DB = s_ent.D[kB];
-            int decA = 0, decB = 0;
-            double dxA = 0, dyA = 0, dzA = 0, r2A = 0, dxB = 0, dyB = 0, dzB = 0, r2B = 0;
-            if(warp_central) {
-                decA = classify<false>(AA, BA, DA, px, py, pz, aold, P, dxA, dyA, dzA, r2A);
-                decB = classify<false>(AB, BB, DB, px, py, pz, aold, P, dxB, dyB, dzB, r2B);
-            } else {
-                decA = classify<true>(AA, BA, DA, px, py, pz, aold, P, dxA, dyA, dzA, r2A);
-                decB = classify<true>(AB, BB, DB, px, py, pz, aold, P, dxB, dyB, dzB, r2B);
+            int decA = classify32(s_ent.C[kA], s_ent.F[kA], s_ent.T[kA], L32, W32);
+            int decB = classify32(s_ent.C[kB], s_ent.F[kB], s_ent.T[kB], L32, W32);
+            if((MA.w & 4)) decA = 3;
+            if((MB.w & 4)) decB = 3;
+            if(__any_sync(0xffffffffu, (awakeA && decA == 3) || (awakeB && decB == 3))) {
+                // rare: some lane is within rounding of a threshold (or the node sits on the box seam):
+                // the reference's own fp64 comparisons decide
+                decA = classify_exact(s_ent.A[kA], nodeB[s_ent.N[kA]], px, py, pz, aold, P, !warp_central);
+                decB = classify_exact(s_ent.A[kB], nodeB[s_ent.N[kB]], px, py, pz, aold, P, !warp_central);
             }
             decA = awakeA ? decA : -1; decB = awakeB ? decB : -1;
-            const unsigned openA = __ballot_sync(0xffffffffu, decA == 2), openB = __ballot_sync(0xffffffffu, decB == 2);
-#pragma unroll
-          for(int half = 0; half < 2; half++) {
-            const int k = half ? kB : kA;
-            const int4 M = half ? MB : MA;
-            const int decision = half ? decB : decA;
-            const unsigned openmask = half ? openB : openA;
-            const int eflags = M.w;
-            const bool wantopen = decision == 2;
-            if(decision == 1) {
-                if(half) monopole(dxB, dyB, dzB, r2B, AB.w, P, TabD4{tab}, ax, ay, az, pot);
-                else monopole(dxA, dyA, dzA, r2A, AA.w, P, TabD4{tab}, ax, ay, az, pot);
-                if(COUNT) n_acc++;
+            accbits |= (decA == 1 ? 1u : 0u) << kA; accbits |= (decB == 1 ? 1u : 0u) << kB;
+            openbits |= (decA == 2 ? 1u : 0u) << kA; openbits |= (decB == 2 ? 1u : 0u) << kB;
+            if(COUNT) { n_disc += (decA == 0) + (decB == 0); }
+            if(!(MA.w & 1)) { const unsigned o = __ballot_sync(0xffffffffu, decA == 2); if(lane == kA) myopeners = o; }
+            if(haveB && !(MB.w & 1)) { const unsigned o = __ballot_sync(0xffffffffu, decB == 2); if(lane == kB) myopeners = o; }
+        }
+        // ---- phase 2, accepted nodes: monopole x tabulated window in fp64 (apply_accn_to_output), every lane
+        // working through ITS OWN accepted slots (lanes accept different nodes; this keeps them all busy)
+        if(COUNT) n_acc += __popc(accbits);
+        while(__any_sync(0xffffffffu, accbits != 0)) {
+            if(accbits) {
+                const int k = __ffs(accbits) - 1; accbits &= accbits - 1;
+                const double4 AN = s_ent.A[k];
+                double dx = AN.x - px, dy = AN.y - py, dz = AN.z - pz;
+                if(!warp_central) { dx = nearest(dx, P.box, P.halfbox); dy = nearest(dy, P.box, P.halfbox); dz = nearest(dz, P.box, P.halfbox); }
+                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                monopole(dx, dy, dz, r2, AN.w, P, TabF2{tab}, ax, ay, az, pot);
             }
-            if(COUNT && decision == 0) n_disc++;
-            if(openmask == 0) continue;
-            if(eflags & 1) {
-                // particle leaf (gravshort-tree.c:344-352): every lane that opened it appends the
-                // piece(s) to its own list; pieces of <= 8 particles (only leaves at the key-depth
-                // limit hold more)
-                if(COUNT && wantopen) n_part += M.y;
-                for(int o = 0; o < M.y; o += 8) {
-                    const int c = M.y - o < 8 ? M.y - o : 8;
-                    piece_push<MERGE>(wantopen, PIECE(M.x + o, c), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
+        }
+        // ---- phase 3, opened particle leaves (gravshort-tree.c:344-352): every lane appends its own leaves, in
+        // slot order, to its piece list; pieces of <= 8 particles (only leaves at the key-depth limit hold more)
+        if(COUNT) { n_open += __popc(openbits & ~leafmask); }
+        openbits &= leafmask;
+        while(__any_sync(0xffffffffu, openbits != 0)) {
+            const bool want = openbits != 0;
+            int pstart = 0, cnt = 0;
+            if(want) {
+                const int k = __ffs(openbits) - 1; openbits &= openbits - 1;
+                const int4 M = s_ent.M[k];
+                pstart = M.x; cnt = M.y;
+                if(COUNT) n_part += cnt;
+            }
+            if(__any_sync(0xffffffffu, cnt > 8)) {
+                const int maxc = (int) __reduce_max_sync(0xffffffffu, (unsigned) cnt);
+                for(int o = 0; o < maxc; o += 8) {
+                    const int c = cnt - o < 8 ? cnt - o : 8;
+                    piece_push<MERGE>(want && o < cnt, PIECE(pstart + o, c > 0 ? c : 0), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
                 }
-            } else {
-                if(COUNT && wantopen) n_open++;
-                if(lane == k) myopeners = openmask;
-            }
-          }
+            } else
+                piece_push<MERGE>(want, PIECE(pstart, cnt), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
         }
         // ---- lane-parallel: push the children of opened internal nodes
         int4 k0 = make_int4(-1, -1, -1, -1), k1 = k0;
@@ -473,7 +578,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
         __syncwarp();
     }
     // hand over to k_grav_pairs (target-slot order: coalesced)
-    piece_finish(valid, tslot, mycnt, Q, lane);
+    piece_finish<MERGE>(valid, tslot, mycnt, mylast, nch_alloc, s_ctab, Q, lane);
     if(valid) {
         partial[tslot] = make_double4(ax, ay, az, pot);
         if(COUNT) counts_out[me] = make_int4(n_acc, n_open, n_disc, n_part);
@@ -694,6 +799,10 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
     P.h2s = P.h2 > 2.3e-308 ? P.h2 : 2.3e-308;
     P.sentinel = (int) E->tree_np;
     P.inv_cell_dx = 1.0 / (cellsize * (double) B200_SR_DX);
+    {   // fp32 pre-classification: r2^2 * aold and mass*len^2 must stay far from the ends of the float range
+        static const bool off = getenv("B200_WALK_F64") != nullptr;
+        P.f32ok = (!off && E->tree_box > 1e-6 && E->tree_box < 1e7) ? 1 : 0;
+    }
     {   // reach of the window table: index >= NTAB-1 <=> r >= (NTAB-1)*dx cells = 15 cells (gravity.c:57-61)
         const double reach = 1.001 * (B200_SR_NTAB - 1) * (double) B200_SR_DX * cellsize;
         P.wrap_lo = reach; P.wrap_hi = E->tree_box - reach;
