@@ -179,7 +179,12 @@ int b200_ctx_create(b200_ctx **out, int device)
     c->e.device = device;
     if(cudaStreamCreateWithFlags(&c->e.stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 6; }
     if(cudaStreamCreateWithFlags(&c->e.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->e.stream); delete c; return 6; }
-    if(cudaStreamCreateWithFlags(&c->e.side_stream, cudaStreamNonBlocking) != cudaSuccess) return 6;
+    {   // the side stream (PM step running beside the tree walk) outranks the main stream: its HBM-bound kernels are
+        // placed as soon as walk blocks retire instead of queueing behind the walk's whole grid
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if(cudaStreamCreateWithPriority(&c->e.side_stream, cudaStreamNonBlocking, hi) != cudaSuccess) return 6;
+    }
     if(cudaEventCreateWithFlags(&c->e.fork_ev, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->e.join_ev, cudaEventDisableTiming) != cudaSuccess) return 6;
     *out = c;
     return 0;

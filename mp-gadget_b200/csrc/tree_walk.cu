@@ -132,7 +132,7 @@ __device__ __forceinline__ void monopole(double dx, double dy, double dz, double
 }
 
 #ifndef WALK_MINB
-#define WALK_MINB 5
+#define WALK_MINB 6
 #endif
 #ifndef PAIR_MINB
 #define PAIR_MINB 2
