@@ -136,6 +136,34 @@ def planewave_lattice(ng, box, xplanes=None, seed=181170, rms=0.2, nmodes=64, km
     return pos.contiguous(), mass
 
 
+BENCH_STATES = {
+    # lattice + plane-wave displacement, rms 1 spacing: leaf occupancy of the octree no longer depends on how the
+    # lattice spacing divides the box (a 2^k lattice puts exactly 8 particles in every leaf), so timings at different
+    # box sizes -- the weak-scaling series -- are like for like.  The default bench state.
+    "displaced": dict(rms=1.0),
+    # SURVEY 8d "z9": rms 0.2 spacing, the particles still sit next to their lattice sites
+    "z9": dict(rms=0.2),
+}
+
+
+def bench_ics(state, ng, box, device="cpu", xplanes=None, seed=181170):
+    """Synthetic boxes of bench.py / the config-size parity tests, as torch tensors pos[n,3] f64, mass[n] f32.
+    'displaced' / 'z9': planewave_lattice at rms 1.0 / 0.2 spacings (any x-range of the same global set: xplanes).
+    'clustered': SURVEY 8d's second state = the reference's do_random_test recipe (tests/test_gravity.c:288-302) at ng^3
+    particles: 1/4 uniform, 1/2 in a clump at Box/2 of size Box/8, 1/4 in a clump at 0.1 Box of size Box/32 (deep tree)."""
+    import torch
+    if state in BENCH_STATES:
+        return planewave_lattice(ng, box, xplanes=xplanes, seed=seed, device=device, **BENCH_STATES[state])
+    if state != "clustered":
+        raise ValueError("unknown bench state %r" % (state,))
+    if xplanes is not None:
+        raise ValueError("the clustered state is generated whole")
+    n = ng ** 3
+    pos = np.mod(clustered_mix(n, box, seed=seed), box)
+    mass = np.full(n, OMEGA0 * rho_crit() * (box / ng) ** 3, dtype=np.float32)
+    return torch.from_numpy(pos).to(device), torch.from_numpy(mass).to(device)
+
+
 class FlatLCDM:
     """What the reference's host takes from cosmology.c / timefac.c / timebinmgr.c, for bench and tool runs of the step
     loop: hubble_function for a flat matter + Lambda background, the drift / kick integrals of timefac.c:12-73
