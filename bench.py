@@ -208,7 +208,8 @@ def sharded_config(world, ng_per_gpu):
     nmesh = min(cands, key=lambda m: abs(m - 3 * ng_tot))
     rcut_spacings = 6.0 * 1.5 * ng_tot / nmesh
     d = 1
-    while (1 << (d + 1)) * rcut_spacings * 1.02 < 1.001 * ng_tot and d < 8:
+    # a top cell must stay wider than Rcut also across the periodic seam, where the 1.001 Box root cell costs 0.001 Box
+    while 1.001 * ng_tot / (1 << (d + 1)) - 0.001 * ng_tot > rcut_spacings * 1.02 and d < 8:
         d += 1
     while (1 << d) % world:
         d -= 1

@@ -103,6 +103,9 @@ int b200_oldacc_from_last_step(b200_ctx *ctx);
  *               (gravpm.c:383-454), gradient (gravpm.c:458-489), readout
  *               (gravpm.c:499-510). */
 int b200_pm_init(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G);
+/* The three scalars grav_short_tree reads from its PetaPM argument (CellSize = BoxSize/Nmesh, Asmth, G;
+ * gravshort-tree.c:101-102, gravshort.h:47-67) for a host that keeps the PM step elsewhere: no mesh is allocated. */
+int b200_walk_set_mesh(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G);
 /* gravpm_out[n][3] (P[i].GravPM) and potential_out[n] (the PM contribution
  * added to P[i].Potential) for every particle; either may be NULL. */
 int b200_pm_force(b200_ctx *ctx, double *gravpm_out, double *potential_out);
@@ -287,8 +290,7 @@ int b200_density_gradrho(b200_ctx *ctx, double *gradrho);
 int b200_hydro_force(b200_ctx *ctx, const b200_sph_params *par, double *hydroaccel, double *dtentropy,
                      double *maxsignalvel, int32_t *ninteract);
 
-/* ---- multi-GPU building blocks (one process + one context per GPU; the host
- * harness moves the buffers between ranks with NCCL) --------------------------
+/* ---- multi-GPU building blocks ------------------------------------------------
  *
  * Top-tree moments: the analogue of force_exchange_pseudodata (MPI_Allgatherv of
  * struct topleaf_momentsdata, libgadget/forcetree.c:1145-1208) and
@@ -299,26 +301,37 @@ int b200_hydro_force(b200_ctx *ctx, const b200_sph_params *par, double *hydroacc
 int b200_tree_top_get_dev(b200_ctx *ctx, int level, double *cells_out);
 int b200_tree_top_set_dev(b200_ctx *ctx, int level, const double *cells_in);
 
-/* Slab-decomposed PM: replaces the 2-D pencil layout + PFFT transposes of
- * petapm_init / petapm_force (libgadget/petapm.c:127-187,284-357,584-885).
- * Rank r owns mesh planes [r*Nmesh/nranks, (r+1)*Nmesh/nranks).  The three
- * device buffers are returned so the harness can exchange halo planes and do the
- * all-to-all transpose:
- *   real  [(nx+2*halo)][Nmesh][Nmesh] f64, plane 0 = global plane x0-halo
- *   cplx  [nx][Nmesh][Nmesh/2+1] complex f64 (after the 2-D transforms)
- *   cplxT [ny][Nmesh][Nmesh/2+1] complex f64 (y-slab, full x; 1-D transforms + Green's function)
- * Sequence per PM step: deposit -> (halo planes added into the neighbours) ->
- * fft2d(0) -> transpose -> fft1d(0) -> transfer -> fft1d(1) -> transpose back ->
- * fft2d(1) -> (halo planes copied from the neighbours) -> readout. */
-int b200_pmslab_init(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G,
-                     int rank, int nranks, int halo,
-                     void **real_buf, void **cplx_buf, void **cplxT_buf);
-/* CIC deposit of the first n_own particles (the rank's own, ghosts follow them). */
-int b200_pmslab_deposit(b200_ctx *ctx, int64_t n_own);
-int b200_pmslab_fft2d(b200_ctx *ctx, int inverse);
-int b200_pmslab_fft1d(b200_ctx *ctx, int inverse);
-int b200_pmslab_transfer(b200_ctx *ctx);
-int b200_pmslab_readout_dev(b200_ctx *ctx, int64_t n_own, double *gravpm_out, double *potential_out);
+/* ---- the sharded TreePM force step (one process + one context per GPU, NCCL issued from C) ----------------
+ * Replaces, for one rank of an N-rank run, what the reference does collectively inside gravpm_force and
+ * grav_short_tree: the domain-boundary exchange of the short-range walk (treewalk.c:325-371,399-793; here a ghost
+ * import of the adjacent top-cell layer), force_exchange_pseudodata / force_treeupdate_pseudos
+ * (forcetree.c:1156-1284; an all-reduce of the level-d cell moments), the pencil exchange of petapm_force
+ * (petapm.c:584-885; halo planes to the neighbours) and PFFT's transposes (petapm.c:305,344; an all-to-all between
+ * the 2-D and the 1-D transforms of an x-slab mesh).  Domain: rank r owns the x-layers [r*2^d/W, (r+1)*2^d/W) of the
+ * cells of the uniform forced top tree of depth d (d such that a cell is wider than Rcut: checked).
+ *
+ * b200_comm_unique_id: 128 bytes from ncclGetUniqueId, made on rank 0 and broadcast by the host (MPI_Bcast in an
+ *   MP-Gadget host, torch.distributed in the harness); two ids -- the tree and the PM chains run on separate streams
+ *   and need separate communicators.  NCCL is taken from the process at run time (dlopen of libnccl.so.2).
+ * b200_comm_init: ncclCommInitRank x 2 on the context's device.  world == 1 needs no ids (self-neighbour copies).
+ * b200_sharded_init: slab mesh, FFT plans, exchange buffers.  halo >= 4 mesh planes; rcut_cells = TreeRcut.
+ * b200_sharded_force_step: DEVICE pointers.  pos_own[n][3], mass_own[n], oldacc3_own[n][3] (FullTreeGravAccel +
+ *   GravPM of the last step, NULL on the first) of the particles inside this rank's layers; writes GravPM[n][3],
+ *   FullTreeGravAccel[n][3], Potential[n] of those particles.  Collective: every rank of the communicator calls it. */
+typedef struct b200_sharded_info {
+    int64_t n_own, n_from_left, n_from_right, n_to_left, n_to_right;
+    /* device time of the phases, ms (CUDA events): ghost import; the PM chain on its stream (runs beside the tree
+     * build and walk); the top-moment all-reduce */
+    double ms_ghost, ms_pm_total, ms_pm_deposit, ms_pm_halo_add, ms_pm_fft2d, ms_pm_pack, ms_pm_a2a_forward,
+           ms_pm_fft1d_transfer, ms_pm_a2a_backward, ms_pm_unpack, ms_pm_ifft2d, ms_pm_halo_fill, ms_pm_readout,
+           ms_top_allreduce;
+} b200_sharded_info;
+int b200_comm_unique_id(void *id_out_128_bytes);
+int b200_comm_init(b200_ctx *ctx, int rank, int world, const void *id_tree, const void *id_pm);
+int b200_sharded_init(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G, int topdepth, int halo, double rcut_cells);
+int b200_sharded_force_step(b200_ctx *ctx, const double *pos_own, const float *mass_own, const double *oldacc3_own, int64_t n_own,
+                            const b200_gravshort_params *par, double *gravpm_out, double *accel_out, double *potential_out,
+                            b200_sharded_info *info);
 
 /* ---- Step loop around the force computation (device-resident particle state) -------------------
  * Replaces, for collisionless and gas particles, drift_all_particles (libgadget/drift.c:84-102),

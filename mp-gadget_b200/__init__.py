@@ -73,6 +73,25 @@ class Timings(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ShardedInfo(C.Structure):
+    """b200_sharded_info"""
+    _fields_ = [(k, C.c_int64) for k in ("n_own", "n_from_left", "n_from_right", "n_to_left", "n_to_right")] + \
+               [(k, C.c_double) for k in ("ms_ghost", "ms_pm_total", "ms_pm_deposit", "ms_pm_halo_add", "ms_pm_fft2d", "ms_pm_pack",
+                                          "ms_pm_a2a_forward", "ms_pm_fft1d_transfer", "ms_pm_a2a_backward", "ms_pm_unpack",
+                                          "ms_pm_ifft2d", "ms_pm_halo_fill", "ms_pm_readout", "ms_top_allreduce")]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the engine library (rank 0 calls it, the host broadcasts the 128 bytes)."""
+    buf = C.create_string_buffer(128)
+    if lib().b200_comm_unique_id(buf) != 0:
+        raise B200Error("b200_comm_unique_id failed (NCCL not available in this process)")
+    return buf.raw
+
+
 COUNTS_DTYPE = np.dtype([("nodes_accepted", "i4"), ("nodes_opened", "i4"),
                          ("nodes_discarded", "i4"), ("particles", "i4")])
 
@@ -88,12 +107,12 @@ PARTICLE_DTYPE = np.dtype({
 EXPORTED = [
     "b200_default_particle_layout", "b200_ctx_create", "b200_ctx_destroy", "b200_last_error",
     "b200_abi_version", "b200_kernel_launches", "b200_set_particles_aos", "b200_set_particles_soa",
-    "b200_set_particles_soa_dev", "b200_oldacc_from_last_step", "b200_pm_init", "b200_pm_force",
+    "b200_set_particles_soa_dev", "b200_oldacc_from_last_step", "b200_pm_init", "b200_walk_set_mesh", "b200_pm_force",
     "b200_pm_force_dev", "b200_pm_set_power", "b200_pm_get_power", "b200_pm_cell_index", "b200_pm_copy_mesh", "b200_tree_build", "b200_tree_free",
     "b200_tree_export", "b200_grav_short_tree", "b200_grav_short_tree_dev", "b200_force_step_aos", "b200_force_step_dev",
     "b200_get_timings", "b200_stream",
-    "b200_tree_top_get_dev", "b200_tree_top_set_dev", "b200_pmslab_init", "b200_pmslab_deposit",
-    "b200_pmslab_fft2d", "b200_pmslab_fft1d", "b200_pmslab_transfer", "b200_pmslab_readout_dev",
+    "b200_tree_top_get_dev", "b200_tree_top_set_dev",
+    "b200_comm_unique_id", "b200_comm_init", "b200_sharded_init", "b200_sharded_force_step",
     "b200_sph_set_gas", "b200_sph_set_timebins", "b200_sph_set_active", "b200_sph_set_hsml_range", "b200_sph_set_state", "b200_density", "b200_density_gradrho", "b200_hydro_force",
     "b200_step_set_state", "b200_step_get_state", "b200_step_adopt_forces", "b200_step_drift", "b200_step_build_active",
     "b200_step_active_sublist", "b200_step_get_active", "b200_step_half_kick", "b200_step_pm_kick",
@@ -194,6 +213,11 @@ class Engine:
     def gravpm_init_periodic(self, BoxSize, Asmth, Nmesh, G):
         self.nmesh = int(Nmesh)
         self._ck(self.L.b200_pm_init(self.ctx, C.c_double(BoxSize), C.c_double(Asmth), C.c_int(Nmesh), C.c_double(G)))
+
+    def walk_set_mesh(self, BoxSize, Asmth, Nmesh, G):
+        """The scalars grav_short_tree takes from the PetaPM struct (cell size, Asmth, G) without allocating a mesh."""
+        self.nmesh = int(Nmesh)
+        self._ck(self.L.b200_walk_set_mesh(self.ctx, C.c_double(BoxSize), C.c_double(Asmth), C.c_int(Nmesh), C.c_double(G)))
 
     def gravpm_force(self, want_potential=True):
         g = np.empty((self.n, 3))
@@ -317,28 +341,25 @@ class Engine:
     def tree_top_set_dev(self, level, ptr):
         self._ck(self.L.b200_tree_top_set_dev(self.ctx, C.c_int(level), C.c_void_p(ptr)))
 
-    def pmslab_init(self, BoxSize, Asmth, Nmesh, G, rank, nranks, halo):
-        r, c, t = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        self._ck(self.L.b200_pmslab_init(self.ctx, C.c_double(BoxSize), C.c_double(Asmth), C.c_int(Nmesh), C.c_double(G),
-                                         C.c_int(rank), C.c_int(nranks), C.c_int(halo), C.byref(r), C.byref(c), C.byref(t)))
+    # -- the sharded TreePM force step (sharded.cu; NCCL issued from C) ---------------
+    def comm_init(self, rank, world, id_tree=None, id_pm=None):
+        """id_*: 128-byte buffers from comm_unique_id() of rank 0, broadcast by the host."""
+        a = (C.c_char * 128).from_buffer_copy(bytes(id_tree)) if id_tree is not None else None
+        b = (C.c_char * 128).from_buffer_copy(bytes(id_pm)) if id_pm is not None else None
+        self._ck(self.L.b200_comm_init(self.ctx, C.c_int(rank), C.c_int(world), a, b))
+
+    def sharded_init(self, BoxSize, Asmth, Nmesh, G, topdepth, halo=6, rcut_cells=0.0):
+        self._ck(self.L.b200_sharded_init(self.ctx, C.c_double(BoxSize), C.c_double(Asmth), C.c_int(Nmesh), C.c_double(G),
+                                          C.c_int(topdepth), C.c_int(halo), C.c_double(rcut_cells)))
         self.nmesh = int(Nmesh)
-        return r.value, c.value, t.value
 
-    def pmslab_deposit(self, n_own):
-        self._ck(self.L.b200_pmslab_deposit(self.ctx, C.c_int64(n_own)))
-
-    def pmslab_fft2d(self, inverse):
-        self._ck(self.L.b200_pmslab_fft2d(self.ctx, C.c_int(inverse)))
-
-    def pmslab_fft1d(self, inverse):
-        self._ck(self.L.b200_pmslab_fft1d(self.ctx, C.c_int(inverse)))
-
-    def pmslab_transfer(self):
-        self._ck(self.L.b200_pmslab_transfer(self.ctx))
-
-    def pmslab_readout_dev(self, n_own, gravpm_ptr, pot_ptr=None):
-        self._ck(self.L.b200_pmslab_readout_dev(self.ctx, C.c_int64(n_own), C.c_void_p(gravpm_ptr),
-                                                C.c_void_p(pot_ptr) if pot_ptr else None))
+    def sharded_force_step(self, par, pos_ptr, mass_ptr, oldacc_ptr, n_own, gravpm_ptr, acc_ptr, pot_ptr):
+        p = GravShortParams(**par) if isinstance(par, dict) else par
+        info = ShardedInfo()
+        v = lambda x: C.c_void_p(x) if x else None
+        self._ck(self.L.b200_sharded_force_step(self.ctx, v(pos_ptr), v(mass_ptr), v(oldacc_ptr), C.c_int64(n_own), C.byref(p),
+                                                v(gravpm_ptr), v(acc_ptr), v(pot_ptr), C.byref(info)))
+        return info
 
     # -- whole step on the reference's AoS -------------------------------------
     def force_step_aos(self, P, par, ptr=None, n=None):

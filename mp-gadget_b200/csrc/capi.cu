@@ -128,7 +128,7 @@ static int ensure_particles(Engine *E, int64_t n)
     return 0;
 }
 
-static int collect_timings(Engine *E)
+int collect_timings(Engine *E)
 {
     b200_timings &t = E->last;
     t.pm_deposit = timer_ms(E, T_PM_DEPOSIT); t.pm_fft_forward = timer_ms(E, T_PM_FFT_FWD);
@@ -219,6 +219,7 @@ void b200_ctx_destroy(b200_ctx *ctx)
     for(int i = 0; i < T_COUNT; i++) if(E->timers[i].a) { cudaEventDestroy(E->timers[i].a); cudaEventDestroy(E->timers[i].b); }
     for(int i = 0; i < 65; i++) if(E->chunk_ev[i]) cudaEventDestroy(E->chunk_ev[i]);
     cudaStreamDestroy(E->copy_stream);
+    sharded_destroy(E);
     cudaStreamDestroy(E->side_stream);
     cudaEventDestroy(E->fork_ev); cudaEventDestroy(E->join_ev);
     cudaStreamDestroy(E->stream);
@@ -294,6 +295,14 @@ int b200_oldacc_from_last_step(b200_ctx *ctx)
     k_oldacc_from_last<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->n, E->have_last_tree ? E->last_tree_acc.p : nullptr,
                                                                           E->have_last_pm ? E->last_pm_acc.p : nullptr, E->oldacc.p);
     CKL(E);
+    return 0;
+}
+
+int b200_walk_set_mesh(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G)
+{
+    ENTER(ctx);
+    if(!(BoxSize > 0) || !(Asmth > 0) || Nmesh < 2) return failmsg(E, "b200_walk_set_mesh: bad arguments");
+    E->Box = BoxSize; E->Asmth = Asmth; E->G = G; E->NmeshWalk = Nmesh;
     return 0;
 }
 
@@ -663,31 +672,6 @@ int b200_tree_top_set_dev(b200_ctx *ctx, int level, const double *cells_in)
     if(int rc = tree_top_set(E, level, cells_in)) return rc;
     CK(cudaStreamSynchronize(E->stream));
     return 0;
-}
-
-int b200_pmslab_init(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, double G, int rank, int nranks, int halo,
-                     void **real_buf, void **cplx_buf, void **cplxT_buf)
-{
-    ENTER(ctx);
-    return pmslab_init(E, BoxSize, Asmth, Nmesh, G, rank, nranks, halo, real_buf, cplx_buf, cplxT_buf);
-}
-int b200_pmslab_deposit(b200_ctx *ctx, int64_t n_own) { ENTER(ctx); return pmslab_deposit(E, n_own); }
-int b200_pmslab_fft2d(b200_ctx *ctx, int inverse) { ENTER(ctx); if(int rc = pmslab_fft2d(E, inverse)) return rc; CK(cudaStreamSynchronize(E->stream)); return 0; }
-int b200_pmslab_fft1d(b200_ctx *ctx, int inverse) { ENTER(ctx); if(int rc = pmslab_fft1d(E, inverse)) return rc; CK(cudaStreamSynchronize(E->stream)); return 0; }
-int b200_pmslab_transfer(b200_ctx *ctx) { ENTER(ctx); if(int rc = pmslab_transfer(E)) return rc; CK(cudaStreamSynchronize(E->stream)); return 0; }
-int b200_pmslab_readout_dev(b200_ctx *ctx, int64_t n_own, double *gravpm_out, double *potential_out)
-{
-    ENTER(ctx);
-    if(int rc = pmslab_readout(E, n_own, gravpm_out, potential_out)) return rc;
-    // keep the PM accelerations of the own particles for b200_oldacc_from_last_step
-    if(gravpm_out && n_own > 0) {
-        CK(E->last_pm_acc.ensure(3 * (size_t) E->n));
-        CK(cudaMemsetAsync(E->last_pm_acc.p, 0, 3 * (size_t) E->n * sizeof(double), E->stream));
-        CK(cudaMemcpyAsync(E->last_pm_acc.p, gravpm_out, 3 * (size_t) n_own * sizeof(double), cudaMemcpyDeviceToDevice, E->stream));
-        E->have_last_pm = true;
-    }
-    CK(cudaStreamSynchronize(E->stream));
-    return collect_timings(E);
 }
 
 int b200_get_timings(const b200_ctx *ctx, b200_timings *t)

@@ -47,6 +47,7 @@ struct NodeAux {           // int4
 };
 
 struct SlabPM;
+struct Sharded;
 
 #define B200_SPART_PAD 16     // massless far-away rows behind spart[np) (tree_walk.cu pair loop)
 
@@ -90,6 +91,7 @@ struct Engine {
     bool pm_ps_valid = false;
     DevBuf<double> pm_ps;      // [3][Nmesh] Power, kk, Nmodes sums + Norm
     SlabPM *slab = nullptr;
+    Sharded *sh = nullptr;      // multi-GPU driver state (sharded.cu)
 
     // ---- tree ----
     bool tree_valid = false;
@@ -214,11 +216,15 @@ struct SlabPM;
 int pmslab_init(Engine *E, double Box, double Asmth, int Nmesh, double G, int rank, int nranks, int halo,
                 void **real_buf, void **cplx_buf, void **cplxT_buf);
 void pmslab_destroy(Engine *E);
-int pmslab_deposit(Engine *E, int64_t n_own);
+int pmslab_deposit(Engine *E, int64_t n_own, bool check = true);
 int pmslab_fft2d(Engine *E, int inverse);
 int pmslab_fft1d(Engine *E, int inverse);
 int pmslab_transfer(Engine *E);
-int pmslab_readout(Engine *E, int64_t n_own, double *d_gravpm, double *d_pot);
+int pmslab_readout(Engine *E, int64_t n_own, double *d_gravpm, double *d_pot, bool check = true);
+
+// multi-GPU driver (sharded.cu)
+void sharded_destroy(Engine *E);
+int collect_timings(Engine *E);       // capi.cu: Engine::last from the event timers
 
 // SPH (sph.cu)
 int sph_set_gas(Engine *E, const double *vel, const double *hsml, const double *entropy, const double *dtentropy,

@@ -9,23 +9,16 @@
 //
 // Real-space buffer:  planes [x0-halo, x0+nx+halo) x N x N  (density, then potential)
 // Spectrum buffer:    [nx][N][N/2+1] complex (after the 2-D transforms)
-// Transposed buffer:  [nyloc][N (x)][N/2+1] complex (y-slab, full x)
+// Transposed buffer:  [N (x)][nyloc][N/2+1] complex (y-slab, full x): exactly what the all-to-all delivers when
+//                     rank s sends its block [ix][jy][kz] of my y-range -- the blocks, concatenated by source rank,
+//                     ARE the x-major array, so the 1-D transforms along x run on the receive buffer in place
+//                     (one strided cuFFT plan, stride nyloc*(N/2+1), batch nyloc*(N/2+1)) and nothing is unpacked.
 // Forces are the 4-point difference of the potential fused into the CIC readout
 // (see pm.cu header for why that equals the reference's k-space gradient).
-#include "engine.h"
+#include "pm_slab.h"
 #include <math.h>
 
 namespace b200 {
-
-struct SlabPM {
-    double Box = 0, Asmth = 0, G = 0;
-    int N = 0, Nz = 0, rank = 0, nranks = 1, halo = 0;
-    int x0 = 0, nx = 0, y0 = 0, ny = 0;
-    DevBuf<double> real, cplx, cplxT, ktab;
-    DevBuf<int> err;
-    cufftHandle p2f = 0, p2i = 0, p1 = 0;
-    bool plans = false;
-};
 
 static const char *cufft_str2(cufftResult r) { return r == CUFFT_ALLOC_FAILED ? "CUFFT_ALLOC_FAILED" : (r == CUFFT_INVALID_SIZE ? "CUFFT_INVALID_SIZE" : "CUFFT_ERROR"); }
 #define CKF(call) do { cufftResult _r = (call); if(_r != CUFFT_SUCCESS) return failmsg(E, std::string(#call) + ": " + cufft_str2(_r)); } while(0)
@@ -74,7 +67,7 @@ k_slab_deposit(const double *__restrict__ pos, const float *__restrict__ mass, c
     }
 }
 
-// potential_transfer (gravpm.c:383-454) in the transposed layout [jy][ix][iz], ky = y0 + jy
+// potential_transfer (gravpm.c:383-454) in the transposed layout [ix][jy][iz], ky = y0 + jy
 __global__ void __launch_bounds__(256)
 k_slab_transfer(double2 *__restrict__ v, int N, int Nz, int y0, int ny, const double *__restrict__ ktab,
                 double asmth2, double pot_factor)
@@ -83,8 +76,8 @@ k_slab_transfer(double2 *__restrict__ v, int N, int Nz, int y0, int ny, const do
     for(size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t) gridDim.x * blockDim.x) {
         const int iz = (int) (idx % Nz);
         const size_t row = idx / Nz;
-        const int ix = (int) (row % N);
-        const int iy = y0 + (int) (row / N);
+        const int iy = y0 + (int) (row % ny);
+        const int ix = (int) (row / ny);
         const int kx = ix <= N / 2 ? ix : ix - N;
         const int ky = iy <= N / 2 ? iy : iy - N;
         const long long k2 = (long long) kx * kx + (long long) ky * ky + (long long) iz * iz;
@@ -101,7 +94,9 @@ k_slab_transfer(double2 *__restrict__ v, int N, int Nz, int y0, int ny, const do
 }
 
 // readout_potential / readout_force_* (gravpm.c:499-510) with the 4-point
-// difference of the potential evaluated on the fly at each CIC corner.
+// difference of the potential evaluated on the fly at each CIC corner (the arithmetic of
+// k_pm_readout_fused, pm.cu, on the slab's local planes).  The six planes / rows / columns the
+// two corners per axis need are wrapped once per particle.
 __global__ void __launch_bounds__(128)
 k_slab_readout(const double *__restrict__ pos, const uint8_t *__restrict__ flags, int64_t n, double cellsize,
                int N, int x0, int nx, int halo, const double *__restrict__ pot, double inv12h,
@@ -116,33 +111,39 @@ k_slab_readout(const double *__restrict__ pos, const uint8_t *__restrict__ flags
         const int nxh = nx + 2 * halo;
         const double wx[2] = {1 - res[0], res[0]}, wy[2] = {1 - res[1], res[1]}, wz[2] = {1 - res[2], res[2]};
         const size_t NN = (size_t) N * N;
-        bool bad = false;
+        int xs[6], ys[6], zs[6];
+        // local plane of global plane ic[0] - 2; the following five are consecutive (no wrap inside slab + halos)
+        const int lx0 = local_plane(ic[0] - 2, x0, nxh, halo, N);
+        const int y0 = wrapi2(ic[1] - 2, N), z0 = wrapi2(ic[2] - 2, N);
+        const bool bad = lx0 < 0 || lx0 + 5 >= nxh;
 #pragma unroll
-        for(int c = 0; c < 8; c++) {
-            const int ox = c & 1, oy = (c >> 1) & 1, oz = (c >> 2) & 1;
-            const int gx = ic[0] + ox;
-            const int lx = local_plane(gx, x0, nxh, halo, N);
-            const int lxm1 = local_plane(gx - 1, x0, nxh, halo, N), lxp1 = local_plane(gx + 1, x0, nxh, halo, N);
-            const int lxm2 = local_plane(gx - 2, x0, nxh, halo, N), lxp2 = local_plane(gx + 2, x0, nxh, halo, N);
-            if(lx < 0 || lxm1 < 0 || lxp1 < 0 || lxm2 < 0 || lxp2 < 0) { bad = true; continue; }
-            const int y = wrapi2(ic[1] + oy, N), z = wrapi2(ic[2] + oz, N);
-            const int ym1 = wrapi2(y - 1, N), yp1 = wrapi2(y + 1, N), ym2 = wrapi2(y - 2, N), yp2 = wrapi2(y + 2, N);
-            const int zm1 = wrapi2(z - 1, N), zp1 = wrapi2(z + 1, N), zm2 = wrapi2(z - 2, N), zp2 = wrapi2(z + 2, N);
-            const size_t yz = (size_t) y * N + z;
-            const double *pl = pot + (size_t) lx * NN;
-            const double gx_ = 8.0 * (__ldg(pot + lxp1 * NN + yz) - __ldg(pot + lxm1 * NN + yz))
-                             - (__ldg(pot + lxp2 * NN + yz) - __ldg(pot + lxm2 * NN + yz));
-            const double gy_ = 8.0 * (__ldg(pl + (size_t) yp1 * N + z) - __ldg(pl + (size_t) ym1 * N + z))
-                             - (__ldg(pl + (size_t) yp2 * N + z) - __ldg(pl + (size_t) ym2 * N + z));
-            const double gz_ = 8.0 * (__ldg(pl + (size_t) y * N + zp1) - __ldg(pl + (size_t) y * N + zm1))
-                             - (__ldg(pl + (size_t) y * N + zp2) - __ldg(pl + (size_t) y * N + zm2));
-            const double w = __dmul_rn(__dmul_rn(wx[ox], wy[oy]), wz[oz]);
-            a0 = __dadd_rn(a0, __dmul_rn(w, -gx_ * inv12h));
-            a1 = __dadd_rn(a1, __dmul_rn(w, -gy_ * inv12h));
-            a2 = __dadd_rn(a2, __dmul_rn(w, -gz_ * inv12h));
-            p  = __dadd_rn(p,  __dmul_rn(w, __ldg(pl + yz)));
+        for(int k = 0; k < 6; k++) {
+            xs[k] = bad ? 0 : lx0 + k;
+            ys[k] = y0 + k >= N ? y0 + k - N : y0 + k;
+            zs[k] = z0 + k >= N ? z0 + k - N : z0 + k;
         }
         if(bad) atomicAdd(err, 1);
+        else {
+#pragma unroll
+            for(int c = 0; c < 8; c++) {
+                const int ox = c & 1, oy = (c >> 1) & 1, oz = (c >> 2) & 1;
+                const int jx = 2 + ox, jy = 2 + oy, jz = 2 + oz;
+                const size_t rowyz = (size_t) ys[jy] * N + zs[jz];
+                const size_t rowxz = (size_t) xs[jx] * NN + zs[jz];
+                const size_t rowxy = (size_t) xs[jx] * NN + (size_t) ys[jy] * N;
+                const double gx_ = 8.0 * (__ldg(pot + xs[jx + 1] * NN + rowyz) - __ldg(pot + xs[jx - 1] * NN + rowyz))
+                                 - (__ldg(pot + xs[jx + 2] * NN + rowyz) - __ldg(pot + xs[jx - 2] * NN + rowyz));
+                const double gy_ = 8.0 * (__ldg(pot + rowxz + (size_t) ys[jy + 1] * N) - __ldg(pot + rowxz + (size_t) ys[jy - 1] * N))
+                                 - (__ldg(pot + rowxz + (size_t) ys[jy + 2] * N) - __ldg(pot + rowxz + (size_t) ys[jy - 2] * N));
+                const double gz_ = 8.0 * (__ldg(pot + rowxy + zs[jz + 1]) - __ldg(pot + rowxy + zs[jz - 1]))
+                                 - (__ldg(pot + rowxy + zs[jz + 2]) - __ldg(pot + rowxy + zs[jz - 2]));
+                const double w = __dmul_rn(__dmul_rn(wx[ox], wy[oy]), wz[oz]);
+                a0 = __dadd_rn(a0, __dmul_rn(w, -gx_ * inv12h));
+                a1 = __dadd_rn(a1, __dmul_rn(w, -gy_ * inv12h));
+                a2 = __dadd_rn(a2, __dmul_rn(w, -gz_ * inv12h));
+                p  = __dadd_rn(p,  __dmul_rn(w, __ldg(pot + xs[jx] * NN + rowyz)));
+            }
+        }
     }
     if(gravpm) { gravpm[3 * i] = a0; gravpm[3 * i + 1] = a1; gravpm[3 * i + 2] = a2; }
     if(potout) potout[i] = p;
@@ -159,7 +160,7 @@ void pmslab_destroy(Engine *E)
     SlabPM *S = E->slab;
     if(!S) return;
     if(S->plans) { cufftDestroy(S->p2f); cufftDestroy(S->p2i); cufftDestroy(S->p1); }
-    S->real.release(); S->cplx.release(); S->cplxT.release(); S->ktab.release(); S->err.release();
+    S->real.release(); S->cplx.release(); S->cplxT.release(); S->ktab.release(); S->err.release(); S->work.release();
     delete S;
     E->slab = nullptr;
 }
@@ -182,13 +183,21 @@ int pmslab_init(Engine *E, double Box, double Asmth, int Nmesh, double G, int ra
     CK(S->cplxT.ensure(2 * (size_t) S->ny * N * Nz));
     CK(S->err.ensure(4));
     CK(cudaMemsetAsync(S->err.p, 0, 4 * sizeof(int), E->stream));
+    // three plans that never run concurrently share one work area
     int n2[2] = {Nmesh, Nmesh};
-    CKF(cufftPlanMany(&S->p2f, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, S->nx));
-    CKF(cufftPlanMany(&S->p2i, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, S->nx));
     int n1[1] = {Nmesh};
     int emb[1] = {Nmesh};
-    CKF(cufftPlanMany(&S->p1, 1, n1, emb, (int) Nz, 1, emb, (int) Nz, 1, CUFFT_Z2Z, (int) Nz));
+    const int strideT = S->ny * (int) Nz;
+    size_t ws[3] = {0, 0, 0};
+    CKF(cufftCreate(&S->p2f)); CKF(cufftCreate(&S->p2i)); CKF(cufftCreate(&S->p1));
     S->plans = true;
+    CKF(cufftSetAutoAllocation(S->p2f, 0)); CKF(cufftSetAutoAllocation(S->p2i, 0)); CKF(cufftSetAutoAllocation(S->p1, 0));
+    CKF(cufftMakePlanMany(S->p2f, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_D2Z, S->nx, &ws[0]));
+    CKF(cufftMakePlanMany(S->p2i, 2, n2, nullptr, 1, 0, nullptr, 1, 0, CUFFT_Z2D, S->nx, &ws[1]));
+    CKF(cufftMakePlanMany(S->p1, 1, n1, emb, strideT, 1, emb, strideT, 1, CUFFT_Z2Z, strideT, &ws[2]));
+    size_t wmax = ws[0] > ws[1] ? ws[0] : ws[1]; if(ws[2] > wmax) wmax = ws[2];
+    CK(S->work.ensure(wmax + 256));
+    CKF(cufftSetWorkArea(S->p2f, S->work.p)); CKF(cufftSetWorkArea(S->p2i, S->work.p)); CKF(cufftSetWorkArea(S->p1, S->work.p));
     CKF(cufftSetStream(S->p2f, E->stream)); CKF(cufftSetStream(S->p2i, E->stream)); CKF(cufftSetStream(S->p1, E->stream));
     std::vector<double> tab(Nmesh);
     for(int i = 0; i < Nmesh; i++) {
@@ -208,7 +217,7 @@ int pmslab_init(Engine *E, double Box, double Asmth, int Nmesh, double G, int ra
     return 0;
 }
 
-int pmslab_deposit(Engine *E, int64_t n_own)
+int pmslab_deposit(Engine *E, int64_t n_own, bool check)
 {
     SlabPM *S = E->slab;
     if(!S) return failmsg(E, "b200_pmslab_deposit: call b200_pmslab_init first");
@@ -222,6 +231,7 @@ int pmslab_deposit(Engine *E, int64_t n_own)
         CKL(E);
     }
     timer_stop(E, T_PM_DEPOSIT);
+    if(!check) return 0;
     int herr = 0;
     CK(cudaMemcpyAsync(&herr, S->err.p, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
@@ -246,12 +256,9 @@ int pmslab_fft1d(Engine *E, int inverse)
 {
     SlabPM *S = E->slab;
     if(!S) return failmsg(E, "b200_pmslab_fft1d: no slab");
-    const size_t plane = (size_t) S->N * S->Nz;
-    for(int j = 0; j < S->ny; j++) {
-        cufftDoubleComplex *p = (cufftDoubleComplex *) S->cplxT.p + (size_t) j * plane;
-        CKF(cufftExecZ2Z(S->p1, p, p, inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
-    }
-    E->launches += S->ny;
+    cufftDoubleComplex *p = (cufftDoubleComplex *) S->cplxT.p;
+    CKF(cufftExecZ2Z(S->p1, p, p, inverse ? CUFFT_INVERSE : CUFFT_FORWARD));
+    E->launches += 1;
     return 0;
 }
 
@@ -268,7 +275,7 @@ int pmslab_transfer(Engine *E)
     return 0;
 }
 
-int pmslab_readout(Engine *E, int64_t n_own, double *d_gravpm, double *d_pot)
+int pmslab_readout(Engine *E, int64_t n_own, double *d_gravpm, double *d_pot, bool check)
 {
     SlabPM *S = E->slab;
     if(!S) return failmsg(E, "b200_pmslab_readout: no slab");
@@ -280,10 +287,20 @@ int pmslab_readout(Engine *E, int64_t n_own, double *d_gravpm, double *d_pot)
         CKL(E);
     }
     timer_stop(E, T_PM_READOUT);
+    if(!check) return 0;
     int herr = 0;
     CK(cudaMemcpyAsync(&herr, S->err.p, sizeof(int), cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     if(herr) { cudaMemsetAsync(S->err.p, 0, sizeof(int), E->stream); return failmsg(E, "b200_pmslab_readout: particles outside this rank's slab + halo"); }
+    return 0;
+}
+
+// Set the stream of the three plans (the PM step may run on a side stream).
+int pmslab_set_stream(Engine *E, cudaStream_t st)
+{
+    SlabPM *S = E->slab;
+    if(!S) return failmsg(E, "pmslab_set_stream: no slab");
+    CKF(cufftSetStream(S->p2f, st)); CKF(cufftSetStream(S->p2i, st)); CKF(cufftSetStream(S->p1, st));
     return 0;
 }
 

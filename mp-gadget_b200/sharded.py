@@ -121,6 +121,9 @@ class Domain:
         self.per = self.ncell // world
         self.lo, self.hi = rank * self.per, (rank + 1) * self.per
         self.cellwidth = 1.001 * self.box / self.ncell
+        # width over which the last layer holds particles across the periodic seam (the root cell is 1.001 Box wide):
+        # this, not cellwidth, has to exceed Rcut / the largest smoothing length
+        self.seamwidth = self.cellwidth - 0.001 * self.box
         self.domainfac = 1.0 / (self.box * 1.001) * float(1 << 21)       # PEANO(), utils/peano.h:15-21
 
     def layer_of(self, x):
@@ -197,108 +200,124 @@ def halo_fill(comm, real, nx, h, buf_a, buf_b):
 
 
 class ShardedTreePM:
-    def __init__(self, engine, box, nmesh, asmth, G, topdepth, dist=None, halo=6, device="cuda"):
+    """One rank of the sharded TreePM force step.  The step itself is b200_sharded_force_step (csrc/sharded.cu): ghost
+    import, slab PM with its halo exchanges and all-to-all transposes, tree build, top-moment all-reduce and walk are
+    issued from C on the engine's streams with NCCL.  This class only bootstraps the communicators (the two NCCL ids
+    travel over torch.distributed, as they would over MPI_Bcast in an MP-Gadget host) and owns the output tensors.
+    world size 1 needs no NCCL (self-neighbour copies): that is how the single-GPU tests compare it with the unsharded path."""
+
+    def __init__(self, engine, box, nmesh, asmth, G, topdepth, dist=None, halo=6, device="cuda", rcut_cells=None):
+        import importlib
+        pkg = importlib.import_module(__package__)
         self.e = engine
-        self.comm = Comm(dist)
-        self.rank, self.world = self.comm.rank, self.comm.world
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
         self.box, self.nmesh, self.asmth, self.G = float(box), int(nmesh), float(asmth), float(G)
         self.dom = Domain(box, topdepth, self.rank, self.world)
         self.device = torch.device(device)
-        self.halo = halo
-        if nmesh % (2 * self.world):
-            raise ValueError("Nmesh must be a multiple of 2*world")
-        self.nx = nmesh // self.world
-        self.nz = nmesh // 2 + 1
-        r, c, t = engine.pmslab_init(box, asmth, nmesh, G, self.rank, self.world, halo)
-        N, nx, nz, h = nmesh, self.nx, self.nz, halo
-        self.real = dev_tensor(r, (nx + 2 * h, N, N), self.device)
-        self.cplx = dev_tensor(c, (nx, N, nz, 2), self.device)
-        self.cplxT = dev_tensor(t, (nx, N, nz, 2), self.device)          # [ny][x][kz], ny == nx
-        self.sendbuf = torch.empty((self.world, nx, nx, nz, 2), dtype=torch.float64, device=self.device) if self.world > 1 else None
-        self.recvbuf = torch.empty_like(self.sendbuf) if self.world > 1 else None
-        self.halo_a = torch.empty((h, N, N), dtype=torch.float64, device=self.device)
-        self.halo_b = torch.empty_like(self.halo_a)
-        self.own_cells = self.dom.own_cell_mask(self.device)
-        self.top = torch.empty((8 ** topdepth, 4), dtype=torch.float64, device=self.device)
-        self.timings = {}
-
-    # ---- particles ---------------------------------------------------------
-    def load(self, pos, mass, oldacc=None, rcut_cells=None):
-        """pos [n,3] f64, mass [n] f32 device tensors of the rank's OWN particles
-        (every x inside the rank's layers).  Imports the ghost layers and hands
-        own+ghost to the engine."""
-        if rcut_cells is not None:
-            rcut = rcut_cells * self.asmth * self.box / self.nmesh
-            if not self.dom.cellwidth > rcut * 1.0001:
-                raise ValueError("top-tree cells (%.4g) must be wider than Rcut (%.4g): lower topdepth" % (self.dom.cellwidth, rcut))
-        n_own = pos.shape[0]
-        to_l, to_r = self.dom.ghost_sets(pos[:, 0])
-        pm = torch.cat([pos, mass.to(torch.float64)[:, None]], dim=1)
-        fr, fl = self.comm.neighbour_exchange_var(pm[to_l], pm[to_r])
-        ghosts = torch.cat([fl, fr], dim=0)
-        self.n_own = n_own
-        self.pos = torch.cat([pos, ghosts[:, :3]], dim=0).contiguous()
-        self.mass = torch.cat([mass, ghosts[:, 3].to(torch.float32)], dim=0).contiguous()
-        self.n_tot = self.pos.shape[0]
-        self.oldacc = None
-        if oldacc is not None:
-            self.oldacc = torch.zeros((self.n_tot, 3), dtype=torch.float64, device=self.device)
-            self.oldacc[:n_own] = oldacc
-        torch.cuda.synchronize() if self.device.type == "cuda" else None
-        self.e.set_particles_dev(self.pos.data_ptr(), self.mass.data_ptr(), self.n_tot,
-                                 oldacc_ptr=self.oldacc.data_ptr() if self.oldacc is not None else None)
-        self.targets = torch.arange(n_own, dtype=torch.int32, device=self.device)
-        self.acc = torch.zeros((self.n_tot, 3), dtype=torch.float64, device=self.device)
-        self.pot = torch.zeros(self.n_tot, dtype=torch.float64, device=self.device)
-        self.gpm = torch.zeros((self.n_tot, 3), dtype=torch.float64, device=self.device)
-        return self.n_tot - n_own
-
-    # ---- PM ------------------------------------------------------------------
-    def _sync(self):
-        if self.device.type == "cuda":
-            torch.cuda.synchronize()
-
-    def pm_force(self):
-        e, h, nx = self.e, self.halo, self.nx
-        e.pmslab_deposit(self.n_own)
-        # density halo planes -> add into the neighbours' edge planes (petapm.c:787-790)
-        halo_add(self.comm, self.real, nx, h, self.halo_a, self.halo_b)
-        self._sync()
-        e.pmslab_fft2d(0)
-        slab_transpose_forward(self.comm, self.cplx, self.cplxT, self.sendbuf, self.recvbuf, self._sync)
-        self._sync()
-        e.pmslab_fft1d(0)
-        e.pmslab_transfer()
-        e.pmslab_fft1d(1)
-        slab_transpose_backward(self.comm, self.cplx, self.cplxT, self.sendbuf, self.recvbuf, self._sync)
-        self._sync()
-        e.pmslab_fft2d(1)
-        # potential halo planes <- neighbours' edge planes (petapm.c:848-885)
-        halo_fill(self.comm, self.real, nx, h, self.halo_a, self.halo_b)
-        self._sync()
-        e.pmslab_readout_dev(self.n_own, self.gpm.data_ptr(), None)
-        return self.gpm[:self.n_own]
-
-    # ---- tree ------------------------------------------------------------------
-    def tree_force(self, par):
-        e, d = self.e, self.dom.d
-        info = e.force_tree_build(self.box, toplevel_depth=d)
-        self.tree_info = info
+        self.topdepth = int(topdepth)
         if self.world > 1:
-            e.tree_top_get_dev(d, self.top.data_ptr())
-            self.top[~self.own_cells] = 0.0
-            self._sync()
-            self.comm.all_reduce_sum(self.top)
-            self._sync()
-            e.tree_top_set_dev(d, self.top.data_ptr())
-        e.grav_short_tree_dev(par, self.acc.data_ptr(), self.pot.data_ptr(),
-                              active_ptr=self.targets.data_ptr(), nactive=self.n_own)
-        return self.acc[:self.n_own], self.pot[:self.n_own]
+            if rcut_cells is None:
+                raise ValueError("rcut_cells (TreeRcut) is required: the ghost layer must be validated against the cut-off radius")
+            ids = torch.zeros(256, dtype=torch.uint8, device=self.device)
+            if self.rank == 0:
+                raw = pkg.comm_unique_id() + pkg.comm_unique_id()
+                ids.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+            dist.broadcast(ids, 0)
+            raw = bytes(ids.cpu().numpy().tobytes())
+            engine.comm_init(self.rank, self.world, raw[:128], raw[128:])
+        else:
+            engine.comm_init(0, 1)
+        engine.sharded_init(box, asmth, nmesh, G, topdepth, halo=halo, rcut_cells=float(rcut_cells or 0.0))
+        self.n_own = self.n_tot = 0
+        self._out_n = -1
+        self.info = None
+        self.last_oldacc = None
 
-    def force_step(self, par):
-        gpm = self.pm_force()
-        acc, pot = self.tree_force(par)
-        return gpm, acc, pot
+    def _outputs(self, n):
+        if n != self._out_n:
+            self.gpm = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+            self.acc = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+            self.pot = torch.empty(n, dtype=torch.float64, device=self.device)
+            self._out_n = n
+
+    def force_step(self, pos, mass, oldacc, par):
+        """pos [n,3] f64, mass [n] f32, oldacc [n,3] f64 or None: device tensors of the rank's OWN particles (every x
+        inside the rank's layers), already visible to the engine's stream.  Returns (GravPM, FullTreeGravAccel,
+        Potential) of those particles: tensors owned by this object, overwritten by the next call."""
+        n = int(pos.shape[0])
+        self._outputs(n)
+        info = self.e.sharded_force_step(par, pos.data_ptr(), mass.data_ptr(), oldacc.data_ptr() if oldacc is not None else None, n,
+                                         self.gpm.data_ptr(), self.acc.data_ptr(), self.pot.data_ptr())
+        self.info = info
+        self.last_oldacc = oldacc
+        self.n_own = n
+        self.n_tot = n + int(info.n_from_left) + int(info.n_from_right)
+        return self.gpm, self.acc, self.pot
+
+    def phase_ms(self):
+        return {} if self.info is None else {k: v for k, v in self.info.asdict().items() if k.startswith("ms_")}
+
+    def parity_check(self, pos, mass, acc, gpm, par, nsample=4096, check_pm=None):
+        """The sharded result (acc, gpm of the last force_step on pos, mass) of sampled own particles against ONE engine
+        holding the whole box: every rank gathers all particles, builds the same forced top tree, walks its sample with
+        the old accelerations the sharded step used, and (while the unsharded mesh fits beside this rank's state) runs
+        the unsharded PM.  Returns the errors relative to the mean |acceleration| of the sample."""
+        import importlib
+        pkg = importlib.import_module(__package__)
+        dist, dev = self.dist, self.device
+        n = int(pos.shape[0])
+        counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        counts[self.rank] = n
+        if dist is not None:
+            dist.all_reduce(counts)
+        counts = [int(c) for c in counts.cpu()]
+        ntot = sum(counts)
+        off = sum(counts[:self.rank])
+        allpos = torch.zeros((ntot, 3), dtype=torch.float64, device=dev)
+        allmass = torch.zeros(ntot, dtype=torch.float32, device=dev)
+        allpos[off:off + n] = pos; allmass[off:off + n] = mass
+        if dist is not None:
+            dist.all_reduce(allpos); dist.all_reduce(allmass)
+        old = None
+        if self.last_oldacc is not None:
+            old = torch.zeros((ntot, 3), dtype=torch.float64, device=dev)
+            old[off:off + n] = self.last_oldacc
+        g = torch.Generator(device="cpu"); g.manual_seed(1234 + self.rank)
+        sample = torch.sort(torch.randperm(n, generator=g)[:min(nsample, n)])[0].to(dev)
+        targets = (sample + off).to(torch.int32).contiguous()
+        if check_pm is None:
+            check_pm = self.nmesh <= 1280             # the unsharded mesh + spectrum + cuFFT work area must fit beside this rank's state
+        torch.cuda.synchronize()
+        e2 = pkg.Engine(self.device.index or 0)
+        out = {"nsample": int(sample.shape[0]), "pm_checked": bool(check_pm)}
+        try:
+            e2.set_particles_dev(allpos.data_ptr(), allmass.data_ptr(), ntot, oldacc_ptr=old.data_ptr() if old is not None else None)
+            a2 = torch.zeros((ntot, 3), dtype=torch.float64, device=dev); p2 = torch.zeros(ntot, dtype=torch.float64, device=dev)
+            if check_pm:
+                e2.gravpm_init_periodic(self.box, self.asmth, self.nmesh, self.G)
+                g2 = torch.zeros((ntot, 3), dtype=torch.float64, device=dev)
+                e2.gravpm_force_dev(g2.data_ptr(), None)
+                torch.cuda.synchronize()
+                gref = g2[targets.long()]
+                out["pm_max_err_over_max"] = float((gref - gpm[sample]).abs().max() / g2.abs().max())
+                del g2
+            else:
+                e2.walk_set_mesh(self.box, self.asmth, self.nmesh, self.G)
+                gref = gpm[sample]
+            e2.force_tree_build(self.box, toplevel_depth=self.topdepth)
+            e2.grav_short_tree_dev(par, a2.data_ptr(), p2.data_ptr(), active_ptr=targets.data_ptr(), nactive=int(targets.shape[0]))
+            torch.cuda.synchronize()
+            ref = a2[targets.long()]
+            mean = torch.sqrt(((ref + gref) ** 2).sum(1)).mean()
+            out["acc_max_err_over_mean"] = float((ref - acc[sample]).abs().max() / mean)
+            out["compared"] = "sampled own targets of every rank: sharded step vs one engine holding the whole box (same forced top tree)"
+            out["tolerance"] = 1e-6
+            out["ok"] = bool(out["acc_max_err_over_mean"] < 1e-6 and out.get("pm_max_err_over_max", 0.0) < 1e-6)
+        finally:
+            e2.close()
+        return out
 
 
 class ShardedSPH:
@@ -370,7 +389,7 @@ class ShardedSPH:
         hmax = torch.tensor([float(full["hsml"][:n].max()) if n else 0.0], dtype=torch.float64, device=self.device)
         if self.world > 1:
             self.comm.dist.all_reduce(hmax, op=self.comm.dist.ReduceOp.MAX)
-        if self.world > 1 and not self.dom.cellwidth > float(hmax.item()):
+        if self.world > 1 and not self.dom.seamwidth > float(hmax.item()):
             raise ValueError("top-tree cells (%.4g) must be wider than the largest smoothing length (%.4g): lower topdepth"
                              % (self.dom.cellwidth, float(hmax.item())))
         self.e.sph_set_state(density=full["density"], egywtdensity=full["egywtdensity"], dhsmlfac=full["dhsmlfac"],

@@ -1,6 +1,7 @@
 """Multi-GPU host logic.  CPU: world_size-2 gloo processes exercise the domain
-cut, ghost import, halo-plane exchange and the slab-FFT transposes against
-single-process numpy.  GPU: the sharded driver with world size 1 against the
+cut, ghost import, halo-plane exchange and the slab-FFT transposes (the message
+pattern csrc/sharded.cu issues over NCCL, stated in torch) against
+single-process numpy.  GPU: b200_sharded_force_step with world size 1 against the
 unsharded engine path, and (when >= 2 GPUs are visible) 2 ranks under torchrun."""
 import importlib
 import os
@@ -125,10 +126,12 @@ def test_sharded_world1_equals_unsharded(b200, ics):
     a0, p0, _ = e0.grav_short_tree(par)
     e0.close()
     e1 = b200.Engine(0)
-    s = sh.ShardedTreePM(e1, box, nmesh, 1.5, G, topdepth=2, dist=None)
-    s.load(torch.from_numpy(pos).cuda(), torch.from_numpy(mass).cuda(), rcut_cells=par["Rcut"])
-    g1, a1, p1 = s.force_step(par)
+    s = sh.ShardedTreePM(e1, box, nmesh, 1.5, G, topdepth=2, dist=None, rcut_cells=par["Rcut"])
+    tp, tm = torch.from_numpy(pos).cuda(), torch.from_numpy(mass).cuda()
+    torch.cuda.synchronize()
+    g1, a1, p1 = s.force_step(tp, tm, None, par)
     g1, a1, p1 = g1.cpu().numpy(), a1.cpu().numpy(), p1.cpu().numpy()
+    assert s.n_tot == s.n_own == n
     e1.close()
     assert np.abs(g1 - g0).max() <= 1e-10 * np.abs(g0).max()
     assert np.abs(a1 - a0).max() <= 1e-12 * np.sqrt((a0 ** 2).sum(1)).mean()
@@ -148,11 +151,19 @@ G = 43.0071
 pos, mass = ics.zeldovich_lattice(32, 32.0, seed=3); box, nmesh = 32.0, 96
 par = ics.tree_params(box, len(mass), treeusebh=1)
 e = pkg.Engine(local)
-s = sh.ShardedTreePM(e, box, nmesh, 1.5, G, topdepth=3, dist=dist, device="cuda:%%d" %% local)
+s = sh.ShardedTreePM(e, box, nmesh, 1.5, G, topdepth=3, dist=dist, device="cuda:%%d" %% local, rcut_cells=par["Rcut"])
 tp = torch.from_numpy(pos).cuda(); tm = torch.from_numpy(mass).cuda()
 sel = s.dom.owner_of(tp[:, 0]) == rank
-nghost = s.load(tp[sel].contiguous(), tm[sel].contiguous(), rcut_cells=par["Rcut"])
-g, a, p = s.force_step(par)
+op, om = tp[sel].contiguous(), tm[sel].contiguous()
+torch.cuda.synchronize()
+g, a, p = s.force_step(op, om, None, par)
+nghost = s.n_tot - s.n_own
+par2 = dict(par); par2["TreeUseBH"] = 0
+old = (a + g).clone()
+g, a, p = s.force_step(op, om, old, par2)          # second pass: relative criterion fed by the first
+chk = s.parity_check(op, om, a, g, par2, nsample=2000)
+assert chk["ok"] and chk["pm_checked"], chk
+g, a, p = s.force_step(op, om, None, par)
 idx = torch.nonzero(sel)[:, 0].cpu().numpy()
 np.savez(os.path.join(%(out)r, "shard_%%d.npz" %% rank), idx=idx, g=g.cpu().numpy(), a=a.cpu().numpy(), p=p.cpu().numpy(), nghost=nghost)
 dist.barrier(); dist.destroy_process_group()
