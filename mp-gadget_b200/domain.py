@@ -3,7 +3,10 @@ domain_determine_global_toptree (libgadget/domain.c:1281-1340) and domain_balanc
 C-ABI stages (b200_domain_sample_keys on the device, b200_domain_toptree_* / b200_domain_assign_balanced on the host).
 The exchanges are the reference's own -- two all-reduces, the pairwise tree merge of
 domain_nonrecursively_combine_topTree (domain.c:1190-1278), one broadcast -- carried by torch.distributed (gloo on CPU
-tests, NCCL on GPUs; the messages are a few kilobytes).  The particle exchange itself (exchange.c) is not built."""
+tests, NCCL on GPUs; the messages are a few kilobytes).  exchange() / decompose() / maintain() below restate
+domain_exchange_once, domain_decompose_full (first policy) and domain_maintain for particle state held in torch tensors.
+One departure from the reference: maintain() moves every particle whose top leaf changed task at once, where
+domain.c:315-317 leaves gravitationally inactive dark matter in place until its next active step."""
 import numpy as np
 import torch
 
@@ -14,24 +17,40 @@ def _as_tensor(a):
     return torch.from_numpy(a.view(np.uint8).reshape(-1))
 
 
+class TopTreeOverflow(B200Error):
+    """The top tree ran out of nodes at some stage on some rank.  Raised on EVERY rank (the error flags are reduced, as the
+    reference does with MPIU_Any, domain.c:1266-1272,1292,1334), so the caller can retry collectively with more nodes."""
+
+
+def _any(flag, dist):
+    """MPIU_Any: true on every rank when `flag` is set on one."""
+    if dist is None:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int64)
+    dist.all_reduce(t)
+    return int(t) > 0
+
+
 def global_toptree(sample_keys, ntopleaves, dist=None, maxnodes=None):
     """sample_keys: this rank's subsample keys (Engine.sample_keys).  -> (TopTree, leaf number per node, nleaf), identical on
-    every rank.  ntopleaves = policy->NTopLeaves (DomainOverDecompositionFactor * NTask * (attempt + 1), domain.c:369-371)."""
+    every rank.  ntopleaves = policy->NTopLeaves (DomainOverDecompositionFactor * NTask * (attempt + 1), domain.c:369-371).
+    A failure of any stage on any rank raises TopTreeOverflow on every rank: no rank is left waiting in a collective."""
     rank = dist.get_rank() if dist is not None else 0
     world = dist.get_world_size() if dist is not None else 1
     if maxnodes is None:
         maxnodes = 8 * max(len(sample_keys), 1) * world + 64 * ntopleaves
     T = TopTree(maxnodes)
-    rc = T.local(sample_keys)
-    if rc:
-        raise B200Error("top tree: local refinement failed (%d)" % rc)
-    tot = torch.tensor([int(T.tree["Count"][0]), int(T.tree["Cost"][0])], dtype=torch.int64)
+    err = bool(T.local(sample_keys))                                                     # domain.c:1286-1296
+    tot = torch.tensor([0 if err else int(T.tree["Count"][0]), 0 if err else int(T.tree["Cost"][0]), 1 if err else 0], dtype=torch.int64)
     if dist is not None:
         dist.all_reduce(tot)
+    if int(tot[2]) > 0:
+        raise TopTreeOverflow("top tree: local refinement failed on %d rank(s)" % int(tot[2]))
     countlimit, costlimit = int(tot[0]) // ntopleaves, int(tot[1]) // ntopleaves          # :1301-1302
     T.truncate(countlimit, costlimit)
     # domain_nonrecursively_combine_topTree: at separation sep the leaders of odd groups hand their tree to the leader of
-    # the even group on their left and drop out, until rank 0 holds the merge of all
+    # the even group on their left and drop out, until rank 0 holds the merge of all.  A rank whose merge fails keeps
+    # taking part (its partners are already in their send / recv); the flag is reduced after the loop (:1266-1272).
     alive = True
     sep = 1
     while sep < world:
@@ -44,21 +63,25 @@ def global_toptree(sample_keys, ntopleaves, dist=None, maxnodes=None):
                     other = TopTree(max(int(n), T.size.value, 1))
                     dist.recv(_as_tensor(other.nodes)[: int(n) * TOPNODE_DTYPE.itemsize], src=src)
                     other.size.value = int(n)
-                    if T.size.value + int(n) > maxnodes or (int(n) > 0 and T.merge(other)):
-                        raise B200Error("top tree: out of nodes while merging")
+                    if not err and (T.size.value + int(n) > maxnodes or (int(n) > 0 and T.merge(other))):
+                        err = True
             else:
                 dist.send(torch.tensor([T.size.value], dtype=torch.int64), dst=rank - sep)
                 dist.send(_as_tensor(T.nodes)[: T.size.value * TOPNODE_DTYPE.itemsize].clone(), dst=rank - sep)
                 alive = False
         sep *= 2
+    if _any(err, dist):
+        raise TopTreeOverflow("top tree: out of nodes while merging")
     if dist is not None and world > 1:
         n = torch.tensor([T.size.value if rank == 0 else 0], dtype=torch.int64)
         dist.broadcast(n, src=0)
+        if int(n) < 0 or int(n) >= maxnodes:                                              # :1318-1321, the same value on every rank
+            raise TopTreeOverflow("top tree: merged size %d does not fit %d nodes" % (int(n), maxnodes))
         T.size.value = int(n)
         buf = _as_tensor(T.nodes)[: int(n) * TOPNODE_DTYPE.itemsize]
         dist.broadcast(buf, src=0)
-    if T.global_refine(countlimit, costlimit):
-        raise B200Error("top tree: out of nodes in the global refinement")
+    if _any(bool(T.global_refine(countlimit, costlimit)), dist):                          # :1334
+        raise TopTreeOverflow("top tree: out of nodes in the global refinement")
     nleaf, leaf = T.leaves()
     return T, leaf, nleaf
 
@@ -145,8 +168,16 @@ def decompose(engine, box, dist=None, overdecomposition=4, subsample=256, attemp
     leaving (indices), target (task per leaving particle), togo, ngarbage)."""
     world = dist.get_world_size() if dist is not None else 1
     rank = dist.get_rank() if dist is not None else 0
-    ntopleaves = overdecomposition * world * (attempt + 1)                 # domain_policies_init, domain.c:369-371
-    T, leaf, nleaf = global_toptree(engine.sample_keys(box, subsample), ntopleaves, dist)
+    keys = engine.sample_keys(box, subsample)
+    while True:                 # the retry loop of domain_decompose_full over its policies (domain.c:170-200): every rank
+        try:                    # sees the same TopTreeOverflow, so every rank moves on to the next policy together
+            ntopleaves = overdecomposition * world * (attempt + 1)         # domain_policies_init, domain.c:369-371
+            T, leaf, nleaf = global_toptree(keys, ntopleaves, dist)
+            break
+        except TopTreeOverflow:
+            attempt += 1
+            if attempt >= 8:
+                raise
     top = topnode_arrays(T, leaf)
     engine.peano_keys(box)
     topleaf = engine.topleaf(*top)

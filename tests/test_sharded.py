@@ -326,6 +326,21 @@ for k, case in enumerate(DS.TOPTREE_CASES):
     assert counts.sum() >= sum(case["n"]) and np.array_equal(task, oracle.domain_assign_balanced(world, counts))
     load = np.bincount(task, weights=counts, minlength=world)
     assert set(task) == set(range(world)) and load.max() <= 1.6 * load.mean(), load
+# a node budget only the LAST rank's merge exceeds: the failure must reach every rank (MPIU_Any, domain.c:1266-1272)
+# instead of leaving the others in the next collective
+case = DS.TOPTREE_CASES[0]
+pos = DS.clustered(case["n"][min(rank, 1)], case["box"], 7 + rank)
+keys = oracle.peano_keys(pos[::4], case["box"])
+for maxnodes in (40, 200):
+    try:
+        dom.global_toptree(keys, case["ntopleaves"], dist, maxnodes=maxnodes)
+        raised = 0
+    except dom.TopTreeOverflow:
+        raised = 1
+    t = torch.tensor([raised], dtype=torch.int64); lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert int(lo) == int(hi), "ranks disagree about the failure"
+assert raised == 1 or maxnodes > 40
 print("ok", flush=True)
 dist.destroy_process_group()
 '''
