@@ -132,7 +132,7 @@ struct Engine {
     DevBuf<double> s_out3, s_out1a, s_out1b;
     DevBuf<int> s_outi, s_outi2, s_niter, s_nint;
     DevBuf<double> s_left, s_right;       // smoothing-length brackets of the density iteration
-    DevBuf<double> s_hD;                  // curve order: dloga of the particle's hydro bin
+    DevBuf<double> s_hD;                  // curve order: two more double4 rows per particle (hC, hT of k_sph_gather_hydro)
     DevBuf<double> s_bins;                // [5][B200_TIMEBINS + 1] per-bin factors
     DevBuf<uint8_t> s_bin_grav, s_bin_hydro, s_active;
     DevBuf<int> sph_list_a, sph_list_b;   // target lists of the density passes

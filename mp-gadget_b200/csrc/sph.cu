@@ -321,6 +321,9 @@ k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restri
     PieceList L;
     L.pool = pool; L.ctab = s_ctab; L.empty = PIECE(sentinel, 0);
     const int g = lane >> 3, slot = lane & 7;
+    const unsigned ltmask = (1u << lane) - 1u;
+    __shared__ int s_q_all[WALK_WARPS][64];
+    int *s_q = s_q_all[threadIdx.x >> 5];
     double acc[NSUM_DENS];
 #pragma unroll
     for(int q = 0; q < NSUM_DENS; q++) acc[q] = 0;
@@ -343,44 +346,68 @@ k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restri
         // candidate of its kept leaves is its own nearest image (the reach bounds their distance).
         const double tr = __shfl_sync(0xffffffffu, myreach, t);
         const bool central = tx >= tr && tx + tr <= S.box && ty >= tr && ty + tr <= S.box && tz >= tr && tz + tr <= S.box;
-        Ent4 eN = fetch_ent(L, 0, g);
-        for(int base = 0; base < ntp; base += 16) {
-            const Ent4 eC = eN;
-            eN = fetch_ent(L, base + 16, g);
-#pragma unroll
-            for(int kk = 0; kk < 4; kk++) {
-                const unsigned e = eC.e[kk];
-                if(slot >= (int) (e & 15u)) continue;
+        // Candidates are screened 32 at a time (r^2 <= h^2, treewalk.c:1223-1233); the neighbours (about 1/4 of them) are
+        // queued in shared memory and density_ngbiter runs on full warps, in the same loop body.
+        int qn = 0;
+        Ent4 eC = fetch_ent(L, 0, g), eN = fetch_ent(L, 16, g);
+#pragma unroll 1
+        for(int it = 0;; it++) {
+            const int base = (it >> 2) << 4, kk = it & 3;
+            const bool more = base < ntp;               // warp-uniform
+            if(!more && qn == 0) break;
+            if(more) {
+                const unsigned e = kk == 0 ? eC.e[0] : (kk == 1 ? eC.e[1] : (kk == 2 ? eC.e[2] : eC.e[3]));
                 const int o = (int) (e >> 4) + slot;
-                const double2 qa = spart_xy[o], qb = spart_zm[o];       // whole sectors per 8-lane group
-                // treewalk.c:1223-1233
-                double d0 = tx - qa.x, d1 = ty - qa.y, d2 = tz - qb.x;
-                if(!central) { d0 = nearest_s(d0, S.box, S.halfbox); d1 = nearest_s(d1, S.box, S.halfbox); d2 = nearest_s(d2, S.box, S.halfbox); }
-                double r2 = d0 * d0; r2 += d1 * d1; r2 += d2 * d2;
-                if(r2 > h2) continue;
-                ni++;
-                if(r2 < k.HH) {                       // density_ngbiter density.c:451-518
-                    const double r = sqrt(r2);
-                    const double u = r * k.Hinv;
-                    const double wk = kern_w(k, u, S);
-                    s[0] += wk * vol;
-                    const double dwk = kern_dw(k, u, S);
-                    const double mj = qb.y;
-                    s[1] += mj * wk;
-                    const double dW = -(3 * k.Hinv * wk + u * dwk);
-                    s[2] += mj * dW;
-                    const double4 vo = svel[o];
-                    if(DoEgy) { s[3] += mj * vo.w * wk; s[4] += mj * vo.w * dW; }
-                    if(r > 0) {
-                        const double fac = mj * dwk / r;
-                        const double v0 = tvx - vo.x, v1 = tvy - vo.y, v2 = tvz - vo.z;
-                        s[5] += -fac * (d0 * v0 + d1 * v1 + d2 * v2);
-                        s[6] += fac * (v1 * d2 - d1 * v2);
-                        s[7] += fac * (v2 * d0 - d2 * v0);
-                        s[8] += fac * (v0 * d1 - d0 * v1);
-                        s[9] += fac * d0; s[10] += fac * d1; s[11] += fac * d2;         // density.c:512-515
+                bool pass = false;
+                if(slot < (int) (e & 15u)) {
+                    const double2 qa = spart_xy[o], qb = spart_zm[o];       // whole sectors per 8-lane group
+                    double d0 = tx - qa.x, d1 = ty - qa.y, d2 = tz - qb.x;
+                    if(!central) { d0 = nearest_s(d0, S.box, S.halfbox); d1 = nearest_s(d1, S.box, S.halfbox); d2 = nearest_s(d2, S.box, S.halfbox); }
+                    double r2 = d0 * d0; r2 += d1 * d1; r2 += d2 * d2;
+                    pass = !(r2 > h2);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if(pass) s_q[qn + __popc(bal & ltmask)] = o;
+                qn += __popc(bal);
+                ni += pass ? 1 : 0;
+                if(kk == 3) { eC = eN; eN = fetch_ent(L, base + 32, g); }
+                __syncwarp();
+            }
+            if(qn >= 32 || (!more && qn > 0)) {
+                if(lane < qn) {
+                    const int o = s_q[lane];
+                    const double2 qa = spart_xy[o], qb = spart_zm[o];
+                    double d0 = tx - qa.x, d1 = ty - qa.y, d2 = tz - qb.x;
+                    if(!central) { d0 = nearest_s(d0, S.box, S.halfbox); d1 = nearest_s(d1, S.box, S.halfbox); d2 = nearest_s(d2, S.box, S.halfbox); }
+                    double r2 = d0 * d0; r2 += d1 * d1; r2 += d2 * d2;
+                    if(r2 < k.HH) {                       // density_ngbiter density.c:451-518
+                        const double r = sqrt(r2);
+                        const double u = r * k.Hinv;
+                        const double wk = kern_w(k, u, S);
+                        s[0] += wk * vol;
+                        const double dwk = kern_dw(k, u, S);
+                        const double mj = qb.y;
+                        s[1] += mj * wk;
+                        const double dW = -(3 * k.Hinv * wk + u * dwk);
+                        s[2] += mj * dW;
+                        const double4 vo = svel[o];
+                        if(DoEgy) { s[3] += mj * vo.w * wk; s[4] += mj * vo.w * dW; }
+                        if(r > 0) {
+                            const double fac = mj * dwk / r;
+                            const double v0 = tvx - vo.x, v1 = tvy - vo.y, v2 = tvz - vo.z;
+                            s[5] += -fac * (d0 * v0 + d1 * v1 + d2 * v2);
+                            s[6] += fac * (v1 * d2 - d1 * v2);
+                            s[7] += fac * (v2 * d0 - d2 * v0);
+                            s[8] += fac * (v0 * d1 - d0 * v1);
+                            s[9] += fac * d0; s[10] += fac * d1; s[11] += fac * d2;         // density.c:512-515
+                        }
                     }
                 }
+                const int mv = lane + 32 < qn ? s_q[32 + lane] : 0;
+                __syncwarp();
+                if(lane + 32 < qn) s_q[lane] = mv;
+                qn = qn > 32 ? qn - 32 : 0;
+                __syncwarp();
             }
         }
 #pragma unroll
@@ -503,20 +530,24 @@ k_sph_hmax_up(int first, int last, const int *__restrict__ b_firstchild, const i
     nodeH[b_dfs[b]] = hm;
 }
 
-// per-particle hydro inputs in curve order
+// Per-particle hydro inputs in curve order.  Everything hydro_ngbiter (hydra.c:350-505) derives from the OTHER particle
+// alone -- kernel normalisation of h_j, P_j / rho_j^2, sound speed, Balsara factor, the density-contrast ratio -- is formed
+// here once per particle with the reference's own expressions instead of once per pair (11 of the 14 divisions and 2 of
+// the 3 square roots of a pair).
+//   hA = {h, 1/h, dWknorm(h), predicted density}      hB = {P/eom^2, c_s, f2 (Balsara), rr2}
+//   hC = {DhsmlEgyDensityFactor, dloga of the hydro bin, 1/EntVarPred, eom}     (eom = predicted EgyWtDensity or density)
 __global__ void __launch_bounds__(256)
 k_sph_gather_hydro(int np, const int *__restrict__ sidx, SphDev S, const double *__restrict__ hsml, const double *__restrict__ density,
                    const double *__restrict__ egy, const double *__restrict__ dhsmlfac, const double *__restrict__ divvel,
                    const double *__restrict__ curlvel, const double4 *__restrict__ svel,
-                   double4 *__restrict__ hA, double4 *__restrict__ hB, double *__restrict__ hD)
+                   double4 *__restrict__ hA, double4 *__restrict__ hB, double4 *__restrict__ hC, double4 *__restrict__ hT)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if(j >= np) return;
     const int64_t i = sidx[j];
     const int DI = S.p.DensityIndependentSphOn;
-    const double dens = density[i], dvv = divvel[i];
+    const double dens = density[i], dvv = divvel[i], h = hsml[i], curl = curlvel[i];
     const double drift = S.bins[3 * NB + S.bh[i]];
-    hD[j] = S.bins[4 * NB + S.bh[i]];
     // SPH_DensityPred hydra.c:300-312
     double dj = dens - dvv * dens * drift; if(!(dj >= 1e-6 * dens)) dj = 1e-6 * dens;
     const double eom0 = DI ? egy[i] : dens;
@@ -524,18 +555,36 @@ k_sph_gather_hydro(int np, const int *__restrict__ sidx, SphDev S, const double 
     const double ev = svel[j].w;
     double P = 0;                                   // PressurePred hydra.c:67-77, cache hydra.c:195-214
     if(ev != 0 && ev * eom > 0) P = exp(GAMMA * log(ev * eom));
-    hA[j] = make_double4(hsml[i], dj, eom, P);
-    hB[j] = make_double4(dvv, curlvel[i], dhsmlfac[i], eom0);
+    Kern k; kern_init(k, h, S);
+    const double cs = sqrt(GAMMA * P / eom);                                           // hydra.c:388
+    const double f2 = fabs(dvv) / (fabs(dvv) + curl + 0.0001 * cs / S.fac_mu / h);     // hydra.c:444-445
+    double rr2 = 1;                                                                   // hydra.c:486-497
+    if(DI) {
+        rr2 = 0;
+        if(S.p.DensityContrastLimit >= 0) {
+            rr2 = eom / dj;
+            if(S.p.DensityContrastLimit > 0 && S.p.DensityContrastLimit < rr2) rr2 = S.p.DensityContrastLimit;
+        }
+    }
+    hA[j] = make_double4(h, k.Hinv, k.dWknorm, dj);
+    hB[j] = make_double4(P / (eom * eom), cs, f2, rr2);
+    hC[j] = make_double4(dhsmlfac[i], S.bins[4 * NB + S.bh[i]], 1.0 / ev, eom);
+    // the same particle as a TARGET (hydro_copy hydra.c:247-277 uses the un-predicted density of the slot): {P, eom0, divv, curl}
+    hT[j] = make_double4(P, eom0, dvv, curl);
 }
 
 // hydro_ngbiter (hydra.c:318-506) over the piece lists of the symmetric search, then
 // hydro_postprocess (hydra.c:514-528).  Candidates = particles of the kept leaves
 // (treewalk.c:962-999 filters them by r^2 <= max(h_i, h_j)^2).
-__global__ void __launch_bounds__(128, 3)
+// Candidates are screened 32 at a time; the survivors (about 1/4 of the particles of the opened leaves) are queued
+// in shared memory and evaluated 32 at a time, so the long pair arithmetic runs on full warps.  Screening and
+// evaluation share ONE loop body (a second inlined copy of the pair arithmetic doubled the kernel and made it
+// instruction-fetch bound: ncu "no instruction" stalls, profiles/r01_sph_hydro_pairs_ncu_summary.txt).
+__global__ void __launch_bounds__(128, 4)
 k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict__ sidx,
                   const double4 *__restrict__ spart, const double2 *__restrict__ spart_xy, const double2 *__restrict__ spart_zm,
                   const double *__restrict__ reach, const double4 *__restrict__ svel,
-                  const double4 *__restrict__ hA, const double4 *__restrict__ hB, const double *__restrict__ hD,
+                  const double4 *__restrict__ hA, const double4 *__restrict__ hB, const double4 *__restrict__ hC, const double4 *__restrict__ hT,
                   const double *__restrict__ density, SphDev S,
                   const unsigned *__restrict__ pool, const int *__restrict__ chunk_tab, int maxch, const int *__restrict__ piece_cnt,
                   double *__restrict__ acc_out, double *__restrict__ dte_out, double *__restrict__ maxsig_out, int *__restrict__ ninteract)
@@ -570,88 +619,39 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
         if(ntp == 0) continue;                          // warp-uniform
         // the target's rows: one broadcast load each
         const int jt = __shfl_sync(0xffffffffu, myj, t), met = __shfl_sync(0xffffffffu, me, t);
-        const double4 pm = spart[jt], vm = svel[jt], a_i = hA[jt], b_i = hB[jt];
+        const double4 pm = spart[jt], vm = svel[jt], a_i = hA[jt], c_i = hC[jt], t_i = hT[jt];
         // no periodic wrap for a target farther than its search reach from every face (see k_sph_density_pairs)
         const double tr = __shfl_sync(0xffffffffu, myreach, t);
         const bool wrap = !(pm.x >= tr && pm.x + tr <= S.box && pm.y >= tr && pm.y + tr <= S.box && pm.z >= tr && pm.z + tr <= S.box);
-        const double h_i = a_i.x, P_i = a_i.w, eom_i = b_i.w, dens_i = density[met], dloga_i = hD[jt];
+        const double h_i = a_i.x, P_i = t_i.x, eom_i = t_i.y, dens_i = density[met], dloga_i = c_i.y;
         // hydro_copy hydra.c:247-277
         const double cs_i = sqrt(GAMMA * P_i / eom_i);
-        const double F1 = fabs(b_i.x) / (fabs(b_i.x) + b_i.y + 0.0001 * cs_i / h_i / S.fac_mu);
+        const double F1 = fabs(t_i.z) / (fabs(t_i.z) + t_i.w + 0.0001 * cs_i / h_i / S.fac_mu);
         const double p_over_rho2_i = P_i / (eom_i * eom_i);
+        const double inv_evp_i = 1.0 / vm.w;
+        double rr1 = 1;
+        if(DI) {
+            rr1 = 0;
+            if(S.p.DensityContrastLimit >= 0) {
+                rr1 = eom_i / dens_i;
+                if(S.p.DensityContrastLimit > 0 && S.p.DensityContrastLimit < rr1) rr1 = S.p.DensityContrastLimit;
+            }
+        }
+        const double pd_i = p_over_rho2_i * c_i.x * rr1;         // hydra.c:499-500, target side
         Kern ki; kern_init(ki, h_i, S);
         double A0 = 0, A1 = 0, A2 = 0, DtE = 0, MaxSig = cs_i;
         int ncand = 0;
         L.t = t; L.nt = ntp;
-        // hydro_ngbiter (hydra.c:350-505) for one neighbour that passed r^2 <= max(h_i, h_j)^2
-        auto heavy = [&](int o) {
-            const double2 qa = spart_xy[o], qb = spart_zm[o];
-            const double4 q = make_double4(qa.x, qa.y, qb.x, qb.y), a_j = hA[o];
-            double d0 = pm.x - q.x, d1 = pm.y - q.y, d2 = pm.z - q.z;
-            if(wrap) { d0 = nearest_s(d0, S.box, S.halfbox); d1 = nearest_s(d1, S.box, S.halfbox); d2 = nearest_s(d2, S.box, S.halfbox); }
-            double rsq = d0 * d0; rsq += d1 * d1; rsq += d2 * d2;
-            Kern kj; kern_init(kj, a_j.x, S);
-            if(rsq <= 0 || !(rsq < ki.HH || rsq < kj.HH)) return;
-            const double r = sqrt(rsq);
-            const double4 vo = svel[o], b_j = hB[o];
-            const double density_j = a_j.y, eom_j = a_j.z, P_j = a_j.w;
-            const double p_over_rho2_j = P_j / (eom_j * eom_j);
-            const double cs_j = sqrt(GAMMA * P_j / eom_j);
-            double vsig = cs_i + cs_j;
-            if(vsig > MaxSig) MaxSig = vsig;
-            const double v0 = vm.x - vo.x, v1 = vm.y - vo.y, v2 = vm.z - vo.z;
-            const double vdotr = d0 * v0 + d1 * v1 + d2 * v2;
-            const double vdotr2 = vdotr + S.hubble_a2 * rsq;
-            const double dwk_i = kern_dw(ki, r * ki.Hinv, S);
-            const double dwk_j = kern_dw(kj, r * kj.Hinv, S);
-            double visc = 0;
-            if(vdotr2 < 0) {
-                const double mu_ij = S.fac_mu * vdotr2 / r;
-                const double rho_ij = 0.5 * (dens_i + density_j);
-                double vs = cs_i + cs_j;
-                vs -= 3 * mu_ij;
-                if(vs > MaxSig) MaxSig = vs;
-                const double f2 = fabs(b_j.x) / (fabs(b_j.x) + b_j.y + 0.0001 * cs_j / S.fac_mu / a_j.x);
-                visc = 0.25 * S.p.ArtBulkViscConst * vs * (-mu_ij) / rho_ij * (F1 + f2);
-                const double dlj = hD[o];
-                const double dloga = 2 * (dloga_i > dlj ? dloga_i : dlj);          // hydra.c:463
-                if(dloga > 0 && (dwk_i + dwk_j) < 0) {
-                    const double msum = pm.w + q.w;
-                    if(msum > 0) {
-                        const double lim = 0.5 * S.fac_vsic_fix * vdotr2 / (0.5 * msum * (dwk_i + dwk_j) * r * dloga);
-                        if(lim < visc) visc = lim;
-                    }
-                }
-            }
-            const double hfc_visc = 0.5 * q.w * visc * (dwk_i + dwk_j) / r;
-            double hfc = hfc_visc, rr1 = 1, rr2 = 1;
-            if(DI) {
-                rr1 = 0; rr2 = 0;
-                hfc += q.w * (dwk_i * p_over_rho2_i * vo.w / vm.w + dwk_j * p_over_rho2_j * vm.w / vo.w) / r;
-                if(S.p.DensityContrastLimit >= 0) {
-                    rr1 = eom_i / dens_i;
-                    rr2 = eom_j / density_j;
-                    if(S.p.DensityContrastLimit > 0) {
-                        if(S.p.DensityContrastLimit < rr1) rr1 = S.p.DensityContrastLimit;
-                        if(S.p.DensityContrastLimit < rr2) rr2 = S.p.DensityContrastLimit;
-                    }
-                }
-            }
-            hfc += q.w * (p_over_rho2_i * b_i.z * dwk_i * rr1 + p_over_rho2_j * b_j.z * dwk_j * rr2) / r;
-            A0 += (-hfc * d0); A1 += (-hfc * d1); A2 += (-hfc * d2);
-            DtE += (0.5 * hfc_visc * vdotr2);
-        };
-        // Candidates are screened 32 at a time (treewalk.c:962-999); the survivors (about 1/4 of the
-        // particles of the opened leaves) are queued in shared memory and evaluated 32 at a time,
-        // so the long pair arithmetic runs on full warps.
         int qn = 0;
-        Ent4 eN = fetch_ent(L, 0, g);
-        for(int base = 0; base < ntp; base += 16) {
-            const Ent4 eC = eN;
-            eN = fetch_ent(L, base + 16, g);
-#pragma unroll
-            for(int kk = 0; kk < 4; kk++) {
-                const unsigned e = eC.e[kk];
+        Ent4 eC = fetch_ent(L, 0, g), eN = fetch_ent(L, 16, g);
+#pragma unroll 1
+        for(int it = 0;; it++) {
+            const int base = (it >> 2) << 4, kk = it & 3;
+            const bool more = base < ntp;               // warp-uniform
+            if(!more && qn == 0) break;
+            if(more) {
+                // ---- screening of one entry per 8-lane group (treewalk.c:962-999)
+                const unsigned e = kk == 0 ? eC.e[0] : (kk == 1 ? eC.e[1] : (kk == 2 ? eC.e[2] : eC.e[3]));
                 if(slot == 0) ncand += (int) (e & 15u);
                 const int o = (int) (e >> 4) + slot;
                 bool pass = false;
@@ -667,19 +667,62 @@ k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict
                 const unsigned bal = __ballot_sync(0xffffffffu, pass);
                 if(pass) s_q[qn + __popc(bal & ltmask)] = o;
                 qn += __popc(bal);
+                if(kk == 3) { eC = eN; eN = fetch_ent(L, base + 32, g); }
                 __syncwarp();
-                if(qn >= 32) {
-                    heavy(s_q[lane]);
-                    const int mv = lane < qn - 32 ? s_q[32 + lane] : 0;
-                    __syncwarp();
-                    if(lane < qn - 32) s_q[lane] = mv;
-                    qn -= 32;
-                    __syncwarp();
+            }
+            if(qn >= 32 || (!more && qn > 0)) {
+                // ---- hydro_ngbiter (hydra.c:350-505) for up to 32 queued neighbours, one per lane
+                if(lane < qn) {
+                    const int o = s_q[lane];
+                    const double2 qa = spart_xy[o], qb = spart_zm[o];
+                    const double4 a_j = hA[o];
+                    double d0 = pm.x - qa.x, d1 = pm.y - qa.y, d2 = pm.z - qb.x;
+                    if(wrap) { d0 = nearest_s(d0, S.box, S.halfbox); d1 = nearest_s(d1, S.box, S.halfbox); d2 = nearest_s(d2, S.box, S.halfbox); }
+                    double rsq = d0 * d0; rsq += d1 * d1; rsq += d2 * d2;
+                    if(rsq > 0 && (rsq < ki.HH || rsq < a_j.x * a_j.x)) {
+                        const double r = sqrt(rsq), rinv = 1.0 / r, mj = qb.y;
+                        const double4 vo = svel[o], b_j = hB[o], c_j = hC[o];
+                        const double density_j = a_j.w, p_over_rho2_j = b_j.x, cs_j = b_j.y;
+                        Kern kj; kj.H = a_j.x; kj.HH = 0; kj.Hinv = a_j.y; kj.Wknorm = 0; kj.dWknorm = a_j.z;
+                        const double vsig = cs_i + cs_j;
+                        if(vsig > MaxSig) MaxSig = vsig;
+                        const double v0 = vm.x - vo.x, v1 = vm.y - vo.y, v2 = vm.z - vo.z;
+                        const double vdotr = d0 * v0 + d1 * v1 + d2 * v2;
+                        const double vdotr2 = vdotr + S.hubble_a2 * rsq;
+                        const double dwk_i = kern_dw(ki, r * ki.Hinv, S);
+                        const double dwk_j = kern_dw(kj, r * kj.Hinv, S);
+                        double visc = 0;
+                        if(vdotr2 < 0) {
+                            const double mu_ij = S.fac_mu * vdotr2 * rinv;
+                            const double rho_ij = 0.5 * (dens_i + density_j);
+                            double vs = cs_i + cs_j;
+                            vs -= 3 * mu_ij;
+                            if(vs > MaxSig) MaxSig = vs;
+                            visc = 0.25 * S.p.ArtBulkViscConst * vs * (-mu_ij) / rho_ij * (F1 + b_j.z);
+                            const double dloga = 2 * (dloga_i > c_j.y ? dloga_i : c_j.y);          // hydra.c:463
+                            if(dloga > 0 && (dwk_i + dwk_j) < 0) {
+                                const double msum = pm.w + mj;
+                                if(msum > 0) {
+                                    const double lim = 0.5 * S.fac_vsic_fix * vdotr2 / (0.5 * msum * (dwk_i + dwk_j) * r * dloga);
+                                    if(lim < visc) visc = lim;
+                                }
+                            }
+                        }
+                        const double hfc_visc = 0.5 * mj * visc * (dwk_i + dwk_j) * rinv;
+                        double hfc = hfc_visc;
+                        if(DI) hfc += mj * (dwk_i * p_over_rho2_i * (vo.w * inv_evp_i) + dwk_j * p_over_rho2_j * (vm.w * c_j.z)) * rinv;
+                        hfc += mj * (pd_i * dwk_i + p_over_rho2_j * c_j.x * dwk_j * b_j.w) * rinv;
+                        A0 += (-hfc * d0); A1 += (-hfc * d1); A2 += (-hfc * d2);
+                        DtE += (0.5 * hfc_visc * vdotr2);
+                    }
                 }
+                const int mv = lane + 32 < qn ? s_q[32 + lane] : 0;
+                __syncwarp();
+                if(lane + 32 < qn) s_q[lane] = mv;
+                qn = qn > 32 ? qn - 32 : 0;
+                __syncwarp();
             }
         }
-        if(lane < qn) heavy(s_q[lane]);
-        __syncwarp();
         A0 = warp_sum(A0); A1 = warp_sum(A1); A2 = warp_sum(A2); DtE = warp_sum(DtE); MaxSig = warp_max(MaxSig);
         ncand = (int) __reduce_add_sync(0xffffffffu, (unsigned) ncand);
         if(lane == t) { rA0 = A0; rA1 = A1; rA2 = A2; rDtE = DtE; rMaxSig = MaxSig; rncand = ncand; rdens = dens_i; }
@@ -957,11 +1000,12 @@ int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte,
     if(int rc = make_dev(E, p, S)) return rc;
     if(S.p.DensityIndependentSphOn && !E->sph_DoEgy) return failmsg(E, "b200_hydro_force: pressure-entropy SPH needs b200_density with DoEgyDensity=1");
     const int np = (int) E->tree_np;
-    CK(E->s_hA.ensure(4 * (size_t) (np > 0 ? np : 1))); CK(E->s_hB.ensure(4 * (size_t) (np > 0 ? np : 1))); CK(E->s_hD.ensure((size_t) (np > 0 ? np : 1)));
+    CK(E->s_hA.ensure(4 * (size_t) (np > 0 ? np : 1))); CK(E->s_hB.ensure(4 * (size_t) (np > 0 ? np : 1))); CK(E->s_hD.ensure(8 * (size_t) (np > 0 ? np : 1)));
     timer_start(E, T_SPH_HYDRO);
     if(np > 0) {
         k_sph_gather_hydro<<<(np + 255) / 256, 256, 0, E->stream>>>(np, E->sidx.p, S, E->s_hsml.p, E->s_density.p, E->s_egy.p, E->s_dhsmlfac.p,
-            E->s_divvel.p, E->s_curlvel.p, (const double4 *) E->s_svel.p, (double4 *) E->s_hA.p, (double4 *) E->s_hB.p, E->s_hD.p);
+            E->s_divvel.p, E->s_curlvel.p, (const double4 *) E->s_svel.p, (double4 *) E->s_hA.p, (double4 *) E->s_hB.p, (double4 *) E->s_hD.p,
+            (double4 *) E->s_hD.p + (size_t) (np > 0 ? np : 1));
         CKL(E);
         CK(E->sph_list_a.ensure((size_t) np + 1)); CK(E->sph_list_b.ensure((size_t) np + 1));
         const int *tg = nullptr;
@@ -990,7 +1034,7 @@ int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte,
         if(nt > 0)
         k_sph_hydro_pairs<<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>(tg, nt, E->sidx.p, (const double4 *) E->spart.p,
             (const double2 *) E->spart_xy.p, (const double2 *) E->spart_zm.p, E->walk_partial.p, (const double4 *) E->s_svel.p,
-            (const double4 *) E->s_hA.p, (const double4 *) E->s_hB.p, E->s_hD.p, E->s_density.p, S,
+            (const double4 *) E->s_hA.p, (const double4 *) E->s_hB.p, (const double4 *) E->s_hD.p, (const double4 *) E->s_hD.p + (size_t) (np > 0 ? np : 1), E->s_density.p, S,
             E->walk_pool.p, E->walk_chunktab.p, E->walk_maxch, E->walk_cnt.p, d_acc, d_dte, d_maxsig, d_ninteract);
         CKL(E);
     }
