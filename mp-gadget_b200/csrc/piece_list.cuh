@@ -25,8 +25,12 @@ namespace b200 {
 // entry = first particle << 4 | count (0..8)
 #define PIECE(pstart, cnt) (((unsigned) (pstart) << 4) | (unsigned) (cnt))
 
-#define WALK_STACK 344        // (node, mask) entries per warp
-#define WALK_RESERVE 154      // head-room so that single pops (<= 7 net pushes each, depth <= 21+) never overflow
+// Per-warp stack of the gravity walk: opened internal nodes (node, mask).  A batch pops >= 1 entries and pushes <= 32;
+// above WALK_STACK - WALK_RESERVE the batches shrink to one node's children (net growth <= 7 per tree level, depth <= 22).
+#ifndef WALK_STACK
+#define WALK_STACK 320
+#endif
+#define WALK_RESERVE 192
 
 struct PiecePool {
     unsigned *__restrict__ pool;    // chunk pool
@@ -87,6 +91,51 @@ __device__ __forceinline__ void piece_push(bool want, unsigned entry, int &mycnt
         mycnt++;
         last = entry;
     }
+}
+
+// The same in two steps, for a batch of appends per lane: piece_reserve (all 32 lanes; nadd = entries this lane is
+// about to append) makes sure the warp owns the chunks of the longest resulting list, after which piece_append
+// (any subset of lanes, no votes) stores.  With MERGE a list may end shorter than reserved; the chunk stays the warp's.
+__device__ __forceinline__ void piece_reserve(int nadd, int mycnt, int &nch_alloc, int *s_ctab, const PiecePool &Q, int group, int lane)
+{
+    const int needch = (int) __reduce_max_sync(0xffffffffu, nadd > 0 ? (unsigned) ((mycnt + nadd - 1) >> CH_SHIFT) + 1u : 0u);
+    if(needch > nch_alloc) {                    // warp-uniform
+        if(needch > Q.maxch) { if(lane == 0) atomicOr(Q.ctl + 1, 2); }
+        else {
+            if(lane == 0)
+                for(int ch = nch_alloc; ch < needch; ch++) {
+                    const int id = atomicAdd(Q.ctl, 1);
+                    s_ctab[ch] = id;
+                    Q.chunk_tab[(size_t) group * Q.maxch + ch] = id;
+                }
+            nch_alloc = needch;
+        }
+        __syncwarp();
+    }
+}
+
+template <bool MERGE>
+__device__ __forceinline__ void piece_append(unsigned entry, int &mycnt, unsigned &last, int nch_alloc, const int *s_ctab,
+                                             const PiecePool &Q, int lane)
+{
+    if(MERGE) {
+        if(mycnt > 0 && (entry >> 4) == (last >> 4) + (last & 15u) && (last & 15u) + (entry & 15u) <= 8u) { last += entry & 15u; return; }
+        if(mycnt > 0) {                                     // the previous entry is final now
+            const int at = mycnt - 1, ch = at >> CH_SHIFT;
+            if(ch < nch_alloc) {
+                const int id = s_ctab[ch];
+                if(id < Q.cap) Q.pool[(size_t) id * CH_WORDS + (at & (CH_SLOTS - 1)) * 32 + lane] = last;
+            }
+        }
+    } else {
+        const int ch = mycnt >> CH_SHIFT;
+        if(ch < nch_alloc) {
+            const int id = s_ctab[ch];
+            if(id < Q.cap) Q.pool[(size_t) id * CH_WORDS + (mycnt & (CH_SLOTS - 1)) * 32 + lane] = entry;
+        }
+    }
+    mycnt++;
+    last = entry;
 }
 
 // End of a walk: the pending entry (MERGE), list lengths in target-slot order + statistics.

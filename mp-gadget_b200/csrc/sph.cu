@@ -40,6 +40,9 @@ namespace b200 {
 #define NORM_COEFF 4.188790204786
 #define FACT1 0.366025403785      // treewalk.c:19
 #define SPH_MAXITER 400
+// per-warp stack of child nodes in k_sph_walk: (node, mask) entries; head-room so that single pops (<= 7 net pushes each, depth <= 21+) never overflow
+#define SPH_WALK_STACK 344
+#define SPH_WALK_RESERVE 154
 
 struct SphDev {
     b200_sph_params p;
@@ -175,8 +178,8 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
            double *__restrict__ reach)     // [target slot] bound on the distance to any candidate of the kept leaves
 {
     extern __shared__ int s_ctab_dyn[];                 // [WALK_WARPS][Q.maxch]
-    __shared__ int s_stk_node_all[WALK_WARPS][WALK_STACK];
-    __shared__ unsigned s_stk_mask_all[WALK_WARPS][WALK_STACK];
+    __shared__ int s_stk_node_all[WALK_WARPS][SPH_WALK_STACK];
+    __shared__ unsigned s_stk_mask_all[WALK_WARPS][SPH_WALK_STACK];
     __shared__ SphBatch s_ent_all[WALK_WARPS];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int *s_ctab = s_ctab_dyn + wib * Q.maxch;
@@ -212,7 +215,7 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
     while(sp > 0) {
         int nb = sp < 32 ? sp : 32;
         {
-            const int room = (WALK_STACK - WALK_RESERVE - sp) / 7;
+            const int room = (SPH_WALK_STACK - SPH_WALK_RESERVE - sp) / 7;
             if(nb > room) nb = room > 1 ? room : 1;
         }
         sp -= nb;

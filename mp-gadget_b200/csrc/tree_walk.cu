@@ -214,6 +214,27 @@ __device__ __forceinline__ void pair_fast(double dx, double dy, double dz, doubl
     pot = fma(-mr, wp, pot);
 }
 
+// An accepted node in the walk kernel: apply_accn_to_output with the {T, Tpot} float table.  Newtonian regime
+// straight-line; inside the softening radius (practically never for an accepted node) the general path.
+__device__ __forceinline__ void node_term(double dx, double dy, double dz, double r2, double m,
+                                          const WalkPar &P, const float2 *tab,
+                                          double &ax, double &ay, double &az, double &pot)
+{
+    if(!(r2 >= P.h2s)) { monopole(dx, dy, dz, r2, m, P, TabF2{tab}, ax, ay, az, pot); return; }
+    const double rinv = rsqrt_pos(r2);
+    const double r = r2 * rinv;
+    const double mr = m * rinv;
+    const double ti = r * P.inv_cell_dx;
+    const int t = min((int) ti, B200_SR_NTAB - 2);
+    const double w1 = ti - (double) t;
+    const float2 a = tab[t], b = tab[t + 1];
+    const double f0 = (double) a.x, p0 = (double) a.y;
+    const double wf = fma(w1, (double) b.x - f0, f0), wp = fma(w1, (double) b.y - p0, p0);
+    const double fac = ti < (double) (B200_SR_NTAB - 1) ? mr * rinv * rinv * wf : 0.0;     // gravity.c:60-61: dropped beyond the table
+    ax = fma(dx, fac, ax); ay = fma(dy, fac, ay); az = fma(dz, fac, az);
+    pot = ti < (double) (B200_SR_NTAB - 1) ? fma(-mr, wp, pot) : pot;
+}
+
 // One source row of a leaf piece for this lane's slot.  Slots past the count read
 // the rows that follow (spart is padded with far-away massless rows) and are
 // neutralised through the mass.
@@ -426,30 +447,54 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
     int n_acc = 0, n_open = 0, n_disc = 0, n_part = 0;
 
     // The walk visits the same (target, node) pairs as the reference's depth-first
-    // walk: a target reaches a node iff it opened every ancestor (the mask).  Nodes
-    // are taken from a per-warp stack 32 at a time so that their rows are fetched
-    // in parallel (one node per lane) instead of one dependent load per step.
-    int sp = 1;
-    if(lane == 0) { s_stk_node[0] = 0; s_stk_mask[0] = validmask; }
+    // walk: a target reaches a node iff it opened every ancestor (the mask).  The per-warp
+    // stack holds OPENED INTERNAL NODES (node, mask of the lanes that opened it), one entry
+    // whatever the number of children; a batch is formed by expanding the topmost entries into
+    // up to 32 children whose rows are then fetched in parallel, one node per lane.  (A stack
+    // of children, 8 entries per opened node, filled up and throttled the batches to ~10 nodes.)
+    int sp = 0, nb = 1;
+    if(lane == 0) { s_ent.N[0] = 0; s_ent.M[0].z = (int) validmask; }
     __syncwarp();
-    while(true) {
-        if(sp == 0) break;
-        int nb = sp < 32 ? sp : 32;
-        {
-            const int room = (WALK_STACK - WALK_RESERVE - sp) / 7;
-            if(nb > room) nb = room > 1 ? room : 1;
+    for(bool first = true;; first = false) {
+        if(!first) {
+            if(sp == 0) break;
+            // ---- expansion: lane j looks at entry sp-1-j (the top 16); children are counted from nodeK
+            int myc = 0, pnode = 0;
+            unsigned pmask = 0;
+            int4 k0 = make_int4(-1, -1, -1, -1), k1 = k0;
+            if(lane < 16 && lane < sp) {
+                pnode = s_stk_node[sp - 1 - lane]; pmask = s_stk_mask[sp - 1 - lane];
+                k0 = nodeK[2 * (size_t) pnode]; k1 = nodeK[2 * (size_t) pnode + 1];
+                myc = (k0.x >= 0) + (k0.y >= 0) + (k0.z >= 0) + (k0.w >= 0) + (k1.x >= 0) + (k1.y >= 0) + (k1.z >= 0) + (k1.w >= 0);
+            }
+            int S = myc;            // inclusive scan from the top of the stack downwards
+#pragma unroll
+            for(int o = 1; o < 16; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, S, o); if(lane >= o) S += v; }
+            // deep in a narrow descent the batch is limited to one node's children so that the stack cannot overflow
+            const int cap = sp > WALK_STACK - WALK_RESERVE ? 8 : 32;
+            const int J = __popc(__ballot_sync(0xffffffffu, lane < 16 && lane < sp && S <= cap));      // >= 1 (a node has <= 8 children)
+            nb = __shfl_sync(0xffffffffu, S, J - 1);
+            if(lane < J) {
+                int w = nb - S;     // entries deeper in the stack first: batch slots stay in curve order
+                const int kids[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+                for(int c = 0; c < 8; c++) if(kids[c] >= 0) { s_ent.N[w] = kids[c]; s_ent.M[w].z = (int) pmask; w++; }
+            }
+            sp -= J;
+            __syncwarp();
         }
-        sp -= nb;
-        // ---- lane-parallel: lane l fetches entry sp + l, tests it against the warp's bounding box
-        int mynode = -1, mynch = 0;
-        bool dead = false, isleaf = false;
+        // ---- lane-parallel: lane l fetches batch entry l, tests it against the warp's bounding box
+        int mynode = -1;
+        bool dead = false, isleaf = false, bigleaf = false;
+        unsigned mydisc = 0;            // lanes (targets) for which the box tests discard the node this lane fetched
         if(lane < nb) {
-            mynode = s_stk_node[sp + lane];
-            const unsigned emask0 = s_stk_mask[sp + lane];
+            mynode = s_ent.N[lane];
+            const unsigned emask0 = (unsigned) s_ent.M[lane].z;
             const double4 eB = nodeB[mynode];
             const int4 C = nodeC[mynode];
             int eflags0 = C.w ? 1 : 0;
             isleaf = C.w != 0;
+            bigleaf = isleaf && C.z > 8;
             const double bcx = s_bbox[0], bcy = s_bbox[1], bcz = s_bbox[2], hbd = s_bbox[6];
             // Early discard for all lanes (gravshort-tree.c:198-215): along some axis the
             // node centre is farther than rcut + len/2 (+ rounding margin) from the whole
@@ -460,7 +505,9 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             if(!warp_central) {
                 ex = nearest(ex, P.box, P.halfbox); ey = nearest(ey, P.box, P.halfbox); ez = nearest(ez, P.box, P.halfbox);
             }
-            if(fabs(ex) - s_bbox[3] > lim || fabs(ey) - s_bbox[4] > lim || fabs(ez) - s_bbox[5] > lim) { eflags0 |= 2; dead = true; }
+            if(fabs(ex) - s_bbox[3] > lim || fabs(ey) - s_bbox[4] > lim || fabs(ez) - s_bbox[5] > lim) mydisc = emask0;
+            const unsigned emask = emask0 & ~mydisc;
+            if(emask == 0) { eflags0 |= 2; dead = true; }
             else {
                 const double4 eA = nodeA[mynode];
                 s_ent.A[lane] = eA;
@@ -481,7 +528,7 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
                                             (float) (4e-7 * (cinf + hbd + eff + eB.w)),
                                             (float) eff, (float) __dmul_rn(0.6, eB.w));
             }
-            s_ent.M[lane] = make_int4(C.y, C.z, (int) emask0, eflags0);
+            s_ent.M[lane] = make_int4(C.y, C.z, (int) emask, eflags0);
             s_ent.N[lane] = mynode;
         }
         __syncwarp();
@@ -490,13 +537,11 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
         // an internal node needs the warp's vote (who descends).
         unsigned myopeners = 0;       // lane l keeps the openers of entry l
         unsigned accbits = 0, openbits = 0;     // batch slots this lane accepted / opened
-        const unsigned deadmask = __ballot_sync(0xffffffffu, dead);
         const unsigned leafmask = __ballot_sync(0xffffffffu, isleaf);
         unsigned live = __ballot_sync(0xffffffffu, lane < nb && !dead);
         if(COUNT) {
-            const unsigned myemask = lane < nb ? (unsigned) s_ent.M[lane].z : 0u;
-            for(unsigned m = deadmask; m; m &= m - 1) {
-                const unsigned e = __shfl_sync(0xffffffffu, myemask, __ffs(m) - 1);
+            for(unsigned m = __ballot_sync(0xffffffffu, mydisc != 0); m; m &= m - 1) {
+                const unsigned e = __shfl_sync(0xffffffffu, mydisc, __ffs(m) - 1);
                 if((e >> lane) & 1u) n_disc++;
             }
         }
@@ -524,22 +569,41 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             if(haveB && !(MB.w & 1)) { const unsigned o = __ballot_sync(0xffffffffu, decB == 2); if(lane == kB) myopeners = o; }
         }
         // ---- phase 2, accepted nodes: monopole x tabulated window in fp64 (apply_accn_to_output), every lane
-        // working through ITS OWN accepted slots (lanes accept different nodes; this keeps them all busy)
+        // working through ITS OWN accepted slots (lanes accept different nodes; this keeps them all busy), two
+        // slots per turn (independent chains)
         if(COUNT) n_acc += __popc(accbits);
         while(__any_sync(0xffffffffu, accbits != 0)) {
             if(accbits) {
-                const int k = __ffs(accbits) - 1; accbits &= accbits - 1;
-                const double4 AN = s_ent.A[k];
-                double dx = AN.x - px, dy = AN.y - py, dz = AN.z - pz;
-                if(!warp_central) { dx = nearest(dx, P.box, P.halfbox); dy = nearest(dy, P.box, P.halfbox); dz = nearest(dz, P.box, P.halfbox); }
-                const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                monopole(dx, dy, dz, r2, AN.w, P, TabF2{tab}, ax, ay, az, pot);
+                const int k0 = __ffs(accbits) - 1; accbits &= accbits - 1;
+                const bool two = accbits != 0;
+                const int k1 = two ? __ffs(accbits) - 1 : k0; accbits &= accbits - 1;
+                const double4 A0 = s_ent.A[k0], A1 = s_ent.A[k1];
+                double dx0 = A0.x - px, dy0 = A0.y - py, dz0 = A0.z - pz, dx1 = A1.x - px, dy1 = A1.y - py, dz1 = A1.z - pz;
+                if(!warp_central) {
+                    dx0 = nearest(dx0, P.box, P.halfbox); dy0 = nearest(dy0, P.box, P.halfbox); dz0 = nearest(dz0, P.box, P.halfbox);
+                    dx1 = nearest(dx1, P.box, P.halfbox); dy1 = nearest(dy1, P.box, P.halfbox); dz1 = nearest(dz1, P.box, P.halfbox);
+                }
+                const double r20 = __dadd_rn(__dadd_rn(__dmul_rn(dx0, dx0), __dmul_rn(dy0, dy0)), __dmul_rn(dz0, dz0));
+                const double r21 = __dadd_rn(__dadd_rn(__dmul_rn(dx1, dx1), __dmul_rn(dy1, dy1)), __dmul_rn(dz1, dz1));
+                node_term(dx0, dy0, dz0, r20, A0.w, P, tab, ax, ay, az, pot);
+                node_term(dx1, dy1, dz1, r21, two ? A1.w : 0.0, P, tab, ax, ay, az, pot);
             }
         }
         // ---- phase 3, opened particle leaves (gravshort-tree.c:344-352): every lane appends its own leaves, in
         // slot order, to its piece list; pieces of <= 8 particles (only leaves at the key-depth limit hold more)
         if(COUNT) { n_open += __popc(openbits & ~leafmask); }
         openbits &= leafmask;
+        if(__ballot_sync(0xffffffffu, bigleaf) == 0) {
+            // chunks for the longest list this batch can produce are reserved by one vote; the appends need none
+            piece_reserve(__popc(openbits), mycnt, nch_alloc, s_ctab, Q, group, lane);
+            while(openbits) {
+                const int k = __ffs(openbits) - 1; openbits &= openbits - 1;
+                const int4 M = s_ent.M[k];
+                if(COUNT) n_part += M.y;
+                piece_append<MERGE>(PIECE(M.x, M.y), mycnt, mylast, nch_alloc, s_ctab, Q, lane);
+            }
+            __syncwarp();
+        } else
         while(__any_sync(0xffffffffu, openbits != 0)) {
             const bool want = openbits != 0;
             int pstart = 0, cnt = 0;
@@ -558,23 +622,17 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             } else
                 piece_push<MERGE>(want, PIECE(pstart, cnt), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
         }
-        // ---- lane-parallel: push the children of opened internal nodes
-        int4 k0 = make_int4(-1, -1, -1, -1), k1 = k0;
-        if(myopeners) {
-            k0 = nodeK[2 * (size_t) mynode]; k1 = nodeK[2 * (size_t) mynode + 1];
-            mynch = (k0.x >= 0) + (k0.y >= 0) + (k0.z >= 0) + (k0.w >= 0) + (k1.x >= 0) + (k1.y >= 0) + (k1.z >= 0) + (k1.w >= 0);
+        // ---- lane-parallel: push the opened internal nodes, in slot order
+        {
+            const unsigned pushers = __ballot_sync(0xffffffffu, myopeners != 0);
+            const int np_ = __popc(pushers);
+            if(sp + np_ > WALK_STACK) { if(lane == 0) atomicOr(Q.ctl + 1, 4); break; }      // cannot happen (WALK_RESERVE); reported, not ignored
+            if(myopeners) {
+                const int w = sp + __popc(pushers & ((1u << lane) - 1u));
+                s_stk_node[w] = mynode; s_stk_mask[w] = myopeners;
+            }
+            sp += np_;
         }
-        int off = mynch;        // inclusive scan over lanes
-#pragma unroll
-        for(int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if(lane >= o) off += v; }
-        const int total = __shfl_sync(0xffffffffu, off, 31);
-        if(mynch) {
-            int w = sp + off - mynch;
-            const int kids[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-#pragma unroll
-            for(int c = 0; c < 8; c++) if(kids[c] >= 0) { s_stk_node[w] = kids[c]; s_stk_mask[w] = myopeners; w++; }
-        }
-        sp += total;
         __syncwarp();
     }
     // hand over to k_grav_pairs (target-slot order: coalesced)
@@ -718,6 +776,7 @@ int piece_pool_check(Engine *E, int64_t nwarps, bool *retry, int attempt)
     CK(cudaMemcpyAsync(h, E->scratch_i.p + 64, 4 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     *retry = false;
+    if(h[1] & 4) return failmsg(E, "tree walk: node stack overflow (tree deeper than the walk kernels allow)");
     if(h[1] & 2) {      // a list outgrew the warp's chunk table: repeat with a table 8x as long
         if(E->walk_maxch >= WALK_MAXCH_LIMIT)
             return failmsg(E, "tree walk: a particle opened more than " + std::to_string(CH_SLOTS * WALK_MAXCH_LIMIT) + " leaf pieces");
