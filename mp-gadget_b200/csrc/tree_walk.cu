@@ -53,6 +53,7 @@ struct WalkPar {
     int usebh;
     int ntargets;
     int f32ok;                  // the fp32 pre-classification of the walk may be used (box within float range)
+    float rcut2f, th2lo, th2hi; // fp32 thresholds of that pre-classification (theta^2 widened by 2e-6 either way)
 };
 
 __device__ __forceinline__ double nearest(double x, double box, double halfbox)   // NEAREST partmanager.h:99
@@ -336,6 +337,26 @@ struct Walk32 {
     bool rel;
 };
 
+// Per-warp staging of the pair-wise phase 1: the targets' fp32 constants (read by whichever lane works on a pair
+// of that target) and the decisions as bit sets: acc/opn/dis[l] = batch slots target l accepted / opened /
+// discarded, openers[k] = targets that opened slot k, first[k] = index of slot k's first pair.
+struct PairStage {
+    float4 t32[32];     // position - bbox centre, alo
+    float ahi[32];
+    unsigned acc[32], opn[32], dis[32], openers[32];
+    int first[32];
+};
+
+// position of the r-th (0-based) set bit of m (r < popc(m)): the byte by two population counts, the bit inside it
+// from a table [byte value][r] in shared memory
+__device__ __forceinline__ int nth_set_bit(unsigned m, int r, const unsigned char *lut)
+{
+    int pos = 0;
+    int c = __popc(m & 0xffffu); if(r >= c) { r -= c; pos = 16; m >>= 16; }
+    c = __popc(m & 0xffu); if(r >= c) { r -= c; pos += 8; m >>= 8; }
+    return pos + lut[(m & 0xffu) * 8 + r];
+}
+
 // Interval version of classify(): every comparison of shall_we_discard_node / shall_we_open_node
 // (gravshort-tree.c:198-241) is evaluated at both ends of the rounding-error interval of its fp32
 // operands (r2 in [r2 - tau2, r2 + tau2], max |centre - p| in [c - mu, c + mu], the thresholds widened by
@@ -386,8 +407,15 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
     __shared__ unsigned s_stk_mask_all[WALK_WARPS][WALK_STACK];
     __shared__ BatchEntry s_ent_all[WALK_WARPS];
     __shared__ double s_bbox_all[WALK_WARPS][8];        // bbox centre, half extents, half diagonal of the warp's targets
+    __shared__ PairStage s_res_all[WALK_WARPS];
+    __shared__ unsigned char s_nthbit[256 * 8];         // nth_set_bit
     for(int k = threadIdx.x; k < B200_SR_NTAB; k += blockDim.x)
         tab[k] = make_float2(gtab[k], gtab[B200_SR_NTAB + k]);       // monopole() never takes t >= NTAB-1 as the base row
+    for(int k = threadIdx.x; k < 256 * 8; k += blockDim.x) {
+        int b = k >> 3, r = k & 7, pos = 0;
+        for(int i = 0; i < 8; i++) if((b >> i) & 1) { if(r == 0) { pos = i; break; } r--; }
+        s_nthbit[k] = (unsigned char) pos;
+    }
     __syncthreads();
     const int wib = threadIdx.x >> 5;
     int *s_ctab = s_ctab_dyn + wib * Q.maxch;
@@ -395,6 +423,8 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
     unsigned *s_stk_mask = s_stk_mask_all[wib];
     BatchEntry &s_ent = s_ent_all[wib];
     double *s_bbox = s_bbox_all[wib];
+    PairStage &s_res = s_res_all[wib];
+    const unsigned ltmask = (1u << (threadIdx.x & 31)) - 1u;
     int mycnt = 0;          // pieces in this lane's list
     unsigned mylast = 0;    // its last entry (merged with the next piece when contiguous; stored when the next one starts)
     int nch_alloc = 0;      // chunks this warp owns (warp-uniform)
@@ -437,10 +467,11 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
         const bool tiny = !(a32 >= 1e-30f);
         L32.alo = tiny ? 0.f : a32 * (1.f - 2e-6f);
         L32.ahi = (tiny ? 1e-30f : a32) * (1.f + 2e-6f);
+        s_res.t32[lane] = make_float4(L32.px, L32.py, L32.pz, L32.alo);
+        s_res.ahi[lane] = L32.ahi;
     }
     Walk32 W32;
-    W32.rcut2 = (float) P.rcut2;
-    W32.th2lo = (float) P.theta2 * (1.f - 2e-6f); W32.th2hi = (float) P.theta2 * (1.f + 2e-6f);
+    W32.rcut2 = P.rcut2f; W32.th2lo = P.th2lo; W32.th2hi = P.th2hi;
     W32.rel = P.usebh == 0;
 
     double ax = 0, ay = 0, az = 0, pot = 0;
@@ -483,91 +514,119 @@ k_grav_walk(const double4 *__restrict__ nodeA, const double4 *__restrict__ nodeB
             sp -= J;
             __syncwarp();
         }
-        // ---- lane-parallel: lane l fetches batch entry l, tests it against the warp's bounding box
-        int mynode = -1;
-        bool dead = false, isleaf = false, bigleaf = false;
-        unsigned mydisc = 0;            // lanes (targets) for which the box tests discard the node this lane fetched
+        // ---- lane-parallel: lane l fetches batch entry l and tests it against the warp's bounding box; the
+        // survivors are staged in consecutive slots 0..nl-1 (batch order kept)
+        bool dead = true;
+        unsigned mydisc = 0;            // lanes (targets) for which the box test discards the node this lane fetched
+        unsigned emask = 0;
+        int mynode = -1, eflags0 = 0;
+        double4 eA = make_double4(0, 0, 0, 0), eB = eA;
+        int4 C = make_int4(0, 0, 0, 0);
+        double ex = 0, ey = 0, ez = 0, eff = 0;
         if(lane < nb) {
             mynode = s_ent.N[lane];
             const unsigned emask0 = (unsigned) s_ent.M[lane].z;
-            const double4 eB = nodeB[mynode];
-            const int4 C = nodeC[mynode];
-            int eflags0 = C.w ? 1 : 0;
-            isleaf = C.w != 0;
-            bigleaf = isleaf && C.z > 8;
-            const double bcx = s_bbox[0], bcy = s_bbox[1], bcz = s_bbox[2], hbd = s_bbox[6];
+            eB = nodeB[mynode]; C = nodeC[mynode]; eA = nodeA[mynode];
+            eflags0 = C.w ? 1 : 0;
             // Early discard for all lanes (gravshort-tree.c:198-215): along some axis the
             // node centre is farther than rcut + len/2 (+ rounding margin) from the whole
             // bounding box; the centre of mass lies inside the cell, so r2 > rcut^2 follows.
-            const double eff = P.rcut + 0.5 * eB.w;
+            eff = P.rcut + 0.5 * eB.w;
             const double lim = eff + 1e-9 * (eff + eB.w);
-            double ex = eB.x - bcx, ey = eB.y - bcy, ez = eB.z - bcz;
+            ex = eB.x - s_bbox[0]; ey = eB.y - s_bbox[1]; ez = eB.z - s_bbox[2];
             if(!warp_central) {
                 ex = nearest(ex, P.box, P.halfbox); ey = nearest(ey, P.box, P.halfbox); ez = nearest(ez, P.box, P.halfbox);
             }
             if(fabs(ex) - s_bbox[3] > lim || fabs(ey) - s_bbox[4] > lim || fabs(ez) - s_bbox[5] > lim) mydisc = emask0;
-            const unsigned emask = emask0 & ~mydisc;
-            if(emask == 0) { eflags0 |= 2; dead = true; }
-            else {
-                const double4 eA = nodeA[mynode];
-                s_ent.A[lane] = eA;
-                double mx = eA.x - bcx, my = eA.y - bcy, mz = eA.z - bcz;
-                if(!warp_central) {
-                    mx = nearest(mx, P.box, P.halfbox); my = nearest(my, P.box, P.halfbox); mz = nearest(mz, P.box, P.halfbox);
-                }
-                const double ml2 = __dmul_rn(__dmul_rn(eA.w, eB.w), eB.w);
-                const double cinf = fmax(fmax(fabs(ex), fabs(ey)), fabs(ez));
-                const double minf = fmax(fmax(fabs(mx), fabs(my)), fabs(mz));
-                const double rmax = sqrt(mx * mx + my * my + mz * mz) + hbd;
-                // a lane's NEAREST(node - p) equals (node - bc wrapped) - (p - bc) only away from the +-box/2 seam
-                const bool seam = !warp_central && (fmax(cinf, minf) + hbd >= 0.999999 * P.halfbox);
-                if(!P.f32ok || seam || (ml2 > 0.0 && ml2 < 1e-30)) eflags0 |= 4;
-                s_ent.C[lane] = make_float4((float) ex, (float) ey, (float) ez, (float) eB.w);
-                s_ent.F[lane] = make_float4((float) mx, (float) my, (float) mz, (float) ml2);
-                s_ent.T[lane] = make_float4((float) (1e-6 * (rmax * rmax + hbd * hbd) + 4e-7 * P.rcut2),
-                                            (float) (4e-7 * (cinf + hbd + eff + eB.w)),
-                                            (float) eff, (float) __dmul_rn(0.6, eB.w));
-            }
-            s_ent.M[lane] = make_int4(C.y, C.z, (int) emask, eflags0);
-            s_ent.N[lane] = mynode;
+            emask = emask0 & ~mydisc;
+            dead = emask == 0;
         }
-        __syncwarp();
-        // ---- phase 1, per-target decisions on the staged nodes that survived the bounding-box test, two at a
-        // time (independent arithmetic chains).  Results stay in per-lane bit sets over the batch slots; only
-        // an internal node needs the warp's vote (who descends).
-        unsigned myopeners = 0;       // lane l keeps the openers of entry l
-        unsigned accbits = 0, openbits = 0;     // batch slots this lane accepted / opened
-        const unsigned leafmask = __ballot_sync(0xffffffffu, isleaf);
-        unsigned live = __ballot_sync(0xffffffffu, lane < nb && !dead);
+        const unsigned livemask = __ballot_sync(0xffffffffu, !dead);      // every lane has read its entry by now
+        const int nl = __popc(livemask);
+        if(!dead) {
+            const int ck = __popc(livemask & ltmask);
+            const double bcx = s_bbox[0], bcy = s_bbox[1], bcz = s_bbox[2], hbd = s_bbox[6];
+            s_ent.A[ck] = eA;
+            double mx = eA.x - bcx, my = eA.y - bcy, mz = eA.z - bcz;
+            if(!warp_central) {
+                mx = nearest(mx, P.box, P.halfbox); my = nearest(my, P.box, P.halfbox); mz = nearest(mz, P.box, P.halfbox);
+            }
+            const double ml2 = __dmul_rn(__dmul_rn(eA.w, eB.w), eB.w);
+            const double cinf = fmax(fmax(fabs(ex), fabs(ey)), fabs(ez));
+            const double minf = fmax(fmax(fabs(mx), fabs(my)), fabs(mz));
+            const double rmax = sqrt(mx * mx + my * my + mz * mz) + hbd;
+            // a lane's NEAREST(node - p) equals (node - bc wrapped) - (p - bc) only away from the +-box/2 seam
+            const bool seam = !warp_central && (fmax(cinf, minf) + hbd >= 0.999999 * P.halfbox);
+            if(!P.f32ok || seam || (ml2 > 0.0 && ml2 < 1e-30)) eflags0 |= 4;
+            s_ent.C[ck] = make_float4((float) ex, (float) ey, (float) ez, (float) eB.w);
+            s_ent.F[ck] = make_float4((float) mx, (float) my, (float) mz, (float) ml2);
+            s_ent.T[ck] = make_float4((float) (1e-6 * (rmax * rmax + hbd * hbd) + 4e-7 * P.rcut2),
+                                      (float) (4e-7 * (cinf + hbd + eff + eB.w)),
+                                      (float) eff, (float) __dmul_rn(0.6, eB.w));
+            s_ent.M[ck] = make_int4(C.y, C.z, (int) emask, eflags0);
+            s_ent.N[ck] = mynode;
+        }
         if(COUNT) {
             for(unsigned m = __ballot_sync(0xffffffffu, mydisc != 0); m; m &= m - 1) {
                 const unsigned e = __shfl_sync(0xffffffffu, mydisc, __ffs(m) - 1);
                 if((e >> lane) & 1u) n_disc++;
             }
         }
-        while(live) {
-            const int kA = __ffs(live) - 1; live &= live - 1;
-            const bool haveB = live != 0;
-            const int kB = haveB ? __ffs(live) - 1 : kA; live &= live - 1;
-            const int4 MA = s_ent.M[kA], MB = s_ent.M[kB];
-            const bool awakeA = (((unsigned) MA.z) >> lane) & 1u, awakeB = haveB && ((((unsigned) MB.z) >> lane) & 1u);
-            int decA = classify32(s_ent.C[kA], s_ent.F[kA], s_ent.T[kA], L32, W32);
-            int decB = classify32(s_ent.C[kB], s_ent.F[kB], s_ent.T[kB], L32, W32);
-            if((MA.w & 4)) decA = 3;
-            if((MB.w & 4)) decB = 3;
-            if(__any_sync(0xffffffffu, (awakeA && decA == 3) || (awakeB && decB == 3))) {
-                // rare: some lane is within rounding of a threshold (or the node sits on the box seam):
-                // the reference's own fp64 comparisons decide
-                decA = classify_exact(s_ent.A[kA], nodeB[s_ent.N[kA]], px, py, pz, aold, P, !warp_central);
-                decB = classify_exact(s_ent.A[kB], nodeB[s_ent.N[kB]], px, py, pz, aold, P, !warp_central);
-            }
-            decA = awakeA ? decA : -1; decB = awakeB ? decB : -1;
-            accbits |= (decA == 1 ? 1u : 0u) << kA; accbits |= (decB == 1 ? 1u : 0u) << kB;
-            openbits |= (decA == 2 ? 1u : 0u) << kA; openbits |= (decB == 2 ? 1u : 0u) << kB;
-            if(COUNT) { n_disc += (decA == 0) + (decB == 0); }
-            if(!(MA.w & 1)) { const unsigned o = __ballot_sync(0xffffffffu, decA == 2); if(lane == kA) myopeners = o; }
-            if(haveB && !(MB.w & 1)) { const unsigned o = __ballot_sync(0xffffffffu, decB == 2); if(lane == kB) myopeners = o; }
+        s_res.acc[lane] = 0; s_res.opn[lane] = 0; s_res.openers[lane] = 0;
+        if(COUNT) s_res.dis[lane] = 0;
+        __syncwarp();
+        // ---- phase 1, the per-target decisions, over the (node, target) pairs that exist: node k of the batch is
+        // tested only for the lanes of its mask (about half of them on average), 32 pairs at a time whatever
+        // nodes they belong to.  Pair w of the batch -> node k by the prefix sums of the mask populations,
+        // target l = the (w - first pair of k)-th set bit of the mask.  Decisions go to bit sets in shared memory.
+        const int4 Mc = lane < nl ? s_ent.M[lane] : make_int4(0, 0, 0, 0);
+        int T;
+        int excl;
+        {
+            int incl = __popc((unsigned) Mc.z);
+#pragma unroll
+            for(int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if(lane >= o) incl += v; }
+            T = __shfl_sync(0xffffffffu, incl, 31);
+            excl = incl - __popc((unsigned) Mc.z);
+            s_res.first[lane] = excl;
         }
+        const unsigned leafmask = __ballot_sync(0xffffffffu, (Mc.w & 1) != 0);
+        const bool bigleaf = (Mc.w & 1) && Mc.y > 8;
+        __syncwarp();
+        for(int base = 0; base < T; base += 32) {
+            const int sj = excl - base;
+            const unsigned startmask = __reduce_or_sync(0xffffffffu, (lane < nl && sj >= 1 && sj <= 31) ? 1u << sj : 0u);
+            const int kfirst = __popc(__ballot_sync(0xffffffffu, lane < nl && excl <= base)) - 1;
+            const bool act = base + lane < T;
+            int dec = -1, k = 0, l = 0;
+            if(act) {
+                k = kfirst + __popc(startmask & (0xfffffffeu & (0xffffffffu >> (31 - lane))));
+                const int4 M = s_ent.M[k];
+                l = nth_set_bit((unsigned) M.z, base + lane - s_res.first[k], s_nthbit);
+                const float4 tp = s_res.t32[l];
+                Lane32 L; L.px = tp.x; L.py = tp.y; L.pz = tp.z; L.alo = tp.w; L.ahi = s_res.ahi[l];
+                dec = classify32(s_ent.C[k], s_ent.F[k], s_ent.T[k], L, W32);
+                if(M.w & 4) dec = 3;
+                if(M.w & 1) dec |= 8;           // leaf: nobody needs the list of its openers
+            }
+            if(__any_sync(0xffffffffu, (dec & 7) == 3)) {
+                // rare: the pair is within rounding of a threshold (or the node sits on the box seam):
+                // the reference's own fp64 comparisons decide
+                const double qx = __shfl_sync(0xffffffffu, px, l), qy = __shfl_sync(0xffffffffu, py, l), qz = __shfl_sync(0xffffffffu, pz, l);
+                const double qa = __shfl_sync(0xffffffffu, aold, l);
+                if((dec & 7) == 3) dec = (dec & 8) | classify_exact(s_ent.A[k], nodeB[s_ent.N[k]], qx, qy, qz, qa, P, !warp_central);
+            }
+            if(act) {
+                if((dec & 7) == 1) atomicOr(&s_res.acc[l], 1u << k);
+                else if((dec & 7) == 2) { atomicOr(&s_res.opn[l], 1u << k); if(!(dec & 8)) atomicOr(&s_res.openers[k], 1u << l); }
+                else if(COUNT) atomicOr(&s_res.dis[l], 1u << k);
+            }
+        }
+        __syncwarp();
+        unsigned accbits = s_res.acc[lane], openbits = s_res.opn[lane];     // batch slots this lane accepted / opened
+        const unsigned myopeners = s_res.openers[lane];                     // lane k: the lanes that opened slot k (internal nodes)
+        mynode = lane < nl ? s_ent.N[lane] : -1;
+        if(COUNT) n_disc += __popc(s_res.dis[lane]);
         // ---- phase 2, accepted nodes: monopole x tabulated window in fp64 (apply_accn_to_output), every lane
         // working through ITS OWN accepted slots (lanes accept different nodes; this keeps them all busy), two
         // slots per turn (independent chains)
@@ -861,6 +920,7 @@ int grav_short_tree(Engine *E, const b200_gravshort_params *par, const int32_t *
     {   // fp32 pre-classification: r2^2 * aold and mass*len^2 must stay far from the ends of the float range
         static const bool off = getenv("B200_WALK_F64") != nullptr;
         P.f32ok = (!off && E->tree_box > 1e-6 && E->tree_box < 1e7) ? 1 : 0;
+        P.rcut2f = (float) P.rcut2; P.th2lo = (float) P.theta2 * (1.f - 2e-6f); P.th2hi = (float) P.theta2 * (1.f + 2e-6f);
     }
     {   // reach of the window table: index >= NTAB-1 <=> r >= (NTAB-1)*dx cells = 15 cells (gravity.c:57-61)
         const double reach = 1.001 * (B200_SR_NTAB - 1) * (double) B200_SR_DX * cellsize;
