@@ -40,9 +40,10 @@ namespace b200 {
 #define NORM_COEFF 4.188790204786
 #define FACT1 0.366025403785      // treewalk.c:19
 #define SPH_MAXITER 400
-// per-warp stack of child nodes in k_sph_walk: (node, mask) entries; head-room so that single pops (<= 7 net pushes each, depth <= 21+) never overflow
-#define SPH_WALK_STACK 344
-#define SPH_WALK_RESERVE 154
+// per-warp stack of kept internal nodes in k_sph_walk: (node, mask) entries; above STACK - RESERVE the batches shrink to
+// one node's children (net growth <= 7 per tree level, depth <= 22; a batch pushes <= 32)
+#define SPH_WALK_STACK 320
+#define SPH_WALK_RESERVE 192
 
 struct SphDev {
     b200_sph_params p;
@@ -166,6 +167,7 @@ struct SphBatch {
     double4 B[32];    // center, len
     int4 M[32];       // pstart, count, mask of lanes that kept every ancestor, flags (bit0 leaf, bit1 culled for all lanes)
     double H[32];     // hmax of the node (symmetric search)
+    int N[32];        // node index (batch input)
 };
 
 // Neighbour search for 32 targets.  targets: sorted (curve-order) particle indices, NULL = 0..nt-1.
@@ -174,9 +176,13 @@ template <bool SYM>
 __global__ void __launch_bounds__(128, 5)
 k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, const int4 *__restrict__ nodeK,
            const double *__restrict__ nodeH, const double4 *__restrict__ spart, const int *__restrict__ sidx,
-           const int *__restrict__ targets, int nt, const double *__restrict__ hsml, SphDev S, PiecePool Q,
+           const int *__restrict__ targets, int nt, int tpw, const double *__restrict__ hsml, SphDev S, PiecePool Q,
            double *__restrict__ reach)     // [target slot] bound on the distance to any candidate of the kept leaves
 {
+    // tpw = targets per warp (lanes 0..tpw-1): 32 for a pass over (nearly) all particles; the later passes of the
+    // smoothing-length iteration are sparse -- 32 consecutive unconverged targets lie far apart and the union of
+    // their searches approaches the whole tree -- and use 8 or 1.
+    __shared__ double4 s_tgt_all[WALK_WARPS][32];       // position, search radius of the warp's targets
     extern __shared__ int s_ctab_dyn[];                 // [WALK_WARPS][Q.maxch]
     __shared__ int s_stk_node_all[WALK_WARPS][SPH_WALK_STACK];
     __shared__ unsigned s_stk_mask_all[WALK_WARPS][SPH_WALK_STACK];
@@ -186,10 +192,11 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
     int *s_stk_node = s_stk_node_all[wib];
     unsigned *s_stk_mask = s_stk_mask_all[wib];
     SphBatch &s_ent = s_ent_all[wib];
+    double4 *s_tgt = s_tgt_all[wib];
     const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int tslot = group * 32 + lane;
-    const bool valid = tslot < nt;
-    if(group * 32 >= nt) return;            // warp-uniform
+    const int tslot = group * tpw + lane;
+    const bool valid = lane < tpw && tslot < nt;
+    if((int64_t) group * tpw >= nt) return; // warp-uniform
     double px = 0, py = 0, pz = 0, h = 0;
     if(valid) {
         const int j = targets ? targets[tslot] : tslot;
@@ -197,6 +204,7 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
         px = pm.x; py = pm.y; pz = pm.z;
         h = hsml[sidx[j]];
     }
+    s_tgt[lane] = make_double4(px, py, pz, h);
     const double big = 1e300;
     const double lox = warp_min(valid ? px : big), hix = warp_max(valid ? px : -big);
     const double loy = warp_min(valid ? py : big), hiy = warp_max(valid ? py : -big);
@@ -209,77 +217,118 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
     unsigned mylast = 0;
     double myreach = 0;
 
-    int sp = 1;
-    if(lane == 0) { s_stk_node[0] = 0; s_stk_mask[0] = validmask; }
+    // The stack holds KEPT INTERNAL NODES (node, mask of the lanes that kept it); a batch is formed by expanding the
+    // topmost entries into up to 32 children (see k_grav_walk, tree_walk.cu).
+    int sp = 0, nb = 1;
+    if(lane == 0) { s_ent.N[0] = 0; s_ent.M[0].z = (int) validmask; }
     __syncwarp();
-    while(sp > 0) {
-        int nb = sp < 32 ? sp : 32;
-        {
-            const int room = (SPH_WALK_STACK - SPH_WALK_RESERVE - sp) / 7;
-            if(nb > room) nb = room > 1 ? room : 1;
+    for(bool first = true;; first = false) {
+        if(!first) {
+            if(sp == 0) break;
+            int myc = 0;
+            unsigned pmask = 0;
+            int4 k0 = make_int4(-1, -1, -1, -1), k1 = k0;
+            if(lane < 16 && lane < sp) {
+                const int pnode = s_stk_node[sp - 1 - lane]; pmask = s_stk_mask[sp - 1 - lane];
+                k0 = nodeK[2 * (size_t) pnode]; k1 = nodeK[2 * (size_t) pnode + 1];
+                myc = (k0.x >= 0) + (k0.y >= 0) + (k0.z >= 0) + (k0.w >= 0) + (k1.x >= 0) + (k1.y >= 0) + (k1.z >= 0) + (k1.w >= 0);
+            }
+            int Sc = myc;           // inclusive scan from the top of the stack downwards
+#pragma unroll
+            for(int o = 1; o < 16; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, Sc, o); if(lane >= o) Sc += v; }
+            const int cap = sp > SPH_WALK_STACK - SPH_WALK_RESERVE ? 8 : 32;
+            const int J = __popc(__ballot_sync(0xffffffffu, lane < 16 && lane < sp && Sc <= cap));
+            nb = __shfl_sync(0xffffffffu, Sc, J - 1);
+            if(lane < J) {
+                int w = nb - Sc;
+                const int kids[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+                for(int c = 0; c < 8; c++) if(kids[c] >= 0) { s_ent.N[w] = kids[c]; s_ent.M[w].z = (int) pmask; w++; }
+            }
+            sp -= J;
+            __syncwarp();
         }
-        sp -= nb;
-        // ---- lane-parallel: lane l fetches entry sp + l and tests it against the warp's bounding box
-        int mynode = -1, mynch = 0;
+        // ---- lane-parallel: lane l fetches batch entry l and tests it against the warp's bounding box
+        int mynode = -1;
+        bool dead = true, bigleaf = false, isleaf = false;
+        unsigned emask0 = 0;
+        double4 eB = make_double4(0, 0, 0, 0);
+        double eH = 0;
         if(lane < nb) {
-            mynode = s_stk_node[sp + lane];
-            const unsigned emask0 = s_stk_mask[sp + lane];
-            const double4 eB = nodeB[mynode];
+            mynode = s_ent.N[lane];
+            emask0 = (unsigned) s_ent.M[lane].z;
+            eB = nodeB[mynode];
             const int4 C = nodeC[mynode];
-            const double eH = SYM ? nodeH[mynode] : 0.0;
-            int eflags0 = C.w ? 1 : 0;
+            eH = SYM ? nodeH[mynode] : 0.0;
+            isleaf = C.w != 0;
+            bigleaf = isleaf && C.z > 8;
             // cull_node's per-axis test (treewalk.c:1023-1036) for the whole warp: the largest search
             // radius of the warp against the distance from the node centre to the bounding box
             const double dist = ((SYM && eH > hw) ? eH : hw) + 0.5 * eB.w;
             const double lim = dist + 1e-9 * (dist + eB.w);
             const double ex = nearest_s(eB.x - bcx, S.box, S.halfbox), ey = nearest_s(eB.y - bcy, S.box, S.halfbox),
                          ez = nearest_s(eB.z - bcz, S.box, S.halfbox);
-            if(fabs(ex) - bhx > lim || fabs(ey) - bhy > lim || fabs(ez) - bhz > lim) eflags0 |= 2;
+            dead = fabs(ex) - bhx > lim || fabs(ey) - bhy > lim || fabs(ez) - bhz > lim;
             s_ent.B[lane] = eB;
             s_ent.H[lane] = eH;
-            s_ent.M[lane] = make_int4(C.y, C.z, (int) emask0, eflags0);
+            s_ent.M[lane] = make_int4(C.y, C.z, (int) emask0, isleaf ? 1 : 0);
         }
         __syncwarp();
-        // ---- per-target exact decisions
-        unsigned myopeners = 0;
-        const bool dead = lane < nb && (s_ent.M[lane].w & 2);
-        unsigned live = __ballot_sync(0xffffffffu, lane < nb && !dead);
-        while(live) {
-            const int k = __ffs(live) - 1; live &= live - 1;
-            const int4 M = s_ent.M[k];
-            const bool awake = (((unsigned) M.z) >> lane) & 1u;
-            const bool keep = awake && cull_keep(s_ent.B[k], s_ent.H[k], px, py, pz, h, SYM, S);
-            const unsigned openmask = __ballot_sync(0xffffffffu, keep);
-            if(openmask == 0) continue;
-            if(M.w & 1) {
-                if(keep) {      // every particle of a kept leaf is within search distance + len of the target (cull_node)
-                    const double hn = s_ent.H[k], len = s_ent.B[k].w;
-                    const double r = ((SYM && hn > h) ? hn : h) + len;
-                    myreach = r > myreach ? r : myreach;
-                }
-                for(int o = 0; o < M.y; o += 8) {
-                    const int c = M.y - o < 8 ? M.y - o : 8;
-                    piece_push<true>(keep, PIECE(M.x + o, c), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
-                }
-            } else if(lane == k) myopeners = openmask;
+        // ---- exact decisions, one TARGET per turn: every lane tests the node it holds (in registers) against the
+        // target's position and radius (broadcast from shared memory), so a turn is 32 (node, target) tests whatever
+        // the number of targets in the warp.  The vote gives the target its kept leaves; a lane collects who kept its node.
+        unsigned myopeners = 0, keepbits = 0;
+        const unsigned leafmask = __ballot_sync(0xffffffffu, isleaf);
+        const unsigned anybig = __ballot_sync(0xffffffffu, bigleaf);
+        for(unsigned m = __reduce_or_sync(0xffffffffu, dead ? 0u : emask0); m; m &= m - 1) {
+            const int t = __ffs(m) - 1;
+            const double4 T = s_tgt[t];
+            const bool keep = !dead && ((emask0 >> t) & 1u) && cull_keep(eB, eH, T.x, T.y, T.z, T.w, SYM, S);
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if(lane == t) keepbits = bal & leafmask;
+            if(keep && !isleaf) myopeners |= 1u << t;
         }
-        // ---- lane-parallel: push the children of kept internal nodes
-        int4 k0 = make_int4(-1, -1, -1, -1), k1 = k0;
-        if(myopeners) {
-            k0 = nodeK[2 * (size_t) mynode]; k1 = nodeK[2 * (size_t) mynode + 1];
-            mynch = (k0.x >= 0) + (k0.y >= 0) + (k0.z >= 0) + (k0.w >= 0) + (k1.x >= 0) + (k1.y >= 0) + (k1.z >= 0) + (k1.w >= 0);
+        // ---- kept leaves: every lane appends its own pieces in slot order; chunks reserved by one vote
+        if(anybig == 0) {
+            piece_reserve(__popc(keepbits), mycnt, nch_alloc, s_ctab, Q, group, lane);
+            while(keepbits) {
+                const int k = __ffs(keepbits) - 1; keepbits &= keepbits - 1;
+                const int4 M = s_ent.M[k];
+                // every particle of a kept leaf is within search distance + len of the target (cull_node)
+                const double hn = s_ent.H[k], len = s_ent.B[k].w;
+                const double r = ((SYM && hn > h) ? hn : h) + len;
+                myreach = r > myreach ? r : myreach;
+                piece_append<true>(PIECE(M.x, M.y), mycnt, mylast, nch_alloc, s_ctab, Q, lane);
+            }
+            __syncwarp();
+        } else
+        while(__any_sync(0xffffffffu, keepbits != 0)) {         // a leaf at the key-depth limit holds more than 8 particles
+            const bool want = keepbits != 0;
+            int4 M = make_int4(0, 0, 0, 0);
+            if(want) {
+                const int k = __ffs(keepbits) - 1; keepbits &= keepbits - 1;
+                M = s_ent.M[k];
+                const double hn = s_ent.H[k], len = s_ent.B[k].w;
+                const double r = ((SYM && hn > h) ? hn : h) + len;
+                myreach = r > myreach ? r : myreach;
+            }
+            const int maxc = (int) __reduce_max_sync(0xffffffffu, (unsigned) (want ? M.y : 0));
+            for(int o = 0; o < maxc; o += 8) {
+                const int c = M.y - o < 8 ? M.y - o : 8;
+                piece_push<true>(want && o < M.y, PIECE(M.x + o, c > 0 ? c : 0), mycnt, mylast, nch_alloc, s_ctab, Q, group, lane);
+            }
         }
-        int off = mynch;
-#pragma unroll
-        for(int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if(lane >= o) off += v; }
-        const int total = __shfl_sync(0xffffffffu, off, 31);
-        if(mynch) {
-            int w = sp + off - mynch;
-            const int kids[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-#pragma unroll
-            for(int c = 0; c < 8; c++) if(kids[c] >= 0) { s_stk_node[w] = kids[c]; s_stk_mask[w] = myopeners; w++; }
+        // ---- lane-parallel: push the kept internal nodes, in slot order
+        {
+            const unsigned pushers = __ballot_sync(0xffffffffu, myopeners != 0);
+            const int np_ = __popc(pushers);
+            if(sp + np_ > SPH_WALK_STACK) { if(lane == 0) atomicOr(Q.ctl + 1, 4); break; }
+            if(myopeners) {
+                const int w = sp + __popc(pushers & ((1u << lane) - 1u));
+                s_stk_node[w] = mynode; s_stk_mask[w] = myopeners;
+            }
+            sp += np_;
         }
-        sp += total;
         __syncwarp();
     }
     piece_finish<true>(valid, tslot, mycnt, mylast, nch_alloc, s_ctab, Q, lane);
@@ -294,7 +343,7 @@ __global__ void __launch_bounds__(128, 4)
 k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restrict__ sidx,
                     const double4 *__restrict__ spart, const double2 *__restrict__ spart_xy, const double2 *__restrict__ spart_zm,
                     const double *__restrict__ reach,
-                    const double4 *__restrict__ svel, SphDev S, int update_hsml, int DoEgy,
+                    const double4 *__restrict__ svel, SphDev S, int update_hsml, int DoEgy, int tpw,
                     const unsigned *__restrict__ pool, const int *__restrict__ chunk_tab, int maxch, const int *__restrict__ piece_cnt, int sentinel,
                     double *__restrict__ hsml, double *__restrict__ left, double *__restrict__ right,
                     double *__restrict__ density, double *__restrict__ egy, double *__restrict__ dhsmlfac,
@@ -306,9 +355,9 @@ k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restri
     int *s_ctab = s_ctab_dyn + (threadIdx.x >> 5) * maxch;
     const int lane = threadIdx.x & 31;
     const int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int tslot = group * 32 + lane;
-    const bool valid = tslot < nt;
-    if(group * 32 >= nt) return;            // warp-uniform
+    const int tslot = group * tpw + lane;   // the walk's assignment: tpw targets per warp
+    const bool valid = lane < tpw && tslot < nt;
+    if((int64_t) group * tpw >= nt) return; // warp-uniform
     int me = -1, mycnt = 0;
     double4 pm = make_double4(0, 0, 0, 0), vm = pm;
     double h = 1, myreach = 0;
@@ -331,7 +380,7 @@ k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restri
 #pragma unroll
     for(int q = 0; q < NSUM_DENS; q++) acc[q] = 0;
     int nint = 0;
-    for(int t = 0; t < 32; t++) {
+    for(int t = 0; t < tpw; t++) {
         const int ntp = __shfl_sync(0xffffffffu, mycnt, t);
         if(ntp == 0) continue;                          // warp-uniform
         const double tx = __shfl_sync(0xffffffffu, pm.x, t), ty = __shfl_sync(0xffffffffu, pm.y, t), tz = __shfl_sync(0xffffffffu, pm.z, t);
@@ -937,8 +986,13 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
         const int *tg = nullptr;
         int nt = np;
         if(int rc = sph_first_targets(E, np, tg_other, tg_next, &tg, &nt)) return rc;
+        int nt0 = nt;
         for(int pass = 0; nt > 0; pass++) {
-            const int64_t nwarps = (nt + 31) / 32;
+            // targets per warp: the unconverged targets of the later passes are sparse in space (k_sph_walk)
+            static const int force_tpw = getenv("B200_SPH_TPW") ? atoi(getenv("B200_SPH_TPW")) : 0;
+            int tpw = (double) nt >= 0.5 * nt0 ? 32 : ((double) nt >= 0.02 * nt0 ? 8 : 1);
+            if(force_tpw == 1 || force_tpw == 8 || force_tpw == 32) tpw = force_tpw;
+            const int64_t nwarps = (nt + tpw - 1) / tpw;
             const unsigned nb = (unsigned) ((nwarps * 32 + 127) / 128);
             CK(E->walk_partial.ensure((size_t) nwarps * 32 * 4));
             piece_pool_reset(E);
@@ -947,7 +1001,7 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
                 if(int rc = piece_pool_begin(E, nwarps, &Q)) return rc;
                 CK(piece_set_smem(k_sph_walk<false>, piece_ctab_bytes(E, WALK_WARPS)));
                 k_sph_walk<false><<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>((const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, (const int4 *) E->nodeK.p,
-                    E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, tg, nt, E->s_hsml.p, S, Q, E->walk_partial.p);
+                    E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, tg, nt, tpw, E->s_hsml.p, S, Q, E->walk_partial.p);
                 CKL(E);
                 bool retry = false;
                 if(int rc = piece_pool_check(E, nwarps, &retry, attempt)) return rc;
@@ -956,7 +1010,7 @@ int sph_density(Engine *E, const b200_sph_params *p, int update_hsml, int DoEgy,
             CK(piece_set_smem(k_sph_density_pairs, piece_ctab_bytes(E, WALK_WARPS)));
             k_sph_density_pairs<<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>(tg, nt, E->sidx.p, (const double4 *) E->spart.p,
                 (const double2 *) E->spart_xy.p, (const double2 *) E->spart_zm.p, E->walk_partial.p, (const double4 *) E->s_svel.p,
-                S, update_hsml, DoEgy, E->walk_pool.p, E->walk_chunktab.p, E->walk_maxch, E->walk_cnt.p, 0,
+                S, update_hsml, DoEgy, tpw, E->walk_pool.p, E->walk_chunktab.p, E->walk_maxch, E->walk_cnt.p, 0,
                 E->s_hsml.p, E->s_left.p, E->s_right.p, E->s_density.p, E->s_egy.p, E->s_dhsmlfac.p, E->s_divvel.p, E->s_curlvel.p,
                 E->s_dthsml.p, E->s_numngb.p, E->s_gradrho.p, E->s_nint.p, E->s_niter.p, E->walk_flags.p, E->scratch_i.p + 12);
             CKL(E);
@@ -1025,7 +1079,7 @@ int sph_hydro(Engine *E, const b200_sph_params *p, double *d_acc, double *d_dte,
             if(int rc = piece_pool_begin(E, nwarps, &Q)) return rc;
             CK(piece_set_smem(k_sph_walk<true>, piece_ctab_bytes(E, WALK_WARPS)));
             k_sph_walk<true><<<nb, 128, piece_ctab_bytes(E, WALK_WARPS), E->stream>>>((const double4 *) E->nodeB.p, (const int4 *) E->nodeC.p, (const int4 *) E->nodeK.p,
-                E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, tg, nt, E->s_hsml.p, S, Q, E->walk_partial.p);
+                E->nodeH.p, (const double4 *) E->spart.p, E->sidx.p, tg, nt, 32, E->s_hsml.p, S, Q, E->walk_partial.p);
             CKL(E);
             bool retry = false;
             if(int rc = piece_pool_check(E, nwarps, &retry, attempt)) return rc;

@@ -1,11 +1,10 @@
 #!/bin/bash
-# GPU parity tests + the bench's hydro section (SPH density / hydro timings)
+# SPH GPU tests + the density / hydro timing probe.  args: values of B200_SPH_TPW to try (0 = adaptive)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 600 python bench.py --no-cpu --steps 2 > gpurun_out/bench_quick.json 2>/dev/null
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/bench_quick.json").read().strip().splitlines()[-1])
-h = d["hydro"]
-print(d["ms_per_step"], "density", h["density_ms"], "hydro", h["hydro_ms"], h["density_passes_mean"], h["neighbours_mean"])
-PY
+{
+timeout 900 python -m pytest tests/test_sph.py tests/test_dropin.py -m gpu -x -q 2>&1 | tail -3
+for v in "$@"; do
+  export B200_SPH_TPW=$v
+  echo "== tpw $v"; timeout 600 python tools/sph_prof.py 128 2 2>&1 | tail -2
+done
+} 2>&1 | tee -a gpurun_out/r2_sph.log
