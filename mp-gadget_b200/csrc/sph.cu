@@ -339,7 +339,10 @@ k_sph_walk(const double4 *__restrict__ nodeB, const int4 *__restrict__ nodeC, co
 
 // density_ngbiter over the piece lists + density_postprocess + density_check_neighbours for the
 // targets of this pass.  State (Hsml, Left, Right, niter) is indexed by particle index.
-__global__ void __launch_bounds__(128, 4)
+#ifndef SPH_DENS_MINB
+#define SPH_DENS_MINB 6
+#endif
+__global__ void __launch_bounds__(128, SPH_DENS_MINB)
 k_sph_density_pairs(const int *__restrict__ targets, int nt, const int *__restrict__ sidx,
                     const double4 *__restrict__ spart, const double2 *__restrict__ spart_xy, const double2 *__restrict__ spart_zm,
                     const double *__restrict__ reach,
@@ -632,7 +635,10 @@ k_sph_gather_hydro(int np, const int *__restrict__ sidx, SphDev S, const double 
 // in shared memory and evaluated 32 at a time, so the long pair arithmetic runs on full warps.  Screening and
 // evaluation share ONE loop body (a second inlined copy of the pair arithmetic doubled the kernel and made it
 // instruction-fetch bound: ncu "no instruction" stalls, profiles/r01_sph_hydro_pairs_ncu_summary.txt).
-__global__ void __launch_bounds__(128, 4)
+#ifndef SPH_HYDRO_MINB
+#define SPH_HYDRO_MINB 5
+#endif
+__global__ void __launch_bounds__(128, SPH_HYDRO_MINB)
 k_sph_hydro_pairs(const int *__restrict__ targets, int nt, const int *__restrict__ sidx,
                   const double4 *__restrict__ spart, const double2 *__restrict__ spart_xy, const double2 *__restrict__ spart_zm,
                   const double *__restrict__ reach, const double4 *__restrict__ svel,
