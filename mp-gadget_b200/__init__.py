@@ -386,6 +386,11 @@ class Engine:
         self._ck(self.L.b200_domain_peano_keys(self.ctx, C.c_double(box), _p(keys)))
         return keys[:self.n]
 
+    def domain_set_topnodes(self, top):
+        """DomainDecomp::TopNodes as (Daughter, StartKey, Shift, Leaf): the forced top tree of force_tree_build(toplevel_depth=-1)"""
+        a = [_c(top[0], np.int32), _c(top[1], np.uint64), _c(top[2], np.int32), _c(top[3], np.int32)]
+        self._ck(self.L.b200_domain_set_topnodes(self.ctx, C.c_int32(len(a[0])), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3])))
+
     def topleaf(self, daughter, startkey, shift, leaf):
         """domain_get_topleaf (domain.h:71-78) of every particle over TopNodes given as arrays (after peano_keys)"""
         a = [_c(daughter, np.int32), _c(startkey, np.uint64), _c(shift, np.int32), _c(leaf, np.int32)]

@@ -95,7 +95,7 @@ k_domain_leaf_counts(int64_t n, const int *__restrict__ topleaf, const uint8_t *
     if(l >= 0 && l < nleaf) atomicAdd(&counts[l], 1ull);
 }
 
-static int domain_need_tables(Engine *E)
+int domain_need_tables(Engine *E)
 {
     if(E->dk_tab.p) return 0;
     uint8_t tab[768];
@@ -411,7 +411,7 @@ static void number_leaves(const Node *t, int no, int32_t *next, int32_t *leaf)  
 
 void domain_release(Engine *E)
 {
-    E->dk_keys.release(); E->dk_tab.release(); E->dk_daughter.release(); E->dk_startkey.release(); E->dk_shift.release(); E->dk_leaf.release(); E->dk_topleaf.release(); E->dk_counts.release(); E->dk_sample.release(); E->dk_xflag.release(); E->dk_xlist.release(); E->dk_iota.release(); E->dk_task.release();
+    E->b_top.release(); E->dk_keys.release(); E->dk_tab.release(); E->dk_daughter.release(); E->dk_startkey.release(); E->dk_shift.release(); E->dk_leaf.release(); E->dk_topleaf.release(); E->dk_counts.release(); E->dk_sample.release(); E->dk_xflag.release(); E->dk_xlist.release(); E->dk_iota.release(); E->dk_task.release();
 }
 
 } // namespace b200

@@ -178,6 +178,7 @@ struct Engine {
     DevBuf<uint8_t> dk_xflag;
     DevBuf<unsigned long long> dk_counts, dk_sample;
     int dk_ntop = 0;
+    DevBuf<int> b_top;                                 // tree build below the domain's top nodes: top node | curve state << 24 per cell
     int64_t dk_keys_n = -1, dk_topleaf_n = -1;
 
     Timer timers[T_COUNT];
@@ -240,6 +241,7 @@ int sph_set_state(Engine *E, const double *density, const double *egy, const dou
 // step loop (steploop.cu), domain keys (domain_keys.cu)
 void step_release(Engine *E);
 void domain_release(Engine *E);
+int domain_need_tables(Engine *E);    // domain_keys.cu: the curve's state machine in dk_tab
 
 // walk (tree_walk.cu)
 int walk_init_tables(Engine *E);

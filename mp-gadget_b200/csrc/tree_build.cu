@@ -34,8 +34,17 @@ __global__ void __launch_bounds__(256)
 k_tree_keys(const double *__restrict__ pos, const uint8_t *__restrict__ type,
             const uint8_t *__restrict__ flags, const int *__restrict__ active, int64_t nin,
             double c0, double len0, double box, int topdepth, int mask, unsigned long long *__restrict__ keys,
-            int *__restrict__ idx, int *__restrict__ nvalid)
+            int *__restrict__ idx, int *__restrict__ nvalid,
+            // an arbitrary domain top tree instead of a uniform depth (NULL = uniform): TopNodes[].Daughter / StartKey / Shift
+            // and the state machine of the Peano-Hilbert curve (domain_keys.cu)
+            const int *__restrict__ top_daughter, const unsigned long long *__restrict__ top_startkey,
+            const int *__restrict__ top_shift, const uint8_t *__restrict__ ph_tab)
 {
+    __shared__ uint8_t s_tab[768];
+    if(top_daughter) {
+        for(int k = threadIdx.x; k < 768; k += blockDim.x) s_tab[k] = ph_tab[k];
+        __syncthreads();
+    }
     const int64_t j = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     bool ok = false;
     if(j < nin) {
@@ -58,6 +67,21 @@ k_tree_keys(const double *__restrict__ pos, const uint8_t *__restrict__ type,
             const int ix = (int) ((x + box / 2000) * DomainFac);
             const int iy = (int) ((y + box / 2000) * DomainFac);
             const int iz = (int) ((z + box / 2000) * DomainFac);
+            if(top_daughter) {
+                // P[i].TopLeaf = domain_get_topleaf(PEANO(Pos)) (domain.h:71-78, peano.h:15-21): the particle follows the
+                // lattice down to the level of its top leaf (forcetree.c:819-823)
+                unsigned long long pk = 0;
+                int st = 0;
+#pragma unroll 1
+                for(int bit = 20; bit >= 0; bit--) {
+                    const int pix = (((ix >> bit) & 1) << 2) | (((iy >> bit) & 1) << 1) | ((iz >> bit) & 1);
+                    pk = (pk << 3) | s_tab[st * 8 + pix];
+                    st = s_tab[384 + st * 8 + pix];
+                }
+                int no = 0;
+                while(top_daughter[no] >= 0) no = top_daughter[no] + (int) ((pk - top_startkey[no]) >> (top_shift[no] - 3));
+                topdepth = (63 - top_shift[no]) / 3;
+            }
 #pragma unroll 1
             for(int l = 0; l < KEY_LEVELS; l++) {
                 const double lenhalf = 0.25 * len;
@@ -86,12 +110,17 @@ __global__ void __launch_bounds__(128)
 k_tree_split(const unsigned long long *__restrict__ keys, int first, int last, int level,
              int topdepth, int cap, int *__restrict__ counters,
              int *__restrict__ b_start, int *__restrict__ b_count, int *__restrict__ b_father,
-             int *__restrict__ b_firstchild, int *__restrict__ b_nchild, double *__restrict__ b_center)
+             int *__restrict__ b_firstchild, int *__restrict__ b_nchild, double *__restrict__ b_center,
+             // arbitrary top tree (NULL = uniform depth): b_top[node] = top node | curve state << 24, or -1 below the top leaves
+             int *__restrict__ b_top, const int *__restrict__ top_daughter, const uint8_t *__restrict__ ph_tab)
 {
     const int node = first + blockIdx.x * blockDim.x + threadIdx.x;
     if(node >= last) return;
     const int s = b_start[node], cnt = b_count[node];
-    const bool forced = level < topdepth;
+    const int mytop = top_daughter ? b_top[node] : -1;
+    const int mydau = mytop >= 0 ? top_daughter[mytop & 0xffffff] : -1;
+    // force_create_node_for_topnode forcetree.c:869-934: a cell whose top node has daughters gets all eight children
+    const bool forced = top_daughter ? mydau >= 0 : level < topdepth;
     bool internal = forced || cnt > LEAFCAP;
     if(internal && level >= KEY_LEVELS) {
         internal = false;
@@ -110,14 +139,14 @@ k_tree_split(const unsigned long long *__restrict__ keys, int first, int last, i
         }
         bound[d] = lo;
     }
-    const bool keep_empty = (level + 1) <= topdepth;
+    const bool keep_empty = top_daughter ? forced : (level + 1) <= topdepth;
     int nch = 0;
     for(int d = 0; d < 8; d++) nch += (keep_empty || bound[d + 1] > bound[d]) ? 1 : 0;
     // Forced top-tree levels are complete (every cell has 8 children), so their
     // children go to fixed slots: cell (level l, Morton index m) sits at
     // (8^l - 1)/7 + m.  b200_tree_top_get/set rely on this.
     int base;
-    if(forced) {
+    if(forced && !top_daughter) {
         base = last + 8 * (node - first);
         atomicMax(&counters[0], last + 8 * (last - first));
     } else {
@@ -141,12 +170,21 @@ k_tree_split(const unsigned long long *__restrict__ keys, int first, int last, i
         b_center[4 * (size_t) ch + 1] = (d & 2) ? cy + lenhalf : cy - lenhalf;
         b_center[4 * (size_t) ch + 2] = (d & 4) ? cz + lenhalf : cz - lenhalf;
         b_center[4 * (size_t) ch + 3] = 0.5 * len;
+        if(top_daughter) {
+            int ctop = -1;
+            if(forced) {        // the daughter covering octant d is found through the curve (forcetree.c:886,904)
+                const int st = mytop >> 24, pix = ((d & 1) << 2) | (((d >> 1) & 1) << 1) | ((d >> 2) & 1);
+                ctop = (mydau + ph_tab[st * 8 + pix]) | ((int) ph_tab[384 + st * 8 + pix] << 24);
+            }
+            b_top[ch] = ctop;
+        }
     }
 }
 
 __global__ void k_tree_root(int np, double c0, double len0, int *b_start, int *b_count, int *b_father,
-                            double *b_center, int *counters)
+                            double *b_center, int *counters, int *b_top)
 {
+    if(b_top) b_top[0] = 0;
     b_start[0] = 0; b_count[0] = np; b_father[0] = -1;
     b_center[0] = c0; b_center[1] = c0; b_center[2] = c0; b_center[3] = len0;
     counters[0] = 1; counters[1] = 0; counters[2] = 0;
@@ -276,7 +314,17 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
 {
     E->tree_valid = false;
     if(!(Box > 0)) return failmsg(E, "b200_tree_build: BoxSize must be positive");
-    if(toplevel_depth < 0 || toplevel_depth > 8) return failmsg(E, "b200_tree_build: toplevel_depth out of range [0,8]");
+    // toplevel_depth = -1: the forced top tree is the domain's (b200_domain_set_topnodes), of any shape
+    const bool topn = toplevel_depth == -1;
+    if(topn) {
+        if(E->dk_ntop == 0) return failmsg(E, "b200_tree_build: toplevel_depth = -1 needs b200_domain_set_topnodes first");
+        if(int rc = domain_need_tables(E)) return rc;
+    }
+    else if(toplevel_depth < 0 || toplevel_depth > 8) return failmsg(E, "b200_tree_build: toplevel_depth out of range [0,8] (or -1: the domain's top nodes)");
+    const int *t_dau = topn ? E->dk_daughter.p : nullptr;
+    const unsigned long long *t_key = topn ? E->dk_startkey.p : nullptr;
+    const int *t_shift = topn ? E->dk_shift.p : nullptr;
+    const uint8_t *t_tab = topn ? E->dk_tab.p : nullptr;
     const int64_t nin = d_active ? nactive : E->n;
     if(nin >= (1ll << 30)) return failmsg(E, "b200_tree_build: too many particles for 32-bit node indices");
     const double c0 = Box / 2., len0 = Box * 1.001;       // forcetree.c:662-664
@@ -291,7 +339,8 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
     timer_start(E, T_TREE_KEYS);
     if(nin > 0) {
         k_tree_keys<<<(unsigned) ((nin + 255) / 256), 256, 0, E->stream>>>(E->pos.p, E->type.p, E->flags.p, d_active, nin,
-                                                                         c0, len0, Box, toplevel_depth, mask, E->keys_alt.p, E->sidx_alt.p, d_cnt + 4);
+                                                                         c0, len0, Box, toplevel_depth, mask, E->keys_alt.p, E->sidx_alt.p, d_cnt + 4,
+                                                                         t_dau, t_key, t_shift, t_tab);
         CKL(E);
     }
     timer_stop(E, T_TREE_KEYS);
@@ -314,6 +363,7 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
     timer_start(E, T_TREE_NODES);
     int cap = (int) (np * 0.75) + 4096;
     { int64_t top = 1; for(int l = 0; l < toplevel_depth; l++) top *= 8; cap += (int) (top * 2.5); }
+    if(topn) cap += 2 * E->dk_ntop;
     std::vector<int> lvl;       // level offsets in BFS numbering
     int nn = 0, overfull = 0;
     for(int attempt = 0; attempt < 8; attempt++) {
@@ -321,7 +371,8 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
         CK(E->b_firstchild.ensure(cap)); CK(E->b_nchild.ensure(cap));
         CK(E->b_size.ensure(cap)); CK(E->b_dfs.ensure(cap));
         CK(E->b_center.ensure(4 * (size_t) cap));
-        k_tree_root<<<1, 1, 0, E->stream>>>(np, c0, len0, E->b_start.p, E->b_count.p, E->b_father.p, E->b_center.p, d_cnt);
+        if(topn) CK(E->b_top.ensure(cap));
+        k_tree_root<<<1, 1, 0, E->stream>>>(np, c0, len0, E->b_start.p, E->b_count.p, E->b_father.p, E->b_center.p, d_cnt, topn ? E->b_top.p : nullptr);
         CKL(E);
         lvl.clear(); lvl.push_back(0); lvl.push_back(1);
         int h[3] = {1, 0, 0};
@@ -330,7 +381,8 @@ int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t
             if(last == first) break;
             k_tree_split<<<(last - first + 127) / 128, 128, 0, E->stream>>>(E->keys.p, first, last, level, toplevel_depth, cap, d_cnt,
                                                                         E->b_start.p, E->b_count.p, E->b_father.p,
-                                                                        E->b_firstchild.p, E->b_nchild.p, E->b_center.p);
+                                                                        E->b_firstchild.p, E->b_nchild.p, E->b_center.p,
+                                                                        topn ? E->b_top.p : nullptr, t_dau, t_tab);
             CKL(E);
             CK(cudaMemcpyAsync(h, d_cnt, 3 * sizeof(int), cudaMemcpyDeviceToHost, E->stream));
             CK(cudaStreamSynchronize(E->stream));

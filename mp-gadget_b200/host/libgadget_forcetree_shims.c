@@ -24,6 +24,7 @@
 #include <libgadget/timestep.h>
 #include <libgadget/walltime.h>
 
+void b200_shim_topnodes_from_domain(const DomainDecomp *ddecomp);
 static double TreeAllocFactor;
 void init_forcetree_params(const double treeallocfactor) { TreeAllocFactor = treeallocfactor; }     /* forcetree.c:30-35 */
 
@@ -49,6 +50,7 @@ static ForceTree describe_tree(int mask, DomainDecomp *ddecomp, const ActivePart
     tree.firstnode = PartManager->MaxPart;
     tree.lastnode = tree.firstnode;
     tree.numnodes = 0;                       /* no host nodes */
+    b200_shim_topnodes_from_domain(ddecomp);             /* the device tree is built below these (b200_tree_build, toplevel_depth = -1) */
     tree.TopLeaves = ddecomp->TopLeaves;
     tree.NTopLeaves = ddecomp->NTopLeaves;
     MPI_Comm_rank(MPI_COMM_WORLD, &tree.ThisTask);

@@ -38,6 +38,7 @@
 
 /* the context shared by all shim files (libgadget_shim_ctx.c) */
 b200_ctx *b200_shim_context(void);
+void b200_shim_topnodes_from_tree(const ForceTree *tree);
 #define b200_shim_ctx b200_shim_context
 #define B200_CK(call) do { if((call) != 0) endrun(1, "b200: %s\n", b200_last_error(b200_shim_context())); } while(0)
 
@@ -87,7 +88,9 @@ void grav_short_tree(const ActiveParticles *act, PetaPM *pm, ForceTree *tree, My
 
     B200_CK(b200_pm_init(ctx, tree->BoxSize, pm->Asmth, pm->Nmesh, pm->G));
     B200_CK(b200_set_particles_aos(ctx, P, n, &lay));
-    B200_CK(b200_tree_build(ctx, tree->BoxSize, tree->mask, act->ActiveParticle, act->NumActiveParticle, 0, NULL));
+    /* the same node set as force_tree_build: below the domain's top nodes (forcetree.c:654-687) */
+    b200_shim_topnodes_from_tree(tree);
+    B200_CK(b200_tree_build(ctx, tree->BoxSize, tree->mask, act->ActiveParticle, act->NumActiveParticle, -1, NULL));
 
     b200_gravshort_params par;
     memset(&par, 0, sizeof(par));

@@ -42,6 +42,7 @@
 
 /* the context shared by all shim files (libgadget_shim_ctx.c) */
 b200_ctx *b200_shim_context(void);
+void b200_shim_topnodes_from_tree(const ForceTree *tree);
 #define sph_ctx b200_shim_context
 #define B200_CK(call) do { if((call) != 0) endrun(1, "b200: %s\n", b200_last_error(b200_shim_context())); } while(0)
 
@@ -222,7 +223,8 @@ void density(const ActiveParticles *act, int update_hsml, int DoEgyDensity, int 
     if(sizeof(struct particle_data) != (size_t) lay.stride)
         endrun(2, "b200: struct particle_data is %lu bytes, the shim was built for %ld\n", sizeof(struct particle_data), (long) lay.stride);
     B200_CK(b200_set_particles_aos(ctx, P, n, &lay));
-    B200_CK(b200_tree_build(ctx, tree->BoxSize, GASMASK, NULL, 0, 0, NULL));       /* force_tree_rebuild_mask(GASMASK), run.c:466 */
+    b200_shim_topnodes_from_tree(tree);
+    B200_CK(b200_tree_build(ctx, tree->BoxSize, GASMASK, NULL, 0, -1, NULL));      /* force_tree_rebuild_mask(GASMASK), run.c:466 */
     ShimNumPart = n; ShimDoEgy = DoEgyDensity;
 
     const size_t m = (size_t) (n > 0 ? n : 1);

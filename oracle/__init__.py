@@ -69,7 +69,7 @@ def _c(a, dt):
 class OracleTree:
     """oracle_tree_build wrapper; .nodes is a structured numpy view in DFS order."""
 
-    def __init__(self, pos, mass, box, type=None, hsml=None, mask=63, active=None, toplevel_depth=0):
+    def __init__(self, pos, mass, box, type=None, hsml=None, mask=63, active=None, toplevel_depth=0, top_daughter=None):
         self.pos = _c(pos, np.float64)
         self.mass = _c(mass, np.float32)
         self.type = _c(type, np.uint8)
@@ -78,9 +78,12 @@ class OracleTree:
         self.n = len(self.mass)
         self.t = Tree()
         na = 0 if self.active is None else len(self.active)
-        rc = lib().oracle_tree_build(C.byref(self.t), _p(self.pos), _p(self.mass), _p(self.type),
-                                     _p(self.hsml), C.c_int64(self.n), C.c_double(box), C.c_int(mask),
-                                     _p(self.active), C.c_int64(na), C.c_int(toplevel_depth))
+        # top_daughter: the Daughter column of an arbitrary domain top tree (forcetree.c:654-687) instead of a uniform depth
+        self.top_daughter = _c(top_daughter, np.int32)
+        rc = lib().oracle_tree_build_top(C.byref(self.t), _p(self.pos), _p(self.mass), _p(self.type),
+                                         _p(self.hsml), C.c_int64(self.n), C.c_double(box), C.c_int(mask),
+                                         _p(self.active), C.c_int64(na), C.c_int(toplevel_depth),
+                                         _p(self.top_daughter), C.c_int32(0 if self.top_daughter is None else len(self.top_daughter)))
         if rc:
             raise RuntimeError("oracle_tree_build failed (coincident particles?)")
         buf = (Node * self.t.numnodes).from_address(C.addressof(self.t.nodes.contents))

@@ -53,6 +53,10 @@ typedef struct oracle_tree {
 int oracle_tree_build(oracle_tree *t, const double *pos, const float *mass,
                       const uint8_t *type, const double *hsml, int64_t n, double BoxSize,
                       int mask, const int32_t *active, int64_t nactive, int toplevel_depth);
+int oracle_tree_build_top(oracle_tree *t, const double *pos, const float *mass,
+                          const uint8_t *type, const double *hsml, int64_t n, double BoxSize,
+                          int mask, const int32_t *active, int64_t nactive, int toplevel_depth,
+                          const int32_t *top_daughter, int32_t ntop);
 void oracle_tree_free(oracle_tree *t);
 
 typedef struct oracle_gravshort_params {

@@ -29,6 +29,9 @@ typedef struct {
     const double *hsml;
     int32_t *scratch;
     int toplevel_depth;
+    /* an arbitrary domain top tree (DomainDecomp::TopNodes, domain.h:20-33) instead of a uniform depth: Daughter[] */
+    const int32_t *top_daughter;
+    int32_t ntop;
     int failed;
     double BoxSize;
 } builder;
@@ -41,9 +44,9 @@ typedef struct {
  * except for positions within rounding of a cell boundary; to follow the
  * reference there too, top-tree levels use the lattice bits.  Below the top
  * leaves it is get_subnode, forcetree.c:278-284 (strict >). */
-static inline int octant_of(const builder *b, const double *x, const double c[3], int level)
+static inline int octant_of(const builder *b, const double *x, const double c[3], int level, int in_top)
 {
-    if(level < b->toplevel_depth) {
+    if(in_top) {
         const double DomainFac = 1.0 / (b->BoxSize * 1.001) * (((uint64_t) 1) << 21);
         int s = 0;
         for(int j = 0; j < 3; j++) {
@@ -92,8 +95,12 @@ static void leaf_moments(builder *b, oracle_node *nd)
 /* Build the subtree holding idx[0..cnt) rooted at a cell (center c, side len).
  * Child geometry: init_internal_node forcetree.c:302-320; octant choice:
  * get_subnode forcetree.c:278-284 (strict >). Returns the node's DFS index. */
+uint64_t oracle_peano_key(int x, int y, int z, int bits);      /* oracle_domain.c */
+
+/* topnode: index of the cell's node in the domain top tree, -1 below the top leaves (and always in uniform-depth
+ * mode); cx[3]: the cell's integer coordinates at its level (force_create_node_for_topnode forcetree.c:869-934). */
 static int64_t build_cell(builder *b, int32_t *idx, int64_t cnt, const double c[3], double len,
-                          int level, int64_t father)
+                          int level, int64_t father, int32_t topnode, const int cx[3])
 {
     const int64_t me = new_node(b);
     {
@@ -103,11 +110,11 @@ static int64_t build_cell(builder *b, int32_t *idx, int64_t cnt, const double c[
         nd->firstchild = -1;
         nd->len = len;
         nd->level = level;
-        nd->toplevel = level <= b->toplevel_depth;
+        nd->toplevel = b->top_daughter ? topnode >= 0 : level <= b->toplevel_depth;
         for(int j = 0; j < 3; j++) nd->center[j] = c[j];
         for(int k = 0; k < 8; k++) nd->part[k] = -1;
     }
-    const int forced_internal = level < b->toplevel_depth;
+    const int forced_internal = b->top_daughter ? (topnode >= 0 && b->top_daughter[topnode] >= 0) : level < b->toplevel_depth;
     if(cnt <= LEAFCAP && !forced_internal) {
         oracle_node *nd = &b->nodes[me];
         nd->nocc = (int32_t) cnt;
@@ -121,7 +128,7 @@ static int64_t build_cell(builder *b, int32_t *idx, int64_t cnt, const double c[
     int64_t count[8] = {0}, start[9];
     for(int64_t k = 0; k < cnt; k++) {
         const double *x = &b->pos[3 * (int64_t) idx[k]];
-        const int s = octant_of(b, x, c, level);
+        const int s = octant_of(b, x, c, level, forced_internal);
         count[s]++;
     }
     start[0] = 0;
@@ -131,7 +138,7 @@ static int64_t build_cell(builder *b, int32_t *idx, int64_t cnt, const double c[
         for(int s = 0; s < 8; s++) fill[s] = start[s];
         for(int64_t k = 0; k < cnt; k++) {
             const double *x = &b->pos[3 * (int64_t) idx[k]];
-            const int s = octant_of(b, x, c, level);
+            const int s = octant_of(b, x, c, level, forced_internal);
             b->scratch[fill[s]++] = idx[k];
         }
         memcpy(idx, b->scratch, cnt * sizeof(int32_t));
@@ -141,13 +148,21 @@ static int64_t build_cell(builder *b, int32_t *idx, int64_t cnt, const double c[
     int64_t kids[8]; int nk = 0;
     for(int s = 0; s < 8; s++) {
         /* pruning of empty non-top-level children: forcetree.c:1028-1049 */
-        if(count[s] == 0 && !(level + 1 <= b->toplevel_depth)) continue;
+        if(count[s] == 0 && !forced_internal) continue;
         double cc[3];
         for(int j = 0; j < 3; j++) {
             const int sign = (s & (1 << j)) ? 1 : -1;
             cc[j] = c[j] + sign * lenhalf;
         }
-        kids[nk++] = build_cell(b, idx + start[s], count[s], cc, 0.5 * len, level + 1, me);
+        int32_t ctop = -1;
+        const int ccx[3] = {2 * cx[0] + (s & 1), 2 * cx[1] + ((s >> 1) & 1), 2 * cx[2] + ((s >> 2) & 1)};
+        if(b->top_daughter && forced_internal) {
+            /* forcetree.c:886,904: the daughter that covers this octant is found through the curve */
+            const int sub = (int) (7 & oracle_peano_key(ccx[0], ccx[1], ccx[2], level + 1));
+            ctop = b->top_daughter[topnode] + sub;
+            if(ctop >= b->ntop) { b->failed = 1; ctop = -1; }
+        }
+        kids[nk++] = build_cell(b, idx + start[s], count[s], cc, 0.5 * len, level + 1, me, ctop, ccx);
     }
     /* moments of an internal node: forcetree.c:1081-1101 (children in octant order) */
     oracle_node *nd = &b->nodes[me];
@@ -183,6 +198,16 @@ int oracle_tree_build(oracle_tree *t, const double *pos, const float *mass,
                       const uint8_t *type, const double *hsml, int64_t n, double BoxSize,
                       int mask, const int32_t *active, int64_t nactive, int toplevel_depth)
 {
+    return oracle_tree_build_top(t, pos, mass, type, hsml, n, BoxSize, mask, active, nactive, toplevel_depth, NULL, 0);
+}
+
+/* The same with the forced top tree given as the Daughter[] column of DomainDecomp::TopNodes (force_tree_create_topnodes,
+ * forcetree.c:654-687): a cell is forced to be internal, with all eight children, iff its top node has daughters. */
+int oracle_tree_build_top(oracle_tree *t, const double *pos, const float *mass,
+                          const uint8_t *type, const double *hsml, int64_t n, double BoxSize,
+                          int mask, const int32_t *active, int64_t nactive, int toplevel_depth,
+                          const int32_t *top_daughter, int32_t ntop)
+{
     builder b;
     memset(&b, 0, sizeof(b));
     b.pos = pos; b.mass = mass; b.type = type; b.hsml = hsml;
@@ -201,7 +226,9 @@ int oracle_tree_build(oracle_tree *t, const double *pos, const float *mass,
     }
     /* root: force_tree_create_topnodes forcetree.c:662-664 */
     const double c[3] = {BoxSize / 2., BoxSize / 2., BoxSize / 2.};
-    build_cell(&b, idx, cnt, c, BoxSize * 1.001, 0, -1);
+    const int cx0[3] = {0, 0, 0};
+    b.top_daughter = top_daughter; b.ntop = ntop;
+    build_cell(&b, idx, cnt, c, BoxSize * 1.001, 0, -1, top_daughter ? 0 : -1, cx0);
     thread_siblings(b.nodes, b.used);
     free(idx); free(b.scratch);
     t->nodes = b.nodes;

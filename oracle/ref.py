@@ -50,6 +50,19 @@ class Ref:
         self.L.ref_tree_build(C.c_int64(self.n), _p(pos), _p(mass), _p(type), _p(oldacc), C.c_double(box), C.c_int(topdepth))
         return int(self.L.ref_numnodes())
 
+    def tree_build_top(self, pos, mass, box, top, type=None, oldacc=None):
+        """force_tree_full below an arbitrary domain top tree: top = (Daughter, StartKey, Shift, Leaf) of DomainDecomp::TopNodes"""
+        pos = np.ascontiguousarray(pos, np.float64)
+        mass = np.ascontiguousarray(mass, np.float32)
+        type = None if type is None else np.ascontiguousarray(type, np.uint8)
+        oldacc = None if oldacc is None else np.ascontiguousarray(oldacc, np.float64)
+        d, sk, sh, lf = (np.ascontiguousarray(top[0], np.int32), np.ascontiguousarray(top[1], np.uint64),
+                         np.ascontiguousarray(top[2], np.int32), np.ascontiguousarray(top[3], np.int32))
+        self.n = len(mass)
+        self.L.ref_tree_build_top(C.c_int64(self.n), _p(pos), _p(mass), _p(type), _p(oldacc), C.c_double(box),
+                                  C.c_int(len(d)), _p(d), _p(sk), _p(sh), _p(lf))
+        return int(self.L.ref_numnodes())
+
     def grav_short_tree(self, par, G, nmesh, asmth):
         acc = np.zeros((self.n, 3))
         pot = np.zeros(self.n)

@@ -166,7 +166,33 @@ static void build_uniform_domain(DomainDecomp *d, int depth)
     }
 }
 
-void ref_build_uniform_domain(DomainDecomp *d, int depth) { build_uniform_domain(d, depth); }     /* for the other fixture files */
+void ref_build_uniform_domain(DomainDecomp *d, int depth) { build_uniform_domain(d, depth); }
+/* An arbitrary top tree handed in as the columns of DomainDecomp::TopNodes (domain.h:20-33); leaves numbered by `leaf`. */
+static void build_domain_from_arrays(DomainDecomp *d, int ntop, const int *daughter, const uint64_t *startkey, const int *shift, const int *leaf)
+{
+    int nleaf = 0;
+    for(int t = 0; t < ntop; t++) if(daughter[t] < 0) nleaf++;
+    d->domain_allocated_flag = 1;
+    d->NTopNodes = ntop;
+    d->NTopLeaves = nleaf;
+    d->TopNodes = (struct topnode_data *) mymalloc("TopNodes", sizeof(struct topnode_data) * ntop);
+    d->TopLeaves = (struct topleaf_data *) mymalloc("TopLeaves", sizeof(struct topleaf_data) * nleaf);
+    d->Tasks = (struct task_data *) mymalloc("Tasks", sizeof(struct task_data));
+    d->Tasks[0].StartLeaf = 0;
+    d->Tasks[0].EndLeaf = nleaf;
+    d->DomainComm = MPI_COMM_WORLD;
+    for(int t = 0; t < ntop; t++) {
+        memset(&d->TopNodes[t], 0, sizeof(d->TopNodes[t]));
+        d->TopNodes[t].Daughter = daughter[t]; d->TopNodes[t].StartKey = startkey[t]; d->TopNodes[t].Shift = shift[t];
+        d->TopNodes[t].Leaf = daughter[t] < 0 ? leaf[t] : -1;
+        if(daughter[t] < 0) {
+            d->TopLeaves[leaf[t]].Task = 0;
+            d->TopLeaves[leaf[t]].topnode = t;
+            d->TopLeaves[leaf[t]].treenode = -1;
+        }
+    }
+}
+     /* for the other fixture files */
 
 int ref_init(double arena_gib, int nthreads)
 {
@@ -199,14 +225,34 @@ static void free_all(void)
 
 /* Load particles (DM type 1 unless type given), build the domain and the full tree.
  * oldacc[n][3] is stored in FullTreeGravAccel (GravPM = 0) for the relative criterion. */
+static int ref_tree_build_dd(int64_t n, const double *pos, const float *mass, const unsigned char *type,
+                             const double *oldacc, double BoxSize, int topdepth,
+                             int ntop, const int *daughter, const uint64_t *startkey, const int *shift, const int *leaf);
+
 int ref_tree_build(int64_t n, const double *pos, const float *mass, const unsigned char *type,
                    const double *oldacc, double BoxSize, int topdepth)
+{
+    return ref_tree_build_dd(n, pos, mass, type, oldacc, BoxSize, topdepth, 0, NULL, NULL, NULL, NULL);
+}
+
+/* The same below an arbitrary domain top tree (force_tree_create_topnodes, forcetree.c:654-687,869-934). */
+int ref_tree_build_top(int64_t n, const double *pos, const float *mass, const unsigned char *type,
+                       const double *oldacc, double BoxSize,
+                       int ntop, const int *daughter, const uint64_t *startkey, const int *shift, const int *leaf)
+{
+    return ref_tree_build_dd(n, pos, mass, type, oldacc, BoxSize, 0, ntop, daughter, startkey, shift, leaf);
+}
+
+static int ref_tree_build_dd(int64_t n, const double *pos, const float *mass, const unsigned char *type,
+                             const double *oldacc, double BoxSize, int topdepth,
+                             int ntop, const int *daughter, const uint64_t *startkey, const int *shift, const int *leaf)
 {
     free_all();
     particle_alloc_memory(PartManager, BoxSize, n);
     have_particles = 1;
     PartManager->NumPart = n;
-    build_uniform_domain(&dd, topdepth);
+    if(ntop > 0) build_domain_from_arrays(&dd, ntop, daughter, startkey, shift, leaf);
+    else build_uniform_domain(&dd, topdepth);
     #pragma omp parallel for
     for(int64_t i = 0; i < n; i++) {
         memset(&P[i], 0, sizeof(P[i]));

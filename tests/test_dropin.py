@@ -150,3 +150,34 @@ def test_reference_driver_calls_gpu_gravpm_force(name, tmp_path):
     assert np.array_equal(ps[:, 2].astype(np.int64), g("ps_N"))
     assert np.all(np.abs(ps[:, 1] - g("ps_P")) <= 2e-5 * np.abs(g("ps_P")))
     assert np.all(np.abs(ps[:, 0] - g("ps_k")) <= 2e-5 * np.abs(g("ps_k")))
+
+
+GTOP = np.load(os.path.join(HERE, "golden", "ref_tree_top.npz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(R.SO_DROPIN), reason="oracle/_ref/libref_dropin.so not built")
+@pytest.mark.parametrize("so", ["SO_DROPIN", "SO_DROPIN_ALL"])
+def test_shims_build_below_the_domain_top_tree(so):
+    """The device tree is built below the caller's domain top tree (forcetree.c:654-687), taken from the host tree's
+    top-level nodes (grav_short_tree gets no DomainDecomp) or, in GPU-only tree mode, from ddecomp->TopNodes: with the
+    same node set the walk takes the reference's decisions, so the accelerations agree to rounding, not just to 1e-6."""
+    if not os.path.exists(getattr(R, so)):
+        pytest.skip("not built")
+    r = R.Ref(arena_gib=2.0, nthreads=2, so=getattr(R, so))
+    name = "uniform3000"
+    pos, mass, box = GOLD[name + "/pos"], GOLD[name + "/mass"], float(GOLD[name + "/box"])
+    for tname in ("top97", "top321"):
+        top = tuple(GTOP["%s/%s" % (tname, k)] for k in ("daughter", "startkey", "shift", "leaf"))
+        for usebh in (1, 0):
+            v = GOLD["%s/bh%d/par" % (name, usebh)]
+            par = dict(zip(PARKEYS, [float(x) for x in v])); par["TreeUseBH"] = int(par["TreeUseBH"])
+            r.tree_build_top(pos, mass, box, top, oldacc=GOLD[name + "/oldacc"])
+            acc, pot = r.grav_short_tree(par, 43.0071, int(GOLD[name + "/nmesh"]), 1.5)
+            racc = GTOP["%s/%s/bh%d/acc" % (tname, name, usebh)]
+            assert np.abs(acc - racc).max() < 1e-11 * np.sqrt((racc ** 2).sum(1)).mean()
+    # the 64-leaf domain of the reference's multi-threaded build
+    r.tree_build(pos, mass, box, oldacc=GOLD[name + "/oldacc"], topdepth=2)
+    acc, pot = r.grav_short_tree(par, 43.0071, int(GOLD[name + "/nmesh"]), 1.5)
+    racc = GOLD["%s/bh0/acc" % name]
+    assert np.abs(acc - racc).max() < 1e-6 * np.sqrt((racc ** 2).sum(1)).mean()

@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 900 python -m pytest tests/test_golden.py tests/test_dropin.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -15
