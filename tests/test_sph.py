@@ -195,3 +195,35 @@ def test_oracle_sph_mixed_timebins_equal_reference(name):
         assert _close(d[k], m("mixed_" + k), 1e-12), k          # inactive particles: untouched state
     for k in ("acc", "dtentropy", "maxsignalvel"):
         assert _close(h[k][act], m("mixed_" + k)[act], 1e-11), k
+
+
+# ---- the quartic spline (DENSITY_KERNEL_QUARTIC_SPLINE = 4, densitykernel.h:17-21) ----------------------------------
+GOLD_Q = np.load(os.path.join(HERE, "golden", "ref_sph_quartic.npz"))
+
+
+@pytest.mark.parametrize("DI", [0, 1])
+def test_oracle_sph_quartic_equals_reference(DI):
+    pos, mass, vel, ent, box, h0 = _inputs("zeldovich16")
+    n = len(mass)
+    t = oracle.OracleTree(pos, mass, box, type=np.zeros(n, np.uint8), mask=1)
+    sp = oracle.sph_params(KernelType=4, MinGasHsml=0.006, DensityIndependentSphOn=DI, **HYDRO)
+    d = oracle.density(t, sp, h0, vel=vel, entropy=ent, DoEgyDensity=DI)
+    assert d["rc"] == 0
+    key = "zeldovich16/k4_di%d/" % DI
+    for k in DENS_KEYS:
+        assert _close(d[k], GOLD_Q[key + k], 1e-12), k
+    h = oracle.hydro(t, sp, d, vel=vel, entropy=ent)
+    for k in ("acc", "dtentropy", "maxsignalvel"):
+        assert _close(h[k], GOLD_Q[key + "hydro_" + k], 1e-11), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("DI", [0, 1])
+def test_gpu_sph_quartic_equals_reference(b200, engine, DI):
+    pos, mass, vel, ent, box, h0 = _inputs("zeldovich16")
+    d, h = _gpu_sph(b200, engine, pos, mass, vel, ent, box, h0, 4, DI)
+    key = "zeldovich16/k4_di%d/" % DI
+    for k in DENS_KEYS:
+        assert _close(d[k], GOLD_Q[key + k], 1e-11), k
+    for k in ("acc", "dtentropy", "maxsignalvel"):
+        assert _close(h[k], GOLD_Q[key + "hydro_" + k], 1e-10), k
