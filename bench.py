@@ -585,6 +585,7 @@ def main():
     pinned = torch.empty(n * 160, dtype=torch.uint8).pin_memory()
     pinned.numpy()[:] = P.view(np.uint8).reshape(-1)
     del P, d_pos, d_mass
+    e2e_bytes = e.force_step_aos_bytes()
     for _ in range(2):
         e.force_step_aos(None, par, ptr=pinned.data_ptr(), n=n)
     barrier()
@@ -651,9 +652,10 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": cfg,
-        "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": n * 160, "d2h_bytes_per_step": n * 160,
+        "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": n * e2e_bytes[0], "d2h_bytes_per_step": n * e2e_bytes[1],
                 "ms_per_step": ms_e2e / Ke, "wall_ms_per_step": 1e3 * wall_e2e / Ke,
-                "h2d_ms": te2e["h2d"], "d2h_ms": te2e["d2h"], "api": "b200_force_step_aos (pinned host AoS, 160 B/particle)",
+                "h2d_ms": te2e["h2d"], "d2h_ms": te2e["d2h"], "api": "b200_force_step_aos (the reference's 160-byte particle records in pinned host memory; %d B/particle in and %d B/particle "
+                                                                     "out cross PCIe as strided copies)" % e2e_bytes,
                 "check_vs_device_arm": chk},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -203,10 +203,16 @@ int b200_grav_short_tree_dev(b200_ctx *ctx, const b200_gravshort_params *par,
 /* ---- whole DM force step on the caller's AoS (the e2e path) ----------------
  * = gravpm_force + force_tree_full + grav_short_tree as run.c:519-548 does on a
  * PM step with SplitGravityTimestepsOn=0: reads P[], writes P[i].GravPM,
- * P[i].FullTreeGravAccel and P[i].Potential in place. */
+ * P[i].FullTreeGravAccel and P[i].Potential in place.
+ * Only the bytes that matter cross PCIe, as strided copies: Pos..Type (40 B of the 160-byte record) before the PM step
+ * and the tree build start, FullTreeGravAccel + GravPM (48 B) underneath them for the walk's opening criterion; the same
+ * 48 B and Potential travel back group by group behind the walk.  A layout that does not fit (unaligned fields, spans
+ * wider than 0.7 of the record) or B200_E2E_BULK=1 moves whole records instead. */
 int b200_force_step_aos(b200_ctx *ctx, void *particles, int64_t n,
                         const b200_particle_layout *layout,
                         const b200_gravshort_params *par);
+/* Bytes per particle that call moves host->device / device->host for `layout` (NULL = the default layout). */
+void b200_force_step_aos_bytes(const b200_particle_layout *layout, int64_t *h2d, int64_t *d2h);
 /* The same three calls on particles already resident in HBM
  * (b200_set_particles_*): outputs are DEVICE pointers [n][3] / [n], any may be
  * NULL.  gravpm_force runs on a second stream concurrently with

@@ -109,7 +109,7 @@ EXPORTED = [
     "b200_abi_version", "b200_kernel_launches", "b200_set_particles_aos", "b200_set_particles_soa",
     "b200_set_particles_soa_dev", "b200_oldacc_from_last_step", "b200_pm_init", "b200_walk_set_mesh", "b200_pm_force",
     "b200_pm_force_dev", "b200_pm_set_power", "b200_pm_get_power", "b200_pm_cell_index", "b200_pm_copy_mesh", "b200_tree_build", "b200_tree_free",
-    "b200_tree_export", "b200_grav_short_tree", "b200_grav_short_tree_dev", "b200_force_step_aos", "b200_force_step_dev",
+    "b200_tree_export", "b200_grav_short_tree", "b200_grav_short_tree_dev", "b200_force_step_aos", "b200_force_step_aos_bytes", "b200_force_step_dev",
     "b200_get_timings", "b200_stream",
     "b200_tree_top_get_dev", "b200_tree_top_set_dev",
     "b200_comm_unique_id", "b200_comm_init", "b200_sharded_init", "b200_sharded_force_step",
@@ -362,6 +362,12 @@ class Engine:
         return info
 
     # -- whole step on the reference's AoS -------------------------------------
+    def force_step_aos_bytes(self):
+        """(host->device, device->host) bytes per particle force_step_aos moves for the default record layout"""
+        a, b = C.c_int64(), C.c_int64()
+        self.L.b200_force_step_aos_bytes(None, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def force_step_aos(self, P, par, ptr=None, n=None):
         p = GravShortParams(**par) if isinstance(par, dict) else par
         if ptr is None:

@@ -116,6 +116,47 @@ k_pack_aos(uint8_t *__restrict__ aos, int64_t n, b200_particle_layout L,
     }
 }
 
+// The strided ingest of b200_force_step_aos: the caller's records are never copied whole.  Span A = the bytes that hold
+// Pos, Mass, the flag byte and Type (what the PM step and the tree build read), span B = FullTreeGravAccel..GravPM
+// (the walk's opening criterion reads |sum|, and both are outputs).  o_* are offsets inside the span.
+__global__ void __launch_bounds__(256)
+k_unpack_span_a(const uint8_t *__restrict__ a, int64_t n, int w, int o_pos, int o_mass, int o_flags, int o_type,
+                double *__restrict__ pos, float *__restrict__ mass, uint8_t *__restrict__ type, uint8_t *__restrict__ flags)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const uint8_t *r = a + i * w;
+    const double *p = (const double *) (r + o_pos);
+    pos[3 * i] = p[0]; pos[3 * i + 1] = p[1]; pos[3 * i + 2] = p[2];
+    mass[i] = *(const float *) (r + o_mass);
+    type[i] = r[o_type];
+    flags[i] = r[o_flags] & 3;
+}
+__global__ void __launch_bounds__(256)
+k_unpack_span_b(const uint8_t *__restrict__ b, int64_t n, int w, int o_ft, int o_pm, double *__restrict__ oldacc)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const double *ft = (const double *) (b + i * w + o_ft), *pm = (const double *) (b + i * w + o_pm);
+    double s = 0;                       // grav_get_abs_accel gravshort.h:69-86
+#pragma unroll
+    for(int j = 0; j < 3; j++) {
+        const double v = __dadd_rn(ft[j], pm[j]);
+        s = __dadd_rn(s, __dmul_rn(v, v));
+    }
+    oldacc[i] = sqrt(s);
+}
+__global__ void __launch_bounds__(256)
+k_pack_span_b(uint8_t *__restrict__ b, int64_t n, int w, int o_ft, int o_pm, const double *__restrict__ gravpm,
+              const double *__restrict__ treeacc, int64_t first)
+{
+    const int64_t i = first + (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= first + n) return;
+    double *pm = (double *) (b + i * w + o_pm), *ft = (double *) (b + i * w + o_ft);
+    pm[0] = gravpm[3 * i]; pm[1] = gravpm[3 * i + 1]; pm[2] = gravpm[3 * i + 2];
+    ft[0] = treeacc[3 * i]; ft[1] = treeacc[3 * i + 1]; ft[2] = treeacc[3 * i + 2];
+}
+
 static int ensure_particles(Engine *E, int64_t n)
 {
     const size_t m = (size_t) (n > 0 ? n : 1);
@@ -217,7 +258,7 @@ void b200_ctx_destroy(b200_ctx *ctx)
     E->s_hA.release(); E->s_hB.release(); E->s_out3.release(); E->s_out1a.release(); E->s_out1b.release(); E->s_outi.release(); E->s_outi2.release();
     E->s_niter.release(); E->s_nint.release();
     for(int i = 0; i < T_COUNT; i++) if(E->timers[i].a) { cudaEventDestroy(E->timers[i].a); cudaEventDestroy(E->timers[i].b); }
-    for(int i = 0; i < 65; i++) if(E->chunk_ev[i]) cudaEventDestroy(E->chunk_ev[i]);
+    for(int i = 0; i < 66; i++) if(E->chunk_ev[i]) cudaEventDestroy(E->chunk_ev[i]);
     cudaStreamDestroy(E->copy_stream);
     sharded_destroy(E);
     cudaStreamDestroy(E->side_stream);
@@ -518,6 +559,32 @@ int b200_force_step_dev(b200_ctx *ctx, const b200_gravshort_params *par, double 
     return collect_timings(E);
 }
 
+// Spans of the strided ingest / write-back (see k_unpack_span_a).  Returns false when the layout does not fit the
+// scheme (fields not 8-byte aligned inside the spans, spans too wide to pay): the caller then moves whole records.
+static bool aos_spans(const b200_particle_layout &L, int &a0, int &aw, int &b0, int &bw)
+{
+    auto lo = [](int x, int y) { return x < y ? x : y; };
+    auto hi = [](int x, int y) { return x > y ? x : y; };
+    a0 = lo(lo(L.off_pos, L.off_mass), lo(L.off_flags, L.off_type));
+    const int a1 = hi(hi(L.off_pos + 24, L.off_mass + 4), hi(L.off_flags + 1, L.off_type + 1));
+    a0 &= ~7; aw = ((a1 + 7) & ~7) - a0;
+    b0 = lo(L.off_fulltreeacc, L.off_gravpm);
+    const int b1 = hi(L.off_fulltreeacc, L.off_gravpm) + 24;
+    bw = b1 - b0;
+    if((b0 & 7) || (bw & 7) || (L.off_pos & 7) || (L.off_potential & 7) || (L.stride & 7)) return false;
+    return aw + bw <= (int) (0.7 * L.stride);
+}
+
+/* Bytes per particle b200_force_step_aos moves over PCIe in each direction for this layout. */
+void b200_force_step_aos_bytes(const b200_particle_layout *layout, int64_t *h2d, int64_t *d2h)
+{
+    b200_particle_layout L; if(layout) L = *layout; else b200_default_particle_layout(&L);
+    int a0, aw, b0, bw;
+    const bool strided = aos_spans(L, a0, aw, b0, bw) && !getenv("B200_E2E_BULK");
+    if(h2d) *h2d = strided ? aw + bw : L.stride;
+    if(d2h) *d2h = strided ? bw + 8 : L.stride;
+}
+
 int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_layout *layout,
                         const b200_gravshort_params *par)
 {
@@ -525,7 +592,32 @@ int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_l
     if(E->Nmesh == 0) return failmsg(E, "b200_force_step_aos: call b200_pm_init first");
     if(!par) return failmsg(E, "b200_force_step_aos: null params");
     b200_particle_layout L; if(layout) L = *layout; else b200_default_particle_layout(&L);
-    if(int rc = b200_set_particles_aos(ctx, P, n, &L)) return rc;
+    int a0 = 0, aw = 0, b0 = 0, bw = 0;
+    const bool strided = aos_spans(L, a0, aw, b0, bw) && !getenv("B200_E2E_BULK");
+    uint8_t *spanB = nullptr;
+    if(!strided) { if(int rc = b200_set_particles_aos(ctx, P, n, &L)) return rc; }
+    else {
+        // Two strided copies instead of the whole records (160 B/particle): span A (Pos .. Type, 40 B) first -- the PM step
+        // and the tree build start as soon as it is unpacked -- and span B (FullTreeGravAccel, GravPM, 48 B), which only
+        // the walk needs, on the copy stream underneath them.
+        if(n < 0 || (n > 0 && !P)) return failmsg(E, "b200_force_step_aos: bad arguments");
+        if(int rc = ensure_particles(E, n)) return rc;
+        if(n > 0) {
+            CK(E->aos.ensure((size_t) n * (aw + bw)));
+            uint8_t *spanA = E->aos.p; spanB = E->aos.p + (size_t) n * aw;
+            timer_start(E, T_H2D);
+            CK(cudaMemcpy2DAsync(spanA, aw, (const uint8_t *) P + a0, L.stride, aw, n, cudaMemcpyHostToDevice, E->stream));
+            timer_stop(E, T_H2D);
+            k_unpack_span_a<<<(unsigned) ((n + 255) / 256), 256, 0, E->stream>>>(spanA, n, aw, L.off_pos - a0, L.off_mass - a0, L.off_flags - a0,
+                                                                               L.off_type - a0, E->pos.p, E->mass.p, E->type.p, E->flags.p);
+            CKL(E);
+            if(!E->chunk_ev[65]) CK(cudaEventCreateWithFlags(&E->chunk_ev[65], cudaEventDisableTiming));
+            CK(cudaEventRecord(E->chunk_ev[65], E->stream));                // span A is in: the link is free for span B
+            CK(cudaStreamWaitEvent(E->copy_stream, E->chunk_ev[65], 0));
+            CK(cudaMemcpy2DAsync(spanB, bw, (const uint8_t *) P + b0, L.stride, bw, n, cudaMemcpyHostToDevice, E->copy_stream));
+            CK(cudaEventRecord(E->chunk_ev[65], E->copy_stream));
+        }
+    }
     if(n == 0) return 0;
     const size_t m = (size_t) n;
     CK(E->last_pm_acc.ensure(3 * m)); CK(E->last_tree_acc.ensure(3 * m)); CK(E->d_pot.ensure(m));
@@ -534,19 +626,41 @@ int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_l
     // force_tree_full + grav_short_tree (run.c:546-548)
     if(int rc = tree_build(E, E->Box, 63, nullptr, 0, 0, nullptr)) return rc;
     E->have_last_pm = E->have_last_tree = true;
+    if(strided) {
+        CK(cudaStreamWaitEvent(E->stream, E->chunk_ev[65], 0));
+        k_unpack_span_b<<<(unsigned) ((n + 255) / 256), 256, 0, E->stream>>>(spanB, n, bw, L.off_fulltreeacc - b0, L.off_gravpm - b0, E->oldacc.p);
+        CKL(E);
+    }
+    // Results of a group of particles: into the caller's records.  Strided path: span B (packed in place, so bytes of
+    // the span that are not outputs keep the caller's values) and the potential column; otherwise the whole records.
+    auto pack = [&](int64_t lo, int64_t hi) -> int {
+        if(strided) k_pack_span_b<<<(unsigned) ((hi - lo + 255) / 256), 256, 0, E->stream>>>(spanB, hi - lo, bw, L.off_fulltreeacc - b0, L.off_gravpm - b0,
+                                                                                           E->last_pm_acc.p, E->last_tree_acc.p, lo);
+        else k_pack_aos<<<(unsigned) ((hi - lo + 255) / 256), 256, 0, E->stream>>>(E->aos.p, hi - lo, L, E->last_pm_acc.p, E->last_tree_acc.p, E->d_pot.p, 1, lo);
+        CKL(E);
+        return 0;
+    };
+    auto copy_back = [&](int64_t lo, int64_t hi, cudaStream_t st) -> int {
+        if(strided) {
+            CK(cudaMemcpy2DAsync((uint8_t *) P + lo * L.stride + b0, L.stride, spanB + lo * bw, bw, bw, hi - lo, cudaMemcpyDeviceToHost, st));
+            // TREEWALK_REDUCE assigns in primary mode (treewalk.h:202): the tree potential replaces the PM potential
+            CK(cudaMemcpy2DAsync((uint8_t *) P + lo * L.stride + L.off_potential, L.stride, E->d_pot.p + lo, sizeof(double), sizeof(double), hi - lo,
+                                 cudaMemcpyDeviceToHost, st));
+        } else CK(cudaMemcpyAsync((uint8_t *) P + lo * L.stride, E->aos.p + lo * L.stride, (size_t) (hi - lo) * L.stride, cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
     // The walk is issued in groups of equal particle-index ranges (targets in curve
-    // order inside each group): as soon as a group is done its records are packed and
+    // order inside each group): as soon as a group is done its results are packed and
     // copied back on the copy stream while the next group is walked, so the write-back
-    // (160 B/particle over PCIe) hides behind the walk.  B200_E2E_CHUNKS overrides.
+    // hides behind the walk.  B200_E2E_CHUNKS overrides.
     int nchunks = n >= (1 << 20) ? 8 : 1;
     if(const char *ev = getenv("B200_E2E_CHUNKS")) { nchunks = atoi(ev); if(nchunks < 1) nchunks = 1; if(nchunks > 64) nchunks = 64; }
     if(nchunks == 1) {
         if(int rc = grav_short_tree(E, par, nullptr, 0, E->last_tree_acc.p, E->d_pot.p, nullptr)) return rc;
         if(int rc = pm_join(E)) return rc;
-        k_pack_aos<<<(unsigned) ((n + 255) / 256), 256, 0, E->stream>>>(E->aos.p, n, L, E->last_pm_acc.p, E->last_tree_acc.p, E->d_pot.p, 1, 0);
-        CKL(E);
+        if(int rc = pack(0, n)) return rc;
         timer_start(E, T_D2H);
-        CK(cudaMemcpyAsync(P, E->aos.p, m * L.stride, cudaMemcpyDeviceToHost, E->stream));
+        if(int rc = copy_back(0, n, E->stream)) return rc;
         timer_stop(E, T_D2H);
     } else {
         const int64_t chunk = (n + nchunks - 1) / nchunks;
@@ -560,13 +674,12 @@ int b200_force_step_aos(b200_ctx *ctx, void *P, int64_t n, const b200_particle_l
             if(nc > 0)
                 if(int rc = grav_short_tree(E, par, E->targets_sorted.p + off[c], nc, E->last_tree_acc.p, E->d_pot.p, nullptr, true)) return rc;
             if(c == 0) if(int rc = pm_join(E)) return rc;       // GravPM is packed with the first group
-            k_pack_aos<<<(unsigned) ((hi - lo + 255) / 256), 256, 0, E->stream>>>(E->aos.p, hi - lo, L, E->last_pm_acc.p, E->last_tree_acc.p, E->d_pot.p, 1, lo);
-            CKL(E);
+            if(int rc = pack(lo, hi)) return rc;
             if(c == nchunks - 1 || hi == n) timer_start(E, T_D2H);      // the exposed tail of the write-back
             if(!E->chunk_ev[c]) CK(cudaEventCreateWithFlags(&E->chunk_ev[c], cudaEventDisableTiming));
             CK(cudaEventRecord(E->chunk_ev[c], E->stream));
             CK(cudaStreamWaitEvent(E->copy_stream, E->chunk_ev[c], 0));
-            CK(cudaMemcpyAsync((uint8_t *) P + lo * L.stride, E->aos.p + lo * L.stride, (size_t) (hi - lo) * L.stride, cudaMemcpyDeviceToHost, E->copy_stream));
+            if(int rc = copy_back(lo, hi, E->copy_stream)) return rc;
         }
         if(!E->chunk_ev[nchunks]) CK(cudaEventCreateWithFlags(&E->chunk_ev[nchunks], cudaEventDisableTiming));
         CK(cudaEventRecord(E->chunk_ev[nchunks], E->copy_stream));

@@ -55,7 +55,7 @@ struct Engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;     // host<->device copies that overlap kernels on `stream`
-    cudaEvent_t chunk_ev[65] = {};
+    cudaEvent_t chunk_ev[66] = {};           // [0..64] walk groups of the AoS step, [65] its span-B ingest
     cudaStream_t side_stream = nullptr;     // PM long-range step when it runs concurrently with the tree walk
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     std::string err;

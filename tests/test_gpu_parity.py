@@ -159,13 +159,20 @@ def test_reference_gravity_bounds(engine, ics, name, direct):
     assert err.mean() < 0.8 * errtol
 
 
+@pytest.mark.parametrize("bulk", [0, 1])
 @pytest.mark.parametrize("chunks", [1, 3, 8])
-def test_force_step_aos(engine, b200, ics, chunks, monkeypatch):
+def test_force_step_aos(engine, b200, ics, chunks, bulk, monkeypatch):
     """b200_force_step_aos on the reference's 160-byte particle records equals
     the separate PM + tree calls and writes GravPM / FullTreeGravAccel / Potential in place.
     chunks > 1: the walk is issued in index-range groups whose records travel back
-    while the next group is walked (the path large inputs take)."""
+    while the next group is walked (the path large inputs take).  bulk = 0: only the 40 + 48 input bytes and 48 + 8
+    output bytes of a record cross PCIe, as strided copies; bulk = 1: whole records (the path of an unusual layout)."""
     monkeypatch.setenv("B200_E2E_CHUNKS", str(chunks))
+    if bulk:
+        monkeypatch.setenv("B200_E2E_BULK", "1")
+    else:
+        monkeypatch.delenv("B200_E2E_BULK", raising=False)
+    assert engine.force_step_aos_bytes() == ((160, 160) if bulk else (88, 56))
     pos, box = _distributions(ics)["gslrandom16"]
     n = len(pos)
     P = np.zeros(n, dtype=b200.PARTICLE_DTYPE)
@@ -176,6 +183,8 @@ def test_force_step_aos(engine, b200, ics, chunks, monkeypatch):
     rng = np.random.default_rng(5)
     P["FullTreeGravAccel"] = rng.standard_normal((n, 3)) * 300
     P["GravPM"] = rng.standard_normal((n, 3)) * 30
+    P["Vel"] = rng.standard_normal((n, 3)); P["Hsml"] = rng.random(n); P["Potential"] = -7.0
+    before = P.copy()
     old = P["FullTreeGravAccel"] + P["GravPM"]
     par = ics.tree_params(box, n, treeusebh=0, rcut=7.0)
     engine.gravpm_init_periodic(box, 1.5, 48, G)
@@ -193,6 +202,9 @@ def test_force_step_aos(engine, b200, ics, chunks, monkeypatch):
         assert np.abs(P["FullTreeGravAccel"] - acc).max() <= 1e-12 * np.abs(acc).max()
         assert np.abs(P["Potential"] - pot).max() <= 1e-12 * np.abs(pot).max()
     assert np.array_equal(P["Pos"], pos) and np.all(P["ID"] == np.arange(n))
+    for f in P.dtype.names:         # every other byte of the records is the caller's
+        if f not in ("GravPM", "FullTreeGravAccel", "Potential"):
+            assert np.array_equal(P[f], before[f]), f
 
 
 def test_force_step_dev(engine, ics):
