@@ -307,6 +307,14 @@ def run_sharded(args, rank, world, local, dist, pkg, ics, W, K):
     barrier()
     ms_e2e = ev2.elapsed_time(ev3)
     clocks = sampler.stop() if rank == 0 else None
+    hydro = None
+    if args.sharded_hydro:
+        del hpos, hmass, hacc, hgpm, hpot, hold
+        # gas cells one level coarser than the gravity cut: the ghost layer must be wider than the largest smoothing length
+        hd = topdepth - 1
+        while hd > 0 and (1 << hd) % world:
+            hd -= 1
+        hydro = sharded_hydro_entry(rank, world, dev, dist, pkg, sh, e, pos, mass, box, ng_tot, max(hd, 1), stream)
     tt = torch.tensor([ms_dev, ms_e2e, float(nghost), float(n_own)] + ([parity["acc_max_err_over_mean"]] if parity else [0.0]),
                       dtype=torch.float64, device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -340,8 +348,78 @@ def run_sharded(args, rank, world, local, dist, pkg, ics, W, K):
             "parity": None if parity is None else dict(parity, acc_max_err_over_mean_all_ranks=par_max),
             "timing": "CUDA events on the engine's stream around K steps, max over ranks",
         }
+        if hydro is not None:
+            out["hydro"] = hydro
         print(json.dumps(out), flush=True)
     dist.destroy_process_group()
+
+
+def sharded_hydro_entry(rank, world, dev, dist, pkg, sh, e, pos, mass, box, ng_tot, topdepth, stream, K=2):
+    """BASELINE.json configs[4] (gas part): the displaced box as GAS, sharded like the gravity step -- ghost-layer import,
+    density with the smoothing-length iteration for the own particles, converged state of the exported particles sent
+    back, hmax refresh, symmetric hydro pass -- with the whole SPH state resident in HBM (ShardedSPH).  Timed: the step a
+    run takes every time (Hsml predicted from the last step: converged values +- 1 %), all particles active, and a
+    mixed-time-bin sub-step in which a quarter of the particles is active and the rest are sources with their old state."""
+    import numpy as np
+    import torch
+    n = pos.shape[0]
+    gen = torch.Generator(device=dev); gen.manual_seed(1000 + rank)
+    vel = 0.05 * torch.randn((n, 3), dtype=torch.float64, device=dev, generator=gen)
+    ent = torch.ones(n, dtype=torch.float64, device=dev)
+    h0 = torch.full((n,), 3.0 * 0.8 * box / ng_tot, dtype=torch.float64, device=dev)
+    sp = pkg.sph_params(KernelType=2, DensityIndependentSphOn=1, MinGasHsml=1e-4, atime=0.1, hubble=3.0, dloga_bin=0.01)
+    s = sh.ShardedSPH(e, box, topdepth, dist=dist, device=str(dev))
+
+    def step(hs, active=None, bins=None):
+        nghost = s.load(pos, mass, hs, vel=vel, entropy=ent)
+        if bins is not None:
+            tab = {k: np.zeros(47) for k in ("gravkick", "hydrokick", "dloga_pred", "drift")}; tab["dloga_bin"] = np.full(47, 0.01)
+            s.set_mixed(bins, tab, active)
+        d = s.density(sp, DoEgyDensity=1)
+        h = s.hydro_force(sp)
+        return nghost, d, h
+
+    def timed(fn):
+        fn()                                        # untimed: sizes the piece pools for this mode
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(K):
+            out = fn()
+        ev1.record(stream)
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1) / K], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), out
+
+    try:
+        nghost, d, h = step(h0)                                         # cold start: converges Hsml (and sizes the pools)
+        hconv = d["hsml"].clone()
+        hw = (hconv * (1.0 + 0.01 * torch.randn(n, dtype=torch.float64, device=dev, generator=gen))).contiguous()
+        ms_cold, _ = timed(lambda: step(h0))
+        ms_warm, (nghost, dw, hwf) = timed(lambda: step(hw))
+        passes = float(dw["niter"].to(torch.float64).mean().item())
+        # mixed time bins: every fourth own particle active (bin 10), the others (bin 12) keep the state of the last full pass
+        idx = torch.arange(n, device=dev)
+        act = idx[(idx % 4) == 0].to(torch.int32).contiguous()
+        bins = torch.where((idx % 4) == 0, 10, 12).to(torch.uint8)
+        ms_mixed, _ = timed(lambda: step(hw, active=act, bins=bins))
+        tot = torch.tensor([float(n), float(nghost)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot)
+        return {"workload": "%d^3 gas (displaced box) sharded over %d GPUs: ghost import + gas tree + density + state return + hydro, state resident in HBM" % (ng_tot, world),
+                "n_gas_total": int(tot[0].item()), "ghosts_total": int(tot[1].item()), "kernel": "quintic, 113 neighbours, pressure-entropy",
+                "sph_step_cold_ms": ms_cold, "sph_step_ms": ms_warm, "density_passes_mean": passes,
+                "gas_per_s": tot[0].item() / (ms_warm * 1e-3),
+                "mixed_bin_substep_ms": ms_mixed, "mixed_bin_active_fraction": 0.25,
+                "active_gas_per_s_mixed": 0.25 * tot[0].item() / (ms_mixed * 1e-3),
+                "timing": "CUDA events on the engine's stream, max over ranks; Hsml of the timed step = converged values +- 1 % (what drift.c:60-70 hands density() every step after the first)"}
+    except Exception as ex:
+        # a failure on one rank leaves the others inside a collective: say so at once and take the job down (torchrun
+        # stops the other ranks) instead of waiting for the NCCL watchdog
+        import traceback
+        sys.stderr.write("[rank %d] sharded hydro entry failed: %r\n%s\n" % (rank, ex, traceback.format_exc()))
+        sys.stderr.flush()
+        os._exit(17)
 
 
 def gpu_state_line(pkg, ics, e, state, ng, box, nmesh, K=2):
@@ -453,6 +531,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU arm (cpu_baseline + parity of the 256^3 step)")
     ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds after which --impl reference stops adding timed steps")
     ap.add_argument("--no-hydro", action="store_true", help="skip the SPH density + hydro timing (configs[2])")
+    ap.add_argument("--sharded-hydro", action="store_true", help="multi-GPU: add the sharded SPH entry (configs[4], gas part) to the line")
     ap.add_argument("--no-states", action="store_true", help="skip the extra z9 / clustered state entries")
     ap.add_argument("--no-steploop", action="store_true", help="skip the device-resident step-loop entry")
     ap.add_argument("--no-parity", action="store_true", help="multi-GPU: skip the sampled parity check")
@@ -477,7 +556,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))
 
     W = max(args.warmup, 3)
     K = args.steps

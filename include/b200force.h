@@ -272,7 +272,11 @@ int b200_sph_set_hsml_range(b200_ctx *ctx, const double *hsml, int64_t first, in
 int b200_sph_set_state(b200_ctx *ctx, const double *density, const double *egywtdensity, const double *dhsmlfac,
                        const double *divvel, const double *curlvel);
 
-/* Per-particle gas state, host arrays indexed by particle index (entries of
+/* The array arguments of the b200_sph_* setters and the outputs of b200_density / b200_hydro_force may live in host OR
+ * device memory (the copies are issued with cudaMemcpyDefault): a multi-GPU driver keeps the gas state in HBM and hands
+ * over device pointers (mp-gadget_b200/sharded.py, ShardedSPH).
+ *
+ * Per-particle gas state, arrays indexed by particle index (entries of
  * non-gas particles are ignored): Vel[n][3], Hsml[n] (required), Entropy[n],
  * DtEntropy[n], FullTreeGravAccel[n][3], GravPM[n][3], HydroAccel[n][3]; NULL = 0
  * (Entropy NULL = 1).  P[].Vel/Hsml, SphP[].Entropy/DtEntropy/HydroAccel of the

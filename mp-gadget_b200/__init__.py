@@ -147,12 +147,23 @@ def lib():
     return _lib
 
 
+def _is_dev(a):
+    return hasattr(a, "data_ptr")          # a torch tensor (device-resident callers: sharded.py)
+
+
 def _p(a):
-    return None if a is None else C.c_void_p(a.ctypes.data)
+    if a is None:
+        return None
+    return C.c_void_p(a.data_ptr()) if _is_dev(a) else C.c_void_p(a.ctypes.data)
 
 
 def _c(a, dt):
-    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+    if a is None:
+        return None
+    if _is_dev(a):
+        assert str(a.dtype).endswith(np.dtype(dt).name) and a.is_contiguous(), "device arrays must come as contiguous %s" % np.dtype(dt).name
+        return a
+    return np.ascontiguousarray(a, dtype=dt)
 
 
 class B200Error(RuntimeError):
@@ -317,19 +328,27 @@ class Engine:
         arr = [_c(x, np.float64) for x in (density, egywtdensity, dhsmlfac, divvel, curlvel)]
         self._ck(self.L.b200_sph_set_state(self.ctx, *[_p(x) for x in arr]))
 
-    def density(self, sp, update_hsml=1, DoEgyDensity=0):
+    def _zeros(self, shape, dt, device):
+        if device is None:
+            return np.zeros(shape, dt)
+        import torch
+        return torch.zeros(shape, dtype={np.float64: torch.float64, np.int32: torch.int32}[dt], device=device)
+
+    def density(self, sp, update_hsml=1, DoEgyDensity=0, device=None):
+        """device: a torch device -> the outputs are tensors in HBM (no host copy)"""
         n = self.n
-        out = dict(hsml=np.zeros(n), density=np.zeros(n), egywtdensity=np.zeros(n), dhsmlfac=np.zeros(n), divvel=np.zeros(n),
-                   curlvel=np.zeros(n), dthsml=np.zeros(n), numngb=np.zeros(n), ninteract=np.zeros(n, np.int32),
-                   niter=np.zeros(n, np.int32))
+        z = lambda dt: self._zeros(n, dt, device)
+        out = dict(hsml=z(np.float64), density=z(np.float64), egywtdensity=z(np.float64), dhsmlfac=z(np.float64), divvel=z(np.float64),
+                   curlvel=z(np.float64), dthsml=z(np.float64), numngb=z(np.float64), ninteract=z(np.int32), niter=z(np.int32))
         self._ck(self.L.b200_density(self.ctx, C.byref(sp), C.c_int(update_hsml), C.c_int(DoEgyDensity),
                                      *[_p(out[k]) for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel",
                                                             "dthsml", "numngb", "ninteract", "niter")]))
         return out
 
-    def hydro_force(self, sp):
+    def hydro_force(self, sp, device=None):
         n = self.n
-        out = dict(acc=np.zeros((n, 3)), dtentropy=np.zeros(n), maxsignalvel=np.zeros(n), ninteract=np.zeros(n, np.int32))
+        out = dict(acc=self._zeros((n, 3), np.float64, device), dtentropy=self._zeros(n, np.float64, device),
+                   maxsignalvel=self._zeros(n, np.float64, device), ninteract=self._zeros(n, np.int32, device))
         self._ck(self.L.b200_hydro_force(self.ctx, C.byref(sp), _p(out["acc"]), _p(out["dtentropy"]), _p(out["maxsignalvel"]),
                                          _p(out["ninteract"])))
         return out

@@ -717,9 +717,9 @@ int b200_sph_set_state(b200_ctx *ctx, const double *density, const double *egywt
     return sph_set_state(E, density, egywtdensity, dhsmlfac, divvel, curlvel);
 }
 
-static int d2h_opt(Engine *E, void *dst, const void *src, size_t bytes)
+static int d2h_opt(Engine *E, void *dst, const void *src, size_t bytes)       // dst: host or device memory (UVA)
 {
-    if(dst && bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, E->stream));
+    if(dst && bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, E->stream));
     return 0;
 }
 

@@ -866,9 +866,9 @@ int sph_set_timebins(Engine *E, const uint8_t *bin_grav, const uint8_t *bin_hydr
     const size_t n = (size_t) (E->n > 0 ? E->n : 1);
     CK(E->s_bins.ensure(5 * NB)); CK(E->s_bin_grav.ensure(n)); CK(E->s_bin_hydro.ensure(n));
     CK(cudaMemcpyAsync(E->s_bins.p, bins, 5 * NB * sizeof(double), cudaMemcpyHostToDevice, E->stream));
-    if(bin_grav) CK(cudaMemcpyAsync(E->s_bin_grav.p, bin_grav, E->n, cudaMemcpyHostToDevice, E->stream));
+    if(bin_grav) CK(cudaMemcpyAsync(E->s_bin_grav.p, bin_grav, E->n, cudaMemcpyDefault, E->stream));
     else CK(cudaMemsetAsync(E->s_bin_grav.p, 0, n, E->stream));
-    if(bin_hydro) CK(cudaMemcpyAsync(E->s_bin_hydro.p, bin_hydro, E->n, cudaMemcpyHostToDevice, E->stream));
+    if(bin_hydro) CK(cudaMemcpyAsync(E->s_bin_hydro.p, bin_hydro, E->n, cudaMemcpyDefault, E->stream));
     else CK(cudaMemsetAsync(E->s_bin_hydro.p, 0, n, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     E->s_bins_set = true;
@@ -883,7 +883,7 @@ int sph_set_active(Engine *E, const int32_t *active, int64_t nactive)
     CK(E->s_active.ensure(n)); CK(E->targets.ensure((size_t) (nactive > 0 ? nactive : 1)));
     CK(cudaMemsetAsync(E->s_active.p, 0, n, E->stream));
     if(nactive > 0) {
-        CK(cudaMemcpyAsync(E->targets.p, active, nactive * sizeof(int32_t), cudaMemcpyHostToDevice, E->stream));
+        CK(cudaMemcpyAsync(E->targets.p, active, nactive * sizeof(int32_t), cudaMemcpyDefault, E->stream));
         k_sph_mark_active<<<(unsigned) ((nactive + 255) / 256), 256, 0, E->stream>>>(nactive, E->targets.p, E->s_active.p); CKL(E);
     }
     CK(cudaStreamSynchronize(E->stream));
@@ -898,7 +898,7 @@ int sph_set_state(Engine *E, const double *density, const double *egy, const dou
         {density, &E->s_density}, {egy, &E->s_egy}, {dhsmlfac, &E->s_dhsmlfac}, {divvel, &E->s_divvel}, {curlvel, &E->s_curlvel}};
     for(auto &it : items) {
         CK(it.dst->ensure(n));
-        if(it.src) CK(cudaMemcpyAsync(it.dst->p, it.src, E->n * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+        if(it.src) CK(cudaMemcpyAsync(it.dst->p, it.src, E->n * sizeof(double), cudaMemcpyDefault, E->stream));
     }
     CK(cudaStreamSynchronize(E->stream));
     return 0;
@@ -916,7 +916,7 @@ int sph_set_gas(Engine *E, const double *vel, const double *hsml, const double *
         *it.have = it.src != nullptr;
         if(!it.src) continue;
         CK(it.dst->ensure(it.k * n));
-        CK(cudaMemcpyAsync(it.dst->p, it.src, it.k * E->n * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+        CK(cudaMemcpyAsync(it.dst->p, it.src, it.k * E->n * sizeof(double), cudaMemcpyDefault, E->stream));
     }
     if(!hsml) return failmsg(E, "b200_sph_set_gas: hsml is required");
     CK(cudaStreamSynchronize(E->stream));
@@ -950,7 +950,7 @@ int sph_set_hsml_range(Engine *E, const double *hsml, int64_t first, int64_t cou
 {
     if(!E->s_have[1]) return failmsg(E, "b200_sph_set_hsml_range: call b200_sph_set_gas first");
     if(first < 0 || count < 0 || first + count > E->n) return failmsg(E, "b200_sph_set_hsml_range: bad range");
-    if(count > 0) CK(cudaMemcpyAsync(E->s_hsml.p + first, hsml, count * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+    if(count > 0) CK(cudaMemcpyAsync(E->s_hsml.p + first, hsml, count * sizeof(double), cudaMemcpyDefault, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     return sph_update_hmax(E);
 }

@@ -348,57 +348,93 @@ class ShardedSPH:
         self.box = float(box)
         self.dom = Domain(box, topdepth, self.rank, self.world)
         self.device = torch.device(device)
+        # every tensor operation of this class is issued on the ENGINE's stream: the engine reads and writes these tensors
+        # through raw device pointers, which torch's own stream would not order
+        self.stream = torch.cuda.ExternalStream(engine.stream(), device=self.device)
+
+    def _enter(self):
+        self._caller = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(self._caller)           # inputs made on the caller's stream
+        return torch.cuda.stream(self.stream)
+
+    def _leave(self):
+        self._caller.wait_stream(self.stream)           # results are used on the caller's stream
 
     def load(self, pos, mass, hsml, vel=None, entropy=None, dtentropy=None, fullacc=None, gravpm=None, hydroacc=None):
-        """Own gas particles (device tensors, every x inside the rank's layers)."""
-        n = pos.shape[0]
-        z3 = lambda a: torch.zeros((n, 3), dtype=torch.float64, device=self.device) if a is None else a
-        one = torch.ones(n, dtype=torch.float64, device=self.device)
-        cols = [pos, mass.to(torch.float64)[:, None], z3(vel), hsml[:, None], (one if entropy is None else entropy)[:, None],
-                (0 * one if dtentropy is None else dtentropy)[:, None], z3(fullacc), z3(gravpm), z3(hydroacc)]
-        own = torch.cat(cols, dim=1).contiguous()
-        self.to_l, self.to_r = self.dom.ghost_sets(pos[:, 0])
-        fr, fl = self.comm.neighbour_exchange_var(own[self.to_l], own[self.to_r])
-        self.n_from_left, self.n_from_right = fl.shape[0], fr.shape[0]
-        allp = torch.cat([own, fl, fr], dim=0)
-        self.n_own, self.n_tot = n, allp.shape[0]
-        a = allp.cpu().numpy()
-        self.host = dict(pos=np.ascontiguousarray(a[:, 0:3]), mass=np.ascontiguousarray(a[:, 3]).astype(np.float32),
-                         vel=np.ascontiguousarray(a[:, 4:7]), hsml=np.ascontiguousarray(a[:, 7]), entropy=np.ascontiguousarray(a[:, 8]),
-                         dtentropy=np.ascontiguousarray(a[:, 9]), fullacc=np.ascontiguousarray(a[:, 10:13]),
-                         gravpm=np.ascontiguousarray(a[:, 13:16]), hydroacc=np.ascontiguousarray(a[:, 16:19]))
-        h = self.host
-        self.e.set_particles(h["pos"], h["mass"], type=np.zeros(self.n_tot, np.uint8))
-        self.e.force_tree_build(self.box, mask=1)
-        self.e.sph_set_gas(h["hsml"], vel=h["vel"], entropy=h["entropy"], dtentropy=h["dtentropy"], fullacc=h["fullacc"],
-                           gravpm=h["gravpm"], hydroacc=h["hydroacc"])
-        self.e.sph_set_active(np.arange(n, dtype=np.int32))
-        return self.n_tot - n
+        """Own gas particles (device tensors, every x inside the rank's layers).  The state stays in HBM: the ghosts arrive
+        by neighbour exchange of device tensors and the engine takes device pointers (include/b200force.h, SPH section)."""
+        with self._enter():
+            n = pos.shape[0]
+            z3 = lambda a: torch.zeros((n, 3), dtype=torch.float64, device=self.device) if a is None else a
+            one = torch.ones(n, dtype=torch.float64, device=self.device)
+            cols = [pos, mass.to(torch.float64)[:, None], z3(vel), hsml[:, None], (one if entropy is None else entropy)[:, None],
+                    (0 * one if dtentropy is None else dtentropy)[:, None], z3(fullacc), z3(gravpm), z3(hydroacc)]
+            own = torch.cat(cols, dim=1).contiguous()
+            self.to_l, self.to_r = self.dom.ghost_sets(pos[:, 0])
+            fr, fl = self.comm.neighbour_exchange_var(own[self.to_l], own[self.to_r])
+            self.n_from_left, self.n_from_right = fl.shape[0], fr.shape[0]
+            allp = torch.cat([own, fl, fr], dim=0)
+            self.n_own, self.n_tot = n, allp.shape[0]
+            col = lambda a, b: allp[:, a:b].contiguous() if b - a > 1 else allp[:, a].contiguous()
+            st = self.dev = dict(pos=col(0, 3), mass=allp[:, 3].to(torch.float32).contiguous(), vel=col(4, 7), hsml=col(7, 8), entropy=col(8, 9),
+                                 dtentropy=col(9, 10), fullacc=col(10, 13), gravpm=col(13, 16), hydroacc=col(16, 19),
+                                 type=torch.zeros(self.n_tot, dtype=torch.uint8, device=self.device),
+                                 own=torch.arange(n, dtype=torch.int32, device=self.device))
+            del allp, own
+            self.e.set_particles_dev(st["pos"].data_ptr(), st["mass"].data_ptr(), self.n_tot, type_ptr=st["type"].data_ptr())
+            self.e.force_tree_build(self.box, mask=1)
+            self.e.sph_set_gas(st["hsml"], vel=st["vel"], entropy=st["entropy"], dtentropy=st["dtentropy"], fullacc=st["fullacc"],
+                               gravpm=st["gravpm"], hydroacc=st["hydroacc"])
+            self.e.sph_set_active(st["own"])
+            self._leave()
+            return self.n_tot - n
+
+    def set_active(self, active_own):
+        """Restrict the targets of the next density / hydro pass to these own particles (int32 device tensor of indices
+        < n_own): the active particles of a sub-step (timestep.c:1334-1431); everything else stays a source."""
+        with self._enter():
+            self.e.sph_set_active(active_own.to(torch.int32).contiguous())
+
+    def set_mixed(self, bins_own, tables, active_own, ghost_bin=12):
+        """A sub-step with mixed time bins after load(): per-particle time bins (uint8 device tensor for the own particles;
+        the ghosts, sources only, get ghost_bin) with the per-bin factor tables of Engine.sph_set_timebins, the state of the
+        last density pass for the particles that stay inactive, and the active own particles as targets."""
+        with self._enter():
+            bh = torch.cat([bins_own.to(torch.uint8), torch.full((self.n_tot - self.n_own,), ghost_bin, dtype=torch.uint8, device=self.device)]).contiguous()
+            self.e.sph_set_timebins(bh, bh, tables)
+            self.e.sph_set_state(**{k: self.state[k] for k in ("density", "egywtdensity", "dhsmlfac", "divvel", "curlvel")})
+            self.e.sph_set_active(active_own.to(torch.int32).contiguous())
 
     def density(self, sp, DoEgyDensity=0):
-        d = self.e.density(sp, update_hsml=1, DoEgyDensity=DoEgyDensity)
-        n = self.n_own
-        # converged state of the particles I exported, back to the ranks that hold them as ghosts
-        st = torch.from_numpy(np.stack([d[k][:n] for k in self.STATE_KEYS], axis=1)).to(self.device)
-        fr, fl = self.comm.neighbour_exchange_var(st[self.to_l].contiguous(), st[self.to_r].contiguous())
-        assert fl.shape[0] == self.n_from_left and fr.shape[0] == self.n_from_right
-        g = torch.cat([fl, fr], dim=0).cpu().numpy()
-        full = {k: d[k].copy() for k in self.STATE_KEYS}
-        for c, k in enumerate(self.STATE_KEYS):
-            full[k][n:] = g[:, c]
-        hmax = torch.tensor([float(full["hsml"][:n].max()) if n else 0.0], dtype=torch.float64, device=self.device)
-        if self.world > 1:
-            self.comm.dist.all_reduce(hmax, op=self.comm.dist.ReduceOp.MAX)
-        if self.world > 1 and not self.dom.seamwidth > float(hmax.item()):
-            raise ValueError("top-tree cells (%.4g) must be wider than the largest smoothing length (%.4g): lower topdepth"
-                             % (self.dom.cellwidth, float(hmax.item())))
-        self.e.sph_set_state(density=full["density"], egywtdensity=full["egywtdensity"], dhsmlfac=full["dhsmlfac"],
-                             divvel=full["divvel"], curlvel=full["curlvel"])
-        if self.n_tot > n:
-            self.e.sph_set_hsml_range(full["hsml"][n:], n)
-        self.state = full
-        return {k: v[:n] for k, v in d.items() if hasattr(v, "__len__") and len(v) == self.n_tot}
+        with self._enter():
+
+            d = self.e.density(sp, update_hsml=1, DoEgyDensity=DoEgyDensity, device=self.device)
+            n = self.n_own
+            # converged state of the particles I exported, back to the ranks that hold them as ghosts
+            st = torch.stack([d[k][:n] for k in self.STATE_KEYS], dim=1)
+            fr, fl = self.comm.neighbour_exchange_var(st[self.to_l].contiguous(), st[self.to_r].contiguous())
+            assert fl.shape[0] == self.n_from_left and fr.shape[0] == self.n_from_right
+            g = torch.cat([fl, fr], dim=0)
+            full = {}
+            for c, k in enumerate(self.STATE_KEYS):
+                full[k] = torch.cat([d[k][:n], g[:, c]]).contiguous()
+            hmax = full["hsml"][:n].max().reshape(1) if n else torch.zeros(1, dtype=torch.float64, device=self.device)
+            if self.world > 1:
+                self.comm.dist.all_reduce(hmax, op=self.comm.dist.ReduceOp.MAX)
+            if self.world > 1 and not self.dom.seamwidth > float(hmax.item()):
+                raise ValueError("top-tree cells (%.4g) must be wider than the largest smoothing length (%.4g): lower topdepth"
+                                 % (self.dom.cellwidth, float(hmax.item())))
+            self.e.sph_set_state(density=full["density"], egywtdensity=full["egywtdensity"], dhsmlfac=full["dhsmlfac"],
+                                 divvel=full["divvel"], curlvel=full["curlvel"])
+            if self.n_tot > n:
+                self.e.sph_set_hsml_range(full["hsml"][n:].contiguous(), n)
+            self.state = full
+            self._leave()
+            return {k: v[:n] for k, v in d.items()}
 
     def hydro_force(self, sp):
-        h = self.e.hydro_force(sp)
-        return {k: v[:self.n_own] for k, v in h.items()}
+        with self._enter():
+
+            h = self.e.hydro_force(sp, device=self.device)
+            self._leave()
+            return {k: v[:self.n_own] for k, v in h.items()}

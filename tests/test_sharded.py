@@ -235,10 +235,10 @@ def test_sharded_sph_world1_equals_unsharded(b200, ics):
     d1 = s.density(sp, DoEgyDensity=1)
     h1 = s.hydro_force(sp)
     e.close()
-    for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel"):
-        assert np.array_equal(d1[k], d0[k]), k
+    for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel"):       # the state never left the device
+        assert d1[k].is_cuda and np.array_equal(d1[k].cpu().numpy(), d0[k]), k
     for k in ("acc", "dtentropy", "maxsignalvel"):
-        assert np.array_equal(h1[k], h0[k]), k
+        assert np.array_equal(h1[k].cpu().numpy(), h0[k]), k
 
 
 SPH_GPU_WORKER = r'''
@@ -263,8 +263,8 @@ sp = pkg.sph_params(KernelType=1, DensityIndependentSphOn=1, MinGasHsml=1e-4, at
 d = s.density(sp, DoEgyDensity=1)
 h = s.hydro_force(sp)
 np.savez(os.path.join(%(out)r, "sph_%%d.npz" %% rank), idx=np.nonzero(sel)[0], nghost=nghost,
-         **{"d_" + k: d[k] for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel")},
-         **{"h_" + k: h[k] for k in ("acc", "dtentropy", "maxsignalvel")})
+         **{"d_" + k: d[k].cpu().numpy() for k in ("hsml", "density", "egywtdensity", "dhsmlfac", "divvel", "curlvel")},
+         **{"h_" + k: h[k].cpu().numpy() for k in ("acc", "dtentropy", "maxsignalvel")})
 dist.barrier(); dist.destroy_process_group()
 '''
 
