@@ -32,6 +32,7 @@
 
 #include <libgadget/utils/endrun.h>
 #include <libgadget/utils/mymalloc.h>
+#include <libgadget/utils/system.h>
 #include <libgadget/partmanager.h>
 #include <libgadget/slotsmanager.h>
 #include <libgadget/timestep.h>
@@ -148,6 +149,42 @@ void __wrap_drift_all_particles(inttime_t ti0, inttime_t ti1, Cosmology *CP, con
     walltime_measure("/Drift");
 }
 
+/* The per-bin occupancy log of build_active_particles (print_timebin_statistics, timestep.c:1491-1585, file-static there):
+ * the counts come from the device histogram (TimeBinCountType of b200_step_build_active), summed over the ranks as the
+ * reference does, and the root prints the step header and one line per occupied bin. */
+static void shim_timebin_statistics(const DriftKickTimes *times, int NumCurrentTiStep, const int64_t *loc, double Time)
+{
+    static int64_t tot[6 * (TIMEBINS + 1)];
+    MPI_Reduce((void *) loc, tot, 6 * (TIMEBINS + 1), MPI_INT64, MPI_SUM, 0, MPI_COMM_WORLD);
+    int ThisTask;
+    MPI_Comm_rank(MPI_COMM_WORLD, &ThisTask);
+    if(ThisTask != 0) return;
+    int64_t nforce = 0, npart = 0, ntype[6] = {0};
+    for(int bin = 0; bin <= TIMEBINS; bin++) {
+        int64_t inbin = 0;
+        for(int ty = 0; ty < 6; ty++) { inbin += tot[(TIMEBINS + 1) * ty + bin]; ntype[ty] += tot[(TIMEBINS + 1) * ty + bin]; }
+        npart += inbin;
+        if(is_timebin_active(bin, times->Ti_Current)) nforce += inbin;
+    }
+    const double dloga = get_dloga_for_bin(times->mintimebin, times->Ti_Current);
+    message(0, "Begin Step %d, Time: %g (%lx), Redshift: %g, Nf = %014ld, Systemstep: %g, Dloga: %g, status: %s\n",
+            NumCurrentTiStep, Time, times->Ti_Current, 1.0 / Time - 1, nforce, dloga * Time, dloga, is_PM_timestep(times) ? "PM-Step" : "");
+    message(0, "TotNumPart: %013ld SPH %013ld BH %010ld STAR %013ld \n", npart, ntype[0], ntype[5], ntype[4]);
+    message(0, "Occupied: % 12ld % 12ld % 12ld % 12ld % 12ld % 12ld dt\n", 0L, 1L, 2L, 3L, 4L, 5L);
+    int64_t act[6] = {0}, acttot = 0;
+    for(int bin = TIMEBINS; bin >= 0; bin--) {
+        const int64_t *c = tot + bin;
+        const int64_t inbin = c[0] + c[TIMEBINS + 1] + c[2 * (TIMEBINS + 1)] + c[3 * (TIMEBINS + 1)] + c[4 * (TIMEBINS + 1)] + c[5 * (TIMEBINS + 1)];
+        if(inbin == 0) continue;
+        const int on = is_timebin_active(bin, times->Ti_Current);
+        message(0, " %c bin=%2d % 12ld % 12ld % 12ld % 12ld % 12ld % 12ld %6g\n", on ? 'X' : ' ', bin, c[0], c[TIMEBINS + 1], c[2 * (TIMEBINS + 1)],
+                c[3 * (TIMEBINS + 1)], c[4 * (TIMEBINS + 1)], c[5 * (TIMEBINS + 1)], get_dloga_for_bin(bin, times->Ti_Current));
+        if(on) { acttot += inbin; for(int ty = 0; ty < 6; ty++) act[ty] += c[ty * (TIMEBINS + 1)]; }
+    }
+    message(0, "               -----------------------------------\n");
+    message(0, "Total:    % 12ld % 12ld % 12ld % 12ld % 12ld % 12ld  Sum:% 14ld\n", act[0], act[1], act[2], act[3], act[4], act[5], acttot);
+}
+
 /* ---- timestep.c:1334-1431 ---- */
 void __wrap_build_active_particles(ActiveParticles *act, const DriftKickTimes *const times, const int NumCurrentTiStep, const double Time,
                                    const struct part_manager_type *const PartManager)
@@ -155,8 +192,9 @@ void __wrap_build_active_particles(ActiveParticles *act, const DriftKickTimes *c
     b200_ctx *ctx = b200_shim_context();
     step_upload();
     int64_t counts[3];
+    static int64_t bincounts[6 * (TIMEBINS + 1)];
     const int is_pm = is_PM_timestep(times);
-    B200_CK(b200_step_build_active(ctx, times->Ti_Current, is_pm, NumGasSlots(), counts, NULL));
+    B200_CK(b200_step_build_active(ctx, times->Ti_Current, is_pm, NumGasSlots(), counts, bincounts));
     act->NumActiveParticle = counts[0]; act->NumActiveGravity = counts[1]; act->NumActiveHydro = counts[2];
     act->Particles = PartManager->Base;
     act->ActiveParticle = NULL;
@@ -168,6 +206,7 @@ void __wrap_build_active_particles(ActiveParticles *act, const DriftKickTimes *c
         if(nout != act->NumActiveParticle) endrun(1, "b200 step shims: active list length %ld != %ld\n", (long) nout, (long) act->NumActiveParticle);
     }
     walltime_measure("/Timeline/Active");
+    shim_timebin_statistics(times, NumCurrentTiStep, bincounts, Time);
 }
 
 /* ---- timestep.c:874-994 ---- */

@@ -213,21 +213,26 @@ class StepEngine:
         self._ck(self.L.b200_step_get_state(self.ctx, C.byref(so)))
         return out
 
-    def hydro_timesteps(self, maxsig, atime, first=False):
-        """find_hydro_timesteps on the current active list -> (bad count, TimeBinHydro[n])"""
+    def hydro_timesteps(self, maxsig, atime, first=False, fetch=True):
+        """find_hydro_timesteps on the current active list -> (bad count, TimeBinHydro[n]).  maxsig = None: the
+        SphP[].MaxSignalVel already in the step state (adopt_hydro); fetch = False: only the count crosses PCIe (the loop
+        drivers), the bins stay on the device."""
         ms = _c(maxsig, np.float64)
         nbad = C.c_int64()
         self._ck(self.L.b200_step_hydro_timesteps(self.ctx, C.byref(self.sp), C.byref(self.t), _p(ms), C.c_double(atime),
                                                   C.c_double(float(self.hubble(atime))), C.byref(nbad)))
-        return int(nbad.value), self.get()["bin_hydro"]
+        return int(nbad.value), (self.get()["bin_hydro"] if fetch else None)
 
-    def find_timesteps(self, maxsig, atime, asmth=None, first=False):
+    def find_timesteps(self, maxsig, atime, asmth=None, first=False, fetch=True):
         """find_timesteps (SplitGravityTimestepsOn = 0) on the current active list -> (bad, TimeBinGravity[n], TimeBinHydro[n]);
-        the PM smoothing scale comes from gravpm_init_periodic (set_gravity)."""
+        the PM smoothing scale comes from gravpm_init_periodic (set_gravity).  maxsig = None and fetch = False as in
+        hydro_timesteps: nothing of size n crosses PCIe."""
         ms = _c(maxsig, np.float64)
         nbad = C.c_int64()
         self._ck(self.L.b200_step_find_timesteps(self.ctx, C.byref(self.sp), C.byref(self.t), _p(ms), C.c_int(1 if self.is_pm() else 0),
                                                  C.c_double(atime), C.c_double(float(self.hubble(atime))), C.byref(nbad)))
+        if not fetch:
+            return int(nbad.value), None, None
         g = self.get()
         return int(nbad.value), g["bin_grav"], g["bin_hydro"]
 
@@ -270,7 +275,7 @@ class StepEngine:
             self._ck(self.L.b200_step_hier_timesteps(self.ctx, C.byref(self.sp), C.byref(self.gp), C.byref(t), C.c_int64(int(counts[1])),
                                                      C.c_int(1 if is_pm else 0), C.c_double(atime), C.c_double(float(self.hubble(atime))), _p(info)))
         if maxsig is not None:          # run.c:767-773
-            b2, _ = self.hydro_timesteps(maxsig, atime, first)
+            b2, _ = self.hydro_timesteps(maxsig, atime, first, fetch=False)
             info[2] += b2
             self.kick(1, atime)
         self.kick(3)
@@ -296,7 +301,7 @@ class StepEngine:
         self.kick(0, atime); self.kick(3)
         if is_pm:
             self.kick(2)
-        bad, _, _ = self.find_timesteps(np.zeros(self.n), atime, first=first)
+        bad, _, _ = self.find_timesteps(None, atime, first=first, fetch=False)      # no gas criterion input: the state's own MaxSignalVel
         self.kick(0, atime); self.kick(3)
         if is_pm:
             self.kick(2)
