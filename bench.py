@@ -39,7 +39,7 @@ CPU_KIND = "reference tree + restated PM"       # forcetree.c/treewalk.c/gravsho
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (profiles/),
 # 256^3 workload; None where no capture of the current kernel exists
-NCU_TRAFFIC = {"k_grav_pairs": 6.85e9, "k_grav_walk": None}
+NCU_TRAFFIC = {"k_grav_pairs": 7.45e9, "k_grav_walk": 10.70e9}      # profiles/r02_grav_{pairs,walk}_ncu_summary.txt
 FP64_DFMA_PER_SM_CLK = 64.0                      # B200: 64 fp64 FMA lanes per SM
 
 
