@@ -26,17 +26,24 @@ gen = torch.Generator(device=dev); gen.manual_seed(1000)
 vel = 0.05 * torch.randn((n, 3), dtype=torch.float64, device=dev, generator=gen)
 ent = torch.ones(n, dtype=torch.float64, device=dev)
 h0 = torch.full((n,), 3.0 * 0.8, dtype=torch.float64, device=dev)
+import time
 def step(hs, active=None, bins=None, tag=""):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
     nghost = s.load(pos, mass, hs, vel=vel, entropy=ent)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
     if bins is not None:
         tab = {k: np.zeros(47) for k in ("gravkick", "hydrokick", "dloga_pred", "drift")}; tab["dloga_bin"] = np.full(47, 0.01)
         s.set_mixed(bins, tab, active)
+    torch.cuda.synchronize(); t2 = time.perf_counter()
     try:
         d = s.density(sp, DoEgyDensity=1)
     except Exception as ex:
         hh = torch.zeros(s.n_tot, dtype=torch.float64, device=dev)
         print(tag, "FAILED", ex); raise
+    torch.cuda.synchronize(); t3 = time.perf_counter()
     h = s.hydro_force(sp)
+    torch.cuda.synchronize(); t4 = time.perf_counter()
+    print("r%d" % local, tag, "wall ms: load %.1f set %.1f density %.1f hydro %.1f" % (1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3)), flush=True)
     sel = slice(None) if active is None else active.long()
     print("r%d" % local, tag, "ghosts", nghost, "niter mean %.2f max %d" % (d["niter"][sel].double().mean().item(), d["niter"][sel].max().item()),
           "hsml min %.3f max %.3f" % (d["hsml"].min().item(), d["hsml"].max().item()), "dens min %.3g" % d["density"].min().item(),
@@ -48,4 +55,4 @@ for k in range(2): step(hw, tag="warm%d" % k)
 idx = torch.arange(n, device=dev)
 act = idx[(idx % 4) == 0].to(torch.int32).contiguous()
 bins = torch.where((idx % 4) == 0, 10, 12).to(torch.uint8)
-for k in range(3): step(hw, active=act, bins=bins, tag="mixed%d" % k)
+for k in range(5): step(hw, active=act, bins=bins, tag="mixed%d" % k)
