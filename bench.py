@@ -275,7 +275,11 @@ def run_sharded(args, rank, world, local, dist, pkg, ics, W, K):
     nghost = s.n_tot - s.n_own
     sharded_phases = s.phase_ms() if hasattr(s, "phase_ms") else {}
 
-    last_oldacc = s.last_oldacc.clone() if getattr(s, "last_oldacc", None) is not None else None     # inputs of the step the parity check repeats
+    # inputs and results of the last timed step, which the parity check below repeats (the result tensors are views of the
+    # engine's output buffers: later steps overwrite them)
+    last_oldacc = s.last_oldacc.clone() if getattr(s, "last_oldacc", None) is not None else None
+    if not args.no_parity:
+        last = {k: v.clone() for k, v in last.items()}
 
     # e2e: own particles from pinned host memory in, accelerations back to pinned host memory
     hpos = torch.empty((n_own, 3), dtype=torch.float64).pin_memory(); hpos.copy_(pos)
