@@ -731,6 +731,7 @@ def main():
     fp64_peak_slots = 148 * FP64_DFMA_PER_SM_CLK * smhz * 1e6 / 26.0
     N3 = float(nmesh) ** 3
     Mc = float(nmesh) ** 2 * (nmesh // 2 + 1)
+    own_fft = e.pm_transform_kind() == 1
     kern = {
         "k_grav_walk": {"ms": walk_ms, "alg_bytes": walk_bytes},
         "k_grav_pairs": {"ms": pairs_ms, "alg_bytes": pairs_bytes, "pair_evaluations": pair_slots,
@@ -738,9 +739,15 @@ def main():
                          "fp64_pipe_frac": pair_slots / (pairs_ms * 1e-3) / fp64_peak_slots,
                          "fp64_pipe_note": "26 fp64-pipe instructions per pair slot against 148 SMs x 64 lanes x %.0f MHz" % smhz},
         "k_pm_deposit+clear": {"ms": phase["pm_deposit"], "alg_bytes": 156.0 * n + 8 * N3},
-        "cufft_d2z": {"ms": phase["pm_fft_forward"], "alg_bytes": 16 * N3},
-        "k_pm_potential_transfer": {"ms": phase["pm_transfer"], "alg_bytes": 32 * Mc},
-        "cufft_z2d": {"ms": phase["pm_fft_inverse"], "alg_bytes": 16 * N3},
+        # the transforms.  Own passes (csrc/pm_fft.cu): every pass reads and writes each value once -- z pass 8 B/cell real
+        # side + 16 B/mode spectrum side, column passes 32 B/mode.  cuFFT: 16 B/cell per transform is the floor it is held to.
+        **({"k_fft_z_forward+k_fft_columns<y>": {"ms": phase["pm_fft_forward"], "alg_bytes": 8 * N3 + 48 * Mc},
+            "k_fft_columns<x forward, potential_transfer, x inverse>": {"ms": phase["pm_transfer"], "alg_bytes": 32 * Mc},
+            "k_fft_columns<y inverse>+k_fft_z_inverse": {"ms": phase["pm_fft_inverse"], "alg_bytes": 8 * N3 + 48 * Mc}}
+           if own_fft else
+           {"cufft_d2z": {"ms": phase["pm_fft_forward"], "alg_bytes": 16 * N3},
+            "k_pm_potential_transfer": {"ms": phase["pm_transfer"], "alg_bytes": 32 * Mc},
+            "cufft_z2d": {"ms": phase["pm_fft_inverse"], "alg_bytes": 16 * N3}}),
         # difference + readout fused: the potential mesh is read once (8 B/cell) instead of the
         # 32 B/cell of the three force meshes, plus the particle side of the gather
         "k_pm_readout_fused": {"ms": phase["pm_gradient"] + phase["pm_readout"], "alg_bytes": 8 * N3 + (24.0 + 32.0) * n},
@@ -751,7 +758,8 @@ def main():
         k["frac"] = k["GBps"] / hbm if k["GBps"] else None
     cfg = workload_config(ng, nmesh, args.state)
     cfg.update({"particles_per_gpu": n, "l2": "inputs larger than L2 (particle arrays %.0f MB, mesh %.1f GB)" % (n * 28 / 1e6, N3 * 8 / 1e9),
-                "parallelism": "single GPU"})
+                "parallelism": "single GPU",
+                "pm_transforms": "own shared-memory passes, Green's function fused (csrc/pm_fft.cu)" if own_fft else "cuFFT D2Z/Z2D + k_pm_potential_transfer"})
     # the dominant kernel of the step: whichever half of the short-range tree gravity took longer
     dom = max(("k_grav_walk", "k_grav_pairs"), key=lambda k: kern[k]["ms"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["GBps"], "peak": hbm, "unit": "GB/s",

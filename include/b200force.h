@@ -110,6 +110,11 @@ int b200_walk_set_mesh(b200_ctx *ctx, double BoxSize, double Asmth, int Nmesh, d
  * added to P[i].Potential) for every particle; either may be NULL. */
 int b200_pm_force(b200_ctx *ctx, double *gravpm_out, double *potential_out);
 int b200_pm_force_dev(b200_ctx *ctx, double *gravpm_out, double *potential_out);
+/* How pfft_execute_dft_r2c -> potential_transfer -> pfft_execute_dft_c2r (petapm.c:305,326-344) run for the
+ * mesh b200_pm_init set up: 1 = the engine's five shared-memory passes with the Green's function inside the
+ * x pass (mesh sizes 2^a 3^b 5^c up to 1614), 0 = cuFFT D2Z / Z2D around a separate Green's-function kernel
+ * (other sizes, or B200_PM_FFT=cufft in the environment at b200_pm_init), -1 = no mesh. */
+int b200_pm_transform_kind(b200_ctx *ctx);
 /* Matter power spectrum side effect of gravpm_force: potential_transfer calls
  * powerspectrum_add_mode on every density mode before scaling it
  * (gravpm.c:330-361,440).  b200_pm_set_power(ctx, 1) makes the next b200_pm_force

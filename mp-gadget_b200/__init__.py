@@ -108,7 +108,7 @@ EXPORTED = [
     "b200_default_particle_layout", "b200_ctx_create", "b200_ctx_destroy", "b200_last_error",
     "b200_abi_version", "b200_kernel_launches", "b200_set_particles_aos", "b200_set_particles_soa",
     "b200_set_particles_soa_dev", "b200_oldacc_from_last_step", "b200_pm_init", "b200_walk_set_mesh", "b200_pm_force",
-    "b200_pm_force_dev", "b200_pm_set_power", "b200_pm_get_power", "b200_pm_cell_index", "b200_pm_copy_mesh", "b200_tree_build", "b200_tree_free",
+    "b200_pm_force_dev", "b200_pm_transform_kind", "b200_pm_set_power", "b200_pm_get_power", "b200_pm_cell_index", "b200_pm_copy_mesh", "b200_tree_build", "b200_tree_free",
     "b200_tree_export", "b200_grav_short_tree", "b200_grav_short_tree_dev", "b200_force_step_aos", "b200_force_step_aos_bytes", "b200_force_step_dev",
     "b200_get_timings", "b200_stream",
     "b200_tree_top_get_dev", "b200_tree_top_set_dev",
@@ -239,6 +239,10 @@ class Engine:
     def gravpm_force_dev(self, gravpm_ptr=None, pot_ptr=None):
         self._ck(self.L.b200_pm_force_dev(self.ctx, C.c_void_p(gravpm_ptr) if gravpm_ptr else None,
                                           C.c_void_p(pot_ptr) if pot_ptr else None))
+
+    def pm_transform_kind(self):
+        """1: the engine's own shared-memory transform passes (csrc/pm_fft.cu); 0: cuFFT; -1: no mesh."""
+        return int(self.L.b200_pm_transform_kind(self.ctx))
 
     def pm_power(self):
         """Raw power-spectrum sums of the last gravpm_force (after pm_set_power(True))."""

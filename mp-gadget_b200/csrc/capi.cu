@@ -376,6 +376,13 @@ static int pm_force_common(Engine *E, double *gravpm_out, double *potential_out,
 int b200_pm_force(b200_ctx *ctx, double *gravpm_out, double *potential_out) { ENTER(ctx); return pm_force_common(E, gravpm_out, potential_out, true); }
 int b200_pm_force_dev(b200_ctx *ctx, double *gravpm_out, double *potential_out) { ENTER(ctx); return pm_force_common(E, gravpm_out, potential_out, false); }
 
+int b200_pm_transform_kind(b200_ctx *ctx)
+{
+    if(!ctx) return -1;
+    Engine *E = &ctx->e;
+    return E->Nmesh == 0 || (!E->ownfft && !E->plans) ? -1 : (E->ownfft ? 1 : 0);
+}
+
 int b200_pm_set_power(b200_ctx *ctx, int on)
 {
     ENTER(ctx);
@@ -523,11 +530,11 @@ static int pm_force_forked(Engine *E, double *d_gravpm, double *d_pot)
     CK(cudaStreamWaitEvent(E->side_stream, E->fork_ev, 0));
     cudaStream_t main_stream = E->stream;
     E->stream = E->side_stream;
-    cufftSetStream(E->plan_fwd, E->stream); cufftSetStream(E->plan_inv, E->stream);
+    if(E->plans) { cufftSetStream(E->plan_fwd, E->stream); cufftSetStream(E->plan_inv, E->stream); }
     const int rc = pm_force(E, d_gravpm, d_pot);
     cudaEventRecord(E->join_ev, E->stream);
     E->stream = main_stream;
-    cufftSetStream(E->plan_fwd, E->stream); cufftSetStream(E->plan_inv, E->stream);
+    if(E->plans) { cufftSetStream(E->plan_fwd, E->stream); cufftSetStream(E->plan_inv, E->stream); }
     return rc;
 }
 static int pm_join(Engine *E)

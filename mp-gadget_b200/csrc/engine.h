@@ -48,6 +48,7 @@ struct NodeAux {           // int4
 
 struct SlabPM;
 struct Sharded;
+struct OwnFFT;
 
 #define B200_SPART_PAD 16     // massless far-away rows behind spart[np) (tree_walk.cu pair loop)
 
@@ -84,6 +85,8 @@ struct Engine {
     DevBuf<double> fmesh;      // 3 force meshes
     DevBuf<double> ktab;       // per-dimension deconvolution factor 1/sinc^2, [Nmesh]
     DevBuf<uint8_t> fftwork;
+    OwnFFT *ownfft = nullptr;  // pm_fft.cu: the shared-memory transform passes (null: cuFFT plans above)
+    DevBuf<double> fft_tab;    // its twiddle and row-order tables
     bool potential_valid = false;
     bool pm_fused = true;      // difference + readout in one kernel, no force meshes (B200_PM_FUSED=0: separate passes)
     bool fmesh_valid = false;
@@ -202,6 +205,13 @@ int pm_deposit(Engine *E);
 int pm_force(Engine *E, double *d_gravpm, double *d_pot);   // device outputs, [n][3] / [n], may be null
 int pm_force_meshes(Engine *E);
 int pm_cell_index(Engine *E, int32_t *d_icell);
+
+// PM transforms (pm_fft.cu)
+bool pmfft_supported(int N);
+int pmfft_init(Engine *E, int N);
+void pmfft_destroy(Engine *E);
+size_t pmfft_cplx_doubles(const Engine *E);
+int pmfft_potential(Engine *E, double asmth2, double pot_factor, double binsperunit, double *ps);
 
 // tree (tree_build.cu)
 int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t nactive,

@@ -25,6 +25,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace b200 {
 
@@ -284,6 +285,7 @@ void pm_destroy(Engine *E)
         cufftDestroy(E->plan_inv);
         E->plans = false;
     }
+    pmfft_destroy(E);
     E->mesh.release(); E->cplx.release(); E->fmesh.release(); E->ktab.release(); E->fftwork.release();
     E->Nmesh = 0;
 }
@@ -293,16 +295,23 @@ int pm_init(Engine *E, double Box, double Asmth, int Nmesh, double G)
 {
     if(Nmesh < 8 || (Nmesh & 1)) return failmsg(E, "b200_pm_init: Nmesh must be even and >= 8");
     if(!(Box > 0)) return failmsg(E, "b200_pm_init: BoxSize must be positive");
-    if(E->plans && E->Nmesh == Nmesh) {
+    if((E->plans || E->ownfft) && E->Nmesh == Nmesh) {
         E->Box = Box; E->Asmth = Asmth; E->G = G;
     } else {
         pm_destroy(E);
         E->Box = Box; E->Asmth = Asmth; E->G = G; E->Nmesh = Nmesh;
         const size_t N = Nmesh, Nz = Nmesh / 2 + 1;
         CK(E->mesh.ensure(N * N * N));
-        CK(E->cplx.ensure(2 * N * N * Nz));
         E->pm_fused = !(getenv("B200_PM_FUSED") && atoi(getenv("B200_PM_FUSED")) == 0);
         if(!E->pm_fused) CK(E->fmesh.ensure(3 * N * N * N));
+        // the transforms: five shared-memory passes with the Green's function inside (pm_fft.cu) for mesh sizes
+        // 2^a 3^b 5^c that fit a tile; cuFFT + k_pm_potential_transfer otherwise or with B200_PM_FFT=cufft
+        const char *sel = getenv("B200_PM_FFT");
+        if(pmfft_supported(Nmesh) && !(sel && !strcmp(sel, "cufft"))) {
+            if(int rc = pmfft_init(E, Nmesh)) return rc;
+            CK(E->cplx.ensure(pmfft_cplx_doubles(E)));
+        } else {
+        CK(E->cplx.ensure(2 * N * N * Nz));
         size_t ws_f = 0, ws_i = 0;
         CKF(cufftCreate(&E->plan_fwd));
         CKF(cufftCreate(&E->plan_inv));
@@ -317,6 +326,7 @@ int pm_init(Engine *E, double Box, double Asmth, int Nmesh, double G)
         CKF(cufftSetWorkArea(E->plan_inv, E->fftwork.p));
         CKF(cufftSetStream(E->plan_fwd, E->stream));
         CKF(cufftSetStream(E->plan_inv, E->stream));
+        }
     }
     // CIC deconvolution table, gravpm.c:403-407: tmp = (k*pi)/Nmesh; 1/sinc(tmp)^2.
     std::vector<double> tab(Nmesh);
@@ -383,6 +393,18 @@ int pm_force(Engine *E, double *d_gravpm, double *d_pot)
     if(int rc = pm_deposit(E)) return rc;
     timer_stop(E, T_PM_DEPOSIT);
 
+    const double asmth2 = pow((2 * M_PI) * E->Asmth / N, 2);       // gravpm.c:386
+    const double pot_factor = -E->G / (M_PI * E->Box);              // gravpm.c:392
+    if(E->ownfft) {
+        double *ps = nullptr;
+        if(E->pm_power) {
+            CK(E->pm_ps.ensure(3 * (size_t) N + 1));
+            CK(cudaMemsetAsync(E->pm_ps.p, 0, (3 * (size_t) N + 1) * sizeof(double), E->stream));
+            ps = E->pm_ps.p;
+        }
+        if(int rc = pmfft_potential(E, asmth2, pot_factor, (N - 1) / log(sqrt(3.) * N / 2.0), ps)) return rc;
+        if(ps) E->pm_ps_valid = true;
+    } else {
     timer_start(E, T_PM_FFT_FWD);
     CKF(cufftExecD2Z(E->plan_fwd, E->mesh.p, (cufftDoubleComplex *) E->cplx.p));
     E->launches += 1;
@@ -390,8 +412,6 @@ int pm_force(Engine *E, double *d_gravpm, double *d_pot)
 
     timer_start(E, T_PM_TRANSFER);
     {
-        const double asmth2 = pow((2 * M_PI) * E->Asmth / N, 2);       // gravpm.c:386
-        const double pot_factor = -E->G / (M_PI * E->Box);              // gravpm.c:392
         if(E->pm_power) {
             CK(E->pm_ps.ensure(3 * (size_t) N + 1));
             CK(cudaMemsetAsync(E->pm_ps.p, 0, (3 * (size_t) N + 1) * sizeof(double), E->stream));
@@ -411,6 +431,7 @@ int pm_force(Engine *E, double *d_gravpm, double *d_pot)
     CKF(cufftExecZ2D(E->plan_inv, (cufftDoubleComplex *) E->cplx.p, E->mesh.p));
     E->launches += 1;
     timer_stop(E, T_PM_FFT_INV);
+    }
     E->potential_valid = true;
 
     E->fmesh_valid = false;

@@ -1,0 +1,550 @@
+// pm_fft.cu -- the PM step's transforms as five shared-memory passes with the Green's function inside.
+//
+// Replaces, for one resident mesh, pfft_execute_dft_r2c -> potential_transfer -> pfft_execute_dft_c2r
+// (petapm.c:305,326-344, gravpm.c:383-454): the density mesh goes in, the potential mesh comes out.
+// cuFFT needs 5 passes over the data per 3-D transform plus the transfer kernel in between (11 passes,
+// 20 ms at 768^3); here every pass moves each value through HBM exactly once in each direction:
+//
+//   z forward   real lines [x][y][0..N)  -> half spectrum [x][y][0..N/2]      (length-N/2 complex FFT of the
+//                                                                               packed line + split)
+//   y forward   columns over y, in place
+//   x forward + potential_transfer (+ powerspectrum_add_mode) + x inverse, in place, one kernel
+//   y inverse   in place
+//   z inverse   half spectrum -> real lines
+//
+// A tile is L rows x 8 complex values (128 contiguous bytes of the half spectrum) in shared memory; 8
+// neighbouring threads own the 8 columns of a row, so every shared-memory access of a quarter warp is
+// one conflict-free 128-byte wavefront whatever the row, and every global access is a full 128-byte
+// line.  The transform is an in-place decimation-in-frequency chain (radix 4/2/3/5, two radix-4 levels
+// or a radix-4 and a radix-2 level fused in registers = radix 16 / 8); its digit-reversed output order is
+// never undone in shared memory: stores and the Green's function look rows up through a small table,
+// and the inverse is the exact mirror chain (decimation in time), which takes digit-reversed rows and
+// returns natural order.  Conventions are cuFFT's / PFFT's: unnormalised in both directions.
+#include "engine.h"
+#include <math.h>
+#include <stdlib.h>
+
+#ifndef B200_DYN_SMEM
+#define B200_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+namespace b200 {
+
+#define FFT_T 8
+#define FFT_MAXST 12
+enum { ST_44 = 44, ST_42 = 42 };
+
+struct FftPlan {
+    int L;                          // line length
+    int nst;                        // stage groups
+    int kind[FFT_MAXST];            // ST_44, ST_42 or the radix of a single stage (2, 3, 4, 5)
+    int m[FFT_MAXST];               // sub-transform length the group starts from
+    const double2 *tw;              // exp(-2 pi i k / L), k in [0, L)
+    const unsigned short *pos;      // row that holds frequency k after the forward chain
+    const unsigned short *freq;     // frequency held by row l
+};
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a conj(b)
+template <bool INV> __device__ __forceinline__ double2 twm(double2 a, double2 w) { return INV ? cmulc(a, w) : cmul(a, w); }
+
+// u_q = sum_p v_p exp(-+ 2 pi i p q / R), in place
+template <bool INV> __device__ __forceinline__ void bf2(double2 &a, double2 &b)
+{
+    const double2 s = cadd(a, b), d = csub(a, b);
+    a = s; b = d;
+}
+template <bool INV> __device__ __forceinline__ void bf4(double2 &v0, double2 &v1, double2 &v2, double2 &v3)
+{
+    const double2 t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3), t3 = csub(v1, v3);
+    const double2 jt = INV ? make_double2(-t3.y, t3.x) : make_double2(t3.y, -t3.x);      // -+ i t3
+    v0 = cadd(t0, t2); v2 = csub(t0, t2);
+    v1 = cadd(t1, jt); v3 = csub(t1, jt);
+}
+template <bool INV> __device__ __forceinline__ void bf3(double2 &v0, double2 &v1, double2 &v2)
+{
+    const double s3 = 0.86602540378443864676;
+    const double2 t1 = cadd(v1, v2);
+    const double2 t2 = make_double2(v0.x - 0.5 * t1.x, v0.y - 0.5 * t1.y);
+    const double2 d = csub(v1, v2);
+    const double2 t3 = make_double2(s3 * d.x, s3 * d.y);
+    const double2 jt = INV ? make_double2(-t3.y, t3.x) : make_double2(t3.y, -t3.x);
+    v0 = cadd(v0, t1);
+    v1 = cadd(t2, jt); v2 = csub(t2, jt);
+}
+template <bool INV> __device__ __forceinline__ void bf5(double2 &v0, double2 &v1, double2 &v2, double2 &v3, double2 &v4)
+{
+    const double c1 = 0.30901699437494742410, c2 = -0.80901699437494742410;
+    const double s1 = 0.95105651629515357212, s2 = 0.58778525229247312917;
+    const double2 a1 = cadd(v1, v4), a2 = cadd(v2, v3), b1 = csub(v1, v4), b2 = csub(v2, v3);
+    const double2 r1 = make_double2(v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y);
+    const double2 r2 = make_double2(v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y);
+    const double2 i1 = make_double2(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y);
+    const double2 i2 = make_double2(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y);
+    const double2 j1 = INV ? make_double2(-i1.y, i1.x) : make_double2(i1.y, -i1.x);
+    const double2 j2 = INV ? make_double2(-i2.y, i2.x) : make_double2(i2.y, -i2.x);
+    v0 = cadd(v0, cadd(a1, a2));
+    v1 = cadd(r1, j1); v4 = csub(r1, j1);
+    v2 = cadd(r2, j2); v3 = csub(r2, j2);
+}
+
+// One stage of radix R at sub-length m for column t.  Forward: butterfly, then twiddle exp(-2 pi i j q / m);
+// inverse: the conjugate twiddle, then the conjugate butterfly (the adjoint of the forward stage).
+template <int R, bool INV>
+__device__ __forceinline__ void stage1(double2 *tile, const double2 *tw, int L, int m, int t, int lane, int NL)
+{
+    const int s = m / R, nb = L / R, tws = L / m;
+    for(int b = lane; b < nb; b += NL) {
+        const int g = b / s, j = b - g * s;
+        double2 *e = tile + ((size_t) (g * m + j)) * FFT_T + t;
+        double2 v[R];
+#pragma unroll
+        for(int q = 0; q < R; q++) v[q] = e[(size_t) q * s * FFT_T];
+        if(INV) {
+#pragma unroll
+            for(int q = 1; q < R; q++) v[q] = cmulc(v[q], tw[j * q * tws]);
+        }
+        if(R == 2) bf2<INV>(v[0], v[1]);
+        if(R == 3) bf3<INV>(v[0], v[1], v[2]);
+        if(R == 4) bf4<INV>(v[0], v[1], v[2], v[3]);
+        if(R == 5) bf5<INV>(v[0], v[1], v[2], v[3], v[4]);
+        if(!INV) {
+#pragma unroll
+            for(int q = 1; q < R; q++) v[q] = cmul(v[q], tw[j * q * tws]);
+        }
+#pragma unroll
+        for(int q = 0; q < R; q++) e[(size_t) q * s * FFT_T] = v[q];
+    }
+}
+
+// exp(-2 pi i k / 16)
+#define C16_1 make_double2(0.92387953251128675613, -0.38268343236508977173)
+#define C16_2 make_double2(0.70710678118654752440, -0.70710678118654752440)
+#define C16_3 make_double2(0.38268343236508977173, -0.92387953251128675613)
+#define C16_4 make_double2(0.0, -1.0)
+#define C16_6 make_double2(-0.70710678118654752440, -0.70710678118654752440)
+#define C16_9 make_double2(-0.92387953251128675613, 0.38268343236508977173)
+
+__device__ __forceinline__ double2 c16(int k)
+{
+    switch(k) {
+        case 1: return C16_1;
+        case 2: return C16_2;
+        case 3: return C16_3;
+        case 4: return C16_4;
+        case 6: return C16_6;
+        case 9: return C16_9;
+        default: return make_double2(1.0, 0.0);
+    }
+}
+
+// Two radix-4 stages (sub-lengths m and m/4) on 16 values held in registers: the twiddle of the first,
+// exp(-2 pi i (j + a m/16) q / m), is the loaded exp(-2 pi i j q / m) times the constant 16th root a q.
+template <bool INV>
+__device__ __forceinline__ void stage44(double2 *tile, const double2 *tw, int L, int m, int t, int lane, int NL)
+{
+    const int s = m / 16, nb = L / 16, tws = L / m;
+    for(int b = lane; b < nb; b += NL) {
+        const int g = b / s, j = b - g * s;
+        double2 *e = tile + ((size_t) (g * m + j)) * FFT_T + t;
+        double2 v[16];
+#pragma unroll
+        for(int p = 0; p < 16; p++) v[p] = e[(size_t) p * s * FFT_T];
+        const int jt = j * tws;
+        if(!INV) {
+            const double2 w1 = tw[jt], w2 = tw[2 * jt], w3 = tw[3 * jt];
+#pragma unroll
+            for(int a = 0; a < 4; a++) {
+                bf4<false>(v[a], v[a + 4], v[a + 8], v[a + 12]);
+                double2 u1 = cmul(v[a + 4], w1), u2 = cmul(v[a + 8], w2), u3 = cmul(v[a + 12], w3);
+                if(a > 0) { u1 = cmul(u1, c16(a)); u2 = cmul(u2, c16(2 * a)); u3 = cmul(u3, c16(3 * a)); }
+                v[a + 4] = u1; v[a + 8] = u2; v[a + 12] = u3;
+            }
+            const double2 x1 = tw[4 * jt], x2 = tw[8 * jt], x3 = tw[12 * jt];
+#pragma unroll
+            for(int q = 0; q < 4; q++) {
+                bf4<false>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                v[4 * q + 1] = cmul(v[4 * q + 1], x1); v[4 * q + 2] = cmul(v[4 * q + 2], x2); v[4 * q + 3] = cmul(v[4 * q + 3], x3);
+            }
+        } else {
+            const double2 x1 = tw[4 * jt], x2 = tw[8 * jt], x3 = tw[12 * jt];
+#pragma unroll
+            for(int q = 0; q < 4; q++) {
+                v[4 * q + 1] = cmulc(v[4 * q + 1], x1); v[4 * q + 2] = cmulc(v[4 * q + 2], x2); v[4 * q + 3] = cmulc(v[4 * q + 3], x3);
+                bf4<true>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            const double2 w1 = tw[jt], w2 = tw[2 * jt], w3 = tw[3 * jt];
+#pragma unroll
+            for(int a = 0; a < 4; a++) {
+                double2 u1 = cmulc(v[a + 4], w1), u2 = cmulc(v[a + 8], w2), u3 = cmulc(v[a + 12], w3);
+                if(a > 0) { u1 = cmulc(u1, c16(a)); u2 = cmulc(u2, c16(2 * a)); u3 = cmulc(u3, c16(3 * a)); }
+                v[a + 4] = u1; v[a + 8] = u2; v[a + 12] = u3;
+                bf4<true>(v[a], v[a + 4], v[a + 8], v[a + 12]);
+            }
+        }
+#pragma unroll
+        for(int p = 0; p < 16; p++) e[(size_t) p * s * FFT_T] = v[p];
+    }
+}
+
+// A radix-4 stage (sub-length m) and a radix-2 stage (sub-length m/4) on 8 values held in registers.
+template <bool INV>
+__device__ __forceinline__ void stage42(double2 *tile, const double2 *tw, int L, int m, int t, int lane, int NL)
+{
+    const int s = m / 8, nb = L / 8, tws = L / m;
+    for(int b = lane; b < nb; b += NL) {
+        const int g = b / s, j = b - g * s;
+        double2 *e = tile + ((size_t) (g * m + j)) * FFT_T + t;
+        double2 v[8];
+#pragma unroll
+        for(int p = 0; p < 8; p++) v[p] = e[(size_t) p * s * FFT_T];
+        const int jt = j * tws;
+        const double2 w1 = tw[jt], w2 = tw[2 * jt], w3 = tw[3 * jt], x1 = tw[4 * jt];
+        if(!INV) {
+#pragma unroll
+            for(int a = 0; a < 2; a++) {
+                bf4<false>(v[a], v[a + 2], v[a + 4], v[a + 6]);
+                double2 u1 = cmul(v[a + 2], w1), u2 = cmul(v[a + 4], w2), u3 = cmul(v[a + 6], w3);
+                if(a > 0) { u1 = cmul(u1, c16(2)); u2 = cmul(u2, c16(4)); u3 = cmul(u3, c16(6)); }     // 8th roots
+                v[a + 2] = u1; v[a + 4] = u2; v[a + 6] = u3;
+            }
+#pragma unroll
+            for(int q = 0; q < 4; q++) {
+                bf2<false>(v[2 * q], v[2 * q + 1]);
+                v[2 * q + 1] = cmul(v[2 * q + 1], x1);
+            }
+        } else {
+#pragma unroll
+            for(int q = 0; q < 4; q++) {
+                v[2 * q + 1] = cmulc(v[2 * q + 1], x1);
+                bf2<true>(v[2 * q], v[2 * q + 1]);
+            }
+#pragma unroll
+            for(int a = 0; a < 2; a++) {
+                double2 u1 = cmulc(v[a + 2], w1), u2 = cmulc(v[a + 4], w2), u3 = cmulc(v[a + 6], w3);
+                if(a > 0) { u1 = cmulc(u1, c16(2)); u2 = cmulc(u2, c16(4)); u3 = cmulc(u3, c16(6)); }
+                v[a + 2] = u1; v[a + 4] = u2; v[a + 6] = u3;
+                bf4<true>(v[a], v[a + 2], v[a + 4], v[a + 6]);
+            }
+        }
+#pragma unroll
+        for(int p = 0; p < 8; p++) e[(size_t) p * s * FFT_T] = v[p];
+    }
+}
+
+// The whole chain on the tile.  Forward: natural rows in, row pos[k] holds frequency k on return.
+// Inverse: row pos[k] holds frequency k on entry, natural rows (times L) on return.
+// Ends with a barrier.
+template <bool INV>
+__device__ __forceinline__ void fft_tile(double2 *tile, const double2 *tw, const FftPlan &P, int t, int lane, int NL)
+{
+    for(int i = 0; i < P.nst; i++) {
+        const int g = INV ? P.nst - 1 - i : i;
+        const int m = P.m[g];
+        switch(P.kind[g]) {
+            case ST_44: stage44<INV>(tile, tw, P.L, m, t, lane, NL); break;
+            case ST_42: stage42<INV>(tile, tw, P.L, m, t, lane, NL); break;
+            case 4: stage1<4, INV>(tile, tw, P.L, m, t, lane, NL); break;
+            case 2: stage1<2, INV>(tile, tw, P.L, m, t, lane, NL); break;
+            case 3: stage1<3, INV>(tile, tw, P.L, m, t, lane, NL); break;
+            default: stage1<5, INV>(tile, tw, P.L, m, t, lane, NL); break;
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ void load_twiddles(double2 *tw_s, const FftPlan &P)
+{
+    for(int i = threadIdx.x; i < P.L; i += blockDim.x) tw_s[i] = P.tw[i];
+}
+
+// z forward: 8 consecutive real lines of the mesh per block; line = N reals = L = N/2 packed complex values
+// z[j] = x[2j] + i x[2j+1].  With Z = FFT_L(z):  X[k] = (Z[k] + conj Z[L-k])/2 - i exp(-2 pi i k/N) (Z[k] - conj Z[L-k])/2,
+// k = 0..L (Z[L] = Z[0]).  Output rows have pitch Nzp >= L + 1 (a multiple of 8); the padding is zeroed.
+__global__ void __launch_bounds__(256, 2)
+k_fft_z_forward(const double *__restrict__ mesh, double2 *__restrict__ out, long long nlines, int Nzp,
+                FftPlan P, const double2 *__restrict__ wN)
+{
+    B200_DYN_SMEM(smem);
+    double2 *tile = (double2 *) smem;
+    double2 *tw_s = tile + (size_t) P.L * FFT_T;
+    const int L = P.L, t = threadIdx.x & (FFT_T - 1), lane = threadIdx.x / FFT_T, NL = blockDim.x / FFT_T;
+    const long long line = (long long) blockIdx.x * FFT_T + t;
+    const bool ok = line < nlines;
+    load_twiddles(tw_s, P);
+    const double2 *in = (const double2 *) mesh + line * L;
+    for(int l = lane; l < L; l += NL) tile[(size_t) l * FFT_T + t] = ok ? in[l] : make_double2(0.0, 0.0);
+    __syncthreads();
+    fft_tile<false>(tile, tw_s, P, t, lane, NL);
+    if(!ok) return;
+    double2 *o = out + line * Nzp;
+    for(int kk = lane; kk <= L / 2; kk += NL) {
+        if(kk == 0) {
+            const double2 Z0 = tile[(size_t) P.pos[0] * FFT_T + t];
+            o[0] = make_double2(Z0.x + Z0.y, 0.0);
+            o[L] = make_double2(Z0.x - Z0.y, 0.0);
+            continue;
+        }
+        const int k2 = L - kk;
+        const double2 Z1 = tile[(size_t) P.pos[kk] * FFT_T + t], Z2 = tile[(size_t) P.pos[k2] * FFT_T + t];
+        const double2 A = make_double2(Z1.x + Z2.x, Z1.y - Z2.y);          // Z1 + conj Z2
+        const double2 B = make_double2(Z1.x - Z2.x, Z1.y + Z2.y);          // Z1 - conj Z2
+        const double2 Q = cmul(wN[kk], B);
+        o[kk] = make_double2(0.5 * (A.x + Q.y), 0.5 * (A.y - Q.x));
+        if(k2 != kk) o[k2] = make_double2(0.5 * (A.x - Q.y), 0.5 * (-A.y - Q.x));
+    }
+    for(int k = L + 1 + lane; k < Nzp; k += NL) o[k] = make_double2(0.0, 0.0);
+}
+
+// z inverse: Z[k] = (X[k] + conj X[L-k]) + i exp(+2 pi i k/N) (X[k] - conj X[L-k]), inverse FFT_L, unpack: N x the real line.
+__global__ void __launch_bounds__(256, 2)
+k_fft_z_inverse(const double2 *__restrict__ in, double *__restrict__ mesh, long long nlines, int Nzp,
+                FftPlan P, const double2 *__restrict__ wN)
+{
+    B200_DYN_SMEM(smem);
+    double2 *tile = (double2 *) smem;
+    double2 *tw_s = tile + (size_t) P.L * FFT_T;
+    const int L = P.L, t = threadIdx.x & (FFT_T - 1), lane = threadIdx.x / FFT_T, NL = blockDim.x / FFT_T;
+    const long long line = (long long) blockIdx.x * FFT_T + t;
+    const bool ok = line < nlines;
+    load_twiddles(tw_s, P);
+    const double2 *x = in + line * Nzp;
+    for(int kk = lane; kk <= L / 2; kk += NL) {
+        const int k2 = L - kk;
+        double2 X1 = make_double2(0.0, 0.0), X2 = X1;
+        if(ok) { X1 = x[kk]; X2 = x[k2]; }
+        if(kk == 0) { X1.y = 0.0; X2.y = 0.0; }          // the two real modes of a Hermitian line (cuFFT ignores their imaginary parts too)
+        const double2 A = make_double2(X1.x + X2.x, X1.y - X2.y);
+        const double2 B = make_double2(X1.x - X2.x, X1.y + X2.y);
+        const double2 Q = cmulc(B, wN[kk]);
+        tile[(size_t) P.pos[kk] * FFT_T + t] = make_double2(A.x - Q.y, A.y + Q.x);
+        if(kk != 0 && k2 != kk) tile[(size_t) P.pos[k2] * FFT_T + t] = make_double2(A.x + Q.y, -A.y + Q.x);
+    }
+    __syncthreads();
+    fft_tile<true>(tile, tw_s, P, t, lane, NL);
+    if(!ok) return;
+    double2 *o = (double2 *) mesh + line * L;
+    for(int l = lane; l < L; l += NL) o[l] = tile[(size_t) l * FFT_T + t];
+}
+
+struct GreenArgs {
+    int N, Nz;
+    const double *ktab;
+    double asmth2, pot_factor, binsperunit;
+    double *ps;
+};
+
+// Column passes over the half spectrum, in place.  Block (outer, tk) owns rows base + l * stride, l in [0, L), of 8
+// complex values each, base = outer * outer_stride + 8 tk.
+//   MODE 0: forward transform, rows back in frequency order.            (y forward: outer = ix, stride = Nzp)
+//   MODE 1: inverse transform of rows given in frequency order.         (y inverse)
+//   MODE 2, 3: forward, potential_transfer (gravpm.c:383-454; MODE 3 also powerspectrum_add_mode, gravpm.c:330-361),
+//           inverse.                                                    (x: outer = iy, stride = N Nzp)
+template <int MODE>
+__global__ void __launch_bounds__(256, 2)
+k_fft_columns(double2 *__restrict__ v, int ntile, size_t outer_stride, size_t stride, FftPlan P, GreenArgs G)
+{
+    B200_DYN_SMEM(smem);
+    double2 *tile = (double2 *) smem;
+    double2 *tw_s = tile + (size_t) P.L * FFT_T;
+    double *s_ps = (double *) (tw_s + P.L);          // MODE 3: [3][N]
+    const int L = P.L, t = threadIdx.x & (FFT_T - 1), lane = threadIdx.x / FFT_T, NL = blockDim.x / FFT_T;
+    const int outer = blockIdx.x / ntile, tk = blockIdx.x - outer * ntile;
+    double2 *g = v + (size_t) outer * outer_stride + (size_t) tk * FFT_T + t;
+    load_twiddles(tw_s, P);
+    if(MODE == 3) for(int b = threadIdx.x; b < 3 * G.N; b += blockDim.x) s_ps[b] = 0;
+    if(MODE == 1)
+        for(int k = lane; k < L; k += NL) tile[(size_t) P.pos[k] * FFT_T + t] = g[(size_t) k * stride];
+    else
+        for(int l = lane; l < L; l += NL) tile[(size_t) l * FFT_T + t] = g[(size_t) l * stride];
+    __syncthreads();
+    if(MODE == 1) {
+        fft_tile<true>(tile, tw_s, P, t, lane, NL);
+        for(int l = lane; l < L; l += NL) g[(size_t) l * stride] = tile[(size_t) l * FFT_T + t];
+        return;
+    }
+    fft_tile<false>(tile, tw_s, P, t, lane, NL);
+    if(MODE == 0) {
+        for(int k = lane; k < L; k += NL) g[(size_t) k * stride] = tile[(size_t) P.pos[k] * FFT_T + t];
+        return;
+    }
+    {
+        const int N = G.N, iy = outer, iz = tk * FFT_T + t;
+        if(iz < G.Nz) {
+            const int ky = iy <= N / 2 ? iy : iy - N;       // petapm_mesh_to_k petapm.c:81-84
+            const double fyz = G.ktab[iy], fz = G.ktab[iz];
+            for(int l = lane; l < L; l += NL) {
+                const int ix = P.freq[l];
+                const int kx = ix <= N / 2 ? ix : ix - N;
+                const long long k2 = (long long) kx * kx + (long long) ky * ky + (long long) iz * iz;
+                double2 val = tile[(size_t) l * FFT_T + t];
+                if(k2 == 0) {
+                    if(MODE == 3) G.ps[3 * N] = val.x * val.x + val.y * val.y;       // gravpm.c:332-336
+                    val.x = 0.0; val.y = 0.0;                                        // gravpm.c:441-449
+                } else {
+                    const double smth = exp((double) (-k2) * G.asmth2) / (double) k2;
+                    const double f = (G.ktab[ix] * fyz) * fz;
+                    if(MODE == 3) {
+                        const int kint = (int) floor(G.binsperunit * log((double) k2) / 2.);
+                        if(kint < N) {
+                            const double w = (iz == 0 || iz == N / 2) ? 1.0 : 2.0;
+                            const double mm = val.x * val.x + val.y * val.y;
+                            atomicAdd(&s_ps[kint], w * mm * f * f);
+                            atomicAdd(&s_ps[N + kint], w * sqrt((double) k2));
+                            atomicAdd(&s_ps[2 * N + kint], w);
+                        }
+                    }
+                    const double fac = ((G.pot_factor * smth) * f) * f;
+                    val.x *= fac; val.y *= fac;
+                }
+                tile[(size_t) l * FFT_T + t] = val;
+            }
+        }
+        __syncthreads();
+        fft_tile<true>(tile, tw_s, P, t, lane, NL);
+        for(int l = lane; l < L; l += NL) g[(size_t) l * stride] = tile[(size_t) l * FFT_T + t];
+        if(MODE == 3)
+            for(int b = threadIdx.x; b < 3 * N; b += blockDim.x) if(s_ps[b] != 0) atomicAdd(&G.ps[b], s_ps[b]);
+    }
+}
+
+// ---- host side ----
+
+static bool plan_stages(int L, std::vector<int> &kind, std::vector<int> &ms, std::vector<int> &radices)
+{
+    int n = L, m = L, p2 = 0;
+    while(n % 2 == 0) { n /= 2; p2++; }
+    int n3 = 0, n5 = 0;
+    while(n % 3 == 0) { n /= 3; n3++; }
+    while(n % 5 == 0) { n /= 5; n5++; }
+    if(n != 1) return false;
+    while(p2 >= 4) { kind.push_back(ST_44); ms.push_back(m); radices.push_back(4); radices.push_back(4); m /= 16; p2 -= 4; }
+    if(p2 == 3) { kind.push_back(ST_42); ms.push_back(m); radices.push_back(4); radices.push_back(2); m /= 8; p2 = 0; }
+    if(p2 == 2) { kind.push_back(4); ms.push_back(m); radices.push_back(4); m /= 4; p2 = 0; }
+    if(p2 == 1) { kind.push_back(2); ms.push_back(m); radices.push_back(2); m /= 2; p2 = 0; }
+    for(int i = 0; i < n3; i++) { kind.push_back(3); ms.push_back(m); radices.push_back(3); m /= 3; }
+    for(int i = 0; i < n5; i++) { kind.push_back(5); ms.push_back(m); radices.push_back(5); m /= 5; }
+    return (int) kind.size() <= FFT_MAXST;
+}
+
+// tables of one line length behind fft_tab + off (doubles): tw[L] double2 | pos[L], freq[L] unsigned short
+static size_t plan_bytes(int L) { return (size_t) L * 16 + (((size_t) L * 4 + 15) & ~(size_t) 15); }
+
+static bool plan_fill(int L, unsigned char *h, FftPlan *P, const unsigned char *dev)
+{
+    std::vector<int> kind, ms, rad;
+    if(!plan_stages(L, kind, ms, rad)) return false;
+    double2 *tw = (double2 *) h;
+    unsigned short *pos = (unsigned short *) (h + (size_t) L * 16), *freq = pos + L;
+    for(int k = 0; k < L; k++) {
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * k / L;
+        tw[k].x = (double) cosl(a); tw[k].y = (double) sinl(a);
+    }
+    for(int k = 0; k < L; k++) {
+        int kk = k, p = 0, m = L;
+        for(size_t i = 0; i < rad.size(); i++) { const int q = kk % rad[i]; kk /= rad[i]; m /= rad[i]; p += q * m; }
+        pos[k] = (unsigned short) p; freq[p] = (unsigned short) k;
+    }
+    P->L = L; P->nst = (int) kind.size();
+    for(int i = 0; i < P->nst; i++) { P->kind[i] = kind[i]; P->m[i] = ms[i]; }
+    P->tw = (const double2 *) dev;
+    P->pos = (const unsigned short *) (dev + (size_t) L * 16);
+    P->freq = P->pos + L;
+    return true;
+}
+
+struct OwnFFT {
+    int N = 0, Nzp = 0, threads = 256;
+    FftPlan pN, pH;               // line lengths N (columns) and N/2 (packed z lines)
+    const double2 *wN = nullptr;  // exp(-2 pi i k / N), k in [0, N/2]
+    size_t smemN = 0, smemH = 0;
+};
+
+void pmfft_destroy(Engine *E)
+{
+    delete E->ownfft; E->ownfft = nullptr;
+    E->fft_tab.release();
+}
+
+bool pmfft_supported(int N)
+{
+    std::vector<int> a, b, c;
+    if(N < 8 || (N & 1) || N > 65534) return false;
+    if(!plan_stages(N, a, b, c)) return false;
+    a.clear(); b.clear(); c.clear();
+    if(!plan_stages(N / 2, a, b, c)) return false;
+    return (size_t) N * FFT_T * 16 + (size_t) N * 16 + 3 * (size_t) N * 8 <= 227 * 1024;
+}
+
+// Tables and kernel attributes for mesh size N.  The half spectrum lives in E->cplx with row pitch Nzp.
+int pmfft_init(Engine *E, int N)
+{
+    pmfft_destroy(E);
+    if(!pmfft_supported(N)) return failmsg(E, "pmfft_init: mesh size not supported by the shared-memory transform");
+    OwnFFT *F = new OwnFFT();
+    E->ownfft = F;
+    F->N = N;
+    F->Nzp = (N / 2 + 1 + FFT_T - 1) / FFT_T * FFT_T;
+    if(const char *s = getenv("B200_FFT_THREADS")) { const int v = atoi(s); if(v >= 32 && v <= 256 && v % 32 == 0) F->threads = v; }
+    const int L = N / 2;
+    const size_t bN = plan_bytes(N), bH = plan_bytes(L), bW = (size_t) (L + 1) * 16;
+    std::vector<unsigned char> h(bN + bH + bW);
+    CK(E->fft_tab.ensure((bN + bH + bW) / 8 + 2));
+    const unsigned char *dev = (const unsigned char *) E->fft_tab.p;
+    if(!plan_fill(N, h.data(), &F->pN, dev) || !plan_fill(L, h.data() + bN, &F->pH, dev + bN)) return failmsg(E, "pmfft_init: plan");
+    double2 *w = (double2 *) (h.data() + bN + bH);
+    for(int k = 0; k <= L; k++) {
+        const long double a = -2.0L * 3.14159265358979323846264338327950288L * k / N;
+        w[k].x = (double) cosl(a); w[k].y = (double) sinl(a);
+    }
+    F->wN = (const double2 *) (dev + bN + bH);
+    CK(cudaMemcpyAsync(E->fft_tab.p, h.data(), h.size(), cudaMemcpyHostToDevice, E->stream));
+    CK(cudaStreamSynchronize(E->stream));
+    F->smemN = (size_t) N * FFT_T * 16 + (size_t) N * 16;
+    F->smemH = (size_t) L * FFT_T * 16 + (size_t) L * 16;
+    CK(cudaFuncSetAttribute(k_fft_z_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemH));
+    CK(cudaFuncSetAttribute(k_fft_z_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemH));
+    CK(cudaFuncSetAttribute(k_fft_columns<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
+    CK(cudaFuncSetAttribute(k_fft_columns<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
+    CK(cudaFuncSetAttribute(k_fft_columns<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
+    CK(cudaFuncSetAttribute(k_fft_columns<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (F->smemN + 3 * (size_t) N * 8)));
+    return 0;
+}
+
+size_t pmfft_cplx_doubles(const Engine *E) { return 2 * (size_t) E->ownfft->N * E->ownfft->N * E->ownfft->Nzp; }
+
+// density mesh (E->mesh) -> potential mesh (E->mesh); E->cplx is the work area.  ps != NULL: [3][N] + 1 power-spectrum sums.
+int pmfft_potential(Engine *E, double asmth2, double pot_factor, double binsperunit, double *ps)
+{
+    OwnFFT *F = E->ownfft;
+    const int N = F->N, Nzp = F->Nzp, ntile = Nzp / FFT_T, th = F->threads;
+    const long long nlines = (long long) N * N;
+    const unsigned zblocks = (unsigned) ((nlines + FFT_T - 1) / FFT_T), cblocks = (unsigned) N * ntile;
+    double2 *c = (double2 *) E->cplx.p;
+    GreenArgs G = {N, N / 2 + 1, E->ktab.p, asmth2, pot_factor, binsperunit, ps};
+
+    timer_start(E, T_PM_FFT_FWD);
+    k_fft_z_forward<<<zblocks, th, F->smemH, E->stream>>>(E->mesh.p, c, nlines, Nzp, F->pH, F->wN);
+    CKL(E);
+    k_fft_columns<0><<<cblocks, th, F->smemN, E->stream>>>(c, ntile, (size_t) N * Nzp, (size_t) Nzp, F->pN, G);
+    CKL(E);
+    timer_stop(E, T_PM_FFT_FWD);
+
+    timer_start(E, T_PM_TRANSFER);
+    if(ps) k_fft_columns<3><<<cblocks, th, F->smemN + 3 * (size_t) N * 8, E->stream>>>(c, ntile, (size_t) Nzp, (size_t) N * Nzp, F->pN, G);
+    else k_fft_columns<2><<<cblocks, th, F->smemN, E->stream>>>(c, ntile, (size_t) Nzp, (size_t) N * Nzp, F->pN, G);
+    CKL(E);
+    timer_stop(E, T_PM_TRANSFER);
+
+    timer_start(E, T_PM_FFT_INV);
+    k_fft_columns<1><<<cblocks, th, F->smemN, E->stream>>>(c, ntile, (size_t) N * Nzp, (size_t) Nzp, F->pN, G);
+    CKL(E);
+    k_fft_z_inverse<<<zblocks, th, F->smemH, E->stream>>>(c, E->mesh.p, nlines, Nzp, F->pH, F->wN);
+    CKL(E);
+    timer_stop(E, T_PM_FFT_INV);
+    return 0;
+}
+
+} // namespace b200

@@ -17,7 +17,7 @@ SO = os.path.join(OUT, "libsteploop_emul.so")
 
 def rewrite_launches(text):
     out, pos, count = [], 0, 0
-    for m in re.finditer(r"(\w+)<<<", text):
+    for m in re.finditer(r"(\w+(?:<\w+>)?)<<<", text):
         start = m.start()
         end_cfg = text.index(">>>", m.end())
         cfg = [c.strip() for c in text[m.end():end_cfg].split(",")]
@@ -91,3 +91,26 @@ def build_dropin(force=False):
 if __name__ == "__main__":
     print(build(force=True))
     print(build_dropin(force=True))
+
+
+FFT_SO = os.path.join(OUT, "libpmfft_emul.so")
+
+
+def build_fft(force=False):
+    """mp-gadget_b200/csrc/pm_fft.cu (kernels and host driver unchanged) for the host, driven by tests/emul/fft_driver.cpp."""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(ROOT, "mp-gadget_b200", "csrc", "pm_fft.cu")
+    drv = os.path.join(HERE, "fft_driver.cpp")
+    deps = [src, drv, os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(ROOT, "mp-gadget_b200", "csrc", "engine.h"), __file__]
+    if not force and os.path.exists(FFT_SO) and all(os.path.getmtime(d) <= os.path.getmtime(FFT_SO) for d in deps):
+        return FFT_SO
+    text, n = rewrite_launches(open(src).read())
+    assert n >= 6, n
+    gen = os.path.join(OUT, "pm_fft_emul.cpp")
+    with open(gen, "w") as f:
+        f.write("// GENERATED from mp-gadget_b200/csrc/pm_fft.cu by tests/emul/build.py -- do not edit\n" + text)
+    inc = ["-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "mp-gadget_b200", "csrc")]
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off"] +
+                          (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if ASAN else []) +
+                          ["-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-o", FFT_SO, gen, drv] + inc)
+    return FFT_SO

@@ -55,6 +55,19 @@ static inline void __syncthreads(void)
 {
 #pragma omp barrier
 }
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { double2 r = {x, y}; return r; }
+#define __align__(n)
+/* dynamic shared memory: one static arena per launch (blocks run one after the other) */
+extern unsigned char emul_dyn_smem[256 * 1024];
+#define B200_DYN_SMEM(name) unsigned char *name = emul_dyn_smem
+static inline double atomicAdd(double *p, double v)
+{
+    double old;
+#pragma omp critical(emul_atomic_double)
+    { old = *p; *p = old + v; }
+    return old;
+}
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long) v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }

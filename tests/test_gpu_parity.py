@@ -231,6 +231,61 @@ def test_force_step_dev(engine, ics):
         assert np.array_equal(d[2].cpu().numpy(), pot)
 
 
+@pytest.mark.parametrize("nmesh", [40, 48, 96, 192])
+def test_pm_own_transforms_equal_cufft(b200, ics, nmesh, monkeypatch):
+    """The engine's shared-memory transform passes with the Green's function inside (csrc/pm_fft.cu) against cuFFT D2Z ->
+    k_pm_potential_transfer -> cuFFT Z2D on the same deposit: potential mesh, readouts and the power-spectrum sums.
+    Mesh sizes: 40 = 2^3.5, 48 = 2^4.3, 96 = 2^5.3, 192 = 2^6.3 (configs[0]); 768 is covered by test_config_parity.py."""
+    pos, _ = ics.zeldovich_lattice(32, 32.0)
+    mass = (1 + np.arange(len(pos)) % 3).astype(np.float32)
+    res = []
+    for sel in ("own", "cufft"):
+        monkeypatch.setenv("B200_PM_FFT", sel)
+        e = b200.Engine(0)
+        try:
+            e.set_particles(pos, mass)
+            e.gravpm_init_periodic(32.0, 1.5, nmesh, G)
+            assert e.pm_transform_kind() == (1 if sel == "own" else 0)
+            e.pm_set_power(True)
+            g, p = e.gravpm_force()
+            res.append((g, p, e.pm_copy_mesh(1), e.pm_power()))
+            e.pm_set_power(False)
+            g2, _ = e.gravpm_force()           # the pass without the power-spectrum sums
+            assert np.abs(g2 - g).max() <= 1e-12 * np.abs(g).max()
+        finally:
+            e.close()
+    (g, p, m, ps), (g0, p0, m0, ps0) = res
+    assert np.abs(m - m0).max() <= 1e-13 * np.abs(m0).max()
+    assert np.abs(g - g0).max() <= 1e-11 * np.abs(g0).max()
+    assert np.abs(p - p0).max() <= 1e-12 * np.abs(p0).max()
+    assert np.array_equal(ps[2], ps0[2])
+    assert abs(ps[3] - ps0[3]) <= 1e-12 * ps0[3]
+    assert np.abs(ps[1] - ps0[1]).max() <= 1e-12 * ps0[1].max()
+    assert np.abs(ps[0] - ps0[0]).max() <= 1e-11 * ps0[0].max()
+
+
+def test_pm_transform_fallback_sizes(b200, ics):
+    """Mesh sizes the shared-memory passes do not take (a prime factor other than 2, 3, 5) run on cuFFT."""
+    pos, _ = ics.zeldovich_lattice(16, 16.0)
+    mass = np.ones(len(pos), np.float32)
+    e = b200.Engine(0)
+    try:
+        assert e.pm_transform_kind() == -1
+        e.set_particles(pos, mass)
+        e.gravpm_init_periodic(16.0, 1.5, 56, G)
+        assert e.pm_transform_kind() == 0
+        g, _ = e.gravpm_force()
+        og, _, _ = oracle.pm_force(pos, mass, 16.0, 56, 1.5, G)
+        assert np.abs(g - og).max() <= 1e-9 * np.abs(og).max()
+        e.gravpm_init_periodic(16.0, 1.5, 60, G)
+        assert e.pm_transform_kind() == 1
+        g, _ = e.gravpm_force()
+        og, _, _ = oracle.pm_force(pos, mass, 16.0, 60, 1.5, G)
+        assert np.abs(g - og).max() <= 1e-9 * np.abs(og).max()
+    finally:
+        e.close()
+
+
 def test_pm_power_spectrum_side_effect(engine, ics):
     """gravpm_force's power spectrum (powerspectrum_add_mode inside potential_transfer,
     gravpm.c:330-361,440): mode counts bit-exact, sums to rounding; forces unchanged."""
