@@ -48,7 +48,6 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a conj(b)
-template <bool INV> __device__ __forceinline__ double2 twm(double2 a, double2 w) { return INV ? cmulc(a, w) : cmul(a, w); }
 
 // u_q = sum_p v_p exp(-+ 2 pi i p q / R), in place
 template <bool INV> __device__ __forceinline__ void bf2(double2 &a, double2 &b)
@@ -90,69 +89,32 @@ template <bool INV> __device__ __forceinline__ void bf5(double2 &v0, double2 &v1
     v2 = cadd(r2, j2); v3 = csub(r2, j2);
 }
 
-// One stage of radix R at sub-length m for column t.  Forward: butterfly, then twiddle exp(-2 pi i j q / m);
-// inverse: the conjugate twiddle, then the conjugate butterfly (the adjoint of the forward stage).
-template <int R, bool INV>
-__device__ __forceinline__ void stage1(double2 *tile, const double2 *tw, int L, int m, int t, int lane, int NL)
-{
-    const int s = m / R, nb = L / R, tws = L / m;
-    for(int b = lane; b < nb; b += NL) {
-        const int g = b / s, j = b - g * s;
-        double2 *e = tile + ((size_t) (g * m + j)) * FFT_T + t;
-        double2 v[R];
-#pragma unroll
-        for(int q = 0; q < R; q++) v[q] = e[(size_t) q * s * FFT_T];
-        if(INV) {
-#pragma unroll
-            for(int q = 1; q < R; q++) v[q] = cmulc(v[q], tw[j * q * tws]);
-        }
-        if(R == 2) bf2<INV>(v[0], v[1]);
-        if(R == 3) bf3<INV>(v[0], v[1], v[2]);
-        if(R == 4) bf4<INV>(v[0], v[1], v[2], v[3]);
-        if(R == 5) bf5<INV>(v[0], v[1], v[2], v[3], v[4]);
-        if(!INV) {
-#pragma unroll
-            for(int q = 1; q < R; q++) v[q] = cmul(v[q], tw[j * q * tws]);
-        }
-#pragma unroll
-        for(int q = 0; q < R; q++) e[(size_t) q * s * FFT_T] = v[q];
-    }
-}
-
 // exp(-2 pi i k / 16)
-#define C16_1 make_double2(0.92387953251128675613, -0.38268343236508977173)
-#define C16_2 make_double2(0.70710678118654752440, -0.70710678118654752440)
-#define C16_3 make_double2(0.38268343236508977173, -0.92387953251128675613)
-#define C16_4 make_double2(0.0, -1.0)
-#define C16_6 make_double2(-0.70710678118654752440, -0.70710678118654752440)
-#define C16_9 make_double2(-0.92387953251128675613, 0.38268343236508977173)
-
 __device__ __forceinline__ double2 c16(int k)
 {
     switch(k) {
-        case 1: return C16_1;
-        case 2: return C16_2;
-        case 3: return C16_3;
-        case 4: return C16_4;
-        case 6: return C16_6;
-        case 9: return C16_9;
+        case 1: return make_double2(0.92387953251128675613, -0.38268343236508977173);
+        case 2: return make_double2(0.70710678118654752440, -0.70710678118654752440);
+        case 3: return make_double2(0.38268343236508977173, -0.92387953251128675613);
+        case 4: return make_double2(0.0, -1.0);
+        case 6: return make_double2(-0.70710678118654752440, -0.70710678118654752440);
+        case 9: return make_double2(-0.92387953251128675613, 0.38268343236508977173);
         default: return make_double2(1.0, 0.0);
     }
 }
 
-// Two radix-4 stages (sub-lengths m and m/4) on 16 values held in registers: the twiddle of the first,
-// exp(-2 pi i (j + a m/16) q / m), is the loaded exp(-2 pi i j q / m) times the constant 16th root a q.
-template <bool INV>
-__device__ __forceinline__ void stage44(double2 *tile, const double2 *tw, int L, int m, int t, int lane, int NL)
+// ---- one stage group on the values of one butterfly, in registers ----
+// v[p] is the value of row base + p s (s = m / R).  Forward: butterfly, then the twiddle exp(-2 pi i j q / m);
+// inverse: the conjugate twiddle, then the conjugate butterfly (the adjoint of the forward group).  jt = j L / m
+// indexes the table tw[k] = exp(-2 pi i k / L).
+template <int KIND> struct GroupSize { static const int R = KIND == ST_44 ? 16 : (KIND == ST_42 ? 8 : KIND); };
+
+template <int KIND, bool INV>
+__device__ __forceinline__ void group_compute(double2 *v, const double2 *tw, int jt)
 {
-    const int s = m / 16, nb = L / 16, tws = L / m;
-    for(int b = lane; b < nb; b += NL) {
-        const int g = b / s, j = b - g * s;
-        double2 *e = tile + ((size_t) (g * m + j)) * FFT_T + t;
-        double2 v[16];
-#pragma unroll
-        for(int p = 0; p < 16; p++) v[p] = e[(size_t) p * s * FFT_T];
-        const int jt = j * tws;
+    if(KIND == ST_44) {
+        // two radix-4 stages (sub-lengths m and m/4): the twiddle of the first, exp(-2 pi i (j + a m/16) q / m), is the
+        // loaded exp(-2 pi i j q / m) times the constant 16th root a q
         if(!INV) {
             const double2 w1 = tw[jt], w2 = tw[2 * jt], w3 = tw[3 * jt];
 #pragma unroll
@@ -184,23 +146,8 @@ __device__ __forceinline__ void stage44(double2 *tile, const double2 *tw, int L,
                 bf4<true>(v[a], v[a + 4], v[a + 8], v[a + 12]);
             }
         }
-#pragma unroll
-        for(int p = 0; p < 16; p++) e[(size_t) p * s * FFT_T] = v[p];
-    }
-}
-
-// A radix-4 stage (sub-length m) and a radix-2 stage (sub-length m/4) on 8 values held in registers.
-template <bool INV>
-__device__ __forceinline__ void stage42(double2 *tile, const double2 *tw, int L, int m, int t, int lane, int NL)
-{
-    const int s = m / 8, nb = L / 8, tws = L / m;
-    for(int b = lane; b < nb; b += NL) {
-        const int g = b / s, j = b - g * s;
-        double2 *e = tile + ((size_t) (g * m + j)) * FFT_T + t;
-        double2 v[8];
-#pragma unroll
-        for(int p = 0; p < 8; p++) v[p] = e[(size_t) p * s * FFT_T];
-        const int jt = j * tws;
+    } else if(KIND == ST_42) {
+        // a radix-4 stage (sub-length m) and a radix-2 stage (sub-length m/4)
         const double2 w1 = tw[jt], w2 = tw[2 * jt], w3 = tw[3 * jt], x1 = tw[4 * jt];
         if(!INV) {
 #pragma unroll
@@ -229,35 +176,113 @@ __device__ __forceinline__ void stage42(double2 *tile, const double2 *tw, int L,
                 bf4<true>(v[a], v[a + 2], v[a + 4], v[a + 6]);
             }
         }
+    } else {
+        const int R = GroupSize<KIND>::R;
+        if(INV) {
 #pragma unroll
-        for(int p = 0; p < 8; p++) e[(size_t) p * s * FFT_T] = v[p];
-    }
-}
-
-// The whole chain on the tile.  Forward: natural rows in, row pos[k] holds frequency k on return.
-// Inverse: row pos[k] holds frequency k on entry, natural rows (times L) on return.
-// Ends with a barrier.
-template <bool INV>
-__device__ __forceinline__ void fft_tile(double2 *tile, const double2 *tw, const FftPlan &P, int t, int lane, int NL)
-{
-    for(int i = 0; i < P.nst; i++) {
-        const int g = INV ? P.nst - 1 - i : i;
-        const int m = P.m[g];
-        switch(P.kind[g]) {
-            case ST_44: stage44<INV>(tile, tw, P.L, m, t, lane, NL); break;
-            case ST_42: stage42<INV>(tile, tw, P.L, m, t, lane, NL); break;
-            case 4: stage1<4, INV>(tile, tw, P.L, m, t, lane, NL); break;
-            case 2: stage1<2, INV>(tile, tw, P.L, m, t, lane, NL); break;
-            case 3: stage1<3, INV>(tile, tw, P.L, m, t, lane, NL); break;
-            default: stage1<5, INV>(tile, tw, P.L, m, t, lane, NL); break;
+            for(int q = 1; q < R; q++) v[q] = cmulc(v[q], tw[jt * q]);
         }
-        __syncthreads();
+        if(KIND == 2) bf2<INV>(v[0], v[1]);
+        if(KIND == 3) bf3<INV>(v[0], v[1], v[2]);
+        if(KIND == 4) bf4<INV>(v[0], v[1], v[2], v[3]);
+        if(KIND == 5) bf5<INV>(v[0], v[1], v[2], v[3], v[4]);
+        if(!INV) {
+#pragma unroll
+            for(int q = 1; q < R; q++) v[q] = cmul(v[q], tw[jt * q]);
+        }
     }
 }
 
-__device__ __forceinline__ void load_twiddles(double2 *tw_s, const FftPlan &P)
+// ---- where a group's rows come from and go to ----
+// A group reads its rows either from the shared-memory tile or straight from global memory (the first group of a chain:
+// 16 independent 128-byte lines in flight per quarter warp, and the tile is neither written nor read for it), and writes
+// them to the tile or straight to global memory (the last group).  `map` translates a chain row into the global row
+// (frequency order <-> the digit-reversed row order of the chain); null = identity.
+struct RowsTile {
+    double2 *p;             // tile + t
+    __device__ __forceinline__ double2 ld(int row) const { return p[(size_t) row * FFT_T]; }
+    __device__ __forceinline__ void st(int row, double2 v) const { p[(size_t) row * FFT_T] = v; }
+};
+struct RowsGlobal {
+    double2 *p;             // first row + t
+    size_t stride;
+    const unsigned short *map;
+    bool ok;                // stores enabled (ragged last tile of the z passes)
+    __device__ __forceinline__ double2 ld(int row) const { return p[(size_t) (map ? map[row] : row) * stride]; }
+    __device__ __forceinline__ void st(int row, double2 v) const { if(ok) p[(size_t) (map ? map[row] : row) * stride] = v; }
+};
+struct NoMid { __device__ __forceinline__ double2 operator()(int, double2 v) const { return v; } };
+
+// DIR 0: forward group; 1: inverse group; 2: forward group, mid(row, value) on every row, inverse group (the turn of the
+// x pass: the last forward group, the Green's function and the first inverse group on the same registers).
+template <int KIND, int DIR, class Src, class Dst, class Mid>
+__device__ __forceinline__ void run_group(const Src &src, const Dst &dst, const Mid &mid, const double2 *tw, int L, int m, int lane, int NL)
 {
-    for(int i = threadIdx.x; i < P.L; i += blockDim.x) tw_s[i] = P.tw[i];
+    const int R = GroupSize<KIND>::R;
+    const int s = m / R, nb = L / R, tws = L / m;
+    for(int b = lane; b < nb; b += NL) {
+        const int g = b / s, j = b - g * s, base = g * m + j;
+        double2 v[R];
+#pragma unroll
+        for(int p = 0; p < R; p++) v[p] = src.ld(base + p * s);
+        if(DIR == 0 || DIR == 2) group_compute<KIND, false>(v, tw, j * tws);
+        if(DIR == 2) {
+#pragma unroll
+            for(int p = 0; p < R; p++) v[p] = mid(base + p * s, v[p]);
+        }
+        if(DIR == 1 || DIR == 2) group_compute<KIND, true>(v, tw, j * tws);
+#pragma unroll
+        for(int p = 0; p < R; p++) dst.st(base + p * s, v[p]);
+    }
+}
+
+template <int DIR, class Src, class Dst, class Mid>
+__device__ __forceinline__ void run_kind(int kind, const Src &src, const Dst &dst, const Mid &mid, const double2 *tw, int L, int m, int lane, int NL)
+{
+    switch(kind) {
+        case ST_44: run_group<ST_44, DIR>(src, dst, mid, tw, L, m, lane, NL); break;
+        case ST_42: run_group<ST_42, DIR>(src, dst, mid, tw, L, m, lane, NL); break;
+        case 4: run_group<4, DIR>(src, dst, mid, tw, L, m, lane, NL); break;
+        case 2: run_group<2, DIR>(src, dst, mid, tw, L, m, lane, NL); break;
+        case 3: run_group<3, DIR>(src, dst, mid, tw, L, m, lane, NL); break;
+        default: run_group<5, DIR>(src, dst, mid, tw, L, m, lane, NL); break;
+    }
+}
+
+// Groups [first, last] of the chain in forward (DIR 0: ascending) or inverse (DIR 1: descending) order; the first group
+// executed reads `src`, the last one writes `dst`, everything in between goes through the tile.  A barrier follows every
+// group that wrote the tile.
+template <int DIR, class Src, class Dst>
+__device__ __forceinline__ void run_chain(const FftPlan &P, int first, int last, const Src &src, const Dst &dst, const RowsTile &tile,
+                                          bool dst_is_tile, const double2 *tw, int lane, int NL)
+{
+    const int n = last - first + 1;
+    for(int i = 0; i < n; i++) {
+        const int g = DIR == 1 ? last - i : first + i;
+        const bool a = i == 0, z = i == n - 1;
+        if(a && z && !dst_is_tile) {
+            // a single group: its global stores (through a row map) must not overtake the loads of other threads
+            run_kind<DIR>(P.kind[g], src, tile, NoMid(), tw, P.L, P.m[g], lane, NL);
+            __syncthreads();
+            for(int l = lane; l < P.L; l += NL) dst.st(l, tile.ld(l));
+        } else if(a && z) run_kind<DIR>(P.kind[g], src, dst, NoMid(), tw, P.L, P.m[g], lane, NL);
+        else if(a) run_kind<DIR>(P.kind[g], src, tile, NoMid(), tw, P.L, P.m[g], lane, NL);
+        else if(z) run_kind<DIR>(P.kind[g], tile, dst, NoMid(), tw, P.L, P.m[g], lane, NL);
+        else run_kind<DIR>(P.kind[g], tile, tile, NoMid(), tw, P.L, P.m[g], lane, NL);
+        if(!z || dst_is_tile) __syncthreads();
+    }
+}
+
+// tables of the plan into shared memory behind the tile: tw[L] | pos[L] | freq[L]
+struct SmemTables { double2 *tw; unsigned short *pos, *freq; };
+__device__ __forceinline__ SmemTables load_tables(double2 *tile, const FftPlan &P)
+{
+    SmemTables S;
+    S.tw = tile + (size_t) P.L * FFT_T;
+    S.pos = (unsigned short *) (S.tw + P.L);
+    S.freq = S.pos + P.L;
+    for(int i = threadIdx.x; i < P.L; i += blockDim.x) { S.tw[i] = P.tw[i]; S.pos[i] = P.pos[i]; S.freq[i] = P.freq[i]; }
+    return S;
 }
 
 // z forward: 8 consecutive real lines of the mesh per block; line = N reals = L = N/2 packed complex values
@@ -269,26 +294,26 @@ k_fft_z_forward(const double *__restrict__ mesh, double2 *__restrict__ out, long
 {
     B200_DYN_SMEM(smem);
     double2 *tile = (double2 *) smem;
-    double2 *tw_s = tile + (size_t) P.L * FFT_T;
     const int L = P.L, t = threadIdx.x & (FFT_T - 1), lane = threadIdx.x / FFT_T, NL = blockDim.x / FFT_T;
-    const long long line = (long long) blockIdx.x * FFT_T + t;
+    long long line = (long long) blockIdx.x * FFT_T + t;
     const bool ok = line < nlines;
-    load_twiddles(tw_s, P);
-    const double2 *in = (const double2 *) mesh + line * L;
-    for(int l = lane; l < L; l += NL) tile[(size_t) l * FFT_T + t] = ok ? in[l] : make_double2(0.0, 0.0);
+    if(!ok) line = nlines - 1;             // ragged last tile: the spare columns recompute the last line and store nothing
+    const SmemTables S = load_tables(tile, P);
     __syncthreads();
-    fft_tile<false>(tile, tw_s, P, t, lane, NL);
+    const RowsTile T = {tile + t};
+    const RowsGlobal in = {(double2 *) mesh + line * L, 1, nullptr, false};
+    run_chain<0>(P, 0, P.nst - 1, in, T, T, true, S.tw, lane, NL);
     if(!ok) return;
     double2 *o = out + line * Nzp;
     for(int kk = lane; kk <= L / 2; kk += NL) {
         if(kk == 0) {
-            const double2 Z0 = tile[(size_t) P.pos[0] * FFT_T + t];
+            const double2 Z0 = T.ld(S.pos[0]);
             o[0] = make_double2(Z0.x + Z0.y, 0.0);
             o[L] = make_double2(Z0.x - Z0.y, 0.0);
             continue;
         }
         const int k2 = L - kk;
-        const double2 Z1 = tile[(size_t) P.pos[kk] * FFT_T + t], Z2 = tile[(size_t) P.pos[k2] * FFT_T + t];
+        const double2 Z1 = T.ld(S.pos[kk]), Z2 = T.ld(S.pos[k2]);
         const double2 A = make_double2(Z1.x + Z2.x, Z1.y - Z2.y);          // Z1 + conj Z2
         const double2 B = make_double2(Z1.x - Z2.x, Z1.y + Z2.y);          // Z1 - conj Z2
         const double2 Q = cmul(wN[kk], B);
@@ -305,28 +330,27 @@ k_fft_z_inverse(const double2 *__restrict__ in, double *__restrict__ mesh, long 
 {
     B200_DYN_SMEM(smem);
     double2 *tile = (double2 *) smem;
-    double2 *tw_s = tile + (size_t) P.L * FFT_T;
     const int L = P.L, t = threadIdx.x & (FFT_T - 1), lane = threadIdx.x / FFT_T, NL = blockDim.x / FFT_T;
-    const long long line = (long long) blockIdx.x * FFT_T + t;
+    long long line = (long long) blockIdx.x * FFT_T + t;
     const bool ok = line < nlines;
-    load_twiddles(tw_s, P);
+    if(!ok) line = nlines - 1;
+    const SmemTables S = load_tables(tile, P);
+    __syncthreads();
+    const RowsTile T = {tile + t};
     const double2 *x = in + line * Nzp;
     for(int kk = lane; kk <= L / 2; kk += NL) {
         const int k2 = L - kk;
-        double2 X1 = make_double2(0.0, 0.0), X2 = X1;
-        if(ok) { X1 = x[kk]; X2 = x[k2]; }
+        double2 X1 = x[kk], X2 = x[k2];
         if(kk == 0) { X1.y = 0.0; X2.y = 0.0; }          // the two real modes of a Hermitian line (cuFFT ignores their imaginary parts too)
         const double2 A = make_double2(X1.x + X2.x, X1.y - X2.y);
         const double2 B = make_double2(X1.x - X2.x, X1.y + X2.y);
         const double2 Q = cmulc(B, wN[kk]);
-        tile[(size_t) P.pos[kk] * FFT_T + t] = make_double2(A.x - Q.y, A.y + Q.x);
-        if(kk != 0 && k2 != kk) tile[(size_t) P.pos[k2] * FFT_T + t] = make_double2(A.x + Q.y, -A.y + Q.x);
+        T.st(S.pos[kk], make_double2(A.x - Q.y, A.y + Q.x));
+        if(kk != 0 && k2 != kk) T.st(S.pos[k2], make_double2(A.x + Q.y, -A.y + Q.x));
     }
     __syncthreads();
-    fft_tile<true>(tile, tw_s, P, t, lane, NL);
-    if(!ok) return;
-    double2 *o = (double2 *) mesh + line * L;
-    for(int l = lane; l < L; l += NL) o[l] = tile[(size_t) l * FFT_T + t];
+    const RowsGlobal o = {(double2 *) mesh + line * L, 1, nullptr, ok};
+    run_chain<1>(P, 0, P.nst - 1, T, o, T, false, S.tw, lane, NL);
 }
 
 struct GreenArgs {
@@ -336,77 +360,86 @@ struct GreenArgs {
     double *ps;
 };
 
+// potential_transfer (gravpm.c:383-454) on the value of chain row `row` of column iz, line iy; POWER: also
+// powerspectrum_add_mode (gravpm.c:330-361) on the untouched density mode, into the block's shared-memory bins.
+template <bool POWER>
+struct GreenMid {
+    GreenArgs G;
+    const unsigned short *freq;
+    int iy, iz, ky;
+    double fy, fz;
+    double *s_ps;
+    __device__ __forceinline__ double2 operator()(int row, double2 val) const
+    {
+        const int N = G.N;
+        if(iz >= G.Nz) return val;                       // padding columns of the row pitch
+        const int ix = freq[row];
+        const int kx = ix <= N / 2 ? ix : ix - N;       // petapm_mesh_to_k petapm.c:81-84
+        const long long k2 = (long long) kx * kx + (long long) ky * ky + (long long) iz * iz;
+        if(k2 == 0) {
+            if(POWER) G.ps[3 * N] = val.x * val.x + val.y * val.y;       // gravpm.c:332-336
+            return make_double2(0.0, 0.0);                               // gravpm.c:441-449
+        }
+        const double smth = exp((double) (-k2) * G.asmth2) / (double) k2;
+        const double f = (G.ktab[ix] * fy) * fz;
+        if(POWER) {
+            const int kint = (int) floor(G.binsperunit * log((double) k2) / 2.);
+            if(kint < N) {
+                const double w = (iz == 0 || iz == N / 2) ? 1.0 : 2.0;
+                const double mm = val.x * val.x + val.y * val.y;
+                atomicAdd(&s_ps[kint], w * mm * f * f);
+                atomicAdd(&s_ps[N + kint], w * sqrt((double) k2));
+                atomicAdd(&s_ps[2 * N + kint], w);
+            }
+        }
+        const double fac = ((G.pot_factor * smth) * f) * f;
+        return make_double2(val.x * fac, val.y * fac);
+    }
+};
+
 // Column passes over the half spectrum, in place.  Block (outer, tk) owns rows base + l * stride, l in [0, L), of 8
 // complex values each, base = outer * outer_stride + 8 tk.
 //   MODE 0: forward transform, rows back in frequency order.            (y forward: outer = ix, stride = Nzp)
 //   MODE 1: inverse transform of rows given in frequency order.         (y inverse)
-//   MODE 2, 3: forward, potential_transfer (gravpm.c:383-454; MODE 3 also powerspectrum_add_mode, gravpm.c:330-361),
-//           inverse.                                                    (x: outer = iy, stride = N Nzp)
+//   MODE 2, 3: forward, potential_transfer (MODE 3 also the power-spectrum sums), inverse.
+//                                                                       (x: outer = iy, stride = N Nzp)
 template <int MODE>
 __global__ void __launch_bounds__(256, 2)
 k_fft_columns(double2 *__restrict__ v, int ntile, size_t outer_stride, size_t stride, FftPlan P, GreenArgs G)
 {
     B200_DYN_SMEM(smem);
     double2 *tile = (double2 *) smem;
-    double2 *tw_s = tile + (size_t) P.L * FFT_T;
-    double *s_ps = (double *) (tw_s + P.L);          // MODE 3: [3][N]
-    const int L = P.L, t = threadIdx.x & (FFT_T - 1), lane = threadIdx.x / FFT_T, NL = blockDim.x / FFT_T;
+    const int t = threadIdx.x & (FFT_T - 1), lane = threadIdx.x / FFT_T, NL = blockDim.x / FFT_T;
     const int outer = blockIdx.x / ntile, tk = blockIdx.x - outer * ntile;
     double2 *g = v + (size_t) outer * outer_stride + (size_t) tk * FFT_T + t;
-    load_twiddles(tw_s, P);
+    const SmemTables S = load_tables(tile, P);
+    double *s_ps = (double *) (S.freq + P.L);          // MODE 3: [3][N]
     if(MODE == 3) for(int b = threadIdx.x; b < 3 * G.N; b += blockDim.x) s_ps[b] = 0;
-    if(MODE == 1)
-        for(int k = lane; k < L; k += NL) tile[(size_t) P.pos[k] * FFT_T + t] = g[(size_t) k * stride];
-    else
-        for(int l = lane; l < L; l += NL) tile[(size_t) l * FFT_T + t] = g[(size_t) l * stride];
     __syncthreads();
-    if(MODE == 1) {
-        fft_tile<true>(tile, tw_s, P, t, lane, NL);
-        for(int l = lane; l < L; l += NL) g[(size_t) l * stride] = tile[(size_t) l * FFT_T + t];
-        return;
-    }
-    fft_tile<false>(tile, tw_s, P, t, lane, NL);
+    const RowsTile T = {tile + t};
+    const int last = P.nst - 1;
     if(MODE == 0) {
-        for(int k = lane; k < L; k += NL) g[(size_t) k * stride] = tile[(size_t) P.pos[k] * FFT_T + t];
-        return;
-    }
-    {
-        const int N = G.N, iy = outer, iz = tk * FFT_T + t;
-        if(iz < G.Nz) {
-            const int ky = iy <= N / 2 ? iy : iy - N;       // petapm_mesh_to_k petapm.c:81-84
-            const double fyz = G.ktab[iy], fz = G.ktab[iz];
-            for(int l = lane; l < L; l += NL) {
-                const int ix = P.freq[l];
-                const int kx = ix <= N / 2 ? ix : ix - N;
-                const long long k2 = (long long) kx * kx + (long long) ky * ky + (long long) iz * iz;
-                double2 val = tile[(size_t) l * FFT_T + t];
-                if(k2 == 0) {
-                    if(MODE == 3) G.ps[3 * N] = val.x * val.x + val.y * val.y;       // gravpm.c:332-336
-                    val.x = 0.0; val.y = 0.0;                                        // gravpm.c:441-449
-                } else {
-                    const double smth = exp((double) (-k2) * G.asmth2) / (double) k2;
-                    const double f = (G.ktab[ix] * fyz) * fz;
-                    if(MODE == 3) {
-                        const int kint = (int) floor(G.binsperunit * log((double) k2) / 2.);
-                        if(kint < N) {
-                            const double w = (iz == 0 || iz == N / 2) ? 1.0 : 2.0;
-                            const double mm = val.x * val.x + val.y * val.y;
-                            atomicAdd(&s_ps[kint], w * mm * f * f);
-                            atomicAdd(&s_ps[N + kint], w * sqrt((double) k2));
-                            atomicAdd(&s_ps[2 * N + kint], w);
-                        }
-                    }
-                    const double fac = ((G.pot_factor * smth) * f) * f;
-                    val.x *= fac; val.y *= fac;
-                }
-                tile[(size_t) l * FFT_T + t] = val;
-            }
+        const RowsGlobal in = {g, stride, nullptr, true}, out = {g, stride, S.freq, true};
+        run_chain<0>(P, 0, last, in, out, T, false, S.tw, lane, NL);
+    } else if(MODE == 1) {
+        const RowsGlobal in = {g, stride, S.freq, true}, out = {g, stride, nullptr, true};
+        run_chain<1>(P, 0, last, in, out, T, false, S.tw, lane, NL);
+    } else {
+        const RowsGlobal io = {g, stride, nullptr, true};
+        const int iy = outer, iz = tk * FFT_T + t, N = G.N;
+        const GreenMid<MODE == 3> mid = {G, S.freq, iy, iz, iy <= N / 2 ? iy : iy - N, G.ktab[iy], G.ktab[iz < G.Nz ? iz : 0], s_ps};
+        const int kind = P.kind[last], m = P.m[last];
+        if(last == 0) run_kind<2>(kind, io, io, mid, S.tw, P.L, m, lane, NL);
+        else {
+            run_chain<0>(P, 0, last - 1, io, T, T, true, S.tw, lane, NL);
+            run_kind<2>(kind, T, T, mid, S.tw, P.L, m, lane, NL);
+            __syncthreads();
+            run_chain<1>(P, 0, last - 1, T, io, T, false, S.tw, lane, NL);
         }
-        __syncthreads();
-        fft_tile<true>(tile, tw_s, P, t, lane, NL);
-        for(int l = lane; l < L; l += NL) g[(size_t) l * stride] = tile[(size_t) l * FFT_T + t];
-        if(MODE == 3)
+        if(MODE == 3) {
+            __syncthreads();
             for(int b = threadIdx.x; b < 3 * N; b += blockDim.x) if(s_ps[b] != 0) atomicAdd(&G.ps[b], s_ps[b]);
+        }
     }
 }
 
@@ -430,6 +463,7 @@ static bool plan_stages(int L, std::vector<int> &kind, std::vector<int> &ms, std
 }
 
 // tables of one line length behind fft_tab + off (doubles): tw[L] double2 | pos[L], freq[L] unsigned short
+static size_t smem_bytes(int L) { return (size_t) L * FFT_T * 16 + (size_t) L * 16 + (((size_t) L * 4 + 15) & ~(size_t) 15); }
 static size_t plan_bytes(int L) { return (size_t) L * 16 + (((size_t) L * 4 + 15) & ~(size_t) 15); }
 
 static bool plan_fill(int L, unsigned char *h, FftPlan *P, const unsigned char *dev)
@@ -475,7 +509,7 @@ bool pmfft_supported(int N)
     if(!plan_stages(N, a, b, c)) return false;
     a.clear(); b.clear(); c.clear();
     if(!plan_stages(N / 2, a, b, c)) return false;
-    return (size_t) N * FFT_T * 16 + (size_t) N * 16 + 3 * (size_t) N * 8 <= 227 * 1024;
+    return smem_bytes(N) + 3 * (size_t) N * 8 <= 227 * 1024;
 }
 
 // Tables and kernel attributes for mesh size N.  The half spectrum lives in E->cplx with row pitch Nzp.
@@ -502,8 +536,8 @@ int pmfft_init(Engine *E, int N)
     F->wN = (const double2 *) (dev + bN + bH);
     CK(cudaMemcpyAsync(E->fft_tab.p, h.data(), h.size(), cudaMemcpyHostToDevice, E->stream));
     CK(cudaStreamSynchronize(E->stream));
-    F->smemN = (size_t) N * FFT_T * 16 + (size_t) N * 16;
-    F->smemH = (size_t) L * FFT_T * 16 + (size_t) L * 16;
+    F->smemN = smem_bytes(N);
+    F->smemH = smem_bytes(L);
     CK(cudaFuncSetAttribute(k_fft_z_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemH));
     CK(cudaFuncSetAttribute(k_fft_z_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemH));
     CK(cudaFuncSetAttribute(k_fft_columns<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
