@@ -198,18 +198,30 @@ __device__ __forceinline__ void group_compute(double2 *v, const double2 *tw, int
 // 16 independent 128-byte lines in flight per quarter warp, and the tile is neither written nor read for it), and writes
 // them to the tile or straight to global memory (the last group).  `map` translates a chain row into the global row
 // (frequency order <-> the digit-reversed row order of the chain); null = identity.
+// Tile element (row, column t) lives in slot (t + row) & 7 of its 128-byte row: 8 threads on the 8 columns of one row
+// and 8 threads on 8 consecutive rows of one column (the z passes' global-memory side) are both conflict-free.
 struct RowsTile {
-    double2 *p;             // tile + t
-    __device__ __forceinline__ double2 ld(int row) const { return p[(size_t) row * FFT_T]; }
-    __device__ __forceinline__ void st(int row, double2 v) const { p[(size_t) row * FFT_T] = v; }
+    double2 *tile;
+    int t;
+    __device__ __forceinline__ double2 ld(int row) const { return tile[(size_t) row * FFT_T + ((t + row) & (FFT_T - 1))]; }
+    __device__ __forceinline__ void st(int row, double2 v) const { tile[(size_t) row * FFT_T + ((t + row) & (FFT_T - 1))] = v; }
 };
+// CONJ: values are conjugated on the way in and out, which turns the forward chain into the inverse transform.
+template <bool CONJ>
 struct RowsGlobal {
-    double2 *p;             // first row + t
+    double2 *p;             // first row + column
     size_t stride;
     const unsigned short *map;
     bool ok;                // stores enabled (ragged last tile of the z passes)
-    __device__ __forceinline__ double2 ld(int row) const { return p[(size_t) (map ? map[row] : row) * stride]; }
-    __device__ __forceinline__ void st(int row, double2 v) const { if(ok) p[(size_t) (map ? map[row] : row) * stride] = v; }
+    __device__ __forceinline__ double2 ld(int row) const
+    {
+        const double2 v = p[(size_t) (map ? map[row] : row) * stride];
+        return CONJ ? make_double2(v.x, -v.y) : v;
+    }
+    __device__ __forceinline__ void st(int row, double2 v) const
+    {
+        if(ok) p[(size_t) (map ? map[row] : row) * stride] = CONJ ? make_double2(v.x, -v.y) : v;
+    }
 };
 struct NoMid { __device__ __forceinline__ double2 operator()(int, double2 v) const { return v; } };
 
@@ -219,20 +231,40 @@ template <int KIND, int DIR, class Src, class Dst, class Mid>
 __device__ __forceinline__ void run_group(const Src &src, const Dst &dst, const Mid &mid, const double2 *tw, int L, int m, int lane, int NL)
 {
     const int R = GroupSize<KIND>::R;
+    const int U = R <= 3 ? 4 : (R <= 5 ? 2 : 1);      // butterflies per turn: 8 to 16 independent rows in flight per thread
     const int s = m / R, nb = L / R, tws = L / m;
-    for(int b = lane; b < nb; b += NL) {
-        const int g = b / s, j = b - g * s, base = g * m + j;
-        double2 v[R];
+    for(int b0 = lane; b0 < nb; b0 += NL * U) {
+        double2 v[U * R];
+        int base[U], jt[U];
+        bool live[U];
 #pragma unroll
-        for(int p = 0; p < R; p++) v[p] = src.ld(base + p * s);
-        if(DIR == 0 || DIR == 2) group_compute<KIND, false>(v, tw, j * tws);
-        if(DIR == 2) {
+        for(int u = 0; u < U; u++) {
+            int b = b0 + u * NL;
+            live[u] = b < nb;
+            if(!live[u]) b = b0;                 // a spare slot of the last turn repeats the first butterfly and stores nothing
+            const int g = b / s, j = b - g * s;
+            base[u] = g * m + j; jt[u] = j * tws;
 #pragma unroll
-            for(int p = 0; p < R; p++) v[p] = mid(base + p * s, v[p]);
+            for(int p = 0; p < R; p++) v[u * R + p] = src.ld(base[u] + p * s);
         }
-        if(DIR == 1 || DIR == 2) group_compute<KIND, true>(v, tw, j * tws);
 #pragma unroll
-        for(int p = 0; p < R; p++) dst.st(base + p * s, v[p]);
+        for(int u = 0; u < U; u++) {
+            if(DIR == 0 || DIR == 2) group_compute<KIND, false>(v + u * R, tw, jt[u]);
+            if(DIR == 2) {
+                if(live[u]) {
+#pragma unroll
+                    for(int p = 0; p < R; p++) v[u * R + p] = mid(base[u] + p * s, v[u * R + p]);
+                }
+            }
+            if(DIR == 1 || DIR == 2) group_compute<KIND, true>(v + u * R, tw, jt[u]);
+        }
+#pragma unroll
+        for(int u = 0; u < U; u++) {
+            if(live[u]) {
+#pragma unroll
+                for(int p = 0; p < R; p++) dst.st(base[u] + p * s, v[u * R + p]);
+            }
+        }
     }
 }
 
@@ -249,26 +281,39 @@ __device__ __forceinline__ void run_kind(int kind, const Src &src, const Dst &ds
     }
 }
 
-// Groups [first, last] of the chain in forward (DIR 0: ascending) or inverse (DIR 1: descending) order; the first group
-// executed reads `src`, the last one writes `dst`, everything in between goes through the tile.  A barrier follows every
-// group that wrote the tile.
-template <int DIR, class Src, class Dst>
-__device__ __forceinline__ void run_chain(const FftPlan &P, int first, int last, const Src &src, const Dst &dst, const RowsTile &tile,
-                                          bool dst_is_tile, const double2 *tw, int lane, int NL)
+// Which column and which butterflies a thread works on.  Standard: 8 neighbouring threads = the 8 columns of one row.
+// Transposed (the groups of the z passes that touch global memory, where a column is a contiguous line): 8 neighbouring
+// threads = 8 consecutive rows of one column.
+struct ThreadMap { int t, lane; };
+__device__ __forceinline__ ThreadMap map_standard() { ThreadMap M = {(int) (threadIdx.x & (FFT_T - 1)), (int) (threadIdx.x / FFT_T)}; return M; }
+__device__ __forceinline__ ThreadMap map_transposed()
 {
-    const int n = last - first + 1;
+    ThreadMap M = {(int) ((threadIdx.x / FFT_T) & (FFT_T - 1)), (int) ((threadIdx.x / (FFT_T * FFT_T)) * FFT_T + (threadIdx.x & (FFT_T - 1)))};
+    return M;
+}
+
+// Groups [first, last] of the chain in forward (DIR 0: ascending) or inverse (DIR 1: descending) order; the first group
+// executed reads `src` under thread map Ma, the last one writes `dst` under Mz, everything in between goes through the
+// tile under the standard map.  A barrier follows every group that wrote the tile.
+template <int DIR, class Src, class Dst>
+__device__ __forceinline__ void run_chain(const FftPlan &P, int first, int last, const Src &src, const Dst &dst, double2 *tile,
+                                          bool dst_is_tile, const double2 *tw, ThreadMap Ma, ThreadMap Mz)
+{
+    const int n = last - first + 1, NL = blockDim.x / FFT_T;
+    const ThreadMap Ms = map_standard();
+    const RowsTile Ta = {tile, Ma.t}, Tz = {tile, Mz.t}, Ts = {tile, Ms.t};
     for(int i = 0; i < n; i++) {
         const int g = DIR == 1 ? last - i : first + i;
         const bool a = i == 0, z = i == n - 1;
         if(a && z && !dst_is_tile) {
             // a single group: its global stores (through a row map) must not overtake the loads of other threads
-            run_kind<DIR>(P.kind[g], src, tile, NoMid(), tw, P.L, P.m[g], lane, NL);
+            run_kind<DIR>(P.kind[g], src, Ta, NoMid(), tw, P.L, P.m[g], Ma.lane, NL);
             __syncthreads();
-            for(int l = lane; l < P.L; l += NL) dst.st(l, tile.ld(l));
-        } else if(a && z) run_kind<DIR>(P.kind[g], src, dst, NoMid(), tw, P.L, P.m[g], lane, NL);
-        else if(a) run_kind<DIR>(P.kind[g], src, tile, NoMid(), tw, P.L, P.m[g], lane, NL);
-        else if(z) run_kind<DIR>(P.kind[g], tile, dst, NoMid(), tw, P.L, P.m[g], lane, NL);
-        else run_kind<DIR>(P.kind[g], tile, tile, NoMid(), tw, P.L, P.m[g], lane, NL);
+            for(int l = Ma.lane; l < P.L; l += NL) dst.st(l, Ta.ld(l));
+        } else if(a && z) run_kind<DIR>(P.kind[g], src, dst, NoMid(), tw, P.L, P.m[g], Ma.lane, NL);
+        else if(a) run_kind<DIR>(P.kind[g], src, Ta, NoMid(), tw, P.L, P.m[g], Ma.lane, NL);
+        else if(z) run_kind<DIR>(P.kind[g], Tz, dst, NoMid(), tw, P.L, P.m[g], Mz.lane, NL);
+        else run_kind<DIR>(P.kind[g], Ts, Ts, NoMid(), tw, P.L, P.m[g], Ms.lane, NL);
         if(!z || dst_is_tile) __syncthreads();
     }
 }
@@ -294,18 +339,20 @@ k_fft_z_forward(const double *__restrict__ mesh, double2 *__restrict__ out, long
 {
     B200_DYN_SMEM(smem);
     double2 *tile = (double2 *) smem;
-    const int L = P.L, t = threadIdx.x & (FFT_T - 1), lane = threadIdx.x / FFT_T, NL = blockDim.x / FFT_T;
-    long long line = (long long) blockIdx.x * FFT_T + t;
+    const int L = P.L, NL = blockDim.x / FFT_T;
+    const ThreadMap Mg = map_transposed(), Ms = map_standard();
+    long long line = (long long) blockIdx.x * FFT_T + Mg.t;
     const bool ok = line < nlines;
     if(!ok) line = nlines - 1;             // ragged last tile: the spare columns recompute the last line and store nothing
     const SmemTables S = load_tables(tile, P);
     __syncthreads();
-    const RowsTile T = {tile + t};
-    const RowsGlobal in = {(double2 *) mesh + line * L, 1, nullptr, false};
-    run_chain<0>(P, 0, P.nst - 1, in, T, T, true, S.tw, lane, NL);
+    const RowsGlobal<false> in = {(double2 *) mesh + line * L, 1, nullptr, false};
+    if(P.nst == 1) { const RowsTile T1 = {tile, Mg.t}; run_chain<0>(P, 0, 0, in, T1, tile, true, S.tw, Mg, Mg); }
+    else { const RowsTile T1 = {tile, Ms.t}; run_chain<0>(P, 0, P.nst - 1, in, T1, tile, true, S.tw, Mg, Ms); }
     if(!ok) return;
+    const RowsTile T = {tile, Mg.t};
     double2 *o = out + line * Nzp;
-    for(int kk = lane; kk <= L / 2; kk += NL) {
+    for(int kk = Mg.lane; kk <= L / 2; kk += NL) {
         if(kk == 0) {
             const double2 Z0 = T.ld(S.pos[0]);
             o[0] = make_double2(Z0.x + Z0.y, 0.0);
@@ -320,7 +367,7 @@ k_fft_z_forward(const double *__restrict__ mesh, double2 *__restrict__ out, long
         o[kk] = make_double2(0.5 * (A.x + Q.y), 0.5 * (A.y - Q.x));
         if(k2 != kk) o[k2] = make_double2(0.5 * (A.x - Q.y), 0.5 * (-A.y - Q.x));
     }
-    for(int k = L + 1 + lane; k < Nzp; k += NL) o[k] = make_double2(0.0, 0.0);
+    for(int k = L + 1 + Mg.lane; k < Nzp; k += NL) o[k] = make_double2(0.0, 0.0);
 }
 
 // z inverse: Z[k] = (X[k] + conj X[L-k]) + i exp(+2 pi i k/N) (X[k] - conj X[L-k]), inverse FFT_L, unpack: N x the real line.
@@ -330,15 +377,16 @@ k_fft_z_inverse(const double2 *__restrict__ in, double *__restrict__ mesh, long 
 {
     B200_DYN_SMEM(smem);
     double2 *tile = (double2 *) smem;
-    const int L = P.L, t = threadIdx.x & (FFT_T - 1), lane = threadIdx.x / FFT_T, NL = blockDim.x / FFT_T;
-    long long line = (long long) blockIdx.x * FFT_T + t;
+    const int L = P.L, NL = blockDim.x / FFT_T;
+    const ThreadMap Mg = map_transposed(), Ms = map_standard();
+    long long line = (long long) blockIdx.x * FFT_T + Mg.t;
     const bool ok = line < nlines;
     if(!ok) line = nlines - 1;
     const SmemTables S = load_tables(tile, P);
     __syncthreads();
-    const RowsTile T = {tile + t};
+    const RowsTile T = {tile, Mg.t};
     const double2 *x = in + line * Nzp;
-    for(int kk = lane; kk <= L / 2; kk += NL) {
+    for(int kk = Mg.lane; kk <= L / 2; kk += NL) {
         const int k2 = L - kk;
         double2 X1 = x[kk], X2 = x[k2];
         if(kk == 0) { X1.y = 0.0; X2.y = 0.0; }          // the two real modes of a Hermitian line (cuFFT ignores their imaginary parts too)
@@ -349,8 +397,9 @@ k_fft_z_inverse(const double2 *__restrict__ in, double *__restrict__ mesh, long 
         if(kk != 0 && k2 != kk) T.st(S.pos[k2], make_double2(A.x + Q.y, -A.y + Q.x));
     }
     __syncthreads();
-    const RowsGlobal o = {(double2 *) mesh + line * L, 1, nullptr, ok};
-    run_chain<1>(P, 0, P.nst - 1, T, o, T, false, S.tw, lane, NL);
+    const RowsGlobal<false> o = {(double2 *) mesh + line * L, 1, nullptr, ok};
+    if(P.nst == 1) run_chain<1>(P, 0, 0, T, o, tile, false, S.tw, Mg, Mg);
+    else { const RowsTile T1 = {tile, Ms.t}; run_chain<1>(P, 0, P.nst - 1, T1, o, tile, false, S.tw, Ms, Mg); }
 }
 
 struct GreenArgs {
@@ -409,32 +458,35 @@ k_fft_columns(double2 *__restrict__ v, int ntile, size_t outer_stride, size_t st
 {
     B200_DYN_SMEM(smem);
     double2 *tile = (double2 *) smem;
-    const int t = threadIdx.x & (FFT_T - 1), lane = threadIdx.x / FFT_T, NL = blockDim.x / FFT_T;
+    const int NL = blockDim.x / FFT_T;
+    const ThreadMap M = map_standard();
+    const int t = M.t, lane = M.lane;
     const int outer = blockIdx.x / ntile, tk = blockIdx.x - outer * ntile;
     double2 *g = v + (size_t) outer * outer_stride + (size_t) tk * FFT_T + t;
     const SmemTables S = load_tables(tile, P);
     double *s_ps = (double *) (S.freq + P.L);          // MODE 3: [3][N]
     if(MODE == 3) for(int b = threadIdx.x; b < 3 * G.N; b += blockDim.x) s_ps[b] = 0;
     __syncthreads();
-    const RowsTile T = {tile + t};
+    const RowsTile T = {tile, t};
     const int last = P.nst - 1;
     if(MODE == 0) {
-        const RowsGlobal in = {g, stride, nullptr, true}, out = {g, stride, S.freq, true};
-        run_chain<0>(P, 0, last, in, out, T, false, S.tw, lane, NL);
+        const RowsGlobal<false> in = {g, stride, nullptr, true}, out = {g, stride, S.freq, true};
+        run_chain<0>(P, 0, last, in, out, tile, false, S.tw, M, M);
     } else if(MODE == 1) {
-        const RowsGlobal in = {g, stride, S.freq, true}, out = {g, stride, nullptr, true};
-        run_chain<1>(P, 0, last, in, out, T, false, S.tw, lane, NL);
+        // the inverse as the conjugate of the forward chain on conjugated input: the 16-row group reads global memory
+        const RowsGlobal<true> in = {g, stride, nullptr, true}, out = {g, stride, S.freq, true};
+        run_chain<0>(P, 0, last, in, out, tile, false, S.tw, M, M);
     } else {
-        const RowsGlobal io = {g, stride, nullptr, true};
+        const RowsGlobal<false> io = {g, stride, nullptr, true};
         const int iy = outer, iz = tk * FFT_T + t, N = G.N;
         const GreenMid<MODE == 3> mid = {G, S.freq, iy, iz, iy <= N / 2 ? iy : iy - N, G.ktab[iy], G.ktab[iz < G.Nz ? iz : 0], s_ps};
         const int kind = P.kind[last], m = P.m[last];
         if(last == 0) run_kind<2>(kind, io, io, mid, S.tw, P.L, m, lane, NL);
         else {
-            run_chain<0>(P, 0, last - 1, io, T, T, true, S.tw, lane, NL);
+            run_chain<0>(P, 0, last - 1, io, T, tile, true, S.tw, M, M);
             run_kind<2>(kind, T, T, mid, S.tw, P.L, m, lane, NL);
             __syncthreads();
-            run_chain<1>(P, 0, last - 1, T, io, T, false, S.tw, lane, NL);
+            run_chain<1>(P, 0, last - 1, T, io, tile, false, S.tw, M, M);
         }
         if(MODE == 3) {
             __syncthreads();
@@ -521,7 +573,7 @@ int pmfft_init(Engine *E, int N)
     E->ownfft = F;
     F->N = N;
     F->Nzp = (N / 2 + 1 + FFT_T - 1) / FFT_T * FFT_T;
-    if(const char *s = getenv("B200_FFT_THREADS")) { const int v = atoi(s); if(v >= 32 && v <= 256 && v % 32 == 0) F->threads = v; }
+    if(const char *s = getenv("B200_FFT_THREADS")) { const int v = atoi(s); if(v >= 64 && v <= 256 && v % 64 == 0) F->threads = v; }       // map_transposed() needs whole 8 x 8 thread groups
     const int L = N / 2;
     const size_t bN = plan_bytes(N), bH = plan_bytes(L), bW = (size_t) (L + 1) * 16;
     std::vector<unsigned char> h(bN + bH + bW);

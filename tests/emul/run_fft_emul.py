@@ -1,7 +1,7 @@
 """mp-gadget_b200/csrc/pm_fft.cu -- kernels and host driver, source unchanged -- on the CPU emulation of tests/emul:
 density mesh -> potential mesh against numpy's rfftn / Green's function / irfftn, and the power-spectrum sums of the
 fused x pass against a direct numpy restatement of powerspectrum_add_mode (gravpm.c:330-361).  TEST INFRASTRUCTURE ONLY.
-Started by tests/test_pm_fft_emul.py in a subprocess (OMP_WAIT_POLICY=passive, B200_FFT_THREADS=32)."""
+Started by tests/test_pm_fft_emul.py in a subprocess (OMP_WAIT_POLICY=passive, B200_FFT_THREADS=64)."""
 import ctypes as C
 import os
 import sys
