@@ -206,6 +206,14 @@ struct RowsTile {
     __device__ __forceinline__ double2 ld(int row) const { return tile[(size_t) row * FFT_T + ((t + row) & (FFT_T - 1))]; }
     __device__ __forceinline__ void st(int row, double2 v) const { tile[(size_t) row * FFT_T + ((t + row) & (FFT_T - 1))] = v; }
 };
+// The same through a row map (the z passes keep a second tile in frequency order for the split / merge of the packed line).
+struct RowsTileMap {
+    double2 *tile;
+    int t;
+    const unsigned short *map;
+    __device__ __forceinline__ double2 ld(int row) const { const int r = map[row]; return tile[(size_t) r * FFT_T + ((t + r) & (FFT_T - 1))]; }
+    __device__ __forceinline__ void st(int row, double2 v) const { const int r = map[row]; tile[(size_t) r * FFT_T + ((t + r) & (FFT_T - 1))] = v; }
+};
 // CONJ: values are conjugated on the way in and out, which turns the forward chain into the inverse transform.
 template <bool CONJ>
 struct RowsGlobal {
@@ -320,10 +328,10 @@ __device__ __forceinline__ void run_chain(const FftPlan &P, int first, int last,
 
 // tables of the plan into shared memory behind the tile: tw[L] | pos[L] | freq[L]
 struct SmemTables { double2 *tw; unsigned short *pos, *freq; };
-__device__ __forceinline__ SmemTables load_tables(double2 *tile, const FftPlan &P)
+__device__ __forceinline__ SmemTables load_tables(double2 *behind_tiles, const FftPlan &P)
 {
     SmemTables S;
-    S.tw = tile + (size_t) P.L * FFT_T;
+    S.tw = behind_tiles;
     S.pos = (unsigned short *) (S.tw + P.L);
     S.freq = S.pos + P.L;
     for(int i = threadIdx.x; i < P.L; i += blockDim.x) { S.tw[i] = P.tw[i]; S.pos[i] = P.pos[i]; S.freq[i] = P.freq[i]; }
@@ -344,23 +352,24 @@ k_fft_z_forward(const double *__restrict__ mesh, double2 *__restrict__ out, long
     long long line = (long long) blockIdx.x * FFT_T + Mg.t;
     const bool ok = line < nlines;
     if(!ok) line = nlines - 1;             // ragged last tile: the spare columns recompute the last line and store nothing
-    const SmemTables S = load_tables(tile, P);
+    double2 *tile2 = tile + (size_t) L * FFT_T;          // the transform in frequency order
+    const SmemTables S = load_tables(tile2 + (size_t) L * FFT_T, P);
     __syncthreads();
     const RowsGlobal<false> in = {(double2 *) mesh + line * L, 1, nullptr, false};
-    if(P.nst == 1) { const RowsTile T1 = {tile, Mg.t}; run_chain<0>(P, 0, 0, in, T1, tile, true, S.tw, Mg, Mg); }
-    else { const RowsTile T1 = {tile, Ms.t}; run_chain<0>(P, 0, P.nst - 1, in, T1, tile, true, S.tw, Mg, Ms); }
+    if(P.nst == 1) { const RowsTileMap T1 = {tile2, Mg.t, S.freq}; run_chain<0>(P, 0, 0, in, T1, tile, true, S.tw, Mg, Mg); }
+    else { const RowsTileMap T1 = {tile2, Ms.t, S.freq}; run_chain<0>(P, 0, P.nst - 1, in, T1, tile, true, S.tw, Mg, Ms); }
     if(!ok) return;
-    const RowsTile T = {tile, Mg.t};
+    const RowsTile T = {tile2, Mg.t};
     double2 *o = out + line * Nzp;
     for(int kk = Mg.lane; kk <= L / 2; kk += NL) {
         if(kk == 0) {
-            const double2 Z0 = T.ld(S.pos[0]);
+            const double2 Z0 = T.ld(0);
             o[0] = make_double2(Z0.x + Z0.y, 0.0);
             o[L] = make_double2(Z0.x - Z0.y, 0.0);
             continue;
         }
         const int k2 = L - kk;
-        const double2 Z1 = T.ld(S.pos[kk]), Z2 = T.ld(S.pos[k2]);
+        const double2 Z1 = T.ld(kk), Z2 = T.ld(k2);
         const double2 A = make_double2(Z1.x + Z2.x, Z1.y - Z2.y);          // Z1 + conj Z2
         const double2 B = make_double2(Z1.x - Z2.x, Z1.y + Z2.y);          // Z1 - conj Z2
         const double2 Q = cmul(wN[kk], B);
@@ -382,9 +391,10 @@ k_fft_z_inverse(const double2 *__restrict__ in, double *__restrict__ mesh, long 
     long long line = (long long) blockIdx.x * FFT_T + Mg.t;
     const bool ok = line < nlines;
     if(!ok) line = nlines - 1;
-    const SmemTables S = load_tables(tile, P);
+    double2 *tile2 = tile + (size_t) L * FFT_T;          // the packed line's spectrum in frequency order
+    const SmemTables S = load_tables(tile2 + (size_t) L * FFT_T, P);
     __syncthreads();
-    const RowsTile T = {tile, Mg.t};
+    const RowsTile T = {tile2, Mg.t};
     const double2 *x = in + line * Nzp;
     for(int kk = Mg.lane; kk <= L / 2; kk += NL) {
         const int k2 = L - kk;
@@ -393,13 +403,13 @@ k_fft_z_inverse(const double2 *__restrict__ in, double *__restrict__ mesh, long 
         const double2 A = make_double2(X1.x + X2.x, X1.y - X2.y);
         const double2 B = make_double2(X1.x - X2.x, X1.y + X2.y);
         const double2 Q = cmulc(B, wN[kk]);
-        T.st(S.pos[kk], make_double2(A.x - Q.y, A.y + Q.x));
-        if(kk != 0 && k2 != kk) T.st(S.pos[k2], make_double2(A.x + Q.y, -A.y + Q.x));
+        T.st(kk, make_double2(A.x - Q.y, A.y + Q.x));
+        if(kk != 0 && k2 != kk) T.st(k2, make_double2(A.x + Q.y, -A.y + Q.x));
     }
     __syncthreads();
     const RowsGlobal<false> o = {(double2 *) mesh + line * L, 1, nullptr, ok};
-    if(P.nst == 1) run_chain<1>(P, 0, 0, T, o, tile, false, S.tw, Mg, Mg);
-    else { const RowsTile T1 = {tile, Ms.t}; run_chain<1>(P, 0, P.nst - 1, T1, o, tile, false, S.tw, Ms, Mg); }
+    if(P.nst == 1) { const RowsTileMap T1 = {tile2, Mg.t, S.freq}; run_chain<1>(P, 0, 0, T1, o, tile, false, S.tw, Mg, Mg); }
+    else { const RowsTileMap T1 = {tile2, Ms.t, S.freq}; run_chain<1>(P, 0, P.nst - 1, T1, o, tile, false, S.tw, Ms, Mg); }
 }
 
 struct GreenArgs {
@@ -463,7 +473,7 @@ k_fft_columns(double2 *__restrict__ v, int ntile, size_t outer_stride, size_t st
     const int t = M.t, lane = M.lane;
     const int outer = blockIdx.x / ntile, tk = blockIdx.x - outer * ntile;
     double2 *g = v + (size_t) outer * outer_stride + (size_t) tk * FFT_T + t;
-    const SmemTables S = load_tables(tile, P);
+    const SmemTables S = load_tables(tile + (size_t) P.L * FFT_T, P);
     double *s_ps = (double *) (S.freq + P.L);          // MODE 3: [3][N]
     if(MODE == 3) for(int b = threadIdx.x; b < 3 * G.N; b += blockDim.x) s_ps[b] = 0;
     __syncthreads();
@@ -561,7 +571,7 @@ bool pmfft_supported(int N)
     if(!plan_stages(N, a, b, c)) return false;
     a.clear(); b.clear(); c.clear();
     if(!plan_stages(N / 2, a, b, c)) return false;
-    return smem_bytes(N) + 3 * (size_t) N * 8 <= 227 * 1024;
+    return smem_bytes(N) + 3 * (size_t) N * 8 <= 227 * 1024 && smem_bytes(N / 2) + (size_t) (N / 2) * FFT_T * 16 <= 227 * 1024;
 }
 
 // Tables and kernel attributes for mesh size N.  The half spectrum lives in E->cplx with row pitch Nzp.
@@ -589,7 +599,7 @@ int pmfft_init(Engine *E, int N)
     CK(cudaMemcpyAsync(E->fft_tab.p, h.data(), h.size(), cudaMemcpyHostToDevice, E->stream));
     CK(cudaStreamSynchronize(E->stream));
     F->smemN = smem_bytes(N);
-    F->smemH = smem_bytes(L);
+    F->smemH = smem_bytes(L) + (size_t) L * FFT_T * 16;          // two tiles
     CK(cudaFuncSetAttribute(k_fft_z_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemH));
     CK(cudaFuncSetAttribute(k_fft_z_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemH));
     CK(cudaFuncSetAttribute(k_fft_columns<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
