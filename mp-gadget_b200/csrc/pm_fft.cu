@@ -30,8 +30,13 @@
 
 namespace b200 {
 
-#define FFT_T 8
+#ifndef FFT_T
+#define FFT_T 8        // complex values per tile row: 128 bytes (4 = 64-byte rows, experiment builds)
+#endif
 #define FFT_MAXST 12
+#ifndef FFT_MINB
+#define FFT_MINB 2      // resident blocks per SM the kernels are compiled for (register cap 128 at 256 threads)
+#endif
 enum { ST_44 = 44, ST_42 = 42 };
 
 struct FftPlan {
@@ -341,7 +346,7 @@ __device__ __forceinline__ SmemTables load_tables(double2 *behind_tiles, const F
 // z forward: 8 consecutive real lines of the mesh per block; line = N reals = L = N/2 packed complex values
 // z[j] = x[2j] + i x[2j+1].  With Z = FFT_L(z):  X[k] = (Z[k] + conj Z[L-k])/2 - i exp(-2 pi i k/N) (Z[k] - conj Z[L-k])/2,
 // k = 0..L (Z[L] = Z[0]).  Output rows have pitch Nzp >= L + 1 (a multiple of 8); the padding is zeroed.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, FFT_MINB)
 k_fft_z_forward(const double *__restrict__ mesh, double2 *__restrict__ out, long long nlines, int Nzp,
                 FftPlan P, const double2 *__restrict__ wN)
 {
@@ -380,7 +385,7 @@ k_fft_z_forward(const double *__restrict__ mesh, double2 *__restrict__ out, long
 }
 
 // z inverse: Z[k] = (X[k] + conj X[L-k]) + i exp(+2 pi i k/N) (X[k] - conj X[L-k]), inverse FFT_L, unpack: N x the real line.
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, FFT_MINB)
 k_fft_z_inverse(const double2 *__restrict__ in, double *__restrict__ mesh, long long nlines, int Nzp,
                 FftPlan P, const double2 *__restrict__ wN)
 {
@@ -463,7 +468,7 @@ struct GreenMid {
 //   MODE 2, 3: forward, potential_transfer (MODE 3 also the power-spectrum sums), inverse.
 //                                                                       (x: outer = iy, stride = N Nzp)
 template <int MODE>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, FFT_MINB)
 k_fft_columns(double2 *__restrict__ v, int ntile, size_t outer_stride, size_t stride, FftPlan P, GreenArgs G)
 {
     B200_DYN_SMEM(smem);

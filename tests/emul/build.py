@@ -112,5 +112,6 @@ def build_fft(force=False):
     inc = ["-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "mp-gadget_b200", "csrc")]
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off"] +
                           (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if ASAN else []) +
-                          ["-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-o", FFT_SO, gen, drv] + inc)
+                          ["-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-o", FFT_SO, gen, drv] + inc +
+                          (["-DFFT_T=" + os.environ["EMUL_FFT_T"]] if os.environ.get("EMUL_FFT_T") else []))
     return FFT_SO
