@@ -812,8 +812,10 @@ def main():
             S.set_times(np.zeros(7, np.int64), np.zeros(47, np.int64), np.zeros(47, np.int64))
             sub = []
             for k in range(7):
+                S.prof = {}
                 t0 = time.perf_counter(); bad, sinfo = S.advance(first=(k == 0), pm=True); dt = time.perf_counter() - t0
-                sub.append({"wall_ms": 1e3 * dt, "active": int(sinfo[1]), "is_pm": int(sinfo[2]), "bad": bad})
+                sub.append({"wall_ms": 1e3 * dt, "active": int(sinfo[1]), "is_pm": int(sinfo[2]), "bad": bad,
+                            "stages_ms": {a: round(b, 2) for a, b in S.prof.items()}})
             out["steploop"] = {"substeps": sub, "host_bytes_per_substep": "scalars only", "aos_roundtrip_bytes_per_force_call": 2 * 160 * n,
                                "what": "hierarchical KDK sub-steps (timestep.c:296-598) with the particle state resident in HBM"}
         except Exception as ex:

@@ -258,22 +258,34 @@ class StepEngine:
             t.Ti_Current = t.Ti_Current + dti_from_timebin(t.mintimebin)          # find_next_kick timestep.c:1324-1328
         atime = self.atime()
         is_pm = self.is_pm()
+        prof = getattr(self, "prof", None)          # optional {stage: wall ms} of this pass (every stage ends with a scalar read-back)
+        import time as _time
+        def stage(name, t0):
+            if prof is not None:
+                prof[name] = prof.get(name, 0.0) + 1e3 * (_time.perf_counter() - t0)
+            return _time.perf_counter()
+        tt = _time.perf_counter()
         if not first:
             self.drift(last, t.Ti_Current)
         _, counts = self.build_active()
+        tt = stage("drift+active", tt)
         if maxsig is not None:          # gas takes part with its hydro accelerations held fixed: closing hydro kick, run.c:498-499
             self.kick(1, atime)
         if pm and is_pm:
             self.pm_force()
+        tt = stage("pm_force", tt)
         if counts[1] > 0:               # run.c:533
             self._ck(self.L.b200_step_hier_accelerations(self.ctx, C.byref(self.sp), C.byref(self.gp), C.byref(t), C.c_int64(int(counts[1]))))
+        tt = stage("hier_accelerations", tt)
         self.kick(3)
         if is_pm:
             self.kick(2)
+        tt = stage("kicks", tt)
         info = np.zeros(3, np.int64)
         if counts[1] > 0:
             self._ck(self.L.b200_step_hier_timesteps(self.ctx, C.byref(self.sp), C.byref(self.gp), C.byref(t), C.c_int64(int(counts[1])),
                                                      C.c_int(1 if is_pm else 0), C.c_double(atime), C.c_double(float(self.hubble(atime))), _p(info)))
+        tt = stage("hier_timesteps", tt)
         if maxsig is not None:          # run.c:767-773
             b2, _ = self.hydro_timesteps(maxsig, atime, first, fetch=False)
             info[2] += b2
@@ -281,6 +293,7 @@ class StepEngine:
         self.kick(3)
         if is_pm:
             self.kick(2)
+        stage("kicks", tt)
         return int(info[2]), np.array([counts[0], counts[1], 1 if is_pm else 0], np.int64)
 
     def advance_nonsplit(self, asmth=None, first=False, pm=False):
