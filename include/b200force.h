@@ -491,6 +491,17 @@ int b200_domain_exchange_plan(b200_ctx *ctx, const int32_t *task_of_leaf, int32_
  * cost; host arithmetic, no context.  Non-zero where the reference would endrun. */
 int b200_domain_assign_balanced(int32_t ntask, int32_t nleaf, const int64_t *cost, int32_t nseg_per_task, int32_t *task_out);
 
+/* ---- friends-of-friends, primary linking -------------------------------------------------------
+ * Replaces fof_label_primary + fof_primary_ngbiter (libgadget/fof.c:366-470,540-579), the repeated treewalk_run of the
+ * FOF group finder, for the particles set with b200_set_particles_*: particles whose type is in primary_mask
+ * (FOFPrimaryLinkTypes, bit t = type t) and that lie within linking_length of each other (periodic, NEAREST) form one
+ * group; minid_out[i] = the smallest ids[] of i's group (HaloLabel[i].MinID at the fixed point), the particle's own ID
+ * for other types, garbage and swallowed particles.  ids and minid_out are host arrays of n entries; *ngroups_out
+ * (may be NULL) = number of groups holding a primary particle.  BoxSize / linking_length up to 1024 grid cells a side
+ * are used; a linking length above a third of the box is examined pair by pair (at most 65536 primary particles). */
+int b200_fof_primary(b200_ctx *ctx, const int64_t *ids, int primary_mask, double BoxSize, double linking_length,
+                     int64_t *minid_out, int64_t *ngroups_out);
+
 /* Device-side timing of the phases of the last call, milliseconds (CUDA
  * events on the engine's stream).  Names follow the reference's walltime
  * categories (libgadget/walltime.c, gravshort-tree.c:134-144, petapm.c:280-355). */

@@ -120,6 +120,7 @@ EXPORTED = [
     "b200_domain_peano_keys", "b200_domain_set_topnodes", "b200_domain_topleaf", "b200_domain_leaf_counts", "b200_domain_assign_balanced", "b200_domain_exchange_plan",
     "b200_domain_sample_keys", "b200_domain_toptree_local", "b200_domain_toptree_truncate", "b200_domain_toptree_merge",
     "b200_domain_toptree_global_refine", "b200_domain_toptree_leaves",
+    "b200_fof_primary",
 ]
 
 
@@ -239,6 +240,15 @@ class Engine:
     def gravpm_force_dev(self, gravpm_ptr=None, pot_ptr=None):
         self._ck(self.L.b200_pm_force_dev(self.ctx, C.c_void_p(gravpm_ptr) if gravpm_ptr else None,
                                           C.c_void_p(pot_ptr) if pot_ptr else None))
+
+    def fof_primary(self, ids, box, ll, mask=2):
+        """fof_label_primary (fof.c:366-470) for the particles set: (MinID of every particle, number of groups)."""
+        ids = _c(ids, np.int64)
+        assert len(ids) == self.n
+        out = np.empty(self.n, np.int64)
+        ng = C.c_int64(0)
+        self._ck(self.L.b200_fof_primary(self.ctx, _p(ids), C.c_int(mask), C.c_double(box), C.c_double(ll), _p(out), C.byref(ng)))
+        return out, int(ng.value)
 
     def pm_transform_kind(self):
         """1: the engine's own shared-memory transform passes (csrc/pm_fft.cu); 0: cuFFT; -1: no mesh."""

@@ -250,7 +250,7 @@ void b200_ctx_destroy(b200_ctx *ctx)
     E->nodeF.release(); E->nodeH.release(); E->nodeK.release(); E->scratch_i.release(); E->targets.release(); E->targets_sorted.release(); E->walk_flags.release();
     E->d_acc.release(); E->d_pot.release(); E->d_counts.release(); E->srtab.release();
     E->walk_pool.release(); E->walk_chunktab.release(); E->walk_cnt.release(); E->walk_partial.release();
-    step_release(E); domain_release(E);
+    step_release(E); domain_release(E); fof_release(E);
     // the SPH state and scratch (grow-only buffers have no destructor: everything is released here)
     E->s_vel.release(); E->s_hsml.release(); E->s_entropy.release(); E->s_dtentropy.release(); E->s_fullacc.release(); E->s_gravpm.release();
     E->s_hydroacc.release(); E->s_velpred.release(); E->s_evp.release(); E->s_density.release(); E->s_egy.release(); E->s_dhsmlfac.release();
@@ -375,6 +375,13 @@ static int pm_force_common(Engine *E, double *gravpm_out, double *potential_out,
 
 int b200_pm_force(b200_ctx *ctx, double *gravpm_out, double *potential_out) { ENTER(ctx); return pm_force_common(E, gravpm_out, potential_out, true); }
 int b200_pm_force_dev(b200_ctx *ctx, double *gravpm_out, double *potential_out) { ENTER(ctx); return pm_force_common(E, gravpm_out, potential_out, false); }
+
+int b200_fof_primary(b200_ctx *ctx, const int64_t *ids, int primary_mask, double BoxSize, double linking_length,
+                     int64_t *minid_out, int64_t *ngroups_out)
+{
+    ENTER(ctx);
+    return fof_primary(E, ids, primary_mask, BoxSize, linking_length, minid_out, ngroups_out);
+}
 
 int b200_pm_transform_kind(b200_ctx *ctx)
 {

@@ -184,6 +184,13 @@ struct Engine {
     DevBuf<int> b_top;                                 // tree build below the domain's top nodes: top node | curve state << 24 per cell
     int64_t dk_keys_n = -1, dk_topleaf_n = -1;
 
+    // ---- friends-of-friends (fof.cu) ----
+    DevBuf<unsigned> fof_key, fof_key_alt;             // grid cell of every primary particle, unsorted / sorted
+    DevBuf<int> fof_val, fof_val_alt, fof_parent, fof_root;
+    DevBuf<double> fof_spos;                           // positions in cell order
+    DevBuf<long long> fof_ids, fof_out;
+    DevBuf<unsigned long long> fof_min;
+
     Timer timers[T_COUNT];
     b200_timings last = {};
 };
@@ -252,6 +259,10 @@ int sph_set_state(Engine *E, const double *density, const double *egy, const dou
 void step_release(Engine *E);
 void domain_release(Engine *E);
 int domain_need_tables(Engine *E);    // domain_keys.cu: the curve's state machine in dk_tab
+
+// friends-of-friends (fof.cu)
+int fof_primary(Engine *E, const int64_t *ids, int mask, double Box, double ll, int64_t *minid_out, int64_t *ngroups_out);
+void fof_release(Engine *E);
 
 // walk (tree_walk.cu)
 int walk_init_tables(Engine *E);

@@ -130,3 +130,34 @@ def fof_cases():
         typ = np.ones(n, np.uint8); typ[::7] = 0; typ[-2:] = 1
         out.append((pos, ids, typ, box, ll))
     return out
+
+
+def fof_edge_cases():
+    """(pos, ids, type, box, ll, mask, flags): a box so small that the grid has one cell (ll above a third of the box); two
+    link types; garbage and swallowed particles among the primaries; a linking length that joins everything; one that joins
+    nothing; groups along every face and corner of the box; a single particle."""
+    out = []
+    rng = np.random.default_rng(11)
+    n = 300
+    pos = rng.random((n, 3)) * 1.0
+    ids = rng.permutation(n).astype(np.int64) + 1
+    out.append((pos, ids, np.ones(n, np.uint8), 1.0, 0.4, 2, None))                       # nc < 3: every pair examined
+    n = 3000; box = 50.0
+    pos = rng.random((n, 3)) * box
+    typ = rng.integers(0, 6, n).astype(np.uint8)
+    ids = rng.permutation(n).astype(np.int64) + 5
+    ll = 0.6 * box / n ** (1 / 3)
+    out.append((pos, ids, typ, box, ll, (1 << 1) | (1 << 4), None))                       # dark matter and stars link
+    flags = np.zeros(n, np.uint8); flags[::5] = 1; flags[3::11] = 2
+    out.append((pos, ids, np.ones(n, np.uint8), box, ll, 2, flags))                       # garbage / swallowed take no part
+    out.append((pos[:500], ids[:500], np.ones(500, np.uint8), box, 0.34 * box, 2, None))  # one cell again, everything joins
+    out.append((pos, ids, np.ones(n, np.uint8), box, 1e-6, 2, None))                      # nothing joins (1024-cell cap)
+    m = 12
+    g = (np.arange(m) + 0.5) / m * box
+    face = np.array([[x, y, z] for x in (0.01, box - 0.01) for y in g for z in g] + [[x, y, z] for y in (0.02, box - 0.02) for x in g for z in g]
+                    + [[x, y, z] for z in (0.0, box - 0.03) for x in g for y in g])
+    face = face + 0.3 * rng.standard_normal(face.shape)
+    face = np.mod(face, box)
+    out.append((face, rng.permutation(len(face)).astype(np.int64), np.ones(len(face), np.uint8), box, 1.2, 2, None))   # groups across faces, edges, corners
+    out.append((np.array([[1.0, 2.0, 3.0]]), np.array([42], np.int64), np.ones(1, np.uint8), box, 1.0, 2, None))
+    return out

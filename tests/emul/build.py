@@ -115,3 +115,27 @@ def build_fft(force=False):
                           ["-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-o", FFT_SO, gen, drv] + inc +
                           (["-DFFT_T=" + os.environ["EMUL_FFT_T"]] if os.environ.get("EMUL_FFT_T") else []))
     return FFT_SO
+
+
+FOF_SO = os.path.join(OUT, "libfof_emul.so")
+
+
+def build_fof(force=False):
+    """mp-gadget_b200/csrc/fof.cu (kernels and host driver unchanged) for the host, driven by tests/emul/fof_driver.cpp."""
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(ROOT, "mp-gadget_b200", "csrc", "fof.cu")
+    drv = os.path.join(HERE, "fof_driver.cpp")
+    deps = [src, drv, os.path.join(HERE, "include", "cuda_runtime.h"), os.path.join(HERE, "include", "cub", "cub.cuh"),
+            os.path.join(ROOT, "mp-gadget_b200", "csrc", "engine.h"), __file__]
+    if not force and os.path.exists(FOF_SO) and all(os.path.getmtime(d) <= os.path.getmtime(FOF_SO) for d in deps):
+        return FOF_SO
+    text, n = rewrite_launches(open(src).read())
+    assert n >= 7, n
+    gen = os.path.join(OUT, "fof_emul.cpp")
+    with open(gen, "w") as f:
+        f.write("// GENERATED from mp-gadget_b200/csrc/fof.cu by tests/emul/build.py -- do not edit\n" + text)
+    inc = ["-I", os.path.join(HERE, "include"), "-I", os.path.join(ROOT, "mp-gadget_b200", "csrc")]
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-ffp-contract=off"] +
+                          (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if ASAN else []) +
+                          ["-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-o", FOF_SO, gen, drv] + inc)
+    return FOF_SO

@@ -71,6 +71,12 @@ static inline double atomicAdd(double *p, double v)
 static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long) v); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicCAS(int *p, int expected, int desired)
+{
+    __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return expected;          /* the value found, as CUDA returns it */
+}
+template <class T> static inline T __ldcg(const T *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v)
 {
     unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
