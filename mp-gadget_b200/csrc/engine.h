@@ -185,7 +185,7 @@ struct Engine {
     int64_t dk_keys_n = -1, dk_topleaf_n = -1;
 
     // ---- friends-of-friends (fof.cu) ----
-    DevBuf<unsigned> fof_key, fof_key_alt;             // grid cell of every primary particle, unsorted / sorted
+    DevBuf<unsigned long long> fof_key, fof_key_alt;   // grid cell of every primary particle, sorted / unsorted
     DevBuf<int> fof_val, fof_val_alt, fof_parent, fof_root;
     DevBuf<double> fof_spos;                           // positions in cell order
     DevBuf<long long> fof_ids, fof_out;

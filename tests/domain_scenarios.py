@@ -160,4 +160,12 @@ def fof_edge_cases():
     face = np.mod(face, box)
     out.append((face, rng.permutation(len(face)).astype(np.int64), np.ones(len(face), np.uint8), box, 1.2, 2, None))   # groups across faces, edges, corners
     out.append((np.array([[1.0, 2.0, 3.0]]), np.array([42], np.int64), np.ones(1, np.uint8), box, 1.0, 2, None))
+    # a clump far denser than the linking length (hundreds of particles per grid cell) over a corner of the box, a thin
+    # filament leaving it, and background particles: the clique cells' early exits and whole-cell hooks
+    nd = 4000
+    clump = np.mod(0.4 * rng.standard_normal((nd, 3)), box)
+    fil = np.stack([np.linspace(1.0, 20.0, 400), np.full(400, 0.2), np.full(400, box - 0.2)], axis=1) + 0.02 * rng.standard_normal((400, 3))
+    bg = rng.random((1500, 3)) * box
+    pts = np.mod(np.concatenate([clump, fil, bg]), box)
+    out.append((pts, rng.permutation(len(pts)).astype(np.int64) + 3, np.ones(len(pts), np.uint8), box, 0.3, 2, None))
     return out

@@ -29,16 +29,18 @@ def run(L, pos, ids, typ, box, ll, mask=2, flags=None):
 def main():
     L = C.CDLL(EB.build_fof())
     G = np.load(os.path.join(ROOT, "tests", "golden", "ref_fof.npz"))
-    for k, (pos, ids, typ, box, ll) in enumerate(DS.fof_cases()):
-        got, ng = run(L, pos, ids, typ, box, ll)
-        assert np.array_equal(got, G["%d/minid" % k]), k
-        assert ng == len(np.unique(got[typ == 1])), (ng, k)
-    for pos, ids, typ, box, ll, mask, flags in DS.fof_edge_cases():
-        got, ng = run(L, pos, ids, typ, box, ll, mask, flags)
-        keep = np.ones(len(ids), bool) if flags is None else (flags & 3) == 0
-        want = ids.copy()
-        want[keep] = oracle.fof_primary(pos[keep], ids[keep], typ[keep], box, ll, mask=mask)
-        assert np.array_equal(got, want), (box, ll, mask)
+    for mode in ("clique", "cells"):             # the clique-cell search (default where the grid allows) and the plain cell list
+        os.environ["B200_FOF"] = mode
+        for k, (pos, ids, typ, box, ll) in enumerate(DS.fof_cases()):
+            got, ng = run(L, pos, ids, typ, box, ll)
+            assert np.array_equal(got, G["%d/minid" % k]), (mode, k)
+            assert ng == len(np.unique(got[typ == 1])), (mode, ng, k)
+        for pos, ids, typ, box, ll, mask, flags in DS.fof_edge_cases():
+            got, ng = run(L, pos, ids, typ, box, ll, mask, flags)
+            keep = np.ones(len(ids), bool) if flags is None else (flags & 3) == 0
+            want = ids.copy()
+            want[keep] = oracle.fof_primary(pos[keep], ids[keep], typ[keep], box, ll, mask=mask)
+            assert np.array_equal(got, want), (mode, box, ll, mask)
     print("fof ok")
 
 

@@ -66,20 +66,23 @@ def test_fof_emulation_under_address_sanitizer():
 
 
 @pytest.mark.gpu
-def test_gpu_fof_primary_equals_reference(engine):
+def test_gpu_fof_primary_equals_reference(engine, monkeypatch):
     """b200_fof_primary on the device: the reference's golden labels, the oracle on the edge cases, and a 200 000-particle
     clustered box (long chains of hooks, many threads per group) against the oracle."""
-    for k, (pos, ids, typ, box, ll) in enumerate(DS.fof_cases()):
-        engine.set_particles(pos, np.ones(len(ids), np.float32), type=typ)
-        got, ng = engine.fof_primary(ids, box, ll)
-        assert np.array_equal(got, GOLD["%d/minid" % k]), k
-        assert ng == len(np.unique(got[typ == 1]))
-    for pos, ids, typ, box, ll, mask, flags in DS.fof_edge_cases():
-        if flags is not None:
-            continue                       # the SoA entry point takes no garbage flags; covered under emulation
-        engine.set_particles(pos, np.ones(len(ids), np.float32), type=typ)
-        got, _ = engine.fof_primary(ids, box, ll, mask=mask)
-        assert np.array_equal(got, oracle.fof_primary(pos, ids, typ, box, ll, mask=mask)), (box, ll, mask)
+    for mode in ("clique", "cells"):      # the clique-cell search (default where the grid allows it) and the plain cell list
+        monkeypatch.setenv("B200_FOF", mode)
+        for k, (pos, ids, typ, box, ll) in enumerate(DS.fof_cases()):
+            engine.set_particles(pos, np.ones(len(ids), np.float32), type=typ)
+            got, ng = engine.fof_primary(ids, box, ll)
+            assert np.array_equal(got, GOLD["%d/minid" % k]), (mode, k)
+            assert ng == len(np.unique(got[typ == 1]))
+        for pos, ids, typ, box, ll, mask, flags in DS.fof_edge_cases():
+            if flags is not None:
+                continue                       # the SoA entry point takes no garbage flags; covered under emulation
+            engine.set_particles(pos, np.ones(len(ids), np.float32), type=typ)
+            got, _ = engine.fof_primary(ids, box, ll, mask=mask)
+            assert np.array_equal(got, oracle.fof_primary(pos, ids, typ, box, ll, mask=mask)), (mode, box, ll, mask)
+    monkeypatch.delenv("B200_FOF")
     rng = np.random.default_rng(5)
     n, box = 200000, 100.0
     centres = rng.random((40, 3)) * box
