@@ -115,6 +115,26 @@ int b200_pm_force_dev(b200_ctx *ctx, double *gravpm_out, double *potential_out);
  * x pass (mesh sizes 2^a 3^b 5^c up to 1614), 0 = cuFFT D2Z / Z2D around a separate Green's-function kernel
  * (other sizes, or B200_PM_FFT=cufft in the environment at b200_pm_init), -1 = no mesh. */
 int b200_pm_transform_kind(b200_ctx *ctx);
+/* The generic inverse pass of the PM engine: petapm_force_c2r (libgadget/petapm.c:326-362) for
+ * callers that bring their own source spectrum and transfer functions -- MP-GenIC's displacement_fields
+ * (libgenic/zeldovich.c:150-253: Density, DispX/Y/Z, VelX/Y/Z) and the radius filters of petapm_reion_c2r
+ * (petapm.c:416-577).  For every function j: spectrum_j = transfer_j(rho_k) (pm_apply_transfer_function,
+ * petapm.c:1092-1132), C2R (unnormalised, like pfft's backward plan), out_j[i] = sum over the 8 CIC cells of particle i
+ * of weight * mesh (the readout_* callbacks, zeldovich.c:338-359; particles = the set given to b200_set_particles_*).
+ * rho_k: host, complex [Nmesh][Nmesh][Nmesh/2+1], x slowest (the reference keeps the same modes in PFFT's transposed
+ * [y][z][x] order).  A transfer function is radial in the INTEGER wave number: table[k2], k2 = kx^2 + ky^2 + kz^2 in
+ * [0, 3 (Nmesh/2)^2], filled by the caller with the reference's own formula -- density_transfer:
+ * exp(-k2 / Nmesh^2) DeltaSpec(k) / sqrt(L^3) (zeldovich.c:276-289); disp_transfer: DeltaSpec(k) or dlogGrowth(k) times
+ * 1 / (2 pi sqrt(L) k2) (:291-313) -- so the device applies exactly the factor the host function would.
+ *   kind 0:        value *= table[k2]
+ *   kind 1, 2, 3:  fac = table[k2] * k_axis (x, y, z);  (re, im) <- (-im fac, re fac)        (disp_transfer's swap)
+ * The k2 = 0 mode passes unchanged (`if(k2)`).  Needs the engine's own transform passes (b200_pm_transform_kind == 1). */
+typedef struct b200_pm_function {
+    int kind;
+    const double *table;      /* host, 3 (Nmesh/2)^2 + 1 entries */
+    double *out;              /* host, n entries */
+} b200_pm_function;
+int b200_pm_c2r_readout(b200_ctx *ctx, const double *rho_k, int nfunc, const b200_pm_function *functions);
 /* Matter power spectrum side effect of gravpm_force: potential_transfer calls
  * powerspectrum_add_mode on every density mode before scaling it
  * (gravpm.c:330-361,440).  b200_pm_set_power(ctx, 1) makes the next b200_pm_force

@@ -108,7 +108,7 @@ EXPORTED = [
     "b200_default_particle_layout", "b200_ctx_create", "b200_ctx_destroy", "b200_last_error",
     "b200_abi_version", "b200_kernel_launches", "b200_set_particles_aos", "b200_set_particles_soa",
     "b200_set_particles_soa_dev", "b200_oldacc_from_last_step", "b200_pm_init", "b200_walk_set_mesh", "b200_pm_force",
-    "b200_pm_force_dev", "b200_pm_transform_kind", "b200_pm_set_power", "b200_pm_get_power", "b200_pm_cell_index", "b200_pm_copy_mesh", "b200_tree_build", "b200_tree_free",
+    "b200_pm_force_dev", "b200_pm_c2r_readout", "b200_pm_transform_kind", "b200_pm_set_power", "b200_pm_get_power", "b200_pm_cell_index", "b200_pm_copy_mesh", "b200_tree_build", "b200_tree_free",
     "b200_tree_export", "b200_grav_short_tree", "b200_grav_short_tree_dev", "b200_force_step_aos", "b200_force_step_aos_bytes", "b200_force_step_dev",
     "b200_get_timings", "b200_stream",
     "b200_tree_top_get_dev", "b200_tree_top_set_dev",
@@ -249,6 +249,25 @@ class Engine:
         ng = C.c_int64(0)
         self._ck(self.L.b200_fof_primary(self.ctx, _p(ids), C.c_int(mask), C.c_double(box), C.c_double(ll), _p(out), C.byref(ng)))
         return out, int(ng.value)
+
+    def pm_c2r_readout(self, rho_k, functions):
+        """petapm_force_c2r (petapm.c:326-362) with a caller's spectrum: rho_k complex [Nmesh, Nmesh, Nmesh/2+1]; functions =
+        [(kind, table[k2]), ...] -> one array of n read-outs per function."""
+        N = self.nmesh
+        rk = _c(np.asarray(rho_k, np.complex128), np.complex128)
+        assert rk.shape == (N, N, N // 2 + 1)
+
+        class F(C.Structure):
+            _fields_ = [("kind", C.c_int), ("table", C.c_void_p), ("out", C.c_void_p)]
+        nk2 = 3 * (N // 2) ** 2 + 1
+        tabs = [_c(t, np.float64) for _, t in functions]
+        assert all(len(t) == nk2 for t in tabs)
+        outs = [np.zeros(max(self.n, 1)) for _ in functions]
+        arr = (F * max(len(functions), 1))()
+        for j, (kind, _) in enumerate(functions):
+            arr[j].kind = int(kind); arr[j].table = tabs[j].ctypes.data; arr[j].out = outs[j].ctypes.data
+        self._ck(self.L.b200_pm_c2r_readout(self.ctx, C.c_void_p(rk.ctypes.data), C.c_int(len(functions)), arr))
+        return [o[:self.n] for o in outs]
 
     def pm_transform_kind(self):
         """1: the engine's own shared-memory transform passes (csrc/pm_fft.cu); 0: cuFFT; -1: no mesh."""

@@ -383,6 +383,13 @@ int b200_fof_primary(b200_ctx *ctx, const int64_t *ids, int primary_mask, double
     return fof_primary(E, ids, primary_mask, BoxSize, linking_length, minid_out, ngroups_out);
 }
 
+int b200_pm_c2r_readout(b200_ctx *ctx, const double *rho_k, int nfunc, const b200_pm_function *functions)
+{
+    ENTER(ctx);
+    if(E->Nmesh == 0) return failmsg(E, "b200_pm_c2r_readout: call b200_pm_init first");
+    return pmfft_c2r_readout(E, rho_k, nfunc, functions);
+}
+
 int b200_pm_transform_kind(b200_ctx *ctx)
 {
     if(!ctx) return -1;

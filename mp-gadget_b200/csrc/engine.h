@@ -87,6 +87,7 @@ struct Engine {
     DevBuf<uint8_t> fftwork;
     OwnFFT *ownfft = nullptr;  // pm_fft.cu: the shared-memory transform passes (null: cuFFT plans above)
     DevBuf<double> fft_tab;    // its twiddle and row-order tables
+    DevBuf<double> pm_rhok, pm_table;   // b200_pm_c2r_readout: the caller's source spectrum (padded row pitch), one transfer table
     bool potential_valid = false;
     bool pm_fused = true;      // difference + readout in one kernel, no force meshes (B200_PM_FUSED=0: separate passes)
     bool fmesh_valid = false;
@@ -219,6 +220,7 @@ int pmfft_init(Engine *E, int N);
 void pmfft_destroy(Engine *E);
 size_t pmfft_cplx_doubles(const Engine *E);
 int pmfft_potential(Engine *E, double asmth2, double pot_factor, double binsperunit, double *ps);
+int pmfft_c2r_readout(Engine *E, const double *rho_k, int nfunc, const b200_pm_function *f);
 
 // tree (tree_build.cu)
 int tree_build(Engine *E, double Box, int mask, const int32_t *d_active, int64_t nactive,

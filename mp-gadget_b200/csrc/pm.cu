@@ -286,6 +286,7 @@ void pm_destroy(Engine *E)
         E->plans = false;
     }
     pmfft_destroy(E);
+    E->pm_rhok.release(); E->pm_table.release();
     E->mesh.release(); E->cplx.release(); E->fmesh.release(); E->ktab.release(); E->fftwork.release();
     E->Nmesh = 0;
 }

@@ -648,4 +648,110 @@ int pmfft_potential(Engine *E, double asmth2, double pot_factor, double binsperu
     return 0;
 }
 
+// ---- the generic inverse pass: petapm_force_c2r (petapm.c:326-362) for callers that bring their own source spectrum and
+// transfer functions (MP-GenIC's displacement_fields, libgenic/zeldovich.c:150-253; the radius filters of petapm_reion_c2r,
+// petapm.c:416-577).  A transfer function is radial in the integer wave number, table[k2], filled by the caller with the
+// reference's own formula, so the device applies exactly the factor the host function would.
+//   kind 0 (density_transfer, zeldovich.c:276-289):  value *= table[k2]
+//   kind a = 1, 2, 3 (disp_transfer, :291-313, axis x, y, z): fac = table[k2] * k_axis;  (re, im) <- (-im fac, re fac)
+// The k2 = 0 mode passes unchanged (the reference's `if(k2)`); pm_apply_transfer_function copies src to dst first
+// (petapm.c:1126-1130).
+__global__ void __launch_bounds__(256)
+k_pm_apply_radial(const double2 *__restrict__ src, double2 *__restrict__ dst, int N, int Nz, int Nzp, int kind, const double *__restrict__ table)
+{
+    const size_t total = (size_t) N * N * Nzp;
+    for(size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t) gridDim.x * blockDim.x) {
+        const int iz = (int) (idx % Nzp);
+        const size_t row = idx / Nzp;
+        const int iy = (int) (row % N), ix = (int) (row / N);
+        double2 v = make_double2(0.0, 0.0);
+        if(iz < Nz) {
+            v = src[idx];
+            const int kx = ix <= N / 2 ? ix : ix - N, ky = iy <= N / 2 ? iy : iy - N, kz = iz;       // petapm_mesh_to_k petapm.c:81-84
+            const long long k2 = (long long) kx * kx + (long long) ky * ky + (long long) kz * kz;
+            if(k2) {
+                if(kind == 0) { const double fac = table[k2]; v.x *= fac; v.y *= fac; }
+                else {
+                    const double fac = table[k2] * (kind == 1 ? kx : (kind == 2 ? ky : kz));
+                    const double tmp = v.x;
+                    v.x = -v.y * fac; v.y = tmp * fac;
+                }
+            }
+        }
+        dst[idx] = v;
+    }
+}
+
+// readout_* of the caller (zeldovich.c:338-359): out[i] = sum over the 8 CIC cells of weight * mesh, weights and cell
+// order of pm_iterate_one (petapm.c:955-1006)
+__global__ void __launch_bounds__(256)
+k_pm_readout_field(const double *__restrict__ pos, const uint8_t *__restrict__ flags, int64_t n, double cellsize, int N,
+                   const double *__restrict__ mesh, double *__restrict__ out)
+{
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    double acc = 0;
+    if(!(flags[i] & 3)) {
+        int ic[3]; double res[3];
+#pragma unroll
+        for(int k = 0; k < 3; k++) {
+            const double t = pos[3 * i + k] / cellsize;
+            const double f = floor(t);
+            ic[k] = (int) f; res[k] = t - f;
+        }
+        int c0[3], c1[3];
+#pragma unroll
+        for(int k = 0; k < 3; k++) { c0[k] = ((ic[k] % N) + N) % N; c1[k] = (((ic[k] + 1) % N) + N) % N; }
+        const double wx[2] = {1 - res[0], res[0]}, wy[2] = {1 - res[1], res[1]}, wz[2] = {1 - res[2], res[2]};
+#pragma unroll
+        for(int c = 0; c < 8; c++) {
+            const int ox = c & 1, oy = (c >> 1) & 1, oz = (c >> 2) & 1;
+            const double w = (wx[ox] * wy[oy]) * wz[oz];
+            const size_t lin = ((size_t) (ox ? c1[0] : c0[0]) * N + (oy ? c1[1] : c0[1])) * N + (oz ? c1[2] : c0[2]);
+            acc += w * mesh[lin];
+        }
+    }
+    out[i] = acc;
+}
+
+// rho_k: host, complex [N][N][N/2+1] (x slowest).  For every function: transfer, inverse transform (the mirror passes of
+// pmfft_potential: x, y, z), readout into f[j].out (host, n doubles).  E->mesh and E->cplx are overwritten.
+int pmfft_c2r_readout(Engine *E, const double *rho_k, int nfunc, const b200_pm_function *f)
+{
+    OwnFFT *F = E->ownfft;
+    if(!F) return failmsg(E, "b200_pm_c2r_readout: needs the engine's own transform passes (mesh size 2^a 3^b 5^c, b200_pm_init without B200_PM_FFT=cufft)");
+    if(!rho_k || nfunc < 0 || (nfunc > 0 && !f)) return failmsg(E, "b200_pm_c2r_readout: null argument");
+    const int N = F->N, Nz = N / 2 + 1, Nzp = F->Nzp, ntile = Nzp / FFT_T, th = F->threads;
+    const long long nlines = (long long) N * N;
+    const unsigned zblocks = (unsigned) ((nlines + FFT_T - 1) / FFT_T), cblocks = (unsigned) N * ntile;
+    const size_t nk2 = 3 * (size_t) (N / 2) * (N / 2) + 1;
+    const size_t n = (size_t) (E->n > 0 ? E->n : 1);
+    CK(E->pm_rhok.ensure(2 * (size_t) N * N * Nzp));
+    CK(E->pm_table.ensure(nk2));
+    CK(E->d_pot.ensure(n));
+    CK(cudaMemcpy2DAsync(E->pm_rhok.p, (size_t) Nzp * 16, rho_k, (size_t) Nz * 16, (size_t) Nz * 16, (size_t) nlines, cudaMemcpyHostToDevice, E->stream));
+    GreenArgs G = {N, Nz, E->ktab.p, 0.0, 0.0, 0.0, nullptr};
+    double2 *c = (double2 *) E->cplx.p;
+    for(int j = 0; j < nfunc; j++) {
+        if(f[j].kind < 0 || f[j].kind > 3 || !f[j].table || (E->n > 0 && !f[j].out)) return failmsg(E, "b200_pm_c2r_readout: bad function entry");
+        CK(cudaMemcpyAsync(E->pm_table.p, f[j].table, nk2 * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+        k_pm_apply_radial<<<148 * 16, 256, 0, E->stream>>>((const double2 *) E->pm_rhok.p, c, N, Nz, Nzp, f[j].kind, E->pm_table.p);
+        CKL(E);
+        k_fft_columns<1><<<cblocks, th, F->smemN, E->stream>>>(c, ntile, (size_t) Nzp, (size_t) N * Nzp, F->pN, G);          // x
+        CKL(E);
+        k_fft_columns<1><<<cblocks, th, F->smemN, E->stream>>>(c, ntile, (size_t) N * Nzp, (size_t) Nzp, F->pN, G);          // y
+        CKL(E);
+        k_fft_z_inverse<<<zblocks, th, F->smemH, E->stream>>>(c, E->mesh.p, nlines, Nzp, F->pH, F->wN);
+        CKL(E);
+        if(E->n > 0) {
+            k_pm_readout_field<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->pos.p, E->flags.p, E->n, E->Box / N, N, E->mesh.p, E->d_pot.p);
+            CKL(E);
+            CK(cudaMemcpyAsync(f[j].out, E->d_pot.p, (size_t) E->n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
+        }
+        CK(cudaStreamSynchronize(E->stream));          // the table buffer is reused by the next function
+    }
+    E->potential_valid = false;
+    return 0;
+}
+
 } // namespace b200

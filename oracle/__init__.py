@@ -258,6 +258,36 @@ def pm_force(pos, mass, box, nmesh, asmth, G, workers=-1, return_mesh=False):
     return res
 
 
+def pm_c2r_readout(pos, box, nmesh, rho_k, functions, workers=-1):
+    """petapm_force_c2r (petapm.c:326-362) restated for a caller's spectrum: for every (kind, table) the transfer of
+    pm_apply_transfer_function (petapm.c:1092-1132) in the forms of libgenic/zeldovich.c:276-313 -- kind 0: value *= table[k2];
+    kind 1..3: fac = table[k2] * k_axis, (re, im) <- (-im fac, re fac); k2 = 0 unchanged --, the unnormalised inverse
+    transform and the CIC read-out of oracle_pm_readout.  rho_k: complex [nmesh, nmesh, nmesh//2+1], x slowest."""
+    import scipy.fft as sfft
+    pos = _c(pos, np.float64)
+    n = len(pos)
+    N = nmesh
+    k = np.arange(N)
+    k = np.where(k <= N // 2, k, k - N)
+    kx, ky, kz = k[:, None, None], k[None, :, None], np.arange(N // 2 + 1)[None, None, :]
+    k2 = kx * kx + ky * ky + kz * kz
+    L = lib()
+    outs = []
+    for kind, table in functions:
+        table = np.asarray(table, np.float64)
+        fac = table[k2]
+        if kind == 0:
+            fk = np.where(k2 > 0, rho_k * fac, rho_k)
+        else:
+            fac = fac * (kx, ky, kz)[kind - 1]
+            fk = np.where(k2 > 0, (-rho_k.imag * fac) + 1j * (rho_k.real * fac), rho_k)
+        real = np.ascontiguousarray(sfft.irfftn(np.ascontiguousarray(fk), s=(N,) * 3, workers=workers, norm="forward"))
+        out = np.zeros(n)
+        L.oracle_pm_readout(_p(real), _p(pos), C.c_int64(n), C.c_double(box), C.c_int(N), out.ctypes.data_as(C.c_void_p), C.c_int64(1))
+        outs.append(out)
+    return outs
+
+
 def direct_sum(pos, mass, box, G, softening_h, repeat=1):
     pos = _c(pos, np.float64)
     mass = _c(mass, np.float32)

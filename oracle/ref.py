@@ -138,6 +138,24 @@ class Ref:
                                 C.c_char_p(outdir.encode()), C.c_double(time), _p(g), _p(p))
         return g, p
 
+    def petapm_c2r(self, pos, box, nmesh, rho_k, functions):
+        """petapm_force_init + petapm_force_c2r + petapm_force_finish of the reference (petapm.c:263-362) driven as
+        libgenic/zeldovich.c:150-229 drives them, on a given spectrum rho_k[nmesh, nmesh, nmesh//2+1] (x slowest) with
+        table-driven transfers [(kind, table[k2]), ...] -> one read-out array per function (needs so=SO_PM)."""
+        pos = np.ascontiguousarray(pos, np.float64)
+        n = len(pos)
+        rk = np.ascontiguousarray(np.asarray(rho_k, np.complex128))
+        assert rk.shape == (nmesh, nmesh, nmesh // 2 + 1)
+        nk2 = 3 * (nmesh // 2) ** 2 + 1
+        kinds = np.array([k for k, _ in functions], np.int32)
+        tabs = np.ascontiguousarray(np.stack([np.asarray(t, np.float64) for _, t in functions]))
+        assert tabs.shape == (len(functions), nk2)
+        out = np.zeros((len(functions), n))
+        rc = self.L.ref_petapm_c2r(C.c_int64(n), _p(pos), C.c_double(box), C.c_int(nmesh), C.c_void_p(rk.ctypes.data), C.c_int(len(functions)),
+                                   _p(kinds), _p(tabs), C.c_int64(nk2), _p(out))
+        assert rc == 0
+        return [out[j] for j in range(len(functions))]
+
     def peano_keys(self, pos, box):
         pos = np.ascontiguousarray(pos, np.float64); keys = np.zeros(len(pos), np.uint64)
         self.L.ref_peano_keys(C.c_int64(len(pos)), _p(pos), C.c_double(box), _p(keys))

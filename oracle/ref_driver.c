@@ -546,6 +546,107 @@ int ref_gravpm_force(int64_t n, const double *pos, const float *mass, double Box
 #endif
     return 0;
 }
+
+#ifndef REF_PM_SHIM
+/* petapm_force_init + petapm_force_c2r + petapm_force_finish (petapm.c:263-362) driven the way MP-GenIC's
+ * displacement_fields drives them (libgenic/zeldovich.c:150-229): one region round the particles (makeregion, :113-143), a
+ * source spectrum handed in instead of gaussian_fill, up to 8 functions whose transfers have the forms of density_transfer /
+ * disp_transfer (:276-313) with the k-dependent factor read from a table by the integer k2, and readouts that add
+ * weight * mesh into out[f][i] (:338-359).  rho_k comes in natural [x][y][kz] order and is placed into the reference's
+ * transposed Fourier region through its own offsets and strides (petapm.c:1092-1125: region axes are y, z, x). */
+#define C2R_MAXF 8
+static const double *c2r_table[C2R_MAXF];
+static int c2r_kind[C2R_MAXF];
+static double *c2r_out[C2R_MAXF];
+static void c2r_transfer(int f, int64_t k2, int kpos[3], pfft_complex *value)
+{
+    if(k2) {
+        if(c2r_kind[f] == 0) {
+            const double fac = c2r_table[f][k2];
+            value[0][0] *= fac;
+            value[0][1] *= fac;
+        } else {
+            const double fac = c2r_table[f][k2] * kpos[c2r_kind[f] - 1];
+            const double tmp = value[0][0];
+            value[0][0] = -value[0][1] * fac;
+            value[0][1] = tmp * fac;
+        }
+    }
+}
+#define C2R_FN(f) static void c2r_transfer_##f(PetaPM *pm, int64_t k2, int kpos[3], pfft_complex *value) { c2r_transfer(f, k2, kpos, value); } \
+                  static void c2r_readout_##f(PetaPM *pm, int i, double *mesh, double weight) { c2r_out[f][i] += weight * mesh[0]; }
+C2R_FN(0) C2R_FN(1) C2R_FN(2) C2R_FN(3) C2R_FN(4) C2R_FN(5) C2R_FN(6) C2R_FN(7)
+static PetaPMRegion *c2r_makeregion(PetaPM *pm, PetaPMParticleStruct *pstruct, void *userdata, int *Nregions)
+{
+    PetaPMRegion *regions = (PetaPMRegion *) mymalloc2("Regions", sizeof(PetaPMRegion));
+    double min[3] = {pm->BoxSize, pm->BoxSize, pm->BoxSize}, max[3] = {0, 0, 0};
+    for(int64_t i = 0; i < PartManager->NumPart; i++)
+        for(int k = 0; k < 3; k++) {
+            if(min[k] > P[i].Pos[k]) min[k] = P[i].Pos[k];
+            if(max[k] < P[i].Pos[k]) max[k] = P[i].Pos[k];
+        }
+    for(int k = 0; k < 3; k++) {
+        regions[0].offset[k] = floor(min[k] / pm->BoxSize * pm->Nmesh - 1);
+        regions[0].size[k] = ceil(max[k] / pm->BoxSize * pm->Nmesh + 2);
+        regions[0].size[k] -= regions[0].offset[k];
+    }
+    petapm_region_init_strides(&regions[0]);
+    *Nregions = 1;
+    return regions;
+}
+int ref_petapm_c2r(int64_t n, const double *pos, double BoxSize, int Nmesh, const double *rho_k, int nfunc, const int *kind,
+                   const double *tables, int64_t nk2, double *out)
+{
+    if(nfunc > C2R_MAXF) return 1;
+    free_all();
+    particle_alloc_memory(PartManager, BoxSize, n);
+    have_particles = 1;
+    PartManager->NumPart = n;
+    for(int64_t i = 0; i < n; i++) {
+        memset(&P[i], 0, sizeof(P[i]));
+        for(int k = 0; k < 3; k++) P[i].Pos[k] = pos[3 * i + k];
+        P[i].Mass = 1; P[i].Type = 1; P[i].ID = i;
+    }
+    static PetaPM pm;
+    static int pm_module_ready = 0;
+    if(!pm_module_ready) { petapm_module_init(omp_get_max_threads()); pm_module_ready = 1; }
+    memset(&pm, 0, sizeof(pm));
+    petapm_init(&pm, BoxSize, 1.25, Nmesh, 1.0, MPI_COMM_WORLD);          /* Asmth and G play no part in the c2r pass */
+    PetaPMParticleStruct pstruct = {P, sizeof(P[0]), (char *) &P[0].Pos[0] - (char *) P, (char *) &P[0].Mass - (char *) P, NULL, NULL, (int) n};
+    static void (*tf[C2R_MAXF])(PetaPM *, int64_t, int *, pfft_complex *) = {c2r_transfer_0, c2r_transfer_1, c2r_transfer_2, c2r_transfer_3,
+                                                                               c2r_transfer_4, c2r_transfer_5, c2r_transfer_6, c2r_transfer_7};
+    static void (*rf[C2R_MAXF])(PetaPM *, int, double *, double) = {c2r_readout_0, c2r_readout_1, c2r_readout_2, c2r_readout_3,
+                                                                     c2r_readout_4, c2r_readout_5, c2r_readout_6, c2r_readout_7};
+    static char names[C2R_MAXF][8];
+    PetaPMFunctions functions[C2R_MAXF + 1];
+    memset(functions, 0, sizeof(functions));
+    for(int f = 0; f < nfunc; f++) {
+        c2r_kind[f] = kind[f]; c2r_table[f] = tables + (size_t) f * nk2; c2r_out[f] = out + (size_t) f * n;
+        for(int64_t i = 0; i < n; i++) c2r_out[f][i] = 0;
+        snprintf(names[f], sizeof(names[f]), "F%d", f);
+        functions[f].name = names[f]; functions[f].transfer = tf[f]; functions[f].readout = rf[f];
+    }
+    int Nregions = 0;
+    PetaPMRegion *regions = petapm_force_init(&pm, c2r_makeregion, &pstruct, &Nregions, NULL);
+    pfft_complex *rk = petapm_alloc_rhok(&pm);
+    PetaPMRegion *fr = petapm_get_fourier_region(&pm);
+    const int Nz = Nmesh / 2 + 1;
+    for(int ix = 0; ix < Nmesh; ix++) for(int iy = 0; iy < Nmesh; iy++) for(int iz = 0; iz < Nz; iz++) {
+        /* region axes: y, z, x */
+        const int a = iy - fr->offset[0], b = iz - fr->offset[1], c = ix - fr->offset[2];
+        if(a < 0 || b < 0 || c < 0 || a >= fr->size[0] || b >= fr->size[1] || c >= fr->size[2]) continue;
+        const size_t ip = (size_t) a * fr->strides[0] + (size_t) b * fr->strides[1] + (size_t) c * fr->strides[2];
+        const size_t in = ((size_t) ix * Nmesh + iy) * Nz + iz;
+        rk[ip][0] = rho_k[2 * in]; rk[ip][1] = rho_k[2 * in + 1];
+    }
+    petapm_force_c2r(&pm, rk, regions, Nregions, functions);
+    myfree(rk);
+    myfree(regions);
+    petapm_force_finish(&pm);
+    petapm_destroy(&pm);
+    return 0;
+}
+#endif
 #endif
 
 #ifdef REF_WITH_STEP

@@ -42,3 +42,27 @@ extern "C" int emul_pmfft_potential(int N, double *mesh, const double *ktab, dou
     delete E;
     return rc;
 }
+
+extern "C" int emul_pm_c2r_readout(int N, double box, int64_t n, const double *pos, const double *rho_k, int nfunc, const int *kind,
+                                   const double *tables, int64_t nk2, double *out)
+{
+    Engine *E = new Engine();
+    int rc = pmfft_init(E, N);
+    const size_t m = (size_t) (n > 0 ? n : 1);
+    if(!rc) {
+        if(E->mesh.ensure((size_t) N * N * N) || E->cplx.ensure(pmfft_cplx_doubles(E)) || E->ktab.ensure(N) || E->pos.ensure(3 * m) || E->flags.ensure(m)) rc = 2;
+        else {
+            E->n = n; E->Box = box; E->Nmesh = N;
+            memcpy(E->pos.p, pos, 3 * n * sizeof(double));
+            memset(E->flags.p, 0, m);
+            b200_pm_function f[16];
+            for(int j = 0; j < nfunc; j++) { f[j].kind = kind[j]; f[j].table = tables + (size_t) j * nk2; f[j].out = out + (size_t) j * n; }
+            rc = pmfft_c2r_readout(E, rho_k, nfunc, f);
+        }
+    }
+    if(rc) fprintf(stderr, "emul_pm_c2r_readout: %s\n", E->err.c_str());
+    pmfft_destroy(E);
+    E->mesh.release(); E->cplx.release(); E->ktab.release(); E->pos.release(); E->flags.release(); E->pm_rhok.release(); E->pm_table.release(); E->d_pot.release();
+    delete E;
+    return rc;
+}

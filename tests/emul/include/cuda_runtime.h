@@ -29,6 +29,11 @@ enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = malloc(n ? n : 1); if(*p) memset(*p, 0xFF, n ? n : 1); return *p ? 0 : 2; }
 static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { if(n) memmove(d, s, n); return 0; }
+static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dpitch, const void *s, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t)
+{
+    for(size_t r = 0; r < height; r++) memmove((char *) d + r * dpitch, (const char *) s + r * spitch, width);
+    return 0;
+}
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { if(n) memset(d, v, n); return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaGetLastError(void) { return 0; }

@@ -65,5 +65,32 @@ def main(sizes):
     print("fft ok")
 
 
+def c2r():
+    """b200_pm_c2r_readout's device side (k_pm_apply_radial, the three inverse passes, k_pm_readout_field) against the golden
+    of the reference's own petapm_force_c2r (tests/golden/ref_pm_c2r.npz)."""
+    ROOT = os.path.dirname(os.path.dirname(HERE))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pm_c2r_scenarios as SC
+    G = np.load(os.path.join(ROOT, "tests", "golden", "ref_pm_c2r.npz"))
+    L = C.CDLL(EB.build_fft())
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    for name, pos, box, nmesh, rho_k, fn in SC.cases():
+        pos = np.ascontiguousarray(pos); rk = np.ascontiguousarray(rho_k)
+        kinds = np.array([k for k, _ in fn], np.int32)
+        tabs = np.ascontiguousarray(np.stack([t for _, t in fn]))
+        out = np.zeros((len(fn), len(pos)))
+        rc = L.emul_pm_c2r_readout(C.c_int(nmesh), C.c_double(box), C.c_int64(len(pos)), p(pos), p(rk), C.c_int(len(fn)), p(kinds), p(tabs),
+                                   C.c_int64(tabs.shape[1]), p(out))
+        assert rc == 0
+        for j in range(len(fn)):
+            want = G["%s/out%d" % (name, j)]
+            err = np.abs(out[j] - want).max() / np.abs(want).max()
+            assert err < 1e-12, (name, j, err)
+    print("c2r ok")
+
+
 if __name__ == "__main__":
-    main([int(a) for a in sys.argv[1:]] or [10, 16, 24, 40])
+    if sys.argv[1:] == ["c2r"]:
+        c2r()
+    else:
+        main([int(a) for a in sys.argv[1:]] or [10, 16, 24, 40])
