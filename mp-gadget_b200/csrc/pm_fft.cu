@@ -605,12 +605,25 @@ int pmfft_init(Engine *E, int N)
     CK(cudaStreamSynchronize(E->stream));
     F->smemN = smem_bytes(N);
     F->smemH = smem_bytes(L) + (size_t) L * FFT_T * 16;          // two tiles
-    CK(cudaFuncSetAttribute(k_fft_z_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemH));
-    CK(cudaFuncSetAttribute(k_fft_z_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemH));
-    CK(cudaFuncSetAttribute(k_fft_columns<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
-    CK(cudaFuncSetAttribute(k_fft_columns<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
-    CK(cudaFuncSetAttribute(k_fft_columns<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
-    CK(cudaFuncSetAttribute(k_fft_columns<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (F->smemN + 3 * (size_t) N * 8)));
+    // The limit is a property of the kernel, not of this engine: engines with different mesh sizes share it, so it only
+    // ever grows (one device per process).
+    static size_t limH = 0, limN = 0, limP = 0;
+    const size_t smemP = F->smemN + 3 * (size_t) N * 8;
+    if(F->smemH > limH) {
+        CK(cudaFuncSetAttribute(k_fft_z_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemH));
+        CK(cudaFuncSetAttribute(k_fft_z_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemH));
+        limH = F->smemH;
+    }
+    if(F->smemN > limN) {
+        CK(cudaFuncSetAttribute(k_fft_columns<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
+        CK(cudaFuncSetAttribute(k_fft_columns<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
+        CK(cudaFuncSetAttribute(k_fft_columns<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) F->smemN));
+        limN = F->smemN;
+    }
+    if(smemP > limP) {
+        CK(cudaFuncSetAttribute(k_fft_columns<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smemP));
+        limP = smemP;
+    }
     return 0;
 }
 
