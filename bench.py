@@ -558,6 +558,7 @@ def main():
     ap.add_argument("--sharded-hydro", action="store_true", help="multi-GPU: add the sharded SPH entry (configs[4], gas part) to the line")
     ap.add_argument("--no-states", action="store_true", help="skip the extra z9 / clustered state entries")
     ap.add_argument("--no-steploop", action="store_true", help="skip the device-resident step-loop entry")
+    ap.add_argument("--no-extras", action="store_true", help="skip the generic inverse PM pass and friends-of-friends probes (tools/c2r_probe.py, fof_probe.py)")
     ap.add_argument("--no-parity", action="store_true", help="multi-GPU: skip the sampled parity check")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -826,7 +827,23 @@ def main():
                                "what": "hierarchical KDK sub-steps (timestep.c:296-598) with the particle state resident in HBM; one untimed PM sub-step before"}
         except Exception as ex:
             out["steploop"] = {"failed": repr(ex)}
+    if not args.no_extras:
+        # SURVEY 8f ranks 3 and 4 at bench size, each in its own process (its own context; nothing it does can touch the line above)
+        out["extras"] = {"pm_c2r_readout": run_probe("c2r_probe.py", [str(ng), str(nmesh)]), "fof_primary": run_probe("fof_probe.py", [str(ng), "clustered"])}
     print(json.dumps(out), flush=True)
+
+
+def run_probe(script, argv, timeout=240):
+    """The JSON line a tools/ probe prints, or what went wrong."""
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script)] + argv, capture_output=True, text=True, timeout=timeout)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"failed": (r.stderr or r.stdout)[-400:]}
+        return json.loads(lines[-1])
+    except Exception as ex:
+        return {"failed": repr(ex)}
 
 
 if __name__ == "__main__":

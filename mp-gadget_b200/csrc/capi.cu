@@ -387,7 +387,8 @@ int b200_pm_c2r_readout(b200_ctx *ctx, const double *rho_k, int nfunc, const b20
 {
     ENTER(ctx);
     if(E->Nmesh == 0) return failmsg(E, "b200_pm_c2r_readout: call b200_pm_init first");
-    return pmfft_c2r_readout(E, rho_k, nfunc, functions);
+    if(int rc = pmfft_c2r_readout(E, rho_k, nfunc, functions)) return rc;
+    return collect_timings(E);
 }
 
 int b200_pm_transform_kind(b200_ctx *ctx)

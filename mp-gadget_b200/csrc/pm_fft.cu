@@ -748,17 +748,24 @@ int pmfft_c2r_readout(Engine *E, const double *rho_k, int nfunc, const b200_pm_f
     for(int j = 0; j < nfunc; j++) {
         if(f[j].kind < 0 || f[j].kind > 3 || !f[j].table || (E->n > 0 && !f[j].out)) return failmsg(E, "b200_pm_c2r_readout: bad function entry");
         CK(cudaMemcpyAsync(E->pm_table.p, f[j].table, nk2 * sizeof(double), cudaMemcpyHostToDevice, E->stream));
+        // the timers keep the phases of the last function (b200_get_timings: pm_transfer, pm_fft_inverse, pm_readout)
+        timer_start(E, T_PM_TRANSFER);
         k_pm_apply_radial<<<148 * 16, 256, 0, E->stream>>>((const double2 *) E->pm_rhok.p, c, N, Nz, Nzp, f[j].kind, E->pm_table.p);
         CKL(E);
+        timer_stop(E, T_PM_TRANSFER);
+        timer_start(E, T_PM_FFT_INV);
         k_fft_columns<1><<<cblocks, th, F->smemN, E->stream>>>(c, ntile, (size_t) Nzp, (size_t) N * Nzp, F->pN, G);          // x
         CKL(E);
         k_fft_columns<1><<<cblocks, th, F->smemN, E->stream>>>(c, ntile, (size_t) N * Nzp, (size_t) Nzp, F->pN, G);          // y
         CKL(E);
         k_fft_z_inverse<<<zblocks, th, F->smemH, E->stream>>>(c, E->mesh.p, nlines, Nzp, F->pH, F->wN);
         CKL(E);
+        timer_stop(E, T_PM_FFT_INV);
         if(E->n > 0) {
+            timer_start(E, T_PM_READOUT);
             k_pm_readout_field<<<(unsigned) ((E->n + 255) / 256), 256, 0, E->stream>>>(E->pos.p, E->flags.p, E->n, E->Box / N, N, E->mesh.p, E->d_pot.p);
             CKL(E);
+            timer_stop(E, T_PM_READOUT);
             CK(cudaMemcpyAsync(f[j].out, E->d_pot.p, (size_t) E->n * sizeof(double), cudaMemcpyDeviceToHost, E->stream));
         }
         CK(cudaStreamSynchronize(E->stream));          // the table buffer is reused by the next function
