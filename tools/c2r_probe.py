@@ -38,9 +38,35 @@ tm = e.timings()
 assert all(np.isfinite(a).all() for a in res)
 lin = max(float(np.abs(res[4 + k] - 0.7 * res[1 + k]).max() / (np.abs(res[1 + k]).max() + 1e-300)) for k in range(3))
 assert lin < 1e-12, lin
+# the CPU restatement (oracle.pm_c2r_readout: numpy transfer, scipy irfftn, C read-out -- pinned to the reference's own petapm.c
+# by tests/golden/ref_pm_c2r.npz) on a 1/8 sample of the same workload, all host threads: its time, and the GPU against it
+cpu = None
+try:
+    import oracle
+    ngs, nms = ng // 2, nmesh // 2
+    sbox = float(ngs)
+    sp_t, sm_t = ics.bench_ics("displaced", ngs, sbox, device="cpu")
+    spos, smass = sp_t.numpy(), sm_t.numpy()
+    srk = np.empty((nms, nms, nms // 2 + 1), np.complex128)
+    srk[:] = 1.0
+    srk[1::2, :, :] *= -1.0
+    sd, sdi, sv = SC.genic_tables(nms, sbox, growth=0.7)
+    sfn = [(0, sd), (1, sdi), (2, sdi), (3, sdi), (1, sv), (2, sv), (3, sv)]
+    t0 = time.perf_counter(); want = oracle.pm_c2r_readout(spos, sbox, nms, srk, sfn); dt = time.perf_counter() - t0
+    e.set_particles(spos, smass)
+    e.gravpm_init_periodic(sbox, 1.5, nms, 43.0071)
+    got = e.pm_c2r_readout(srk, sfn)
+    err = max(float(np.abs(a - b).max() / np.abs(b).max()) for a, b in zip(got, want))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cpu = {"value": 7 * float(nms) ** 3 / dt, "unit": "mesh cells x functions / s", "cores": cores,
+           "kind": "port (oracle.pm_c2r_readout: scipy irfftn + C read-out)", "sample": "Nmesh %d, %d^3 particles, 7 functions: %.1f s" % (nms, ngs, dt),
+           "gpu_vs_port_max_rel_on_sample": err, "tolerance": 1e-10, "ok": bool(err < 1e-10)}
+except Exception as ex:
+    cpu = {"failed": repr(ex)}
 print(json.dumps({"what": "b200_pm_c2r_readout: 7 functions (MP-GenIC displacement_fields set), Nmesh %d, %d^3 particles" % (nmesh, ng),
                   "wall_ms": [round(x, 1) for x in ms], "wall_ms_per_function": round(min(ms) / 7, 1),
                   "device_ms_last_function": {"transfer": round(tm["pm_transfer"], 3), "inverse_passes": round(tm["pm_fft_inverse"], 3), "readout": round(tm["pm_readout"], 3)},
                   "host_bytes_in": int(rk.nbytes + 7 * dens.nbytes), "host_bytes_out": int(7 * n * 8),
+                  "cells_x_functions_per_s": 7 * float(nmesh) ** 3 / (min(ms) * 1e-3), "cpu_baseline": cpu,
                   "kernel_launches": e.kernel_launches(), "linearity_max_rel": lin,
                   "checks": "read-outs finite; velocity read-outs = 0.7 x displacement read-outs (tables differ by that factor)"}))
