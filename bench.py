@@ -833,7 +833,7 @@ def main():
     print(json.dumps(out), flush=True)
 
 
-def run_probe(script, argv, timeout=240):
+def run_probe(script, argv, timeout=150):
     """The JSON line a tools/ probe prints, or what went wrong."""
     import subprocess
     try:
