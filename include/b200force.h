@@ -21,9 +21,10 @@
  *    b200_domain_assign_balanced functions take no context: they are the host part of the domain decomposition
  *    (sequential integer work on a tree of a few hundred nodes, as in the reference) and run anywhere.
  *
- * Sections: particles and context; PM (gravpm.c, petapm.c); tree build and short-range walk (forcetree.c,
- * gravshort-tree.c); whole force step; SPH density and hydro (density.c, hydra.c); multi-GPU building blocks; step loop
- * (drift.c, timestep.c); domain decomposition (peano.c, domain.c, exchange.c); timings.
+ * Sections: particles and context; PM (gravpm.c, petapm.c) incl. the generic inverse pass (petapm_force_c2r, libgenic/zeldovich.c);
+ * tree build and short-range walk (forcetree.c, gravshort-tree.c); whole force step; SPH density and hydro (density.c, hydra.c);
+ * multi-GPU building blocks; step loop (drift.c, timestep.c); domain decomposition (peano.c, domain.c, exchange.c);
+ * friends-of-friends primary linking (fof.c); timings.
  */
 #ifndef B200FORCE_H
 #define B200FORCE_H
