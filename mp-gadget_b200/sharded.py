@@ -296,7 +296,18 @@ class ShardedTreePM:
             e2.set_particles_dev(allpos.data_ptr(), allmass.data_ptr(), ntot, oldacc_ptr=old.data_ptr() if old is not None else None)
             a2 = torch.zeros((ntot, 3), dtype=torch.float64, device=dev); p2 = torch.zeros(ntot, dtype=torch.float64, device=dev)
             if check_pm:
-                e2.gravpm_init_periodic(self.box, self.asmth, self.nmesh, self.G)
+                # the reference PM of this check runs on cuFFT: independent of the slab PM under test and of the engine's
+                # own transform passes (which the single-GPU bench and tests check against cuFFT and the CPU arm)
+                import os
+                prev = os.environ.get("B200_PM_FFT")
+                os.environ["B200_PM_FFT"] = "cufft"
+                try:
+                    e2.gravpm_init_periodic(self.box, self.asmth, self.nmesh, self.G)
+                finally:
+                    if prev is None:
+                        os.environ.pop("B200_PM_FFT", None)
+                    else:
+                        os.environ["B200_PM_FFT"] = prev
                 g2 = torch.zeros((ntot, 3), dtype=torch.float64, device=dev)
                 e2.gravpm_force_dev(g2.data_ptr(), None)
                 torch.cuda.synchronize()
